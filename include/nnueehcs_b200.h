@@ -1,0 +1,158 @@
+/*
+ * nnueehcs_b200 -- C ABI of the B200-native uncertainty-estimation hot path.
+ *
+ * The reference (cjlauer16/NNUEEHCS) is pure Python and has no FFI layer; the boundary this
+ * library replaces is the body of three Python methods and two metric functions.  Each entry
+ * point below names the reference interface it stands in for (paths relative to the reference
+ * root).  All pointers are raw device (or, where stated, host) pointers, all sizes are plain
+ * integers; no torch / C++ types cross this boundary.  INTEGRATION.md shows the ctypes binding
+ * a maintainer of the reference would add.
+ *
+ * Threading / streams: every call enqueues work on the CUDA stream passed as `stream`
+ * (a cudaStream_t cast to void*; NULL = legacy default stream) on the current device and
+ * returns without synchronising unless stated otherwise.  Errors never abort(): a non-zero
+ * status is returned and uq_last_error() (thread-local) describes it, so the Python side can
+ * raise ValueError (UQ_ERR_INVALID / UQ_ERR_UNSUPPORTED) or RuntimeError (UQ_ERR_CUDA), the
+ * two exception kinds the reference's callers handle (examples/bo_driven/bo.py:469-497).
+ */
+#ifndef NNUEEHCS_B200_H
+#define NNUEEHCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UQ_ABI_VERSION 1
+
+/* status codes */
+#define UQ_OK 0
+#define UQ_ERR_INVALID 1     /* bad argument / configuration  -> ValueError   */
+#define UQ_ERR_CUDA 2        /* CUDA runtime failure          -> RuntimeError */
+#define UQ_ERR_UNSUPPORTED 3 /* shape/precision not built     -> ValueError   */
+#define UQ_ERR_WORKSPACE 4   /* workspace too small           -> RuntimeError */
+
+/* which wrapper's forward is being evaluated */
+#define UQ_MODE_ENSEMBLE 0   /* EnsembleModel.forward      nnueehcs/models.py:99-108  */
+#define UQ_MODE_MC_DROPOUT 1 /* MCDropoutModel.forward     nnueehcs/models.py:147-163 */
+#define UQ_MODE_DELTA_UQ 2   /* DeltaUQMLP.forward         nnueehcs/models.py:313-341 */
+
+/* arithmetic the MLP stack runs in */
+#define UQ_PREC_FP32 0 /* CUDA-core FFMA, fp32 accumulate: the 1e-5 parity mode            */
+#define UQ_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the throughput mode */
+
+/* what uq_forward writes */
+#define UQ_OUT_MEAN_STD 0 /* out0 = mean, out1 = unbiased std (what evaluation.py consumes)   */
+#define UQ_OUT_MOMENTS 1  /* out0 = mean, out1 = M2, count returned in *out_count (K-shards) */
+
+typedef struct uq_model uq_model_t; /* opaque: packed weights of K members */
+
+/*
+ * One Linear (+ optional eval-mode BatchNorm1d, ReLU, Dropout) block of the nn.Sequential that
+ * nnueehcs/model_builder.py:30-73 (build_network) produces.  Device pointers, float32,
+ * `weight` is [out_features, in_features] row-major exactly as torch stores nn.Linear.weight.
+ * Null bn_* pointers mean "no BatchNorm after this Linear".
+ */
+typedef struct uq_layer_desc {
+  int32_t in_features;
+  int32_t out_features;
+  const float* weight;
+  const float* bias;      /* [out] or NULL */
+  const float* bn_weight; /* gamma, [out] or NULL */
+  const float* bn_bias;   /* beta */
+  const float* bn_mean;   /* running_mean */
+  const float* bn_var;    /* running_var */
+  float bn_eps;
+  int32_t relu;    /* 1: ReLU follows (after BN if present) */
+  int32_t dropout; /* 1: an nn.Dropout follows this block's activation (MC dropout only) */
+} uq_layer_desc;
+
+typedef struct uq_forward_args {
+  int32_t mode;         /* UQ_MODE_*  */
+  int32_t precision;    /* UQ_PREC_*  */
+  int32_t output;       /* UQ_OUT_*   */
+  int32_t member_begin; /* K-axis shard: members / passes / anchors [begin, begin+count) */
+  int32_t member_count; /*   of this call; full range = [0, K)                            */
+  int32_t total_members; /* K of the whole job (Philox pass ids and anchors index by global id) */
+  int32_t dropout_active; /* 0: "dropout-off" parity case (P identical passes) */
+  int32_t reserved0;
+  double dropout_p;     /* MCDropoutModel.dropout_percent (models.py:132-134) */
+  uint64_t philox_seed; /* native masks: Philox4x32-10 keyed by seed, counter =     */
+  uint64_t philox_offset; /*   (global pass id, dropout layer, sample, feature group)  */
+  const uint8_t* masks; /* injected keep-masks or NULL. Layout: for dropout layer l (in module
+                           order) a block [total_members][n][width_l] of bytes (0/1), blocks
+                           concatenated in layer order. */
+  const float* anchors; /* Delta-UQ anchors [total_members][d_in] (d_in = net input / 2) */
+} uq_forward_args;
+
+/* -- library ------------------------------------------------------------------------------ */
+int uq_abi_version(void);
+const char* uq_last_error(void);
+/* number of kernels this library launched on this thread since the last reset (bench.py's
+   gpu_launches) */
+uint64_t uq_launch_count(void);
+void uq_launch_count_reset(void);
+
+/* -- model packing: replaces the weight walk the wrappers do implicitly through
+      nn.Sequential.__call__ (models.py:103,156-158).  `layers` is
+      [n_members][n_layers] (host array of descriptors holding device pointers).  The library
+      copies/folds what it needs (fp32 weights + eval-BN scale/shift; bf16 UMMA-swizzled image
+      with BN folded) into its own device buffers; the caller may free its tensors after the
+      call's stream work has completed. */
+int uq_model_create(uq_model_t** out, int32_t n_members, int32_t n_layers,
+                    const uq_layer_desc* layers, void* stream);
+int uq_model_destroy(uq_model_t* model);
+/* 1 if the bf16 tcgen05 path supports this model's shapes, else 0 (reason in uq_last_error) */
+int uq_model_supports_bf16(const uq_model_t* model);
+
+/* -- the forward: K x net(x) -> stack -> mean(0), std(0), fused.
+      x: [n, d_in] float32 row-major on device.  out0/out1: [n, d_out] float32 on device.
+      workspace: device scratch of at least uq_forward_workspace_bytes(...) bytes (may be NULL
+      when that returns 0).  *out_count (host, may be NULL) receives member_count. */
+size_t uq_forward_workspace_bytes(const uq_model_t* model, int64_t n, const uq_forward_args* args);
+int uq_forward(const uq_model_t* model, const float* x, int64_t n, const uq_forward_args* args,
+               float* out0, float* out1, void* workspace, size_t workspace_bytes,
+               double* out_count, void* stream);
+
+/* same call with HOST buffers (pinned or pageable): H2D of x, forward, D2H of both outputs,
+   synchronises `stream` before returning.  This is the end-to-end path bench.py times. */
+int uq_forward_host(const uq_model_t* model, const float* x_host, int64_t n,
+                    const uq_forward_args* args, float* out0_host, float* out1_host,
+                    void* stream);
+
+/* -- K-axis shards: Chan merge of per-shard (count, mean, M2), then unbiased std.
+      means/m2s: [n_shards][len] float32 device (e.g. the NCCL all-gather buffer),
+      counts: host array [n_shards].  Writes mean/std [len]. */
+int uq_moments_merge(const float* means, const float* m2s, const double* counts,
+                     int32_t n_shards, int64_t len, float* out_mean, float* out_std,
+                     void* stream);
+
+/* -- native dropout masks: writes the Philox keep-masks uq_forward would draw for dropout layer
+      `dropout_layer` as bytes [total_members][n][width] (the injected-mask layout), so a
+      native-RNG MC-dropout run can be replayed bit-for-bit through the CPU oracle. */
+int uq_philox_keep_masks(uint8_t* out, int64_t n, int32_t width, int32_t total_members,
+                         int32_t dropout_layer, double dropout_p, uint64_t seed, uint64_t offset,
+                         void* stream);
+
+/* -- metrics -------------------------------------------------------------------------------
+      uq_wasserstein_1d replaces scipy.stats.wasserstein_distance as called from
+      WassersteinEvaluation._evaluate_uncertainties (nnueehcs/evaluation.py:182).
+      u, v: float32 device arrays; result (float64) written to *out_host after the call
+      synchronises `stream`.  workspace from uq_wasserstein_workspace_bytes. */
+size_t uq_wasserstein_workspace_bytes(int64_t nu, int64_t nv);
+int uq_wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, double* out_host,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*    uq_kde_jsd replaces JensenShannonEvaluation.pdf_jsd (nnueehcs/evaluation.py:268-276):
+      Scott-bandwidth Gaussian KDE of each sample on a shared `grid_pts`-point linspace between
+      the joint min and max, then the Jensen-Shannon distance of the two pdf vectors. */
+size_t uq_kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int32_t grid_pts);
+int uq_kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
+               double* out_host, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNUEEHCS_B200_H */

@@ -1,0 +1,114 @@
+"""ctypes binding of ``include/nnueehcs_b200.h``.
+
+The product path has no CPU fallback: if the native library is not built this module raises,
+and every op raises with it.  Build with ``python -m nnueehcs_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+UQ_OK, UQ_ERR_INVALID, UQ_ERR_CUDA, UQ_ERR_UNSUPPORTED, UQ_ERR_WORKSPACE = 0, 1, 2, 3, 4
+MODE_ENSEMBLE, MODE_MC_DROPOUT, MODE_DELTA_UQ = 0, 1, 2
+PREC_FP32, PREC_BF16 = 0, 1
+OUT_MEAN_STD, OUT_MOMENTS = 0, 1
+
+# every symbol include/nnueehcs_b200.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "uq_abi_version", "uq_last_error", "uq_launch_count", "uq_launch_count_reset",
+    "uq_model_create", "uq_model_destroy", "uq_model_supports_bf16",
+    "uq_forward_workspace_bytes", "uq_forward", "uq_forward_host", "uq_moments_merge",
+    "uq_philox_keep_masks", "uq_wasserstein_workspace_bytes", "uq_wasserstein_1d",
+    "uq_kde_jsd_workspace_bytes", "uq_kde_jsd",
+)
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [
+        ("in_features", C.c_int32),
+        ("out_features", C.c_int32),
+        ("weight", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("bn_weight", C.c_void_p),
+        ("bn_bias", C.c_void_p),
+        ("bn_mean", C.c_void_p),
+        ("bn_var", C.c_void_p),
+        ("bn_eps", C.c_float),
+        ("relu", C.c_int32),
+        ("dropout", C.c_int32),
+    ]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("precision", C.c_int32),
+        ("output", C.c_int32),
+        ("member_begin", C.c_int32),
+        ("member_count", C.c_int32),
+        ("total_members", C.c_int32),
+        ("dropout_active", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("dropout_p", C.c_double),
+        ("philox_seed", C.c_uint64),
+        ("philox_offset", C.c_uint64),
+        ("masks", C.c_void_p),
+        ("anchors", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the native library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.environ.get("NNUEEHCS_B200_LIB", LIB_PATH)
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"nnueehcs_b200 native library not found at {path}; run "
+            "`python -m nnueehcs_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, i32, i64, u64, sz, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t, C.c_double
+    lib.uq_abi_version.restype = C.c_int
+    lib.uq_last_error.restype = C.c_char_p
+    lib.uq_launch_count.restype = u64
+    lib.uq_launch_count_reset.restype = None
+    lib.uq_model_create.argtypes = [C.POINTER(vp), i32, i32, C.POINTER(LayerDesc), vp]
+    lib.uq_model_destroy.argtypes = [vp]
+    lib.uq_model_supports_bf16.argtypes = [vp]
+    lib.uq_forward_workspace_bytes.argtypes = [vp, i64, C.POINTER(ForwardArgs)]
+    lib.uq_forward_workspace_bytes.restype = sz
+    lib.uq_forward.argtypes = [vp, vp, i64, C.POINTER(ForwardArgs), vp, vp, vp, sz,
+                               C.POINTER(dbl), vp]
+    lib.uq_forward_host.argtypes = [vp, vp, i64, C.POINTER(ForwardArgs), vp, vp, vp]
+    lib.uq_moments_merge.argtypes = [vp, vp, C.POINTER(dbl), i32, i64, vp, vp, vp]
+    lib.uq_philox_keep_masks.argtypes = [vp, i64, i32, i32, i32, dbl, u64, u64, vp]
+    lib.uq_wasserstein_workspace_bytes.argtypes = [i64, i64]
+    lib.uq_wasserstein_workspace_bytes.restype = sz
+    lib.uq_wasserstein_1d.argtypes = [vp, i64, vp, i64, C.POINTER(dbl), vp, sz, vp]
+    lib.uq_kde_jsd_workspace_bytes.argtypes = [i64, i64, i32]
+    lib.uq_kde_jsd_workspace_bytes.restype = sz
+    lib.uq_kde_jsd.argtypes = [vp, i64, vp, i64, i32, C.POINTER(dbl), vp, sz, vp]
+    for name in ("uq_model_create", "uq_model_destroy", "uq_model_supports_bf16", "uq_forward",
+                 "uq_forward_host", "uq_moments_merge", "uq_philox_keep_masks",
+                 "uq_wasserstein_1d", "uq_kde_jsd"):
+        getattr(lib, name).restype = C.c_int
+    if lib.uq_abi_version() != 1:
+        raise RuntimeError("nnueehcs_b200: ABI version mismatch between _lib.py and the library")
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    """Map a C status to the exception kinds the reference's callers handle."""
+    if status == UQ_OK:
+        return
+    msg = load().uq_last_error().decode("utf-8", "replace")
+    if status in (UQ_ERR_INVALID, UQ_ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    raise RuntimeError(msg)

@@ -1,0 +1,110 @@
+// Shared declarations of the nnueehcs_b200 native library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nnueehcs_b200.h"
+
+namespace uq {
+
+// ---- error plumbing: never abort, hand a status + message back through the C ABI ------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define UQ_CUDA(expr)                                                          \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) return uq::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define UQ_LAUNCH_CHECK()                                                       \
+  do {                                                                          \
+    uq::count_launch();                                                         \
+    cudaError_t _e = cudaGetLastError();                                        \
+    if (_e != cudaSuccess) return uq::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+#define UQ_REQUIRE(cond, code, ...)   \
+  do {                                \
+    if (!(cond)) {                    \
+      uq::set_error(__VA_ARGS__);     \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// ---- packed model ------------------------------------------------------------------------------
+struct Layer {
+  int in = 0, out = 0;
+  bool has_bn = false, relu = false, dropout = false;
+  // fp32 parity path, all members stacked on the leading axis
+  float* w = nullptr;      // [K][out][in]
+  float* bias = nullptr;   // [K][out]   (zeros when the Linear has no bias)
+  float* alpha = nullptr;  // [K][out]   eval-BN scale  gamma / sqrt(var + eps)   (has_bn)
+  float* beta = nullptr;   // [K][out]   eval-BN shift  beta_bn - mean * alpha     (has_bn)
+  // bf16 tcgen05 path (only when the model is tensor-core eligible)
+  float* bias_folded = nullptr;  // [K][out]  (bias * alpha + beta), fp32
+};
+
+// Geometry of the bf16 fused kernel's packed weight image (see mlp_tc.cu).
+struct TcPlan {
+  bool ok = false;
+  std::string why_not;
+  int d_in = 0;        // network input features
+  int k0 = 0;          // padded K of the first MMA layer (multiple of 16, <= 64)
+  int hidden = 0;      // H: common width of all hidden layers (multiple of 64, 64..512)
+  int n_mma_layers = 0;  // layers executed as MMAs: Linear 0 .. L-2
+  int d_out = 0;       // final Linear out features (1..8): CUDA-core epilogue dot
+  size_t stage_bytes = 0;        // bytes of one weight stage [n_tile x 64] bf16
+  int n_tile = 0;                // MMA N per stage (H if H <= 256 else 256)
+  int stages_per_member = 0;
+  __nv_bfloat16* image = nullptr;  // [K][stages_per_member][stage_bytes]
+  float* w_last = nullptr;         // [K][d_out][H] fp32 (dropout scale NOT folded; see kernel)
+  float* b_last = nullptr;         // [K][d_out]
+};
+
+}  // namespace uq
+
+struct uq_model {
+  int device = 0;
+  int n_members = 0;
+  int n_layers = 0;
+  int d_in = 0, d_out = 0, max_width = 0;
+  int n_dropout = 0;
+  std::vector<uq::Layer> layers;
+  std::vector<void*> allocations;
+  uq::TcPlan tc;
+};
+
+namespace uq {
+
+// fp32 parity path (mlp_fp32.cu)
+size_t fp32_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a);
+int fp32_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_args* a,
+                 float* out0, float* out1, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// bf16 tcgen05 path (mlp_tc.cu)
+void tc_plan(uq_model* m);  // fills m->tc.ok / geometry (no allocation)
+int tc_pack(uq_model* m, cudaStream_t st);
+size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a);
+int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_args* a,
+               float* out0, float* out1, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// moments (moments.cu)
+int moments_merge(const float* means, const float* m2s, const double* counts, int n_shards,
+                  int64_t len, float* out_mean, float* out_std, cudaStream_t st);
+
+// metrics (wasserstein.cu / kde_jsd.cu)
+size_t wasserstein_workspace_bytes(int64_t nu, int64_t nv);
+int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, double* out_host,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
+size_t kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int grid_pts);
+int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+            double* out_host, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace uq

@@ -1,0 +1,270 @@
+// Jensen-Shannon distance between two Scott-bandwidth Gaussian KDEs on a shared linspace grid.
+//
+// Replaces JensenShannonEvaluation.pdf_jsd (nnueehcs/evaluation.py:268-276):
+//     kde1 = gaussian_kde(dist1); kde2 = gaussian_kde(dist2)
+//     x    = linspace(min(both), max(both), 20000)
+//     jensenshannon(kde1(x), kde2(x))
+// scipy's KDE is pdf(g) = 1/(n h sqrt(2 pi)) sum_i exp(-((x_i-g)/h)^2/2) with
+// h = sqrt(unbiased var) * n^(-1/5); jensenshannon renormalises each pdf vector to sum 1, so the
+// constant in front cancels and only the raw kernel sums are needed.
+//
+// Work is N x G Gaussian evaluations if done naively (2e12 at 100 M values).  Here the samples
+// are radix-sorted first, so a chunk of 2048 consecutive values only touches the grid points
+// within 9 h of its value range (a Gaussian term beyond 9 sigma is < 3e-18 of the peak) -- about
+// 500 of the 20 000 points at 50 M values per sample -- and the inner loop runs in float32 on
+// coordinates taken relative to the chunk's window origin (computed in float64, so no
+// cancellation), one MUFU.EX2 per pair, flushed to float64 every 256 terms.  Each block adds its
+// window's partial sums to the float64 grid with atomics; a last block turns the two grids into
+// the JS distance.
+#include <math.h>
+
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace uq {
+namespace {
+
+constexpr int KDE_THREADS = 256;
+constexpr int KDE_CHUNK = 2048;      // sorted samples per block
+constexpr int KDE_GP = 4;            // grid points per thread per pass
+constexpr int KDE_SUB = 256;         // float32 accumulation run before flushing to float64
+constexpr double KDE_Z = 9.0;        // truncation in kernel standard deviations
+constexpr int STAT_BLOCKS = 296;
+
+struct KdeParams {       // written by setup_kernel, read by eval_kernel
+  double lo, step;       // grid: g_j = lo + j * step
+  double h[2];           // bandwidth (kernel std) of each sample
+  double scale[2];       // sqrt(log2(e)/2) / h : exp(-z^2/2) == exp2(-((x-g)*scale)^2)
+};
+
+// per-block float64 partial sums of (x - x0) and (x - x0)^2 on the sorted array (x0 = minimum)
+__global__ void __launch_bounds__(256)
+stats_kernel(const float* __restrict__ xs, int64_t n, double* __restrict__ partials) {
+  __shared__ double sh[2][8];
+  const double x0 = (double)xs[0];
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double d = (double)xs[i] - x0;
+    s1 += d;
+    s2 += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+    s2 += __shfl_down_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = s1;
+    sh[1][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) a += sh[0][w], b += sh[1][w];
+    partials[2 * blockIdx.x] = a;
+    partials[2 * blockIdx.x + 1] = b;
+  }
+}
+
+__global__ void setup_kernel(const float* __restrict__ us, int64_t nu, const float* __restrict__ vs,
+                             int64_t nv, const double* __restrict__ pu,
+                             const double* __restrict__ pv, int grid_pts, KdeParams* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s1 = 0, s2 = 0;
+  for (int b = 0; b < STAT_BLOCKS; ++b) s1 += pu[2 * b], s2 += pu[2 * b + 1];
+  const double var_u = (s2 - s1 * s1 / (double)nu) / (double)(nu - 1);
+  s1 = 0, s2 = 0;
+  for (int b = 0; b < STAT_BLOCKS; ++b) s1 += pv[2 * b], s2 += pv[2 * b + 1];
+  const double var_v = (s2 - s1 * s1 / (double)nv) / (double)(nv - 1);
+  KdeParams p;
+  p.h[0] = sqrt(var_u) * pow((double)nu, -0.2);
+  p.h[1] = sqrt(var_v) * pow((double)nv, -0.2);
+  const double lo = fmin((double)us[0], (double)vs[0]);
+  const double hi = fmax((double)us[nu - 1], (double)vs[nv - 1]);
+  p.lo = lo;
+  p.step = (hi - lo) / (double)(grid_pts - 1);
+  const double c = sqrt(0.5 * 1.4426950408889634);
+  p.scale[0] = c / p.h[0];
+  p.scale[1] = c / p.h[1];
+  *out = p;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// blockIdx.x < chunks_u : chunk of the first sample, else of the second
+__global__ void __launch_bounds__(KDE_THREADS)
+kde_eval_kernel(const float* __restrict__ us, int64_t nu, const float* __restrict__ vs, int64_t nv,
+                int64_t chunks_u, int grid_pts, const KdeParams* __restrict__ params,
+                double* __restrict__ pdf /* [2][grid_pts] */) {
+  __shared__ __align__(16) float sx[KDE_CHUNK];
+  const int which = (int64_t)blockIdx.x < chunks_u ? 0 : 1;
+  const float* xs = which ? vs : us;
+  const int64_t n = which ? nv : nu;
+  const int64_t c0 = ((int64_t)blockIdx.x - (which ? chunks_u : 0)) * KDE_CHUNK;
+  const int64_t c1 = (c0 + KDE_CHUNK) < n ? (c0 + KDE_CHUNK) : n;
+  const KdeParams p = *params;
+  const double h = p.h[which], scale = p.scale[which];
+  double* out = pdf + (size_t)which * grid_pts;
+
+  // window of grid indices within KDE_Z bandwidths of this chunk's value range
+  const double x_first = (double)xs[c0], x_last = (double)xs[c1 - 1];
+  int jlo = 0, jhi = grid_pts - 1;
+  if (p.step > 0.0) {
+    const double a = ceil((x_first - KDE_Z * h - p.lo) / p.step);
+    const double b = floor((x_last + KDE_Z * h - p.lo) / p.step);
+    if (a > 0.0) jlo = a > (double)(grid_pts - 1) ? grid_pts - 1 : (int)a;
+    if (b < (double)(grid_pts - 1)) jhi = b < 0.0 ? 0 : (int)b;
+  }
+  const double g0 = p.lo + (double)jlo * p.step;  // window origin, float64
+
+  // stage the chunk as scaled coordinates relative to the window origin
+  for (int i = threadIdx.x; i < KDE_CHUNK; i += KDE_THREADS) {
+    const int64_t gi = c0 + i;
+    sx[i] = gi < c1 ? (float)(((double)xs[gi] - g0) * scale) : 3.0e18f;  // pad: exp2(-inf) = 0
+  }
+  __syncthreads();
+
+  const double step_s = p.step * scale;
+  for (int jb = jlo; jb <= jhi; jb += KDE_THREADS * KDE_GP) {
+    float b[KDE_GP];
+    double acc64[KDE_GP];
+#pragma unroll
+    for (int g = 0; g < KDE_GP; ++g) {
+      const int j = jb + g * KDE_THREADS + threadIdx.x;
+      b[g] = (float)((double)(j - jlo) * step_s);
+      acc64[g] = 0.0;
+    }
+    for (int s0 = 0; s0 < KDE_CHUNK; s0 += KDE_SUB) {
+      float acc[KDE_GP];
+#pragma unroll
+      for (int g = 0; g < KDE_GP; ++g) acc[g] = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < KDE_SUB; i += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&sx[s0 + i]);  // warp-broadcast
+#pragma unroll
+        for (int g = 0; g < KDE_GP; ++g) {
+          const float d0 = a.x - b[g], d1 = a.y - b[g], d2 = a.z - b[g], d3 = a.w - b[g];
+          acc[g] += ex2_approx(-d0 * d0) + ex2_approx(-d1 * d1) +
+                    (ex2_approx(-d2 * d2) + ex2_approx(-d3 * d3));
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < KDE_GP; ++g) acc64[g] += (double)acc[g];
+    }
+#pragma unroll
+    for (int g = 0; g < KDE_GP; ++g) {
+      const int j = jb + g * KDE_THREADS + threadIdx.x;
+      if (j <= jhi && acc64[g] != 0.0) atomicAdd(&out[j], acc64[g]);
+    }
+  }
+}
+
+// scipy.spatial.distance.jensenshannon on the two raw kernel-sum vectors
+__global__ void __launch_bounds__(1024)
+jsd_kernel(const double* __restrict__ pdf, int grid_pts, double* __restrict__ result) {
+  __shared__ double sh[2][1024];
+  const int t = threadIdx.x;
+  const double* pu = pdf;
+  const double* pv = pdf + grid_pts;
+  double a = 0.0, b = 0.0;
+  for (int j = t; j < grid_pts; j += 1024) a += pu[j], b += pv[j];
+  sh[0][t] = a; sh[1][t] = b;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) sh[0][t] += sh[0][t + o], sh[1][t] += sh[1][t + o];
+    __syncthreads();
+  }
+  const double su = sh[0][0], sv = sh[1][0];
+  __syncthreads();
+  double left = 0.0, right = 0.0;
+  for (int j = t; j < grid_pts; j += 1024) {
+    const double p = pu[j] / su, q = pv[j] / sv;
+    const double m = (p + q) / 2.0;
+    if (p > 0.0 && m > 0.0) left += p * log(p / m);
+    if (q > 0.0 && m > 0.0) right += q * log(q / m);
+  }
+  sh[0][t] = left; sh[1][t] = right;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) sh[0][t] += sh[0][t + o], sh[1][t] += sh[1][t + o];
+    __syncthreads();
+  }
+  if (t == 0) *result = sqrt((sh[0][0] + sh[1][0]) / 2.0);
+}
+
+struct WsLayout {
+  size_t u, ut, v, vt, scratch, partials, params, pdf, result, total;
+};
+
+WsLayout layout(int64_t nu, int64_t nv, int grid_pts) {
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  WsLayout L;
+  size_t o = 0;
+  L.u = o; o += al(sizeof(float) * (size_t)nu);
+  L.ut = o; o += al(sizeof(float) * (size_t)nu);
+  L.v = o; o += al(sizeof(float) * (size_t)nv);
+  L.vt = o; o += al(sizeof(float) * (size_t)nv);
+  const size_t su = radix_sort_scratch_bytes(nu), sv = radix_sort_scratch_bytes(nv);
+  L.scratch = o; o += al(su > sv ? su : sv);
+  L.partials = o; o += al(sizeof(double) * 4 * STAT_BLOCKS);
+  L.params = o; o += al(sizeof(KdeParams));
+  L.pdf = o; o += al(sizeof(double) * 2 * (size_t)grid_pts);
+  L.result = o; o += 256;
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+
+size_t kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int grid_pts) {
+  if (nu < 1 || nv < 1 || grid_pts < 2) return 0;
+  return layout(nu, nv, grid_pts).total;
+}
+
+int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts, double* out_host,
+            void* ws, size_t ws_bytes, cudaStream_t st) {
+  const WsLayout L = layout(nu, nv, grid_pts);
+  UQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, UQ_ERR_WORKSPACE,
+             "kde_jsd needs %zu workspace bytes, got %zu", L.total, ws_bytes);
+  char* b = static_cast<char*>(ws);
+  float* du = reinterpret_cast<float*>(b + L.u);
+  float* dut = reinterpret_cast<float*>(b + L.ut);
+  float* dv = reinterpret_cast<float*>(b + L.v);
+  float* dvt = reinterpret_cast<float*>(b + L.vt);
+  double* partials = reinterpret_cast<double*>(b + L.partials);
+  KdeParams* params = reinterpret_cast<KdeParams*>(b + L.params);
+  double* pdf = reinterpret_cast<double*>(b + L.pdf);
+  double* result = reinterpret_cast<double*>(b + L.result);
+  UQ_CUDA(cudaMemcpyAsync(du, u, sizeof(float) * (size_t)nu, cudaMemcpyDeviceToDevice, st));
+  UQ_CUDA(cudaMemcpyAsync(dv, v, sizeof(float) * (size_t)nv, cudaMemcpyDeviceToDevice, st));
+  float *su = nullptr, *sv = nullptr;
+  int rc = radix_sort_f32(du, dut, nu, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
+  if (rc != UQ_OK) return rc;
+  rc = radix_sort_f32(dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
+  if (rc != UQ_OK) return rc;
+  stats_kernel<<<STAT_BLOCKS, 256, 0, st>>>(su, nu, partials);
+  UQ_LAUNCH_CHECK();
+  stats_kernel<<<STAT_BLOCKS, 256, 0, st>>>(sv, nv, partials + 2 * STAT_BLOCKS);
+  UQ_LAUNCH_CHECK();
+  setup_kernel<<<1, 32, 0, st>>>(su, nu, sv, nv, partials, partials + 2 * STAT_BLOCKS, grid_pts,
+                                 params);
+  UQ_LAUNCH_CHECK();
+  UQ_CUDA(cudaMemsetAsync(pdf, 0, sizeof(double) * 2 * (size_t)grid_pts, st));
+  const int64_t chunks_u = (nu + KDE_CHUNK - 1) / KDE_CHUNK;
+  const int64_t chunks_v = (nv + KDE_CHUNK - 1) / KDE_CHUNK;
+  kde_eval_kernel<<<(unsigned)(chunks_u + chunks_v), KDE_THREADS, 0, st>>>(
+      su, nu, sv, nv, chunks_u, grid_pts, params, pdf);
+  UQ_LAUNCH_CHECK();
+  jsd_kernel<<<1, 1024, 0, st>>>(pdf, grid_pts, result);
+  UQ_LAUNCH_CHECK();
+  UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
+  UQ_CUDA(cudaStreamSynchronize(st));
+  return UQ_OK;
+}
+
+}  // namespace uq

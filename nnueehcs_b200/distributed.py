@@ -1,0 +1,71 @@
+"""K-axis sharding of the UQ forward over the GPUs of one node.
+
+The reference is single-GPU (no collective anywhere).  The B200-native
+path shards the member axis -- ensemble members, MC-dropout passes or Delta-UQ anchors -- across
+ranks (one process per GPU, ``torch.distributed`` over NCCL/NVLink): every rank sees all N samples
+(x is ~20 B/sample), reduces its own members inside the fused kernel to per-sample
+``(count, mean, M2)``, and the shards are combined with ONE collective -- an all-gather of the
+``[2, N, out]`` float32 (mean, M2) slab -- followed by a Chan merge kernel
+(``uq_moments_merge``).  Moments cross the wire rather than raw power sums because
+``sum(y^2) - sum(y)^2/n`` cancels catastrophically in fp32 when std << |mean|, which is the
+in-distribution case.  Philox masks are keyed by the *global* pass id, so the result does not
+depend on the number of ranks.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def split_range(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous balanced split of ``range(total)``: returns (begin, count) of ``rank``."""
+    begin = (total * rank) // world
+    end = (total * (rank + 1)) // world
+    return begin, end - begin
+
+
+class KShard:
+    def __init__(self, group: Optional["dist.ProcessGroup"] = None):
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("KShard needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def split(self, total: int, rank: Optional[int] = None) -> Tuple[int, int]:
+        return split_range(total, self.world, self.rank if rank is None else rank)
+
+    def counts(self, total: int) -> List[int]:
+        return [self.split(total, r)[1] for r in range(self.world)]
+
+    def exchange(self, mean: torch.Tensor, m2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The one collective: all-gather every rank's (mean, M2) slab -> two ``[world, ...]``
+        tensors ordered by rank."""
+        slab = torch.stack([mean, m2]).contiguous()
+        gathered = torch.empty((self.world,) + tuple(slab.shape), dtype=slab.dtype,
+                               device=slab.device)
+        dist.all_gather_into_tensor(gathered, slab, group=self.group)
+        return gathered[:, 0], gathered[:, 1]
+
+    def forward(self, packed: "ops.PackedModel", x: torch.Tensor, mode: str, *, total_members: int,
+                precision: str = "fp32", **kw) -> Tuple[torch.Tensor, torch.Tensor]:
+        begin, count = self.split(total_members)
+        if count > 0:
+            mean, m2 = packed.forward(x, mode, total_members=total_members, precision=precision,
+                                      member_begin=begin, member_count=count, output="moments",
+                                      **kw)
+        else:  # more ranks than members: this rank contributes an empty shard
+            mean = torch.zeros((x.shape[0], packed.d_out), dtype=torch.float32, device=x.device)
+            m2 = torch.zeros_like(mean)
+        means, m2s = self.exchange(mean, m2)
+        counts = self.counts(total_members)
+        live = [r for r, c in enumerate(counts) if c > 0]
+        if len(live) != self.world:
+            idx = torch.tensor(live, device=means.device)
+            means, m2s = means.index_select(0, idx), m2s.index_select(0, idx)
+            counts = [counts[r] for r in live]
+        return ops.moments_merge(means.contiguous(), m2s.contiguous(), counts)

@@ -1,0 +1,261 @@
+"""Thin Python layer over the C ABI: torch supplies device memory and streams, nothing else.
+
+Every function here ends in a call into ``libnnueehcs_b200.so``; there is no torch
+implementation of any of these ops and no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .extract import (Block, _f32_cuda, dropout_widths, split_blocks, structure_signature)
+
+_PREC = {"fp32": _lib.PREC_FP32, "float32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16,
+         "bfloat16": _lib.PREC_BF16}
+_MODE = {"ensemble": _lib.MODE_ENSEMBLE, "mc_dropout": _lib.MODE_MC_DROPOUT,
+         "delta_uq": _lib.MODE_DELTA_UQ}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(
+            f"nnueehcs_b200: {what} must be a CUDA tensor -- the fused UQ forward runs on the GPU "
+            "only (no CPU fallback)")
+
+
+def launch_count() -> int:
+    return int(_lib.load().uq_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().uq_launch_count_reset()
+
+
+class PackedModel:
+    """Device-resident packed weights of K structurally identical MLPs (``uq_model_t``)."""
+
+    def __init__(self, nets: Sequence[nn.Sequential], device: torch.device):
+        lib = _lib.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("nnueehcs_b200: models can only be packed on a CUDA device")
+        all_blocks = [split_blocks(net) for net in nets]
+        sig = structure_signature(all_blocks[0])
+        for i, b in enumerate(all_blocks[1:], 1):
+            if structure_signature(b) != sig:
+                raise ValueError(f"ensemble member {i} has a different architecture than member 0")
+        self.signature = sig
+        self.n_members = len(nets)
+        self.n_layers = len(sig)
+        self.d_in = sig[0][0]
+        self.d_out = sig[-1][1]
+        self.dropout_widths = dropout_widths(all_blocks[0])
+        self.device = device
+        keep: list = []
+        descs = (_lib.LayerDesc * (self.n_members * self.n_layers))()
+        for k, blocks in enumerate(all_blocks):
+            for l, blk in enumerate(blocks):
+                d = descs[k * self.n_layers + l]
+                self._fill(d, blk, device, keep)
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.uq_model_create(C.byref(handle), self.n_members, self.n_layers, descs,
+                                           _stream_ptr(device)))
+        self._handle = handle
+        self._lib = lib
+        self.supports_bf16 = bool(lib.uq_model_supports_bf16(handle))
+        self.bf16_reason = "" if self.supports_bf16 else lib.uq_last_error().decode()
+        del keep  # uq_model_create synchronised its stream: our staging copies may go
+
+    @staticmethod
+    def _fill(d: "_lib.LayerDesc", blk: Block, device, keep) -> None:
+        lin = blk.linear
+        d.in_features, d.out_features = lin.in_features, lin.out_features
+        w = _f32_cuda(lin.weight, device, keep)
+        b = _f32_cuda(lin.bias, device, keep)
+        d.weight = w.data_ptr()
+        d.bias = b.data_ptr() if b is not None else None
+        if blk.bn is not None:
+            bn = blk.bn
+            g = _f32_cuda(bn.weight, device, keep)
+            bb = _f32_cuda(bn.bias, device, keep)
+            d.bn_weight = g.data_ptr() if g is not None else None
+            d.bn_bias = bb.data_ptr() if bb is not None else None
+            d.bn_mean = _f32_cuda(bn.running_mean, device, keep).data_ptr()
+            d.bn_var = _f32_cuda(bn.running_var, device, keep).data_ptr()
+            d.bn_eps = float(bn.eps)
+        d.relu = 1 if blk.relu else 0
+        d.dropout = 1 if blk.dropout else 0
+
+    def close(self) -> None:
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            self._lib.uq_model_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _args(self, mode, precision, total_members, member_begin, member_count, dropout_p,
+              dropout_active, seed, offset, masks, anchors, output) -> "_lib.ForwardArgs":
+        a = _lib.ForwardArgs()
+        a.mode = _MODE[mode]
+        if precision not in _PREC:
+            raise ValueError(f"unknown precision {precision!r} (use 'fp32' or 'bf16')")
+        a.precision = _PREC[precision]
+        a.output = _lib.OUT_MOMENTS if output == "moments" else _lib.OUT_MEAN_STD
+        a.member_begin = int(member_begin)
+        a.member_count = int(total_members - member_begin if member_count is None else member_count)
+        a.total_members = int(total_members)
+        a.dropout_active = 1 if dropout_active else 0
+        a.dropout_p = float(dropout_p)
+        a.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+        a.masks = masks.data_ptr() if masks is not None else None
+        a.anchors = anchors.data_ptr() if anchors is not None else None
+        return a
+
+    def forward(self, x: torch.Tensor, mode: str, *, total_members: int, precision: str = "fp32",
+                member_begin: int = 0, member_count: Optional[int] = None,
+                dropout_p: float = 0.0, dropout_active: bool = True, seed: int = 0,
+                offset: int = 0, masks: Optional[torch.Tensor] = None,
+                anchors: Optional[torch.Tensor] = None,
+                output: str = "mean_std") -> Tuple[torch.Tensor, torch.Tensor]:
+        """(mean, std) -- or (mean, M2) with ``output='moments'`` -- of shape ``[n, d_out]``."""
+        _require_cuda(x, "x")
+        d_x = self.d_in // 2 if mode == "delta_uq" else self.d_in
+        if x.dim() != 2 or x.shape[1] != d_x:
+            raise ValueError(f"x must be [n, {d_x}], got {tuple(x.shape)}")
+        if x.shape[0] == 0:
+            raise ValueError("x has no rows")
+        xf = x.detach()
+        if xf.dtype != torch.float32 or not xf.is_contiguous():
+            xf = xf.to(torch.float32).contiguous()
+        if masks is not None:
+            _require_cuda(masks, "masks")
+            if masks.dtype != torch.uint8 or not masks.is_contiguous():
+                raise ValueError("masks must be a contiguous uint8 tensor")
+            need = sum(total_members * x.shape[0] * w for w in self.dropout_widths)
+            if masks.numel() != need:
+                raise ValueError(f"masks has {masks.numel()} bytes, expected {need}")
+        if anchors is not None:
+            _require_cuda(anchors, "anchors")
+            anchors = anchors.detach().to(torch.float32).contiguous()
+            if anchors.dim() != 2 or anchors.shape[1] != d_x or anchors.shape[0] < total_members:
+                raise ValueError(f"anchors must be [>= {total_members}, {d_x}]")
+        a = self._args(mode, precision, total_members, member_begin, member_count, dropout_p,
+                       dropout_active, seed, offset, masks, anchors, output)
+        n = xf.shape[0]
+        dev = xf.device
+        with torch.cuda.device(dev):
+            out0 = torch.empty((n, self.d_out), dtype=torch.float32, device=dev)
+            out1 = torch.empty((n, self.d_out), dtype=torch.float32, device=dev)
+            wsb = int(self._lib.uq_forward_workspace_bytes(self._handle, n, C.byref(a)))
+            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+            _lib.check(self._lib.uq_forward(self._handle, xf.data_ptr(), n, C.byref(a),
+                                            out0.data_ptr(), out1.data_ptr(), ws.data_ptr(), wsb,
+                                            None, _stream_ptr(dev)))
+        return out0, out1
+
+    def forward_host(self, x_host: torch.Tensor, out0_host: torch.Tensor, out1_host: torch.Tensor,
+                     mode: str, *, total_members: int, precision: str = "fp32",
+                     dropout_p: float = 0.0, dropout_active: bool = True, seed: int = 0,
+                     offset: int = 0, anchors: Optional[torch.Tensor] = None) -> None:
+        """End-to-end call on HOST buffers (``uq_forward_host``): H2D, forward, D2H, sync."""
+        for t in (x_host, out0_host, out1_host):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("forward_host takes contiguous float32 CPU tensors")
+        a = self._args(mode, precision, total_members, 0, None, dropout_p, dropout_active, seed,
+                       offset, None, anchors, "mean_std")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.uq_forward_host(self._handle, x_host.data_ptr(), x_host.shape[0],
+                                                 C.byref(a), out0_host.data_ptr(),
+                                                 out1_host.data_ptr(), _stream_ptr(self.device)))
+
+
+def philox_keep_masks(n: int, widths: Sequence[int], total_members: int, dropout_p: float, seed: int,
+                      offset: int, device) -> torch.Tensor:
+    """The keep-masks the native Philox path draws, in the injected-mask layout (uint8)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    total = sum(total_members * n * w for w in widths)
+    out = torch.empty(total, dtype=torch.uint8, device=device)
+    off = 0
+    with torch.cuda.device(device):
+        for l, w in enumerate(widths):
+            _lib.check(lib.uq_philox_keep_masks(out.data_ptr() + off, n, w, total_members, l,
+                                                float(dropout_p), int(seed), int(offset),
+                                                _stream_ptr(device)))
+            off += total_members * n * w
+    return out
+
+
+def moments_merge(means: torch.Tensor, m2s: torch.Tensor, counts: Sequence[float]
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Chan-merge ``[S, ...]`` shard moments into (mean, unbiased std) of shape ``[...]``."""
+    lib = _lib.load()
+    _require_cuda(means, "means")
+    _require_cuda(m2s, "m2s")
+    means = means.contiguous()
+    m2s = m2s.contiguous()
+    if means.dtype != torch.float32 or m2s.dtype != torch.float32 or means.shape != m2s.shape:
+        raise ValueError("means / m2s must be float32 tensors of the same shape")
+    s = means.shape[0]
+    if len(counts) != s:
+        raise ValueError("one count per shard is required")
+    length = means[0].numel()
+    out_mean = torch.empty(means.shape[1:], dtype=torch.float32, device=means.device)
+    out_std = torch.empty_like(out_mean)
+    cnt = (C.c_double * s)(*[float(c) for c in counts])
+    with torch.cuda.device(means.device):
+        _lib.check(lib.uq_moments_merge(means.data_ptr(), m2s.data_ptr(), cnt, s, length,
+                                        out_mean.data_ptr(), out_std.data_ptr(),
+                                        _stream_ptr(means.device)))
+    return out_mean, out_std
+
+
+def _flat_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    _require_cuda(t, what)
+    t = t.detach().reshape(-1)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+def wasserstein_1d(u: torch.Tensor, v: torch.Tensor) -> float:
+    """``scipy.stats.wasserstein_distance(u, v)`` for float32 device samples."""
+    lib = _lib.load()
+    u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
+    if u.numel() == 0 or v.numel() == 0:
+        raise ValueError("Distribution can't be empty.")
+    out = C.c_double()
+    with torch.cuda.device(u.device):
+        wsb = int(lib.uq_wasserstein_workspace_bytes(u.numel(), v.numel()))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
+        _lib.check(lib.uq_wasserstein_1d(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
+                                         C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
+    return float(out.value)
+
+
+def kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000) -> float:
+    """``JensenShannonEvaluation.pdf_jsd(u, v, num_points)`` for float32 device samples."""
+    lib = _lib.load()
+    u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
+    out = C.c_double()
+    with torch.cuda.device(u.device):
+        wsb = int(lib.uq_kde_jsd_workspace_bytes(u.numel(), v.numel(), num_points))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
+        _lib.check(lib.uq_kde_jsd(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), num_points,
+                                  C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
+    return float(out.value)
