@@ -245,7 +245,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
   uint8_t* a_smem = smem;                                    // KC chunks of 16 KB
   uint8_t* w_smem = smem + (size_t)p.KC * CHUNK_BYTES;       // n_stages x stage_bytes
   Barriers* bars = reinterpret_cast<Barriers*>(w_smem + (size_t)p.n_stages * p.stage_bytes);
-  float* xchg = reinterpret_cast<float*>(bars + 1);          // [2][128][MAX_DOUT] dot exchange
+  float* xchg = reinterpret_cast<float*>(bars + 1);          // [2][128][d_out] dot exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_tiles * p.splits;
@@ -513,9 +513,9 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
         }
 
         // ---- combine the two column-parity halves of the dot products, then Welford ----------
-        float* xb = xchg + (size_t)(mcount & 1) * TILE_M * MAX_DOUT;
+        float* xb = xchg + (size_t)(mcount & 1) * TILE_M * p.d_out;
         if (hf == 1) {
-          for (int o = 0; o < p.d_out; ++o) xb[row * MAX_DOUT + o] = dot[o];
+          for (int o = 0; o < p.d_out; ++o) xb[row * p.d_out + o] = dot[o];
         }
         epi_bar_sync();
         if (hf == 0) {
@@ -523,7 +523,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const float inv_n = 1.f / wf_n;
           const float* bl = p.b_last + (size_t)wslot * p.d_out;
           for (int o = 0; o < p.d_out; ++o) {
-            float y = dot[o] + (p.KC > 1 ? xb[row * MAX_DOUT + o] : 0.f) + __ldg(bl + o);
+            float y = dot[o] + (p.KC > 1 ? xb[row * p.d_out + o] : 0.f) + __ldg(bl + o);
             if (p.last_relu) y = fmaxf(y, 0.f);
             const float dlt = y - wf_mean[o];
             wf_mean[o] += dlt * inv_n;
@@ -612,7 +612,7 @@ __global__ void fold_bias_kernel(const float* __restrict__ bias, const float* __
 size_t tc_smem_bytes(const TcPlan& t, int n_stages) {
   const int KC = t.hidden / 64;
   return 1024 + (size_t)KC * CHUNK_BYTES + (size_t)n_stages * t.stage_bytes + sizeof(Barriers) +
-         2 * TILE_M * MAX_DOUT * sizeof(float) + 64;
+         2 * TILE_M * (size_t)t.d_out * sizeof(float) + 64;
 }
 
 int pick_stages(const TcPlan& t) {

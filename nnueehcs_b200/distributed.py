@@ -51,6 +51,27 @@ class KShard:
         dist.all_gather_into_tensor(gathered, slab, group=self.group)
         return gathered[:, 0], gathered[:, 1]
 
+    def forward_owned(self, packed: "ops.PackedModel", x: torch.Tensor, mode: str, *,
+                      local_members: int, precision: str = "fp32",
+                      **kw) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Each rank's ``packed`` holds ONLY its own shard of the members (an ensemble whose
+        weights are distributed over the GPUs): reduce locally, exchange moments, merge."""
+        mean, m2 = packed.forward(x, mode, total_members=local_members, precision=precision,
+                                  output="moments", **kw)
+        means, m2s = self.exchange(mean, m2)
+        return ops.moments_merge(means.contiguous(), m2s.contiguous(),
+                                 self.owned_counts(local_members, x.device))
+
+    def owned_counts(self, local_members: int, device) -> List[float]:
+        """Member count of every rank's shard (gathered once, then cached: it is static)."""
+        cache = self.__dict__.setdefault("_owned_counts", {})
+        if local_members not in cache:
+            cnt = torch.tensor([float(local_members)], dtype=torch.float64, device=device)
+            all_cnt = torch.empty(self.world, dtype=torch.float64, device=device)
+            dist.all_gather_into_tensor(all_cnt, cnt, group=self.group)
+            cache[local_members] = all_cnt.tolist()
+        return cache[local_members]
+
     def forward(self, packed: "ops.PackedModel", x: torch.Tensor, mode: str, *, total_members: int,
                 precision: str = "fp32", **kw) -> Tuple[torch.Tensor, torch.Tensor]:
         begin, count = self.split(total_members)

@@ -33,6 +33,10 @@ def split_blocks(net: nn.Sequential) -> List[Block]:
         if isinstance(m, nn.Linear):
             blocks.append(Block(linear=m))
             continue
+        if not isinstance(m, (nn.BatchNorm1d, nn.ReLU, nn.Dropout)):
+            raise ValueError(
+                f"layer {idx}: {type(m).__name__} is not supported by the fused UQ forward "
+                "(supported: Linear, BatchNorm1d, ReLU, Dropout)")
         if not blocks:
             raise ValueError(f"layer {idx} ({type(m).__name__}) precedes the first Linear")
         cur = blocks[-1]
@@ -53,10 +57,6 @@ def split_blocks(net: nn.Sequential) -> List[Block]:
             if cur.dropout:
                 raise ValueError(f"layer {idx}: two Dropouts in a row")
             cur.dropout = True
-        else:
-            raise ValueError(
-                f"layer {idx}: {type(m).__name__} is not supported by the fused UQ forward "
-                "(supported: Linear, BatchNorm1d, ReLU, Dropout)")
     if not blocks:
         raise ValueError("network has no Linear layer")
     for a, b in zip(blocks[:-1], blocks[1:]):

@@ -1,0 +1,358 @@
+"""Parity of the CUDA UQ forward with the reference (B200 only: ``pytest -m gpu``).
+
+Every comparison goes through the C ABI (``ops.PackedModel`` -> ``uq_forward``) or the wrapper
+mirror on top of it.  References are (a) the golden outputs of the reference's own classes
+(``tests/golden``) and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances
+----------
+fp32 mode : north_star's 1e-5 relative, read as ``|got-ref| <= 1e-5*|ref| + 1e-5*max|mean_ref|``
+            (the absolute floor is tied to the output scale because std -> 0 in-distribution).
+bf16 mode : stated tolerance ``|got-ref| <= 3e-2 * max|ref|`` for the mean and
+            ``<= 6e-2 * max|ref_std| + 3e-2 * max|ref_mean|`` for the std (bf16 has 8 mantissa bits;
+            activations and weights are rounded once per layer).  Measured errors are printed.
+"""
+import numpy as np
+import pytest
+import torch
+
+from nnueehcs_b200 import ops
+from nnueehcs_b200.model_builder import (DeltaUQMLPModelBuilder, EnsembleModelBuilder,
+                                         MCDropoutModelBuilder, build_network)
+from oracle import uq_oracle
+from tests.util import (assert_close_ref, delta_arch, golden_arch, golden_masks, injected_to_masks,
+                        load_golden, masks_to_injected, mc_arch_with_dropout, nets_from_golden)
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+RTOL32 = 1e-5
+
+
+def _bf16_check(mean, std, ref_mean, ref_std, what):
+    mean, std = mean.double().cpu(), std.double().cpu()
+    ref_mean, ref_std = torch.as_tensor(ref_mean).double(), torch.as_tensor(ref_std).double()
+    ms, ss = float(ref_mean.abs().max()), float(ref_std.abs().max())
+    e_mean = float((mean - ref_mean).abs().max())
+    e_std = float((std - ref_std).abs().max())
+    print(f"[bf16 {what}] max|mean err| = {e_mean:.3e} ({e_mean / ms:.3e} of scale), "
+          f"max|std err| = {e_std:.3e} ({e_std / max(ss, 1e-30):.3e} of std scale)")
+    assert e_mean <= 3e-2 * ms, f"{what}: bf16 mean error {e_mean} vs scale {ms}"
+    assert e_std <= 6e-2 * ss + 3e-2 * ms, f"{what}: bf16 std error {e_std}"
+
+
+# ---- ensemble -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["ensemble_small.npz", "ensemble_bn.npz", "ensemble_binomial.npz"])
+def test_ensemble_fp32_matches_reference_golden(name):
+    g = load_golden(name)
+    k = int(g["k"])
+    packed = ops.PackedModel(nets_from_golden(g, k), DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    mean, std = packed.forward(x, "ensemble", total_members=k, precision="fp32")
+    assert mean.shape == g["mean"].shape
+    assert_close_ref(mean, g["mean"], RTOL32, what=f"{name} mean")
+    assert_close_ref(std, g["std"], RTOL32, scale_ref=g["mean"], what=f"{name} std")
+
+
+@pytest.mark.parametrize("name", ["ensemble_bn.npz", "ensemble_binomial.npz"])
+def test_ensemble_bf16_within_stated_tolerance(name):
+    g = load_golden(name)
+    k = int(g["k"])
+    packed = ops.PackedModel(nets_from_golden(g, k), DEV)
+    assert packed.supports_bf16, packed.bf16_reason
+    x = torch.from_numpy(g["x"]).to(DEV)
+    mean, std = packed.forward(x, "ensemble", total_members=k, precision="bf16")
+    _bf16_check(mean, std, g["mean"], g["std"], name)
+
+
+def test_bf16_rejects_unsupported_shapes_loudly():
+    g = load_golden("ensemble_small.npz")  # 25-wide layers, 5 outputs
+    packed = ops.PackedModel(nets_from_golden(g, int(g["k"])), DEV)
+    assert not packed.supports_bf16
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with pytest.raises(ValueError, match="bf16 path unavailable"):
+        packed.forward(x, "ensemble", total_members=int(g["k"]), precision="bf16")
+
+
+def test_ensemble_wrapper_drop_in():
+    """Model built by the builder mirror from the YAML-style description, golden weights loaded,
+    ``model(x, return_ue=True)`` as ``evaluation.py:135`` calls it."""
+    g = load_golden("ensemble_binomial.npz")
+    k = int(g["k"])
+    model = EnsembleModelBuilder(golden_arch(g), {"num_models": k}).build()
+    for net, ref in zip(model.models, nets_from_golden(g, k)):
+        net.load_state_dict(ref.state_dict())
+    model.to(DEV)
+    model.eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with torch.no_grad():
+        mean, std = model(x, return_ue=True)
+        only_mean = model(x)
+    assert_close_ref(mean, g["mean"], RTOL32, what="wrapper mean")
+    assert_close_ref(std, g["std"], RTOL32, scale_ref=g["mean"], what="wrapper std")
+    assert torch.equal(only_mean, mean)
+    # packed-weight cache: reused while weights are untouched, rebuilt after an in-place update
+    cache = model.__dict__["_uq_cache"][1]
+    model(x)
+    assert model.__dict__["_uq_cache"][1] is cache
+    with torch.no_grad():
+        model.models[0][-1].bias.add_(1.0)
+    mean2 = model(x)
+    assert model.__dict__["_uq_cache"][1] is not cache
+    assert_close_ref(mean2, g["mean"] + 1.0 / k, RTOL32, what="wrapper mean after update")
+    # float64 datasets (bo.py:396 casts models with .to(dset.dtype)): outputs keep x's dtype
+    m64, s64 = model(x.double(), return_ue=True)
+    assert m64.dtype == torch.float64 and s64.dtype == torch.float64
+
+
+# ---- MC dropout -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["mcdropout_small.npz", "mcdropout_binomial.npz"])
+def test_mc_dropout_fp32_injected_reference_masks(name):
+    g = load_golden(name)
+    p, passes = float(g["p"]), int(g["passes"])
+    net = nets_from_golden(g, 1, arch=mc_arch_with_dropout(golden_arch(g), p))[0]
+    packed = ops.PackedModel([net], DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    inj = masks_to_injected(golden_masks(g)).to(DEV)
+    mean, std = packed.forward(x, "mc_dropout", total_members=passes, precision="fp32",
+                               dropout_p=p, masks=inj)
+    assert_close_ref(mean, g["mean"], RTOL32, what=f"{name} mean")
+    assert_close_ref(std, g["std"], RTOL32, scale_ref=g["mean"], what=f"{name} std")
+
+
+@pytest.mark.parametrize("name", ["mcdropout_small.npz", "mcdropout_binomial.npz"])
+def test_mc_dropout_off_fp32(name):
+    g = load_golden(name)
+    p, passes = float(g["p"]), int(g["passes"])
+    net = nets_from_golden(g, 1, arch=mc_arch_with_dropout(golden_arch(g), p))[0]
+    packed = ops.PackedModel([net], DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    mean, std = packed.forward(x, "mc_dropout", total_members=passes, precision="fp32",
+                               dropout_p=p, dropout_active=False)
+    assert_close_ref(mean, g["mean_off"], RTOL32, what=f"{name} mean_off")
+    assert float(std.abs().max()) <= RTOL32 * float(np.abs(g["mean_off"]).max())
+
+
+def test_mc_dropout_bf16_injected_masks():
+    g = load_golden("mcdropout_binomial.npz")
+    p, passes = float(g["p"]), int(g["passes"])
+    net = nets_from_golden(g, 1, arch=mc_arch_with_dropout(golden_arch(g), p))[0]
+    packed = ops.PackedModel([net], DEV)
+    assert packed.supports_bf16, packed.bf16_reason
+    x = torch.from_numpy(g["x"]).to(DEV)
+    inj = masks_to_injected(golden_masks(g)).to(DEV)
+    mean, std = packed.forward(x, "mc_dropout", total_members=passes, precision="bf16",
+                               dropout_p=p, masks=inj)
+    _bf16_check(mean, std, g["mean"], g["std"], "mcdropout_binomial injected")
+    mean0, std0 = packed.forward(x, "mc_dropout", total_members=passes, precision="bf16",
+                                 dropout_p=p, dropout_active=False)
+    _bf16_check(mean0, std0, g["mean_off"], g["std_off"], "mcdropout_binomial off")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mc_dropout_native_philox_replays_exactly_through_oracle(precision):
+    """Native masks are a pure function of (seed, pass, layer, sample, feature): export them with
+    uq_philox_keep_masks, replay through the CPU oracle, compare -- exact parity for the native
+    RNG path, not just statistics."""
+    g = load_golden("mcdropout_binomial.npz")
+    p, passes, seed = 0.2, 12, 20261018
+    net = nets_from_golden(g, 1, arch=mc_arch_with_dropout(golden_arch(g), p))[0]
+    packed = ops.PackedModel([net], DEV)
+    x_cpu = torch.from_numpy(g["x"])[:150]
+    x = x_cpu.to(DEV)
+    mean, std = packed.forward(x, "mc_dropout", total_members=passes, precision=precision,
+                               dropout_p=p, seed=seed)
+    flat = ops.philox_keep_masks(x.shape[0], packed.dropout_widths, passes, p, seed, 0, DEV)
+    masks = injected_to_masks(flat.cpu(), x.shape[0], packed.dropout_widths, passes)
+    ref_mean, ref_std = uq_oracle.mc_dropout_forward(net, x_cpu, passes, p, masks=masks)
+    if precision == "fp32":
+        assert_close_ref(mean, ref_mean, RTOL32, what="philox replay mean")
+        assert_close_ref(std, ref_std, RTOL32, scale_ref=ref_mean, what="philox replay std")
+    else:
+        _bf16_check(mean, std, ref_mean, ref_std, "philox replay")
+    # and feeding the exported masks back as injected masks gives the identical result
+    mean_i, std_i = packed.forward(x, "mc_dropout", total_members=passes, precision=precision,
+                                   dropout_p=p, masks=flat)
+    assert torch.equal(mean, mean_i) and torch.equal(std, std_i)
+
+
+def test_philox_mask_statistics():
+    p, n, w, passes = 0.2, 4096, 128, 16
+    flat = ops.philox_keep_masks(n, [w], passes, p, 7, 0, DEV).float()
+    m = flat.reshape(passes, n, w)
+    total = m.numel()
+    keep = float(m.mean())
+    # 99.99 % two-sided binomial interval
+    half = 3.9 * (p * (1 - p) / total) ** 0.5
+    assert abs(keep - (1 - p)) < half + 2 ** -16
+    # different passes / features are uncorrelated: pairwise agreement ~ keep^2 + (1-keep)^2
+    agree = float((m[0] == m[1]).float().mean())
+    assert abs(agree - (keep ** 2 + (1 - keep) ** 2)) < 5e-3
+    other = ops.philox_keep_masks(n, [w], passes, p, 8, 0, DEV).float()
+    assert float((other == flat).float().mean()) < 0.75
+    again = ops.philox_keep_masks(n, [w], passes, p, 7, 0, DEV).float()
+    assert torch.equal(again, flat)
+
+
+def test_mc_dropout_wrapper_statistical_parity_with_reference_rng():
+    """Native Philox vs the reference's torch-RNG run (golden): per-sample mean inside
+    +-5 standard errors, pooled std ratio inside the chi-square band (stated CI)."""
+    g = load_golden("mcdropout_binomial.npz")
+    p = float(g["p"])
+    passes = 512
+    model = MCDropoutModelBuilder(golden_arch(g), {"num_samples": passes,
+                                                   "dropout_percent": p}).build()
+    ref_net = nets_from_golden(g, 1, arch=mc_arch_with_dropout(golden_arch(g), p))[0]
+    model.model.load_state_dict(ref_net.state_dict())
+    model.to(DEV)
+    model.eval()
+    x_cpu = torch.from_numpy(g["x"])[:64]
+    torch.manual_seed(3)
+    with torch.no_grad():
+        mean, std = model(x_cpu.to(DEV), return_ue=True)
+    torch.manual_seed(11)
+    ref_mean, ref_std = uq_oracle.mc_dropout_forward(ref_net, x_cpu, passes, p)  # torch RNG
+    se = (ref_std ** 2 / passes + std.cpu() ** 2 / passes).sqrt().clamp_min(1e-7)
+    z = ((mean.cpu() - ref_mean).abs() / se).max()
+    assert float(z) < 5.0, f"mean z-score {float(z)}"
+    ratio = (std.cpu() / ref_std)
+    assert float(ratio.min()) > 0.8 and float(ratio.max()) < 1.25, (ratio.min(), ratio.max())
+    # nn.Module.eval semantics (dropout off) -> identical passes, std == 0
+    torch.nn.Module.eval(model)
+    with torch.no_grad():
+        m_off, s_off = model(x_cpu.to(DEV), return_ue=True)
+    assert float(s_off.abs().max()) <= 1e-5 * float(m_off.abs().max())
+
+
+# ---- Delta-UQ (parity unpinned: oracle restatement only) -------------------------------------------
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_delta_uq_matches_restatement(precision):
+    g = load_golden("deltauq_small.npz")
+    k = int(g["k"])
+    net = nets_from_golden(g, 1, arch=delta_arch(golden_arch(g)))[0]
+    packed = ops.PackedModel([net], DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    anchors = torch.from_numpy(g["anchors"]).to(DEV)
+    mean, std = packed.forward(x, "delta_uq", total_members=k, precision=precision,
+                               anchors=anchors)
+    ref_mean, ref_std = uq_oracle.delta_uq_forward(net, torch.from_numpy(g["x"]),
+                                                   torch.from_numpy(g["anchors"]), k)
+    if precision == "fp32":
+        assert_close_ref(mean, ref_mean, RTOL32, what="delta mean")
+        assert_close_ref(std, ref_std, RTOL32, scale_ref=ref_mean, what="delta std")
+    else:
+        _bf16_check(mean, std, ref_mean, ref_std, "delta_uq")
+
+
+def test_delta_uq_wrapper():
+    g = load_golden("deltauq_small.npz")
+    k = int(g["k"])
+    model = DeltaUQMLPModelBuilder(golden_arch(g), {"estimator": "std", "num_anchors": k,
+                                                    "anchored_batch_size": int(g["chunk"])}).build()
+    ref_net = nets_from_golden(g, 1, arch=delta_arch(golden_arch(g)))[0]
+    model.net.load_state_dict(ref_net.state_dict())
+    model.anchors = torch.from_numpy(g["anchors"])
+    model.to(DEV)
+    model.eval()
+    with torch.no_grad():
+        mean, std = model(torch.from_numpy(g["x"]).to(DEV), return_ue=True)
+    assert_close_ref(mean, g["mean"], 2e-5, what="delta wrapper mean")
+    assert_close_ref(std, g["std"], 2e-5, scale_ref=g["mean"], what="delta wrapper std")
+
+
+# ---- K-axis shards, tails, errors ---------------------------------------------------------------------
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_member_shards_merge_to_the_full_result(precision):
+    g = load_golden("ensemble_binomial.npz")
+    k = int(g["k"])
+    packed = ops.PackedModel(nets_from_golden(g, k), DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    full_mean, full_std = packed.forward(x, "ensemble", total_members=k, precision=precision)
+    means, m2s, counts = [], [], []
+    for b, c in ((0, 1), (1, 2)):
+        m, s = packed.forward(x, "ensemble", total_members=k, precision=precision,
+                              member_begin=b, member_count=c, output="moments")
+        means.append(m), m2s.append(s), counts.append(c)
+    mean, std = ops.moments_merge(torch.stack(means), torch.stack(m2s), counts)
+    tol = 1e-6 if precision == "fp32" else 2e-6
+    assert_close_ref(mean, full_mean, tol, what="sharded mean")
+    assert_close_ref(std, full_std, 10 * tol, scale_ref=full_mean, what="sharded std")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("n", [1, 127, 129, 1000])
+def test_ragged_sample_counts(precision, n):
+    g = load_golden("ensemble_bn.npz")
+    k = int(g["k"])
+    nets = nets_from_golden(g, k)
+    packed = ops.PackedModel(nets, DEV)
+    x_cpu = torch.rand(n, 5, generator=torch.Generator().manual_seed(n))
+    mean, std = packed.forward(x_cpu.to(DEV), "ensemble", total_members=k, precision=precision)
+    ref_mean, ref_std = uq_oracle.ensemble_forward(nets, x_cpu)
+    if precision == "fp32":
+        assert_close_ref(mean, ref_mean, RTOL32, what=f"n={n} mean")
+        assert_close_ref(std, ref_std, RTOL32, scale_ref=ref_mean, what=f"n={n} std")
+    else:
+        _bf16_check(mean, std, ref_mean, ref_std, f"n={n}")
+
+
+def test_many_passes_few_samples_uses_member_splits():
+    """cfg-1 shape (few sample tiles, many passes): the bf16 kernel also splits the pass axis over
+    CTAs and Chan-merges the partial moments; result must equal the fp32 path on the same masks."""
+    g = load_golden("mcdropout_binomial.npz")
+    p, passes, seed = 0.2, 96, 5
+    net = nets_from_golden(g, 1, arch=mc_arch_with_dropout(golden_arch(g), p))[0]
+    packed = ops.PackedModel([net], DEV)
+    x = torch.rand(300, 5, generator=torch.Generator().manual_seed(1)).to(DEV)
+    m32, s32 = packed.forward(x, "mc_dropout", total_members=passes, precision="fp32",
+                              dropout_p=p, seed=seed)
+    m16, s16 = packed.forward(x, "mc_dropout", total_members=passes, precision="bf16",
+                              dropout_p=p, seed=seed)
+    _bf16_check(m16, s16, m32.cpu(), s32.cpu(), "member splits")
+
+
+def test_single_member_std_is_nan_like_torch():
+    g = load_golden("ensemble_bn.npz")
+    nets = nets_from_golden(g, 1)
+    packed = ops.PackedModel(nets, DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    for precision in ("fp32", "bf16"):
+        mean, std = packed.forward(x, "ensemble", total_members=1, precision=precision)
+        assert torch.isnan(std).all() and torch.isfinite(mean).all()
+
+
+def test_argument_errors():
+    g = load_golden("ensemble_bn.npz")
+    k = int(g["k"])
+    packed = ops.PackedModel(nets_from_golden(g, k), DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with pytest.raises(ValueError, match="total_members"):
+        packed.forward(x, "ensemble", total_members=k + 1)
+    with pytest.raises(ValueError, match="single packed network"):
+        packed.forward(x, "mc_dropout", total_members=4, dropout_p=0.1)
+    with pytest.raises(ValueError, match=r"x must be \[n, 5\]"):
+        packed.forward(x[:, :3], "ensemble", total_members=k)
+    with pytest.raises(ValueError, match="no rows"):
+        packed.forward(x[:0], "ensemble", total_members=k)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        packed.forward(x.cpu(), "ensemble", total_members=k)
+    with pytest.raises(ValueError, match="unknown precision"):
+        packed.forward(x, "ensemble", total_members=k, precision="fp8")
+    with pytest.raises(ValueError, match="different architecture"):
+        ops.PackedModel([build_network([{"Linear": {"args": [5, 8]}}]),
+                         build_network([{"Linear": {"args": [5, 9]}}])], DEV)
+
+
+def test_host_buffer_entry_point():
+    g = load_golden("ensemble_binomial.npz")
+    k = int(g["k"])
+    packed = ops.PackedModel(nets_from_golden(g, k), DEV)
+    x = torch.from_numpy(g["x"]).contiguous().pin_memory()
+    out0 = torch.empty(g["mean"].shape, dtype=torch.float32).pin_memory()
+    out1 = torch.empty_like(out0).pin_memory()
+    packed.forward_host(x, out0, out1, "ensemble", total_members=k, precision="fp32")
+    assert_close_ref(out0, g["mean"], RTOL32, what="host mean")
+    assert_close_ref(out1, g["std"], RTOL32, scale_ref=g["mean"], what="host std")

@@ -1,0 +1,126 @@
+"""Parity of the CUDA metric kernels with scipy (via goldens and the numpy oracle).  B200 only.
+
+Wasserstein: the kernel performs the same float64 arithmetic as scipy on the same sorted values,
+only the summation order differs -> relative 1e-12.
+KDE-JS: scipy evaluates every kernel term in float64; the kernel evaluates them in float32 on
+window-relative coordinates with MUFU.EX2 and truncates beyond 9 bandwidths -> stated tolerance
+relative 2e-5 on the distance (measured values are printed).
+"""
+import numpy as np
+import pytest
+import torch
+
+from nnueehcs_b200 import evaluation, ops
+from oracle import metrics_oracle
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+JSD_RTOL = 2e-5
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("name", ["metrics_small.npz", "metrics_medium.npz"])
+def test_wasserstein_matches_scipy_golden(name):
+    g = load_golden(name)
+    w = ops.wasserstein_1d(_dev(g["id"]), _dev(g["ood"]))
+    assert w == pytest.approx(float(g["wasserstein"]), rel=1e-12)
+    assert ops.wasserstein_1d(_dev(g["id"]), _dev(g["id"])) == 0.0
+
+
+@pytest.mark.parametrize("nu,nv", [(1, 1), (1, 7), (5, 3), (4096, 4097), (10000, 333),
+                                   (70001, 130003)])
+def test_wasserstein_sizes_ties_and_negatives(nu, nv):
+    rng = np.random.default_rng(nu * 7 + nv)
+    u = rng.normal(0.0, 1.0, nu).astype(np.float32)
+    v = (rng.normal(0.2, 2.0, nv)).astype(np.float32)
+    if nu > 10:
+        u[: nu // 3] = np.round(u[: nu // 3], 1)  # heavy ties, including -0.0 / +0.0
+        v[: nv // 3] = np.round(v[: nv // 3], 1)
+    ref = metrics_oracle.wasserstein_1d(u, v)
+    got = ops.wasserstein_1d(_dev(u), _dev(v))
+    assert got == pytest.approx(ref, rel=1e-11, abs=1e-15)
+    assert ops.wasserstein_1d(_dev(v), _dev(u)) == pytest.approx(ref, rel=1e-11, abs=1e-15)
+
+
+def test_wasserstein_properties_and_reference_edge_cases():
+    # reference tests/test_evaluation.py:189-208, :296-314
+    a = torch.linspace(0, 1, 1000, device=DEV)
+    assert ops.wasserstein_1d(a, a) == 0.0
+    assert ops.wasserstein_1d(a, a + 5.0) == pytest.approx(5.0, rel=1e-6)
+    ext = torch.tensor([1e-10, 1e10, 1.0, 3.0], device=DEV)
+    assert np.isfinite(ops.wasserstein_1d(ext, ext.flip(0) * 2))
+    with pytest.raises(ValueError, match="can't be empty"):
+        ops.wasserstein_1d(a[:0], a)
+    # input tensors are left untouched (the kernel sorts copies)
+    b = torch.rand(5000, device=DEV)
+    keep = b.clone()
+    ops.wasserstein_1d(b, a)
+    assert torch.equal(b, keep)
+
+
+def test_wasserstein_large_shift_property():
+    """size-independent property at scale: W1(u, u + c) == c, W1(u, u) == 0 (8 M + 8 M values)."""
+    n = 8 * 1024 * 1024
+    u = torch.rand(n, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0)) * 0.25
+    assert ops.wasserstein_1d(u, u) == 0.0
+    assert ops.wasserstein_1d(u, u + 0.5) == pytest.approx(0.5, rel=2e-6)
+
+
+@pytest.mark.parametrize("name", ["metrics_small.npz", "metrics_medium.npz"])
+def test_kde_jsd_matches_reference_golden(name):
+    g = load_golden(name)
+    got = ops.kde_jsd(_dev(g["id"]), _dev(g["ood"]))
+    ref = float(g["jsd"])
+    print(f"[kde_jsd {name}] got {got:.12f} ref {ref:.12f} rel err {abs(got - ref) / ref:.3e}")
+    assert got == pytest.approx(ref, rel=JSD_RTOL)
+
+
+@pytest.mark.parametrize("nu,nv,grid", [(50, 60, 500), (2500, 700, 2000), (20000, 30000, 4096)])
+def test_kde_jsd_against_oracle(nu, nv, grid):
+    rng = np.random.default_rng(nu + nv)
+    u = rng.gamma(2.0, 0.05, nu).astype(np.float32)
+    v = rng.gamma(3.0, 0.08, nv).astype(np.float32)
+    ref = metrics_oracle.pdf_jsd(u, v, num_points=grid)
+    got = ops.kde_jsd(_dev(u), _dev(v), grid)
+    print(f"[kde_jsd {nu}x{nv}x{grid}] rel err {abs(got - ref) / ref:.3e}")
+    assert got == pytest.approx(ref, rel=JSD_RTOL)
+
+
+def test_kde_jsd_properties():
+    u = torch.rand(30000, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    assert ops.kde_jsd(u, u.clone()) == pytest.approx(0.0, abs=1e-6)
+    v = u * 0.5 + 2.0  # disjoint supports -> distance -> sqrt(ln 2)
+    d = ops.kde_jsd(u, v)
+    assert d == pytest.approx(np.sqrt(np.log(2.0)), rel=1e-3)
+    assert ops.kde_jsd(v, u) == pytest.approx(d, rel=1e-9)
+    with pytest.raises(ValueError, match="at least 2 values"):
+        ops.kde_jsd(u[:1], v)
+
+
+def test_metric_classes_drop_in():
+    """The evaluator mirror with a DummyModel as in reference tests/test_evaluation.py:11-28."""
+    g = load_golden("metrics_small.npz")
+    id_x, ood_x = torch.zeros(4, 3, device=DEV), torch.ones(4, 3, device=DEV)
+
+    class DummyModel:
+        def __call__(self, x, return_ue=False):
+            s = g["id"] if float(x.sum()) == 0.0 else g["ood"]
+            return None, torch.from_numpy(s).to(DEV).unsqueeze(-1)
+
+        def eval(self):
+            pass
+
+    ev = evaluation.get_uncertainty_evaluator(["wasserstein_distance", "jensen_shannon_distance"])
+    res = ev.evaluate(DummyModel(), (id_x, None), (ood_x, None))
+    assert set(res) == {"wasserstein_distance", "jensen_shannon_distance"}
+    assert all(isinstance(v, float) for v in res.values())
+    assert res["wasserstein_distance"] == pytest.approx(float(g["wasserstein"]), rel=1e-12)
+    assert res["jensen_shannon_distance"] == pytest.approx(float(g["jsd"]), rel=JSD_RTOL)
+    two = evaluation.WassersteinEvaluation()._evaluate_uncertainties(
+        evaluation.UncertaintyEstimate((torch.from_numpy(g["id"]), torch.from_numpy(g["id"]))),
+        evaluation.UncertaintyEstimate((torch.from_numpy(g["ood"]), torch.from_numpy(g["ood"]))))
+    assert two["wasserstein_distance"] == pytest.approx(float(g["wasserstein"]), rel=1e-12)

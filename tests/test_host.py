@@ -1,0 +1,292 @@
+"""Host-side logic (CPU only): the builder/wrapper mirror, the network walk, the C-ABI library.
+
+The builder tests follow the reference's own ``tests/test_model_builder.py`` (layer types and
+shapes :152-186, Delta-UQ input doubling :189-237, ensemble ``num_models`` :240-264, MC-dropout
+placement and train-mode flags :292-334).
+"""
+import ctypes
+import io
+import os
+import pickle
+import re
+
+import pytest
+import torch
+import torch.nn as nn
+import yaml
+
+from nnueehcs_b200 import _lib, build as nbuild, evaluation, extract, ops
+from nnueehcs_b200.model_builder import (DeltaUQMLPModelBuilder, EnsembleModelBuilder,
+                                         KDEModelBuilder, MCDropoutModelBuilder, MLPModelBuilder,
+                                         ModelBuilder, build_network)
+from nnueehcs_b200.models import DeltaUQMLP, EnsembleModel, MCDropoutModel, MLPModel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MODEL_YAML = """
+architecture_cnn:
+  - Conv2d:
+      args: [3, 16, 25]
+      stride: 1
+      padding: 2
+  - ReLU:
+      inplace: true
+  - Conv2d:
+      args: [16, 25, 5]
+architecture_mlp:
+  - Linear:
+      args: [16, 25]
+  - ReLU:
+      inplace: true
+  - Linear:
+      args: [25, 25]
+  - ReLU:
+      inplace: true
+  - Linear:
+      args: [25, 5]
+architecture_mlp4:
+  - Linear:
+      args: [16, 25]
+  - ReLU:
+      inplace: true
+  - Linear:
+      args: [25, 25]
+  - ReLU:
+      inplace: true
+  - Linear:
+      args: [25, 25]
+  - ReLU:
+      inplace: true
+  - Linear:
+      args: [25, 5]
+delta_uq_model:
+  estimator: std
+  num_anchors: 5
+  anchored_batch_size: 64
+ensemble_model:
+  num_models: 3
+mc_dropout_model:
+  num_samples: 7
+  dropout_percent: 0.2
+"""
+
+
+@pytest.fixture
+def descr():
+    return yaml.safe_load(io.StringIO(MODEL_YAML))
+
+
+def test_build_network_layer_types_and_shapes(descr):
+    net = ModelBuilder(descr["architecture_mlp"]).build()
+    assert isinstance(net, nn.Sequential) and len(net) == 5
+    assert [type(m) for m in net] == [nn.Linear, nn.ReLU, nn.Linear, nn.ReLU, nn.Linear]
+    assert (net[0].in_features, net[0].out_features) == (16, 25)
+    assert (net[4].in_features, net[4].out_features) == (25, 5)
+    cnn = ModelBuilder(descr["architecture_cnn"]).build()
+    assert isinstance(cnn[0], nn.Conv2d) and cnn[0].stride == (1, 1) and cnn[0].padding == (2, 2)
+    info = ModelBuilder(descr["architecture_cnn"]).get_info()
+    assert info.is_cnn() and not info.is_mlp() and info.num_layers() == 3 and info.num_inputs() == 3
+    info2 = ModelBuilder(descr["architecture_mlp"]).get_info()
+    assert info2.is_mlp() and info2.num_layers() == 5 and info2.num_inputs() == 16
+    assert not hasattr(info2, "get_estimator")
+    # the builder must not mutate the caller's description
+    assert descr["architecture_mlp"][0]["Linear"]["args"] == [16, 25]
+
+
+def test_mlp_builder_and_unknown_loss(descr):
+    m = MLPModelBuilder(descr["architecture_mlp"]).build()
+    assert isinstance(m, MLPModel)
+    assert m(torch.zeros(2, 16)).shape == (2, 5)
+    with pytest.raises(ValueError, match="Unknown loss function"):
+        MLPModelBuilder(descr["architecture_mlp"], train_config={"loss": "nope"}).build()
+    with pytest.raises(Exception):
+        build_network([{"NoSuchLayer": {"args": [1]}}])
+
+
+def test_ensemble_builder(descr):
+    b = EnsembleModelBuilder(descr["architecture_mlp"], descr["ensemble_model"])
+    model = b.build()
+    assert isinstance(model, EnsembleModel) and len(model.models) == 3
+    assert b.get_info().get_num_models() == 3
+    assert model.vectorize is False  # the reference builder never forwards it
+    # member i is seeded torch.manual_seed(42 + i)  (model_builder.py:229)
+    torch.manual_seed(43)
+    ref1 = build_network(descr["architecture_mlp"])
+    assert torch.equal(ref1[0].weight, model.models[1][0].weight)
+    assert not torch.equal(model.models[0][0].weight, model.models[1][0].weight)
+
+
+def test_mc_dropout_builder_placement_and_modes(descr):
+    b = MCDropoutModelBuilder(descr["architecture_mlp4"], descr["mc_dropout_model"])
+    model = b.build()
+    assert isinstance(model, MCDropoutModel)
+    names = [type(m).__name__ for m in model.model]
+    # Dropout right before every Linear of descr[1:-1]; none before the first or the last Linear
+    assert names == ["Linear", "ReLU", "Dropout", "Linear", "ReLU", "Dropout", "Linear", "ReLU",
+                     "Linear"]
+    assert [m.p for m in model.model if isinstance(m, nn.Dropout)] == [0.2, 0.2]
+    assert model.num_samples == 7 and model.dropout_percent == 0.2
+    info = b.get_info()
+    assert info.get_num_samples() == 7 and info.get_dropout_percent() == 0.2
+    model.eval()
+    for layer in model.model:
+        assert layer.training == isinstance(layer, nn.Dropout)
+    model.train()
+    assert all(layer.training for layer in model.model)
+    # training forward = one plain pass of the net (models.py:148-149)
+    x = torch.randn(4, 16)
+    torch.manual_seed(0)
+    a = model(x)
+    torch.manual_seed(0)
+    assert torch.equal(a, model.model(x))
+
+
+def test_delta_uq_builder_doubles_inputs(descr):
+    b = DeltaUQMLPModelBuilder(descr["architecture_mlp"], descr["delta_uq_model"])
+    model = b.build()
+    assert isinstance(model, DeltaUQMLP)
+    assert model.net[0].in_features == 32 and model.num_anchors == 5 and model.batch_size == 64
+    info = b.get_info()
+    assert info.num_inputs() == 32 and info.get_estimator() == "std" and info.get_batch_size() == 64
+    assert b.build().net[0].in_features == 32  # doubled once, not per build()
+    with pytest.raises(KeyError):
+        DeltaUQMLPModelBuilder(descr["architecture_mlp"],
+                               {"estimator": "std", "num_anchors": 5}).build()
+    # training-mode forward stays stock torch and keeps the batch size
+    model.train()
+    assert model(torch.randn(6, 16)).shape == (6, 5)
+    model.anchors = torch.randn(5, 16)
+    assert model.anchors.shape == (5, 16) and "_anchors" in dict(model.named_buffers())
+
+
+def test_out_of_scope_wrappers_say_so(descr):
+    with pytest.raises(NotImplementedError, match="outside the hot path"):
+        KDEModelBuilder(descr["architecture_mlp"], {"bandwidth": "scott"}).build()
+
+
+def test_split_blocks_vocabulary(descr):
+    net = MCDropoutModelBuilder(descr["architecture_mlp4"], descr["mc_dropout_model"]).build().model
+    blocks = extract.split_blocks(net)
+    assert [(b.linear.out_features, b.bn is not None, b.relu, b.dropout) for b in blocks] == [
+        (25, False, True, True), (25, False, True, True), (25, False, True, False),
+        (5, False, False, False)]
+    assert extract.dropout_widths(blocks) == [25, 25]
+    bn_net = build_network([{"Linear": {"args": [5, 8]}}, {"BatchNorm1d": {"args": [8]}},
+                            {"ReLU": None}, {"Linear": {"args": [8, 1]}}])
+    b2 = extract.split_blocks(bn_net)
+    assert b2[0].bn is bn_net[1] and b2[0].relu and not b2[1].relu
+    with pytest.raises(ValueError, match="Conv2d is not supported"):
+        extract.split_blocks(ModelBuilder(descr["architecture_cnn"]).build())
+    with pytest.raises(ValueError, match="BatchNorm1d must directly follow"):
+        extract.split_blocks(nn.Sequential(nn.Linear(4, 4), nn.ReLU(), nn.BatchNorm1d(4)))
+    with pytest.raises(ValueError, match="do not chain"):
+        extract.split_blocks(nn.Sequential(nn.Linear(4, 4), nn.Linear(5, 1)))
+
+
+def test_tensors_version_tracks_inplace_updates():
+    net = nn.Sequential(nn.Linear(3, 3))
+    k0 = extract.tensors_version([net])
+    assert k0 == extract.tensors_version([net])
+    with torch.no_grad():
+        net[0].weight.add_(1.0)
+    assert k0 != extract.tensors_version([net])
+
+
+def test_eval_forward_requires_cuda_and_never_falls_back(descr):
+    model = EnsembleModelBuilder(descr["architecture_mlp"], descr["ensemble_model"]).build()
+    model.eval()
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        model(torch.zeros(2, 16), return_ue=True)
+    mc = MCDropoutModelBuilder(descr["architecture_mlp4"], descr["mc_dropout_model"]).build()
+    mc.eval()
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        mc(torch.zeros(2, 16), return_ue=True)
+    # training-mode forward is the stock autograd path and works on CPU
+    model.train()
+    mean, std = model(torch.zeros(2, 16), return_ue=True)
+    assert mean.shape == (2, 5) and std.shape == (2, 5) and mean.requires_grad
+
+
+def test_wrappers_pickle_without_device_cache(descr):
+    model = EnsembleModelBuilder(descr["architecture_mlp"], descr["ensemble_model"]).build()
+    model.__dict__["_uq_cache"] = ("key", object())  # pretend a packed handle exists
+    clone = pickle.loads(pickle.dumps(model))
+    assert clone.__dict__["_uq_cache"] is None and clone.uq_precision == model.uq_precision
+    assert torch.equal(clone.models[2][0].weight, model.models[2][0].weight)
+    buf = io.BytesIO()
+    torch.save(model, buf)  # the reference checkpoints whole modules (training.py:64-65)
+    buf.seek(0)
+    again = torch.load(buf, weights_only=False)
+    assert isinstance(again, EnsembleModel) and again.__dict__["_uq_cache"] is None
+
+
+def test_evaluator_factories():
+    ev = evaluation.get_uncertainty_evaluator(["wasserstein_distance",
+                                               {"name": "jensen_shannon_distance"}])
+    assert [m.get_name() for m in ev.metrics] == ["wasserstein_distance", "jensen_shannon_distance"]
+    assert ev.get_all_metrics() == ["wasserstein_distance", "jensen_shannon_distance"]
+    assert ev.get_training_objectives()[0] == {"name": "wasserstein_distance", "type": "maximize"}
+    assert isinstance(evaluation.get_evaluator({"name": "wasserstein"}).metrics[0],
+                      evaluation.WassersteinEvaluation)
+    with pytest.raises(ValueError, match="not on the accelerated hot path"):
+        evaluation.get_uncertainty_evaluator("auroc")
+    with pytest.raises(ValueError, match="Invalid metric type"):
+        evaluation.get_uncertainty_evaluator("bogus")
+
+
+def test_uncertainty_estimate_contract():
+    with pytest.raises(ValueError, match="empty"):
+        evaluation.UncertaintyEstimate(torch.zeros(0))
+    with pytest.raises(ValueError, match="same first dimension"):
+        evaluation.UncertaintyEstimate((torch.zeros(3), torch.zeros(4)))
+    with pytest.raises(TypeError):
+        evaluation.UncertaintyEstimate([1, 2, 3])
+    ue = evaluation.UncertaintyEstimate(torch.arange(6.0).reshape(3, 2))
+    assert ue.dimensions == 1 and ue.flatten().shape == (6,) and ue.mean() == 2.5
+    assert ue.data.shape == (3, 2)
+    two = evaluation.UncertaintyEstimate((torch.ones(3), torch.zeros(3)))
+    assert two.dimensions == 2 and two.mean() == 0.5
+    with pytest.raises(ValueError, match="flatten"):
+        two.flatten()
+
+
+# ---- the C-ABI shared library -------------------------------------------------------------------
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    path = nbuild.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "nnueehcs_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(uq_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    raw = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} not exported"
+    assert lib.uq_abi_version() == 1
+    lib.uq_launch_count_reset()
+    assert lib.uq_launch_count() == 0
+
+
+def test_abi_struct_layouts_match_header():
+    # uq_layer_desc: 2 x int32, 6 pointers, float, 2 x int32 -> 72 bytes on LP64
+    assert ctypes.sizeof(_lib.LayerDesc) == 72
+    assert _lib.LayerDesc.weight.offset == 8 and _lib.LayerDesc.bn_eps.offset == 56
+    # uq_forward_args: 8 x int32, double, 2 x uint64, 2 pointers -> 72 bytes
+    assert ctypes.sizeof(_lib.ForwardArgs) == 72
+    assert _lib.ForwardArgs.dropout_p.offset == 32 and _lib.ForwardArgs.masks.offset == 56
+
+
+def test_argument_errors_surface_as_python_exceptions_without_a_gpu():
+    lib = _lib.load()
+    out = ctypes.c_double()
+    # NULL pointers / empty input are rejected before any CUDA call is made
+    rc = lib.uq_wasserstein_1d(None, 0, None, 0, ctypes.byref(out), None, 0, None)
+    assert rc == _lib.UQ_ERR_INVALID
+    with pytest.raises(ValueError, match="can't be empty"):
+        _lib.check(rc)
+    h = ctypes.c_void_p()
+    rc = lib.uq_model_create(ctypes.byref(h), 0, 0, None, None)
+    assert rc == _lib.UQ_ERR_INVALID and not h.value
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.wasserstein_1d(torch.zeros(4), torch.zeros(4))
