@@ -25,6 +25,8 @@
 //
 // Replaces: EnsembleModel.forward (models.py:99-108), MCDropoutModel.forward (:147-163) and the
 // anchored forward behind DeltaUQMLP.forward (:313-341) for MLPs whose hidden widths are equal.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -42,6 +44,7 @@ constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
 constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_CHUNKS = 8;
+constexpr int TRACE_LEN = 2048;
 
 struct TcParams {
   const float* x;        // [n][d_x]
@@ -76,6 +79,9 @@ struct TcParams {
   float* part_mean;                   // [splits][n*d_out] when splits > 1
   float* part_m2;
   unsigned int* error_flag;
+  unsigned long long* prof;          // optional [grid][16] cycle counters (UQ_TC_PROFILE=1)
+  int debug_flags;                   // bring-up only (UQ_TC_DEBUG): 1 skip epilogue math, 2 skip MMA issue
+  unsigned long long* trace;         // bring-up only (UQ_TC_TRACE): [3 roles][TRACE_LEN][2] (tag, clock) of CTA 0
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -109,8 +115,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as a trapped kernel (clean CUDA error), never as a
 // hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* err,
-                                          int tag) {
-  if (mbar_try_wait(bar, parity)) return;
+                                          int tag, long long* waited = nullptr) {
+  if (waited) {  // profiling build of the wait: the first (potentially blocking) probe counts too
+    const long long tp = clock64();
+    const bool done = mbar_try_wait(bar, parity);
+    long long te;
+    asm volatile("{\n\t.reg .b32 t;\n\tmov.b32 t, %1;\n\tmov.u64 %0, %%clock64;\n\t}"
+                 : "=l"(te) : "r"((uint32_t)done) : "memory");
+    *waited += te - tp;
+    if (done) return;
+  } else if (mbar_try_wait(bar, parity)) {
+    return;
+  }
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -119,6 +135,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
       __trap();
     }
   }
+  if (waited) *waited += clock64() - t0;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -249,6 +266,19 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_tiles * p.splits;
+  const bool prof = p.prof != nullptr;
+  const long long t_start = prof ? clock64() : 0;
+  long long wt[4] = {0, 0, 0, 0};  // waited cycles per barrier kind (profiling only)
+  int tr_n = 0;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto trace = [&](int role, unsigned tag) {
+    if (tracing && tr_n < TRACE_LEN) {
+      unsigned long long* t = p.trace + ((size_t)role * TRACE_LEN + tr_n) * 2;
+      t[0] = tag;
+      t[1] = (unsigned long long)clock64();
+      ++tr_n;
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
@@ -281,13 +311,16 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
           for (int s = 0; s < p.stages_per_member; ++s, ++it) {
             const int slot = it % p.n_stages;
             const uint32_t par = (it / p.n_stages) & 1;
-            mbar_wait(&bars->w_empty[slot], par ^ 1, p.error_flag, 1);
+            mbar_wait(&bars->w_empty[slot], par ^ 1, p.error_flag, 1, prof ? &wt[0] : nullptr);
+            trace(0, (1u << 24) | it);
             mbar_arrive_expect_tx(&bars->w_full[slot], p.stage_bytes);
             bulk_g2s(w_smem + (size_t)slot * p.stage_bytes, src + (size_t)s * p.stage_bytes,
                      p.stage_bytes, &bars->w_full[slot]);
+            trace(0, (2u << 24) | it);
           }
         }
       }
+      if (prof) p.prof[blockIdx.x * 16 + 1] = (unsigned long long)wt[0];  // producer: w_empty
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ===========================================
@@ -307,7 +340,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
             // chunks of the previous layer-step's epilogue already waited for in this step
             uint32_t waited = (g == 0) ? 0xffffffffu : 0u;
             const uint32_t prev_par = (g - 1) & 1;
-            if (l == 0) mbar_wait(&bars->x_ready, xm & 1, p.error_flag, 2);
+            if (l == 0) mbar_wait(&bars->x_ready, xm & 1, p.error_flag, 2, prof ? &wt[0] : nullptr);
             for (int nh = 0; nh < p.NH; ++nh) {
               const int kc_count = (l == 0) ? 1 : p.KC;
               for (int kc = 0; kc < kc_count; ++kc, ++it) {
@@ -317,29 +350,40 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 const int upto = (l == 0) ? need_hi : (kc > need_hi ? kc : need_hi);
                 for (int c = 0; c <= upto && c < p.KC; ++c) {
                   if (!(waited & (1u << c))) {
-                    mbar_wait(&bars->chunk_done[c], prev_par, p.error_flag, 3);
+                    mbar_wait(&bars->chunk_done[c], prev_par, p.error_flag, 3,
+                              prof ? &wt[1] : nullptr);
                     waited |= 1u << c;
                   }
                 }
                 const int slot = it % p.n_stages;
                 const uint32_t par = (it / p.n_stages) & 1;
-                mbar_wait(&bars->w_full[slot], par, p.error_flag, 4);
+                trace(1, (1u << 24) | it);
+                mbar_wait(&bars->w_full[slot], par, p.error_flag, 4, prof ? &wt[2] : nullptr);
+                trace(1, (2u << 24) | it);
                 tc_fence_after();
                 const uint32_t a_addr = a_base + (uint32_t)kc * CHUNK_BYTES;
                 const uint32_t b_addr = w_base + (uint32_t)slot * p.stage_bytes;
                 const int ksteps = (l == 0) ? p.K0 / 16 : CHUNK_K / 16;
                 const uint32_t d_addr = tmem_base + (uint32_t)(nh * p.n_tile);
-                for (int ks = 0; ks < ksteps; ++ks) {
+                for (int ks = 0; ks < ksteps && !(p.debug_flags & 2); ++ks) {
                   umma_bf16(d_addr, make_sw128_desc(a_addr + ks * 32),
                             make_sw128_desc(b_addr + ks * 32), idesc,
                             (kc > 0 || ks > 0) ? 1u : 0u);
                 }
-                umma_commit(&bars->w_empty[slot]);  // frees the weight stage when MMAs retire
+                if ((p.debug_flags & 6) == 6) mbar_arrive(&bars->w_empty[slot]);  // bring-up probe
+                else umma_commit(&bars->w_empty[slot]);  // frees the weight stage when MMAs retire
+                trace(1, (3u << 24) | it);
               }
             }
             umma_commit(&bars->d_full);  // whole layer accumulated
           }
         }
+      }
+      if (prof) {
+        p.prof[blockIdx.x * 16 + 2] = (unsigned long long)wt[0];  // MMA: x_ready
+        p.prof[blockIdx.x * 16 + 3] = (unsigned long long)wt[1];  // MMA: chunk_done
+        p.prof[blockIdx.x * 16 + 4] = (unsigned long long)wt[2];  // MMA: w_full
+        p.prof[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_start);
       }
     }
   } else {
@@ -413,8 +457,12 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const bool drop = ((p.dropout_mask >> l) & 1u) && p.drop_mode != 0;
           const float* bias = p.bias[l] + (size_t)wslot * p.H;
 
-          mbar_wait(&bars->d_full, g & 1, p.error_flag, 5);
+          // one lane polls (32 lanes spinning on one mbarrier saturate the barrier unit), the
+          // rest of the warp parks on the warp barrier
+          if (lane == 0) mbar_wait(&bars->d_full, g & 1, p.error_flag, 5, prof ? &wt[0] : nullptr);
+          __syncwarp();
           tc_fence_after();
+          if (warp == 2 && lane == 0) trace(2, (1u << 24) | g);
 
           if (last) {
             // every MMA that reads the A chunks has retired: stage the next member's input row
@@ -427,12 +475,14 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
               nsplit = nunit % p.splits;
               nk = (int)(((int64_t)p.member_count * nsplit) / p.splits);
             }
+            const long long tx0 = prof ? clock64() : 0;
             if (have_next) write_x(ntile, p.member_begin + nk);
+            if (prof) wt[1] += clock64() - tx0;
           }
 
           for (int c = hf; c < p.KC; c += 2) {
 #pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < 2 && !(p.debug_flags & 1); ++b) {
               const int col0 = c * CHUNK_K + b * 32;
               uint32_t acc[32];
               tmem_ld32(lane_addr + (uint32_t)col0, acc);
@@ -504,6 +554,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
             if (!last) fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->chunk_done[c]);
+            if (warp == 2 && lane == 0) trace(2, (2u << 24) | (g << 4) | c);
           }
           // a warp whose parity has no chunk (KC == 1) still owes nothing: barrier counts 4
           if (((p.dropout_mask >> l) & 1u)) {
@@ -517,7 +568,9 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
         if (hf == 1) {
           for (int o = 0; o < p.d_out; ++o) xb[row * p.d_out + o] = dot[o];
         }
+        const long long tb0 = prof ? clock64() : 0;
         epi_bar_sync();
+        if (prof) wt[2] += clock64() - tb0;
         if (hf == 0) {
           wf_n += 1.f;
           const float inv_n = 1.f / wf_n;
@@ -548,6 +601,13 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
     }
   }
 
+  if (prof && warp >= 2 && lane == 0 && (warp == 2 || warp == 6)) {
+    const int o = warp == 2 ? 5 : 9;
+    p.prof[blockIdx.x * 16 + o + 0] = (unsigned long long)wt[0];  // epilogue: d_full wait
+    p.prof[blockIdx.x * 16 + o + 1] = (unsigned long long)wt[1];  // epilogue: write_x
+    p.prof[blockIdx.x * 16 + o + 2] = (unsigned long long)wt[2];  // epilogue: pair barrier
+    p.prof[blockIdx.x * 16 + o + 3] = (unsigned long long)(clock64() - t_start);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -714,7 +774,7 @@ static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a)
 
 size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a) {
   const int splits = choose_splits(m, n, a);
-  size_t b = 256;  // error flag
+  size_t b = 256 + 148 * 4 * 16 * sizeof(unsigned long long);  // error flag + profile counters
   if (splits > 1) b += 2 * (size_t)splits * (size_t)n * m->d_out * sizeof(float) + 512;
   return b;
 }
@@ -774,12 +834,25 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.output = a->output;
   char* wsb = static_cast<char*>(ws);
   p.error_flag = reinterpret_cast<unsigned int*>(wsb);
+  const size_t prof_bytes = 148 * 4 * 16 * sizeof(unsigned long long);
+  const char* dbg_env = getenv("UQ_TC_DEBUG");
+  p.debug_flags = dbg_env ? atoi(dbg_env) : 0;
+  const char* prof_env = getenv("UQ_TC_PROFILE");
+  const bool want_prof = prof_env && prof_env[0] == '1';
+  p.prof = want_prof ? reinterpret_cast<unsigned long long*>(wsb + 256) : nullptr;
   if (p.splits > 1) {
     const size_t part = (((size_t)p.splits * (size_t)n * m->d_out * sizeof(float)) + 255) & ~(size_t)255;
-    p.part_mean = reinterpret_cast<float*>(wsb + 256);
-    p.part_m2 = reinterpret_cast<float*>(wsb + 256 + part);
+    p.part_mean = reinterpret_cast<float*>(wsb + 256 + prof_bytes);
+    p.part_m2 = reinterpret_cast<float*>(wsb + 256 + prof_bytes + part);
   }
   UQ_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(unsigned int), st));
+  const char* trace_env = getenv("UQ_TC_TRACE");
+  unsigned long long* d_trace = nullptr;
+  if (trace_env && trace_env[0]) {
+    UQ_CUDA(cudaMalloc(&d_trace, 3 * TRACE_LEN * 2 * sizeof(unsigned long long)));
+    UQ_CUDA(cudaMemsetAsync(d_trace, 0, 3 * TRACE_LEN * 2 * sizeof(unsigned long long), st));
+  }
+  p.trace = d_trace;
 
   const size_t smem = tc_smem_bytes(t, p.n_stages);
   UQ_REQUIRE(smem <= 232448, UQ_ERR_UNSUPPORTED, "bf16 kernel needs %zu bytes of shared memory",
@@ -798,6 +871,37 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   int grid = (int)(units < (int64_t)sms * per_sm ? units : (int64_t)sms * per_sm);
   uq_mlp_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(p);
   UQ_LAUNCH_CHECK();
+  if (d_trace) {  // bring-up aid: dump CTA 0's event timeline as CSV (role, tag, clock)
+    std::vector<unsigned long long> h(3 * TRACE_LEN * 2);
+    UQ_CUDA(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+    UQ_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_trace);
+    FILE* f = fopen(trace_env, "w");
+    if (f) {
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < TRACE_LEN; ++i) {
+          const unsigned long long tag = h[((size_t)r * TRACE_LEN + i) * 2];
+          if (tag) fprintf(f, "%d,%llu,%llu,%llu\n", r, tag >> 24, tag & 0xFFFFFF,
+                           h[((size_t)r * TRACE_LEN + i) * 2 + 1]);
+        }
+      fclose(f);
+    }
+  }
+  if (want_prof) {  // debugging aid: synchronises and prints the per-role wait breakdown
+    std::vector<unsigned long long> h((size_t)grid * 16);
+    UQ_CUDA(cudaMemcpyAsync(h.data(), p.prof, h.size() * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+    UQ_CUDA(cudaStreamSynchronize(st));
+    double a[16] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)b * 16 + i] / grid;
+    fprintf(stderr,
+            "[uq_tc_profile] grid %d cycles/CTA: total %.0f | producer wait w_empty %.0f | MMA wait "
+            "x_ready %.0f chunk_done %.0f w_full %.0f | epi(w2) wait d_full %.0f write_x %.0f pairbar "
+            "%.0f total %.0f | epi(w6) wait d_full %.0f pairbar %.0f\n",
+            grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[11]);
+  }
   if (p.splits > 1) {
     double counts[64];
     for (int s = 0; s < p.splits; ++s) {

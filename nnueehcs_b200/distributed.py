@@ -46,9 +46,9 @@ class KShard:
         """The one collective: all-gather every rank's (mean, M2) slab -> two ``[world, ...]``
         tensors ordered by rank."""
         slab = torch.stack([mean, m2]).contiguous()
-        gathered = torch.empty((self.world,) + tuple(slab.shape), dtype=slab.dtype,
-                               device=slab.device)
-        dist.all_gather_into_tensor(gathered, slab, group=self.group)
+        flat = torch.empty(self.world * slab.numel(), dtype=slab.dtype, device=slab.device)
+        dist.all_gather_into_tensor(flat, slab.reshape(-1), group=self.group)
+        gathered = flat.view((self.world,) + tuple(slab.shape))
         return gathered[:, 0], gathered[:, 1]
 
     def forward_owned(self, packed: "ops.PackedModel", x: torch.Tensor, mode: str, *,
