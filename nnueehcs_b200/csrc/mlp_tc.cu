@@ -10,14 +10,19 @@
 //                          A = activations [128 x 64]-chunks in smem, B = weight stage,
 //                          D = [128 x H] fp32 accumulator in TMEM; tcgen05.commit releases
 //                          stages and publishes finished layers;
-//   warps 2..9  epilogue   tcgen05.ld the accumulator, add the (BN-folded) bias, ReLU, apply the
-//                          Philox / injected dropout mask, round to bf16 and write the next
-//                          layer's A operand back into the same smem chunks (in place), chunk by
-//                          chunk so the next layer's MMAs start while the tail is still draining.
-//                          The last Linear (H -> d_out, d_out <= 8) is a CUDA-core dot product
-//                          in the same pass, feeding a per-row Welford (count, mean, M2) across
-//                          members that lives in registers -- the [K, N, out] stack of
-//                          nnueehcs/models.py:103,159 never exists.
+//   warps 2..9  epilogue   tcgen05.ld the accumulator (double-buffered in registers), add the
+//                          (BN-folded) bias, ReLU, apply the Philox / injected dropout mask, round
+//                          to bf16 and write the next layer's A operand back into the same smem
+//                          chunks (in place), chunk by chunk so the next layer's MMAs start while
+//                          the tail is still draining.  The last Linear (H -> d_out <= 8) is a
+//                          CUDA-core dot product in the same pass, feeding a per-row Welford
+//                          (count, mean, M2) across members that lives in registers -- the
+//                          [K, N, out] stack of nnueehcs/models.py:103,159 never exists.
+//
+// Everything shape-dependent is a template parameter (hidden width H, padded output count): the
+// single-thread producer / MMA-issue loops must retire a 32 KB weight stage (4 MMAs = 512 tensor
+// cycles) in well under 512 issue cycles, which a runtime-generic loop cannot do -- the first
+// version of this kernel spent ~2000 cycles per stage on loop overhead alone (profiles/).
 //
 // Layer 0 (d_in <= 21 inputs) is also an MMA: x is split into bf16 hi + lo parts and the folded
 // first-layer weights likewise, laid out as [x_hi | x_lo | x_hi] . [w_hi | w_hi | w_lo] inside
@@ -26,6 +31,7 @@
 // Replaces: EnsembleModel.forward (models.py:99-108), MCDropoutModel.forward (:147-163) and the
 // anchored forward behind DeltaUQMLP.forward (:313-341) for MLPs whose hidden widths are equal.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -42,9 +48,31 @@ constexpr int MAX_DOUT = 8;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
 constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
-constexpr int MAX_STAGES = 8;
-constexpr int MAX_CHUNKS = 8;
-constexpr int TRACE_LEN = 2048;
+constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
+
+// compile-time geometry of one hidden width
+template <int H, int DOUT>
+struct Geo {
+  static_assert(H % 64 == 0 && H >= 64 && H <= 512, "hidden width must be a multiple of 64 <= 512");
+  static constexpr int KC = H / CHUNK_K;                 // activation chunks == K-chunks per layer
+  static constexpr int NH = (H + 255) / 256;             // accumulator halves (MMA N <= 256)
+  static constexpr int NT = H / NH;                      // MMA N
+  static_assert(NT % 16 == 0, "MMA N must be a multiple of 16");
+  static constexpr int TMEM_COLS = H <= 64 ? 64 : H <= 128 ? 128 : H <= 256 ? 256 : 512;
+  static constexpr int STAGE_BYTES = NT * 128;           // [NT x 64] bf16
+  static constexpr int A_BYTES = KC * CHUNK_BYTES;
+  static constexpr int XCHG_BYTES = 2 * TILE_M * DOUT * 4;
+  static constexpr int MISC_BYTES = 1024 /*align slack*/ + 256 /*barriers*/ + XCHG_BYTES;
+  // narrow nets leave room for two CTAs per SM (one CTA's epilogue overlaps the other's MMAs)
+  static constexpr int BUDGET =
+      (H <= 128 ? SMEM_LIMIT / 2 - 1024 : SMEM_LIMIT) - A_BYTES - MISC_BYTES;
+  static constexpr int NS_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int NSTAGES = NS_RAW > 8 ? 8 : NS_RAW;
+  static_assert(NSTAGES >= 2, "not enough shared memory for a weight ring");
+  static constexpr int SMEM_BYTES = A_BYTES + NSTAGES * STAGE_BYTES + MISC_BYTES;
+  // last chunk overlapping accumulator half nh
+  __host__ __device__ static constexpr int hi(int nh) { return ((nh + 1) * NT + CHUNK_K - 1) / CHUNK_K - 1; }
+};
 
 struct TcParams {
   const float* x;        // [n][d_x]
@@ -55,17 +83,14 @@ struct TcParams {
   int n_tiles;
   int splits;            // member-axis splits (partial moments when > 1)
   int member_begin, member_count, total_members;
-  int H, n_tile, NH, KC, K0, split_s, L_mma, d_out;
-  int n_stages;          // smem ring depth
-  uint32_t stage_bytes;
+  int K0, split_s, L_mma, d_out;
   int stages_per_member;
   int shared_weights;
-  int tmem_cols;
-  const __nv_bfloat16* image;
+  const uint8_t* image;
   const float* bias[MAX_MMA_LAYERS];  // [K or 1][H] folded bias per MMA layer
   uint32_t relu_mask, dropout_mask;   // bit l: MMA layer l has ReLU / dropout on its output
-  const float* w_last;                // [K or 1][d_out][H]
-  const float* b_last;                // [K or 1][d_out]
+  const float* w_last;                // [K or 1][DOUT][H]  (zero rows beyond d_out)
+  const float* b_last;                // [K or 1][DOUT]
   int last_relu;
   int drop_mode;                      // 0 none, 1 injected, 2 philox
   float drop_scale;
@@ -79,9 +104,6 @@ struct TcParams {
   float* part_mean;                   // [splits][n*d_out] when splits > 1
   float* part_m2;
   unsigned int* error_flag;
-  unsigned long long* prof;          // optional [grid][16] cycle counters (UQ_TC_PROFILE=1)
-  int debug_flags;                   // bring-up only (UQ_TC_DEBUG): 1 skip epilogue math, 2 skip MMA issue
-  unsigned long long* trace;         // bring-up only (UQ_TC_TRACE): [3 roles][TRACE_LEN][2] (tag, clock) of CTA 0
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -90,52 +112,44 @@ struct TcParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (clean CUDA error), never as a
-// hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* err,
-                                          int tag, long long* waited = nullptr) {
-  if (waited) {  // profiling build of the wait: the first (potentially blocking) probe counts too
-    const long long tp = clock64();
-    const bool done = mbar_try_wait(bar, parity);
-    long long te;
-    asm volatile("{\n\t.reg .b32 t;\n\tmov.b32 t, %1;\n\tmov.u64 %0, %%clock64;\n\t}"
-                 : "=l"(te) : "r"((uint32_t)done) : "memory");
-    *waited += te - tp;
-    if (done) return;
-  } else if (mbar_try_wait(bar, parity)) {
-    return;
-  }
-  const long long t0 = clock64();
+// hung GPU.  Each failed probe suspends in hardware for a few hundred cycles, so 2^24 probes are
+// several seconds.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned int* err,
+                                            int tag) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (++spins > (1u << 24)) {
       if (err) atomicExch(err, 0x80000000u | (unsigned)tag);
       __threadfence_system();
       __trap();
     }
   }
-  if (waited) *waited += clock64() - t0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err,
+                                          int tag) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, tag);
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -149,15 +163,15 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   smem_u32(dst_smem)),
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
                "r"(cols)
                : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -176,10 +190,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
   asm volatile(
@@ -204,6 +218,7 @@ __device__ __forceinline__ void epi_bar_sync() {
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
 // start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30),
 // SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version = 1 in [46,48), layout 2 in [61,64).
+// Advancing by `bytes` inside the operand = adding bytes >> 4 to the 64-bit value.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -214,7 +229,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=F32, A=B=BF16, K-major.
-__host__ __device__ inline uint32_t make_idesc_bf16(int M, int N) {
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
@@ -229,18 +244,17 @@ __host__ __device__ inline uint32_t sw128_offset(int row, int piece) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((piece ^ (row & 7)) << 4));
 }
 
-struct __align__(8) Barriers {
-  uint64_t w_full[MAX_STAGES];
-  uint64_t w_empty[MAX_STAGES];
-  uint64_t chunk_done[MAX_CHUNKS];
-  uint64_t d_full;
-  uint64_t x_ready;
-  uint32_t tmem_base;
-  uint32_t pad;
-};
+// barrier block (byte offsets inside the 256-byte barrier area)
+constexpr uint32_t BAR_W_FULL = 0;       // 8 x 8 B
+constexpr uint32_t BAR_W_EMPTY = 64;     // 8 x 8 B
+constexpr uint32_t BAR_CHUNK = 128;      // 8 x 8 B
+constexpr uint32_t BAR_D_FULL = 192;
+constexpr uint32_t BAR_X_READY = 200;
+constexpr uint32_t BAR_TMEM_PTR = 208;
 
 // input feature i of the network for (sample row, member) -- x, or cat(x - a_k, a_k) for Delta-UQ
-__device__ __forceinline__ float net_input(const TcParams& p, int64_t row, int member_global, int i) {
+__device__ __forceinline__ float net_input(const TcParams& p, int64_t row, int member_global,
+                                           int i) {
   if (row >= p.n) return 0.f;
   if (p.mode == UQ_MODE_DELTA_UQ) {
     const int d = p.d_x;
@@ -250,85 +264,168 @@ __device__ __forceinline__ float net_input(const TcParams& p, int64_t row, int m
   return __ldg(p.x + row * p.d_x + i);
 }
 
+// ---- epilogue math on one 32-column block of one row ---------------------------------------------
+// acc: raw accumulator bits; on return v[] holds bias + ReLU + dropout applied, fp32.
+template <bool RELU, bool DROP>
+__device__ __forceinline__ void epi_activate(const uint32_t (&acc)[32], float (&v)[32],
+                                             const float* __restrict__ bias32, uint32_t keep,
+                                             float keep_scale) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias32) + j4);
+    v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + bv.x;
+    v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + bv.y;
+    v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + bv.z;
+    v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + bv.w;
+  }
+  if (RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (DROP) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
+  }
+}
+
+// keep-mask bits of 32 consecutive features of one row
+__device__ __forceinline__ uint32_t epi_keep_bits(const TcParams& p, int drop, int kg, int drop_ord,
+                                                  int64_t grow, int col0,
+                                                  const uint8_t* mask_layer, int H) {
+  uint32_t keep = 0;
+  if (drop == 2) {
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq)
+      keep |= dropout_keep8(p.key, p.thr16, (uint32_t)kg, (uint32_t)drop_ord, (uint32_t)grow,
+                            (uint32_t)(col0 / 8 + gq))
+              << (8 * gq);
+  } else if (grow < p.n) {
+    const uint4* mrow = reinterpret_cast<const uint4*>(
+        mask_layer + ((size_t)kg * (size_t)p.n + (size_t)grow) * H + col0);
+    const uint4 m0 = __ldg(mrow), m1 = __ldg(mrow + 1);
+    const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      keep |= ((w[j] & 0xFFu) ? 1u : 0u) << (4 * j);
+      keep |= ((w[j] & 0xFF00u) ? 1u : 0u) << (4 * j + 1);
+      keep |= ((w[j] & 0xFF0000u) ? 1u : 0u) << (4 * j + 2);
+      keep |= ((w[j] & 0xFF000000u) ? 1u : 0u) << (4 * j + 3);
+    }
+  }
+  return keep;
+}
+
+// one 32-column block: activation, then either the bf16 A-operand write-back or the last-Linear dot
+template <int H, int DOUT>
+__device__ __forceinline__ void epi_block(const TcParams& p, const uint32_t (&acc)[32],
+                                          const float* __restrict__ bias32, bool relu, int drop,
+                                          uint32_t keep, bool last, uint8_t* a_dst, int piece0,
+                                          int rx, const float* __restrict__ wl32,
+                                          float (&dot)[DOUT]) {
+  float v[32];
+  if (relu) {
+    if (drop) epi_activate<true, true>(acc, v, bias32, keep, p.drop_scale);
+    else epi_activate<true, false>(acc, v, bias32, keep, p.drop_scale);
+  } else {
+    if (drop) epi_activate<false, true>(acc, v, bias32, keep, p.drop_scale);
+    else epi_activate<false, false>(acc, v, bias32, keep, p.drop_scale);
+  }
+  if (!last) {
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc)
+      *reinterpret_cast<uint4*>(a_dst + (((piece0 + pc) ^ rx) << 4)) =
+          make_uint4(pack_bf16x2(v[pc * 8 + 0], v[pc * 8 + 1]),
+                     pack_bf16x2(v[pc * 8 + 2], v[pc * 8 + 3]),
+                     pack_bf16x2(v[pc * 8 + 4], v[pc * 8 + 5]),
+                     pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]));
+  } else {
+#pragma unroll
+    for (int o = 0; o < DOUT; ++o) {
+      float s = dot[o];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wl32 + o * H) + j4);
+        s = fmaf(v[j4 * 4 + 0], wv.x, s);
+        s = fmaf(v[j4 * 4 + 1], wv.y, s);
+        s = fmaf(v[j4 * 4 + 2], wv.z, s);
+        s = fmaf(v[j4 * 4 + 3], wv.w, s);
+      }
+      dot[o] = s;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
+template <int H, int DOUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
+  using G = Geo<H, DOUT>;
+  constexpr int KC = G::KC, NH = G::NH, NT = G::NT, NS = G::NSTAGES;
+  constexpr uint32_t STAGE_BYTES = G::STAGE_BYTES;
+
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_smem = smem;                                    // KC chunks of 16 KB
-  uint8_t* w_smem = smem + (size_t)p.KC * CHUNK_BYTES;       // n_stages x stage_bytes
-  Barriers* bars = reinterpret_cast<Barriers*>(w_smem + (size_t)p.n_stages * p.stage_bytes);
-  float* xchg = reinterpret_cast<float*>(bars + 1);          // [2][128][d_out] dot exchange
+  uint8_t* a_smem = smem;                                  // KC chunks of 16 KB
+  uint8_t* w_smem = smem + G::A_BYTES;                     // NS stages
+  uint8_t* bar_smem = w_smem + NS * STAGE_BYTES;           // 256 B of mbarriers + tmem pointer
+  float* xchg = reinterpret_cast<float*>(bar_smem + 256);  // [2][128][DOUT] dot exchange
+  const uint32_t a_base = smem_u32(a_smem);
+  const uint32_t w_base = smem_u32(w_smem);
+  const uint32_t bars = smem_u32(bar_smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_tiles * p.splits;
-  const bool prof = p.prof != nullptr;
-  const long long t_start = prof ? clock64() : 0;
-  long long wt[4] = {0, 0, 0, 0};  // waited cycles per barrier kind (profiling only)
-  int tr_n = 0;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
-  auto trace = [&](int role, unsigned tag) {
-    if (tracing && tr_n < TRACE_LEN) {
-      unsigned long long* t = p.trace + ((size_t)role * TRACE_LEN + tr_n) * 2;
-      t[0] = tag;
-      t[1] = (unsigned long long)clock64();
-      ++tr_n;
-    }
-  };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(&bars->w_full[s], 1);
-      mbar_init(&bars->w_empty[s], 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bars + BAR_W_FULL + 8 * s, 1);
+      mbar_init(bars + BAR_W_EMPTY + 8 * s, 1);
     }
-    for (int c = 0; c < MAX_CHUNKS; ++c) mbar_init(&bars->chunk_done[c], 4);
-    mbar_init(&bars->d_full, 1);
-    mbar_init(&bars->x_ready, 4);
+    for (int c = 0; c < KC; ++c) mbar_init(bars + BAR_CHUNK + 8 * c, 4);
+    mbar_init(bars + BAR_D_FULL, 1);
+    mbar_init(bars + BAR_X_READY, 4);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 1) tmem_alloc(bars + BAR_TMEM_PTR, (uint32_t)G::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(bar_smem + BAR_TMEM_PTR);
 
   if (warp == 0) {
     // ===================================== producer =============================================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t slot = 0, phase = 0;
+      const size_t member_bytes = (size_t)p.stages_per_member * STAGE_BYTES;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int split = unit % p.splits;
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
         for (int k = mb; k < me; ++k) {
-          const int wslot = p.shared_weights ? 0 : (p.member_begin + k);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.image) +
-                               (size_t)wslot * p.stages_per_member * p.stage_bytes;
-          for (int s = 0; s < p.stages_per_member; ++s, ++it) {
-            const int slot = it % p.n_stages;
-            const uint32_t par = (it / p.n_stages) & 1;
-            mbar_wait(&bars->w_empty[slot], par ^ 1, p.error_flag, 1, prof ? &wt[0] : nullptr);
-            trace(0, (1u << 24) | it);
-            mbar_arrive_expect_tx(&bars->w_full[slot], p.stage_bytes);
-            bulk_g2s(w_smem + (size_t)slot * p.stage_bytes, src + (size_t)s * p.stage_bytes,
-                     p.stage_bytes, &bars->w_full[slot]);
-            trace(0, (2u << 24) | it);
+          const uint8_t* src =
+              p.image + (p.shared_weights ? 0 : (size_t)(p.member_begin + k) * member_bytes);
+          for (int s = 0; s < p.stages_per_member; ++s) {
+            mbar_wait(bars + BAR_W_EMPTY + 8 * slot, phase ^ 1, p.error_flag, 1);
+            mbar_arrive_expect_tx(bars + BAR_W_FULL + 8 * slot, STAGE_BYTES);
+            bulk_g2s(w_base + slot * STAGE_BYTES, src, STAGE_BYTES, bars + BAR_W_FULL + 8 * slot);
+            src += STAGE_BYTES;
+            if (++slot == NS) { slot = 0; phase ^= 1; }
           }
         }
       }
-      if (prof) p.prof[blockIdx.x * 16 + 1] = (unsigned long long)wt[0];  // producer: w_empty
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ===========================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(TILE_M, p.n_tile);
-      const uint32_t a_base = smem_u32(a_smem);
-      const uint32_t w_base = smem_u32(w_smem);
-      uint32_t it = 0;     // weight stage counter
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, NT);
+      const uint64_t a_desc0 = make_sw128_desc(a_base);
+      const uint64_t b_desc0 = make_sw128_desc(w_base);
+      const int k0_steps = p.K0 / 16;
+      uint32_t slot = 0, phase = 0;
       uint32_t g = 0;      // layer-step counter (d_full / chunk_done phases)
       uint32_t xm = 0;     // member counter (x_ready phase)
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -336,54 +433,63 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
         for (int k = mb; k < me; ++k, ++xm) {
-          for (int l = 0; l < p.L_mma; ++l, ++g) {
-            // chunks of the previous layer-step's epilogue already waited for in this step
-            uint32_t waited = (g == 0) ? 0xffffffffu : 0u;
+          // ---- layer 0: A = split input row in chunk 0, K0 <= 64 ------------------------------
+          {
             const uint32_t prev_par = (g - 1) & 1;
-            if (l == 0) mbar_wait(&bars->x_ready, xm & 1, p.error_flag, 2, prof ? &wt[0] : nullptr);
-            for (int nh = 0; nh < p.NH; ++nh) {
-              const int kc_count = (l == 0) ? 1 : p.KC;
-              for (int kc = 0; kc < kc_count; ++kc, ++it) {
-                // the accumulator columns of this N-half must have been drained, and (for
-                // l >= 1) the A chunk kc must have been written, by the previous epilogue
-                const int need_hi = ((nh + 1) * p.n_tile + CHUNK_K - 1) / CHUNK_K - 1;
-                const int upto = (l == 0) ? need_hi : (kc > need_hi ? kc : need_hi);
-                for (int c = 0; c <= upto && c < p.KC; ++c) {
-                  if (!(waited & (1u << c))) {
-                    mbar_wait(&bars->chunk_done[c], prev_par, p.error_flag, 3,
-                              prof ? &wt[1] : nullptr);
-                    waited |= 1u << c;
-                  }
-                }
-                const int slot = it % p.n_stages;
-                const uint32_t par = (it / p.n_stages) & 1;
-                trace(1, (1u << 24) | it);
-                mbar_wait(&bars->w_full[slot], par, p.error_flag, 4, prof ? &wt[2] : nullptr);
-                trace(1, (2u << 24) | it);
+            mbar_wait(bars + BAR_X_READY, xm & 1, p.error_flag, 2);
+            int waited = 0;
+#pragma unroll
+            for (int nh = 0; nh < NH; ++nh) {
+              if (g != 0) {  // accumulator half nh must have been drained by the previous epilogue
+#pragma unroll
+                for (int c = 0; c < KC; ++c)
+                  if (c >= waited && c <= G::hi(nh))
+                    mbar_wait(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
+              }
+              waited = G::hi(nh) + 1;
+              mbar_wait(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 4);
+              tc_fence_after();
+              const uint64_t bd = b_desc0 + (uint64_t)((slot * STAGE_BYTES) >> 4);
+              for (int ks = 0; ks < k0_steps; ++ks)
+                umma_bf16(tmem_base + nh * NT, a_desc0 + 2 * ks, bd + 2 * ks, idesc,
+                          ks > 0 ? 1u : 0u);
+              umma_commit(bars + BAR_W_EMPTY + 8 * slot);
+              if (++slot == NS) { slot = 0; phase ^= 1; }
+            }
+            umma_commit(bars + BAR_D_FULL);
+            ++g;
+          }
+          // ---- hidden layers: A = previous activations (in-place chunks), K = H ----------------
+          for (int l = 1; l < p.L_mma; ++l) {
+            const uint32_t prev_par = (g - 1) & 1;
+            int waited = 0;
+#pragma unroll
+            for (int nh = 0; nh < NH; ++nh) {
+#pragma unroll
+              for (int kc = 0; kc < KC; ++kc) {
+                // accumulator half nh drained + A chunk kc written by the previous epilogue
+                const int need = (G::hi(nh) > kc ? G::hi(nh) : kc) + 1;
+#pragma unroll
+                for (int c = 0; c < KC; ++c)
+                  if (c >= waited && c < need)
+                    mbar_wait(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
+                if (need > waited) waited = need;
+                mbar_wait(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 4);
                 tc_fence_after();
-                const uint32_t a_addr = a_base + (uint32_t)kc * CHUNK_BYTES;
-                const uint32_t b_addr = w_base + (uint32_t)slot * p.stage_bytes;
-                const int ksteps = (l == 0) ? p.K0 / 16 : CHUNK_K / 16;
-                const uint32_t d_addr = tmem_base + (uint32_t)(nh * p.n_tile);
-                for (int ks = 0; ks < ksteps && !(p.debug_flags & 2); ++ks) {
-                  umma_bf16(d_addr, make_sw128_desc(a_addr + ks * 32),
-                            make_sw128_desc(b_addr + ks * 32), idesc,
+                const uint64_t ad = a_desc0 + (uint64_t)((kc * CHUNK_BYTES) >> 4);
+                const uint64_t bd = b_desc0 + (uint64_t)((slot * STAGE_BYTES) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < CHUNK_K / 16; ++ks)
+                  umma_bf16(tmem_base + nh * NT, ad + 2 * ks, bd + 2 * ks, idesc,
                             (kc > 0 || ks > 0) ? 1u : 0u);
-                }
-                if ((p.debug_flags & 6) == 6) mbar_arrive(&bars->w_empty[slot]);  // bring-up probe
-                else umma_commit(&bars->w_empty[slot]);  // frees the weight stage when MMAs retire
-                trace(1, (3u << 24) | it);
+                umma_commit(bars + BAR_W_EMPTY + 8 * slot);  // frees the stage when MMAs retire
+                if (++slot == NS) { slot = 0; phase ^= 1; }
               }
             }
-            umma_commit(&bars->d_full);  // whole layer accumulated
+            umma_commit(bars + BAR_D_FULL);  // whole layer accumulated
+            ++g;
           }
         }
-      }
-      if (prof) {
-        p.prof[blockIdx.x * 16 + 2] = (unsigned long long)wt[0];  // MMA: x_ready
-        p.prof[blockIdx.x * 16 + 3] = (unsigned long long)wt[1];  // MMA: chunk_done
-        p.prof[blockIdx.x * 16 + 4] = (unsigned long long)wt[2];  // MMA: w_full
-        p.prof[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_start);
       }
     }
   } else {
@@ -395,13 +501,15 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t g = 0;                      // layer-step counter
     uint32_t mcount = 0;                 // members processed (exchange buffer parity)
-    const float keep_scale = p.drop_scale;
+    uint8_t* a_row = a_smem + (row >> 3) * 1024 + (row & 7) * 128;  // this row inside chunk 0
+    const int rx = row & 7;
 
     // writes the layer-0 A operand (split input row) into chunk 0, pieces [0, K0/8)
     auto write_x = [&](int tile, int member_global) {
       if (hf == 0) {
         const int64_t grow = (int64_t)tile * TILE_M + row;
         const int d = p.d_in;
+        int seg = 0, i = 0;
         for (int piece = 0; piece < p.K0 / 8; ++piece) {
           uint32_t w4[4];
 #pragma unroll
@@ -409,8 +517,6 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
             float v[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int col = piece * 8 + h2 * 2 + e;
-              const int seg = col / d, i = col - seg * d;
               float out = 0.f;
               if (seg < p.split_s) {
                 const float f = net_input(p, grow, member_global, i);
@@ -418,15 +524,16 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
                 out = (seg == 1) ? (f - hi) : hi;   // [hi | lo | hi]
               }
               v[e] = out;
+              if (++i == d) { i = 0; ++seg; }
             }
             w4[h2] = pack_bf16x2(v[0], v[1]);
           }
-          *reinterpret_cast<uint4*>(a_smem + sw128_offset(row, piece)) =
+          *reinterpret_cast<uint4*>(a_row + ((piece ^ rx) << 4)) =
               make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->x_ready);
+        if (lane == 0) mbar_arrive(bars + BAR_X_READY);
       }
     };
 
@@ -436,147 +543,95 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
       const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
       const int64_t grow = (int64_t)tile * TILE_M + row;
 
-      float wf_n = 0.f, wf_mean[MAX_DOUT], wf_m2[MAX_DOUT];
+      float wf_n = 0.f, wf_mean[DOUT], wf_m2[DOUT];
 #pragma unroll
-      for (int o = 0; o < MAX_DOUT; ++o) wf_mean[o] = 0.f, wf_m2[o] = 0.f;
+      for (int o = 0; o < DOUT; ++o) wf_mean[o] = 0.f, wf_m2[o] = 0.f;
 
       if (unit == (int)blockIdx.x) write_x(tile, p.member_begin + mb);  // very first member
 
       for (int k = mb; k < me; ++k, ++mcount) {
         const int kg = p.member_begin + k;                 // global member / pass id
         const int wslot = p.shared_weights ? 0 : kg;
-        float dot[MAX_DOUT];
+        float dot[DOUT];
 #pragma unroll
-        for (int o = 0; o < MAX_DOUT; ++o) dot[o] = 0.f;
+        for (int o = 0; o < DOUT; ++o) dot[o] = 0.f;
         int drop_ord = 0;
         const uint8_t* mask_layer = p.masks;
 
         for (int l = 0; l < p.L_mma; ++l, ++g) {
           const bool last = (l == p.L_mma - 1);
           const bool relu = (p.relu_mask >> l) & 1u;
-          const bool drop = ((p.dropout_mask >> l) & 1u) && p.drop_mode != 0;
-          const float* bias = p.bias[l] + (size_t)wslot * p.H;
+          const bool has_drop = (p.dropout_mask >> l) & 1u;
+          const int drop = has_drop ? p.drop_mode : 0;
+          const float* bias = p.bias[l] + (size_t)wslot * H;
+          const float* wl = p.w_last + (size_t)wslot * DOUT * H;
 
-          // one lane polls (32 lanes spinning on one mbarrier saturate the barrier unit), the
-          // rest of the warp parks on the warp barrier
-          if (lane == 0) mbar_wait(&bars->d_full, g & 1, p.error_flag, 5, prof ? &wt[0] : nullptr);
+          // one lane polls the layer barrier, the rest of the warp parks on the warp barrier
+          if (lane == 0) mbar_wait(bars + BAR_D_FULL, g & 1, p.error_flag, 5);
           __syncwarp();
           tc_fence_after();
-          if (warp == 2 && lane == 0) trace(2, (1u << 24) | g);
 
           if (last) {
             // every MMA that reads the A chunks has retired: stage the next member's input row
-            int nk = k + 1, ntile = tile, nsplit = split;
+            int nk = k + 1, ntile = tile;
             bool have_next = true;
             if (nk >= me) {
               const int nunit = unit + gridDim.x;
               have_next = nunit < n_units;
               ntile = nunit / p.splits;
-              nsplit = nunit % p.splits;
-              nk = (int)(((int64_t)p.member_count * nsplit) / p.splits);
+              nk = (int)(((int64_t)p.member_count * (nunit % p.splits)) / p.splits);
             }
-            const long long tx0 = prof ? clock64() : 0;
             if (have_next) write_x(ntile, p.member_begin + nk);
-            if (prof) wt[1] += clock64() - tx0;
           }
 
-          for (int c = hf; c < p.KC; c += 2) {
+          // --- drain this warp's chunks; TMEM loads run one 32-column block ahead ---------------
+          uint32_t acc0[32], acc1[32];
+          if (hf < KC) tmem_ld32(lane_addr + (uint32_t)(hf * CHUNK_K), acc0);
 #pragma unroll 1
-            for (int b = 0; b < 2 && !(p.debug_flags & 1); ++b) {
-              const int col0 = c * CHUNK_K + b * 32;
-              uint32_t acc[32];
-              tmem_ld32(lane_addr + (uint32_t)col0, acc);
-              tmem_ld_wait();
-              uint32_t keep = 0xffffffffu;
-              if (drop) {
-                if (p.drop_mode == 2) {
-                  keep = 0;
-#pragma unroll
-                  for (int gq = 0; gq < 4; ++gq)
-                    keep |= dropout_keep8(p.key, p.thr16, (uint32_t)kg, (uint32_t)drop_ord,
-                                          (uint32_t)grow, (uint32_t)(col0 / 8 + gq))
-                            << (8 * gq);
-                } else {
-                  keep = 0;
-                  if (grow < p.n) {
-                    const uint8_t* mrow =
-                        mask_layer + ((size_t)kg * (size_t)p.n + (size_t)grow) * p.H + col0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) keep |= (mrow[j] ? 1u : 0u) << j;
-                  }
-                }
-              }
-              float v[32];
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
-                v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + bv.x;
-                v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + bv.y;
-                v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + bv.z;
-                v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + bv.w;
-              }
-              if (relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-              if (drop) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
-              }
-              if (!last) {
-#pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
-                  const uint4 pk = make_uint4(pack_bf16x2(v[pc * 8 + 0], v[pc * 8 + 1]),
-                                              pack_bf16x2(v[pc * 8 + 2], v[pc * 8 + 3]),
-                                              pack_bf16x2(v[pc * 8 + 4], v[pc * 8 + 5]),
-                                              pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]));
-                  *reinterpret_cast<uint4*>(a_smem + (size_t)c * CHUNK_BYTES +
-                                            sw128_offset(row, b * 4 + pc)) = pk;
-                }
-              } else {
-                const float* wl = p.w_last + (size_t)wslot * p.d_out * p.H + col0;
-                for (int o = 0; o < p.d_out; ++o) {
-                  float s = dot[o];
-#pragma unroll
-                  for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 wv = __ldg(reinterpret_cast<const float4*>(wl + (size_t)o * p.H) + j4);
-                    s = fmaf(v[j4 * 4 + 0], wv.x, s);
-                    s = fmaf(v[j4 * 4 + 1], wv.y, s);
-                    s = fmaf(v[j4 * 4 + 2], wv.z, s);
-                    s = fmaf(v[j4 * 4 + 3], wv.w, s);
-                  }
-                  dot[o] = s;
-                }
-              }
-            }
+          for (int c = hf; c < KC; c += 2) {
+            const int col0 = c * CHUNK_K;
+            uint8_t* a_dst = a_row + (size_t)c * CHUNK_BYTES;
+            uint32_t keep = 0xffffffffu;
+            // ---- block 0 (columns col0 .. col0+31) ----
+            tmem_ld_wait();
+            tmem_ld32(lane_addr + (uint32_t)(col0 + 32), acc1);
+            if (drop) keep = epi_keep_bits(p, drop, kg, drop_ord, grow, col0, mask_layer, H);
+            epi_block<H, DOUT>(p, acc0, bias + col0, relu, drop, keep, last, a_dst, 0, rx,
+                               wl + col0, dot);
+            // ---- block 1 (columns col0+32 .. col0+63) ----
+            tmem_ld_wait();
+            if (c + 2 < KC) tmem_ld32(lane_addr + (uint32_t)(col0 + 2 * CHUNK_K), acc0);
+            if (drop) keep = epi_keep_bits(p, drop, kg, drop_ord, grow, col0 + 32, mask_layer, H);
+            epi_block<H, DOUT>(p, acc1, bias + col0 + 32, relu, drop, keep, last, a_dst, 4, rx,
+                               wl + col0 + 32, dot);
             // chunk c: accumulator columns drained (+ A chunk rewritten) -> release to the MMA warp
             tc_fence_before();
             if (!last) fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->chunk_done[c]);
-            if (warp == 2 && lane == 0) trace(2, (2u << 24) | (g << 4) | c);
+            if (lane == 0) mbar_arrive(bars + BAR_CHUNK + 8 * c);
           }
-          // a warp whose parity has no chunk (KC == 1) still owes nothing: barrier counts 4
-          if (((p.dropout_mask >> l) & 1u)) {
-            if (p.masks) mask_layer += (size_t)p.total_members * (size_t)p.n * (size_t)p.H;
+          if (has_drop) {
+            if (p.masks) mask_layer += (size_t)p.total_members * (size_t)p.n * (size_t)H;
             ++drop_ord;
           }
         }
 
         // ---- combine the two column-parity halves of the dot products, then Welford ----------
-        float* xb = xchg + (size_t)(mcount & 1) * TILE_M * p.d_out;
-        if (hf == 1) {
-          for (int o = 0; o < p.d_out; ++o) xb[row * p.d_out + o] = dot[o];
+        float* xb = xchg + (size_t)(mcount & 1) * TILE_M * DOUT;
+        if (KC > 1) {
+          if (hf == 1) {
+#pragma unroll
+            for (int o = 0; o < DOUT; ++o) xb[row * DOUT + o] = dot[o];
+          }
+          epi_bar_sync();
         }
-        const long long tb0 = prof ? clock64() : 0;
-        epi_bar_sync();
-        if (prof) wt[2] += clock64() - tb0;
         if (hf == 0) {
           wf_n += 1.f;
           const float inv_n = 1.f / wf_n;
-          const float* bl = p.b_last + (size_t)wslot * p.d_out;
-          for (int o = 0; o < p.d_out; ++o) {
-            float y = dot[o] + (p.KC > 1 ? xb[row * p.d_out + o] : 0.f) + __ldg(bl + o);
+          const float* bl = p.b_last + (size_t)wslot * DOUT;
+#pragma unroll
+          for (int o = 0; o < DOUT; ++o) {
+            float y = dot[o] + (KC > 1 ? xb[row * DOUT + o] : 0.f) + __ldg(bl + o);
             if (p.last_relu) y = fmaxf(y, 0.f);
             const float dlt = y - wf_mean[o];
             wf_mean[o] += dlt * inv_n;
@@ -587,32 +642,29 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
 
       // ---- tile done: publish (mean, std) / (mean, M2) ------------------------------------------
       if (hf == 0 && grow < p.n) {
-        for (int o = 0; o < p.d_out; ++o) {
-          const int64_t idx = grow * p.d_out + o;
-          if (p.splits > 1) {
-            p.part_mean[(size_t)split * (size_t)p.n * p.d_out + idx] = wf_mean[o];
-            p.part_m2[(size_t)split * (size_t)p.n * p.d_out + idx] = wf_m2[o];
-          } else {
-            p.out0[idx] = wf_mean[o];
-            p.out1[idx] = (p.output == UQ_OUT_MOMENTS) ? wf_m2[o] : sqrtf(wf_m2[o] / (wf_n - 1.f));
+#pragma unroll
+        for (int o = 0; o < DOUT; ++o) {
+          if (o < p.d_out) {
+            const int64_t idx = grow * p.d_out + o;
+            if (p.splits > 1) {
+              p.part_mean[(size_t)split * (size_t)p.n * p.d_out + idx] = wf_mean[o];
+              p.part_m2[(size_t)split * (size_t)p.n * p.d_out + idx] = wf_m2[o];
+            } else {
+              p.out0[idx] = wf_mean[o];
+              p.out1[idx] =
+                  (p.output == UQ_OUT_MOMENTS) ? wf_m2[o] : sqrtf(wf_m2[o] / (wf_n - 1.f));
+            }
           }
         }
       }
     }
   }
 
-  if (prof && warp >= 2 && lane == 0 && (warp == 2 || warp == 6)) {
-    const int o = warp == 2 ? 5 : 9;
-    p.prof[blockIdx.x * 16 + o + 0] = (unsigned long long)wt[0];  // epilogue: d_full wait
-    p.prof[blockIdx.x * 16 + o + 1] = (unsigned long long)wt[1];  // epilogue: write_x
-    p.prof[blockIdx.x * 16 + o + 2] = (unsigned long long)wt[2];  // epilogue: pair barrier
-    p.prof[blockIdx.x * 16 + o + 3] = (unsigned long long)(clock64() - t_start);
-  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    tmem_dealloc(tmem_base, (uint32_t)G::TMEM_COLS);
   }
 }
 
@@ -669,16 +721,59 @@ __global__ void fold_bias_kernel(const float* __restrict__ bias, const float* __
   out[i] = b;
 }
 
-size_t tc_smem_bytes(const TcPlan& t, int n_stages) {
-  const int KC = t.hidden / 64;
-  return 1024 + (size_t)KC * CHUNK_BYTES + (size_t)n_stages * t.stage_bytes + sizeof(Barriers) +
-         2 * TILE_M * (size_t)t.d_out * sizeof(float) + 64;
+// padded outputs of the last Linear: zero rows / zero bias beyond d_out
+__global__ void pad_last_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                float* __restrict__ w_out, float* __restrict__ b_out, int K,
+                                int d_out, int dpad, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)K * dpad * H;
+  if (i < total) {
+    const int h = (int)(i % H);
+    const int o = (int)((i / H) % dpad);
+    const int k = (int)(i / ((int64_t)H * dpad));
+    w_out[i] = o < d_out ? w[((int64_t)k * d_out + o) * H + h] : 0.f;
+  }
+  if (i < (int64_t)K * dpad) {
+    const int o = (int)(i % dpad), k = (int)(i / dpad);
+    b_out[i] = o < d_out ? b[(int64_t)k * d_out + o] : 0.f;
+  }
 }
 
-int pick_stages(const TcPlan& t) {
-  int s = MAX_STAGES;
-  while (s > 2 && tc_smem_bytes(t, s) > 232448) --s;
-  return s;
+int dout_pad(int d_out) { return d_out == 1 ? 1 : MAX_DOUT; }
+
+template <int H, int DOUT>
+int launch_tc(const TcParams& p, int64_t units, cudaStream_t st) {
+  using G = Geo<H, DOUT>;
+  auto kern = uq_mlp_tc_kernel<H, DOUT>;
+  UQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NUM_THREADS, G::SMEM_BYTES);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm * G::TMEM_COLS > 512) per_sm = 512 / G::TMEM_COLS;  // TMEM columns are per SM
+  if (per_sm > 2) per_sm = 2;
+  const int grid = (int)(units < (int64_t)sms * per_sm ? units : (int64_t)sms * per_sm);
+  kern<<<grid, NUM_THREADS, G::SMEM_BYTES, st>>>(p);
+  UQ_LAUNCH_CHECK();
+  return UQ_OK;
+}
+
+template <int DOUT>
+int dispatch_h(int H, const TcParams& p, int64_t units, cudaStream_t st) {
+  switch (H) {
+    case 64: return launch_tc<64, DOUT>(p, units, st);
+    case 128: return launch_tc<128, DOUT>(p, units, st);
+    case 192: return launch_tc<192, DOUT>(p, units, st);
+    case 256: return launch_tc<256, DOUT>(p, units, st);
+    case 320: return launch_tc<320, DOUT>(p, units, st);
+    case 384: return launch_tc<384, DOUT>(p, units, st);
+    case 448: return launch_tc<448, DOUT>(p, units, st);
+    case 512: return launch_tc<512, DOUT>(p, units, st);
+  }
+  set_error("bf16 kernel: unsupported hidden width %d", H);
+  return UQ_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -698,7 +793,6 @@ void tc_plan(uq_model* m) {
   }
   const int NH = (H + 255) / 256;
   const int n_tile = H / NH;
-  if (n_tile % 16 != 0) { t.why_not = "hidden width not tileable"; return; }
   if (L - 1 > MAX_MMA_LAYERS) { t.why_not = "too many layers"; return; }
   const Layer& last = m->layers[L - 1];
   if (last.out > MAX_DOUT) { t.why_not = "final out_features > 8"; return; }
@@ -757,9 +851,21 @@ int tc_pack(uq_model* m, cudaStream_t st) {
                                                      ly.bias_folded, n);
     UQ_LAUNCH_CHECK();
   }
+  // last Linear, padded to the kernel's compile-time output count
   const Layer& last = m->layers[m->n_layers - 1];
-  t.w_last = last.w;
-  t.b_last = last.bias_folded;
+  const int dpad = dout_pad(t.d_out);
+  void *wl = nullptr, *bl = nullptr;
+  UQ_CUDA(cudaMalloc(&wl, sizeof(float) * (size_t)K * dpad * H));
+  m->allocations.push_back(wl);
+  UQ_CUDA(cudaMalloc(&bl, sizeof(float) * (size_t)K * dpad));
+  m->allocations.push_back(bl);
+  const int64_t total = (int64_t)K * dpad * H;
+  pad_last_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      last.w, last.bias_folded, static_cast<float*>(wl), static_cast<float*>(bl), K, t.d_out, dpad,
+      H);
+  UQ_LAUNCH_CHECK();
+  t.w_last = static_cast<float*>(wl);
+  t.b_last = static_cast<float*>(bl);
   return UQ_OK;
 }
 
@@ -774,7 +880,7 @@ static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a)
 
 size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a) {
   const int splits = choose_splits(m, n, a);
-  size_t b = 256 + 148 * 4 * 16 * sizeof(unsigned long long);  // error flag + profile counters
+  size_t b = 256;  // error flag
   if (splits > 1) b += 2 * (size_t)splits * (size_t)n * m->d_out * sizeof(float) + 512;
   return b;
 }
@@ -797,22 +903,13 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.member_begin = a->member_begin;
   p.member_count = a->member_count;
   p.total_members = a->total_members;
-  p.H = t.hidden;
-  p.n_tile = t.n_tile;
-  p.NH = t.hidden / t.n_tile;
-  p.KC = t.hidden / 64;
   p.K0 = t.k0;
   p.split_s = split_factor(t);
   p.L_mma = t.n_mma_layers;
   p.d_out = t.d_out;
-  p.n_stages = pick_stages(t);
-  p.stage_bytes = (uint32_t)t.stage_bytes;
   p.stages_per_member = t.stages_per_member;
   p.shared_weights = (a->mode != UQ_MODE_ENSEMBLE) ? 1 : 0;
-  int cols = 32;
-  while (cols < t.hidden) cols *= 2;
-  p.tmem_cols = cols;
-  p.image = t.image;
+  p.image = reinterpret_cast<const uint8_t*>(t.image);
   const bool mc = (a->mode == UQ_MODE_MC_DROPOUT) && a->dropout_active;
   for (int l = 0; l < t.n_mma_layers; ++l) {
     p.bias[l] = m->layers[l].bias_folded;
@@ -834,74 +931,18 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.output = a->output;
   char* wsb = static_cast<char*>(ws);
   p.error_flag = reinterpret_cast<unsigned int*>(wsb);
-  const size_t prof_bytes = 148 * 4 * 16 * sizeof(unsigned long long);
-  const char* dbg_env = getenv("UQ_TC_DEBUG");
-  p.debug_flags = dbg_env ? atoi(dbg_env) : 0;
-  const char* prof_env = getenv("UQ_TC_PROFILE");
-  const bool want_prof = prof_env && prof_env[0] == '1';
-  p.prof = want_prof ? reinterpret_cast<unsigned long long*>(wsb + 256) : nullptr;
   if (p.splits > 1) {
-    const size_t part = (((size_t)p.splits * (size_t)n * m->d_out * sizeof(float)) + 255) & ~(size_t)255;
-    p.part_mean = reinterpret_cast<float*>(wsb + 256 + prof_bytes);
-    p.part_m2 = reinterpret_cast<float*>(wsb + 256 + prof_bytes + part);
+    const size_t part =
+        (((size_t)p.splits * (size_t)n * m->d_out * sizeof(float)) + 255) & ~(size_t)255;
+    p.part_mean = reinterpret_cast<float*>(wsb + 256);
+    p.part_m2 = reinterpret_cast<float*>(wsb + 256 + part);
   }
   UQ_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(unsigned int), st));
-  const char* trace_env = getenv("UQ_TC_TRACE");
-  unsigned long long* d_trace = nullptr;
-  if (trace_env && trace_env[0]) {
-    UQ_CUDA(cudaMalloc(&d_trace, 3 * TRACE_LEN * 2 * sizeof(unsigned long long)));
-    UQ_CUDA(cudaMemsetAsync(d_trace, 0, 3 * TRACE_LEN * 2 * sizeof(unsigned long long), st));
-  }
-  p.trace = d_trace;
 
-  const size_t smem = tc_smem_bytes(t, p.n_stages);
-  UQ_REQUIRE(smem <= 232448, UQ_ERR_UNSUPPORTED, "bf16 kernel needs %zu bytes of shared memory",
-             smem);
-  UQ_CUDA(cudaFuncSetAttribute(uq_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, uq_mlp_tc_kernel, NUM_THREADS, smem);
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;  // TMEM columns are per SM
-  if (per_sm > 2) per_sm = 2;
   const int64_t units = (int64_t)p.n_tiles * p.splits;
-  int grid = (int)(units < (int64_t)sms * per_sm ? units : (int64_t)sms * per_sm);
-  uq_mlp_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(p);
-  UQ_LAUNCH_CHECK();
-  if (d_trace) {  // bring-up aid: dump CTA 0's event timeline as CSV (role, tag, clock)
-    std::vector<unsigned long long> h(3 * TRACE_LEN * 2);
-    UQ_CUDA(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, st));
-    UQ_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_trace);
-    FILE* f = fopen(trace_env, "w");
-    if (f) {
-      for (int r = 0; r < 3; ++r)
-        for (int i = 0; i < TRACE_LEN; ++i) {
-          const unsigned long long tag = h[((size_t)r * TRACE_LEN + i) * 2];
-          if (tag) fprintf(f, "%d,%llu,%llu,%llu\n", r, tag >> 24, tag & 0xFFFFFF,
-                           h[((size_t)r * TRACE_LEN + i) * 2 + 1]);
-        }
-      fclose(f);
-    }
-  }
-  if (want_prof) {  // debugging aid: synchronises and prints the per-role wait breakdown
-    std::vector<unsigned long long> h((size_t)grid * 16);
-    UQ_CUDA(cudaMemcpyAsync(h.data(), p.prof, h.size() * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, st));
-    UQ_CUDA(cudaStreamSynchronize(st));
-    double a[16] = {0};
-    for (int b = 0; b < grid; ++b)
-      for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)b * 16 + i] / grid;
-    fprintf(stderr,
-            "[uq_tc_profile] grid %d cycles/CTA: total %.0f | producer wait w_empty %.0f | MMA wait "
-            "x_ready %.0f chunk_done %.0f w_full %.0f | epi(w2) wait d_full %.0f write_x %.0f pairbar "
-            "%.0f total %.0f | epi(w6) wait d_full %.0f pairbar %.0f\n",
-            grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[11]);
-  }
+  const int rc = (dout_pad(t.d_out) == 1) ? dispatch_h<1>(t.hidden, p, units, st)
+                                          : dispatch_h<MAX_DOUT>(t.hidden, p, units, st);
+  if (rc != UQ_OK) return rc;
   if (p.splits > 1) {
     double counts[64];
     for (int s = 0; s < p.splits; ++s) {
