@@ -51,21 +51,34 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every ``csrc/*.cu`` for sm_100a and link the shared library.  Returns its path."""
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """Compile every ``csrc/*.cu`` for sm_100a and link the shared library.  Returns its path.
+
+    ``trace=True`` builds the bring-up variant ``libnnueehcs_b200_trace.so`` (-DUQ_TC_TRACE: the
+    fused kernel logs a per-role event timeline of CTA 0); select it with NNUEEHCS_B200_LIB."""
     os.makedirs(OUT_DIR, exist_ok=True)
+    if trace:
+        return _build_variant("_trace", ["-DUQ_TC_TRACE"], verbose)
     stamp = os.path.join(OUT_DIR, "build.stamp")
     fp = _fingerprint()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
         with open(stamp) as f:
             if f.read().strip() == fp:
                 return LIB_PATH
+    _build_variant("", [], verbose)
+    with open(stamp, "w") as f:
+        f.write(fp)
+    return LIB_PATH
+
+
+def _build_variant(suffix, extra_flags, verbose) -> str:
     nvcc = _nvcc()
+    lib_path = LIB_PATH[:-3] + suffix + ".so"
     objs = []
 
     def compile_one(src):
-        obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+        obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + suffix + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", INCLUDE, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -77,15 +90,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
-        f.write(fp)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                trace="--trace" in sys.argv))

@@ -49,6 +49,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
 constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
+constexpr int TRACE_LEN = 4096;
 
 // compile-time geometry of one hidden width
 template <int H, int DOUT>
@@ -104,6 +105,7 @@ struct TcParams {
   float* part_mean;                   // [splits][n*d_out] when splits > 1
   float* part_m2;
   unsigned int* error_flag;
+  unsigned long long* trace;          // -DUQ_TC_TRACE builds only: [3 roles][TRACE_LEN][2] of CTA 0
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -210,6 +212,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -319,7 +343,7 @@ __device__ __forceinline__ uint32_t epi_keep_bits(const TcParams& p, int drop, i
 template <int H, int DOUT>
 __device__ __forceinline__ void epi_block(const TcParams& p, const uint32_t (&acc)[32],
                                           const float* __restrict__ bias32, bool relu, int drop,
-                                          uint32_t keep, bool last, uint8_t* a_dst, int piece0,
+                                          uint32_t keep, bool last, uint32_t a_dst, int piece0,
                                           int rx, const float* __restrict__ wl32,
                                           float (&dot)[DOUT]) {
   float v[32];
@@ -333,11 +357,11 @@ __device__ __forceinline__ void epi_block(const TcParams& p, const uint32_t (&ac
   if (!last) {
 #pragma unroll
     for (int pc = 0; pc < 4; ++pc)
-      *reinterpret_cast<uint4*>(a_dst + (((piece0 + pc) ^ rx) << 4)) =
-          make_uint4(pack_bf16x2(v[pc * 8 + 0], v[pc * 8 + 1]),
-                     pack_bf16x2(v[pc * 8 + 2], v[pc * 8 + 3]),
-                     pack_bf16x2(v[pc * 8 + 4], v[pc * 8 + 5]),
-                     pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]));
+      st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4),
+                   pack_bf16x2(v[pc * 8 + 0], v[pc * 8 + 1]),
+                   pack_bf16x2(v[pc * 8 + 2], v[pc * 8 + 3]),
+                   pack_bf16x2(v[pc * 8 + 4], v[pc * 8 + 5]),
+                   pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]));
   } else {
 #pragma unroll
     for (int o = 0; o < DOUT; ++o) {
@@ -372,13 +396,27 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
   uint8_t* a_smem = smem;                                  // KC chunks of 16 KB
   uint8_t* w_smem = smem + G::A_BYTES;                     // NS stages
   uint8_t* bar_smem = w_smem + NS * STAGE_BYTES;           // 256 B of mbarriers + tmem pointer
-  float* xchg = reinterpret_cast<float*>(bar_smem + 256);  // [2][128][DOUT] dot exchange
+  const uint32_t xchg = smem_u32(bar_smem + 256);          // [2][128][DOUT] dot exchange (floats)
   const uint32_t a_base = smem_u32(a_smem);
   const uint32_t w_base = smem_u32(w_smem);
   const uint32_t bars = smem_u32(bar_smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_tiles * p.splits;
+#ifdef UQ_TC_TRACE
+  int tr_n = 0;
+  auto trace = [&](int role, unsigned kind, unsigned idx) {
+    if (p.trace != nullptr && blockIdx.x == 0 && tr_n < TRACE_LEN && (role != 1 || lane == 0)) {
+      unsigned long long* t = p.trace + ((size_t)role * TRACE_LEN + tr_n) * 2;
+      t[0] = ((unsigned long long)kind << 24) | idx;
+      t[1] = (unsigned long long)clock64();
+      ++tr_n;
+    }
+  };
+#define UQ_TRACE(role, kind, idx) trace(role, kind, idx)
+#else
+#define UQ_TRACE(role, kind, idx)
+#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -400,6 +438,8 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
     // ===================================== producer =============================================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
+      unsigned tr_it = 0;
+      (void)tr_it;
       const size_t member_bytes = (size_t)p.stages_per_member * STAGE_BYTES;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int split = unit % p.splits;
@@ -412,6 +452,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
             mbar_wait(bars + BAR_W_EMPTY + 8 * slot, phase ^ 1, p.error_flag, 1);
             mbar_arrive_expect_tx(bars + BAR_W_FULL + 8 * slot, STAGE_BYTES);
             bulk_g2s(w_base + slot * STAGE_BYTES, src, STAGE_BYTES, bars + BAR_W_FULL + 8 * slot);
+            UQ_TRACE(0, 2, tr_it++);
             src += STAGE_BYTES;
             if (++slot == NS) { slot = 0; phase ^= 1; }
           }
@@ -420,7 +461,12 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ===========================================
-    if (lane == 0) {
+    // The whole warp walks the loop convergently (operands stay warp-uniform, so the compiler
+    // keeps descriptors in uniform registers); one elected lane issues tcgen05.mma / commit.
+    // Barrier probes run one stage ahead: a try_wait costs ~180 cycles even when the phase has
+    // already completed, so the probe for stage i+1 is issued before stage i's MMAs and its
+    // result is only consumed afterwards.
+    {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, NT);
       const uint64_t a_desc0 = make_sw128_desc(a_base);
       const uint64_t b_desc0 = make_sw128_desc(w_base);
@@ -428,6 +474,27 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
       uint32_t slot = 0, phase = 0;
       uint32_t g = 0;      // layer-step counter (d_full / chunk_done phases)
       uint32_t xm = 0;     // member counter (x_ready phase)
+      bool w_ready = mbar_try_wait(bars + BAR_W_FULL, 0);
+#ifdef UQ_TC_TRACE
+      unsigned tr_it = 0;
+#endif
+      // acquire the current weight stage and probe the next one
+      uint32_t nslot = 0, nphase = 0;
+      bool w_ready_next = false;
+      auto acquire = [&]() {
+        if (!w_ready) mbar_wait_slow(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 4);
+        tc_fence_after();
+        nslot = slot + 1;
+        nphase = phase;
+        if (nslot == NS) { nslot = 0; nphase ^= 1; }
+        w_ready_next = mbar_try_wait(bars + BAR_W_FULL + 8 * nslot, nphase);
+      };
+      auto release = [&]() {
+        if (elect_one()) umma_commit(bars + BAR_W_EMPTY + 8 * slot);  // frees the stage on retire
+        slot = nslot;
+        phase = nphase;
+        w_ready = w_ready_next;
+      };
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int split = unit % p.splits;
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
@@ -437,56 +504,75 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
           {
             const uint32_t prev_par = (g - 1) & 1;
             mbar_wait(bars + BAR_X_READY, xm & 1, p.error_flag, 2);
-            int waited = 0;
 #pragma unroll
             for (int nh = 0; nh < NH; ++nh) {
               if (g != 0) {  // accumulator half nh must have been drained by the previous epilogue
+                uint32_t ok = 0;
 #pragma unroll
                 for (int c = 0; c < KC; ++c)
-                  if (c >= waited && c <= G::hi(nh))
-                    mbar_wait(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
+                  if (c >= (nh == 0 ? 0 : G::hi(nh - 1) + 1) && c <= G::hi(nh))
+                    ok |= (mbar_try_wait(bars + BAR_CHUNK + 8 * c, prev_par) ? 1u : 0u) << c;
+#pragma unroll
+                for (int c = 0; c < KC; ++c)
+                  if (c >= (nh == 0 ? 0 : G::hi(nh - 1) + 1) && c <= G::hi(nh))
+                    if (!((ok >> c) & 1u))
+                      mbar_wait_slow(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
               }
-              waited = G::hi(nh) + 1;
-              mbar_wait(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 4);
-              tc_fence_after();
-              const uint64_t bd = b_desc0 + (uint64_t)((slot * STAGE_BYTES) >> 4);
-              for (int ks = 0; ks < k0_steps; ++ks)
-                umma_bf16(tmem_base + nh * NT, a_desc0 + 2 * ks, bd + 2 * ks, idesc,
-                          ks > 0 ? 1u : 0u);
-              umma_commit(bars + BAR_W_EMPTY + 8 * slot);
-              if (++slot == NS) { slot = 0; phase ^= 1; }
+              acquire();
+              if (elect_one()) {
+                const uint64_t bd = b_desc0 + (uint64_t)((slot * STAGE_BYTES) >> 4);
+                for (int ks = 0; ks < k0_steps; ++ks)
+                  umma_bf16(tmem_base + nh * NT, a_desc0 + 2 * ks, bd + 2 * ks, idesc,
+                            ks > 0 ? 1u : 0u);
+              }
+              release();
             }
-            umma_commit(bars + BAR_D_FULL);
+            if (elect_one()) umma_commit(bars + BAR_D_FULL);
+            UQ_TRACE(1, 4, g);
             ++g;
           }
           // ---- hidden layers: A = previous activations (in-place chunks), K = H ----------------
           for (int l = 1; l < p.L_mma; ++l) {
             const uint32_t prev_par = (g - 1) & 1;
-            int waited = 0;
+            // chunks 0..hi(0): accumulator half 0 drained and the first A chunks written
+            {
+              uint32_t ok = 0;
+#pragma unroll
+              for (int c = 0; c <= G::hi(0); ++c)
+                ok |= (mbar_try_wait(bars + BAR_CHUNK + 8 * c, prev_par) ? 1u : 0u) << c;
+#pragma unroll
+              for (int c = 0; c <= G::hi(0); ++c)
+                if (!((ok >> c) & 1u))
+                  mbar_wait_slow(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
+            }
+            bool c_ready = (G::hi(0) + 1 < KC)
+                               ? mbar_try_wait(bars + BAR_CHUNK + 8 * (G::hi(0) + 1), prev_par)
+                               : true;
 #pragma unroll
             for (int nh = 0; nh < NH; ++nh) {
 #pragma unroll
               for (int kc = 0; kc < KC; ++kc) {
-                // accumulator half nh drained + A chunk kc written by the previous epilogue
-                const int need = (G::hi(nh) > kc ? G::hi(nh) : kc) + 1;
+                if (nh == 0 && kc > G::hi(0)) {  // A chunk kc (and its accumulator columns)
+                  if (!c_ready) mbar_wait_slow(bars + BAR_CHUNK + 8 * kc, prev_par, p.error_flag, 3);
+                  if (kc + 1 < KC) c_ready = mbar_try_wait(bars + BAR_CHUNK + 8 * (kc + 1), prev_par);
+                }
+                UQ_TRACE(1, 1, tr_it);
+                acquire();
+                UQ_TRACE(1, 2, tr_it);
+                if (elect_one()) {
+                  const uint64_t ad = a_desc0 + (uint64_t)((kc * CHUNK_BYTES) >> 4);
+                  const uint64_t bd = b_desc0 + (uint64_t)((slot * STAGE_BYTES) >> 4);
 #pragma unroll
-                for (int c = 0; c < KC; ++c)
-                  if (c >= waited && c < need)
-                    mbar_wait(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
-                if (need > waited) waited = need;
-                mbar_wait(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 4);
-                tc_fence_after();
-                const uint64_t ad = a_desc0 + (uint64_t)((kc * CHUNK_BYTES) >> 4);
-                const uint64_t bd = b_desc0 + (uint64_t)((slot * STAGE_BYTES) >> 4);
-#pragma unroll
-                for (int ks = 0; ks < CHUNK_K / 16; ++ks)
-                  umma_bf16(tmem_base + nh * NT, ad + 2 * ks, bd + 2 * ks, idesc,
-                            (kc > 0 || ks > 0) ? 1u : 0u);
-                umma_commit(bars + BAR_W_EMPTY + 8 * slot);  // frees the stage when MMAs retire
-                if (++slot == NS) { slot = 0; phase ^= 1; }
+                  for (int ks = 0; ks < CHUNK_K / 16; ++ks)
+                    umma_bf16(tmem_base + nh * NT, ad + 2 * ks, bd + 2 * ks, idesc,
+                              (kc > 0 || ks > 0) ? 1u : 0u);
+                }
+                release();
+                UQ_TRACE(1, 3, tr_it++);
               }
             }
-            umma_commit(bars + BAR_D_FULL);  // whole layer accumulated
+            if (elect_one()) umma_commit(bars + BAR_D_FULL);  // whole layer accumulated
+            UQ_TRACE(1, 4, g);
             ++g;
           }
         }
@@ -501,7 +587,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t g = 0;                      // layer-step counter
     uint32_t mcount = 0;                 // members processed (exchange buffer parity)
-    uint8_t* a_row = a_smem + (row >> 3) * 1024 + (row & 7) * 128;  // this row inside chunk 0
+    const uint32_t a_row = a_base + (row >> 3) * 1024 + (row & 7) * 128;  // this row in chunk 0
     const int rx = row & 7;
 
     // writes the layer-0 A operand (split input row) into chunk 0, pieces [0, K0/8)
@@ -528,8 +614,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
             }
             w4[h2] = pack_bf16x2(v[0], v[1]);
           }
-          *reinterpret_cast<uint4*>(a_row + ((piece ^ rx) << 4)) =
-              make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          st_shared_v4(a_row + (uint32_t)((piece ^ rx) << 4), w4[0], w4[1], w4[2], w4[3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -570,6 +655,8 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
           if (lane == 0) mbar_wait(bars + BAR_D_FULL, g & 1, p.error_flag, 5);
           __syncwarp();
           tc_fence_after();
+          if (warp == 2 && lane == 0) { UQ_TRACE(2, 1, g); }
+          if (warp == 6 && lane == 0) { UQ_TRACE(2, 5, g); }
 
           if (last) {
             // every MMA that reads the A chunks has retired: stage the next member's input row
@@ -590,7 +677,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll 1
           for (int c = hf; c < KC; c += 2) {
             const int col0 = c * CHUNK_K;
-            uint8_t* a_dst = a_row + (size_t)c * CHUNK_BYTES;
+            const uint32_t a_dst = a_row + (uint32_t)c * CHUNK_BYTES;
             uint32_t keep = 0xffffffffu;
             // ---- block 0 (columns col0 .. col0+31) ----
             tmem_ld_wait();
@@ -609,6 +696,8 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
             if (!last) fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + BAR_CHUNK + 8 * c);
+            if (warp == 2 && lane == 0) { UQ_TRACE(2, 2, (g << 4) | c); }
+            if (warp == 6 && lane == 0) { UQ_TRACE(2, 6, (g << 4) | c); }
           }
           if (has_drop) {
             if (p.masks) mask_layer += (size_t)p.total_members * (size_t)p.n * (size_t)H;
@@ -617,11 +706,11 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
         }
 
         // ---- combine the two column-parity halves of the dot products, then Welford ----------
-        float* xb = xchg + (size_t)(mcount & 1) * TILE_M * DOUT;
+        const uint32_t xb = xchg + (uint32_t)(((mcount & 1) * TILE_M + row) * DOUT * 4);
         if (KC > 1) {
           if (hf == 1) {
 #pragma unroll
-            for (int o = 0; o < DOUT; ++o) xb[row * DOUT + o] = dot[o];
+            for (int o = 0; o < DOUT; ++o) st_shared_f32(xb + 4 * o, dot[o]);
           }
           epi_bar_sync();
         }
@@ -631,7 +720,7 @@ uq_mlp_tc_kernel(const __grid_constant__ TcParams p) {
           const float* bl = p.b_last + (size_t)wslot * DOUT;
 #pragma unroll
           for (int o = 0; o < DOUT; ++o) {
-            float y = dot[o] + (KC > 1 ? xb[row * DOUT + o] : 0.f) + __ldg(bl + o);
+            float y = dot[o] + (KC > 1 ? ld_shared_f32(xb + 4 * o) : 0.f) + __ldg(bl + o);
             if (p.last_relu) y = fmaxf(y, 0.f);
             const float dlt = y - wf_mean[o];
             wf_mean[o] += dlt * inv_n;
@@ -938,11 +1027,38 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
     p.part_m2 = reinterpret_cast<float*>(wsb + 256 + part);
   }
   UQ_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(unsigned int), st));
+#ifdef UQ_TC_TRACE
+  const char* trace_env = getenv("UQ_TC_TRACE_FILE");
+  unsigned long long* d_trace = nullptr;
+  if (trace_env && trace_env[0]) {
+    UQ_CUDA(cudaMalloc(&d_trace, 3 * TRACE_LEN * 2 * sizeof(unsigned long long)));
+    UQ_CUDA(cudaMemsetAsync(d_trace, 0, 3 * TRACE_LEN * 2 * sizeof(unsigned long long), st));
+  }
+  p.trace = d_trace;
+#endif
 
   const int64_t units = (int64_t)p.n_tiles * p.splits;
   const int rc = (dout_pad(t.d_out) == 1) ? dispatch_h<1>(t.hidden, p, units, st)
                                           : dispatch_h<MAX_DOUT>(t.hidden, p, units, st);
   if (rc != UQ_OK) return rc;
+#ifdef UQ_TC_TRACE
+  if (d_trace) {  // bring-up aid: dump CTA 0's event timeline as CSV (role, kind, index, clock)
+    std::vector<unsigned long long> h(3 * TRACE_LEN * 2);
+    UQ_CUDA(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+    UQ_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_trace);
+    if (FILE* f = fopen(trace_env, "w")) {
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < TRACE_LEN; ++i) {
+          const unsigned long long tag = h[((size_t)r * TRACE_LEN + i) * 2];
+          if (tag) fprintf(f, "%d,%llu,%llu,%llu\n", r, tag >> 24, tag & 0xFFFFFF,
+                           h[((size_t)r * TRACE_LEN + i) * 2 + 1]);
+        }
+      fclose(f);
+    }
+  }
+#endif
   if (p.splits > 1) {
     double counts[64];
     for (int s = 0; s < p.splits; ++s) {
