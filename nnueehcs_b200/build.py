@@ -41,7 +41,8 @@ def _sources():
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
+             if os.path.isfile(os.path.join(CSRC, f))]
     files.append(os.path.join(INCLUDE, "nnueehcs_b200.h"))
     for p in files:
         with open(p, "rb") as f:

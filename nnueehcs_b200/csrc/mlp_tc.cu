@@ -35,21 +35,18 @@
 
 #include "common.cuh"
 #include "philox.cuh"
+#include "tc_params.cuh"
+#include "tc_ptx.cuh"
 
 namespace uq {
 
 namespace {
 
-constexpr int TILE_M = 128;
-constexpr int CHUNK_K = 64;                    // bf16 columns per SW128 row (128 bytes)
-constexpr int CHUNK_BYTES = TILE_M * 128;      // one activation chunk [128 x 64] bf16
-constexpr int MAX_MMA_LAYERS = 16;
-constexpr int MAX_DOUT = 8;
+using namespace tc;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
 constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
-constexpr int TRACE_LEN = 4096;
 
 // compile-time geometry of one hidden width
 template <int H, int DOUT>
@@ -75,198 +72,6 @@ struct Geo {
   __host__ __device__ static constexpr int hi(int nh) { return ((nh + 1) * NT + CHUNK_K - 1) / CHUNK_K - 1; }
 };
 
-struct TcParams {
-  const float* x;        // [n][d_x]
-  int64_t n;
-  int d_x;               // features of x (d_in, or d_in/2 for Delta-UQ)
-  int d_in;              // network input features
-  int mode;
-  int n_tiles;
-  int splits;            // member-axis splits (partial moments when > 1)
-  int member_begin, member_count, total_members;
-  int K0, split_s, L_mma, d_out;
-  int stages_per_member;
-  int shared_weights;
-  const uint8_t* image;
-  const float* bias[MAX_MMA_LAYERS];  // [K or 1][H] folded bias per MMA layer
-  uint32_t relu_mask, dropout_mask;   // bit l: MMA layer l has ReLU / dropout on its output
-  const float* w_last;                // [K or 1][DOUT][H]  (zero rows beyond d_out)
-  const float* b_last;                // [K or 1][DOUT]
-  int last_relu;
-  int drop_mode;                      // 0 none, 1 injected, 2 philox
-  float drop_scale;
-  uint32_t thr16;
-  PhiloxKey key;
-  const uint8_t* masks;               // injected base
-  const float* anchors;               // [total_members][d_x]
-  float* out0;
-  float* out1;
-  int output;                         // UQ_OUT_*
-  float* part_mean;                   // [splits][n*d_out] when splits > 1
-  float* part_m2;
-  unsigned int* error_flag;
-  unsigned long long* trace;          // -DUQ_TC_TRACE builds only: [3 roles][TRACE_LEN][2] of CTA 0
-};
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel (clean CUDA error), never as a
-// hung GPU.  Each failed probe suspends in hardware for a few hundred cycles, so 2^24 probes are
-// several seconds.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned int* err,
-                                            int tag) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      if (err) atomicExch(err, 0x80000000u | (unsigned)tag);
-      __threadfence_system();
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err,
-                                          int tag) {
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, tag);
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
-                                         uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, issued by one thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
-        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(addr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
-                                             uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
-}
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
-      "selp.u32 %0, 1, 0, px;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void epi_bar_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-}
-
-// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
-// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30),
-// SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version = 1 in [46,48), layout 2 in [61,64).
-// Advancing by `bytes` inside the operand = adding bytes >> 4 to the 64-bit value.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=F32, A=B=BF16, K-major.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// byte offset of (row, 16-byte piece) inside a [rows x 64] bf16 SW128 K-major chunk
-__host__ __device__ inline uint32_t sw128_offset(int row, int piece) {
-  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((piece ^ (row & 7)) << 4));
-}
 
 // barrier block (byte offsets inside the 256-byte barrier area)
 constexpr uint32_t BAR_W_FULL = 0;       // 8 x 8 B
@@ -1038,8 +843,19 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
 #endif
 
   const int64_t units = (int64_t)p.n_tiles * p.splits;
-  const int rc = (dout_pad(t.d_out) == 1) ? dispatch_h<1>(t.hidden, p, units, st)
-                                          : dispatch_h<MAX_DOUT>(t.hidden, p, units, st);
+  // CTA-pair kernel (mlp_tc2.cu) for wide nets; narrow nets keep two independent CTAs per SM.
+  // UQ_TC_VARIANT=1|2 overrides (bring-up / A-B measurements).
+  int variant = (t.hidden > 128 && tc2_supported(t.hidden)) ? 2 : 1;
+  if (const char* v = getenv("UQ_TC_VARIANT")) {
+    if (v[0] == '1') variant = 1;
+    if (v[0] == '2' && tc2_supported(t.hidden)) variant = 2;
+  }
+  int rc;
+  if (variant == 2)
+    rc = tc2_launch(p, t.hidden, dout_pad(t.d_out), st);
+  else
+    rc = (dout_pad(t.d_out) == 1) ? dispatch_h<1>(t.hidden, p, units, st)
+                                  : dispatch_h<MAX_DOUT>(t.hidden, p, units, st);
   if (rc != UQ_OK) return rc;
 #ifdef UQ_TC_TRACE
   if (d_trace) {  // bring-up aid: dump CTA 0's event timeline as CSV (role, kind, index, clock)

@@ -1,0 +1,730 @@
+// bf16 tcgen05 path of the UQ forward, CTA-pair variant (cta_group::2).
+//
+// Same fused scheme as mlp_tc.cu -- a persistent, warp-specialised kernel that keeps the
+// activations of a sample tile on the SM for the whole  members x layers  stack -- but two CTAs
+// on the two SMs of a TPC work as one unit:
+//
+//   * each CTA owns its own 128-sample tile (A operand in its shared memory, [128 x H] fp32
+//     accumulator in its tensor memory); one tcgen05.mma.cta_group::2 with M = 256 issued by the
+//     leader CTA (cluster rank 0) drives both tensor cores;
+//   * the B operand (a weight stage [N x 64] bf16) is split: each CTA streams only N/2 rows of
+//     it, so the L2 -> SM weight traffic per flop halves and the same shared-memory budget holds
+//     twice as many stages in flight.  The first version of this kernel (one CTA per tile) spent
+//     ~760 cycles per 32 KB stage waiting on the weight ring against a 512-cycle MMA floor
+//     (profiles/r01_c_*);
+//   * cross-CTA signalling: the peer's weight-stage arrivals are relayed to the leader's "full"
+//     barriers by the peer's (otherwise idle) MMA warp; epilogue warps of both CTAs arrive on the
+//     leader's chunk barriers through mapa'd cluster addresses; tcgen05.commit multicasts
+//     "stage free" and "layer accumulated" to both CTAs.
+//
+// Epilogue (warps 2..9 of each CTA): the folded bias of the layer is staged once per layer-step in
+// shared memory (prefetched one step ahead), the accumulator is drained with double-buffered
+// tcgen05.ld, bias + ReLU + bf16 rounding are two instructions per pair (FADD, FADD,
+// cvt.rn.relu.bf16x2), and the result is stored straight into the next layer's swizzled A chunk.
+// The last Linear is a CUDA-core dot product feeding the per-row Welford, as in mlp_tc.cu.
+//
+// Replaces: EnsembleModel.forward (models.py:99-108), MCDropoutModel.forward (:147-163) and the
+// anchored forward behind DeltaUQMLP.forward (:313-341) for MLPs whose hidden widths are equal.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "tc_params.cuh"
+#include "tc_ptx.cuh"
+
+namespace uq {
+
+namespace {
+
+using namespace tc;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
+constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
+
+template <int H, int DOUT>
+struct Geo2 {
+  static_assert(H % 64 == 0 && H >= 64 && H <= 512, "hidden width must be a multiple of 64 <= 512");
+  static constexpr int KC = H / CHUNK_K;                 // activation chunks == K-chunks per layer
+  static constexpr int NH = (H + 255) / 256;             // accumulator halves (MMA N <= 256)
+  static constexpr int NT = H / NH;                      // MMA N of the pair
+  static_assert(NT % 16 == 0, "MMA N must be a multiple of 16");
+  static constexpr int TMEM_COLS = H <= 64 ? 64 : H <= 128 ? 128 : H <= 256 ? 256 : 512;
+  static constexpr int STAGE_BYTES = NT * 128;           // whole stage [NT x 64] bf16 in the image
+  static constexpr int HALF_BYTES = STAGE_BYTES / 2;     // what one CTA of the pair loads
+  static constexpr int A_BYTES = KC * CHUNK_BYTES;
+  static constexpr int AUX_FLOATS = (DOUT == 1 ? 2 : 1) * H;   // bias [+ w_last] of one step
+  static constexpr int AUX_BYTES = 2 * AUX_FLOATS * 4;         // double-buffered by step parity
+  static constexpr int XCHG_BYTES = 2 * TILE_M * DOUT * 4;
+  static constexpr int MISC_BYTES = 1024 /*align slack*/ + 256 /*barriers*/ + XCHG_BYTES;
+  static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES;
+  static constexpr int NS_RAW = BUDGET / HALF_BYTES;
+  static constexpr int NSTAGES = NS_RAW > 8 ? 8 : NS_RAW;
+  static_assert(NSTAGES >= 2, "not enough shared memory for a weight ring");
+  static constexpr int SMEM_BYTES = A_BYTES + NSTAGES * HALF_BYTES + AUX_BYTES + MISC_BYTES;
+  __host__ __device__ static constexpr int hi(int nh) { return ((nh + 1) * NT + CHUNK_K - 1) / CHUNK_K - 1; }
+};
+
+// barrier block (byte offsets inside the 256-byte barrier area)
+constexpr uint32_t BAR_W_FULL = 0;       // 8 x 8 B   leader: own bytes + peer relay; peer: own bytes
+constexpr uint32_t BAR_W_EMPTY = 64;     // 8 x 8 B   commit multicast from the leader
+constexpr uint32_t BAR_CHUNK = 128;      // 8 x 8 B   leader only: 4 warps of each CTA
+constexpr uint32_t BAR_D_FULL = 192;     //           commit multicast from the leader
+constexpr uint32_t BAR_X_READY = 200;    //           leader only: 4 warps of each CTA
+constexpr uint32_t BAR_TMEM_PTR = 208;
+
+__device__ __forceinline__ float net_input2(const TcParams& p, int64_t row, int member_global,
+                                            int i) {
+  if (row >= p.n) return 0.f;
+  if (p.mode == UQ_MODE_DELTA_UQ) {
+    const int d = p.d_x;
+    const float a = __ldg(p.anchors + (int64_t)member_global * d + (i < d ? i : i - d));
+    return i < d ? __ldg(p.x + row * d + i) - a : a;
+  }
+  return __ldg(p.x + row * p.d_x + i);
+}
+
+// keep-mask bits of 32 consecutive features of one row
+__device__ __forceinline__ uint32_t keep_bits32(const TcParams& p, int drop, int kg, int drop_ord,
+                                                int64_t grow, int col0, const uint8_t* mask_layer,
+                                                int H) {
+  uint32_t keep = 0;
+  if (drop == 2) {
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq)
+      keep |= dropout_keep8(p.key, p.thr16, (uint32_t)kg, (uint32_t)drop_ord, (uint32_t)grow,
+                            (uint32_t)(col0 / 8 + gq))
+              << (8 * gq);
+  } else if (grow < p.n) {
+    const uint4* mrow = reinterpret_cast<const uint4*>(
+        mask_layer + ((size_t)kg * (size_t)p.n + (size_t)grow) * H + col0);
+    const uint4 m0 = __ldg(mrow), m1 = __ldg(mrow + 1);
+    const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      keep |= ((w[j] & 0xFFu) ? 1u : 0u) << (4 * j);
+      keep |= ((w[j] & 0xFF00u) ? 1u : 0u) << (4 * j + 1);
+      keep |= ((w[j] & 0xFF0000u) ? 1u : 0u) << (4 * j + 2);
+      keep |= ((w[j] & 0xFF000000u) ? 1u : 0u) << (4 * j + 3);
+    }
+  }
+  return keep;
+}
+
+// One 32-column block of one accumulator row: + bias, ReLU, dropout, then either the bf16 A-operand
+// write-back (cvt.rn[.relu].bf16x2 + 4 x st.shared.v4) or the last-Linear dot product.
+template <int H, int DOUT, bool RELU, bool DROP, bool LAST>
+__device__ __forceinline__ void epi_block2(const uint32_t (&acc)[32], const float4 (&bv)[8],
+                                           uint32_t keep, float keep_scale, uint32_t a_dst,
+                                           int piece0, int rx, const float* __restrict__ wl_s,
+                                           const float* __restrict__ wl_g, float (&dot)[DOUT]) {
+  float v[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + bv[j4].x;
+    v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + bv[j4].y;
+    v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + bv[j4].z;
+    v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + bv[j4].w;
+  }
+  if (DROP) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
+  }
+  if (!LAST) {
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+      uint32_t w4[4];
+#pragma unroll
+      for (int h2 = 0; h2 < 4; ++h2)
+        w4[h2] = RELU ? cvt_relu_bf16x2(v[pc * 8 + 2 * h2], v[pc * 8 + 2 * h2 + 1])
+                      : cvt_bf16x2(v[pc * 8 + 2 * h2], v[pc * 8 + 2 * h2 + 1]);
+      st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4), w4[0], w4[1], w4[2], w4[3]);
+    }
+  } else {
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (DOUT == 1) {
+      float s = dot[0];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 wv = reinterpret_cast<const float4*>(wl_s)[j4];
+        s = fmaf(v[j4 * 4 + 0], wv.x, s);
+        s = fmaf(v[j4 * 4 + 1], wv.y, s);
+        s = fmaf(v[j4 * 4 + 2], wv.z, s);
+        s = fmaf(v[j4 * 4 + 3], wv.w, s);
+      }
+      dot[0] = s;
+    } else {
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) {
+        float s = dot[o];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wl_g + o * H) + j4);
+          s = fmaf(v[j4 * 4 + 0], wv.x, s);
+          s = fmaf(v[j4 * 4 + 1], wv.y, s);
+          s = fmaf(v[j4 * 4 + 2], wv.z, s);
+          s = fmaf(v[j4 * 4 + 3], wv.w, s);
+        }
+        dot[o] = s;
+      }
+    }
+  }
+}
+
+struct DrainCtx {
+  uint32_t lane_addr;      // TMEM address of this warp's lane quarter, column 0
+  uint32_t a_row;          // smem address of this row inside chunk 0
+  int rx;                  // row & 7
+  int hf;                  // chunk parity handled by this warp
+  int lane;
+  uint32_t chunk_bar0;     // cluster address of the leader's chunk barrier 0
+  const float* bias_s;     // staged bias of this step (shared)
+  const float* wl_s;       // staged w_last (shared, DOUT == 1)
+  const float* wl_g;       // w_last of this member (global, DOUT > 1)
+  int drop;                // 0 none, 1 injected, 2 philox
+  int kg, drop_ord;
+  int64_t grow;
+  const uint8_t* mask_layer;
+};
+
+// Drain this warp's chunks of one layer-step; TMEM loads run one 32-column block ahead.
+template <int H, int DOUT, bool RELU, bool DROP, bool LAST>
+__device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx,
+                                           float (&dot)[DOUT]) {
+  constexpr int KC = H / CHUNK_K;
+  uint32_t acc0[32], acc1[32];
+  if (cx.hf < KC) tmem_ld32(cx.lane_addr + (uint32_t)(cx.hf * CHUNK_K), acc0);
+#pragma unroll 1
+  for (int c = cx.hf; c < KC; c += 2) {
+    const int col0 = c * CHUNK_K;
+    const uint32_t a_dst = cx.a_row + (uint32_t)c * CHUNK_BYTES;
+    uint32_t keep = 0xffffffffu;
+    float4 bv[8];
+    // ---- block 0 (columns col0 .. col0+31) ----
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
+    if (DROP) keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
+    tmem_ld_wait();
+    tmem_ld32(cx.lane_addr + (uint32_t)(col0 + 32), acc1);
+    epi_block2<H, DOUT, RELU, DROP, LAST>(acc0, bv, keep, p.drop_scale, a_dst, 0, cx.rx,
+                                          cx.wl_s + col0, cx.wl_g + col0, dot);
+    // ---- block 1 (columns col0+32 .. col0+63) ----
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4)
+      bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0 + 32)[j4];
+    if (DROP)
+      keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0 + 32, cx.mask_layer, H);
+    tmem_ld_wait();
+    if (c + 2 < KC) tmem_ld32(cx.lane_addr + (uint32_t)(col0 + 2 * CHUNK_K), acc0);
+    epi_block2<H, DOUT, RELU, DROP, LAST>(acc1, bv, keep, p.drop_scale, a_dst, 4, cx.rx,
+                                          cx.wl_s + col0 + 32, cx.wl_g + col0 + 32, dot);
+    // chunk c: accumulator columns drained (+ A chunk rewritten) -> release to the MMA warp
+    tc_fence_before();
+    if (!LAST) fence_proxy_async_smem();
+    __syncwarp();
+    if (cx.lane == 0) mbar_arrive_cluster(cx.chunk_bar0 + 8 * c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused kernel (one cluster = two CTAs = two sample tiles)
+// ------------------------------------------------------------------------------------------------
+template <int H, int DOUT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
+  using G = Geo2<H, DOUT>;
+  constexpr int KC = G::KC, NH = G::NH, NT = G::NT, NS = G::NSTAGES;
+  constexpr uint32_t STAGE_BYTES = G::STAGE_BYTES, HALF_BYTES = G::HALF_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment (pointer arithmetic on the shared array keeps the
+  // address space visible to the compiler: bias / w_last reads below become LDS)
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* a_smem = smem;                                  // KC chunks of 16 KB
+  uint8_t* w_smem = smem + G::A_BYTES;                     // NS half-stages
+  float* aux_smem = reinterpret_cast<float*>(w_smem + NS * HALF_BYTES);  // [2][AUX_FLOATS]
+  uint8_t* bar_smem = reinterpret_cast<uint8_t*>(aux_smem) + G::AUX_BYTES;
+  const uint32_t xchg = smem_u32(bar_smem + 256);          // [2][128][DOUT] dot exchange (floats)
+  const uint32_t a_base = smem_u32(a_smem);
+  const uint32_t w_base = smem_u32(w_smem);
+  const uint32_t bars = smem_u32(bar_smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int n_units = ((p.n_tiles + 1) >> 1) * p.splits;   // (tile pair, member split)
+#ifdef UQ_TC_TRACE
+  int tr_n = 0;
+  auto trace = [&](int role, unsigned kind, unsigned idx) {
+    if (p.trace != nullptr && blockIdx.x == 0 && tr_n < TRACE_LEN && (role != 1 || lane == 0)) {
+      unsigned long long* t = p.trace + ((size_t)role * TRACE_LEN + tr_n) * 2;
+      t[0] = ((unsigned long long)kind << 24) | idx;
+      t[1] = (unsigned long long)clock64();
+      ++tr_n;
+    }
+  };
+  unsigned tr_it = 0;
+  (void)tr_it;
+#define UQ_TRACE(role, kind, idx) trace(role, kind, idx)
+#else
+#define UQ_TRACE(role, kind, idx)
+#endif
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bars + BAR_W_FULL + 8 * s, leader ? 2 : 1);
+      mbar_init(bars + BAR_W_EMPTY + 8 * s, 1);
+    }
+    for (int c = 0; c < KC; ++c) mbar_init(bars + BAR_CHUNK + 8 * c, 8);
+    mbar_init(bars + BAR_D_FULL, 1);
+    mbar_init(bars + BAR_X_READY, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(bars + BAR_TMEM_PTR, (uint32_t)G::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(bar_smem + BAR_TMEM_PTR);
+
+  if (warp == 0) {
+    // ===================================== producer =============================================
+    // streams this CTA's half (N/2 rows) of every weight stage
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      const size_t member_bytes = (size_t)p.stages_per_member * STAGE_BYTES;
+      for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
+        const int split = unit % p.splits;
+        const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
+        const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
+        for (int k = mb; k < me; ++k) {
+          const uint8_t* src =
+              p.image + (p.shared_weights ? 0 : (size_t)(p.member_begin + k) * member_bytes) +
+              rank * HALF_BYTES;
+          for (int s = 0; s < p.stages_per_member; ++s) {
+            mbar_wait(bars + BAR_W_EMPTY + 8 * slot, phase ^ 1, p.error_flag, 1);
+            mbar_arrive_expect_tx(bars + BAR_W_FULL + 8 * slot, HALF_BYTES);
+            bulk_g2s(w_base + slot * HALF_BYTES, src, HALF_BYTES, bars + BAR_W_FULL + 8 * slot);
+            UQ_TRACE(0, 2, tr_it++);
+            src += STAGE_BYTES;
+            if (++slot == NS) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && !leader) {
+    // ===================================== peer relay ===========================================
+    // tells the leader's MMA warp that this CTA's half of a stage has landed
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      const uint32_t full0 = mapa_shared(bars + BAR_W_FULL, 0);
+      for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
+        const int split = unit % p.splits;
+        const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
+        const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
+        const int n_stages = (me - mb) * p.stages_per_member;
+        for (int s = 0; s < n_stages; ++s) {
+          mbar_wait(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 6);
+          mbar_arrive_cluster(full0 + 8 * slot);
+          if (++slot == NS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader) ===================================
+    // The whole warp walks the loop convergently; one elected lane issues tcgen05.mma / commit.
+    // Barrier probes run one stage ahead (a try_wait costs ~180 cycles even when the phase has
+    // already completed).
+    constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, NT);
+    const uint64_t a_desc0 = make_sw128_desc(a_base);
+    const uint64_t b_desc0 = make_sw128_desc(w_base);
+    const int k0_steps = p.K0 / 16;
+    uint32_t slot = 0, phase = 0;
+    uint32_t g = 0;      // layer-step counter (d_full / chunk phases)
+    uint32_t xm = 0;     // member counter (x_ready phase)
+    bool w_ready = mbar_try_wait_cluster(bars + BAR_W_FULL, 0);
+    uint32_t nslot = 0, nphase = 0;
+    bool w_ready_next = false;
+    auto acquire = [&]() {
+      if (!w_ready) mbar_wait_cluster_slow(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 4);
+      tc_fence_after();
+      nslot = slot + 1;
+      nphase = phase;
+      if (nslot == NS) { nslot = 0; nphase ^= 1; }
+      w_ready_next = mbar_try_wait_cluster(bars + BAR_W_FULL + 8 * nslot, nphase);
+    };
+    auto release = [&]() {
+      if (elect_one()) umma_commit_pair(bars + BAR_W_EMPTY + 8 * slot, 3);
+      slot = nslot;
+      phase = nphase;
+      w_ready = w_ready_next;
+    };
+    for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
+      const int split = unit % p.splits;
+      const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
+      const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
+      for (int k = mb; k < me; ++k, ++xm) {
+        // ---- layer 0: A = split input rows in chunk 0, K0 <= 64 --------------------------------
+        {
+          const uint32_t prev_par = (g - 1) & 1;
+          mbar_wait_cluster(bars + BAR_X_READY, xm & 1, p.error_flag, 2);
+#pragma unroll
+          for (int nh = 0; nh < NH; ++nh) {
+            if (g != 0) {  // accumulator half nh must have been drained by the previous epilogue
+              uint32_t ok = 0;
+#pragma unroll
+              for (int c = 0; c < KC; ++c)
+                if (c >= (nh == 0 ? 0 : G::hi(nh - 1) + 1) && c <= G::hi(nh))
+                  ok |= (mbar_try_wait_cluster(bars + BAR_CHUNK + 8 * c, prev_par) ? 1u : 0u) << c;
+#pragma unroll
+              for (int c = 0; c < KC; ++c)
+                if (c >= (nh == 0 ? 0 : G::hi(nh - 1) + 1) && c <= G::hi(nh))
+                  if (!((ok >> c) & 1u))
+                    mbar_wait_cluster_slow(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
+            }
+            acquire();
+            if (elect_one()) {
+              const uint64_t bd = b_desc0 + (uint64_t)((slot * HALF_BYTES) >> 4);
+              for (int ks = 0; ks < k0_steps; ++ks)
+                umma_bf16_pair(tmem_base + nh * NT, a_desc0 + 2 * ks, bd + 2 * ks, idesc,
+                               ks > 0 ? 1u : 0u);
+            }
+            release();
+          }
+          if (elect_one()) umma_commit_pair(bars + BAR_D_FULL, 3);
+          UQ_TRACE(1, 4, g);
+          ++g;
+        }
+        // ---- hidden layers: A = previous activations (in-place chunks), K = H ------------------
+        for (int l = 1; l < p.L_mma; ++l) {
+          const uint32_t prev_par = (g - 1) & 1;
+          {
+            uint32_t ok = 0;
+#pragma unroll
+            for (int c = 0; c <= G::hi(0); ++c)
+              ok |= (mbar_try_wait_cluster(bars + BAR_CHUNK + 8 * c, prev_par) ? 1u : 0u) << c;
+#pragma unroll
+            for (int c = 0; c <= G::hi(0); ++c)
+              if (!((ok >> c) & 1u))
+                mbar_wait_cluster_slow(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
+          }
+          bool c_ready = (G::hi(0) + 1 < KC)
+                             ? mbar_try_wait_cluster(bars + BAR_CHUNK + 8 * (G::hi(0) + 1), prev_par)
+                             : true;
+#pragma unroll
+          for (int nh = 0; nh < NH; ++nh) {
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+              if (nh == 0 && kc > G::hi(0)) {  // A chunk kc (and its accumulator columns)
+                if (!c_ready)
+                  mbar_wait_cluster_slow(bars + BAR_CHUNK + 8 * kc, prev_par, p.error_flag, 3);
+                if (kc + 1 < KC)
+                  c_ready = mbar_try_wait_cluster(bars + BAR_CHUNK + 8 * (kc + 1), prev_par);
+              }
+              UQ_TRACE(1, 1, tr_it);
+              acquire();
+              UQ_TRACE(1, 2, tr_it);
+              if (elect_one()) {
+                const uint64_t ad = a_desc0 + (uint64_t)((kc * CHUNK_BYTES) >> 4);
+                const uint64_t bd = b_desc0 + (uint64_t)((slot * HALF_BYTES) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < CHUNK_K / 16; ++ks)
+                  umma_bf16_pair(tmem_base + nh * NT, ad + 2 * ks, bd + 2 * ks, idesc,
+                                 (kc > 0 || ks > 0) ? 1u : 0u);
+              }
+              release();
+              UQ_TRACE(1, 3, tr_it++);
+            }
+          }
+          if (elect_one()) umma_commit_pair(bars + BAR_D_FULL, 3);  // whole layer accumulated
+          UQ_TRACE(1, 4, g);
+          ++g;
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue =============================================
+    const int ew = warp - 2;             // 0..7
+    const int et = threadIdx.x - 64;     // 0..255
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int hf = ew >> 2;              // column-chunk parity handled by this warp
+    const int row = q * 32 + lane;       // row of the tile == TMEM lane
+    const uint32_t a_row = a_base + (row >> 3) * 1024 + (row & 7) * 128;  // this row in chunk 0
+    const int rx = row & 7;
+    const uint32_t chunk_bar0 = mapa_shared(bars + BAR_CHUNK, 0);
+    const uint32_t xready_bar = mapa_shared(bars + BAR_X_READY, 0);
+    uint32_t g = 0;                      // layer-step counter
+    uint32_t mcount = 0;                 // members processed (exchange buffer parity)
+    constexpr int AUX_PER_THREAD = (G::AUX_FLOATS + EPI_THREADS - 1) / EPI_THREADS;
+
+    // writes the layer-0 A operand (split input row) into chunk 0, pieces [0, K0/8)
+    auto write_x = [&](int tile, int member_global) {
+      if (hf == 0) {
+        const int64_t grow = (int64_t)tile * TILE_M + row;
+        const int d = p.d_in;
+        int seg = 0, i = 0;
+        for (int piece = 0; piece < p.K0 / 8; ++piece) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int h2 = 0; h2 < 4; ++h2) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float out = 0.f;
+              if (seg < p.split_s) {
+                const float f = net_input2(p, grow, member_global, i);
+                const float hi = __bfloat162float(__float2bfloat16_rn(f));
+                out = (seg == 1) ? (f - hi) : hi;   // [hi | lo | hi]
+              }
+              v[e] = out;
+              if (++i == d) { i = 0; ++seg; }
+            }
+            w4[h2] = pack_bf16x2(v[0], v[1]);
+          }
+          st_shared_v4(a_row + (uint32_t)((piece ^ rx) << 4), w4[0], w4[1], w4[2], w4[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(xready_bar);
+      }
+    };
+
+    // bias (+ w_last when the step is the member's last) of a step, one step ahead in registers
+    float aux_pf[AUX_PER_THREAD];
+    auto aux_prefetch = [&](int member_global, int l) {
+      const int wslot = p.shared_weights ? 0 : member_global;
+      const bool last = (l == p.L_mma - 1);
+      const float* bias = p.bias[l] + (size_t)wslot * H;
+      const float* wl = p.w_last + (size_t)wslot * DOUT * H;
+#pragma unroll
+      for (int j = 0; j < AUX_PER_THREAD; ++j) {
+        const int i = et + j * EPI_THREADS;
+        float v = 0.f;
+        if (i < H) v = __ldg(bias + i);
+        else if (DOUT == 1 && last && i < 2 * H) v = __ldg(wl + (i - H));
+        aux_pf[j] = v;
+      }
+    };
+
+    bool first_step = true;
+    for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
+      const int tile = 2 * (unit / p.splits) + (int)rank, split = unit % p.splits;
+      const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
+      const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
+      const int64_t grow = (int64_t)tile * TILE_M + row;
+
+      float wf_n = 0.f, wf_mean[DOUT], wf_m2[DOUT];
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) wf_mean[o] = 0.f, wf_m2[o] = 0.f;
+
+      if (first_step) {  // very first member of this CTA
+        write_x(tile, p.member_begin + mb);
+        aux_prefetch(p.member_begin + mb, 0);
+        first_step = false;
+      }
+
+      for (int k = mb; k < me; ++k, ++mcount) {
+        const int kg = p.member_begin + k;                 // global member / pass id
+        const int wslot = p.shared_weights ? 0 : kg;
+        float dot[DOUT];
+#pragma unroll
+        for (int o = 0; o < DOUT; ++o) dot[o] = 0.f;
+        int drop_ord = 0;
+        const uint8_t* mask_layer = p.masks;
+
+        // coordinates of the member after this one (for x staging and the bias prefetch)
+        int nk = k + 1, ntile = tile;
+        bool have_next = true;
+        if (nk >= me) {
+          const int nunit = unit + n_clusters;
+          have_next = nunit < n_units;
+          ntile = 2 * (nunit / p.splits) + (int)rank;
+          nk = (int)(((int64_t)p.member_count * (nunit % p.splits)) / p.splits);
+        }
+
+        for (int l = 0; l < p.L_mma; ++l, ++g) {
+          const bool last = (l == p.L_mma - 1);
+          const bool relu = (p.relu_mask >> l) & 1u;
+          const bool has_drop = (p.dropout_mask >> l) & 1u;
+          const int drop = has_drop ? p.drop_mode : 0;
+
+          // ---- publish this step's bias (+ w_last) in smem, prefetch the next step's ------------
+          float* aux = aux_smem + (g & 1) * G::AUX_FLOATS;
+#pragma unroll
+          for (int j = 0; j < AUX_PER_THREAD; ++j) {
+            const int i = et + j * EPI_THREADS;
+            if (i < G::AUX_FLOATS) aux[i] = aux_pf[j];
+          }
+          epi_bar_sync();
+          if (!last) aux_prefetch(kg, l + 1);
+          else if (have_next) aux_prefetch(p.member_begin + nk, 0);
+
+          // one lane polls the layer barrier, the rest of the warp parks on the warp barrier
+          if (lane == 0) mbar_wait(bars + BAR_D_FULL, g & 1, p.error_flag, 5);
+          __syncwarp();
+          tc_fence_after();
+          if (warp == 2 && lane == 0) { UQ_TRACE(2, 1, g); }
+
+          // every MMA that reads the A chunks has retired: stage the next member's input rows
+          if (last && have_next) write_x(ntile, p.member_begin + nk);
+
+          DrainCtx cx;
+          cx.lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+          cx.a_row = a_row;
+          cx.rx = rx;
+          cx.hf = hf;
+          cx.lane = lane;
+          cx.chunk_bar0 = chunk_bar0;
+          cx.bias_s = aux;
+          cx.wl_s = aux + H;
+          cx.wl_g = p.w_last + (size_t)wslot * DOUT * H;
+          cx.drop = drop;
+          cx.kg = kg;
+          cx.drop_ord = drop_ord;
+          cx.grow = grow;
+          cx.mask_layer = mask_layer;
+          if (last) {
+            if (relu) {
+              if (drop) drain_step<H, DOUT, true, true, true>(p, cx, dot);
+              else drain_step<H, DOUT, true, false, true>(p, cx, dot);
+            } else {
+              if (drop) drain_step<H, DOUT, false, true, true>(p, cx, dot);
+              else drain_step<H, DOUT, false, false, true>(p, cx, dot);
+            }
+          } else {
+            if (relu) {
+              if (drop) drain_step<H, DOUT, true, true, false>(p, cx, dot);
+              else drain_step<H, DOUT, true, false, false>(p, cx, dot);
+            } else {
+              if (drop) drain_step<H, DOUT, false, true, false>(p, cx, dot);
+              else drain_step<H, DOUT, false, false, false>(p, cx, dot);
+            }
+          }
+          if (warp == 2 && lane == 0) { UQ_TRACE(2, 2, g); }
+          if (has_drop) {
+            if (p.masks) mask_layer += (size_t)p.total_members * (size_t)p.n * (size_t)H;
+            ++drop_ord;
+          }
+        }
+
+        // ---- combine the two column-parity halves of the dot products, then Welford ----------
+        const uint32_t xb = xchg + (uint32_t)(((mcount & 1) * TILE_M + row) * DOUT * 4);
+        if (KC > 1) {
+          if (hf == 1) {
+#pragma unroll
+            for (int o = 0; o < DOUT; ++o) st_shared_f32(xb + 4 * o, dot[o]);
+          }
+          epi_bar_sync();
+        }
+        if (hf == 0) {
+          wf_n += 1.f;
+          const float inv_n = 1.f / wf_n;
+          const float* bl = p.b_last + (size_t)wslot * DOUT;
+#pragma unroll
+          for (int o = 0; o < DOUT; ++o) {
+            float y = dot[o] + (KC > 1 ? ld_shared_f32(xb + 4 * o) : 0.f) + __ldg(bl + o);
+            if (p.last_relu) y = fmaxf(y, 0.f);
+            const float dlt = y - wf_mean[o];
+            wf_mean[o] += dlt * inv_n;
+            wf_m2[o] = fmaf(dlt, y - wf_mean[o], wf_m2[o]);
+          }
+        }
+      }
+
+      // ---- tile done: publish (mean, std) / (mean, M2) ------------------------------------------
+      if (hf == 0 && grow < p.n) {
+#pragma unroll
+        for (int o = 0; o < DOUT; ++o) {
+          if (o < p.d_out) {
+            const int64_t idx = grow * p.d_out + o;
+            if (p.splits > 1) {
+              p.part_mean[(size_t)split * (size_t)p.n * p.d_out + idx] = wf_mean[o];
+              p.part_m2[(size_t)split * (size_t)p.n * p.d_out + idx] = wf_m2[o];
+            } else {
+              p.out0[idx] = wf_mean[o];
+              p.out1[idx] =
+                  (p.output == UQ_OUT_MOMENTS) ? wf_m2[o] : sqrtf(wf_m2[o] / (wf_n - 1.f));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // both CTAs must be done with each other's shared / tensor memory before either leaves
+  __syncwarp();  // the single-lane roles rejoin their warp: cluster barriers are warp-aligned
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, (uint32_t)G::TMEM_COLS);
+  }
+}
+
+template <int H, int DOUT>
+int launch_tc2(const TcParams& p, cudaStream_t st) {
+  using G = Geo2<H, DOUT>;
+  auto kern = uq_mlp_tc2_kernel<H, DOUT>;
+  UQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t units = (int64_t)((p.n_tiles + 1) / 2) * p.splits;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = G::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // how many CTA pairs can be co-resident (one CTA per SM: the TMEM allocation is per pair)
+  int max_clusters = sms / 2;
+  cfg.gridDim = dim3((unsigned)sms, 1, 1);
+  int active = 0;
+  if (cudaOccupancyMaxActiveClusters(&active, kern, &cfg) == cudaSuccess && active > 0 &&
+      active < max_clusters)
+    max_clusters = active;
+  (void)cudaGetLastError();
+  const int clusters = (int)(units < (int64_t)max_clusters ? units : (int64_t)max_clusters);
+  cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+  UQ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  UQ_LAUNCH_CHECK();
+  return UQ_OK;
+}
+
+template <int DOUT>
+int dispatch_h2(int H, const TcParams& p, cudaStream_t st) {
+  switch (H) {
+    case 64: return launch_tc2<64, DOUT>(p, st);
+    case 128: return launch_tc2<128, DOUT>(p, st);
+    case 192: return launch_tc2<192, DOUT>(p, st);
+    case 256: return launch_tc2<256, DOUT>(p, st);
+    case 320: return launch_tc2<320, DOUT>(p, st);
+    case 384: return launch_tc2<384, DOUT>(p, st);
+    case 448: return launch_tc2<448, DOUT>(p, st);
+    case 512: return launch_tc2<512, DOUT>(p, st);
+  }
+  set_error("bf16 pair kernel: unsupported hidden width %d", H);
+  return UQ_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+bool tc2_supported(int hidden) { return hidden % 64 == 0 && hidden >= 64 && hidden <= 512; }
+
+int tc2_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st) {
+  return dout_pad == 1 ? dispatch_h2<1>(hidden, p, st) : dispatch_h2<tc::MAX_DOUT>(hidden, p, st);
+}
+
+}  // namespace uq

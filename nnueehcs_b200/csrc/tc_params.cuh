@@ -1,0 +1,54 @@
+// Launch parameters shared by the fused tcgen05 kernels (mlp_tc.cu, mlp_tc2.cu).
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace uq {
+namespace tc {
+
+constexpr int MAX_MMA_LAYERS = 16;
+constexpr int MAX_DOUT = 8;
+constexpr int TRACE_LEN = 4096;
+
+struct TcParams {
+  const float* x;        // [n][d_x]
+  int64_t n;
+  int d_x;               // features of x (d_in, or d_in/2 for Delta-UQ)
+  int d_in;              // network input features
+  int mode;
+  int n_tiles;
+  int splits;            // member-axis splits (partial moments when > 1)
+  int member_begin, member_count, total_members;
+  int K0, split_s, L_mma, d_out;
+  int stages_per_member;
+  int shared_weights;
+  const uint8_t* image;
+  const float* bias[MAX_MMA_LAYERS];  // [K or 1][H] folded bias per MMA layer
+  uint32_t relu_mask, dropout_mask;   // bit l: MMA layer l has ReLU / dropout on its output
+  const float* w_last;                // [K or 1][DOUT][H]  (zero rows beyond d_out)
+  const float* b_last;                // [K or 1][DOUT]
+  int last_relu;
+  int drop_mode;                      // 0 none, 1 injected, 2 philox
+  float drop_scale;
+  uint32_t thr16;
+  PhiloxKey key;
+  const uint8_t* masks;               // injected base
+  const float* anchors;               // [total_members][d_x]
+  float* out0;
+  float* out1;
+  int output;                         // UQ_OUT_*
+  float* part_mean;                   // [splits][n*d_out] when splits > 1
+  float* part_m2;
+  unsigned int* error_flag;
+  unsigned long long* trace;          // -DUQ_TC_TRACE builds only: [3 roles][TRACE_LEN][2] of CTA 0
+};
+
+}  // namespace tc
+
+// mlp_tc2.cu: CTA-pair (cta_group::2) variant of the fused kernel; same weight image
+int tc2_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st);
+bool tc2_supported(int hidden);
+
+}  // namespace uq
