@@ -389,7 +389,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "peak_source": peaks["source"], "kernel": "uq_mlp_tc_kernel"
+                         "peak_source": peaks["source"], "kernel": "uq_mlp_tc2_kernel (CTA pairs)"
                          if precision == "bf16" else "sgemm_tn_kernel (fp32 CUDA cores)",
                          "flops_per_unit": F, "kernel_ms": kernel_ms,
                          "frac_of_sustained": achieved / peaks["sustained"]},

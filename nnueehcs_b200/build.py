@@ -100,5 +100,11 @@ def _build_variant(suffix, extra_flags, verbose) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
-                trace="--trace" in sys.argv))
+    # bring-up variants: `--variant NAME -DFLAG ...` builds libnnueehcs_b200_NAME.so
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        os.makedirs(OUT_DIR, exist_ok=True)
+        print(_build_variant("_" + sys.argv[i + 1], sys.argv[i + 2:], False))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                    trace="--trace" in sys.argv))

@@ -836,8 +836,8 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   const char* trace_env = getenv("UQ_TC_TRACE_FILE");
   unsigned long long* d_trace = nullptr;
   if (trace_env && trace_env[0]) {
-    UQ_CUDA(cudaMalloc(&d_trace, 3 * TRACE_LEN * 2 * sizeof(unsigned long long)));
-    UQ_CUDA(cudaMemsetAsync(d_trace, 0, 3 * TRACE_LEN * 2 * sizeof(unsigned long long), st));
+    UQ_CUDA(cudaMalloc(&d_trace, TRACE_ROLES * TRACE_LEN * 2 * sizeof(unsigned long long)));
+    UQ_CUDA(cudaMemsetAsync(d_trace, 0, TRACE_ROLES * TRACE_LEN * 2 * sizeof(unsigned long long), st));
   }
   p.trace = d_trace;
 #endif
@@ -859,13 +859,13 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   if (rc != UQ_OK) return rc;
 #ifdef UQ_TC_TRACE
   if (d_trace) {  // bring-up aid: dump CTA 0's event timeline as CSV (role, kind, index, clock)
-    std::vector<unsigned long long> h(3 * TRACE_LEN * 2);
+    std::vector<unsigned long long> h(TRACE_ROLES * TRACE_LEN * 2);
     UQ_CUDA(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, st));
     UQ_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_trace);
     if (FILE* f = fopen(trace_env, "w")) {
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < TRACE_ROLES; ++r)
         for (int i = 0; i < TRACE_LEN; ++i) {
           const unsigned long long tag = h[((size_t)r * TRACE_LEN + i) * 2];
           if (tag) fprintf(f, "%d,%llu,%llu,%llu\n", r, tag >> 24, tag & 0xFFFFFF,

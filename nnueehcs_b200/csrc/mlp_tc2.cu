@@ -33,31 +33,57 @@
 #include "tc_params.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef UQ_TC_TWO_PHASE
+#define UQ_TC_TWO_PHASE 0
+#endif
+#ifndef UQ_ABLATE
+#define UQ_ABLATE 0   // bring-up builds: 1 no A write-back, 2 no proxy fence, 3 no TMEM loads, 4 no bias
+#endif
+
 namespace uq {
 
 namespace {
 
 using namespace tc;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
-constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
+#if UQ_ABLATE == 2
+#define fence_proxy_async_smem() ((void)0)
+#endif
+#if UQ_ABLATE == 3
+#define tmem_ld32(addr, r) do { for (int _i = 0; _i < 32; ++_i) r[_i] = (uint32_t)(addr) * (_i + 1); } while (0)
+#define tmem_ld16(addr, r) do { for (int _i = 0; _i < 16; ++_i) r[_i] = (uint32_t)(addr) * (_i + 1); } while (0)
+#define tmem_ld_wait() ((void)0)
+#endif
 constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
 
-template <int H, int DOUT>
+// NG = epilogue warp groups (4 warps each, one per TMEM lane quarter); group j drains the
+// activation chunks c with c % NG == j.
+template <int H, int DOUT, int NG>
 struct Geo2 {
+  static constexpr int EPI_THREADS = NG * 128;
+  static constexpr int NUM_THREADS = 64 + EPI_THREADS;
   static_assert(H % 64 == 0 && H >= 64 && H <= 512, "hidden width must be a multiple of 64 <= 512");
   static constexpr int KC = H / CHUNK_K;                 // activation chunks == K-chunks per layer
   static constexpr int NH = (H + 255) / 256;             // accumulator halves (MMA N <= 256)
   static constexpr int NT = H / NH;                      // MMA N of the pair
   static_assert(NT % 16 == 0, "MMA N must be a multiple of 16");
   static constexpr int TMEM_COLS = H <= 64 ? 64 : H <= 128 ? 128 : H <= 256 ? 256 : 512;
+  // Two-phase drain (see drain_half0): accumulator half 0 is drained into registers while the
+  // MMAs of half 1 still run.  Needs two halves whose boundary is a chunk boundary.  Measured on
+  // B200 (ensemble16x512_1M): 15.6 ms/step against 14.4 for the single-phase drain -- the
+  // overlapped epilogue competes with the MMA operand fetch for shared-memory bandwidth (stage
+  // period 470 -> 530..730 cycles) and pushes the chip into its power cap -- so it is off.
+  static constexpr bool TWO_PHASE = (UQ_TC_TWO_PHASE != 0) && (NH == 2) && (KC % 2 == 0);
+  static constexpr int C0 = TWO_PHASE ? KC / 2 : 0;      // chunks [0, C0) = accumulator half 0
+  static constexpr int NHELD = TWO_PHASE ? (C0 + NG - 1) / NG : 1;
   static constexpr int STAGE_BYTES = NT * 128;           // whole stage [NT x 64] bf16 in the image
   static constexpr int HALF_BYTES = STAGE_BYTES / 2;     // what one CTA of the pair loads
   static constexpr int A_BYTES = KC * CHUNK_BYTES;
   static constexpr int AUX_FLOATS = (DOUT == 1 ? 2 : 1) * H;   // bias [+ w_last] of one step
   static constexpr int AUX_BYTES = 2 * AUX_FLOATS * 4;         // double-buffered by step parity
-  static constexpr int XCHG_BYTES = 2 * TILE_M * DOUT * 4;
-  static constexpr int MISC_BYTES = 1024 /*align slack*/ + 256 /*barriers*/ + XCHG_BYTES;
+  static constexpr int XCHG_BYTES = 2 * (NG - 1) * TILE_M * DOUT * 4;
+  static constexpr int XS_BYTES = TILE_M * 64;   // stash of the next layer-0 A rows (K0 <= 32)
+  static constexpr int MISC_BYTES =
+      1024 /*align slack*/ + 256 /*barriers*/ + XCHG_BYTES + XS_BYTES;
   static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES;
   static constexpr int NS_RAW = BUDGET / HALF_BYTES;
   static constexpr int NSTAGES = NS_RAW > 8 ? 8 : NS_RAW;
@@ -73,6 +99,7 @@ constexpr uint32_t BAR_CHUNK = 128;      // 8 x 8 B   leader only: 4 warps of ea
 constexpr uint32_t BAR_D_FULL = 192;     //           commit multicast from the leader
 constexpr uint32_t BAR_X_READY = 200;    //           leader only: 4 warps of each CTA
 constexpr uint32_t BAR_TMEM_PTR = 208;
+constexpr uint32_t BAR_D_HALF = 216;     //           commit multicast: accumulator half 0 complete
 
 __device__ __forceinline__ float net_input2(const TcParams& p, int64_t row, int member_global,
                                             int i) {
@@ -112,16 +139,20 @@ __device__ __forceinline__ uint32_t keep_bits32(const TcParams& p, int drop, int
   return keep;
 }
 
-// One 32-column block of one accumulator row: + bias, ReLU, dropout, then either the bf16 A-operand
-// write-back (cvt.rn[.relu].bf16x2 + 4 x st.shared.v4) or the last-Linear dot product.
-template <int H, int DOUT, bool RELU, bool DROP, bool LAST>
-__device__ __forceinline__ void epi_block2(const uint32_t (&acc)[32], const float4 (&bv)[8],
-                                           uint32_t keep, float keep_scale, uint32_t a_dst,
-                                           int piece0, int rx, const float* __restrict__ wl_s,
-                                           const float* __restrict__ wl_g, float (&dot)[DOUT]) {
-  float v[32];
+// One NC-column block of one accumulator row: + bias, dropout, then either ReLU + bf16 rounding
+// into NC/2 packed words (cvt.rn[.relu].bf16x2) or the last-Linear dot product.
+template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST>
+__device__ __forceinline__ void epi_math(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
+                                         uint32_t keep, float keep_scale, uint32_t* packed,
+                                         const float* __restrict__ wl_s,
+                                         const float* __restrict__ wl_g, float (&dot)[DOUT]) {
+#if UQ_ABLATE == 5
+  if (LAST) { dot[0] += __uint_as_float(acc[0]) * 0.f; }
+  return;
+#endif
+  float v[NC];
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
     v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + bv[j4].x;
     v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + bv[j4].y;
     v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + bv[j4].z;
@@ -129,40 +160,35 @@ __device__ __forceinline__ void epi_block2(const uint32_t (&acc)[32], const floa
   }
   if (DROP) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
+    for (int j = 0; j < NC; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
   }
   if (!LAST) {
 #pragma unroll
-    for (int pc = 0; pc < 4; ++pc) {
-      uint32_t w4[4];
-#pragma unroll
-      for (int h2 = 0; h2 < 4; ++h2)
-        w4[h2] = RELU ? cvt_relu_bf16x2(v[pc * 8 + 2 * h2], v[pc * 8 + 2 * h2 + 1])
-                      : cvt_bf16x2(v[pc * 8 + 2 * h2], v[pc * 8 + 2 * h2 + 1]);
-      st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4), w4[0], w4[1], w4[2], w4[3]);
-    }
+    for (int j2 = 0; j2 < NC / 2; ++j2)
+      packed[j2] = RELU ? cvt_relu_bf16x2(v[2 * j2], v[2 * j2 + 1]) : cvt_bf16x2(v[2 * j2], v[2 * j2 + 1]);
   } else {
     if (RELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     if (DOUT == 1) {
-      float s = dot[0];
+      // four independent FMA chains (a single one is latency-bound: 4 cycles x 64 per chunk)
+      float s0 = dot[0], s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
+      for (int j4 = 0; j4 < NC / 4; ++j4) {
         const float4 wv = reinterpret_cast<const float4*>(wl_s)[j4];
-        s = fmaf(v[j4 * 4 + 0], wv.x, s);
-        s = fmaf(v[j4 * 4 + 1], wv.y, s);
-        s = fmaf(v[j4 * 4 + 2], wv.z, s);
-        s = fmaf(v[j4 * 4 + 3], wv.w, s);
+        s0 = fmaf(v[j4 * 4 + 0], wv.x, s0);
+        s1 = fmaf(v[j4 * 4 + 1], wv.y, s1);
+        s2 = fmaf(v[j4 * 4 + 2], wv.z, s2);
+        s3 = fmaf(v[j4 * 4 + 3], wv.w, s3);
       }
-      dot[0] = s;
+      dot[0] = (s0 + s1) + (s2 + s3);
     } else {
 #pragma unroll
       for (int o = 0; o < DOUT; ++o) {
         float s = dot[o];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
+        for (int j4 = 0; j4 < NC / 4; ++j4) {
           const float4 wv = __ldg(reinterpret_cast<const float4*>(wl_g + o * H) + j4);
           s = fmaf(v[j4 * 4 + 0], wv.x, s);
           s = fmaf(v[j4 * 4 + 1], wv.y, s);
@@ -175,11 +201,43 @@ __device__ __forceinline__ void epi_block2(const uint32_t (&acc)[32], const floa
   }
 }
 
+// NW packed words (NW/4 16-byte pieces starting at piece0) -> this row of a swizzled A chunk
+template <int NW>
+__device__ __forceinline__ void epi_store(const uint32_t* packed, uint32_t a_dst, int piece0,
+                                          int rx) {
+#pragma unroll
+  for (int pc = 0; pc < NW / 4; ++pc) {
+#if UQ_ABLATE != 1
+    st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4), packed[pc * 4 + 0],
+                 packed[pc * 4 + 1], packed[pc * 4 + 2], packed[pc * 4 + 3]);
+#else
+    if (packed[pc * 4] == 0x12345678u && packed[pc * 4 + 1] == packed[pc * 4 + 2])
+      st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4), packed[pc * 4 + 0],
+                   packed[pc * 4 + 1], packed[pc * 4 + 2], packed[pc * 4 + 3]);
+#endif
+  }
+}
+
+template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST>
+__device__ __forceinline__ void epi_block2(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
+                                           uint32_t keep, float keep_scale, uint32_t a_dst,
+                                           int piece0, int rx, const float* __restrict__ wl_s,
+                                           const float* __restrict__ wl_g, float (&dot)[DOUT]) {
+  uint32_t packed[NC / 2];
+  epi_math<H, DOUT, NC, RELU, DROP, LAST>(acc, bv, keep, keep_scale, packed, wl_s, wl_g, dot);
+  if (!LAST) epi_store<NC / 2>(packed, a_dst, piece0, rx);
+}
+
+template <int THREADS>
+__device__ __forceinline__ void epi_bar_sync_n() {
+  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+}
+
 struct DrainCtx {
   uint32_t lane_addr;      // TMEM address of this warp's lane quarter, column 0
   uint32_t a_row;          // smem address of this row inside chunk 0
   int rx;                  // row & 7
-  int hf;                  // chunk parity handled by this warp
+  int grp;                 // warp group: drains chunks c with c % NG == grp
   int lane;
   uint32_t chunk_bar0;     // cluster address of the leader's chunk barrier 0
   const float* bias_s;     // staged bias of this step (shared)
@@ -189,54 +247,178 @@ struct DrainCtx {
   int kg, drop_ord;
   int64_t grow;
   const uint8_t* mask_layer;
+#ifdef UQ_TC_TRACE
+  unsigned long long* tr;  // this thread's trace slots (or nullptr)
+  int* tr_n;
+  unsigned g;
+#endif
 };
 
-// Drain this warp's chunks of one layer-step; TMEM loads run one 32-column block ahead.
-template <int H, int DOUT, bool RELU, bool DROP, bool LAST>
-__device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx,
+#ifdef UQ_TC_TRACE
+__device__ __forceinline__ void drain_trace(const DrainCtx& cx, unsigned kind, unsigned c) {
+  if (cx.tr != nullptr && *cx.tr_n < TRACE_LEN) {
+    unsigned long long* t = cx.tr + (size_t)(*cx.tr_n) * 2;
+    t[0] = ((unsigned long long)kind << 24) | (cx.g << 4) | c;
+    t[1] = (unsigned long long)clock64();
+    ++*cx.tr_n;
+  }
+}
+#define UQ_DTRACE(kind, c) drain_trace(cx, kind, c)
+#else
+#define UQ_DTRACE(kind, c)
+#endif
+
+// ---- two-phase drain ------------------------------------------------------------------------------
+// The next layer cannot start before the chunks of accumulator half 0 are drained and rewritten,
+// and they cannot be rewritten in place before every MMA of this layer has read them -- with a
+// single-phase drain the tensor core idles for the whole first half of the epilogue (~2500 cycles
+// per layer at H = 512).  So half 0 is drained as soon as ITS MMAs retire (BAR_D_HALF), while the
+// MMAs of half 1 still run: bias/ReLU/rounding happen then and the packed bf16 rows wait in
+// registers (32 words per chunk).  When the layer completes (BAR_D_FULL) only the st.shared burst,
+// one proxy fence and the barrier arrivals are left on the critical path.
+template <int H, int DOUT, int NG, bool RELU, bool DROP, bool LAST>
+__device__ __forceinline__ void drain_half0(const TcParams& p, const DrainCtx& cx,
+                                            uint32_t* held, float (&dot)[DOUT]) {
+  using G = Geo2<H, DOUT, NG>;
+#pragma unroll
+  for (int i = 0; i < G::NHELD; ++i) {
+    const int c = cx.grp + i * NG;
+    if (c < G::C0) {
+      uint32_t keep32 = 0xffffffffu;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {   // 16-column blocks: phase 1 is off the critical path, and
+        const int col0 = c * CHUNK_K + 16 * b;   // the held rows leave few registers to work in
+        uint32_t acc[16];
+        tmem_ld16(cx.lane_addr + (uint32_t)col0, acc);
+        float4 bv[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
+        if (DROP && (b & 1) == 0)
+          keep32 = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
+        tmem_ld_wait();
+        epi_math<H, DOUT, 16, RELU, DROP, LAST>(acc, bv, keep32 >> (16 * (b & 1)), p.drop_scale,
+                                                held + i * 32 + b * 8, cx.wl_s + col0,
+                                                cx.wl_g + col0, dot);
+      }
+    }
+  }
+}
+
+template <int H, int DOUT, int NG, bool LAST>
+__device__ __forceinline__ void flush_half0(const DrainCtx& cx, const uint32_t* held) {
+  using G = Geo2<H, DOUT, NG>;
+  if (!LAST) {
+#pragma unroll
+    for (int i = 0; i < G::NHELD; ++i) {
+      const int c = cx.grp + i * NG;
+      if (c < G::C0) epi_store<32>(held + i * 32, cx.a_row + (uint32_t)c * CHUNK_BYTES, 0, cx.rx);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (cx.lane == 0) {
+#pragma unroll
+    for (int i = 0; i < G::NHELD; ++i) {
+      const int c = cx.grp + i * NG;
+      if (c < G::C0) mbar_arrive_cluster(cx.chunk_bar0 + 8 * c);
+    }
+  }
+}
+
+// Drain this warp's chunks of one layer-step.  NG == 2: 8 epilogue warps, TMEM loads run one
+// 32-column block ahead in a second register buffer.  NG == 4: 16 epilogue warps (4 per
+// scheduler) hide the tcgen05.ld / LDS latencies by thread-level parallelism instead, within the
+// 112-register budget that 18 warps leave.
+template <int H, int DOUT, int NG, bool RELU, bool DROP, bool LAST>
+__device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx, int c_begin,
                                            float (&dot)[DOUT]) {
   constexpr int KC = H / CHUNK_K;
-  uint32_t acc0[32], acc1[32];
-  if (cx.hf < KC) tmem_ld32(cx.lane_addr + (uint32_t)(cx.hf * CHUNK_K), acc0);
+  if (NG == 2) {
+    uint32_t acc0[32], acc1[32];
+    if (c_begin < KC) tmem_ld32(cx.lane_addr + (uint32_t)(c_begin * CHUNK_K), acc0);
 #pragma unroll 1
-  for (int c = cx.hf; c < KC; c += 2) {
-    const int col0 = c * CHUNK_K;
-    const uint32_t a_dst = cx.a_row + (uint32_t)c * CHUNK_BYTES;
-    uint32_t keep = 0xffffffffu;
-    float4 bv[8];
-    // ---- block 0 (columns col0 .. col0+31) ----
+    for (int c = c_begin; c < KC; c += NG) {
+      const int col0 = c * CHUNK_K;
+      const uint32_t a_dst = cx.a_row + (uint32_t)c * CHUNK_BYTES;
+      uint32_t keep = 0xffffffffu;
+      float4 bv[8];
+      // ---- block 0 (columns col0 .. col0+31) ----
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
-    if (DROP) keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
-    tmem_ld_wait();
-    tmem_ld32(cx.lane_addr + (uint32_t)(col0 + 32), acc1);
-    epi_block2<H, DOUT, RELU, DROP, LAST>(acc0, bv, keep, p.drop_scale, a_dst, 0, cx.rx,
-                                          cx.wl_s + col0, cx.wl_g + col0, dot);
-    // ---- block 1 (columns col0+32 .. col0+63) ----
+      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
+#if UQ_ABLATE == 4
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4)
-      bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0 + 32)[j4];
-    if (DROP)
-      keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0 + 32, cx.mask_layer, H);
-    tmem_ld_wait();
-    if (c + 2 < KC) tmem_ld32(cx.lane_addr + (uint32_t)(col0 + 2 * CHUNK_K), acc0);
-    epi_block2<H, DOUT, RELU, DROP, LAST>(acc1, bv, keep, p.drop_scale, a_dst, 4, cx.rx,
-                                          cx.wl_s + col0 + 32, cx.wl_g + col0 + 32, dot);
-    // chunk c: accumulator columns drained (+ A chunk rewritten) -> release to the MMA warp
-    tc_fence_before();
-    if (!LAST) fence_proxy_async_smem();
-    __syncwarp();
-    if (cx.lane == 0) mbar_arrive_cluster(cx.chunk_bar0 + 8 * c);
+      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
+      if (DROP) keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
+      UQ_DTRACE(10, c);
+      tmem_ld_wait();
+      UQ_DTRACE(11, c);
+      tmem_ld32(cx.lane_addr + (uint32_t)(col0 + 32), acc1);
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep, p.drop_scale, a_dst, 0, cx.rx,
+                                            cx.wl_s + col0, cx.wl_g + col0, dot);
+      UQ_DTRACE(12, c);
+      // ---- block 1 (columns col0+32 .. col0+63) ----
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0 + 32)[j4];
+#if UQ_ABLATE == 4
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
+      if (DROP)
+        keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0 + 32, cx.mask_layer, H);
+      tmem_ld_wait();
+      if (c + NG < KC) tmem_ld32(cx.lane_addr + (uint32_t)(col0 + NG * CHUNK_K), acc0);
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep, p.drop_scale, a_dst, 4, cx.rx,
+                                            cx.wl_s + col0 + 32, cx.wl_g + col0 + 32, dot);
+      UQ_DTRACE(13, c);
+      // chunk c: accumulator columns drained (+ A chunk rewritten) -> release to the MMA warp
+      tc_fence_before();
+      if (!LAST) fence_proxy_async_smem();
+      UQ_DTRACE(14, c);
+      __syncwarp();
+      if (cx.lane == 0) mbar_arrive_cluster(cx.chunk_bar0 + 8 * c);
+      UQ_DTRACE(15, c);
+    }
+  } else {
+#pragma unroll 1
+    for (int c = c_begin; c < KC; c += NG) {
+      const uint32_t a_dst = cx.a_row + (uint32_t)c * CHUNK_BYTES;
+      uint32_t keep32 = 0xffffffffu;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int col0 = c * CHUNK_K + 16 * b;
+        uint32_t acc[16];
+        tmem_ld16(cx.lane_addr + (uint32_t)col0, acc);
+        float4 bv[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
+        if (DROP && (b & 1) == 0)
+          keep32 = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
+        tmem_ld_wait();
+        epi_block2<H, DOUT, 16, RELU, DROP, LAST>(acc, bv, keep32 >> (16 * (b & 1)), p.drop_scale,
+                                                  a_dst, 2 * b, cx.rx, cx.wl_s + col0,
+                                                  cx.wl_g + col0, dot);
+      }
+      tc_fence_before();
+      if (!LAST) fence_proxy_async_smem();
+      __syncwarp();
+      if (cx.lane == 0) mbar_arrive_cluster(cx.chunk_bar0 + 8 * c);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // the fused kernel (one cluster = two CTAs = two sample tiles)
 // ------------------------------------------------------------------------------------------------
-template <int H, int DOUT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int H, int DOUT, int NG>
+__global__ void __launch_bounds__(Geo2<H, DOUT, NG>::NUM_THREADS, 1)
 uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
-  using G = Geo2<H, DOUT>;
+  using G = Geo2<H, DOUT, NG>;
+  constexpr int EPI_THREADS = G::EPI_THREADS;
   constexpr int KC = G::KC, NH = G::NH, NT = G::NT, NS = G::NSTAGES;
   constexpr uint32_t STAGE_BYTES = G::STAGE_BYTES, HALF_BYTES = G::HALF_BYTES;
 
@@ -249,7 +431,8 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
   uint8_t* w_smem = smem + G::A_BYTES;                     // NS half-stages
   float* aux_smem = reinterpret_cast<float*>(w_smem + NS * HALF_BYTES);  // [2][AUX_FLOATS]
   uint8_t* bar_smem = reinterpret_cast<uint8_t*>(aux_smem) + G::AUX_BYTES;
-  const uint32_t xchg = smem_u32(bar_smem + 256);          // [2][128][DOUT] dot exchange (floats)
+  const uint32_t xchg = smem_u32(bar_smem + 256);  // [2][NG-1][128][DOUT] dot exchange (floats)
+  const uint32_t xstash = xchg + G::XCHG_BYTES;    // [K0/8 pieces][128 rows] x 16 B
   const uint32_t a_base = smem_u32(a_smem);
   const uint32_t w_base = smem_u32(w_smem);
   const uint32_t bars = smem_u32(bar_smem);
@@ -263,7 +446,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
 #ifdef UQ_TC_TRACE
   int tr_n = 0;
   auto trace = [&](int role, unsigned kind, unsigned idx) {
-    if (p.trace != nullptr && blockIdx.x == 0 && tr_n < TRACE_LEN && (role != 1 || lane == 0)) {
+    if (p.trace != nullptr && blockIdx.x < 2 && tr_n < TRACE_LEN && (role != 1 || lane == 0)) {
       unsigned long long* t = p.trace + ((size_t)role * TRACE_LEN + tr_n) * 2;
       t[0] = ((unsigned long long)kind << 24) | idx;
       t[1] = (unsigned long long)clock64();
@@ -284,6 +467,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     }
     for (int c = 0; c < KC; ++c) mbar_init(bars + BAR_CHUNK + 8 * c, 8);
     mbar_init(bars + BAR_D_FULL, 1);
+    mbar_init(bars + BAR_D_HALF, 1);
     mbar_init(bars + BAR_X_READY, 8);
     fence_barrier_init();
   }
@@ -311,7 +495,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
             mbar_wait(bars + BAR_W_EMPTY + 8 * slot, phase ^ 1, p.error_flag, 1);
             mbar_arrive_expect_tx(bars + BAR_W_FULL + 8 * slot, HALF_BYTES);
             bulk_g2s(w_base + slot * HALF_BYTES, src, HALF_BYTES, bars + BAR_W_FULL + 8 * slot);
-            UQ_TRACE(0, 2, tr_it++);
+            if (leader) { UQ_TRACE(0, 2, tr_it++); }
             src += STAGE_BYTES;
             if (++slot == NS) { slot = 0; phase ^= 1; }
           }
@@ -332,6 +516,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
         for (int s = 0; s < n_stages; ++s) {
           mbar_wait(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 6);
           mbar_arrive_cluster(full0 + 8 * slot);
+          UQ_TRACE(5, 1, tr_it++);
           if (++slot == NS) { slot = 0; phase ^= 1; }
         }
       }
@@ -352,7 +537,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     uint32_t nslot = 0, nphase = 0;
     bool w_ready_next = false;
     auto acquire = [&]() {
-      if (!w_ready) mbar_wait_cluster_slow(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 4);
+      if (!w_ready) mbar_wait_cluster_inline(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 4);
       tc_fence_after();
       nslot = slot + 1;
       nphase = phase;
@@ -386,7 +571,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
               for (int c = 0; c < KC; ++c)
                 if (c >= (nh == 0 ? 0 : G::hi(nh - 1) + 1) && c <= G::hi(nh))
                   if (!((ok >> c) & 1u))
-                    mbar_wait_cluster_slow(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
+                    mbar_wait_cluster_inline(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
             }
             acquire();
             if (elect_one()) {
@@ -396,6 +581,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
                                ks > 0 ? 1u : 0u);
             }
             release();
+            if (G::TWO_PHASE && nh == 0 && elect_one()) umma_commit_pair(bars + BAR_D_HALF, 3);
           }
           if (elect_one()) umma_commit_pair(bars + BAR_D_FULL, 3);
           UQ_TRACE(1, 4, g);
@@ -412,8 +598,10 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int c = 0; c <= G::hi(0); ++c)
               if (!((ok >> c) & 1u))
-                mbar_wait_cluster_slow(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
+                mbar_wait_cluster_inline(bars + BAR_CHUNK + 8 * c, prev_par, p.error_flag, 3);
           }
+          if (!w_ready) w_ready = mbar_try_wait_cluster(bars + BAR_W_FULL + 8 * slot, phase);
+          UQ_TRACE(1, 5, g);
           bool c_ready = (G::hi(0) + 1 < KC)
                              ? mbar_try_wait_cluster(bars + BAR_CHUNK + 8 * (G::hi(0) + 1), prev_par)
                              : true;
@@ -423,7 +611,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
             for (int kc = 0; kc < KC; ++kc) {
               if (nh == 0 && kc > G::hi(0)) {  // A chunk kc (and its accumulator columns)
                 if (!c_ready)
-                  mbar_wait_cluster_slow(bars + BAR_CHUNK + 8 * kc, prev_par, p.error_flag, 3);
+                  mbar_wait_cluster_inline(bars + BAR_CHUNK + 8 * kc, prev_par, p.error_flag, 3);
                 if (kc + 1 < KC)
                   c_ready = mbar_try_wait_cluster(bars + BAR_CHUNK + 8 * (kc + 1), prev_par);
               }
@@ -441,6 +629,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
               release();
               UQ_TRACE(1, 3, tr_it++);
             }
+            if (G::TWO_PHASE && nh == 0 && elect_one()) umma_commit_pair(bars + BAR_D_HALF, 3);
           }
           if (elect_one()) umma_commit_pair(bars + BAR_D_FULL, 3);  // whole layer accumulated
           UQ_TRACE(1, 4, g);
@@ -450,10 +639,10 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     }
   } else {
     // ===================================== epilogue =============================================
-    const int ew = warp - 2;             // 0..7
-    const int et = threadIdx.x - 64;     // 0..255
+    const int ew = warp - 2;             // 0 .. 4 NG - 1
+    const int et = threadIdx.x - 64;     // 0 .. EPI_THREADS - 1
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int hf = ew >> 2;              // column-chunk parity handled by this warp
+    const int grp = ew >> 2;             // warp group: chunks c with c % NG == grp
     const int row = q * 32 + lane;       // row of the tile == TMEM lane
     const uint32_t a_row = a_base + (row >> 3) * 1024 + (row & 7) * 128;  // this row in chunk 0
     const int rx = row & 7;
@@ -463,9 +652,14 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     uint32_t mcount = 0;                 // members processed (exchange buffer parity)
     constexpr int AUX_PER_THREAD = (G::AUX_FLOATS + EPI_THREADS - 1) / EPI_THREADS;
 
-    // writes the layer-0 A operand (split input row) into chunk 0, pieces [0, K0/8)
-    auto write_x = [&](int tile, int member_global) {
-      if (hf == 0) {
+    // Layer-0 A operand (this row's split input [x_hi | x_lo | x_hi], K0 bf16) of one member.
+    // Building it needs uncoalesced global reads and a generic packing loop (thousands of cycles),
+    // so it is prepared off the critical path in a shared-memory stash -- once per tile, or once
+    // per member for Delta-UQ whose input depends on the anchor -- and copied into chunk 0 with
+    // K0/8 LDS/STS pairs at the moment the chunk becomes free.
+    const bool use_stash = p.K0 <= 32;
+    auto build_x = [&](int tile, int member_global, bool to_stash) {
+      if (grp == 0) {
         const int64_t grow = (int64_t)tile * TILE_M + row;
         const int d = p.d_in;
         int seg = 0, i = 0;
@@ -487,7 +681,25 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
             }
             w4[h2] = pack_bf16x2(v[0], v[1]);
           }
-          st_shared_v4(a_row + (uint32_t)((piece ^ rx) << 4), w4[0], w4[1], w4[2], w4[3]);
+          st_shared_v4(to_stash ? xstash + (uint32_t)((piece * TILE_M + row) << 4)
+                                : a_row + (uint32_t)((piece ^ rx) << 4),
+                       w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
+    };
+    // chunk 0 <- stash (or built in place when the stash is too small), then signal the MMA warp
+    auto publish_x = [&](int tile, int member_global) {
+      if (grp == 0) {
+        if (use_stash) {
+          for (int piece = 0; piece < p.K0 / 8; ++piece) {
+            uint32_t a, b, c, d;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                         : "r"(xstash + (uint32_t)((piece * TILE_M + row) << 4)));
+            st_shared_v4(a_row + (uint32_t)((piece ^ rx) << 4), a, b, c, d);
+          }
+        } else {
+          build_x(tile, member_global, false);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -524,7 +736,8 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
       for (int o = 0; o < DOUT; ++o) wf_mean[o] = 0.f, wf_m2[o] = 0.f;
 
       if (first_step) {  // very first member of this CTA
-        write_x(tile, p.member_begin + mb);
+        if (use_stash) build_x(tile, p.member_begin + mb, true);
+        publish_x(tile, p.member_begin + mb);
         aux_prefetch(p.member_begin + mb, 0);
         first_step = false;
       }
@@ -554,6 +767,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           const bool has_drop = (p.dropout_mask >> l) & 1u;
           const int drop = has_drop ? p.drop_mode : 0;
 
+          if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 0, g); }
           // ---- publish this step's bias (+ w_last) in smem, prefetch the next step's ------------
           float* aux = aux_smem + (g & 1) * G::AUX_FLOATS;
 #pragma unroll
@@ -561,24 +775,19 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
             const int i = et + j * EPI_THREADS;
             if (i < G::AUX_FLOATS) aux[i] = aux_pf[j];
           }
-          epi_bar_sync();
+          epi_bar_sync_n<EPI_THREADS>();
           if (!last) aux_prefetch(kg, l + 1);
           else if (have_next) aux_prefetch(p.member_begin + nk, 0);
-
-          // one lane polls the layer barrier, the rest of the warp parks on the warp barrier
-          if (lane == 0) mbar_wait(bars + BAR_D_FULL, g & 1, p.error_flag, 5);
-          __syncwarp();
-          tc_fence_after();
-          if (warp == 2 && lane == 0) { UQ_TRACE(2, 1, g); }
-
-          // every MMA that reads the A chunks has retired: stage the next member's input rows
-          if (last && have_next) write_x(ntile, p.member_begin + nk);
+          // refresh the x stash while the last layer's MMAs run (its previous content went into
+          // chunk 0 one member ago)
+          if (last && have_next && use_stash && (p.mode == UQ_MODE_DELTA_UQ || ntile != tile))
+            build_x(ntile, p.member_begin + nk, true);
 
           DrainCtx cx;
           cx.lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
           cx.a_row = a_row;
           cx.rx = rx;
-          cx.hf = hf;
+          cx.grp = grp;
           cx.lane = lane;
           cx.chunk_bar0 = chunk_bar0;
           cx.bias_s = aux;
@@ -589,46 +798,96 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           cx.drop_ord = drop_ord;
           cx.grow = grow;
           cx.mask_layer = mask_layer;
-          if (last) {
-            if (relu) {
-              if (drop) drain_step<H, DOUT, true, true, true>(p, cx, dot);
-              else drain_step<H, DOUT, true, false, true>(p, cx, dot);
-            } else {
-              if (drop) drain_step<H, DOUT, false, true, true>(p, cx, dot);
-              else drain_step<H, DOUT, false, false, true>(p, cx, dot);
-            }
-          } else {
-            if (relu) {
-              if (drop) drain_step<H, DOUT, true, true, false>(p, cx, dot);
-              else drain_step<H, DOUT, true, false, false>(p, cx, dot);
-            } else {
-              if (drop) drain_step<H, DOUT, false, true, false>(p, cx, dot);
-              else drain_step<H, DOUT, false, false, false>(p, cx, dot);
-            }
+#ifdef UQ_TC_TRACE
+          {
+            const int role = (lane == 0 && (warp == 2 || (warp == 6 && leader)))
+                                 ? (leader ? (warp == 2 ? 2 : 3) : 4) : -1;
+            cx.tr = (role >= 0 && p.trace != nullptr && blockIdx.x < 2)
+                        ? p.trace + (size_t)role * TRACE_LEN * 2 : nullptr;
+            cx.tr_n = &tr_n;
+            cx.g = g;
           }
-          if (warp == 2 && lane == 0) { UQ_TRACE(2, 2, g); }
+#endif
+#define UQ_STEP_DISPATCH(CALL_TTT, CALL_TFT, CALL_FTT, CALL_FFT, CALL_TTF, CALL_TFF, CALL_FTF, CALL_FFF) \
+  if (last) {                                                                                      \
+    if (relu) { if (drop) { CALL_TTT; } else { CALL_TFT; } }                                       \
+    else { if (drop) { CALL_FTT; } else { CALL_FFT; } }                                            \
+  } else {                                                                                         \
+    if (relu) { if (drop) { CALL_TTF; } else { CALL_TFF; } }                                       \
+    else { if (drop) { CALL_FTF; } else { CALL_FFF; } }                                            \
+  }
+          uint32_t held[G::NHELD * 32];
+          if (G::TWO_PHASE) {
+            // ---- phase 1: accumulator half 0 -> registers while half 1 is still accumulating --
+            if (lane == 0) mbar_wait(bars + BAR_D_HALF, g & 1, p.error_flag, 7);
+            __syncwarp();
+            tc_fence_after();
+            if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 3, g); }
+            UQ_STEP_DISPATCH((drain_half0<H, DOUT, NG, true, true, true>(p, cx, held, dot)),
+                             (drain_half0<H, DOUT, NG, true, false, true>(p, cx, held, dot)),
+                             (drain_half0<H, DOUT, NG, false, true, true>(p, cx, held, dot)),
+                             (drain_half0<H, DOUT, NG, false, false, true>(p, cx, held, dot)),
+                             (drain_half0<H, DOUT, NG, true, true, false>(p, cx, held, dot)),
+                             (drain_half0<H, DOUT, NG, true, false, false>(p, cx, held, dot)),
+                             (drain_half0<H, DOUT, NG, false, true, false>(p, cx, held, dot)),
+                             (drain_half0<H, DOUT, NG, false, false, false>(p, cx, held, dot)))
+            if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 4, g); }
+          }
+
+          // one lane polls the layer barrier, the rest of the warp parks on the warp barrier
+          if (lane == 0) mbar_wait(bars + BAR_D_FULL, g & 1, p.error_flag, 5);
+          __syncwarp();
+          tc_fence_after();
+          if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 1, g); }
+
+          // every MMA that reads the A chunks has retired: stage the next member's input rows
+          if (last && have_next) publish_x(ntile, p.member_begin + nk);
+
+          if (G::TWO_PHASE) {
+            // ---- phase 2: store the held rows, release half 0 to the MMA warp ------------------
+            if (last) flush_half0<H, DOUT, NG, true>(cx, held);
+            else flush_half0<H, DOUT, NG, false>(cx, held);
+            if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 5, g); }
+          }
+          // ---- phase 3: remaining chunks, straight from tensor memory --------------------------
+          const int c_begin = G::C0 + (((grp - G::C0) % NG) + NG) % NG;
+          UQ_STEP_DISPATCH((drain_step<H, DOUT, NG, true, true, true>(p, cx, c_begin, dot)),
+                           (drain_step<H, DOUT, NG, true, false, true>(p, cx, c_begin, dot)),
+                           (drain_step<H, DOUT, NG, false, true, true>(p, cx, c_begin, dot)),
+                           (drain_step<H, DOUT, NG, false, false, true>(p, cx, c_begin, dot)),
+                           (drain_step<H, DOUT, NG, true, true, false>(p, cx, c_begin, dot)),
+                           (drain_step<H, DOUT, NG, true, false, false>(p, cx, c_begin, dot)),
+                           (drain_step<H, DOUT, NG, false, true, false>(p, cx, c_begin, dot)),
+                           (drain_step<H, DOUT, NG, false, false, false>(p, cx, c_begin, dot)))
+          if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 2, g); }
           if (has_drop) {
             if (p.masks) mask_layer += (size_t)p.total_members * (size_t)p.n * (size_t)H;
             ++drop_ord;
           }
         }
 
-        // ---- combine the two column-parity halves of the dot products, then Welford ----------
-        const uint32_t xb = xchg + (uint32_t)(((mcount & 1) * TILE_M + row) * DOUT * 4);
-        if (KC > 1) {
-          if (hf == 1) {
+        // ---- combine the groups' partial dot products, then Welford ---------------------------
+        constexpr int NPART = (KC < NG ? KC : NG) - 1;   // groups other than 0 that hold a part
+        const uint32_t xb = xchg + (uint32_t)((mcount & 1) * (NG - 1) * TILE_M * DOUT * 4);
+        if (NPART > 0) {
+          if (grp >= 1 && grp <= NPART) {
 #pragma unroll
-            for (int o = 0; o < DOUT; ++o) st_shared_f32(xb + 4 * o, dot[o]);
+            for (int o = 0; o < DOUT; ++o)
+              st_shared_f32(xb + (uint32_t)((((grp - 1) * TILE_M + row) * DOUT + o) * 4), dot[o]);
           }
-          epi_bar_sync();
+          epi_bar_sync_n<EPI_THREADS>();
         }
-        if (hf == 0) {
+        if (grp == 0) {
           wf_n += 1.f;
           const float inv_n = 1.f / wf_n;
           const float* bl = p.b_last + (size_t)wslot * DOUT;
 #pragma unroll
           for (int o = 0; o < DOUT; ++o) {
-            float y = dot[o] + (KC > 1 ? ld_shared_f32(xb + 4 * o) : 0.f) + __ldg(bl + o);
+            float y = dot[o];
+#pragma unroll
+            for (int j = 0; j < NPART; ++j)
+              y += ld_shared_f32(xb + (uint32_t)(((j * TILE_M + row) * DOUT + o) * 4));
+            y += __ldg(bl + o);
             if (p.last_relu) y = fmaxf(y, 0.f);
             const float dlt = y - wf_mean[o];
             wf_mean[o] += dlt * inv_n;
@@ -638,7 +897,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
       }
 
       // ---- tile done: publish (mean, std) / (mean, M2) ------------------------------------------
-      if (hf == 0 && grow < p.n) {
+      if (grp == 0 && grow < p.n) {
 #pragma unroll
         for (int o = 0; o < DOUT; ++o) {
           if (o < p.d_out) {
@@ -667,10 +926,10 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-template <int H, int DOUT>
+template <int H, int DOUT, int NG>
 int launch_tc2(const TcParams& p, cudaStream_t st) {
-  using G = Geo2<H, DOUT>;
-  auto kern = uq_mlp_tc2_kernel<H, DOUT>;
+  using G = Geo2<H, DOUT, NG>;
+  auto kern = uq_mlp_tc2_kernel<H, DOUT, NG>;
   UQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -678,7 +937,7 @@ int launch_tc2(const TcParams& p, cudaStream_t st) {
   const int64_t units = (int64_t)((p.n_tiles + 1) / 2) * p.splits;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.blockDim = dim3(G::NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = G::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -703,17 +962,17 @@ int launch_tc2(const TcParams& p, cudaStream_t st) {
   return UQ_OK;
 }
 
-template <int DOUT>
+template <int DOUT, int NG>
 int dispatch_h2(int H, const TcParams& p, cudaStream_t st) {
   switch (H) {
-    case 64: return launch_tc2<64, DOUT>(p, st);
-    case 128: return launch_tc2<128, DOUT>(p, st);
-    case 192: return launch_tc2<192, DOUT>(p, st);
-    case 256: return launch_tc2<256, DOUT>(p, st);
-    case 320: return launch_tc2<320, DOUT>(p, st);
-    case 384: return launch_tc2<384, DOUT>(p, st);
-    case 448: return launch_tc2<448, DOUT>(p, st);
-    case 512: return launch_tc2<512, DOUT>(p, st);
+    case 64: return launch_tc2<64, DOUT, NG>(p, st);
+    case 128: return launch_tc2<128, DOUT, NG>(p, st);
+    case 192: return launch_tc2<192, DOUT, NG>(p, st);
+    case 256: return launch_tc2<256, DOUT, NG>(p, st);
+    case 320: return launch_tc2<320, DOUT, NG>(p, st);
+    case 384: return launch_tc2<384, DOUT, NG>(p, st);
+    case 448: return launch_tc2<448, DOUT, NG>(p, st);
+    case 512: return launch_tc2<512, DOUT, NG>(p, st);
   }
   set_error("bf16 pair kernel: unsupported hidden width %d", H);
   return UQ_ERR_UNSUPPORTED;
@@ -724,7 +983,12 @@ int dispatch_h2(int H, const TcParams& p, cudaStream_t st) {
 bool tc2_supported(int hidden) { return hidden % 64 == 0 && hidden >= 64 && hidden <= 512; }
 
 int tc2_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st) {
-  return dout_pad == 1 ? dispatch_h2<1>(hidden, p, st) : dispatch_h2<tc::MAX_DOUT>(hidden, p, st);
+  if (dout_pad != 1) return dispatch_h2<tc::MAX_DOUT, 2>(hidden, p, st);
+  // 8 epilogue warps by default (measured faster: 16 warps overlap more of the drain with the
+  // MMAs and slow them down); UQ_TC_EPI_WARPS=16 selects the 16-warp variant for A/B runs
+  const char* e = getenv("UQ_TC_EPI_WARPS");
+  if (e && e[0] == '1') return dispatch_h2<1, 4>(hidden, p, st);
+  return dispatch_h2<1, 2>(hidden, p, st);
 }
 
 }  // namespace uq

@@ -11,6 +11,7 @@ namespace tc {
 constexpr int MAX_MMA_LAYERS = 16;
 constexpr int MAX_DOUT = 8;
 constexpr int TRACE_LEN = 4096;
+constexpr int TRACE_ROLES = 6;
 
 struct TcParams {
   const float* x;        // [n][d_x]

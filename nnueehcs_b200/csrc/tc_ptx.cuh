@@ -222,6 +222,19 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
                                                   int tag) {
   if (!mbar_try_wait_cluster(bar, parity)) mbar_wait_cluster_slow(bar, parity, err, tag);
 }
+// Inline variant for the MMA warp's hot path: the out-of-line slow path costs ~400 cycles of
+// instruction fetch when it is entered cold.
+__device__ __forceinline__ void mbar_wait_cluster_inline(uint32_t bar, uint32_t parity,
+                                                         unsigned int* err, int tag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      if (err) atomicExch(err, 0x80000000u | (unsigned)tag);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
                "r"(cols)
