@@ -152,6 +152,46 @@ size_t uq_kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int32_t grid_pts);
 int uq_kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
                double* out_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* -- sharded metrics (one process per GPU).  The reference is
+      single-process scipy (nnueehcs/evaluation.py:182, :268-276) and has no counterpart; these are
+      the per-rank steps that nnueehcs_b200/distributed.py strings together with one all-reduce /
+      all-to-all each. ------------------------------------------------------------------------ */
+
+/*    (min, max, mean, M2 = sum (x - mean)^2) of one shard, float64, written to out_host[4] after
+      synchronising `stream`.  Shards are merged on the host with Chan's formula. */
+size_t uq_sample_stats_workspace_bytes(void);
+int uq_sample_stats(const float* x, int64_t n, double* out_host, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/*    Adds one shard's Gaussian kernel sums to `grid` (float64 [grid_pts], device, accumulated in
+      place) for the grid linspace(lo, hi, grid_pts) and the given kernel bandwidth (both global
+      quantities).  All-reduce the grids of the two samples, then uq_jsd_from_grids. */
+size_t uq_kde_grid_workspace_bytes(int64_t n);
+int uq_kde_grid_accumulate(const float* x, int64_t n, double lo, double hi, double bandwidth,
+                           int32_t grid_pts, double* grid, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/*    scipy.spatial.distance.jensenshannon of two raw kernel-sum vectors, grids = [2][grid_pts]
+      float64 on device; result to *out_host after synchronising `stream`. */
+int uq_jsd_from_grids(const double* grids, int32_t grid_pts, double* out_host, void* stream);
+
+/*    Histogram of the values over uq_key_bins() order-preserving coarse key bins (added to
+      `hist`, uint32 [bins], device): all-reduced to choose balanced value-range splitters. */
+int32_t uq_key_bins(void);
+int uq_key_histogram(const float* x, int64_t n, uint32_t* hist, void* stream);
+/*    Scatter a shard into per-destination segments: value with key bin b goes to part
+      bin_to_part[b] (uint8 [bins], device).  cursors (uint64 [n_parts], device) hold each
+      segment's start offset in `out` on entry and its end offset on return. */
+int uq_partition_by_bin(const float* x, int64_t n, const uint8_t* bin_to_part, int32_t n_parts,
+                        float* out, unsigned long long* cursors, void* stream);
+/*    One value range of the sample-sorted Wasserstein: every u and v value of this rank's range,
+      with u_below / v_below values of each sample in lower ranges.  out_host[3] = {integral of
+      |F_u - F_v| over the local merged values, first merged value, last merged value}.  Workspace
+      as uq_wasserstein_workspace_bytes(max(nu,1), max(nv,1)). */
+int uq_wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv,
+                            int64_t u_below, int64_t v_below, int64_t nu_total, int64_t nv_total,
+                            double* out_host, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,9 @@ EXPORTS = (
     "uq_forward_workspace_bytes", "uq_forward", "uq_forward_host", "uq_moments_merge",
     "uq_philox_keep_masks", "uq_wasserstein_workspace_bytes", "uq_wasserstein_1d",
     "uq_kde_jsd_workspace_bytes", "uq_kde_jsd",
+    "uq_sample_stats_workspace_bytes", "uq_sample_stats", "uq_kde_grid_workspace_bytes",
+    "uq_kde_grid_accumulate", "uq_jsd_from_grids", "uq_key_bins", "uq_key_histogram",
+    "uq_partition_by_bin", "uq_wasserstein_1d_range",
 )
 
 
@@ -94,6 +97,20 @@ def load() -> C.CDLL:
     lib.uq_kde_jsd_workspace_bytes.argtypes = [i64, i64, i32]
     lib.uq_kde_jsd_workspace_bytes.restype = sz
     lib.uq_kde_jsd.argtypes = [vp, i64, vp, i64, i32, C.POINTER(dbl), vp, sz, vp]
+    lib.uq_sample_stats_workspace_bytes.restype = sz
+    lib.uq_sample_stats.argtypes = [vp, i64, C.POINTER(dbl), vp, sz, vp]
+    lib.uq_kde_grid_workspace_bytes.argtypes = [i64]
+    lib.uq_kde_grid_workspace_bytes.restype = sz
+    lib.uq_kde_grid_accumulate.argtypes = [vp, i64, dbl, dbl, dbl, i32, vp, vp, sz, vp]
+    lib.uq_jsd_from_grids.argtypes = [vp, i32, C.POINTER(dbl), vp]
+    lib.uq_key_bins.restype = i32
+    lib.uq_key_histogram.argtypes = [vp, i64, vp, vp]
+    lib.uq_partition_by_bin.argtypes = [vp, i64, vp, i32, vp, vp, vp]
+    lib.uq_wasserstein_1d_range.argtypes = [vp, i64, vp, i64, i64, i64, i64, i64, C.POINTER(dbl),
+                                            vp, sz, vp]
+    for name in ("uq_sample_stats", "uq_kde_grid_accumulate", "uq_jsd_from_grids",
+                 "uq_key_histogram", "uq_partition_by_bin", "uq_wasserstein_1d_range"):
+        getattr(lib, name).restype = C.c_int
     for name in ("uq_model_create", "uq_model_destroy", "uq_model_supports_bf16", "uq_forward",
                  "uq_forward_host", "uq_moments_merge", "uq_philox_keep_masks",
                  "uq_wasserstein_1d", "uq_kde_jsd"):

@@ -337,4 +337,36 @@ int uq_kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int32_t g
                  static_cast<cudaStream_t>(stream));
 }
 
+size_t uq_kde_grid_workspace_bytes(int64_t n) { return kde_grid_workspace_bytes(n); }
+
+int uq_kde_grid_accumulate(const float* x, int64_t n, double lo, double hi, double bandwidth,
+                           int32_t grid_pts, double* grid, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(x && grid && n >= 1, UQ_ERR_INVALID, "uq_kde_grid_accumulate: NULL argument or n < 1");
+  UQ_REQUIRE(grid_pts >= 2 && grid_pts <= (1 << 20), UQ_ERR_INVALID,
+             "uq_kde_grid_accumulate: grid_pts %d outside [2, 2^20]", grid_pts);
+  return kde_grid_accumulate(x, n, lo, hi, bandwidth, grid_pts, grid, workspace, workspace_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int uq_jsd_from_grids(const double* grids, int32_t grid_pts, double* out_host, void* stream) {
+  UQ_REQUIRE(grids && out_host && grid_pts >= 2, UQ_ERR_INVALID,
+             "uq_jsd_from_grids: NULL argument or grid_pts < 2");
+  return jsd_from_grids(grids, grid_pts, out_host, static_cast<cudaStream_t>(stream));
+}
+
+int uq_wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv,
+                            int64_t u_below, int64_t v_below, int64_t nu_total, int64_t nv_total,
+                            double* out_host, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  UQ_REQUIRE(out_host != nullptr, UQ_ERR_INVALID, "uq_wasserstein_1d_range: out is NULL");
+  UQ_REQUIRE(nu >= 0 && nv >= 0 && nu + nv >= 1 && (nu == 0 || u) && (nv == 0 || v),
+             UQ_ERR_INVALID, "uq_wasserstein_1d_range: empty range or NULL pointer");
+  UQ_REQUIRE(nu_total >= 1 && nv_total >= 1 && u_below >= 0 && v_below >= 0 &&
+                 u_below + nu <= nu_total && v_below + nv <= nv_total,
+             UQ_ERR_INVALID, "uq_wasserstein_1d_range: inconsistent counts");
+  return wasserstein_1d_range(u, nu, v, nv, u_below, v_below, nu_total, nv_total, out_host,
+                              workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -103,6 +103,13 @@ int moments_merge(const float* means, const float* m2s, const double* counts, in
 size_t wasserstein_workspace_bytes(int64_t nu, int64_t nv);
 int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, double* out_host,
                    void* ws, size_t ws_bytes, cudaStream_t st);
+int wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv, int64_t u_below,
+                         int64_t v_below, int64_t nu_total, int64_t nv_total, double* out_host,
+                         void* ws, size_t ws_bytes, cudaStream_t st);
+size_t kde_grid_workspace_bytes(int64_t n);
+int kde_grid_accumulate(const float* x, int64_t n, double lo, double hi, double bandwidth,
+                        int grid_pts, double* grid, void* ws, size_t ws_bytes, cudaStream_t st);
+int jsd_from_grids(const double* grids, int grid_pts, double* out_host, cudaStream_t st);
 size_t kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int grid_pts);
 int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
             double* out_host, void* ws, size_t ws_bytes, cudaStream_t st);

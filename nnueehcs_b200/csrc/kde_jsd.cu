@@ -267,4 +267,60 @@ int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts
   return UQ_OK;
 }
 
+// ---- sharded KDE-JS (one GPU's part of each sample) ---------------------------------------------
+size_t kde_grid_workspace_bytes(int64_t n) {
+  if (n < 1) return 0;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  return 2 * al(sizeof(float) * (size_t)n) + al(radix_sort_scratch_bytes(n)) + al(sizeof(KdeParams));
+}
+
+// Adds this shard's Gaussian kernel sums to `grid` (float64 [grid_pts], device).  The grid
+// (lo, hi) and the bandwidth come from the caller: they are properties of the WHOLE sample
+// (global min / max / Scott factor), reduced across ranks before this call.
+int kde_grid_accumulate(const float* x, int64_t n, double lo, double hi, double bandwidth,
+                        int grid_pts, double* grid, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t need = kde_grid_workspace_bytes(n);
+  UQ_REQUIRE(ws != nullptr && ws_bytes >= need, UQ_ERR_WORKSPACE,
+             "kde grid accumulate needs %zu workspace bytes, got %zu", need, ws_bytes);
+  UQ_REQUIRE(bandwidth > 0.0 && hi >= lo, UQ_ERR_INVALID,
+             "kde grid accumulate: bandwidth %g, range [%g, %g]", bandwidth, lo, hi);
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  char* b = static_cast<char*>(ws);
+  float* dx = reinterpret_cast<float*>(b);
+  float* dt = reinterpret_cast<float*>(b + al(sizeof(float) * (size_t)n));
+  char* scratch = b + 2 * al(sizeof(float) * (size_t)n);
+  KdeParams* params = reinterpret_cast<KdeParams*>(scratch + al(radix_sort_scratch_bytes(n)));
+  UQ_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  float* sx = nullptr;
+  int rc = radix_sort_f32(dx, dt, n, scratch, radix_sort_scratch_bytes(n), &sx, st);
+  if (rc != UQ_OK) return rc;
+  KdeParams hp;
+  hp.lo = lo;
+  hp.step = (hi - lo) / (double)(grid_pts - 1);
+  hp.h[0] = hp.h[1] = bandwidth;
+  hp.scale[0] = hp.scale[1] = sqrt(0.5 * 1.4426950408889634) / bandwidth;
+  // pageable source: the copy is staged by the driver before the call returns
+  UQ_CUDA(cudaMemcpyAsync(params, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
+  const int64_t chunks = (n + KDE_CHUNK - 1) / KDE_CHUNK;
+  kde_eval_kernel<<<(unsigned)chunks, KDE_THREADS, 0, st>>>(sx, n, sx, 0, chunks, grid_pts, params,
+                                                           grid);
+  UQ_LAUNCH_CHECK();
+  return UQ_OK;
+}
+
+// Jensen-Shannon distance of two raw kernel-sum vectors ([2][grid_pts] float64, device)
+int jsd_from_grids(const double* grids, int grid_pts, double* out_host, cudaStream_t st) {
+  double* result = nullptr;
+  UQ_CUDA(cudaMallocAsync((void**)&result, sizeof(double), st));
+  jsd_kernel<<<1, 1024, 0, st>>>(grids, grid_pts, result);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(result, st);
+  if (e != cudaSuccess) return cuda_fail(e, "jsd_from_grids", __FILE__, __LINE__);
+  UQ_CUDA(cudaStreamSynchronize(st));
+  return UQ_OK;
+}
+
 }  // namespace uq

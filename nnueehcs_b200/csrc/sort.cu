@@ -59,39 +59,62 @@ upsweep_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int64_t 
   }
 }
 
-// exclusive scan of the digit-major spine, one block
+// exclusive scan of the digit-major spine, one block of 1024 threads walking it in coalesced
+// 4096-element slabs (uint4 per thread) with a running carry
 __global__ void __launch_bounds__(1024) spine_scan_kernel(uint32_t* __restrict__ spine, int total) {
   __shared__ uint32_t warp_sums[32];
-  const int t = threadIdx.x;
-  const int per = (total + 1023) / 1024;
-  const int b = t * per;
-  int e = b + per;
-  if (e > total) e = total;
-  uint32_t s = 0;
-  for (int i = b; i < e; ++i) s += spine[i];
-  uint32_t incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((t & 31) >= o) incl += y;
-  }
-  if ((t & 31) == 31) warp_sums[t >> 5] = incl;
+  __shared__ uint32_t carry_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) carry_s = 0;
   __syncthreads();
-  if (t < 32) {
-    uint32_t ws = warp_sums[t], wi = ws;
+  for (int base = 0; base < total; base += 4096) {
+    const uint32_t carry = carry_s;   // written by warp 0 between the two barriers below
+    const int i0 = base + t * 4;
+    uint32_t v[4] = {0, 0, 0, 0};
+    if (i0 + 3 < total) {
+      const uint4 q = *reinterpret_cast<const uint4*>(spine + i0);
+      v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i0 + e < total) v[e] = spine[i0 + e];
+    }
+    const uint32_t s = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
-      if (t >= o) wi += y;
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
     }
-    warp_sums[t] = wi - ws;
-  }
-  __syncthreads();
-  uint32_t run = warp_sums[t >> 5] + incl - s;
-  for (int i = b; i < e; ++i) {
-    const uint32_t c = spine[i];
-    spine[i] = run;
-    run += c;
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t ws = warp_sums[lane];
+      uint32_t wi = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += y;
+      }
+      warp_sums[lane] = wi - ws;
+      if (lane == 31) carry_s = carry + wi;   // read by everyone only after the next barrier
+    }
+    __syncthreads();
+    uint32_t run = carry + warp_sums[w] + incl - s;
+    uint32_t o4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      o4[e] = run;
+      run += v[e];
+    }
+    if (i0 + 3 < total) {
+      *reinterpret_cast<uint4*>(spine + i0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i0 + e < total) spine[i0 + e] = o4[e];
+    }
+    __syncthreads();   // warp_sums / carry_s are rewritten by the next slab
   }
 }
 
@@ -115,16 +138,33 @@ downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, in
     uint32_t key[SORT_ITEMS];
     uint32_t rank[SORT_ITEMS];
     const int64_t wbase = tile0 + (int64_t)w * 32 * SORT_ITEMS;
+    // all 16 loads of the tile are issued before any of them is consumed: inside the ranking loop
+    // the warp-synchronous steps would otherwise serialise one HBM round trip per round
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+      const int64_t idx = wbase + r * 32 + lane;
+      uint32_t k = 0xFFFFFFFFu;
+      if (idx < end) k = FIRST ? f2key(__ldg(in + idx)) : __ldg(in + idx);
+      key[r] = k;
+    }
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; ++r) {
       const int64_t idx = wbase + r * 32 + lane;
       const bool valid = idx < end;
-      uint32_t k = 0xFFFFFFFFu;
-      if (valid) k = FIRST ? f2key(in[idx]) : in[idx];
-      key[r] = k;
-      // invalid lanes get digit 256 so they never match a real digit
-      const uint32_t d = valid ? ((k >> shift) & 0xFFu) : 256u;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t k = key[r];
+      // lanes holding the same digit, from nine ballots (one per digit bit + validity).
+      // MATCH.ANY does the same in one instruction but runs on the ADU pipe at ~64 cycles per
+      // warp on sm_100 (ncu: ADU 57 % busy, kernel 10x off the HBM roofline); ballots and LOP3s
+      // issue at full rate.
+      const uint32_t d = (k >> shift) & 0xFFu;
+      uint32_t peers = __ballot_sync(0xffffffffu, valid);
+      if (!valid) peers = ~peers;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+      }
       const int leader = __ffs(peers) - 1;
       uint32_t old = 0;
       if (valid && lane == leader) {

@@ -45,7 +45,8 @@ __device__ __forceinline__ int merge_path_smem(const float* U, int nu, const flo
 
 __global__ void __launch_bounds__(MRG_THREADS)
 cdf_integral_kernel(const float* __restrict__ U, int64_t nu, const float* __restrict__ V,
-                    int64_t nv, double* __restrict__ block_partials) {
+                    int64_t nv, int64_t u_below, int64_t v_below, int64_t nu_total,
+                    int64_t nv_total, double* __restrict__ block_partials) {
   __shared__ float su[MRG_TILE + 1];
   __shared__ float sv[MRG_TILE + 1];
   __shared__ int64_t split_i;
@@ -81,8 +82,8 @@ cdf_integral_kernel(const float* __restrict__ U, int64_t nu, const float* __rest
       nxt = take_u ? su[i] : sv[j];
       const double delta = (double)nxt - (double)cur;  // exact: scipy widens to float64 first
       // numpy: idx / size in float64
-      const double cu = (double)(i0 + i) / (double)nu;
-      const double cv = (double)(j0 + j) / (double)nv;
+      const double cu = (double)(u_below + i0 + i) / (double)nu_total;
+      const double cv = (double)(v_below + j0 + j) / (double)nv_total;
       acc += fabs(cu - cv) * delta;
       if (take_u) ++i; else ++j;
       cur = nxt;
@@ -165,7 +166,8 @@ int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, doubl
   rc = radix_sort_f32(dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
   if (rc != UQ_OK) return rc;
   if (nu + nv - 1 > 0) {
-    cdf_integral_kernel<<<(unsigned)L.blocks, MRG_THREADS, 0, st>>>(su, nu, sv, nv, parts);
+    cdf_integral_kernel<<<(unsigned)L.blocks, MRG_THREADS, 0, st>>>(su, nu, sv, nv, 0, 0, nu, nv,
+                                                                    parts);
     UQ_LAUNCH_CHECK();
     sum_partials_kernel<<<1, 1024, 0, st>>>(parts, L.blocks, result);
     UQ_LAUNCH_CHECK();
@@ -174,6 +176,71 @@ int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, doubl
   }
   UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
   UQ_CUDA(cudaStreamSynchronize(st));
+  return UQ_OK;
+}
+
+// One value range of a sample-sorted (multi-GPU) Wasserstein: this rank holds every u and v
+// value of its range; `u_below` / `v_below` values of each sample lie in lower ranges.  Writes
+// {partial integral over the local merged sequence, first merged value, last merged value}.
+int wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv, int64_t u_below,
+                         int64_t v_below, int64_t nu_total, int64_t nv_total, double* out_host,
+                         void* ws, size_t ws_bytes, cudaStream_t st) {
+  const WsLayout L = layout(nu > 0 ? nu : 1, nv > 0 ? nv : 1);
+  UQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, UQ_ERR_WORKSPACE,
+             "wasserstein range needs %zu workspace bytes, got %zu", L.total, ws_bytes);
+  UQ_REQUIRE(nu + nv >= 1 && nu + nv < ((int64_t)1 << 31), UQ_ERR_INVALID,
+             "wasserstein range: %lld values", (long long)(nu + nv));
+  char* b = static_cast<char*>(ws);
+  float* du = reinterpret_cast<float*>(b + L.u);
+  float* dut = reinterpret_cast<float*>(b + L.ut);
+  float* dv = reinterpret_cast<float*>(b + L.v);
+  float* dvt = reinterpret_cast<float*>(b + L.vt);
+  double* parts = reinterpret_cast<double*>(b + L.parts);
+  double* result = reinterpret_cast<double*>(b + L.result);
+  float *su = du, *sv = dv;
+  int rc;
+  if (nu > 0) {
+    UQ_CUDA(cudaMemcpyAsync(du, u, sizeof(float) * (size_t)nu, cudaMemcpyDeviceToDevice, st));
+    rc = radix_sort_f32(du, dut, nu, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
+    if (rc != UQ_OK) return rc;
+  }
+  if (nv > 0) {
+    UQ_CUDA(cudaMemcpyAsync(dv, v, sizeof(float) * (size_t)nv, cudaMemcpyDeviceToDevice, st));
+    rc = radix_sort_f32(dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
+    if (rc != UQ_OK) return rc;
+  }
+  if (nu + nv - 1 > 0) {
+    const int64_t blocks = (nu + nv - 1 + MRG_TILE - 1) / MRG_TILE;
+    cdf_integral_kernel<<<(unsigned)blocks, MRG_THREADS, 0, st>>>(su, nu, sv, nv, u_below, v_below,
+                                                                  nu_total, nv_total, parts);
+    UQ_LAUNCH_CHECK();
+    sum_partials_kernel<<<1, 1024, 0, st>>>(parts, blocks, result);
+    UQ_LAUNCH_CHECK();
+  } else {
+    UQ_CUDA(cudaMemsetAsync(result, 0, sizeof(double), st));
+  }
+  float ends[4] = {0.f, 0.f, 0.f, 0.f};  // u first, u last, v first, v last
+  UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (nu > 0) {
+    UQ_CUDA(cudaMemcpyAsync(&ends[0], su, sizeof(float), cudaMemcpyDeviceToHost, st));
+    UQ_CUDA(cudaMemcpyAsync(&ends[1], su + nu - 1, sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (nv > 0) {
+    UQ_CUDA(cudaMemcpyAsync(&ends[2], sv, sizeof(float), cudaMemcpyDeviceToHost, st));
+    UQ_CUDA(cudaMemcpyAsync(&ends[3], sv + nv - 1, sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  UQ_CUDA(cudaStreamSynchronize(st));
+  double first, last;
+  if (nu > 0 && nv > 0) {
+    first = ends[0] < ends[2] ? ends[0] : ends[2];
+    last = ends[1] > ends[3] ? ends[1] : ends[3];
+  } else if (nu > 0) {
+    first = ends[0], last = ends[1];
+  } else {
+    first = ends[2], last = ends[3];
+  }
+  out_host[1] = first;
+  out_host[2] = last;
   return UQ_OK;
 }
 

@@ -90,3 +90,183 @@ class KShard:
             means, m2s = means.index_select(0, idx), m2s.index_select(0, idx)
             counts = [counts[r] for r in live]
         return ops.moments_merge(means.contiguous(), m2s.contiguous(), counts)
+
+
+# ------------------------------------------------------------------------------------------------
+# Sharded distribution metrics (BASELINE.json configs[4]: 100 M scores over 8 GPUs)
+# ------------------------------------------------------------------------------------------------
+# Every rank holds an arbitrary shard of the ID scores ``u`` and of the OOD scores ``v``.
+#
+# KDE-JS (evaluation.py:268-276): all-gather of 2 x 5 float64 shard statistics -> global
+# min/max/Scott bandwidth (Chan merge) -> every rank adds its shard's kernel sums to the full
+# grid -> ONE all-reduce of 2 x grid_pts float64 -> Jensen-Shannon distance (computed redundantly
+# on every rank).
+#
+# Wasserstein (evaluation.py:182): sample sort.  One all-reduce of a 2 x 16384-bin key histogram
+# picks value-range splitters that balance u+v over the ranks; ONE all-to-all per sample moves
+# every value to the rank that owns its range; each rank sorts and integrates |F_u - F_v| over
+# its range with the global CDF offsets; an all-gather of 4 float64 per rank adds the partial
+# integrals and the terms that straddle two ranges.
+
+class CudaMetricBackend:
+    """The product backend: every step is a kernel in libnnueehcs_b200.so (``ops``)."""
+    key_bins = staticmethod(ops.key_bins)
+    sample_stats = staticmethod(ops.sample_stats)
+    kde_grid_accumulate = staticmethod(ops.kde_grid_accumulate)
+    jsd_from_grids = staticmethod(ops.jsd_from_grids)
+    key_histogram = staticmethod(ops.key_histogram)
+    partition_by_bin = staticmethod(ops.partition_by_bin)
+    wasserstein_1d_range = staticmethod(ops.wasserstein_1d_range)
+
+
+def _world(group):
+    if not dist.is_available() or not dist.is_initialized():
+        raise RuntimeError("sharded metrics need an initialised torch.distributed process group")
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _all_gather_f64(vec: torch.Tensor, group) -> torch.Tensor:
+    rank, world = _world(group)
+    out = torch.empty((world,) + tuple(vec.shape), dtype=vec.dtype, device=vec.device)
+    dist.all_gather_into_tensor(out.view(-1), vec.contiguous().view(-1), group=group) \
+        if vec.is_cuda else dist.all_gather(list(out.unbind(0)), vec.contiguous(), group=group)
+    return out
+
+
+def merge_stats(stats: torch.Tensor):
+    """Chan merge of per-shard rows (n, min, max, mean, M2) -> (n, min, max, mean, M2)."""
+    n, mn, mx, mean, m2 = 0.0, float("inf"), float("-inf"), 0.0, 0.0
+    for row in stats.tolist():
+        nb, mnb, mxb, meanb, m2b = row
+        if nb <= 0:
+            continue
+        mn, mx = min(mn, mnb), max(mx, mxb)
+        tot = n + nb
+        delta = meanb - mean
+        mean = mean + delta * nb / tot
+        m2 = m2 + m2b + delta * delta * n * nb / tot
+        n = tot
+    return n, mn, mx, mean, m2
+
+
+def kde_jsd_sharded(u_local: torch.Tensor, v_local: torch.Tensor, num_points: int = 20000,
+                    group=None, backend=CudaMetricBackend) -> float:
+    """``JensenShannonEvaluation.pdf_jsd`` over samples sharded across the ranks of ``group``."""
+    rank, world = _world(group)
+    dev = u_local.device
+    rows = []
+    for x in (u_local, v_local):
+        x = x.reshape(-1)
+        if x.numel():
+            mn, mx, mean, m2 = backend.sample_stats(x)
+            rows.append([float(x.numel()), mn, mx, mean, m2])
+        else:
+            rows.append([0.0, 0.0, 0.0, 0.0, 0.0])
+    gathered = _all_gather_f64(torch.tensor(rows, dtype=torch.float64, device=dev), group)
+    nu, mnu, mxu, _, m2u = merge_stats(gathered[:, 0])
+    nv, mnv, mxv, _, m2v = merge_stats(gathered[:, 1])
+    if nu < 2 or nv < 2:
+        raise ValueError("kde_jsd_sharded: each sample needs at least 2 values")
+    # scipy.stats.gaussian_kde: Scott factor n^(-1/5) times the unbiased standard deviation
+    h_u = (m2u / (nu - 1.0)) ** 0.5 * nu ** -0.2
+    h_v = (m2v / (nv - 1.0)) ** 0.5 * nv ** -0.2
+    lo, hi = min(mnu, mnv), max(mxu, mxv)
+    grids = torch.zeros((2, num_points), dtype=torch.float64, device=dev)
+    if u_local.numel():
+        backend.kde_grid_accumulate(u_local.reshape(-1), lo, hi, h_u, grids[0])
+    if v_local.numel():
+        backend.kde_grid_accumulate(v_local.reshape(-1), lo, hi, h_v, grids[1])
+    dist.all_reduce(grids, op=dist.ReduceOp.SUM, group=group)
+    return backend.jsd_from_grids(grids)
+
+
+def _all_to_all(send: torch.Tensor, in_splits: List[int], out_splits: List[int], group
+                ) -> torch.Tensor:
+    recv = torch.empty(sum(out_splits), dtype=send.dtype, device=send.device)
+    if send.is_cuda:
+        dist.all_to_all_single(recv, send, out_splits, in_splits, group=group)
+        return recv
+    # gloo (CPU tests) has no all-to-all: pairwise exchange
+    rank, world = _world(group)
+    s_off = [0]
+    for c in in_splits:
+        s_off.append(s_off[-1] + c)
+    r_off = [0]
+    for c in out_splits:
+        r_off.append(r_off[-1] + c)
+    recv[r_off[rank]:r_off[rank + 1]] = send[s_off[rank]:s_off[rank + 1]]
+    reqs = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if in_splits[peer]:
+            reqs.append(dist.isend(send[s_off[peer]:s_off[peer + 1]].contiguous(), peer, group=group))
+        if out_splits[peer]:
+            reqs.append(dist.irecv(recv[r_off[peer]:r_off[peer + 1]], peer, group=group))
+    for r in reqs:
+        r.wait()
+    return recv
+
+
+def choose_bin_owners(hist_total, world: int):
+    """bin -> owning rank so that the ranks' value ranges are contiguous, ordered and balanced.
+    ``hist_total``: 1-D integer array (u + v counts per key bin, all ranks)."""
+    import numpy as np
+    cum = np.cumsum(np.asarray(hist_total, dtype=np.int64))
+    total = int(cum[-1])
+    targets = [(p + 1) * total / world for p in range(world - 1)]
+    ends = np.searchsorted(cum, targets, side="left")          # last bin of parts 0..world-2
+    owners = np.searchsorted(ends, np.arange(cum.size), side="left")
+    return owners.astype(np.uint8)
+
+
+def wasserstein_1d_sharded(u_local: torch.Tensor, v_local: torch.Tensor, group=None,
+                           backend=CudaMetricBackend) -> float:
+    """``scipy.stats.wasserstein_distance(u, v)`` over samples sharded across ``group``."""
+    import numpy as np
+    rank, world = _world(group)
+    if world > 64:
+        raise ValueError("wasserstein_1d_sharded supports at most 64 ranks")
+    dev = u_local.device
+    u_local, v_local = u_local.reshape(-1), v_local.reshape(-1)
+    local_hist = torch.stack([backend.key_histogram(u_local), backend.key_histogram(v_local)])
+    global_hist = local_hist.clone()
+    dist.all_reduce(global_hist, op=dist.ReduceOp.SUM, group=group)
+    gh = global_hist.cpu().numpy()
+    lh = local_hist.cpu().numpy()
+    nu_total, nv_total = int(gh[0].sum()), int(gh[1].sum())
+    if nu_total == 0 or nv_total == 0:
+        raise ValueError("Distribution can't be empty.")
+    owners = choose_bin_owners(gh[0] + gh[1], world)
+    owners_t = torch.from_numpy(owners).to(dev)
+
+    def route(x, hist_row):
+        send_counts = [int(hist_row[owners == p].sum()) for p in range(world)]
+        send = backend.partition_by_bin(x, owners_t, send_counts) if x.numel() else x
+        cnt = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        all_cnt = _all_gather_f64(cnt, group)                  # [src, dst]
+        recv_counts = [int(c) for c in all_cnt[:, rank].tolist()]
+        return _all_to_all(send, send_counts, recv_counts, group)
+
+    mine_u = route(u_local, lh[0])
+    mine_v = route(v_local, lh[1])
+    below = owners < rank
+    u_below, v_below = int(gh[0][below].sum()), int(gh[1][below].sum())
+    if mine_u.numel() + mine_v.numel() > 0:
+        part, first, last = backend.wasserstein_1d_range(mine_u, mine_v, u_below, v_below,
+                                                         nu_total, nv_total)
+        row = [part, first, last, float(mine_u.numel() + mine_v.numel())]
+    else:
+        row = [0.0, 0.0, 0.0, 0.0]
+    rows = _all_gather_f64(torch.tensor(row, dtype=torch.float64, device=dev), group).tolist()
+    total = 0.0
+    prev = None        # (last value, cdf_u, cdf_v) of the previous non-empty range
+    for g, (part, first, last, cnt) in enumerate(rows):
+        if cnt <= 0:
+            continue
+        if prev is not None:
+            total += abs(prev[1] - prev[2]) * (first - prev[0])
+        total += part
+        upto = owners <= g
+        prev = (last, float(gh[0][upto].sum()) / nu_total, float(gh[1][upto].sum()) / nv_total)
+    return total

@@ -259,3 +259,109 @@ def kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000) -> float:
         _lib.check(lib.uq_kde_jsd(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), num_points,
                                   C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
     return float(out.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-rank steps of the sharded metrics (strung together by nnueehcs_b200.distributed)
+# ------------------------------------------------------------------------------------------------
+
+def key_bins() -> int:
+    return int(_lib.load().uq_key_bins())
+
+
+def sample_stats(x: torch.Tensor) -> Tuple[float, float, float, float]:
+    """(min, max, mean, M2) of a float32 device shard, float64 arithmetic."""
+    lib = _lib.load()
+    x = _flat_f32(x, "x")
+    out = (C.c_double * 4)()
+    with torch.cuda.device(x.device):
+        wsb = int(lib.uq_sample_stats_workspace_bytes())
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.uq_sample_stats(x.data_ptr(), x.numel(), out, ws.data_ptr(), wsb,
+                                       _stream_ptr(x.device)))
+    return float(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+
+def kde_grid_accumulate(x: torch.Tensor, lo: float, hi: float, bandwidth: float,
+                        grid: torch.Tensor) -> None:
+    """grid[j] += sum_i exp(-((x_i - g_j) / bandwidth)^2 / 2), g = linspace(lo, hi, len(grid))."""
+    lib = _lib.load()
+    x = _flat_f32(x, "x")
+    _require_cuda(grid, "grid")
+    if grid.dtype != torch.float64 or not grid.is_contiguous() or grid.dim() != 1:
+        raise ValueError("grid must be a contiguous 1-D float64 tensor")
+    with torch.cuda.device(x.device):
+        wsb = int(lib.uq_kde_grid_workspace_bytes(x.numel()))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.uq_kde_grid_accumulate(x.data_ptr(), x.numel(), float(lo), float(hi),
+                                              float(bandwidth), grid.numel(), grid.data_ptr(),
+                                              ws.data_ptr(), wsb, _stream_ptr(x.device)))
+
+
+def jsd_from_grids(grids: torch.Tensor) -> float:
+    """Jensen-Shannon distance of two raw kernel-sum vectors, ``grids`` = float64 [2, G] on device."""
+    lib = _lib.load()
+    _require_cuda(grids, "grids")
+    if grids.dtype != torch.float64 or grids.dim() != 2 or grids.shape[0] != 2:
+        raise ValueError("grids must be float64 [2, G]")
+    grids = grids.contiguous()
+    out = C.c_double()
+    with torch.cuda.device(grids.device):
+        _lib.check(lib.uq_jsd_from_grids(grids.data_ptr(), grids.shape[1], C.byref(out),
+                                         _stream_ptr(grids.device)))
+    return float(out.value)
+
+
+def key_histogram(x: torch.Tensor) -> torch.Tensor:
+    """int64 [key_bins()] counts of ``x`` per coarse order-preserving key bin (on x's device)."""
+    lib = _lib.load()
+    x = _flat_f32(x, "x")
+    hist = torch.zeros(key_bins(), dtype=torch.int32, device=x.device)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            _lib.check(lib.uq_key_histogram(x.data_ptr(), x.numel(), hist.data_ptr(),
+                                            _stream_ptr(x.device)))
+    return hist.to(torch.int64)
+
+
+def partition_by_bin(x: torch.Tensor, bin_to_part: torch.Tensor, part_counts: Sequence[int]
+                     ) -> torch.Tensor:
+    """``x`` regrouped into ``len(part_counts)`` consecutive segments (segment p holds the values
+    whose key bin maps to part p; order inside a segment is arbitrary)."""
+    lib = _lib.load()
+    x = _flat_f32(x, "x")
+    _require_cuda(bin_to_part, "bin_to_part")
+    if bin_to_part.dtype != torch.uint8 or bin_to_part.numel() != key_bins():
+        raise ValueError("bin_to_part must be uint8 [key_bins()]")
+    out = torch.empty_like(x)
+    if x.numel() == 0:
+        return out
+    starts, acc = [], 0
+    for c in part_counts:
+        starts.append(acc)
+        acc += int(c)
+    if acc != x.numel():
+        raise ValueError("part_counts do not add up to the number of values")
+    cursors = torch.tensor(starts, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.uq_partition_by_bin(x.data_ptr(), x.numel(),
+                                           bin_to_part.contiguous().data_ptr(), len(part_counts),
+                                           out.data_ptr(), cursors.data_ptr(),
+                                           _stream_ptr(x.device)))
+    return out
+
+
+def wasserstein_1d_range(u: torch.Tensor, v: torch.Tensor, u_below: int, v_below: int,
+                         nu_total: int, nv_total: int) -> Tuple[float, float, float]:
+    """(partial integral, first merged value, last merged value) of one value range."""
+    lib = _lib.load()
+    u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
+    out = (C.c_double * 3)()
+    with torch.cuda.device(u.device):
+        wsb = int(lib.uq_wasserstein_workspace_bytes(max(u.numel(), 1), max(v.numel(), 1)))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
+        _lib.check(lib.uq_wasserstein_1d_range(
+            u.data_ptr() if u.numel() else None, u.numel(), v.data_ptr() if v.numel() else None,
+            v.numel(), int(u_below), int(v_below), int(nu_total), int(nv_total), out,
+            ws.data_ptr(), wsb, _stream_ptr(u.device)))
+    return float(out[0]), float(out[1]), float(out[2])

@@ -92,3 +92,87 @@ def pdf_jsd(dist1: np.ndarray, dist2: np.ndarray, num_points: int = 20000) -> fl
     hi = max(d1.max(), d2.max())
     x_range = np.linspace(lo, hi, num_points)
     return jensenshannon(gaussian_kde_pdf(d1, x_range), gaussian_kde_pdf(d2, x_range))
+
+
+# ----------------------------------------------------------------------------------------------
+# numpy stand-ins for the per-rank CUDA steps of the sharded metrics (TEST INFRASTRUCTURE):
+# they let the world-size-2 gloo tests exercise nnueehcs_b200.distributed's host logic on CPU,
+# and the GPU tests check each CUDA step against them.
+# ----------------------------------------------------------------------------------------------
+
+KEY_BINS = 16384
+
+
+def key_bin(x: np.ndarray) -> np.ndarray:
+    """Top 14 bits of the order-preserving radix key of float32 values (csrc/shard_metrics.cu)."""
+    b = np.asarray(x, dtype=np.float32).view(np.uint32)
+    k = np.where(b >> 31, ~b, b ^ np.uint32(0x80000000)).astype(np.uint32)
+    return (k >> 18).astype(np.int64)
+
+
+def wasserstein_1d_range(u, v, u_below, v_below, nu_total, nv_total):
+    """Partial integral of |F_u - F_v| over one value range with global CDF offsets."""
+    u = np.sort(np.asarray(u, dtype=np.float64).ravel())
+    v = np.sort(np.asarray(v, dtype=np.float64).ravel())
+    allv = np.sort(np.concatenate([u, v]), kind="mergesort")
+    if allv.size == 0:
+        return 0.0, 0.0, 0.0
+    deltas = np.diff(allv)
+    cu = (u_below + np.searchsorted(u, allv[:-1], side="right")) / nu_total
+    cv = (v_below + np.searchsorted(v, allv[:-1], side="right")) / nv_total
+    return float(np.sum(np.abs(cu - cv) * deltas)), float(allv[0]), float(allv[-1])
+
+
+class NumpyShardBackend:
+    """Same interface as ``nnueehcs_b200.distributed.CudaMetricBackend`` on CPU torch tensors."""
+
+    @staticmethod
+    def key_bins():
+        return KEY_BINS
+
+    @staticmethod
+    def sample_stats(x):
+        a = x.detach().cpu().numpy().astype(np.float64).ravel()
+        mean = a.mean()
+        return float(a.min()), float(a.max()), float(mean), float(((a - mean) ** 2).sum())
+
+    @staticmethod
+    def kde_grid_accumulate(x, lo, hi, bandwidth, grid):
+        import torch
+        a = x.detach().cpu().numpy().astype(np.float64).ravel()
+        g = np.linspace(lo, hi, grid.numel())
+        acc = np.zeros(g.size)
+        for i in range(0, a.size, 4096):
+            z = (a[i:i + 4096, None] - g[None, :]) / bandwidth
+            acc += np.exp(-0.5 * z * z).sum(0)
+        grid += torch.from_numpy(acc).to(grid.device)
+
+    @staticmethod
+    def jsd_from_grids(grids):
+        p, q = grids[0].cpu().numpy(), grids[1].cpu().numpy()
+        p, q = p / p.sum(), q / q.sum()
+        m = (p + q) / 2.0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            left = np.where((p > 0) & (m > 0), p * np.log(p / m), 0.0)
+            right = np.where((q > 0) & (m > 0), q * np.log(q / m), 0.0)
+        return float(np.sqrt((left.sum() + right.sum()) / 2.0))
+
+    @staticmethod
+    def key_histogram(x):
+        import torch
+        a = x.detach().cpu().numpy().ravel()
+        return torch.from_numpy(np.bincount(key_bin(a), minlength=KEY_BINS).astype(np.int64))
+
+    @staticmethod
+    def partition_by_bin(x, bin_to_part, part_counts):
+        import torch
+        a = x.detach().cpu().numpy().ravel()
+        dst = bin_to_part.cpu().numpy()[key_bin(a)]
+        order = np.argsort(dst, kind="stable")
+        assert [int((dst == p).sum()) for p in range(len(part_counts))] == list(part_counts)
+        return torch.from_numpy(a[order].copy())
+
+    @staticmethod
+    def wasserstein_1d_range(u, v, u_below, v_below, nu_total, nv_total):
+        return wasserstein_1d_range(u.cpu().numpy(), v.cpu().numpy(), u_below, v_below, nu_total,
+                                    nv_total)

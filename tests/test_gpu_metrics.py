@@ -124,3 +124,109 @@ def test_metric_classes_drop_in():
         evaluation.UncertaintyEstimate((torch.from_numpy(g["id"]), torch.from_numpy(g["id"]))),
         evaluation.UncertaintyEstimate((torch.from_numpy(g["ood"]), torch.from_numpy(g["ood"]))))
     assert two["wasserstein_distance"] == pytest.approx(float(g["wasserstein"]), rel=1e-12)
+
+
+# ---- per-rank steps of the sharded metrics (each CUDA step against its numpy stand-in) ----------
+
+def _gamma_pair(nu, nv, seed=3):
+    rng = np.random.default_rng(seed)
+    return (rng.gamma(2.0, 0.05, nu).astype(np.float32), rng.gamma(3.0, 0.08, nv).astype(np.float32))
+
+
+def test_sample_stats_matches_numpy():
+    u, _ = _gamma_pair(200_003, 10)
+    mn, mx, mean, m2 = ops.sample_stats(torch.from_numpy(u).to(DEV))
+    a = u.astype(np.float64)
+    assert mn == a.min() and mx == a.max()
+    assert abs(mean - a.mean()) <= 1e-12 * abs(a.mean())
+    assert abs(m2 - ((a - a.mean()) ** 2).sum()) <= 1e-9 * ((a - a.mean()) ** 2).sum()
+
+
+def test_key_histogram_and_partition_match_numpy():
+    u, _ = _gamma_pair(300_001, 10)
+    u[:1000] *= -1.0  # negative keys too
+    t = torch.from_numpy(u).to(DEV)
+    hist = ops.key_histogram(t).cpu().numpy()
+    ref = np.bincount(metrics_oracle.key_bin(u), minlength=metrics_oracle.KEY_BINS)
+    assert np.array_equal(hist, ref)
+    from nnueehcs_b200.distributed import choose_bin_owners
+    owners = choose_bin_owners(hist, 5)
+    counts = [int(hist[owners == p].sum()) for p in range(5)]
+    out = ops.partition_by_bin(t, torch.from_numpy(owners).to(DEV), counts).cpu().numpy()
+    dst = owners[metrics_oracle.key_bin(u)]
+    off = 0
+    for p, c in enumerate(counts):
+        seg = np.sort(out[off:off + c])
+        assert np.array_equal(seg, np.sort(u[dst == p])), p
+        off += c
+    # ranges are ordered: every value of part p is <= every value of part p + 1
+    bounds = np.cumsum(counts)
+    for p in range(4):
+        if counts[p] and counts[p + 1]:
+            assert out[bounds[p] - counts[p]:bounds[p]].max() <= out[bounds[p]:bounds[p + 1]].min()
+
+
+def test_wasserstein_ranges_compose_to_the_full_distance():
+    u, v = _gamma_pair(120_000, 90_000)
+    from nnueehcs_b200.distributed import choose_bin_owners
+    hu = np.bincount(metrics_oracle.key_bin(u), minlength=metrics_oracle.KEY_BINS)
+    hv = np.bincount(metrics_oracle.key_bin(v), minlength=metrics_oracle.KEY_BINS)
+    owners = choose_bin_owners(hu + hv, 3)
+    du, dv = owners[metrics_oracle.key_bin(u)], owners[metrics_oracle.key_bin(v)]
+    total, prev, ub, vb = 0.0, None, 0, 0
+    for p in range(3):
+        up, vp = u[du == p], v[dv == p]
+        part, first, last = ops.wasserstein_1d_range(torch.from_numpy(up).to(DEV),
+                                                     torch.from_numpy(vp).to(DEV), ub, vb,
+                                                     u.size, v.size)
+        rp, rf, rl = metrics_oracle.wasserstein_1d_range(up, vp, ub, vb, u.size, v.size)
+        assert abs(part - rp) <= 1e-10 * max(abs(rp), 1e-30) and first == rf and last == rl
+        if prev is not None:
+            total += abs(prev[1] - prev[2]) * (first - prev[0])
+        total += part
+        ub, vb = ub + up.size, vb + vp.size
+        prev = (last, ub / u.size, vb / v.size)
+    ref = metrics_oracle.wasserstein_1d(u, v)
+    assert abs(total - ref) <= 1e-10 * ref
+
+
+def test_kde_grid_accumulate_and_jsd_match_oracle():
+    u, v = _gamma_pair(30_000, 20_000)
+    G = 2000
+    a, b = u.astype(np.float64), v.astype(np.float64)
+    lo, hi = min(a.min(), b.min()), max(a.max(), b.max())
+    hu = a.std(ddof=1) * a.size ** -0.2
+    hv = b.std(ddof=1) * b.size ** -0.2
+    grids = torch.zeros((2, G), dtype=torch.float64, device=DEV)
+    # two shards per sample accumulate into the same grid
+    ops.kde_grid_accumulate(torch.from_numpy(u[:11_000]).to(DEV), lo, hi, hu, grids[0])
+    ops.kde_grid_accumulate(torch.from_numpy(u[11_000:]).to(DEV), lo, hi, hu, grids[0])
+    ops.kde_grid_accumulate(torch.from_numpy(v).to(DEV), lo, hi, hv, grids[1])
+    j = ops.jsd_from_grids(grids)
+    ref = metrics_oracle.pdf_jsd(u, v, G)
+    assert abs(j - ref) <= 2e-5 * ref, (j, ref)
+    assert abs(j - ops.kde_jsd(torch.from_numpy(u).to(DEV), torch.from_numpy(v).to(DEV), G)) <= 1e-6 * ref
+
+
+def test_sharded_metrics_single_rank_group():
+    """world_size-1 NCCL group: the sharded entry points degenerate to the single-GPU kernels."""
+    import torch.distributed as dist
+    from nnueehcs_b200 import distributed as nd
+    import os, socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=DEV)
+    try:
+        u, v = _gamma_pair(200_000, 150_000)
+        tu, tv = torch.from_numpy(u).to(DEV), torch.from_numpy(v).to(DEV)
+        w = nd.wasserstein_1d_sharded(tu, tv)
+        j = nd.kde_jsd_sharded(tu, tv, 2000)
+        w_ref = metrics_oracle.wasserstein_1d(u, v)
+        j_ref = metrics_oracle.pdf_jsd(u, v, 2000)
+        assert abs(w - w_ref) <= 1e-10 * w_ref
+        assert abs(j - j_ref) <= 2e-5 * j_ref
+    finally:
+        if created:
+            dist.destroy_process_group()
