@@ -37,6 +37,10 @@ WORKLOADS = {
     "mcdropout100_binomial_10k": ("mc_dropout", 5, [128] * 6, 1, 100, 10000, 0.2),
     "deltauq32_binomial_4M": ("delta_uq", 5, [128] * 6, 1, 32, 1 << 22, 0.0),
     "mcdropout_1000x512_64k": ("mc_dropout", 5, [512] * 7, 1, 1000, 1 << 16, 0.2),
+    # configs[3] of BASELINE.json (MC dropout, 1000 passes x 8-layer width-1024 MLP) on a
+    # 64 k-sample slice of its 16 M samples, and the same net without dropout
+    "mcdropout_1000x1024_64k": ("mc_dropout", 5, [1024] * 7, 1, 1000, 1 << 16, 0.2),
+    "ensemble8x1024_256k": ("ensemble", 5, [1024] * 7, 1, 8, 1 << 18, 0.0),
 }
 DEFAULT_WORKLOAD = "ensemble16x512_1M"
 N_ROTATE = 8  # input buffers rotated per step so the working set exceeds the 126 MB L2
@@ -389,7 +393,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "peak_source": peaks["source"], "kernel": "uq_mlp_tc2_kernel (CTA pairs)"
+                         "peak_source": peaks["source"], "kernel": "uq_mlp_tc3_kernel (CTA pairs, 64 rows per CTA)" if max(widths) > 512 else "uq_mlp_tc2_kernel (CTA pairs)"
                          if precision == "bf16" else "sgemm_tn_kernel (fp32 CUDA cores)",
                          "flops_per_unit": F, "kernel_ms": kernel_ms,
                          "frac_of_sustained": achieved / peaks["sustained"]},

@@ -681,8 +681,9 @@ void tc_plan(uq_model* m) {
   for (int l = 0; l < L - 1; ++l) {
     if (m->layers[l].out != H) { t.why_not = "hidden widths differ"; return; }
   }
-  if (H % 64 != 0 || H < 64 || H > 512) {
-    t.why_not = "hidden width must be a multiple of 64 in [64, 512] (got " + std::to_string(H) + ")";
+  if ((H % 64 != 0 || H < 64 || H > 512) && !tc3_supported(H)) {
+    t.why_not = "hidden width must be a multiple of 64 in [64, 512], or 768 / 1024 (got " +
+                std::to_string(H) + ")";
     return;
   }
   const int NH = (H + 255) / 256;
@@ -843,15 +844,19 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
 #endif
 
   const int64_t units = (int64_t)p.n_tiles * p.splits;
-  // CTA-pair kernel (mlp_tc2.cu) for wide nets; narrow nets keep two independent CTAs per SM.
+  // CTA-pair kernel (mlp_tc2.cu) by default: measured faster than the one-CTA-per-tile kernel
+  // of this file at every width (H = 128: 75 vs 89 ms on deltauq32_binomial_4M).
   // UQ_TC_VARIANT=1|2 overrides (bring-up / A-B measurements).
-  int variant = (t.hidden > 128 && tc2_supported(t.hidden)) ? 2 : 1;
+  int variant = tc2_supported(t.hidden) ? 2 : 1;
   if (const char* v = getenv("UQ_TC_VARIANT")) {
     if (v[0] == '1') variant = 1;
     if (v[0] == '2' && tc2_supported(t.hidden)) variant = 2;
   }
+  if (t.hidden > 512) variant = 3;   // wide nets: 64 rows per CTA (mlp_tc3.cu)
   int rc;
-  if (variant == 2)
+  if (variant == 3)
+    rc = tc3_launch(p, t.hidden, dout_pad(t.d_out), st);
+  else if (variant == 2)
     rc = tc2_launch(p, t.hidden, dout_pad(t.d_out), st);
   else
     rc = (dout_pad(t.d_out) == 1) ? dispatch_h<1>(t.hidden, p, units, st)

@@ -1,0 +1,149 @@
+// Epilogue building blocks shared by the CTA-pair kernels (mlp_tc2.cu: 128 rows per CTA,
+// mlp_tc3.cu: 64 rows per CTA): network input fetch, dropout keep bits, the per-block
+// bias / dropout / ReLU / bf16-rounding math and the swizzled A-operand store.
+#pragma once
+#include "philox.cuh"
+#include "tc_params.cuh"
+#include "tc_ptx.cuh"
+
+#ifndef UQ_ABLATE
+#define UQ_ABLATE 0   // bring-up builds: 1 no A write-back, 2 no proxy fence, 3 no TMEM loads, 4 no bias
+#endif
+
+namespace uq {
+namespace tc {
+
+__device__ __forceinline__ float net_input2(const TcParams& p, int64_t row, int member_global,
+                                            int i) {
+  if (row >= p.n) return 0.f;
+  if (p.mode == UQ_MODE_DELTA_UQ) {
+    const int d = p.d_x;
+    const float a = __ldg(p.anchors + (int64_t)member_global * d + (i < d ? i : i - d));
+    return i < d ? __ldg(p.x + row * d + i) - a : a;
+  }
+  return __ldg(p.x + row * p.d_x + i);
+}
+
+// keep-mask bits of 32 consecutive features of one row
+__device__ __forceinline__ uint32_t keep_bits32(const TcParams& p, int drop, int kg, int drop_ord,
+                                                int64_t grow, int col0, const uint8_t* mask_layer,
+                                                int H) {
+  uint32_t keep = 0;
+  if (drop == 2) {
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq)
+      keep |= dropout_keep8(p.key, p.thr16, (uint32_t)kg, (uint32_t)drop_ord, (uint32_t)grow,
+                            (uint32_t)(col0 / 8 + gq))
+              << (8 * gq);
+  } else if (grow < p.n) {
+    const uint4* mrow = reinterpret_cast<const uint4*>(
+        mask_layer + ((size_t)kg * (size_t)p.n + (size_t)grow) * H + col0);
+    const uint4 m0 = __ldg(mrow), m1 = __ldg(mrow + 1);
+    const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      keep |= ((w[j] & 0xFFu) ? 1u : 0u) << (4 * j);
+      keep |= ((w[j] & 0xFF00u) ? 1u : 0u) << (4 * j + 1);
+      keep |= ((w[j] & 0xFF0000u) ? 1u : 0u) << (4 * j + 2);
+      keep |= ((w[j] & 0xFF000000u) ? 1u : 0u) << (4 * j + 3);
+    }
+  }
+  return keep;
+}
+
+// One NC-column block of one accumulator row: + bias, dropout, then either ReLU + bf16 rounding
+// into NC/2 packed words (cvt.rn[.relu].bf16x2) or the last-Linear dot product.
+template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST>
+__device__ __forceinline__ void epi_math(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
+                                         uint32_t keep, float keep_scale, uint32_t* packed,
+                                         const float* __restrict__ wl_s,
+                                         const float* __restrict__ wl_g, float (&dot)[DOUT]) {
+#if UQ_ABLATE == 5
+  if (LAST) { dot[0] += __uint_as_float(acc[0]) * 0.f; }
+  return;
+#endif
+  float v[NC];
+#pragma unroll
+  for (int j4 = 0; j4 < NC / 4; ++j4) {
+    v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + bv[j4].x;
+    v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + bv[j4].y;
+    v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + bv[j4].z;
+    v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + bv[j4].w;
+  }
+  if (DROP) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
+  }
+  if (!LAST) {
+#pragma unroll
+    for (int j2 = 0; j2 < NC / 2; ++j2)
+      packed[j2] = RELU ? cvt_relu_bf16x2(v[2 * j2], v[2 * j2 + 1]) : cvt_bf16x2(v[2 * j2], v[2 * j2 + 1]);
+  } else {
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (DOUT == 1) {
+      // four independent FMA chains (a single one is latency-bound: 4 cycles x 64 per chunk)
+      float s0 = dot[0], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < NC / 4; ++j4) {
+        const float4 wv = reinterpret_cast<const float4*>(wl_s)[j4];
+        s0 = fmaf(v[j4 * 4 + 0], wv.x, s0);
+        s1 = fmaf(v[j4 * 4 + 1], wv.y, s1);
+        s2 = fmaf(v[j4 * 4 + 2], wv.z, s2);
+        s3 = fmaf(v[j4 * 4 + 3], wv.w, s3);
+      }
+      dot[0] = (s0 + s1) + (s2 + s3);
+    } else {
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) {
+        float s = dot[o];
+#pragma unroll
+        for (int j4 = 0; j4 < NC / 4; ++j4) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wl_g + o * H) + j4);
+          s = fmaf(v[j4 * 4 + 0], wv.x, s);
+          s = fmaf(v[j4 * 4 + 1], wv.y, s);
+          s = fmaf(v[j4 * 4 + 2], wv.z, s);
+          s = fmaf(v[j4 * 4 + 3], wv.w, s);
+        }
+        dot[o] = s;
+      }
+    }
+  }
+}
+
+// NW packed words (NW/4 16-byte pieces starting at piece0) -> this row of a swizzled A chunk
+template <int NW>
+__device__ __forceinline__ void epi_store(const uint32_t* packed, uint32_t a_dst, int piece0,
+                                          int rx) {
+#pragma unroll
+  for (int pc = 0; pc < NW / 4; ++pc) {
+#if UQ_ABLATE != 1
+    st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4), packed[pc * 4 + 0],
+                 packed[pc * 4 + 1], packed[pc * 4 + 2], packed[pc * 4 + 3]);
+#else
+    if (packed[pc * 4] == 0x12345678u && packed[pc * 4 + 1] == packed[pc * 4 + 2])
+      st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4), packed[pc * 4 + 0],
+                   packed[pc * 4 + 1], packed[pc * 4 + 2], packed[pc * 4 + 3]);
+#endif
+  }
+}
+
+template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST>
+__device__ __forceinline__ void epi_block2(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
+                                           uint32_t keep, float keep_scale, uint32_t a_dst,
+                                           int piece0, int rx, const float* __restrict__ wl_s,
+                                           const float* __restrict__ wl_g, float (&dot)[DOUT]) {
+  uint32_t packed[NC / 2];
+  epi_math<H, DOUT, NC, RELU, DROP, LAST>(acc, bv, keep, keep_scale, packed, wl_s, wl_g, dot);
+  if (!LAST) epi_store<NC / 2>(packed, a_dst, piece0, rx);
+}
+
+template <int THREADS>
+__device__ __forceinline__ void epi_bar_sync_n() {
+  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+}
+
+}  // namespace tc
+}  // namespace uq

@@ -51,5 +51,8 @@ struct TcParams {
 // mlp_tc2.cu: CTA-pair (cta_group::2) variant of the fused kernel; same weight image
 int tc2_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st);
 bool tc2_supported(int hidden);
+// mlp_tc3.cu: CTA pairs with 64 rows per CTA for hidden widths 768 / 1024; same weight image
+int tc3_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st);
+bool tc3_supported(int hidden);
 
 }  // namespace uq

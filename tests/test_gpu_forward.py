@@ -356,3 +356,88 @@ def test_host_buffer_entry_point():
     packed.forward_host(x, out0, out1, "ensemble", total_members=k, precision="fp32")
     assert_close_ref(out0, g["mean"], RTOL32, what="host mean")
     assert_close_ref(out1, g["std"], RTOL32, scale_ref=g["mean"], what="host std")
+
+
+# ---- wide nets (hidden width 768 / 1024): the 64-rows-per-CTA pair kernel, mlp_tc3.cu -----------
+
+def _wide_arch(d_in, width, n_hidden, d_out, bn=True):
+    arch, prev = [], d_in
+    for _ in range(n_hidden):
+        arch.append({"Linear": {"args": [prev, width]}})
+        if bn:
+            arch.append({"BatchNorm1d": {"args": [width]}})
+        arch.append({"ReLU": {"inplace": True}})
+        prev = width
+    arch.append({"Linear": {"args": [prev, d_out]}})
+    return arch
+
+
+def _randomise_bn(net, seed):
+    gen = torch.Generator().manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=gen) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=gen) + 0.5)
+
+
+@pytest.mark.parametrize("width,n_hidden,k,n,d_out", [(1024, 2, 3, 300, 1), (1024, 7, 2, 129, 1),
+                                                      (768, 3, 2, 64, 3)])
+def test_wide_ensemble_bf16(width, n_hidden, k, n, d_out):
+    nets = []
+    for i in range(k):
+        torch.manual_seed(42 + i)
+        net = build_network(_wide_arch(5, width, n_hidden, d_out)).eval()
+        _randomise_bn(net, 1 + i)
+        nets.append(net)
+    x = torch.rand(n, 5, generator=torch.Generator().manual_seed(0))
+    packed = ops.PackedModel(nets, DEV)
+    assert packed.supports_bf16, packed.bf16_reason
+    mean, std = packed.forward(x.to(DEV), "ensemble", total_members=k, precision="bf16")
+    ref_mean, ref_std = uq_oracle.ensemble_forward(nets, x)
+    _bf16_check(mean, std, ref_mean, ref_std, f"wide ensemble {width}x{n_hidden}")
+    # K-axis shards of the same forward merge to the same result
+    m_a, s_a = packed.forward(x.to(DEV), "ensemble", total_members=k, precision="bf16",
+                              member_begin=0, member_count=1, output="moments")
+    m_b, s_b = packed.forward(x.to(DEV), "ensemble", total_members=k, precision="bf16",
+                              member_begin=1, member_count=k - 1, output="moments")
+    mm, ss = ops.moments_merge(torch.stack([m_a, m_b]), torch.stack([s_a, s_b]), [1, k - 1])
+    assert float((mm - mean).abs().max()) <= 1e-5 * float(mean.abs().max())
+    assert float((ss - std).abs().max()) <= 1e-4 * float(std.abs().max()) + 1e-6
+
+
+def test_wide_mc_dropout_philox_replays_through_oracle():
+    p, passes, seed, n = 0.2, 6, 77, 150
+    torch.manual_seed(42)
+    net = build_network(mc_arch_with_dropout(_wide_arch(5, 1024, 3, 1), p)).eval()
+    _randomise_bn(net, 1)
+    packed = ops.PackedModel([net], DEV)
+    assert packed.supports_bf16, packed.bf16_reason
+    x_cpu = torch.rand(n, 5, generator=torch.Generator().manual_seed(5))
+    mean, std = packed.forward(x_cpu.to(DEV), "mc_dropout", total_members=passes, precision="bf16",
+                               dropout_p=p, seed=seed)
+    flat = ops.philox_keep_masks(n, packed.dropout_widths, passes, p, seed, 0, DEV)
+    masks = injected_to_masks(flat.cpu(), n, packed.dropout_widths, passes)
+    ref_mean, ref_std = uq_oracle.mc_dropout_forward(net, x_cpu, passes, p, masks=masks)
+    _bf16_check(mean, std, ref_mean, ref_std, "wide philox replay")
+    mean_i, std_i = packed.forward(x_cpu.to(DEV), "mc_dropout", total_members=passes,
+                                   precision="bf16", dropout_p=p, masks=flat)
+    assert torch.equal(mean, mean_i) and torch.equal(std, std_i)
+    # many passes over few samples: the member axis is split over CTA pairs and merged
+    mean_s, std_s = packed.forward(x_cpu[:70].to(DEV), "mc_dropout", total_members=96,
+                                   precision="bf16", dropout_p=p, dropout_active=False)
+    # dropout off: 96 identical passes -> zero spread
+    assert float(std_s.abs().max()) <= 1e-3 * float(mean_s.abs().max())
+
+
+def test_wide_delta_uq_bf16():
+    k, n = 4, 200
+    torch.manual_seed(42)
+    net = build_network(delta_arch(_wide_arch(5, 768, 2, 1))).eval()
+    _randomise_bn(net, 1)
+    packed = ops.PackedModel([net], DEV)
+    x = torch.rand(n, 5, generator=torch.Generator().manual_seed(2))
+    anchors = torch.rand(k, 5, generator=torch.Generator().manual_seed(3))
+    mean, std = packed.forward(x.to(DEV), "delta_uq", total_members=k, precision="bf16",
+                               anchors=anchors.to(DEV))
+    ref_mean, ref_std = uq_oracle.delta_uq_forward(net, x, anchors, k)
+    _bf16_check(mean, std, ref_mean, ref_std, "wide delta_uq")

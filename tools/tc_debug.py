@@ -102,6 +102,14 @@ def main():
     ok &= case("16x[512]*3 n=40000", [512] * 3, 16, 40000)
     ok &= case("2x[192]*2 n=200 d_out=3", [192] * 2, 2, 200, d_out=3)
     ok &= case("2x[384]*2 n=200", [384] * 2, 2, 200)
+    if os.environ.get("UQ_TC_DEBUG_WIDE", "1") == "1":
+        ok &= hidden_probe([1024, 1024], n=64)
+        ok &= hidden_probe([1024, 1024], n=128)
+        ok &= case("2x[1024]*1 n=64", [1024], 2, 64)
+        ok &= case("2x[1024]*2 n=64", [1024] * 2, 2, 64)
+        ok &= case("3x[1024]*3 n=1000", [1024] * 3, 3, 1000)
+        ok &= case("2x[768]*3 n=300 d_out=2", [768] * 3, 2, 300, d_out=2)
+        ok &= case("4x[1024]*7 n=20000", [1024] * 7, 4, 20000)
     print("ALL OK" if ok else "SOME FAILED")
     return 0 if ok else 1
 
