@@ -41,6 +41,8 @@ WORKLOADS = {
     # 64 k-sample slice of its 16 M samples, and the same net without dropout
     "mcdropout_1000x1024_64k": ("mc_dropout", 5, [1024] * 7, 1, 1000, 1 << 16, 0.2),
     "ensemble8x1024_256k": ("ensemble", 5, [1024] * 7, 1, 8, 1 << 18, 0.0),
+    # the binomial-options surrogate as a 32-member ensemble (same flops as deltauq32_binomial_4M)
+    "ensemble32x128_4M": ("ensemble", 5, [128] * 6, 1, 32, 1 << 22, 0.0),
 }
 DEFAULT_WORKLOAD = "ensemble16x512_1M"
 N_ROTATE = 8  # input buffers rotated per step so the working set exceeds the 126 MB L2

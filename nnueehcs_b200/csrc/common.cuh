@@ -66,6 +66,10 @@ struct TcPlan {
   __nv_bfloat16* image = nullptr;  // [K][stages_per_member][stage_bytes]
   float* w_last = nullptr;         // [K][d_out][H] fp32 (dropout scale NOT folded; see kernel)
   float* b_last = nullptr;         // [K][d_out]
+  // Delta-UQ variant of the image (single network with an even input width): layer 0 holds only
+  // the columns that multiply x; the anchor enters as a per-anchor bias (see tc_forward)
+  __nv_bfloat16* image_delta = nullptr;
+  int k0_delta = 0;
 };
 
 }  // namespace uq

@@ -33,7 +33,7 @@ using namespace tc;
 // Writes one member's stages.  Stage order == consumption order of the kernel:
 //   layer 0: NH stages (K0 real columns, [w_hi | w_hi | w_lo] split), layer l>=1: NH x KC stages.
 __global__ void pack_image_kernel(__nv_bfloat16* __restrict__ image, const float* __restrict__ w,
-                                  const float* __restrict__ alpha, int layer, int in, int H,
+                                  const float* __restrict__ alpha, int layer, int in, int ld, int H,
                                   int n_tile, int NH, int KC, int K0, int split_s,
                                   size_t stage_elems, int stage_base) {
   // one thread per (stage-local row, 16-byte piece)
@@ -56,13 +56,13 @@ __global__ void pack_image_kernel(__nv_bfloat16* __restrict__ image, const float
     if (layer == 0) {
       const int seg = col / in, ii = col - seg * in;
       if (seg < split_s && col < K0) {
-        const float f = w[(int64_t)n * in + ii] * sc;
+        const float f = w[(int64_t)n * ld + ii] * sc;
         const float hi = __bfloat162float(__float2bfloat16_rn(f));
         out = (seg == 2) ? (f - hi) : hi;        // [hi | hi | lo]
       }
     } else {
       const int kk = kc * 64 + col;
-      out = w[(int64_t)n * in + kk] * sc;
+      out = w[(int64_t)n * ld + kk] * sc;
     }
     vals[e] = __float2bfloat16_rn(out);
   }
@@ -134,13 +134,38 @@ void tc_plan(uq_model* m) {
   t.n_tile = n_tile;
   t.stage_bytes = (size_t)n_tile * 128;
   t.stages_per_member = NH + (L - 2) * NH * (H / 64);
+  t.k0_delta = 0;
+  if (m->n_members == 1 && d_in % 2 == 0) {
+    const int dx = d_in / 2;
+    int sd = 3;
+    while (sd > 1 && sd * dx > 64) --sd;
+    t.k0_delta = ((sd * dx + 15) / 16) * 16;
+  }
   t.ok = true;
 }
 
-static int split_factor(const TcPlan& t) {
+static int split_factor_of(int d_in) {
   int s = 3;
-  while (s > 1 && s * t.d_in > 64) --s;
+  while (s > 1 && s * d_in > 64) --s;
   return s;
+}
+static int split_factor(const TcPlan& t) { return split_factor_of(t.d_in); }
+
+// Delta-UQ: bias0[k][h] = b0'[h] + sum_i (W0'[h][dx + i] - W0'[h][i]) a_k[i]   (W0', b0' = layer 0
+// with eval-BatchNorm folded), so that  W0' [x - a_k; a_k] + b0' = W0'[:, :dx] x + bias0[k]
+__global__ void delta_bias_kernel(const float* __restrict__ w0, const float* __restrict__ alpha,
+                                  const float* __restrict__ bias_folded,
+                                  const float* __restrict__ anchors, int H, int dx, int n_anchors,
+                                  int anchor_begin, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_anchors * H) return;
+  const int h = i % H, k = anchor_begin + i / H;
+  const float sc = alpha ? alpha[h] : 1.0f;
+  float acc = bias_folded[h];
+  for (int j = 0; j < dx; ++j)
+    acc = fmaf((w0[(int64_t)h * 2 * dx + dx + j] - w0[(int64_t)h * 2 * dx + j]) * sc,
+               anchors[(int64_t)k * dx + j], acc);
+  out[(int64_t)k * H + h] = acc;
 }
 
 int tc_pack(uq_model* m, cudaStream_t st) {
@@ -162,11 +187,28 @@ int tc_pack(uq_model* m, cudaStream_t st) {
       const int64_t total = (int64_t)stages * t.n_tile * 8;
       pack_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
           t.image + (size_t)k * member_elems, ly.w + (size_t)k * ly.out * ly.in,
-          ly.has_bn ? ly.alpha + (size_t)k * ly.out : nullptr, l, ly.in, H, t.n_tile, NH, KC,
-          t.k0, s, stage_elems, stage_base);
+          ly.has_bn ? ly.alpha + (size_t)k * ly.out : nullptr, l, ly.in, ly.in, H, t.n_tile, NH,
+          KC, t.k0, s, stage_elems, stage_base);
       UQ_LAUNCH_CHECK();
       stage_base += stages;
     }
+  }
+  if (t.k0_delta > 0) {
+    // same stages, except that layer 0 keeps only the d_in/2 columns that multiply x
+    void* pd = nullptr;
+    UQ_CUDA(cudaMalloc(&pd, member_elems * sizeof(__nv_bfloat16)));
+    m->allocations.push_back(pd);
+    t.image_delta = static_cast<__nv_bfloat16*>(pd);
+    UQ_CUDA(cudaMemcpyAsync(pd, t.image, member_elems * sizeof(__nv_bfloat16),
+                            cudaMemcpyDeviceToDevice, st));
+    UQ_CUDA(cudaMemsetAsync(pd, 0, (size_t)NH * t.stage_bytes, st));
+    const Layer& l0 = m->layers[0];
+    const int dx = l0.in / 2;
+    const int64_t total = (int64_t)NH * t.n_tile * 8;
+    pack_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        t.image_delta, l0.w, l0.has_bn ? l0.alpha : nullptr, 0, dx, l0.in, H, t.n_tile, NH, KC,
+        t.k0_delta, split_factor_of(dx), stage_elems, 0);
+    UQ_LAUNCH_CHECK();
   }
   for (int l = 0; l < m->n_layers; ++l) {
     const Layer& ly = m->layers[l];
@@ -195,11 +237,14 @@ int tc_pack(uq_model* m, cudaStream_t st) {
 }
 
 static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a) {
-  const int64_t tiles = (n + TILE_M - 1) / TILE_M;
+  // sample rows one cluster (CTA pair) works on at a time
+  const bool narrow = tc4_supported(m->tc.hidden, dout_pad(m->tc.d_out)) && !getenv("UQ_TC_NO_SLOTS");
+  const int64_t rows = m->tc.hidden > 512 ? TILE_M : narrow ? tc4_rows_per_unit() : 2 * TILE_M;
+  const int64_t units = (n + rows - 1) / rows;
   int splits = 1;
   if (a->output == UQ_OUT_MOMENTS) return 1;  // a K-shard hands raw moments to the caller
-  // few sample tiles but many members/passes: also spread the member axis over the SMs
-  while (tiles * splits < 2 * 148 && a->member_count / (splits * 2) >= 4 && splits < 64) splits *= 2;
+  // few sample tiles but many members/passes: also spread the member axis over the 74 SM pairs
+  while (units * splits < 148 && a->member_count / (splits * 2) >= 4 && splits < 64) splits *= 2;
   return splits;
 }
 
@@ -207,6 +252,8 @@ size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a
   const int splits = choose_splits(m, n, a);
   size_t b = 256;  // error flag
   if (splits > 1) b += 2 * (size_t)splits * (size_t)n * m->d_out * sizeof(float) + 512;
+  if (a->mode == UQ_MODE_DELTA_UQ)  // per-anchor layer-0 bias [total_members][H]
+    b += (((size_t)a->total_members * m->tc.hidden * sizeof(float)) + 255) & ~(size_t)255;
   return b;
 }
 
@@ -263,6 +310,31 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
     p.part_m2 = reinterpret_cast<float*>(wsb + 256 + part);
   }
   UQ_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(unsigned int), st));
+  if (a->mode == UQ_MODE_DELTA_UQ) {
+    // anchors -> per-anchor layer-0 bias; the kernels then see plain x (d_in / 2 inputs), shared
+    // weights and no per-member input rebuild
+    UQ_REQUIRE(t.image_delta != nullptr, UQ_ERR_UNSUPPORTED,
+               "Delta-UQ bf16 path needs a single packed network with an even input width");
+    size_t off = 256;
+    if (p.splits > 1)
+      off += 2 * ((((size_t)p.splits * (size_t)n * m->d_out * sizeof(float)) + 255) & ~(size_t)255);
+    float* bias0 = reinterpret_cast<float*>(wsb + off);
+    const Layer& l0 = m->layers[0];
+    const int dx = m->d_in / 2;
+    const int total = a->member_count * t.hidden;
+    delta_bias_kernel<<<(total + 255) / 256, 256, 0, st>>>(
+        l0.w, l0.has_bn ? l0.alpha : nullptr, l0.bias_folded, a->anchors, t.hidden, dx,
+        a->member_count, a->member_begin, bias0);
+    UQ_LAUNCH_CHECK();
+    p.bias[0] = bias0;
+    p.bias0_per_member = 1;
+    p.image = reinterpret_cast<const uint8_t*>(t.image_delta);
+    p.d_in = dx;
+    p.K0 = t.k0_delta;
+    p.split_s = split_factor_of(dx);
+    p.mode = UQ_MODE_MC_DROPOUT;   // shared weights, members differ only in bias0
+    p.anchors = nullptr;
+  }
 #ifdef UQ_TC_TRACE
   const char* trace_env = getenv("UQ_TC_TRACE_FILE");
   unsigned long long* d_trace = nullptr;
@@ -273,7 +345,9 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.trace = d_trace;
 #endif
 
+  const bool narrow = tc4_supported(t.hidden, dout_pad(t.d_out)) && !getenv("UQ_TC_NO_SLOTS");
   const int rc = t.hidden > 512 ? tc3_launch(p, t.hidden, dout_pad(t.d_out), st)
+                 : narrow       ? tc4_launch(p, t.hidden, st)
                                 : tc2_launch(p, t.hidden, dout_pad(t.d_out), st);
   if (rc != UQ_OK) return rc;
 #ifdef UQ_TC_TRACE

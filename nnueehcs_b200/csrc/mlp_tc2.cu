@@ -525,33 +525,9 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     // K0/8 LDS/STS pairs at the moment the chunk becomes free.
     const bool use_stash = p.K0 <= 32;
     auto build_x = [&](int tile, int member_global, bool to_stash) {
-      if (grp == 0) {
-        const int64_t grow = (int64_t)tile * TILE_M + row;
-        const int d = p.d_in;
-        int seg = 0, i = 0;
-        for (int piece = 0; piece < p.K0 / 8; ++piece) {
-          uint32_t w4[4];
-#pragma unroll
-          for (int h2 = 0; h2 < 4; ++h2) {
-            float v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              float out = 0.f;
-              if (seg < p.split_s) {
-                const float f = net_input2(p, grow, member_global, i);
-                const float hi = __bfloat162float(__float2bfloat16_rn(f));
-                out = (seg == 1) ? (f - hi) : hi;   // [hi | lo | hi]
-              }
-              v[e] = out;
-              if (++i == d) { i = 0; ++seg; }
-            }
-            w4[h2] = pack_bf16x2(v[0], v[1]);
-          }
-          st_shared_v4(to_stash ? xstash + (uint32_t)((piece * TILE_M + row) << 4)
-                                : a_row + (uint32_t)((piece ^ rx) << 4),
-                       w4[0], w4[1], w4[2], w4[3]);
-        }
-      }
+      if (grp == 0)
+        build_x_row(p, (int64_t)tile * TILE_M + row, member_global, to_stash,
+                    xstash + (uint32_t)(row << 4), (uint32_t)(TILE_M << 4), a_row, rx);
     };
     // chunk 0 <- stash (or built in place when the stash is too small), then signal the MMA warp
     auto publish_x = [&](int tile, int member_global) {
@@ -578,7 +554,8 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     auto aux_prefetch = [&](int member_global, int l) {
       const int wslot = p.shared_weights ? 0 : member_global;
       const bool last = (l == p.L_mma - 1);
-      const float* bias = p.bias[l] + (size_t)wslot * H;
+      const float* bias =
+          p.bias[l] + (size_t)((l == 0 && p.bias0_per_member) ? member_global : wslot) * H;
       const float* wl = p.w_last + (size_t)wslot * DOUT * H;
 #pragma unroll
       for (int j = 0; j < AUX_PER_THREAD; ++j) {
@@ -646,7 +623,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           else if (have_next) aux_prefetch(p.member_begin + nk, 0);
           // refresh the x stash while the last layer's MMAs run (its previous content went into
           // chunk 0 one member ago)
-          if (last && have_next && use_stash && (p.mode == UQ_MODE_DELTA_UQ || ntile != tile))
+          if (last && have_next && use_stash && (ntile != tile))
             build_x(ntile, p.member_begin + nk, true);
 
           DrainCtx cx;

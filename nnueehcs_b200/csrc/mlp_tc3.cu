@@ -320,33 +320,9 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
 
     const bool use_stash = p.K0 <= 32;
     auto build_x = [&](int tile, int member_global, bool to_stash) {
-      if (x_owner) {
-        const int64_t grow = (int64_t)tile * ROWS + row;
-        const int d = p.d_in;
-        int seg = 0, i = 0;
-        for (int piece = 0; piece < p.K0 / 8; ++piece) {
-          uint32_t w4[4];
-#pragma unroll
-          for (int h2 = 0; h2 < 4; ++h2) {
-            float v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              float out = 0.f;
-              if (seg < p.split_s) {
-                const float f = net_input2(p, grow, member_global, i);
-                const float hi = __bfloat162float(__float2bfloat16_rn(f));
-                out = (seg == 1) ? (f - hi) : hi;   // [hi | lo | hi]
-              }
-              v[e] = out;
-              if (++i == d) { i = 0; ++seg; }
-            }
-            w4[h2] = pack_bf16x2(v[0], v[1]);
-          }
-          st_shared_v4(to_stash ? xstash + (uint32_t)((piece * ROWS + row) << 4)
-                                : a_row + (uint32_t)((piece ^ rx) << 4),
-                       w4[0], w4[1], w4[2], w4[3]);
-        }
-      }
+      if (x_owner)
+        build_x_row(p, (int64_t)tile * ROWS + row, member_global, to_stash,
+                    xstash + (uint32_t)(row << 4), (uint32_t)(ROWS << 4), a_row, rx);
     };
     auto publish_x = [&](int tile, int member_global) {
       if (x_owner) {
@@ -371,7 +347,8 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
     auto aux_prefetch = [&](int member_global, int l) {
       const int wslot = p.shared_weights ? 0 : member_global;
       const bool last = (l == p.L_mma - 1);
-      const float* bias = p.bias[l] + (size_t)wslot * H;
+      const float* bias =
+          p.bias[l] + (size_t)((l == 0 && p.bias0_per_member) ? member_global : wslot) * H;
       const float* wl = p.w_last + (size_t)wslot * DOUT * H;
 #pragma unroll
       for (int j = 0; j < AUX_PER_THREAD; ++j) {
@@ -434,7 +411,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
           epi_bar_sync_n<EPI_THREADS>();
           if (!last) aux_prefetch(kg, l + 1);
           else if (have_next) aux_prefetch(p.member_begin + nk, 0);
-          if (last && have_next && use_stash && (p.mode == UQ_MODE_DELTA_UQ || ntile != tile))
+          if (last && have_next && use_stash && (ntile != tile))
             build_x(ntile, p.member_begin + nk, true);
 
           if (lane == 0) mbar_wait(bars + B3_D_FULL, g & 1, p.error_flag, 5);

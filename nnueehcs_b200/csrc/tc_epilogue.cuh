@@ -13,15 +13,51 @@
 namespace uq {
 namespace tc {
 
+// Network input i of a sample row.  Delta-UQ never reaches this with anchors: W0 [x - a; a] + b0
+// = W0a x + (b0 + (W0b - W0a) a), so the kernels see plain x and a per-anchor layer-0 bias.
 __device__ __forceinline__ float net_input2(const TcParams& p, int64_t row, int member_global,
                                             int i) {
+  (void)member_global;
   if (row >= p.n) return 0.f;
-  if (p.mode == UQ_MODE_DELTA_UQ) {
-    const int d = p.d_x;
-    const float a = __ldg(p.anchors + (int64_t)member_global * d + (i < d ? i : i - d));
-    return i < d ? __ldg(p.x + row * d + i) - a : a;
-  }
   return __ldg(p.x + row * p.d_x + i);
+}
+
+// Layer-0 A operand of one sample row: K0 bf16 values [x_hi | x_lo | x_hi | 0 ...] (split_s
+// segments of d_in network inputs each), written as 2-byte shared stores either into the x stash
+// (piece-major: piece * stash_piece_stride) or straight into the swizzled chunk-0 row.  All
+// global loads of the row are issued before the first is used -- the obvious loop over output
+// columns serialises one L1/L2 round trip per element (~4500 cycles per call, measured).
+static __device__ __noinline__ void build_x_row(const TcParams& p, int64_t grow, int member_global,
+                                                bool to_stash, uint32_t stash_row_addr,
+                                                uint32_t stash_piece_stride, uint32_t a_row,
+                                                int rx) {
+  const int d = p.d_in;
+  auto addr = [&](int col) -> uint32_t {
+    const int piece = col >> 3;
+    const uint32_t b = to_stash ? stash_row_addr + (uint32_t)piece * stash_piece_stride
+                                : a_row + (uint32_t)((piece ^ rx) << 4);
+    return b + (uint32_t)((col & 7) << 1);
+  };
+  auto st16 = [&](uint32_t a, __nv_bfloat16 v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(*reinterpret_cast<const uint16_t*>(&v))
+                 : "memory");
+  };
+#pragma unroll 1
+  for (int i0 = 0; i0 < d; i0 += 32) {
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = (i0 + i < d) ? net_input2(p, grow, member_global, i0 + i) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i0 + i < d) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(f[i]);
+        st16(addr(i0 + i), hi);
+        if (p.split_s > 1) st16(addr(d + i0 + i), __float2bfloat16_rn(f[i] - __bfloat162float(hi)));
+        if (p.split_s > 2) st16(addr(2 * d + i0 + i), hi);
+      }
+    }
+  }
+  for (int col = p.split_s * d; col < p.K0; ++col) st16(addr(col), __float2bfloat16_rn(0.f));
 }
 
 // keep-mask bits of 32 consecutive features of one row

@@ -25,6 +25,7 @@ struct TcParams {
   int K0, split_s, L_mma, d_out;
   int stages_per_member;
   int shared_weights;
+  int bias0_per_member;  // layer-0 bias is indexed by the global member id (Delta-UQ anchors)
   const uint8_t* image;
   const float* bias[MAX_MMA_LAYERS];  // [K or 1][H] folded bias per MMA layer
   uint32_t relu_mask, dropout_mask;   // bit l: MMA layer l has ReLU / dropout on its output
@@ -54,5 +55,9 @@ bool tc2_supported(int hidden);
 // mlp_tc3.cu: CTA pairs with 64 rows per CTA for hidden widths 768 / 1024; same weight image
 int tc3_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st);
 bool tc3_supported(int hidden);
+// mlp_tc4.cu: CTA pairs with four sample tiles in flight per CTA for hidden widths 64 / 128, d_out 1
+int tc4_launch(const tc::TcParams& p, int hidden, cudaStream_t st);
+bool tc4_supported(int hidden, int dout_pad);
+int tc4_rows_per_unit();
 
 }  // namespace uq
