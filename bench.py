@@ -48,6 +48,16 @@ DEFAULT_WORKLOAD = "ensemble16x512_1M"
 N_ROTATE = 8  # input buffers rotated per step so the working set exceeds the 126 MB L2
 
 
+def kernel_name(widths, d_out):
+    """Which fused kernel the library dispatches to (csrc/mlp_tc.cu:tc_forward)."""
+    h = max(widths)
+    if h > 512:
+        return "uq_mlp_tc3_kernel (CTA pairs, 64 rows per CTA)"
+    if h <= 128 and d_out == 1:
+        return "uq_mlp_tc4_kernel (CTA pairs, 4 tile slots per CTA)"
+    return "uq_mlp_tc2_kernel (CTA pairs)"
+
+
 def flops_per_unit(d_in, widths, d_out):
     dims = [d_in] + list(widths) + [d_out]
     return 2 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
@@ -395,7 +405,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "peak_source": peaks["source"], "kernel": "uq_mlp_tc3_kernel (CTA pairs, 64 rows per CTA)" if max(widths) > 512 else "uq_mlp_tc2_kernel (CTA pairs)"
+                         "peak_source": peaks["source"], "kernel": kernel_name(widths, d_out)
                          if precision == "bf16" else "sgemm_tn_kernel (fp32 CUDA cores)",
                          "flops_per_unit": F, "kernel_ms": kernel_ms,
                          "frac_of_sustained": achieved / peaks["sustained"]},

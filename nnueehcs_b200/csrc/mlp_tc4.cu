@@ -12,8 +12,10 @@
 // the tensor core is already working on slots t+1.. -- the latency chain of one slot is hidden
 // behind the MMAs of the other three.
 //
-// Per slot: D_FULL[t] (layer accumulated, commit multicast), DRAINED[t] (all 16 epilogue warps of
-// the pair are done with the slot's accumulator and have rewritten its A chunks), X_READY[t].
+// Per slot: D_FULL[t] (layer accumulated, commit multicast), DRAINED[t] (the slot's 8 epilogue warps
+// of the pair are done with its accumulator and have rewritten its A chunks), X_READY[t].  Epilogue
+// warp group g owns the slots t with t % 2 == g (whole rows: no cross-warp exchange for the last
+// Linear's dot product), so two slots are drained concurrently.
 // Everything else (split weight stages, peer relay, bias staging, in-place bf16 write-back,
 // CUDA-core last Linear + per-row Welford) follows mlp_tc2.cu.
 //
@@ -52,10 +54,9 @@ struct Geo4 {
   static constexpr int A_BYTES = TS * A_SLOT_BYTES;
   static constexpr int AUX_FLOATS = 2 * H;               // bias + w_last of one step
   static constexpr int AUX_BYTES = 2 * AUX_FLOATS * 4;
-  static constexpr int XCHG_SLOT_BYTES = 2 * TILE_M * 4; // [2 parities][128 rows] partial dots
   static constexpr int XS_SLOT_BYTES = TILE_M * 64;      // x stash (K0 <= 32)
   static constexpr int BAR_BYTES = 384;
-  static constexpr int MISC_BYTES = 1024 + BAR_BYTES + TS * (XCHG_SLOT_BYTES + XS_SLOT_BYTES);
+  static constexpr int MISC_BYTES = 1024 + BAR_BYTES + TS * XS_SLOT_BYTES;
   static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES;
   static constexpr int NS_RAW = BUDGET / HALF_BYTES;
   static constexpr int NSTAGES = NS_RAW > 8 ? 8 : NS_RAW;
@@ -66,21 +67,21 @@ struct Geo4 {
 constexpr uint32_t B4_W_FULL = 0;       // 8 x 8 B
 constexpr uint32_t B4_W_EMPTY = 64;     // 8 x 8 B
 constexpr uint32_t B4_D_FULL = 128;     // TS x 8 B   commit multicast
-constexpr uint32_t B4_DRAINED = 160;    // TS x 8 B   leader only: 8 warps of each CTA
+constexpr uint32_t B4_DRAINED = 160;    // TS x 8 B   leader only: 4 warps of each CTA
 constexpr uint32_t B4_X_READY = 192;    // TS x 8 B   leader only: 4 warps of each CTA
 constexpr uint32_t B4_TMEM_PTR = 224;
 
-// drain this warp's chunks (c = grp, grp + 2, ... < KC) of one slot
+// drain all chunks of one slot (this warp: 32 rows of it)
 template <int H, bool RELU, bool DROP, bool LAST>
 __device__ __forceinline__ void drain4(const TcParams& p, uint32_t lane_addr, uint32_t a_row, int rx,
-                                       int grp, const float* bias_s, const float* wl_s, int drop,
+                                       const float* bias_s, const float* wl_s, int drop,
                                        int kg, int drop_ord, int64_t grow,
                                        const uint8_t* mask_layer, float (&dot)[1]) {
   constexpr int KC = H / CHUNK_K;
   uint32_t acc0[32], acc1[32];
-  if (grp < KC) tmem_ld32(lane_addr + (uint32_t)(grp * CHUNK_K), acc0);
+  tmem_ld32(lane_addr, acc0);
 #pragma unroll 1
-  for (int c = grp; c < KC; c += NG4) {
+  for (int c = 0; c < KC; ++c) {
     const int col0 = c * CHUNK_K;
     const uint32_t a_dst = a_row + (uint32_t)c * CHUNK_BYTES;
     uint32_t keep = 0xffffffffu;
@@ -96,7 +97,7 @@ __device__ __forceinline__ void drain4(const TcParams& p, uint32_t lane_addr, ui
     for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
     if (DROP) keep = keep_bits32(p, drop, kg, drop_ord, grow, col0 + 32, mask_layer, H);
     tmem_ld_wait();
-    if (c + NG4 < KC) tmem_ld32(lane_addr + (uint32_t)(col0 + NG4 * CHUNK_K), acc0);
+    if (c + 1 < KC) tmem_ld32(lane_addr + (uint32_t)(col0 + CHUNK_K), acc0);
     epi_block2<H, 1, 32, RELU, DROP, LAST>(acc1, bv, keep, p.drop_scale, a_dst, 4, rx,
                                            wl_s + col0 + 32, wl_s + col0 + 32, dot);
   }
@@ -116,8 +117,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
   uint8_t* w_smem = smem + G::A_BYTES;                     // NS half-stages
   float* aux_smem = reinterpret_cast<float*>(w_smem + NS * HALF_BYTES);
   uint8_t* bar_smem = reinterpret_cast<uint8_t*>(aux_smem) + G::AUX_BYTES;
-  const uint32_t xchg = smem_u32(bar_smem + G::BAR_BYTES);           // [TS][2][128] floats
-  const uint32_t xstash = xchg + TS * G::XCHG_SLOT_BYTES;            // [TS][K0/8][128] x 16 B
+  const uint32_t xstash = smem_u32(bar_smem + G::BAR_BYTES);         // [TS][K0/8][128] x 16 B
   const uint32_t a_base = smem_u32(a_smem);
   const uint32_t w_base = smem_u32(w_smem);
   const uint32_t bars = smem_u32(bar_smem);
@@ -137,7 +137,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
     }
     for (int t = 0; t < TS; ++t) {
       mbar_init(bars + B4_D_FULL + 8 * t, 1);
-      mbar_init(bars + B4_DRAINED + 8 * t, 2 * NG4 * 4);
+      mbar_init(bars + B4_DRAINED + 8 * t, 8);
       mbar_init(bars + B4_X_READY + 8 * t, 8);
     }
     fence_barrier_init();
@@ -282,13 +282,13 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
 
     const bool use_stash = p.K0 <= 32;
     auto build_x = [&](int t, int tile, int member_global, bool to_stash) {
-      if (grp == 0)
+      if ((t % NG4) == grp)
         build_x_row(p, (int64_t)tile * TILE_M + row, member_global, to_stash,
                     xstash + (uint32_t)(t * G::XS_SLOT_BYTES + (row << 4)), (uint32_t)(TILE_M << 4),
                     a_row0 + (uint32_t)(t * G::A_SLOT_BYTES), rx);
     };
     auto publish_x = [&](int t, int tile, int member_global) {
-      if (grp == 0) {
+      if ((t % NG4) == grp) {
         if (use_stash) {
           for (int piece = 0; piece < p.K0 / 8; ++piece) {
             uint32_t a, b, c, d;
@@ -332,9 +332,10 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
       const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
       const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
 
-      float wf_n = 0.f, wf_mean[TS], wf_m2[TS];
+      constexpr int OWN = TS / NG4;   // slots owned by this warp's group: t = grp + NG4 * j
+      float wf_n = 0.f, wf_mean[OWN], wf_m2[OWN];
 #pragma unroll
-      for (int t = 0; t < TS; ++t) wf_mean[t] = 0.f, wf_m2[t] = 0.f;
+      for (int j = 0; j < OWN; ++j) wf_mean[j] = 0.f, wf_m2[j] = 0.f;
 
       if (first_step) {
 #pragma unroll 1
@@ -349,9 +350,9 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
       for (int k = mb; k < me; ++k, ++mcount) {
         const int kg = p.member_begin + k;
         const int wslot = p.shared_weights ? 0 : kg;
-        float dot[TS];   // last-Linear partial dot product of each slot (this warp's chunks)
+        float dot[OWN];  // last-Linear dot product of each owned slot's row
 #pragma unroll
-        for (int t = 0; t < TS; ++t) dot[t] = 0.f;
+        for (int j = 0; j < OWN; ++j) dot[j] = 0.f;
         int drop_ord = 0;
         const uint8_t* mask_layer = p.masks;
 
@@ -385,7 +386,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           }
 
 #pragma unroll 1   // one copy of the drain code for all slots (it is ~1.5 k instructions)
-          for (int t = 0; t < TS; ++t) {
+          for (int t = grp; t < TS; t += NG4) {
             float dslot[1] = {0.f};
             if (lane == 0) mbar_wait(bars + B4_D_FULL + 8 * t, g & 1, p.error_flag, 5);
             __syncwarp();
@@ -396,7 +397,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
             const uint32_t a_row = a_row0 + (uint32_t)(t * G::A_SLOT_BYTES);
             const int64_t grow = (int64_t)tile_of(unit, t) * TILE_M + row;
 #define UQ_DRAIN4(R, D, L)                                                                        \
-  drain4<H, R, D, L>(p, lane_addr, a_row, rx, grp, aux, aux + H, drop, kg, drop_ord, grow,        \
+  drain4<H, R, D, L>(p, lane_addr, a_row, rx, aux, aux + H, drop, kg, drop_ord, grow,             \
                      mask_layer, dslot)
             if (last) {
               if (relu) { if (drop) UQ_DRAIN4(true, true, true); else UQ_DRAIN4(true, false, true); }
@@ -408,8 +409,8 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
 #undef UQ_DRAIN4
             if (last) {
 #pragma unroll
-              for (int tt = 0; tt < TS; ++tt)
-                if (tt == t) dot[tt] = dslot[0];
+              for (int j = 0; j < OWN; ++j)
+                if (grp + NG4 * j == t) dot[j] = dslot[0];
             }
             // this warp is done with slot t: accumulator drained, A chunks rewritten
             tc_fence_before();
@@ -423,49 +424,32 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           }
         }
 
-        // ---- combine the two groups' partial dot products, then Welford (per slot) ------------
-        if (KC > 1) {
-          if (grp == 1) {
-#pragma unroll
-            for (int t = 0; t < TS; ++t)
-              st_shared_f32(xchg + (uint32_t)(t * G::XCHG_SLOT_BYTES +
-                                              (((mcount & 1) * TILE_M + row) << 2)),
-                            dot[t]);
-          }
-          epi_bar_sync_n<EPI4_THREADS>();
-        }
-        if (grp == 0) {
+        // ---- Welford over members, per owned slot ---------------------------------------------
+        {
           wf_n += 1.f;
           const float inv_n = 1.f / wf_n;
           const float bl = __ldg(p.b_last + wslot);
 #pragma unroll
-          for (int t = 0; t < TS; ++t) {
-            float y = dot[t];
-            if (KC > 1)
-              y += ld_shared_f32(xchg + (uint32_t)(t * G::XCHG_SLOT_BYTES +
-                                                   (((mcount & 1) * TILE_M + row) << 2)));
-            y += bl;
+          for (int j = 0; j < OWN; ++j) {
+            float y = dot[j] + bl;
             if (p.last_relu) y = fmaxf(y, 0.f);
-            const float dlt = y - wf_mean[t];
-            wf_mean[t] += dlt * inv_n;
-            wf_m2[t] = fmaf(dlt, y - wf_mean[t], wf_m2[t]);
+            const float dlt = y - wf_mean[j];
+            wf_mean[j] += dlt * inv_n;
+            wf_m2[j] = fmaf(dlt, y - wf_mean[j], wf_m2[j]);
           }
         }
       }
 
-      if (grp == 0) {
 #pragma unroll
-        for (int t = 0; t < TS; ++t) {
-          const int64_t grow = (int64_t)tile_of(unit, t) * TILE_M + row;
-          if (grow < p.n) {
-            if (p.splits > 1) {
-              p.part_mean[(size_t)split * (size_t)p.n + grow] = wf_mean[t];
-              p.part_m2[(size_t)split * (size_t)p.n + grow] = wf_m2[t];
-            } else {
-              p.out0[grow] = wf_mean[t];
-              p.out1[grow] =
-                  (p.output == UQ_OUT_MOMENTS) ? wf_m2[t] : sqrtf(wf_m2[t] / (wf_n - 1.f));
-            }
+      for (int j = 0; j < OWN; ++j) {
+        const int64_t grow = (int64_t)tile_of(unit, grp + NG4 * j) * TILE_M + row;
+        if (grow < p.n) {
+          if (p.splits > 1) {
+            p.part_mean[(size_t)split * (size_t)p.n + grow] = wf_mean[j];
+            p.part_m2[(size_t)split * (size_t)p.n + grow] = wf_m2[j];
+          } else {
+            p.out0[grow] = wf_mean[j];
+            p.out1[grow] = (p.output == UQ_OUT_MOMENTS) ? wf_m2[j] : sqrtf(wf_m2[j] / (wf_n - 1.f));
           }
         }
       }
