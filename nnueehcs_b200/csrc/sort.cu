@@ -118,8 +118,10 @@ __global__ void __launch_bounds__(1024) spine_scan_kernel(uint32_t* __restrict__
   }
 }
 
+// 4 blocks per SM (<= 64 registers): the ranking rounds are a chain of dependent warp-collectives
+// and shared-memory updates, so the kernel is latency-bound and wants warps, not registers
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 4)
 downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n, int shift,
                  int64_t tiles_per_block, const uint32_t* __restrict__ spine, int num_blocks) {
   __shared__ uint32_t digit_base[RADIX];

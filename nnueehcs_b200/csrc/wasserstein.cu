@@ -43,22 +43,31 @@ __device__ __forceinline__ int merge_path_smem(const float* U, int nu, const flo
   return lo;
 }
 
+// merge-path split of every block boundary k = b * MRG_TILE, one thread each: done up front so the
+// ~25 dependent global loads of a binary search are paid once in parallel instead of serially by
+// thread 0 of each of the ~50 k integral blocks (that cost 0.6 of the kernel's 0.97 ms)
+__global__ void __launch_bounds__(256)
+merge_partition_kernel(const float* __restrict__ U, int64_t nu, const float* __restrict__ V,
+                       int64_t nv, int64_t blocks, int64_t* __restrict__ splits) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= blocks) return;
+  splits[b] = merge_path(U, nu, V, nv, b * MRG_TILE);
+}
+
 __global__ void __launch_bounds__(MRG_THREADS)
 cdf_integral_kernel(const float* __restrict__ U, int64_t nu, const float* __restrict__ V,
                     int64_t nv, int64_t u_below, int64_t v_below, int64_t nu_total,
-                    int64_t nv_total, double* __restrict__ block_partials) {
+                    int64_t nv_total, const int64_t* __restrict__ splits,
+                    double* __restrict__ block_partials) {
   __shared__ float su[MRG_TILE + 1];
   __shared__ float sv[MRG_TILE + 1];
-  __shared__ int64_t split_i;
   __shared__ double warp_part[MRG_THREADS / 32];
   const int64_t total = nu + nv;
   const int64_t k0 = (int64_t)blockIdx.x * MRG_TILE;           // first merged index of the block
   int64_t k1 = k0 + MRG_TILE;                                   // contributions k in [k0, k1)
   if (k1 > total - 1) k1 = total - 1;
   const int t = threadIdx.x;
-  if (t == 0) split_i = merge_path(U, nu, V, nv, k0);
-  __syncthreads();
-  const int64_t i0 = split_i, j0 = k0 - i0;
+  const int64_t i0 = splits[blockIdx.x], j0 = k0 - i0;
   const int len = (int)(k1 - k0);
   const int lu = (int)((nu - i0) < (int64_t)(len + 1) ? (nu - i0) : (int64_t)(len + 1));
   const int lv = (int)((nv - j0) < (int64_t)(len + 1) ? (nv - j0) : (int64_t)(len + 1));
@@ -116,7 +125,7 @@ sum_partials_kernel(const double* __restrict__ parts, int64_t n, double* __restr
 }
 
 struct WsLayout {
-  size_t u, ut, v, vt, scratch, parts, result, total;
+  size_t u, ut, v, vt, scratch, parts, splits, result, total;
   int64_t blocks;
 };
 
@@ -133,6 +142,7 @@ WsLayout layout(int64_t nu, int64_t nv) {
   L.blocks = (nu + nv - 1 + MRG_TILE - 1) / MRG_TILE;
   if (L.blocks < 1) L.blocks = 1;
   L.parts = o; o += al(sizeof(double) * (size_t)L.blocks);
+  L.splits = o; o += al(sizeof(int64_t) * (size_t)L.blocks);
   L.result = o; o += 256;
   L.total = o;
   return L;
@@ -166,8 +176,12 @@ int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, doubl
   rc = radix_sort_f32(dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
   if (rc != UQ_OK) return rc;
   if (nu + nv - 1 > 0) {
+    int64_t* splits = reinterpret_cast<int64_t*>(b + L.splits);
+    merge_partition_kernel<<<(unsigned)((L.blocks + 255) / 256), 256, 0, st>>>(su, nu, sv, nv,
+                                                                               L.blocks, splits);
+    UQ_LAUNCH_CHECK();
     cdf_integral_kernel<<<(unsigned)L.blocks, MRG_THREADS, 0, st>>>(su, nu, sv, nv, 0, 0, nu, nv,
-                                                                    parts);
+                                                                    splits, parts);
     UQ_LAUNCH_CHECK();
     sum_partials_kernel<<<1, 1024, 0, st>>>(parts, L.blocks, result);
     UQ_LAUNCH_CHECK();
@@ -211,8 +225,12 @@ int wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv,
   }
   if (nu + nv - 1 > 0) {
     const int64_t blocks = (nu + nv - 1 + MRG_TILE - 1) / MRG_TILE;
+    int64_t* splits = reinterpret_cast<int64_t*>(b + L.splits);
+    merge_partition_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, st>>>(su, nu, sv, nv, blocks,
+                                                                             splits);
+    UQ_LAUNCH_CHECK();
     cdf_integral_kernel<<<(unsigned)blocks, MRG_THREADS, 0, st>>>(su, nu, sv, nv, u_below, v_below,
-                                                                  nu_total, nv_total, parts);
+                                                                  nu_total, nv_total, splits, parts);
     UQ_LAUNCH_CHECK();
     sum_partials_kernel<<<1, 1024, 0, st>>>(parts, blocks, result);
     UQ_LAUNCH_CHECK();
