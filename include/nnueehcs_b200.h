@@ -152,6 +152,30 @@ size_t uq_kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int32_t grid_pts);
 int uq_kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
                double* out_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* -- score consumers: the rest of what nnueehcs/evaluation.py derives
+      from the two score vectors, from one pair of device sorts.  Replaces MeanScoreEvaluation /
+      MaxScoreEvaluation / PercentileScoreEvaluation (evaluation.py:292-381, numpy on the host),
+      TNRatTPX._evaluate_scores (:538-580, a Python loop over every unique score), AUROC (:614-624,
+      sklearn on the host) and PercentileBasedClassifier (:637-662 over classification.py:103-143,
+      torch.quantile + four counts).  id / ood: float32 device arrays. ------------------------ */
+typedef struct uq_score_request {
+  double percentile_q;          /* PercentileScoreEvaluation.percentile, in [0, 100]        */
+  double target_tpr;            /* TNRatTPX.target_tpr, in [0, 1]                            */
+  double classifier_percentile; /* PercentileBasedIdOodClassifier.percentile, in [0, 1]      */
+  int32_t tnr_reversed;         /* TNRatTPX.reversed                                         */
+  int32_t classifier_reversed;  /* PercentileBasedClassifier.reversed (scores negated first) */
+} uq_score_request;
+typedef struct uq_score_result {
+  double mean_score, max_score, percentile_score; /* of the ID scores */
+  double auroc;                                   /* OOD = positive class */
+  double tnr_at_tpr;
+  double sensitivity, specificity, fpr, fnr;
+} uq_score_result;
+size_t uq_score_metrics_workspace_bytes(int64_t n_id, int64_t n_ood);
+int uq_score_metrics(const float* id_scores, int64_t n_id, const float* ood_scores, int64_t n_ood,
+                     const uq_score_request* req, uq_score_result* out_host, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* -- sharded metrics (one process per GPU).  The reference is
       single-process scipy (nnueehcs/evaluation.py:182, :268-276) and has no counterpart; these are
       the per-rank steps that nnueehcs_b200/distributed.py strings together with one all-reduce /

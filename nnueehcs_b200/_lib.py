@@ -25,6 +25,7 @@ EXPORTS = (
     "uq_sample_stats_workspace_bytes", "uq_sample_stats", "uq_kde_grid_workspace_bytes",
     "uq_kde_grid_accumulate", "uq_jsd_from_grids", "uq_key_bins", "uq_key_histogram",
     "uq_partition_by_bin", "uq_wasserstein_1d_range",
+    "uq_score_metrics_workspace_bytes", "uq_score_metrics",
 )
 
 
@@ -60,6 +61,17 @@ class ForwardArgs(C.Structure):
         ("masks", C.c_void_p),
         ("anchors", C.c_void_p),
     ]
+
+
+class ScoreRequest(C.Structure):
+    _fields_ = [("percentile_q", C.c_double), ("target_tpr", C.c_double),
+                ("classifier_percentile", C.c_double), ("tnr_reversed", C.c_int32),
+                ("classifier_reversed", C.c_int32)]
+
+
+class ScoreResult(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("mean_score", "max_score", "percentile_score", "auroc",
+                                          "tnr_at_tpr", "sensitivity", "specificity", "fpr", "fnr")]
 
 
 _lib = None
@@ -108,6 +120,11 @@ def load() -> C.CDLL:
     lib.uq_partition_by_bin.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     lib.uq_wasserstein_1d_range.argtypes = [vp, i64, vp, i64, i64, i64, i64, i64, C.POINTER(dbl),
                                             vp, sz, vp]
+    lib.uq_score_metrics_workspace_bytes.argtypes = [i64, i64]
+    lib.uq_score_metrics_workspace_bytes.restype = sz
+    lib.uq_score_metrics.argtypes = [vp, i64, vp, i64, C.POINTER(ScoreRequest),
+                                     C.POINTER(ScoreResult), vp, sz, vp]
+    lib.uq_score_metrics.restype = C.c_int
     for name in ("uq_sample_stats", "uq_kde_grid_accumulate", "uq_jsd_from_grids",
                  "uq_key_histogram", "uq_partition_by_bin", "uq_wasserstein_1d_range"):
         getattr(lib, name).restype = C.c_int

@@ -11,9 +11,14 @@ result keys as the reference; what changes is underneath:
 * ``JensenShannonEvaluation.pdf_jsd`` (``evaluation.py:268-276``) calls the CUDA KDE-on-grid + JS
   kernel instead of two ``scipy.stats.gaussian_kde`` and ``jensenshannon``.
 
-Metrics outside SURVEY.md section 8 (TNR@TPR, AUROC, percentile scores, runtime/throughput,
-classification) are "next" rows and are not built here: asking the factories for them raises
-``ValueError`` naming the metric.
+* the score consumers of SURVEY.md section 8f row 1 -- ``MeanScoreEvaluation``, ``MaxScoreEvaluation``,
+  ``PercentileScoreEvaluation`` (``evaluation.py:292-381``), ``TNRatTPX`` (``:519-605``), ``AUROC``
+  (``:607-635``) and ``PercentileBasedClassifier`` (``:637-662``) -- read one ``uq_score_metrics``
+  result (two device sorts + binary searches) instead of numpy / sklearn / a Python loop over every
+  unique score.
+
+Runtime / throughput / memory metrics and the Euclidean distance are not built: asking the
+factories for them raises ``ValueError`` naming the metric.
 """
 from __future__ import annotations
 
@@ -25,6 +30,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .classification import (PercentileBasedIdOodClassifier,
+                             ReversedPercentileBasedIdOodClassifier)
 
 
 class UncertaintyEstimate:
@@ -185,6 +192,188 @@ class JensenShannonEvaluation(UncertaintyEvaluationMetric):
         return self.name
 
 
+def _scores_1d(ue: UncertaintyEstimate) -> torch.Tensor:
+    if ue.dimensions != 1:
+        raise ValueError("score metrics need 1-D uncertainty estimates")
+    return _on_gpu(ue.flatten())
+
+
+class MeanScoreEvaluation(UncertaintyEvaluationMetric):
+    """Mean ID score, a BO minimisation target (reference ``evaluation.py:292-316``)."""
+    name = "mean_score"
+
+    def _evaluate_uncertainties(self, id_ue, ood_ue) -> dict:
+        if id_ue.dimensions != ood_ue.dimensions:
+            raise ValueError("Uncertainty estimates must have the same dimensions")
+        return {self.name: ops.score_metrics(_scores_1d(id_ue), _scores_1d(ood_ue))["mean_score"]}
+
+    @classmethod
+    def get_objectives(cls):
+        return [{"name": cls.name, "type": "minimize"}]
+
+    @classmethod
+    def get_metrics(cls):
+        return [cls.name]
+
+    def get_name(self):
+        return self.name
+
+
+class MaxScoreEvaluation(UncertaintyEvaluationMetric):
+    """Maximum ID score (reference ``evaluation.py:319-337``)."""
+    name = "max_score"
+
+    def _evaluate_uncertainties(self, id_ue, ood_ue) -> dict:
+        return {self.name: ops.score_metrics(_scores_1d(id_ue), _scores_1d(ood_ue))["max_score"]}
+
+    @classmethod
+    def get_objectives(cls):
+        return [{"name": cls.name, "type": "maximize"}]
+
+    @classmethod
+    def get_metrics(cls):
+        return [cls.name]
+
+    def get_name(self):
+        return self.name
+
+
+class PercentileScoreEvaluation(UncertaintyEvaluationMetric):
+    """``np.percentile`` of the ID scores (reference ``evaluation.py:339-381``)."""
+    name = "percentile_score"
+
+    def __init__(self, percentile: float = 95.0):
+        if not 0 <= percentile <= 100:
+            raise ValueError(f"percentile must be between 0 and 100, got {percentile}")
+        self.percentile = percentile
+
+    @classmethod
+    def from_config(cls, config: dict) -> 'PercentileScoreEvaluation':
+        return cls(percentile=config.get('percentile', 95.0))
+
+    def _evaluate_uncertainties(self, id_ue, ood_ue) -> dict:
+        if id_ue.dimensions != ood_ue.dimensions:
+            raise ValueError("Uncertainty estimates must have the same dimensions")
+        r = ops.score_metrics(_scores_1d(id_ue), _scores_1d(ood_ue), percentile_q=self.percentile)
+        return {self.name: r["percentile_score"]}
+
+    @classmethod
+    def get_objectives(cls):
+        return [{"name": cls.name, "type": "minimize"}]
+
+    @classmethod
+    def get_metrics(cls):
+        return [cls.name]
+
+    def get_name(self):
+        return self.name
+
+
+class ClassificationMetric(EvaluationMetric):
+    """Base of the classification-style metrics (reference ``evaluation.py:158-169``)."""
+
+    def evaluate(self, model: nn.Module, id_data: tuple, ood_data: tuple) -> dict:
+        with torch.no_grad():
+            _, id_scores = model(id_data[0], return_ue=True)
+            _, ood_scores = model(ood_data[0], return_ue=True)
+        return self._evaluate_scores(id_scores, ood_scores)
+
+    @abstractmethod
+    def _evaluate_scores(self, id_scores: torch.Tensor, ood_scores: torch.Tensor) -> dict:
+        pass
+
+
+class TNRatTPX(ClassificationMetric):
+    """True-negative rate at a target true-positive rate (reference ``evaluation.py:519-605``;
+    its loop over every unique score is a closed form on the sorted arrays, see
+    ``oracle/metrics_oracle.py:tnr_at_tpr``)."""
+
+    def __init__(self, target_tpr: float, reversed: bool = False):
+        if not 0 <= target_tpr <= 1:
+            raise ValueError(f"target_tpr must be between 0 and 1, got {target_tpr}")
+        self.target_tpr = target_tpr
+        self.metric_name = 'tnr_at_tpr'
+        self.reversed = reversed
+
+    @classmethod
+    def from_config(cls, config: dict) -> 'TNRatTPX':
+        return cls(target_tpr=config['target_tpr'], reversed=config.get('reversed', False))
+
+    def _evaluate_scores(self, id_scores, ood_scores) -> dict:
+        r = ops.score_metrics(_on_gpu(id_scores), _on_gpu(ood_scores), target_tpr=self.target_tpr,
+                              tnr_reversed=self.reversed)
+        return {str(self): r["tnr_at_tpr"]}
+
+    @classmethod
+    def get_objectives(cls):
+        return [{'name': 'tnr_at_tpr', 'type': 'maximize'}]
+
+    @classmethod
+    def get_metrics(cls):
+        return ['tnr_at_tpr']
+
+    def get_instance_objectives(self):
+        return [{'name': self.metric_name, 'type': 'maximize'}]
+
+    def get_instance_metrics(self):
+        return [self.metric_name]
+
+    def get_name(self):
+        return f'{self.metric_name}{int(100*self.target_tpr)}'
+
+    def __str__(self):
+        return self.get_name()
+
+
+class AUROC(ClassificationMetric):
+    """Area under the ROC curve, OOD = positive class (reference ``evaluation.py:607-635``)."""
+    name = "auroc"
+
+    def _evaluate_scores(self, id_scores, ood_scores) -> dict:
+        return {self.name: ops.score_metrics(_on_gpu(id_scores), _on_gpu(ood_scores))["auroc"]}
+
+    @classmethod
+    def get_objectives(cls):
+        return [{'name': 'auroc', 'type': 'maximize'}]
+
+    @classmethod
+    def get_metrics(cls):
+        return ['auroc']
+
+    def get_name(self):
+        return self.name
+
+
+class PercentileBasedClassifier(ClassificationMetric):
+    """Sensitivity / specificity of the percentile-threshold classifier (reference
+    ``evaluation.py:637-662``; ``reversed`` negates the scores first)."""
+
+    def __init__(self, percentile: float, reversed: bool = False):
+        self._classifier = PercentileBasedIdOodClassifier(percentile)
+        self.reversed = reversed
+
+    def _evaluate_scores(self, id_scores, ood_scores) -> dict:
+        r = ops.score_metrics(_on_gpu(id_scores), _on_gpu(ood_scores),
+                              classifier_percentile=self._classifier.percentile,
+                              classifier_reversed=self.reversed)
+        return {k: r[k] for k in self.get_metrics()}
+
+    @classmethod
+    def get_objectives(cls):
+        return [{'name': 'sensitivity', 'type': 'maximize'},
+                {'name': 'specificity', 'type': 'maximize'}]
+
+    @classmethod
+    def get_metrics(cls):
+        return ['sensitivity', 'specificity']
+
+    def get_name(self):
+        suffix = f'_{int(100*self._classifier.percentile)}'
+        if self.reversed:
+            suffix = f'_reversed{suffix}'
+        return f'percentile_classification{suffix}'
+
+
 class MetricEvaluator:
     """Unified evaluator over several metrics (reference ``evaluation.py:666-697``)."""
 
@@ -216,22 +405,33 @@ _DISTANCE_METRICS = {
     WassersteinEvaluation.name: WassersteinEvaluation,
     JensenShannonEvaluation.name: JensenShannonEvaluation,
 }
-# names the reference's factories also know (evaluation.py:700-812) but that are not on the hot path
-_NEXT_ROWS = ("euclidean_distance", "percentile_classification", "tnr_at_tpr", "runtime",
-              "uncertainty_estimating_runtime", "uncertainty_estimating_throughput",
-              "base_model_throughput", "mean_score", "max_score", "percentile_score", "auroc",
-              "max_memory_usage")
+# names the reference's factories also know (evaluation.py:700-812) but that are not built here
+_NOT_BUILT = ("euclidean_distance", "runtime", "uncertainty_estimating_runtime",
+              "uncertainty_estimating_throughput", "base_model_throughput", "max_memory_usage")
 
 
 def _create_single_evaluator(metric_config: dict) -> EvaluationMetric:
+    """reference ``evaluation.py:774-812``"""
     name = metric_config['name']
     if name in _DISTANCE_METRICS:
         return _DISTANCE_METRICS[name]()
-    if name == 'wasserstein':  # spelling used by get_evaluator (evaluation.py:708)
-        return WassersteinEvaluation()
-    if name in _NEXT_ROWS:
-        raise ValueError(f"metric '{name}' is not on the accelerated hot path (a 'next' row of "
-                         "SURVEY.md section 8); use the reference's evaluator for it")
+    if name == 'percentile_classification':
+        cls = (ReversedPercentileBasedIdOodClassifier if metric_config.get('reversed', False)
+               else PercentileBasedIdOodClassifier)
+        return cls(metric_config['threshold'])
+    if name == 'tnr_at_tpr':
+        return TNRatTPX(metric_config['target_tpr'], metric_config.get('reversed', False))
+    if name == 'mean_score':
+        return MeanScoreEvaluation()
+    if name == 'max_score':
+        return MaxScoreEvaluation()
+    if name == 'percentile_score':
+        return PercentileScoreEvaluation.from_config(metric_config)
+    if name == 'auroc':
+        return AUROC()
+    if name in _NOT_BUILT:
+        raise ValueError(f"metric '{name}' is not built in nnueehcs_b200 (outside the accelerated "
+                         "hot path); use the reference's evaluator for it")
     raise ValueError(f"Invalid metric type: {name}")
 
 
@@ -247,6 +447,18 @@ def get_uncertainty_evaluator(metric_config) -> MetricEvaluator:
 
 
 def get_evaluator(config) -> MetricEvaluator:
-    """dict | list of dicts -> MetricEvaluator (reference ``evaluation.py:700-743``)."""
+    """dict | list of dicts -> MetricEvaluator (reference ``evaluation.py:700-743``: note its own
+    spellings -- 'wasserstein', and 'percentile_classification' -> PercentileBasedClassifier)."""
     configs = config if isinstance(config, list) else [config]
-    return MetricEvaluator([_create_single_evaluator(c) for c in configs])
+    metrics = []
+    for c in configs:
+        name = c['name']
+        if name == 'wasserstein':
+            metrics.append(WassersteinEvaluation())
+        elif name == 'percentile_classification':
+            metrics.append(PercentileBasedClassifier(c['threshold'], c.get('reversed', False)))
+        elif name == 'tnr_at_tpr':
+            metrics.append(TNRatTPX.from_config(c))
+        else:
+            metrics.append(_create_single_evaluator(c))
+    return MetricEvaluator(metrics)

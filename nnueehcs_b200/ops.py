@@ -261,6 +261,27 @@ def kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000) -> float:
     return float(out.value)
 
 
+def score_metrics(id_scores: torch.Tensor, ood_scores: torch.Tensor, *, percentile_q: float = 95.0,
+                  target_tpr: float = 0.95, tnr_reversed: bool = False,
+                  classifier_percentile: float = 0.95, classifier_reversed: bool = False) -> dict:
+    """Mean / max / percentile score, AUROC, TNR@TPR and the percentile classifier's rates from one
+    pair of device sorts (``uq_score_metrics``)."""
+    lib = _lib.load()
+    a, b = _flat_f32(id_scores, "id_scores"), _flat_f32(ood_scores, "ood_scores")
+    if a.numel() == 0 or b.numel() == 0:
+        raise ValueError("score vectors must not be empty")
+    req = _lib.ScoreRequest(float(percentile_q), float(target_tpr), float(classifier_percentile),
+                            1 if tnr_reversed else 0, 1 if classifier_reversed else 0)
+    out = _lib.ScoreResult()
+    with torch.cuda.device(a.device):
+        wsb = int(lib.uq_score_metrics_workspace_bytes(a.numel(), b.numel()))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=a.device)
+        _lib.check(lib.uq_score_metrics(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(),
+                                        C.byref(req), C.byref(out), ws.data_ptr(), wsb,
+                                        _stream_ptr(a.device)))
+    return {k: float(getattr(out, k)) for k, _ in _lib.ScoreResult._fields_}
+
+
 # ------------------------------------------------------------------------------------------------
 # per-rank steps of the sharded metrics (strung together by nnueehcs_b200.distributed)
 # ------------------------------------------------------------------------------------------------

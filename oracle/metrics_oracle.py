@@ -176,3 +176,101 @@ class NumpyShardBackend:
     def wasserstein_1d_range(u, v, u_below, v_below, nu_total, nv_total):
         return wasserstein_1d_range(u.cpu().numpy(), v.cpu().numpy(), u_below, v_below, nu_total,
                                     nv_total)
+
+
+# ----------------------------------------------------------------------------------------------
+# Score consumers: closed forms on the two SORTED score arrays of
+# what the reference computes with Python loops / sklearn / torch.quantile.  Pinned by
+# tests/golden/score_metrics.npz (outputs of the reference's own classes).
+# ----------------------------------------------------------------------------------------------
+
+def _min_count(target: float, denom: int) -> int:
+    """Smallest integer m >= 0 with  m / denom >= target  in Python float arithmetic (the
+    comparison ``tpr >= self.target_tpr`` of nnueehcs/evaluation.py:577)."""
+    m = int(np.ceil(target * denom))
+    while m > 0 and (m - 1) / denom >= target:
+        m -= 1
+    while m / denom < target:
+        m += 1
+    return m
+
+
+def tnr_at_tpr(id_scores, ood_scores, target_tpr: float, reversed_: bool = False) -> float:
+    """``TNRatTPX._evaluate_scores`` (nnueehcs/evaluation.py:538-580) without the loop over every
+    unique score.  tnr is non-decreasing and tpr non-increasing in the threshold, so the best tnr
+    is the one at the LARGEST threshold (a score value) whose tpr still meets the target; that
+    threshold is the largest score below c = the m-th largest positive, and every negative below
+    c is <= it.  Keeps the reference's quirks: in reversed mode tp counts ID scores but is divided
+    by n_ood, and tn counts OOD scores but is divided by n_id."""
+    a = np.sort(np.asarray(id_scores, dtype=np.float32).ravel())
+    b = np.sort(np.asarray(ood_scores, dtype=np.float32).ravel())
+    n_id, n_ood = a.size, b.size
+    if reversed_:
+        if a[0] > b[-1]:
+            return 1.0
+        pos, neg = a, b
+    else:
+        if a[-1] < b[0]:
+            return 1.0
+        pos, neg = b, a
+    m = _min_count(target_tpr, n_ood)          # tp / n_ood >= target  <=>  tp >= m
+    if m > pos.size:
+        return 0.0
+    if m == 0:                                  # every threshold qualifies: largest = max(all)
+        return neg.size / n_id
+    c = pos[pos.size - m]
+    if not (min(a[0], b[0]) < c):               # no score below c: no threshold qualifies
+        return 0.0
+    return int(np.searchsorted(neg, c, side="left")) / n_id
+
+
+def auroc(id_scores, ood_scores) -> float:
+    """``AUROC._evaluate_scores`` (nnueehcs/evaluation.py:614-624): sklearn ``roc_auc_score`` with
+    OOD as the positive class == Mann-Whitney U / (n_id n_ood), ties counted one half."""
+    a = np.sort(np.asarray(id_scores, dtype=np.float32).ravel())
+    b = np.asarray(ood_scores, dtype=np.float32).ravel()
+    lt = np.searchsorted(a, b, side="left").astype(np.int64)
+    le = np.searchsorted(a, b, side="right").astype(np.int64)
+    return float((lt + le).sum()) / (2.0 * a.size * b.size)
+
+
+def torch_quantile_f32(sorted_vals: np.ndarray, q: float) -> np.float32:
+    """``torch.quantile(x, q)`` for a float32 vector, restated: float32 rank, float32 lerp with
+    ATen's two-sided formula."""
+    n = sorted_vals.size
+    rank = np.float32(q) * np.float32(n - 1)
+    below = np.floor(rank)
+    above = np.ceil(rank)
+    w = np.float32(rank - below)
+    lo, hi = sorted_vals[int(below)], sorted_vals[int(above)]
+    diff = np.float32(hi - lo)
+    if w < np.float32(0.5):
+        return np.float32(lo + np.float32(w * diff))
+    return np.float32(hi - np.float32(diff * np.float32(np.float32(1.0) - w)))
+
+
+def percentile_classifier(id_scores, ood_scores, percentile: float, reversed_: bool = False):
+    """``PercentileBasedClassifier`` (evaluation.py:637-662) over
+    ``PercentileBasedIdOodClassifier._evaluate_scores`` (classification.py:103-143): threshold =
+    ``torch.quantile(id, percentile)`` (scores negated first when reversed), then four counts.
+    Returns (sensitivity, specificity, fpr, fnr)."""
+    a = np.asarray(id_scores, dtype=np.float32).ravel()
+    b = np.asarray(ood_scores, dtype=np.float32).ravel()
+    if reversed_:
+        a, b = -a, -b
+    a, b = np.sort(a), np.sort(b)
+    thr = torch_quantile_f32(a, percentile)
+    id_above = a.size - int(np.searchsorted(a, thr, side="right"))
+    ood_above = b.size - int(np.searchsorted(b, thr, side="right"))
+    id_below, ood_below = a.size - id_above, b.size - ood_above
+    def ratio(x, y):
+        return float(x) / (x + y) if (x + y) else 0.0
+    return (ratio(ood_above, ood_below), ratio(id_below, id_above), ratio(id_above, id_below),
+            ratio(ood_below, ood_above))
+
+
+def score_summaries(id_scores, percentile_q: float):
+    """(mean_score, max_score, percentile_score) as the reference computes them with numpy on the
+    float32 ID scores (evaluation.py:303, :323, :365)."""
+    a = np.asarray(id_scores, dtype=np.float32).ravel()
+    return float(np.mean(a)), float(np.max(a)), float(np.percentile(a, percentile_q))

@@ -230,3 +230,57 @@ def test_sharded_metrics_single_rank_group():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+# ---- score consumers (mean / max / percentile score, AUROC, TNR@TPR, percentile classifier) ------
+
+_SG = load_golden("score_metrics.npz")
+
+
+@pytest.mark.parametrize("name", [str(n) for n in _SG["names"]])
+def test_score_metrics_match_reference_golden(name):
+    """uq_score_metrics against the outputs of the reference's own classes.  Counts-based metrics
+    and AUROC are exact (integer arithmetic on the sorted arrays, one float64 division); the mean
+    is a float64 sum here and a float32 pairwise sum in numpy -> 1e-6 relative."""
+    id_s, ood_s = _SG[f"{name}.id"], _SG[f"{name}.ood"]
+    a, b = _dev(id_s), _dev(ood_s)
+    for i in range(len(_SG["tprs"])):
+        q, t, p = float(_SG["pct_score"][i]), float(_SG["tprs"][i]), float(_SG["cls_pct"][i])
+        for rev in (False, True):
+            tag = "rev" if rev else "fwd"
+            r = ops.score_metrics(a, b, percentile_q=q, target_tpr=t, tnr_reversed=rev,
+                                  classifier_percentile=p, classifier_reversed=rev)
+            assert r["tnr_at_tpr"] == float(_SG[f"{name}.tnr_{tag}"][i]), (name, t, rev)
+            got = np.array([r["sensitivity"], r["specificity"], r["fpr"], r["fnr"]])
+            assert np.array_equal(got, _SG[f"{name}.cls_{tag}"][i]), (name, p, rev, got)
+            assert r["auroc"] == pytest.approx(float(_SG[f"{name}.auroc"]), rel=1e-14, abs=1e-15)
+            assert r["max_score"] == float(_SG[f"{name}.max_score"])
+            assert r["mean_score"] == pytest.approx(float(_SG[f"{name}.mean_score"]), rel=1e-6)
+            assert r["percentile_score"] == pytest.approx(float(_SG[f"{name}.percentile_score"][i]),
+                                                          rel=1e-12), (name, q)
+
+
+def test_score_metrics_large_against_oracle_and_mirror_classes():
+    u, v = _gamma_pair(400_000, 300_000, seed=9)
+    a, b = _dev(u), _dev(v)
+    r = ops.score_metrics(a, b, percentile_q=97.5, target_tpr=0.9, classifier_percentile=0.99)
+    assert r["auroc"] == pytest.approx(metrics_oracle.auroc(u, v), rel=1e-14)
+    assert r["tnr_at_tpr"] == metrics_oracle.tnr_at_tpr(u, v, 0.9)
+    sens, spec, fpr, fnr = metrics_oracle.percentile_classifier(u, v, 0.99)
+    assert (r["sensitivity"], r["specificity"], r["fpr"], r["fnr"]) == (sens, spec, fpr, fnr)
+    mean, mx, pct = metrics_oracle.score_summaries(u, 97.5)
+    assert r["max_score"] == mx and r["percentile_score"] == pytest.approx(pct, rel=1e-12)
+    assert r["mean_score"] == pytest.approx(mean, rel=1e-6)
+    # through the mirror classes (same names / keys as the reference)
+    m = evaluation.TNRatTPX(0.9)
+    assert m._evaluate_scores(a[:, None], b[:, None]) == {"tnr_at_tpr90": r["tnr_at_tpr"]}
+    assert evaluation.AUROC()._evaluate_scores(a, b)["auroc"] == r["auroc"]
+    c = evaluation.PercentileBasedClassifier(0.99)._evaluate_scores(a, b)
+    assert c == {"sensitivity": sens, "specificity": spec}
+    from nnueehcs_b200 import classification
+    rv = classification.ReversedPercentileBasedIdOodClassifier(0.95)._evaluate_scores(a, b)
+    thr = float(np.quantile(u.astype(np.float64), 0.05))
+    assert abs(rv["sensitivity"] - float((v <= thr).mean())) < 1e-4
+    assert abs(rv["specificity"] - float((u > thr).mean())) < 1e-4
+    with pytest.raises(ValueError, match="between 0 and 1"):
+        ops.score_metrics(a, b, target_tpr=2.0)

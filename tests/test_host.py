@@ -228,8 +228,25 @@ def test_evaluator_factories():
     assert ev.get_training_objectives()[0] == {"name": "wasserstein_distance", "type": "maximize"}
     assert isinstance(evaluation.get_evaluator({"name": "wasserstein"}).metrics[0],
                       evaluation.WassersteinEvaluation)
-    with pytest.raises(ValueError, match="not on the accelerated hot path"):
-        evaluation.get_uncertainty_evaluator("auroc")
+    with pytest.raises(ValueError, match="not built"):
+        evaluation.get_uncertainty_evaluator("runtime")
+    ev = evaluation.get_uncertainty_evaluator(
+        ["auroc", "mean_score", "max_score", {"name": "percentile_score", "percentile": 90.0},
+         {"name": "tnr_at_tpr", "target_tpr": 0.95},
+         {"name": "percentile_classification", "threshold": 0.95},
+         {"name": "percentile_classification", "threshold": 0.95, "reversed": True}])
+    assert [type(m).__name__ for m in ev.metrics] == [
+        "AUROC", "MeanScoreEvaluation", "MaxScoreEvaluation", "PercentileScoreEvaluation", "TNRatTPX",
+        "PercentileBasedIdOodClassifier", "ReversedPercentileBasedIdOodClassifier"]
+    assert ev.metrics[3].percentile == 90.0 and ev.metrics[4].get_name() == "tnr_at_tpr95"
+    ev = evaluation.get_evaluator([{"name": "percentile_classification", "threshold": 0.9,
+                                    "reversed": True}, {"name": "tnr_at_tpr", "target_tpr": 0.5}])
+    assert ev.metrics[0].get_name() == "percentile_classification_reversed_90"
+    assert ev.get_all_metrics() == ["sensitivity", "specificity", "tnr_at_tpr"]
+    with pytest.raises(ValueError, match="between 0 and 1"):
+        evaluation.TNRatTPX(1.5)
+    with pytest.raises(ValueError, match="between 0 and 100"):
+        evaluation.PercentileScoreEvaluation(101)
     with pytest.raises(ValueError, match="Invalid metric type"):
         evaluation.get_uncertainty_evaluator("bogus")
 
