@@ -113,6 +113,7 @@ struct DrainCtx {
   int kg, drop_ord;
   int64_t grow;
   const uint8_t* mask_layer;
+  float in_scale;          // 1/(1-p) if this layer's input went through an active dropout, else 1
 #ifdef UQ_TC_TRACE
   unsigned long long* tr;  // this thread's trace slots (or nullptr)
   int* tr_n;
@@ -163,7 +164,7 @@ __device__ __forceinline__ void drain_half0(const TcParams& p, const DrainCtx& c
         if (DROP && (b & 1) == 0)
           keep32 = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
         tmem_ld_wait();
-        epi_math<H, DOUT, 16, RELU, DROP, LAST>(acc, bv, keep32 >> (16 * (b & 1)), p.drop_scale,
+        epi_math<H, DOUT, 16, RELU, DROP, LAST>(acc, bv, keep32 >> (16 * (b & 1)), cx.in_scale,
                                                 held + i * 32 + b * 8, cx.wl_s + col0,
                                                 cx.wl_g + col0, dot);
       }
@@ -222,7 +223,7 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
       tmem_ld_wait();
       UQ_DTRACE(11, c);
       tmem_ld32(cx.lane_addr + (uint32_t)(col0 + 32), acc1);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep, p.drop_scale, a_dst, 0, cx.rx,
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep, cx.in_scale, a_dst, 0, cx.rx,
                                             cx.wl_s + col0, cx.wl_g + col0, dot);
       UQ_DTRACE(12, c);
       // ---- block 1 (columns col0+32 .. col0+63) ----
@@ -237,7 +238,7 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
         keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0 + 32, cx.mask_layer, H);
       tmem_ld_wait();
       if (c + NG < KC) tmem_ld32(cx.lane_addr + (uint32_t)(col0 + NG * CHUNK_K), acc0);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep, p.drop_scale, a_dst, 4, cx.rx,
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep, cx.in_scale, a_dst, 4, cx.rx,
                                             cx.wl_s + col0 + 32, cx.wl_g + col0 + 32, dot);
       UQ_DTRACE(13, c);
       // chunk c: accumulator columns drained (+ A chunk rewritten) -> release to the MMA warp
@@ -265,7 +266,7 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
         if (DROP && (b & 1) == 0)
           keep32 = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
         tmem_ld_wait();
-        epi_block2<H, DOUT, 16, RELU, DROP, LAST>(acc, bv, keep32 >> (16 * (b & 1)), p.drop_scale,
+        epi_block2<H, DOUT, 16, RELU, DROP, LAST>(acc, bv, keep32 >> (16 * (b & 1)), cx.in_scale,
                                                   a_dst, 2 * b, cx.rx, cx.wl_s + col0,
                                                   cx.wl_g + col0, dot);
       }
@@ -641,6 +642,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           cx.drop_ord = drop_ord;
           cx.grow = grow;
           cx.mask_layer = mask_layer;
+          cx.in_scale = (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
 #ifdef UQ_TC_TRACE
           {
             const int role = (lane == 0 && (warp == 2 || (warp == 6 && leader)))

@@ -81,7 +81,8 @@ __device__ __forceinline__ void drain3(const TcParams& p, uint32_t lane_addr, ui
                                        int grp, int ch, int lane, uint32_t chunk_bar0,
                                        const float* bias_s, const float* wl_s, const float* wl_g,
                                        int drop, int kg, int drop_ord, int64_t grow,
-                                       const uint8_t* mask_layer, float (&dot)[DOUT]) {
+                                       const uint8_t* mask_layer, float in_scale,
+                                       float (&dot)[DOUT]) {
   using G = Geo3<H, DOUT>;
   uint32_t acc0[32], acc1[32];
   // this warp's chunks, in order: for j = grp, grp + 2, ...: c = CPT j + 2 ch + {0, 1}
@@ -102,7 +103,7 @@ __device__ __forceinline__ void drain3(const TcParams& p, uint32_t lane_addr, ui
       if (DROP) keep = keep_bits32(p, drop, kg, drop_ord, grow, col0, mask_layer, H);
       tmem_ld_wait();
       tmem_ld32(lane_addr + tcol + 32, acc1);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep, p.drop_scale, a_dst, 0, rx,
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep, in_scale, a_dst, 0, rx,
                                                 wl_s + col0, wl_g + col0, dot);
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
@@ -112,7 +113,7 @@ __device__ __forceinline__ void drain3(const TcParams& p, uint32_t lane_addr, ui
       // next chunk of this warp: e == 0 -> same tile, next 64 TMEM columns; else tile j + NG
       if (e == 0) tmem_ld32(lane_addr + tcol + CHUNK_K, acc0);
       else if (j + NG < G::NTILES) tmem_ld32(lane_addr + (uint32_t)((j + NG) * G::TCOLS), acc0);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep, p.drop_scale, a_dst, 4, rx,
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep, in_scale, a_dst, 4, rx,
                                                 wl_s + col0 + 32, wl_g + col0 + 32, dot);
       tc_fence_before();
       if (!LAST) fence_proxy_async_smem();
@@ -420,9 +421,11 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
           if (last && have_next) publish_x(ntile, p.member_begin + nk);
 
           const float* wl_g = p.w_last + (size_t)wslot * DOUT * H;
+          const float in_scale =
+              (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
 #define UQ_DRAIN3(R, D, L)                                                                       \
   drain3<H, DOUT, R, D, L>(p, lane_addr, a_row, rx, grp, ch, lane, chunk_bar0, aux, aux + H, wl_g, \
-                           drop, kg, drop_ord, grow, mask_layer, dot)
+                           drop, kg, drop_ord, grow, mask_layer, in_scale, dot)
           if (last) {
             if (relu) { if (drop) UQ_DRAIN3(true, true, true); else UQ_DRAIN3(true, false, true); }
             else { if (drop) UQ_DRAIN3(false, true, true); else UQ_DRAIN3(false, false, true); }

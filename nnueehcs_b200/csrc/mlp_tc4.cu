@@ -76,7 +76,7 @@ template <int H, bool RELU, bool DROP, bool LAST>
 __device__ __forceinline__ void drain4(const TcParams& p, uint32_t lane_addr, uint32_t a_row, int rx,
                                        const float* bias_s, const float* wl_s, int drop,
                                        int kg, int drop_ord, int64_t grow,
-                                       const uint8_t* mask_layer, float (&dot)[1]) {
+                                       const uint8_t* mask_layer, float in_scale, float (&dot)[1]) {
   constexpr int KC = H / CHUNK_K;
   uint32_t acc0[32], acc1[32];
   tmem_ld32(lane_addr, acc0);
@@ -91,14 +91,14 @@ __device__ __forceinline__ void drain4(const TcParams& p, uint32_t lane_addr, ui
     if (DROP) keep = keep_bits32(p, drop, kg, drop_ord, grow, col0, mask_layer, H);
     tmem_ld_wait();
     tmem_ld32(lane_addr + (uint32_t)(col0 + 32), acc1);
-    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc0, bv, keep, p.drop_scale, a_dst, 0, rx, wl_s + col0,
+    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc0, bv, keep, in_scale, a_dst, 0, rx, wl_s + col0,
                                            wl_s + col0, dot);
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
     if (DROP) keep = keep_bits32(p, drop, kg, drop_ord, grow, col0 + 32, mask_layer, H);
     tmem_ld_wait();
     if (c + 1 < KC) tmem_ld32(lane_addr + (uint32_t)(col0 + CHUNK_K), acc0);
-    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc1, bv, keep, p.drop_scale, a_dst, 4, rx,
+    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc1, bv, keep, in_scale, a_dst, 4, rx,
                                            wl_s + col0 + 32, wl_s + col0 + 32, dot);
   }
 }
@@ -370,6 +370,8 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           const bool relu = (p.relu_mask >> l) & 1u;
           const bool has_drop = (p.dropout_mask >> l) & 1u;
           const int drop = has_drop ? p.drop_mode : 0;
+          const float in_scale =
+              (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
 
           float* aux = aux_smem + (g & 1) * G::AUX_FLOATS;
 #pragma unroll
@@ -398,7 +400,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
             const int64_t grow = (int64_t)tile_of(unit, t) * TILE_M + row;
 #define UQ_DRAIN4(R, D, L)                                                                        \
   drain4<H, R, D, L>(p, lane_addr, a_row, rx, aux, aux + H, drop, kg, drop_ord, grow,             \
-                     mask_layer, dslot)
+                     mask_layer, in_scale, dslot)
             if (last) {
               if (relu) { if (drop) UQ_DRAIN4(true, true, true); else UQ_DRAIN4(true, false, true); }
               else { if (drop) UQ_DRAIN4(false, true, true); else UQ_DRAIN4(false, false, true); }

@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t keep_bits32(const TcParams& p, int drop, int
 // into NC/2 packed words (cvt.rn[.relu].bf16x2) or the last-Linear dot product.
 template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST>
 __device__ __forceinline__ void epi_math(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
-                                         uint32_t keep, float keep_scale, uint32_t* packed,
+                                         uint32_t keep, float in_scale, uint32_t* packed,
                                          const float* __restrict__ wl_s,
                                          const float* __restrict__ wl_g, float (&dot)[DOUT]) {
 #if UQ_ABLATE == 5
@@ -101,14 +101,16 @@ __device__ __forceinline__ void epi_math(const uint32_t (&acc)[NC], const float4
   float v[NC];
 #pragma unroll
   for (int j4 = 0; j4 < NC / 4; ++j4) {
-    v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + bv[j4].x;
-    v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + bv[j4].y;
-    v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + bv[j4].z;
-    v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + bv[j4].w;
+    // in_scale = 1 / (1 - p) when the previous layer's output went through a dropout (which only
+    // zeroes; the rescale rides on this FMA for free), else 1.0 -- fma(acc, 1, b) == acc + b exactly
+    v[j4 * 4 + 0] = fmaf(__uint_as_float(acc[j4 * 4 + 0]), in_scale, bv[j4].x);
+    v[j4 * 4 + 1] = fmaf(__uint_as_float(acc[j4 * 4 + 1]), in_scale, bv[j4].y);
+    v[j4 * 4 + 2] = fmaf(__uint_as_float(acc[j4 * 4 + 2]), in_scale, bv[j4].z);
+    v[j4 * 4 + 3] = fmaf(__uint_as_float(acc[j4 * 4 + 3]), in_scale, bv[j4].w);
   }
   if (DROP) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
+    for (int j = 0; j < NC; ++j) v[j] = ((keep >> j) & 1u) ? v[j] : 0.f;
   }
   if (!LAST) {
 #pragma unroll
@@ -168,11 +170,11 @@ __device__ __forceinline__ void epi_store(const uint32_t* packed, uint32_t a_dst
 
 template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST>
 __device__ __forceinline__ void epi_block2(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
-                                           uint32_t keep, float keep_scale, uint32_t a_dst,
+                                           uint32_t keep, float in_scale, uint32_t a_dst,
                                            int piece0, int rx, const float* __restrict__ wl_s,
                                            const float* __restrict__ wl_g, float (&dot)[DOUT]) {
   uint32_t packed[NC / 2];
-  epi_math<H, DOUT, NC, RELU, DROP, LAST>(acc, bv, keep, keep_scale, packed, wl_s, wl_g, dot);
+  epi_math<H, DOUT, NC, RELU, DROP, LAST>(acc, bv, keep, in_scale, packed, wl_s, wl_g, dot);
   if (!LAST) epi_store<NC / 2>(packed, a_dst, piece0, rx);
 }
 

@@ -375,15 +375,41 @@ class PercentileBasedClassifier(ClassificationMetric):
 
 
 class MetricEvaluator:
-    """Unified evaluator over several metrics (reference ``evaluation.py:666-697``)."""
+    """Unified evaluator over several metrics (reference ``evaluation.py:666-697``).
 
-    def __init__(self, metrics):
+    The reference calls ``metric.evaluate(model, id, ood)`` per metric, and every one of them runs
+    the two UQ forwards again (2 forwards per metric).  With
+    ``share_forward=True`` (default) the forwards run once per model mode and every score-based
+    metric reads the same device-resident scores; ``share_forward=False`` restores the
+    reference's call pattern (for MC dropout that also means fresh masks per metric)."""
+
+    def __init__(self, metrics, share_forward: bool = True):
         self.metrics = metrics
+        self.share_forward = share_forward
 
     def evaluate(self, model: nn.Module, id_data: tuple, ood_data: tuple) -> dict:
         results = {}
+        cache = {}   # model.training -> (id_scores, ood_scores)
         for metric in self.metrics:
-            results.update(metric.evaluate(model, id_data, ood_data))
+            score_based = isinstance(metric, (UncertaintyEvaluationMetric, ClassificationMetric))
+            if not (self.share_forward and score_based):
+                results.update(metric.evaluate(model, id_data, ood_data))
+                continue
+            if isinstance(metric, UncertaintyEvaluationMetric):
+                model.eval()   # as UncertaintyEvaluationMetric.evaluate does (evaluation.py:133)
+            key = bool(model.training)
+            if key not in cache:
+                with torch.no_grad():
+                    _, id_scores = model(id_data[0], return_ue=True)
+                    _, ood_scores = model(ood_data[0], return_ue=True)
+                cache[key] = (id_scores, ood_scores)
+            id_scores, ood_scores = cache[key]
+            if isinstance(metric, UncertaintyEvaluationMetric):
+                r = metric._evaluate_uncertainties(UncertaintyEstimate(id_scores),
+                                                   UncertaintyEstimate(ood_scores))
+                results.update({k: float(v) for k, v in r.items()})
+            else:
+                results.update(metric._evaluate_scores(id_scores, ood_scores))
         return results
 
     def get_training_objectives(self):

@@ -307,3 +307,39 @@ def test_argument_errors_surface_as_python_exceptions_without_a_gpu():
     assert rc == _lib.UQ_ERR_INVALID and not h.value
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.wasserstein_1d(torch.zeros(4), torch.zeros(4))
+
+
+def test_metric_evaluator_shares_one_forward_per_dataset():
+    """the two UQ forwards run once for all score-based metrics (the reference
+    runs them once per metric); ``share_forward=False`` restores the reference's call pattern."""
+    calls = []
+
+    class Model(torch.nn.Module):
+        def forward(self, x, return_ue=False):
+            calls.append(int(x.shape[0]))
+            return x[:, :1], x[:, :1] * 2.0
+
+    class U(evaluation.UncertaintyEvaluationMetric):
+        def __init__(self, name): self._n = name
+        def _evaluate_uncertainties(self, a, b): return {self._n: a.mean() + b.mean()}
+        @classmethod
+        def get_objectives(cls): return []
+        @classmethod
+        def get_metrics(cls): return []
+        def get_name(self): return self._n
+
+    class Cm(evaluation.ClassificationMetric):
+        def _evaluate_scores(self, a, b): return {"c": float(a.sum() + b.sum())}
+        @classmethod
+        def get_objectives(cls): return []
+        @classmethod
+        def get_metrics(cls): return ["c"]
+        def get_name(self): return "c"
+
+    id_d, ood_d = (torch.ones(3, 2), None), (torch.ones(5, 2), None)
+    out = evaluation.MetricEvaluator([U("a"), U("b"), Cm()]).evaluate(Model(), id_d, ood_d)
+    assert calls == [3, 5] and out == {"a": 4.0, "b": 4.0, "c": 16.0}
+    calls.clear()
+    out2 = evaluation.MetricEvaluator([U("a"), U("b"), Cm()], share_forward=False).evaluate(
+        Model(), id_d, ood_d)
+    assert calls == [3, 5] * 3 and out2 == out
