@@ -397,7 +397,7 @@ class MetricEvaluator:
                 continue
             if isinstance(metric, UncertaintyEvaluationMetric):
                 model.eval()   # as UncertaintyEvaluationMetric.evaluate does (evaluation.py:133)
-            key = bool(model.training)
+            key = bool(getattr(model, "training", False))
             if key not in cache:
                 with torch.no_grad():
                     _, id_scores = model(id_data[0], return_ue=True)
