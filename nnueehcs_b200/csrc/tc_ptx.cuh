@@ -35,6 +35,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// (A suspend-time hint on try_wait -- 20 us instead of the default ~100 ns -- removes the probe
+// loops that make up a third of the issued instructions, but was measured slower, 14.9 vs 14.3
+// ms/step: hinted waiters wake up later.)
 // Bounded wait: a protocol bug must surface as a trapped kernel (clean CUDA error), never as a
 // hung GPU.  Each failed probe suspends in hardware for a few hundred cycles, so 2^24 probes are
 // several seconds.
