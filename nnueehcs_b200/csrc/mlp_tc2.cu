@@ -775,10 +775,11 @@ template <int H, int DOUT, int NG>
 int launch_tc2(const TcParams& p, cudaStream_t st) {
   using G = Geo2<H, DOUT, NG>;
   auto kern = uq_mlp_tc2_kernel<H, DOUT, NG>;
-  UQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-  int dev = 0, sms = 148;
+  // per-device launch geometry of this instantiation, queried once (the occupancy query and the
+  // attribute call cost tens of microseconds, which shows on millisecond-sized forwards)
+  static int cached_clusters[16] = {0};
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t units = (int64_t)((p.n_tiles + 1) / 2) * p.splits;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -792,14 +793,20 @@ int launch_tc2(const TcParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // how many CTA pairs can be co-resident (one CTA per SM: the TMEM allocation is per pair)
-  int max_clusters = sms / 2;
-  cfg.gridDim = dim3((unsigned)sms, 1, 1);
-  int active = 0;
-  if (cudaOccupancyMaxActiveClusters(&active, kern, &cfg) == cudaSuccess && active > 0 &&
-      active < max_clusters)
-    max_clusters = active;
-  (void)cudaGetLastError();
+  int max_clusters = dev >= 0 && dev < 16 ? cached_clusters[dev] : 0;
+  if (max_clusters == 0) {
+    UQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    max_clusters = sms / 2;   // one CTA per SM: the TMEM allocation is per pair
+    cfg.gridDim = dim3((unsigned)sms, 1, 1);
+    int active = 0;
+    if (cudaOccupancyMaxActiveClusters(&active, kern, &cfg) == cudaSuccess && active > 0 &&
+        active < max_clusters)
+      max_clusters = active;
+    (void)cudaGetLastError();
+    if (dev >= 0 && dev < 16) cached_clusters[dev] = max_clusters;
+  }
   const int clusters = (int)(units < (int64_t)max_clusters ? units : (int64_t)max_clusters);
   cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
   UQ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));

@@ -124,8 +124,12 @@ template <bool FIRST, bool LAST>
 __global__ void __launch_bounds__(SORT_THREADS, 4)
 downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n, int shift,
                  int64_t tiles_per_block, const uint32_t* __restrict__ spine, int num_blocks) {
-  __shared__ uint32_t digit_base[RADIX];
+  __shared__ uint32_t digit_base[RADIX];   // running global position of each digit's next key
+  __shared__ uint32_t tile_off[RADIX];     // first tile-local position of each digit
+  __shared__ uint32_t gdelta[RADIX];
+  __shared__ uint32_t warp_tot[SORT_WARPS];
   __shared__ uint32_t wh[SORT_WARPS][RADIX];
+  __shared__ uint32_t staged[SORT_TILE];   // the tile in sorted order
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   for (int d = t; d < RADIX; d += SORT_THREADS)
@@ -178,26 +182,52 @@ downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, in
       __syncwarp();
     }
     __syncthreads();
+    // thread t == digit t: offsets of the warps inside the digit's run, the digit's run inside the
+    // tile (block-wide exclusive scan), and where that run goes in global memory
     {
-      // thread t == digit t: exclusive scan over the warps, seeded with the running global base
-      uint32_t run = digit_base[t];
+      uint32_t run = 0;
 #pragma unroll
       for (int ww = 0; ww < SORT_WARPS; ++ww) {
         const uint32_t c = wh[ww][t];
         wh[ww][t] = run;
         run += c;
       }
-      digit_base[t] = run;
+      uint32_t incl = run;   // digits-in-tile inclusive scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      if (lane == 31) warp_tot[w] = incl;
+      __syncthreads();
+      uint32_t before = 0;
+#pragma unroll
+      for (int ww = 0; ww < SORT_WARPS; ++ww)
+        if (ww < w) before += warp_tot[ww];
+      const uint32_t off = before + incl - run;   // first tile-local position of digit t
+      tile_off[t] = off;
+      gdelta[t] = digit_base[t] - off;            // global position = gdelta[d] + local position
+      digit_base[t] += run;
     }
     __syncthreads();
+    // keys go to their tile-local sorted position in shared memory first ...
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; ++r) {
       const int64_t idx = wbase + r * 32 + lane;
       if (idx < end) {
         const uint32_t d = (key[r] >> shift) & 0xFFu;
-        const uint32_t pos = wh[w][d] + rank[r];
-        out[pos] = LAST ? key2f(key[r]) : key[r];
+        staged[tile_off[d] + wh[w][d] + rank[r]] = key[r];
       }
+    }
+    __syncthreads();
+    // ... so that consecutive threads write consecutive addresses of a digit's run: a warp's store
+    // touches a few sectors instead of 32 (the direct scatter was LSU-sector bound)
+    const int tile_n = (int)((end - tile0) < (int64_t)SORT_TILE ? (end - tile0) : (int64_t)SORT_TILE);
+#pragma unroll 4
+    for (int i = t; i < tile_n; i += SORT_THREADS) {
+      const uint32_t k = staged[i];
+      const uint32_t d = (k >> shift) & 0xFFu;
+      out[gdelta[d] + (uint32_t)i] = LAST ? key2f(k) : k;
     }
     __syncthreads();
   }
