@@ -441,3 +441,62 @@ def test_wide_delta_uq_bf16():
                                anchors=anchors.to(DEV))
     ref_mean, ref_std = uq_oracle.delta_uq_forward(net, x, anchors, k)
     _bf16_check(mean, std, ref_mean, ref_std, "wide delta_uq")
+
+
+# ---- every kernel family at awkward sizes --------------------------------------------------------
+
+@pytest.mark.parametrize("width,n_hidden,n,k", [
+    (64, 2, 1, 2),        # narrow-net kernel (4 tile slots), a single row
+    (64, 3, 1025, 3),     # one row into the second unit of 1024
+    (128, 2, 2049, 2),
+    (192, 2, 257, 2),     # pair kernel, one accumulator half, tile pair + 1 row
+    (256, 3, 130, 4),
+    (320, 2, 383, 2),     # two unequal accumulator halves (N = 160)
+    (448, 2, 129, 2),
+    (1024, 2, 1, 2),      # wide-net kernel (64 rows per CTA), a single row
+    (1024, 2, 65, 3),
+    (768, 2, 193, 2),
+])
+def test_bf16_kernels_at_ragged_sizes(width, n_hidden, n, k):
+    nets = []
+    for i in range(k):
+        torch.manual_seed(100 + i)
+        net = build_network(_wide_arch(7, width, n_hidden, 1)).eval()
+        _randomise_bn(net, 50 + i)
+        nets.append(net)
+    x = torch.rand(n, 7, generator=torch.Generator().manual_seed(n))
+    packed = ops.PackedModel(nets, DEV)
+    assert packed.supports_bf16, packed.bf16_reason
+    mean, std = packed.forward(x.to(DEV), "ensemble", total_members=k, precision="bf16")
+    ref_mean, ref_std = uq_oracle.ensemble_forward(nets, x)
+    _bf16_check(mean, std, ref_mean, ref_std, f"ragged {width}x{n_hidden} n={n}")
+    # the same rows inside a larger batch give bit-identical results (tiles are independent)
+    xb = torch.cat([x, torch.rand(300, 7, generator=torch.Generator().manual_seed(1))])
+    mean_b, std_b = packed.forward(xb.to(DEV), "ensemble", total_members=k, precision="bf16")
+    assert torch.equal(mean_b[:n], mean) and torch.equal(std_b[:n], std)
+
+
+def test_narrow_kernel_many_passes_member_splits():
+    """MC dropout on the 6 x 128 surrogate with few samples and many passes: the member axis is
+    split over CTA pairs (each pair runs 4 tile slots) and merged; dropout off -> zero spread and
+    the same mean as a single pass."""
+    g = load_golden("mcdropout_binomial.npz")
+    p = float(g["p"])
+    net = nets_from_golden(g, 1, arch=mc_arch_with_dropout(golden_arch(g), p))[0]
+    packed = ops.PackedModel([net], DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    mean, std = packed.forward(x, "mc_dropout", total_members=256, precision="bf16", dropout_p=p,
+                               dropout_active=False)
+    one, _ = packed.forward(x, "mc_dropout", total_members=2, precision="bf16", dropout_p=p,
+                            dropout_active=False)
+    assert float((mean - one).abs().max()) <= 2e-6 * float(one.abs().max())
+    assert float(std.abs().max()) <= 1e-5 * float(one.abs().max())
+    # live dropout, native Philox: same seed -> same bits regardless of how passes are split
+    a = packed.forward(x, "mc_dropout", total_members=64, precision="bf16", dropout_p=p, seed=5)
+    lo = packed.forward(x, "mc_dropout", total_members=64, precision="bf16", dropout_p=p, seed=5,
+                        member_begin=0, member_count=24, output="moments")
+    hi = packed.forward(x, "mc_dropout", total_members=64, precision="bf16", dropout_p=p, seed=5,
+                        member_begin=24, member_count=40, output="moments")
+    mm, ss = ops.moments_merge(torch.stack([lo[0], hi[0]]), torch.stack([lo[1], hi[1]]), [24, 40])
+    assert float((mm - a[0]).abs().max()) <= 1e-5 * float(a[0].abs().max())
+    assert float((ss - a[1]).abs().max()) <= 1e-3 * float(a[1].abs().max())
