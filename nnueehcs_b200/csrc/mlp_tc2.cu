@@ -34,23 +34,12 @@
 #include "tc_ptx.cuh"
 #include "tc_epilogue.cuh"
 
-#ifndef UQ_TC_TWO_PHASE
-#define UQ_TC_TWO_PHASE 0
-#endif
 
 namespace uq {
 
 namespace {
 
 using namespace tc;
-#if UQ_ABLATE == 2
-#define fence_proxy_async_smem() ((void)0)
-#endif
-#if UQ_ABLATE == 3
-#define tmem_ld32(addr, r) do { for (int _i = 0; _i < 32; ++_i) r[_i] = (uint32_t)(addr) * (_i + 1); } while (0)
-#define tmem_ld16(addr, r) do { for (int _i = 0; _i < 16; ++_i) r[_i] = (uint32_t)(addr) * (_i + 1); } while (0)
-#define tmem_ld_wait() ((void)0)
-#endif
 constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
 
 // NG = epilogue warp groups (4 warps each, one per TMEM lane quarter); group j drains the
@@ -65,14 +54,6 @@ struct Geo2 {
   static constexpr int NT = H / NH;                      // MMA N of the pair
   static_assert(NT % 16 == 0, "MMA N must be a multiple of 16");
   static constexpr int TMEM_COLS = H <= 64 ? 64 : H <= 128 ? 128 : H <= 256 ? 256 : 512;
-  // Two-phase drain (see drain_half0): accumulator half 0 is drained into registers while the
-  // MMAs of half 1 still run.  Needs two halves whose boundary is a chunk boundary.  Measured on
-  // B200 (ensemble16x512_1M): 15.6 ms/step against 14.4 for the single-phase drain -- the
-  // overlapped epilogue competes with the MMA operand fetch for shared-memory bandwidth (stage
-  // period 470 -> 530..730 cycles) and pushes the chip into its power cap -- so it is off.
-  static constexpr bool TWO_PHASE = (UQ_TC_TWO_PHASE != 0) && (NH == 2) && (KC % 2 == 0);
-  static constexpr int C0 = TWO_PHASE ? KC / 2 : 0;      // chunks [0, C0) = accumulator half 0
-  static constexpr int NHELD = TWO_PHASE ? (C0 + NG - 1) / NG : 1;
   static constexpr int STAGE_BYTES = NT * 128;           // whole stage [NT x 64] bf16 in the image
   static constexpr int HALF_BYTES = STAGE_BYTES / 2;     // what one CTA of the pair loads
   static constexpr int A_BYTES = KC * CHUNK_BYTES;
@@ -97,7 +78,6 @@ constexpr uint32_t BAR_CHUNK = 128;      // 8 x 8 B   leader only: 4 warps of ea
 constexpr uint32_t BAR_D_FULL = 192;     //           commit multicast from the leader
 constexpr uint32_t BAR_X_READY = 200;    //           leader only: 4 warps of each CTA
 constexpr uint32_t BAR_TMEM_PTR = 208;
-constexpr uint32_t BAR_D_HALF = 216;     //           commit multicast: accumulator half 0 complete
 
 struct DrainCtx {
   uint32_t lane_addr;      // TMEM address of this warp's lane quarter, column 0
@@ -135,65 +115,6 @@ __device__ __forceinline__ void drain_trace(const DrainCtx& cx, unsigned kind, u
 #define UQ_DTRACE(kind, c)
 #endif
 
-// ---- two-phase drain ------------------------------------------------------------------------------
-// The next layer cannot start before the chunks of accumulator half 0 are drained and rewritten,
-// and they cannot be rewritten in place before every MMA of this layer has read them -- with a
-// single-phase drain the tensor core idles for the whole first half of the epilogue (~2500 cycles
-// per layer at H = 512).  So half 0 is drained as soon as ITS MMAs retire (BAR_D_HALF), while the
-// MMAs of half 1 still run: bias/ReLU/rounding happen then and the packed bf16 rows wait in
-// registers (32 words per chunk).  When the layer completes (BAR_D_FULL) only the st.shared burst,
-// one proxy fence and the barrier arrivals are left on the critical path.
-template <int H, int DOUT, int NG, bool RELU, bool DROP, bool LAST>
-__device__ __forceinline__ void drain_half0(const TcParams& p, const DrainCtx& cx,
-                                            uint32_t* held, float (&dot)[DOUT]) {
-  using G = Geo2<H, DOUT, NG>;
-#pragma unroll
-  for (int i = 0; i < G::NHELD; ++i) {
-    const int c = cx.grp + i * NG;
-    if (c < G::C0) {
-      uint32_t keep32 = 0xffffffffu;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {   // 16-column blocks: phase 1 is off the critical path, and
-        const int col0 = c * CHUNK_K + 16 * b;   // the held rows leave few registers to work in
-        uint32_t acc[16];
-        tmem_ld16(cx.lane_addr + (uint32_t)col0, acc);
-        float4 bv[4];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
-        if (DROP && (b & 1) == 0)
-          keep32 = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
-        tmem_ld_wait();
-        epi_math<H, DOUT, 16, RELU, DROP, LAST>(acc, bv, keep32 >> (16 * (b & 1)), cx.in_scale,
-                                                held + i * 32 + b * 8, cx.wl_s + col0,
-                                                cx.wl_g + col0, dot);
-      }
-    }
-  }
-}
-
-template <int H, int DOUT, int NG, bool LAST>
-__device__ __forceinline__ void flush_half0(const DrainCtx& cx, const uint32_t* held) {
-  using G = Geo2<H, DOUT, NG>;
-  if (!LAST) {
-#pragma unroll
-    for (int i = 0; i < G::NHELD; ++i) {
-      const int c = cx.grp + i * NG;
-      if (c < G::C0) epi_store<32>(held + i * 32, cx.a_row + (uint32_t)c * CHUNK_BYTES, 0, cx.rx);
-    }
-    fence_proxy_async_smem();
-  }
-  tc_fence_before();
-  __syncwarp();
-  if (cx.lane == 0) {
-#pragma unroll
-    for (int i = 0; i < G::NHELD; ++i) {
-      const int c = cx.grp + i * NG;
-      if (c < G::C0) mbar_arrive_cluster(cx.chunk_bar0 + 8 * c);
-    }
-  }
-}
-
 // Drain this warp's chunks of one layer-step.  NG == 2: 8 epilogue warps, TMEM loads run one
 // 32-column block ahead in a second register buffer.  NG == 4: 16 epilogue warps (4 per
 // scheduler) hide the tcgen05.ld / LDS latencies by thread-level parallelism instead, within the
@@ -214,10 +135,6 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
       // ---- block 0 (columns col0 .. col0+31) ----
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
-#if UQ_ABLATE == 4
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
       if (DROP) keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
       UQ_DTRACE(10, c);
       tmem_ld_wait();
@@ -230,10 +147,6 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
         bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0 + 32)[j4];
-#if UQ_ABLATE == 4
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
       if (DROP)
         keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0 + 32, cx.mask_layer, H);
       tmem_ld_wait();
@@ -334,7 +247,6 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     }
     for (int c = 0; c < KC; ++c) mbar_init(bars + BAR_CHUNK + 8 * c, 8);
     mbar_init(bars + BAR_D_FULL, 1);
-    mbar_init(bars + BAR_D_HALF, 1);
     mbar_init(bars + BAR_X_READY, 8);
     fence_barrier_init();
   }
@@ -448,7 +360,6 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
                                ks > 0 ? 1u : 0u);
             }
             release();
-            if (G::TWO_PHASE && nh == 0 && elect_one()) umma_commit_pair(bars + BAR_D_HALF, 3);
           }
           if (elect_one()) umma_commit_pair(bars + BAR_D_FULL, 3);
           UQ_TRACE(1, 4, g);
@@ -496,7 +407,6 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
               release();
               UQ_TRACE(1, 3, tr_it++);
             }
-            if (G::TWO_PHASE && nh == 0 && elect_one()) umma_commit_pair(bars + BAR_D_HALF, 3);
           }
           if (elect_one()) umma_commit_pair(bars + BAR_D_FULL, 3);  // whole layer accumulated
           UQ_TRACE(1, 4, g);
@@ -661,24 +571,6 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     if (relu) { if (drop) { CALL_TTF; } else { CALL_TFF; } }                                       \
     else { if (drop) { CALL_FTF; } else { CALL_FFF; } }                                            \
   }
-          uint32_t held[G::NHELD * 32];
-          if (G::TWO_PHASE) {
-            // ---- phase 1: accumulator half 0 -> registers while half 1 is still accumulating --
-            if (lane == 0) mbar_wait(bars + BAR_D_HALF, g & 1, p.error_flag, 7);
-            __syncwarp();
-            tc_fence_after();
-            if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 3, g); }
-            UQ_STEP_DISPATCH((drain_half0<H, DOUT, NG, true, true, true>(p, cx, held, dot)),
-                             (drain_half0<H, DOUT, NG, true, false, true>(p, cx, held, dot)),
-                             (drain_half0<H, DOUT, NG, false, true, true>(p, cx, held, dot)),
-                             (drain_half0<H, DOUT, NG, false, false, true>(p, cx, held, dot)),
-                             (drain_half0<H, DOUT, NG, true, true, false>(p, cx, held, dot)),
-                             (drain_half0<H, DOUT, NG, true, false, false>(p, cx, held, dot)),
-                             (drain_half0<H, DOUT, NG, false, true, false>(p, cx, held, dot)),
-                             (drain_half0<H, DOUT, NG, false, false, false>(p, cx, held, dot)))
-            if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 4, g); }
-          }
-
           // one lane polls the layer barrier, the rest of the warp parks on the warp barrier
           if (lane == 0) mbar_wait(bars + BAR_D_FULL, g & 1, p.error_flag, 5);
           __syncwarp();
@@ -688,14 +580,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           // every MMA that reads the A chunks has retired: stage the next member's input rows
           if (last && have_next) publish_x(ntile, p.member_begin + nk);
 
-          if (G::TWO_PHASE) {
-            // ---- phase 2: store the held rows, release half 0 to the MMA warp ------------------
-            if (last) flush_half0<H, DOUT, NG, true>(cx, held);
-            else flush_half0<H, DOUT, NG, false>(cx, held);
-            if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 5, g); }
-          }
-          // ---- phase 3: remaining chunks, straight from tensor memory --------------------------
-          const int c_begin = G::C0 + (((grp - G::C0) % NG) + NG) % NG;
+          const int c_begin = grp;
           UQ_STEP_DISPATCH((drain_step<H, DOUT, NG, true, true, true>(p, cx, c_begin, dot)),
                            (drain_step<H, DOUT, NG, true, false, true>(p, cx, c_begin, dot)),
                            (drain_step<H, DOUT, NG, false, true, true>(p, cx, c_begin, dot)),

@@ -6,10 +6,6 @@
 #include "tc_params.cuh"
 #include "tc_ptx.cuh"
 
-#ifndef UQ_ABLATE
-#define UQ_ABLATE 0   // bring-up builds: 1 no A write-back, 2 no proxy fence, 3 no TMEM loads, 4 no bias
-#endif
-
 namespace uq {
 namespace tc {
 
@@ -94,10 +90,6 @@ __device__ __forceinline__ void epi_math(const uint32_t (&acc)[NC], const float4
                                          uint32_t keep, float in_scale, uint32_t* packed,
                                          const float* __restrict__ wl_s,
                                          const float* __restrict__ wl_g, float (&dot)[DOUT]) {
-#if UQ_ABLATE == 5
-  if (LAST) { dot[0] += __uint_as_float(acc[0]) * 0.f; }
-  return;
-#endif
   float v[NC];
 #pragma unroll
   for (int j4 = 0; j4 < NC / 4; ++j4) {
@@ -157,14 +149,8 @@ __device__ __forceinline__ void epi_store(const uint32_t* packed, uint32_t a_dst
                                           int rx) {
 #pragma unroll
   for (int pc = 0; pc < NW / 4; ++pc) {
-#if UQ_ABLATE != 1
     st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4), packed[pc * 4 + 0],
                  packed[pc * 4 + 1], packed[pc * 4 + 2], packed[pc * 4 + 3]);
-#else
-    if (packed[pc * 4] == 0x12345678u && packed[pc * 4 + 1] == packed[pc * 4 + 2])
-      st_shared_v4(a_dst + (uint32_t)(((piece0 + pc) ^ rx) << 4), packed[pc * 4 + 0],
-                   packed[pc * 4 + 1], packed[pc * 4 + 2], packed[pc * 4 + 3]);
-#endif
   }
 }
 
