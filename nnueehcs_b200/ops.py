@@ -154,19 +154,15 @@ class PackedModel:
             anchors = anchors.detach().to(torch.float32).contiguous()
             if anchors.dim() != 2 or anchors.shape[1] != d_x or anchors.shape[0] < total_members:
                 raise ValueError(f"anchors must be [>= {total_members}, {d_x}]")
-        a = self._args(mode, precision, total_members, member_begin, member_count, dropout_p,
-                       dropout_active, seed, offset, masks, anchors, output)
-        n = xf.shape[0]
-        dev = xf.device
-        with torch.cuda.device(dev):
-            out0 = torch.empty((n, self.d_out), dtype=torch.float32, device=dev)
-            out1 = torch.empty((n, self.d_out), dtype=torch.float32, device=dev)
-            wsb = int(self._lib.uq_forward_workspace_bytes(self._handle, n, C.byref(a)))
-            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
-            _lib.check(self._lib.uq_forward(self._handle, xf.data_ptr(), n, C.byref(a),
-                                            out0.data_ptr(), out1.data_ptr(), ws.data_ptr(), wsb,
-                                            None, _stream_ptr(dev)))
-        return out0, out1
+        if precision not in _PREC:
+            raise ValueError(f"unknown precision {precision!r} (use 'fp32' or 'bf16')")
+        count = int(total_members - member_begin if member_count is None else member_count)
+        # the registered custom op (torch.ops.nnueehcs_b200.uq_forward, CUDA dispatch key only)
+        return torch.ops.nnueehcs_b200.uq_forward(
+            int(self._handle.value), xf, _MODE[mode], _PREC[precision],
+            _lib.OUT_MOMENTS if output == "moments" else _lib.OUT_MEAN_STD, int(member_begin),
+            count, int(total_members), bool(dropout_active), float(dropout_p),
+            _as_i64(seed), _as_i64(offset), masks, anchors, int(self.d_out))
 
     def forward_host(self, x_host: torch.Tensor, out0_host: torch.Tensor, out1_host: torch.Tensor,
                      mode: str, *, total_members: int, precision: str = "fp32",
@@ -214,15 +210,7 @@ def moments_merge(means: torch.Tensor, m2s: torch.Tensor, counts: Sequence[float
     s = means.shape[0]
     if len(counts) != s:
         raise ValueError("one count per shard is required")
-    length = means[0].numel()
-    out_mean = torch.empty(means.shape[1:], dtype=torch.float32, device=means.device)
-    out_std = torch.empty_like(out_mean)
-    cnt = (C.c_double * s)(*[float(c) for c in counts])
-    with torch.cuda.device(means.device):
-        _lib.check(lib.uq_moments_merge(means.data_ptr(), m2s.data_ptr(), cnt, s, length,
-                                        out_mean.data_ptr(), out_std.data_ptr(),
-                                        _stream_ptr(means.device)))
-    return out_mean, out_std
+    return torch.ops.nnueehcs_b200.moments_merge(means, m2s, [float(c) for c in counts])
 
 
 def _flat_f32(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -239,26 +227,14 @@ def wasserstein_1d(u: torch.Tensor, v: torch.Tensor) -> float:
     u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
     if u.numel() == 0 or v.numel() == 0:
         raise ValueError("Distribution can't be empty.")
-    out = C.c_double()
-    with torch.cuda.device(u.device):
-        wsb = int(lib.uq_wasserstein_workspace_bytes(u.numel(), v.numel()))
-        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
-        _lib.check(lib.uq_wasserstein_1d(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
-                                         C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
-    return float(out.value)
+    return float(torch.ops.nnueehcs_b200.wasserstein_1d(u, v))
 
 
 def kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000) -> float:
     """``JensenShannonEvaluation.pdf_jsd(u, v, num_points)`` for float32 device samples."""
     lib = _lib.load()
     u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
-    out = C.c_double()
-    with torch.cuda.device(u.device):
-        wsb = int(lib.uq_kde_jsd_workspace_bytes(u.numel(), v.numel(), num_points))
-        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
-        _lib.check(lib.uq_kde_jsd(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), num_points,
-                                  C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
-    return float(out.value)
+    return float(torch.ops.nnueehcs_b200.kde_jsd(u, v, int(num_points)))
 
 
 def score_metrics(id_scores: torch.Tensor, ood_scores: torch.Tensor, *, percentile_q: float = 95.0,
@@ -386,3 +362,97 @@ def wasserstein_1d_range(u: torch.Tensor, v: torch.Tensor, u_below: int, v_below
             v.numel(), int(u_below), int(v_below), int(nu_total), int(nv_total), out,
             ws.data_ptr(), wsb, _stream_ptr(u.device)))
     return float(out[0]), float(out[1]), float(out[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# torch custom-op registration ("registered once so Python sees torch.ops.<ns>.*").
+# The schemas carry tensors and plain numbers only; each implementation is registered for the
+# CUDA dispatch key alone and ends in one call through the C ABI, so a CPU tensor reaching the
+# dispatcher raises (NotImplementedError: no CPU kernel) instead of falling back.
+# ------------------------------------------------------------------------------------------------
+
+def _as_i64(v: int) -> int:
+    v = int(v) & 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _op_uq_forward(handle: int, x: torch.Tensor, mode: int, precision: int, output: int,
+                   member_begin: int, member_count: int, total_members: int,
+                   dropout_active: bool, dropout_p: float, seed: int, offset: int,
+                   masks: Optional[torch.Tensor], anchors: Optional[torch.Tensor], d_out: int
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    a = _lib.ForwardArgs()
+    a.mode, a.precision, a.output = mode, precision, output
+    a.member_begin, a.member_count, a.total_members = member_begin, member_count, total_members
+    a.dropout_active = 1 if dropout_active else 0
+    a.dropout_p = dropout_p
+    a.philox_seed = seed & 0xFFFFFFFFFFFFFFFF
+    a.philox_offset = offset & 0xFFFFFFFFFFFFFFFF
+    a.masks = masks.data_ptr() if masks is not None else None
+    a.anchors = anchors.data_ptr() if anchors is not None else None
+    n, dev = x.shape[0], x.device
+    h = C.c_void_p(handle)
+    with torch.cuda.device(dev):
+        out0 = torch.empty((n, d_out), dtype=torch.float32, device=dev)
+        out1 = torch.empty((n, d_out), dtype=torch.float32, device=dev)
+        wsb = int(lib.uq_forward_workspace_bytes(h, n, C.byref(a)))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        _lib.check(lib.uq_forward(h, x.data_ptr(), n, C.byref(a), out0.data_ptr(),
+                                  out1.data_ptr(), ws.data_ptr(), wsb, None, _stream_ptr(dev)))
+    return out0, out1
+
+
+def _op_moments_merge(means: torch.Tensor, m2s: torch.Tensor, counts: Sequence[float]
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    s = means.shape[0]
+    length = means[0].numel()
+    out_mean = torch.empty(means.shape[1:], dtype=torch.float32, device=means.device)
+    out_std = torch.empty_like(out_mean)
+    cnt = (C.c_double * s)(*[float(c) for c in counts])
+    with torch.cuda.device(means.device):
+        _lib.check(lib.uq_moments_merge(means.data_ptr(), m2s.data_ptr(), cnt, s, length,
+                                        out_mean.data_ptr(), out_std.data_ptr(),
+                                        _stream_ptr(means.device)))
+    return out_mean, out_std
+
+
+def _op_wasserstein_1d(u: torch.Tensor, v: torch.Tensor) -> float:
+    lib = _lib.load()
+    out = C.c_double()
+    with torch.cuda.device(u.device):
+        wsb = int(lib.uq_wasserstein_workspace_bytes(u.numel(), v.numel()))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
+        _lib.check(lib.uq_wasserstein_1d(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
+                                         C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
+    return float(out.value)
+
+
+def _op_kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int) -> float:
+    lib = _lib.load()
+    out = C.c_double()
+    with torch.cuda.device(u.device):
+        wsb = int(lib.uq_kde_jsd_workspace_bytes(u.numel(), v.numel(), num_points))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
+        _lib.check(lib.uq_kde_jsd(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), num_points,
+                                  C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
+    return float(out.value)
+
+
+OP_NAMESPACE = "nnueehcs_b200"
+OP_SCHEMAS = {
+    "uq_forward": "(int handle, Tensor x, int mode, int precision, int output, int member_begin, "
+                  "int member_count, int total_members, bool dropout_active, float dropout_p, "
+                  "int seed, int offset, Tensor? masks, Tensor? anchors, int d_out) "
+                  "-> (Tensor, Tensor)",
+    "moments_merge": "(Tensor means, Tensor m2s, float[] counts) -> (Tensor, Tensor)",
+    "wasserstein_1d": "(Tensor u, Tensor v) -> float",
+    "kde_jsd": "(Tensor u, Tensor v, int num_points) -> float",
+}
+_OP_IMPLS = {"uq_forward": _op_uq_forward, "moments_merge": _op_moments_merge,
+             "wasserstein_1d": _op_wasserstein_1d, "kde_jsd": _op_kde_jsd}
+_op_library = torch.library.Library(OP_NAMESPACE, "DEF")
+for _name, _schema in OP_SCHEMAS.items():
+    _op_library.define(_name + _schema)
+    _op_library.impl(_name, _OP_IMPLS[_name], "CUDA")

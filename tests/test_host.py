@@ -343,3 +343,20 @@ def test_metric_evaluator_shares_one_forward_per_dataset():
     out2 = evaluation.MetricEvaluator([U("a"), U("b"), Cm()], share_forward=False).evaluate(
         Model(), id_d, ood_d)
     assert calls == [3, 5] * 3 and out2 == out
+
+
+def test_custom_ops_are_registered_for_cuda_only():
+    """the C ABI is reachable as torch.ops.nnueehcs_b200.*; the ops have a CUDA
+    implementation and nothing else, so CPU tensors fail loudly at the dispatcher."""
+    ns = getattr(torch.ops, ops.OP_NAMESPACE)
+    for name in ops.OP_SCHEMAS:
+        assert hasattr(ns, name), name
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(f"{ops.OP_NAMESPACE}::{name}", "CUDA")
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(f"{ops.OP_NAMESPACE}::{name}",
+                                                                  "CPU")
+    with pytest.raises(NotImplementedError):
+        ns.wasserstein_1d(torch.rand(8), torch.rand(8))
+    with pytest.raises(NotImplementedError):
+        ns.kde_jsd(torch.rand(8), torch.rand(8), 100)
+    with pytest.raises(NotImplementedError):
+        ns.moments_merge(torch.rand(2, 8), torch.rand(2, 8), [1.0, 1.0])
