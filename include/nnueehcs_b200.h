@@ -145,6 +145,19 @@ size_t uq_wasserstein_workspace_bytes(int64_t nu, int64_t nv);
 int uq_wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, double* out_host,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/*    Same integral with the method spelled out (uq_wasserstein_1d = UQ_WASSERSTEIN_AUTO):
+      BINNED reads each sample once, resolves every key bin on which F_u - F_v keeps one sign from
+      the bin's (count, integer offset sum) alone and sorts only the values of the other bins;
+      SORT radix-sorts both samples (scipy's own route); AUTO = BINNED unless more than half of
+      the values sit in ambiguous bins or a value is inf/NaN.  info_host (may be NULL) receives
+      {method used, u values sorted, v values sorted}. */
+#define UQ_WASSERSTEIN_AUTO 0
+#define UQ_WASSERSTEIN_SORT 1
+#define UQ_WASSERSTEIN_BINNED 2
+int uq_wasserstein_1d_ex(const float* u, int64_t nu, const float* v, int64_t nv, int32_t method,
+                         double* out_host, int64_t* info_host, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /*    uq_kde_jsd replaces JensenShannonEvaluation.pdf_jsd (nnueehcs/evaluation.py:268-276):
       Scott-bandwidth Gaussian KDE of each sample on a shared `grid_pts`-point linspace between
       the joint min and max, then the Jensen-Shannon distance of the two pdf vectors. */

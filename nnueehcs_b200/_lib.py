@@ -14,6 +14,7 @@ UQ_OK, UQ_ERR_INVALID, UQ_ERR_CUDA, UQ_ERR_UNSUPPORTED, UQ_ERR_WORKSPACE = 0, 1,
 MODE_ENSEMBLE, MODE_MC_DROPOUT, MODE_DELTA_UQ = 0, 1, 2
 PREC_FP32, PREC_BF16 = 0, 1
 OUT_MEAN_STD, OUT_MOMENTS = 0, 1
+WASSERSTEIN_AUTO, WASSERSTEIN_SORT, WASSERSTEIN_BINNED = 0, 1, 2
 
 # every symbol include/nnueehcs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
@@ -21,6 +22,7 @@ EXPORTS = (
     "uq_model_create", "uq_model_destroy", "uq_model_supports_bf16",
     "uq_forward_workspace_bytes", "uq_forward", "uq_forward_host", "uq_moments_merge",
     "uq_philox_keep_masks", "uq_wasserstein_workspace_bytes", "uq_wasserstein_1d",
+    "uq_wasserstein_1d_ex",
     "uq_kde_jsd_workspace_bytes", "uq_kde_jsd",
     "uq_sample_stats_workspace_bytes", "uq_sample_stats", "uq_kde_grid_workspace_bytes",
     "uq_kde_grid_accumulate", "uq_jsd_from_grids", "uq_key_bins", "uq_key_histogram",
@@ -106,6 +108,9 @@ def load() -> C.CDLL:
     lib.uq_wasserstein_workspace_bytes.argtypes = [i64, i64]
     lib.uq_wasserstein_workspace_bytes.restype = sz
     lib.uq_wasserstein_1d.argtypes = [vp, i64, vp, i64, C.POINTER(dbl), vp, sz, vp]
+    lib.uq_wasserstein_1d_ex.argtypes = [vp, i64, vp, i64, i32, C.POINTER(dbl), C.POINTER(i64), vp,
+                                         sz, vp]
+    lib.uq_wasserstein_1d_ex.restype = C.c_int
     lib.uq_kde_jsd_workspace_bytes.argtypes = [i64, i64, i32]
     lib.uq_kde_jsd_workspace_bytes.restype = sz
     lib.uq_kde_jsd.argtypes = [vp, i64, vp, i64, i32, C.POINTER(dbl), vp, sz, vp]

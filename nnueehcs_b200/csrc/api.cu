@@ -317,7 +317,17 @@ int uq_wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, do
   UQ_REQUIRE(out_host != nullptr, UQ_ERR_INVALID, "uq_wasserstein_1d: out is NULL");
   UQ_REQUIRE(u && v && nu >= 1 && nv >= 1, UQ_ERR_INVALID,
              "uq_wasserstein_1d: Distribution can't be empty.");
-  return wasserstein_1d(u, nu, v, nv, out_host, workspace, workspace_bytes,
+  return wasserstein_1d(u, nu, v, nv, UQ_WASSERSTEIN_AUTO, out_host, nullptr, workspace,
+                        workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int uq_wasserstein_1d_ex(const float* u, int64_t nu, const float* v, int64_t nv, int32_t method,
+                         double* out_host, int64_t* info_host, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(out_host != nullptr, UQ_ERR_INVALID, "uq_wasserstein_1d_ex: out is NULL");
+  UQ_REQUIRE(u && v && nu >= 1 && nv >= 1, UQ_ERR_INVALID,
+             "uq_wasserstein_1d_ex: Distribution can't be empty.");
+  return wasserstein_1d(u, nu, v, nv, method, out_host, info_host, workspace, workspace_bytes,
                         static_cast<cudaStream_t>(stream));
 }
 

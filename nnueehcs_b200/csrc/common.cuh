@@ -105,8 +105,9 @@ int moments_merge(const float* means, const float* m2s, const double* counts, in
 
 // metrics (wasserstein.cu / kde_jsd.cu)
 size_t wasserstein_workspace_bytes(int64_t nu, int64_t nv);
-int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, double* out_host,
-                   void* ws, size_t ws_bytes, cudaStream_t st);
+int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, int method,
+                   double* out_host, int64_t* info_host, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
 int wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv, int64_t u_below,
                          int64_t v_below, int64_t nu_total, int64_t nv_total, double* out_host,
                          void* ws, size_t ws_bytes, cudaStream_t st);

@@ -221,13 +221,35 @@ def _flat_f32(t: torch.Tensor, what: str) -> torch.Tensor:
     return t
 
 
-def wasserstein_1d(u: torch.Tensor, v: torch.Tensor) -> float:
+_WMETHOD = {"auto": _lib.WASSERSTEIN_AUTO, "sort": _lib.WASSERSTEIN_SORT,
+            "binned": _lib.WASSERSTEIN_BINNED}
+
+
+def wasserstein_1d(u: torch.Tensor, v: torch.Tensor, method: str = "auto") -> float:
     """``scipy.stats.wasserstein_distance(u, v)`` for float32 device samples."""
+    u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
+    if u.numel() == 0 or v.numel() == 0:
+        raise ValueError("Distribution can't be empty.")
+    if method not in _WMETHOD:
+        raise ValueError(f"unknown Wasserstein method {method!r} (auto, sort, binned)")
+    return float(torch.ops.nnueehcs_b200.wasserstein_1d(u, v, _WMETHOD[method]))
+
+
+def wasserstein_1d_info(u: torch.Tensor, v: torch.Tensor, method: str = "auto") -> dict:
+    """Same value plus which method ran and how many values had to be sorted."""
     lib = _lib.load()
     u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
     if u.numel() == 0 or v.numel() == 0:
         raise ValueError("Distribution can't be empty.")
-    return float(torch.ops.nnueehcs_b200.wasserstein_1d(u, v))
+    out, info = C.c_double(), (C.c_int64 * 3)()
+    with torch.cuda.device(u.device):
+        wsb = int(lib.uq_wasserstein_workspace_bytes(u.numel(), v.numel()))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
+        _lib.check(lib.uq_wasserstein_1d_ex(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
+                                            _WMETHOD[method], C.byref(out), info, ws.data_ptr(),
+                                            wsb, _stream_ptr(u.device)))
+    return {"value": float(out.value), "method": "binned" if info[0] == 2 else "sort",
+            "sorted_u": int(info[1]), "sorted_v": int(info[2])}
 
 
 def kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000) -> float:
@@ -418,14 +440,15 @@ def _op_moments_merge(means: torch.Tensor, m2s: torch.Tensor, counts: Sequence[f
     return out_mean, out_std
 
 
-def _op_wasserstein_1d(u: torch.Tensor, v: torch.Tensor) -> float:
+def _op_wasserstein_1d(u: torch.Tensor, v: torch.Tensor, method: int = 0) -> float:
     lib = _lib.load()
     out = C.c_double()
     with torch.cuda.device(u.device):
         wsb = int(lib.uq_wasserstein_workspace_bytes(u.numel(), v.numel()))
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
-        _lib.check(lib.uq_wasserstein_1d(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
-                                         C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
+        _lib.check(lib.uq_wasserstein_1d_ex(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
+                                            method, C.byref(out), None, ws.data_ptr(), wsb,
+                                            _stream_ptr(u.device)))
     return float(out.value)
 
 
@@ -447,7 +470,7 @@ OP_SCHEMAS = {
                   "int seed, int offset, Tensor? masks, Tensor? anchors, int d_out) "
                   "-> (Tensor, Tensor)",
     "moments_merge": "(Tensor means, Tensor m2s, float[] counts) -> (Tensor, Tensor)",
-    "wasserstein_1d": "(Tensor u, Tensor v) -> float",
+    "wasserstein_1d": "(Tensor u, Tensor v, int method=0) -> float",
     "kde_jsd": "(Tensor u, Tensor v, int num_points) -> float",
 }
 _OP_IMPLS = {"uq_forward": _op_uq_forward, "moments_merge": _op_moments_merge,

@@ -274,3 +274,97 @@ def score_summaries(id_scores, percentile_q: float):
     float32 ID scores (evaluation.py:303, :323, :365)."""
     a = np.asarray(id_scores, dtype=np.float32).ravel()
     return float(np.mean(a)), float(np.max(a)), float(np.percentile(a, percentile_q))
+
+
+# ----------------------------------------------------------------------------------------------
+# Bin-moment form of the same Wasserstein integral (csrc/wasserstein.cu, "binned" method).
+# Not part of the reference: a numpy stand-in that the tests check the device tables and the
+# device result against, itself checked against wasserstein_1d above (scipy's arithmetic).
+#
+# The real line is cut at the 16384 key-bin boundaries t_b.  Inside one bin every float32 is
+# t_b + k * ulp_b with k = low 18 key bits, so  integral_bin F_u = ((C_b + c_b) w_b - K_b ulp_b)/n
+# from the bin's count c_b, the count below C_b and the integer sum K_b = sum k.  Where
+# D = F_u - F_v provably keeps one sign across the bin, |integral D| is the bin's contribution;
+# the other ("ambiguous") bins are integrated exactly from their sorted values.
+# ----------------------------------------------------------------------------------------------
+
+def _keys(x: np.ndarray) -> np.ndarray:
+    x = np.asarray(x, dtype=np.float32) + np.float32(0.0)  # -0.0 -> +0.0
+    b = x.view(np.uint32)
+    return np.where(b >> 31, ~b, b ^ np.uint32(0x80000000)).astype(np.uint32)
+
+
+def bin_edges() -> tuple:
+    """(t[KEY_BINS + 1], ulp[KEY_BINS]) as float64: lower edge and float spacing of every bin."""
+    b = np.arange(KEY_BINS + 1, dtype=np.uint64)
+    key = b << np.uint64(18)
+    pos = key >= np.uint64(0x80000000)
+    bits = np.where(pos, key - np.uint64(0x80000000), (~key) & np.uint64(0xFFFFFFFF) & np.uint64(0x7FFFFFFF))
+    e = (bits >> np.uint64(23)).astype(np.int64)          # 0 .. 256 (256 only for b = KEY_BINS)
+    m = (bits & np.uint64(0x7FFFFF)).astype(np.float64)
+    mag = np.where(e == 0, np.ldexp(m, -149), np.ldexp(m + 8388608.0, e - 150))
+    t = np.where(pos, mag, -mag)
+    ulp = np.ldexp(1.0, np.maximum(e[:-1], 1) - 150)
+    return t, ulp
+
+
+def bin_moments(x: np.ndarray) -> tuple:
+    """(count[KEY_BINS], ksum[KEY_BINS]) int64: values per bin and sum of their low 18 key bits."""
+    k = _keys(np.asarray(x).ravel())
+    b = (k >> np.uint32(18)).astype(np.int64)
+    low = (k & np.uint32(0x3FFFF)).astype(np.int64)
+    cnt = np.bincount(b, minlength=KEY_BINS).astype(np.int64)
+    ks = np.bincount(b, weights=low.astype(np.float64), minlength=KEY_BINS)
+    return cnt, np.rint(ks).astype(np.int64)
+
+
+def bin_resolve(cu, ku, cv, kv) -> dict:
+    """Per-bin contribution of the sign-definite bins, the ambiguity flags and the rank offsets
+    the exact pass over the ambiguous bins needs (python ints: products reach 2^62)."""
+    nu, nv = int(cu.sum()), int(cv.sum())
+    t, ulp = bin_edges()
+    Cu = np.concatenate([[0], np.cumsum(cu)]).astype(object)
+    Cv = np.concatenate([[0], np.cumsum(cv)]).astype(object)
+    flags = np.zeros(KEY_BINS, dtype=np.uint8)
+    resolved = 0.0
+    for b in np.nonzero((cu > 0) | (cv > 0) | (Cu[:-1] * nv != Cv[:-1] * nu))[0]:
+        b = int(b)
+        d_ge0 = Cu[b] * nv - (Cv[b] + int(cv[b])) * nu >= 0
+        d_le0 = (Cu[b] + int(cu[b])) * nv - Cv[b] * nu <= 0
+        if d_ge0 or d_le0:
+            w = t[b + 1] - t[b]
+            a = (float(Cu[b] + int(cu[b])) * w - float(ku[b]) * ulp[b]) / float(nu)
+            c = (float(Cv[b] + int(cv[b])) * w - float(kv[b]) * ulp[b]) / float(nv)
+            resolved += abs(a - c)
+        else:
+            flags[b] = 1
+    amb_u = np.concatenate([[0], np.cumsum(cu * flags)])
+    amb_v = np.concatenate([[0], np.cumsum(cv * flags)])
+    skip_u = np.asarray(Cu, dtype=np.int64) - amb_u
+    skip_v = np.asarray(Cv, dtype=np.int64) - amb_v
+    return {"resolved": resolved, "flags": flags, "skip_u": skip_u, "skip_v": skip_v,
+            "amb_u": int(amb_u[-1]), "amb_v": int(amb_v[-1]), "t": t}
+
+
+def wasserstein_1d_binned(u, v) -> float:
+    u = np.asarray(u, dtype=np.float32).ravel()
+    v = np.asarray(v, dtype=np.float32).ravel()
+    cu, ku = bin_moments(u)
+    cv, kv = bin_moments(v)
+    r = bin_resolve(cu, ku, cv, kv)
+    total = r["resolved"]
+    if r["amb_u"] + r["amb_v"]:
+        t, flags = r["t"], r["flags"]
+        nu, nv = float(u.size), float(v.size)
+        bu, bv = (_keys(u) >> np.uint32(18)).astype(np.int64), (_keys(v) >> np.uint32(18)).astype(np.int64)
+        for b in np.nonzero(flags)[0]:
+            xu = np.sort(u[bu == b].astype(np.float64))
+            xv = np.sort(v[bv == b].astype(np.float64))
+            allv = np.sort(np.concatenate([xu, xv]), kind="mergesort")
+            pts = np.concatenate([[t[b]], allv, [t[b + 1]]])
+            ru = np.concatenate([[0], np.searchsorted(xu, allv, side="right")])
+            rv = np.concatenate([[0], np.searchsorted(xv, allv, side="right")])
+            cb, db = int(cu[:b].sum()), int(cv[:b].sum())
+            d = (cb + ru) / nu - (db + rv) / nv
+            total += float(np.sum(np.abs(d) * np.diff(pts)))
+    return float(total)

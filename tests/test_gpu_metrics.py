@@ -62,6 +62,86 @@ def test_wasserstein_properties_and_reference_edge_cases():
     assert torch.equal(b, keep)
 
 
+def _binned_cases():
+    rng = np.random.default_rng(11)
+    g2 = rng.gamma(2.0, 0.05, 300001).astype(np.float32)
+    g3 = rng.gamma(3.0, 0.08, 250000).astype(np.float32)
+    nrm = rng.normal(0.0, 1.0, 100000).astype(np.float32)
+    return {
+        "gamma_id_vs_ood": (g2, g3),                       # every bin resolves in the first pass
+        "same_distribution": (g2, rng.gamma(2.0, 0.05, 150000).astype(np.float32)),
+        "crossing_cdfs": (nrm, rng.normal(0.3, 2.0, 70000).astype(np.float32)),
+        "zeros_vs_uniform": (np.zeros(1000, np.float32), rng.random(500).astype(np.float32)),
+        "wide_range_signed_zero": (np.array([1e-10, 1e10, 3, -5], np.float32),
+                                   np.array([2, -1e5, 0, -0.0, 7], np.float32)),
+        "denormals": ((rng.random(4000) * 1e-39).astype(np.float32),
+                      (rng.random(3000) * 2e-39 - 5e-40).astype(np.float32)),
+        "single_values": (np.array([1.0], np.float32), np.array([2.0], np.float32)),
+        "ties": (np.round(nrm, 1), np.round(nrm[::-1] * 1.5, 1).copy()),
+        "tile_edges": (rng.random(2048 * 3).astype(np.float32),
+                       (rng.random(2048 * 5 + 1) * 1.01).astype(np.float32)),
+    }
+
+
+@pytest.mark.parametrize("case", sorted(_binned_cases()))
+def test_wasserstein_binned_method_equals_sort_method_and_oracle(case):
+    """The one-pass bin-moment method, forced even where it has to sort most values, against the
+    sort method (scipy's route), the float64 oracle, and the numpy stand-in of its bookkeeping."""
+    u, v = _binned_cases()[case]
+    ref = metrics_oracle.wasserstein_1d(u, v)
+    cu, ku = metrics_oracle.bin_moments(u)
+    cv, kv = metrics_oracle.bin_moments(v)
+    book = metrics_oracle.bin_resolve(cu, ku, cv, kv)
+    for a, b, swap in ((u, v, False), (v, u, True)):
+        srt = ops.wasserstein_1d_info(_dev(a), _dev(b), "sort")
+        bnd = ops.wasserstein_1d_info(_dev(a), _dev(b), "binned")
+        auto = ops.wasserstein_1d_info(_dev(a), _dev(b), "auto")
+        assert srt["method"] == "sort" and bnd["method"] == "binned"
+        assert srt["value"] == pytest.approx(ref, rel=1e-11, abs=1e-300)
+        assert bnd["value"] == pytest.approx(ref, rel=1e-11, abs=1e-300)
+        assert auto["value"] == pytest.approx(ref, rel=1e-11, abs=1e-300)
+        amb = (book["amb_v"], book["amb_u"]) if swap else (book["amb_u"], book["amb_v"])
+        assert (bnd["sorted_u"], bnd["sorted_v"]) == amb
+        expect_auto = "binned" if sum(amb) <= (a.size + b.size) // 2 else "sort"
+        assert auto["method"] == expect_auto
+    if case == "gamma_id_vs_ood":
+        assert book["amb_u"] + book["amb_v"] == 0
+
+
+def test_wasserstein_binned_unaligned_views_and_nonfinite_fallback():
+    rng = np.random.default_rng(5)
+    base_u = _dev(rng.gamma(2.0, 0.05, 100003).astype(np.float32))
+    base_v = _dev(rng.gamma(3.0, 0.08, 100003).astype(np.float32))
+    for off in (1, 2, 3):   # float4 body with a scalar head / tail
+        u, v = base_u[off:], base_v[off + 1:-off]
+        ref = metrics_oracle.wasserstein_1d(u.cpu().numpy(), v.cpu().numpy())
+        assert ops.wasserstein_1d(u, v, "binned") == pytest.approx(ref, rel=1e-11)
+    w = base_u.clone()
+    w[17] = float("inf")
+    info = ops.wasserstein_1d_info(w, base_v, "binned")
+    assert info["method"] == "sort"            # inf / NaN: scipy's route decides what comes out
+    assert info["value"] == ops.wasserstein_1d(w, base_v, "sort")
+
+
+def test_wasserstein_binned_at_scale():
+    """BASELINE configs[4] shape on one GPU (50 M + 50 M Gamma scores): one pass, nothing sorted,
+    equal to the sort method to 1e-12."""
+    n = 50_000_000
+    g = torch.Generator(device=DEV).manual_seed(0)
+    u = torch.empty(n, device=DEV).exponential_(1.0, generator=g)
+    u = (u + torch.empty(n, device=DEV).exponential_(1.0, generator=g)) * 0.05       # Gamma(2, .05)
+    v = torch.zeros(n, device=DEV)
+    for _ in range(3):
+        v += torch.empty(n, device=DEV).exponential_(1.0, generator=g)
+    v *= 0.08                                                                         # Gamma(3, .08)
+    b = ops.wasserstein_1d_info(u, v, "binned")
+    s = ops.wasserstein_1d_info(u, v, "sort")
+    assert b["method"] == "binned"
+    assert b["sorted_u"] + b["sorted_v"] < n // 100
+    assert b["value"] == pytest.approx(s["value"], rel=1e-12)
+    assert b["value"] == pytest.approx(0.14, rel=0.01)   # E[v] - E[u] = 0.24 - 0.10 (v dominates u)
+
+
 def test_wasserstein_large_shift_property():
     """size-independent property at scale: W1(u, u + c) == c, W1(u, u) == 0 (8 M + 8 M values)."""
     n = 8 * 1024 * 1024

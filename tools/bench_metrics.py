@@ -63,7 +63,10 @@ def main():
     v = gamma_scores(args.n, 3, 0.08, 1, dev)
     hbm, src = peaks()
     total = 2 * args.n
+    same = gamma_scores(args.n, 2, 0.05, 2, dev)   # a second ID sample: every bin is ambiguous
     for name, fn in (("wasserstein_1d", lambda: ops.wasserstein_1d(u, v)),
+                     ("wasserstein_1d[sort]", lambda: ops.wasserstein_1d(u, v, "sort")),
+                     ("wasserstein_1d[same distribution, auto]", lambda: ops.wasserstein_1d(u, same)),
                      ("kde_jsd", lambda: ops.kde_jsd(u, v, args.grid))):
         ops.reset_launch_count()
         val = fn()
@@ -74,6 +77,11 @@ def main():
                 "values_per_s": total / (mean_ms * 1e-3), "gpu_launches_per_call": int(launches),
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
                              "frac": gbs / hbm, "algorithmic_bytes": total * 4, "peak_source": src}}
+        if name.startswith("wasserstein"):
+            info = ops.wasserstein_1d_info(u, same if "same" in name else v,
+                                           "sort" if "[sort]" in name else "auto")
+            line["method"] = info["method"]
+            line["values_sorted"] = info["sorted_u"] + info["sorted_v"]
         if name == "kde_jsd":
             line["gaussian_terms_equivalent_per_s"] = total * args.grid / (mean_ms * 1e-3)
         print(json.dumps(line), flush=True)
