@@ -229,6 +229,31 @@ int uq_wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t 
                             double* out_host, void* workspace, size_t workspace_bytes,
                             void* stream);
 
+
+/*    Per-rank steps of the sharded BINNED Wasserstein (no counterpart in the reference).
+      uq_bin_moments ADDS one shard to the caller-zeroed tables cnt / ksum (uint64 [uq_key_bins()]
+      each, device): values per key bin and the sum of their low 18 key bits.  The four tables
+      [cnt_u | ksum_u | cnt_v | ksum_v] are all-reduced over the ranks (one collective), then
+      uq_wasserstein_from_bins writes out_host[4] = {integral over the bins on which F_u - F_v
+      keeps one sign, ambiguous u values, ambiguous v values, values in inf/NaN bins} and
+      flags_out[bin] = 1 for ambiguous bins (uint8 [bins], device).  If values are ambiguous,
+      uq_compact_flagged collects a shard's ambiguous values (out: n floats of room; *count_host =
+      how many), the ranks all-gather them, and uq_wasserstein_ambiguous integrates those bins
+      exactly; the distance is the sum of the two parts.  Workspaces:
+      uq_wasserstein_workspace_bytes(1, 1) for from_bins / compact_flagged,
+      uq_wasserstein_workspace_bytes(max(nu_amb,1), max(nv_amb,1)) for ambiguous. */
+int uq_bin_moments(const float* x, int64_t n, uint64_t* cnt, uint64_t* ksum, void* stream);
+int uq_wasserstein_from_bins(const uint64_t* tables, int64_t nu_total, int64_t nv_total,
+                             uint8_t* flags_out, double* out_host, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int uq_compact_flagged(const float* x, int64_t n, const uint8_t* flags, float* out,
+                       int64_t* count_host, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int uq_wasserstein_ambiguous(const float* u_amb, int64_t nu_amb, const float* v_amb,
+                             int64_t nv_amb, const uint64_t* tables, int64_t nu_total,
+                             int64_t nv_total, double* out_host, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ EXPORTS = (
     "uq_kde_grid_accumulate", "uq_jsd_from_grids", "uq_key_bins", "uq_key_histogram",
     "uq_partition_by_bin", "uq_wasserstein_1d_range",
     "uq_score_metrics_workspace_bytes", "uq_score_metrics",
+    "uq_bin_moments", "uq_wasserstein_from_bins", "uq_compact_flagged", "uq_wasserstein_ambiguous",
 )
 
 
@@ -125,6 +126,14 @@ def load() -> C.CDLL:
     lib.uq_partition_by_bin.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     lib.uq_wasserstein_1d_range.argtypes = [vp, i64, vp, i64, i64, i64, i64, i64, C.POINTER(dbl),
                                             vp, sz, vp]
+    lib.uq_bin_moments.argtypes = [vp, i64, vp, vp, vp]
+    lib.uq_wasserstein_from_bins.argtypes = [vp, i64, i64, vp, C.POINTER(dbl), vp, sz, vp]
+    lib.uq_compact_flagged.argtypes = [vp, i64, vp, vp, C.POINTER(i64), vp, sz, vp]
+    lib.uq_wasserstein_ambiguous.argtypes = [vp, i64, vp, i64, vp, i64, i64, C.POINTER(dbl), vp,
+                                             sz, vp]
+    for name in ("uq_bin_moments", "uq_wasserstein_from_bins", "uq_compact_flagged",
+                 "uq_wasserstein_ambiguous"):
+        getattr(lib, name).restype = C.c_int
     lib.uq_score_metrics_workspace_bytes.argtypes = [i64, i64]
     lib.uq_score_metrics_workspace_bytes.restype = sz
     lib.uq_score_metrics.argtypes = [vp, i64, vp, i64, C.POINTER(ScoreRequest),

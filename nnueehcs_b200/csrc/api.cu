@@ -379,4 +379,47 @@ int uq_wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t 
                               workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int uq_bin_moments(const float* x, int64_t n, uint64_t* cnt, uint64_t* ksum, void* stream) {
+  UQ_REQUIRE(x && cnt && ksum && n >= 1, UQ_ERR_INVALID, "uq_bin_moments: NULL argument or n < 1");
+  return bin_moments_accumulate(x, n, reinterpret_cast<unsigned long long*>(cnt),
+                                reinterpret_cast<unsigned long long*>(ksum),
+                                static_cast<cudaStream_t>(stream));
+}
+
+int uq_wasserstein_from_bins(const uint64_t* tables, int64_t nu_total, int64_t nv_total,
+                             uint8_t* flags_out, double* out_host, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(tables && flags_out && out_host, UQ_ERR_INVALID,
+             "uq_wasserstein_from_bins: NULL argument");
+  UQ_REQUIRE(nu_total >= 1 && nv_total >= 1 && nu_total + nv_total < ((int64_t)1 << 31),
+             UQ_ERR_INVALID, "uq_wasserstein_from_bins: Distribution can't be empty (or too large).");
+  return wasserstein_from_bins(reinterpret_cast<const unsigned long long*>(tables), nu_total,
+                               nv_total, flags_out, out_host, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int uq_compact_flagged(const float* x, int64_t n, const uint8_t* flags, float* out,
+                       int64_t* count_host, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  UQ_REQUIRE(x && flags && out && count_host && n >= 1, UQ_ERR_INVALID,
+             "uq_compact_flagged: NULL argument or n < 1");
+  return compact_flagged(x, n, flags, out, count_host, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int uq_wasserstein_ambiguous(const float* u_amb, int64_t nu_amb, const float* v_amb,
+                             int64_t nv_amb, const uint64_t* tables, int64_t nu_total,
+                             int64_t nv_total, double* out_host, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(tables && out_host && nu_amb >= 0 && nv_amb >= 0 && (nu_amb == 0 || u_amb) &&
+                 (nv_amb == 0 || v_amb),
+             UQ_ERR_INVALID, "uq_wasserstein_ambiguous: NULL argument");
+  UQ_REQUIRE(nu_total >= 1 && nv_total >= 1, UQ_ERR_INVALID,
+             "uq_wasserstein_ambiguous: Distribution can't be empty.");
+  return wasserstein_ambiguous(u_amb, nu_amb, v_amb, nv_amb,
+                               reinterpret_cast<const unsigned long long*>(tables), nu_total,
+                               nv_total, out_host, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -108,6 +108,16 @@ size_t wasserstein_workspace_bytes(int64_t nu, int64_t nv);
 int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, int method,
                    double* out_host, int64_t* info_host, void* ws, size_t ws_bytes,
                    cudaStream_t st);
+int bin_moments_accumulate(const float* x, int64_t n, unsigned long long* cnt,
+                           unsigned long long* ksum, cudaStream_t st);
+int wasserstein_from_bins(const unsigned long long* tables, int64_t nu_total, int64_t nv_total,
+                          uint8_t* flags_out, double* out_host, void* ws, size_t ws_bytes,
+                          cudaStream_t st);
+int compact_flagged(const float* x, int64_t n, const uint8_t* flags, float* out,
+                    int64_t* count_host, void* ws, size_t ws_bytes, cudaStream_t st);
+int wasserstein_ambiguous(const float* u_amb, int64_t nu_amb, const float* v_amb, int64_t nv_amb,
+                          const unsigned long long* tables, int64_t nu_total, int64_t nv_total,
+                          double* out_host, void* ws, size_t ws_bytes, cudaStream_t st);
 int wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv, int64_t u_below,
                          int64_t v_below, int64_t nu_total, int64_t nv_total, double* out_host,
                          void* ws, size_t ws_bytes, cudaStream_t st);

@@ -146,7 +146,7 @@ constexpr int WB_BINS = 16384;      // == KEY_BINS of shard_metrics.cu (top 14 k
 constexpr int WB_LOW_BITS = 18;
 constexpr uint32_t WB_LOW_MASK = (1u << WB_LOW_BITS) - 1u;
 constexpr int BM_THREADS = 1024;
-constexpr int64_t BM_MAX_PER_BLOCK = (int64_t)1 << 22;  // 9-bit partial sums stay below 2^32
+constexpr int64_t BM_MAX_PER_BLOCK = (int64_t)1 << 19;  // H = count * 4096 + carries < 2^32 with margin
 
 __device__ __forceinline__ uint32_t wb_key(float x) {
   const uint32_t b = __float_as_uint(x + 0.0f);  // -0.0 -> +0.0: one bin for the value zero
@@ -154,37 +154,38 @@ __device__ __forceinline__ uint32_t wb_key(float x) {
 }
 
 // lower edge of key bin b (b in [0, WB_BINS]) as float64; the inf/NaN bins decode as if the
-// exponent range went on, so every bin has a finite width
+// exponent range went on, so every bin has a finite width.  *ulp = float32 spacing inside bin b.
 __device__ __forceinline__ double wb_edge(int b, double* ulp) {
-  const uint32_t key_hi = (uint32_t)b;                       // key >> 18, 15 bits for b = WB_BINS
+  const uint32_t key_hi = (uint32_t)b;  // key >> 18 (15 bits for b = WB_BINS)
   const bool pos = key_hi >= (1u << 13);
   const uint32_t bits = pos ? ((key_hi - (1u << 13)) << WB_LOW_BITS)
                             : (~(key_hi << WB_LOW_BITS)) & 0x7FFFFFFFu;
-  const int e = (int)(bits >> 23);
-  const double m = (double)(bits & 0x7FFFFFu);
-  const double mag = e == 0 ? scalbn(m, -149) : scalbn(m + 8388608.0, e - 150);
-  if (ulp) *ulp = scalbn(1.0, (e > 1 ? e : 1) - 150);
+  const int e = (int)(bits >> 23);      // 0 .. 256
+  const int es = e > 1 ? e : 1;
+  const double u = __longlong_as_double((long long)(es - 150 + 1023) << 52);  // 2^(es - 150)
+  const double mag = (double)((bits & 0x7FFFFFu) + (e ? 0x800000u : 0u)) * u;   // exact
+  if (ulp) *ulp = u;
   return pos ? mag : -mag;
 }
 
-// One pass over a sample: block-private shared-memory tables (count, sum of the low 9 and of the
-// high 9 of the 18 low key bits -- 32-bit shared atomics are native, 64-bit ones are a CAS loop),
-// flushed with one 64-bit reduction per non-empty bin.
+// One pass over a sample: block-private shared-memory tables, two native 32-bit shared atomics
+// per value (64-bit shared atomics are a CAS loop): L[b] += low 18 key bits (mod 2^32) and
+// H[b] += 4096, + 1 more when the L add wrapped.  So H = count * 4096 + carries and the integer
+// offset sum is carries * 2^32 + L; a block sees at most 2^20 values, which keeps
+// carries < 64 and H below 2^32.  Flushed with one 64-bit reduction per non-empty bin and table.
 __global__ void __launch_bounds__(BM_THREADS, 1)
 bin_moments_kernel(const float* __restrict__ x, int64_t n, unsigned long long* __restrict__ cnt,
                    unsigned long long* __restrict__ ksum) {
   extern __shared__ uint32_t bm_sh[];
-  uint32_t* c = bm_sh;
-  uint32_t* lo = bm_sh + WB_BINS;
-  uint32_t* hi = bm_sh + 2 * WB_BINS;
-  for (int i = threadIdx.x; i < 3 * WB_BINS; i += BM_THREADS) bm_sh[i] = 0;
+  uint32_t* H = bm_sh;
+  uint32_t* L = bm_sh + WB_BINS;
+  for (int i = threadIdx.x; i < 2 * WB_BINS; i += BM_THREADS) bm_sh[i] = 0;
   __syncthreads();
   auto add = [&](float v) {
     const uint32_t k = wb_key(v);
     const uint32_t b = k >> WB_LOW_BITS, low = k & WB_LOW_MASK;
-    atomicAdd(&c[b], 1u);
-    atomicAdd(&lo[b], low & 511u);
-    atomicAdd(&hi[b], low >> 9);
+    const uint32_t old = atomicAdd(&L[b], low);
+    atomicAdd(&H[b], 4096u + ((old + low) < old ? 1u : 0u));
   };
   // scalar head up to 16-byte alignment, float4 body (4 loads in flight per thread), scalar tail
   const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
@@ -210,106 +211,128 @@ bin_moments_kernel(const float* __restrict__ x, int64_t n, unsigned long long* _
   if (tail0 + gtid < n) add(__ldg(x + tail0 + gtid));
   __syncthreads();
   for (int b = threadIdx.x; b < WB_BINS; b += BM_THREADS) {
-    const uint32_t cb = c[b];
-    if (cb) {
-      atomicAdd(&cnt[b], (unsigned long long)cb);
-      atomicAdd(&ksum[b], (unsigned long long)lo[b] + ((unsigned long long)hi[b] << 9));
+    const uint32_t h = H[b];
+    if (h) {
+      atomicAdd(&cnt[b], (unsigned long long)(h >> 12));
+      atomicAdd(&ksum[b], ((unsigned long long)(h & 4095u) << 32) + (unsigned long long)L[b]);
     }
   }
 }
 
-struct BinnedResult {
-  double resolved;     // sum of the sign-definite bins' contributions
-  long long amb_u, amb_v;  // values of each sample in ambiguous bins
-  long long nonfinite;     // values in the inf / NaN bins (the caller falls back to the sort method)
+constexpr int RS_BLOCKS = 64;  // bin_contrib_kernel: 64 blocks x 256 threads, one bin per thread
+struct BinnedResult {          // zeroed together with the tables
+  long long amb_u, amb_v;      // values of each sample in ambiguous bins
+  long long nonfinite;         // values in the inf / NaN bins (the caller falls back to sorting)
+  double parts[RS_BLOCKS];     // per-block sums of the sign-definite bins' contributions
 };
 
-// Single block: prefix counts, per-bin contribution or ambiguity flag, rank offsets of the exact
-// pass (skip_x[b] = values of x below bin b that sit in resolved bins), bin edges.
+// exclusive block-wide scan of a pair of values (1024 threads); ta / tb = block totals
+__device__ __forceinline__ void block_scan_pair(long long a, long long b, long long& ea,
+                                                long long& eb, long long& ta, long long& tb,
+                                                long long* sm /* [64] */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long ia = a, ib = b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long xa = __shfl_up_sync(0xffffffffu, ia, o), xb = __shfl_up_sync(0xffffffffu, ib, o);
+    if (lane >= o) ia += xa, ib += xb;
+  }
+  if (lane == 31) sm[w] = ia, sm[32 + w] = ib;
+  __syncthreads();
+  const long long wa = sm[lane], wb = sm[32 + lane];  // every warp scans the 32 warp totals
+  long long sa = wa, sb = wb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long xa = __shfl_up_sync(0xffffffffu, sa, o), xb = __shfl_up_sync(0xffffffffu, sb, o);
+    if (lane >= o) sa += xa, sb += xb;
+  }
+  const long long base_a = __shfl_sync(0xffffffffu, sa - wa, w);
+  const long long base_b = __shfl_sync(0xffffffffu, sb - wb, w);
+  ta = __shfl_sync(0xffffffffu, sa, 31);
+  tb = __shfl_sync(0xffffffffu, sb, 31);
+  ea = base_a + ia - a;
+  eb = base_b + ib - b;
+  __syncthreads();
+}
+
+// Exclusive prefix sums of a pair of per-bin tables, one bin per thread, 16 blocks of 1024.
+// Block j first adds up the bins of the blocks below it (thread t takes bin i * 1024 + t of every
+// lower block i: coalesced, independent loads), then scans its own 1024 bins.  A single block
+// walking all 16384 bins is limited by one SM's sector rate (measured 27-43 us; this: a few us).
+// With `flags` only flagged bins count (prefix of the ambiguous values) and the output is
+// `minus - prefix` (the rank offsets skip_x of the exact pass).
+constexpr int SCAN_BLOCKS = WB_BINS / 1024;
 __global__ void __launch_bounds__(1024, 1)
-bin_resolve_kernel(const unsigned long long* __restrict__ cnt_u,
+bin_scan_kernel(const unsigned long long* __restrict__ cnt_a,
+                const unsigned long long* __restrict__ cnt_b, const uint8_t* __restrict__ flags,
+                const long long* __restrict__ minus_a, const long long* __restrict__ minus_b,
+                long long* __restrict__ out_a, long long* __restrict__ out_b) {
+  __shared__ long long sm[64];
+  const int t = threadIdx.x;
+  const int j = blockIdx.x;
+  const int b = j * 1024 + t;
+  long long sa = 0, sb = 0;  // counts stay below 2^31: only the low words are loaded
+#pragma unroll 4
+  for (int i = 0; i < j; ++i) {
+    const int bb = i * 1024 + t;
+    if (flags == nullptr || flags[bb]) sa += (uint32_t)cnt_a[bb], sb += (uint32_t)cnt_b[bb];
+  }
+  const bool on = flags == nullptr || flags[b];
+  const long long ca = on ? (long long)(uint32_t)cnt_a[b] : 0;
+  const long long cb = on ? (long long)(uint32_t)cnt_b[b] : 0;
+  const long long ma = minus_a ? minus_a[b] : 0, mb = minus_b ? minus_b[b] : 0;
+  long long ea, eb, base_a, base_b, ta, tb;
+  block_scan_pair(sa, sb, ea, eb, base_a, base_b, sm);
+  block_scan_pair(ca, cb, ea, eb, ta, tb, sm);
+  ea += base_a, eb += base_b;
+  out_a[b] = minus_a ? ma - ea : ea;
+  out_b[b] = minus_b ? mb - eb : eb;
+}
+
+// One bin per thread: contribution of the bin if D = F_u - F_v provably keeps one sign on it,
+// else the ambiguity flag; bin edges for the exact pass.
+__global__ void __launch_bounds__(WB_BINS / RS_BLOCKS)
+bin_contrib_kernel(const unsigned long long* __restrict__ cnt_u,
                    const unsigned long long* __restrict__ ks_u,
                    const unsigned long long* __restrict__ cnt_v,
-                   const unsigned long long* __restrict__ ks_v, long long nu, long long nv,
-                   uint8_t* __restrict__ flags, long long* __restrict__ skip_u,
-                   long long* __restrict__ skip_v, double* __restrict__ edges,
-                   BinnedResult* __restrict__ res) {
-  constexpr int PER = WB_BINS / 1024;  // consecutive bins per thread
-  __shared__ long long sc[4][1024];
-  __shared__ double sd[1024];
+                   const unsigned long long* __restrict__ ks_v,
+                   const long long* __restrict__ pre_u, const long long* __restrict__ pre_v,
+                   long long nu, long long nv, uint8_t* __restrict__ flags,
+                   double* __restrict__ edges, BinnedResult* __restrict__ res) {
+  constexpr int T = WB_BINS / RS_BLOCKS;
+  __shared__ double sd[T];
   const int t = threadIdx.x;
-  const int b0 = t * PER;
-  long long tot_u = 0, tot_v = 0;
-  for (int q = 0; q < PER; ++q) tot_u += (long long)cnt_u[b0 + q], tot_v += (long long)cnt_v[b0 + q];
-  sc[0][t] = tot_u, sc[1][t] = tot_v;
-  __syncthreads();
-  // exclusive scan over the 1024 thread totals (Hillis-Steele, two arrays at once)
-  auto scan2 = [&](int a, int b) {
-    for (int o = 1; o < 1024; o <<= 1) {
-      long long xa = 0, xb = 0;
-      if (t >= o) xa = sc[a][t - o], xb = sc[b][t - o];
-      __syncthreads();
-      sc[a][t] += xa, sc[b][t] += xb;
-      __syncthreads();
-    }
-  };
-  scan2(0, 1);
-  long long Cu = sc[0][t] - tot_u, Cv = sc[1][t] - tot_v;
-  const double dnu = (double)nu, dnv = (double)nv;
+  const int b = blockIdx.x * T + t;
+  const long long cu = (long long)cnt_u[b], cv = (long long)cnt_v[b];
+  const long long Cu = pre_u[b], Cv = pre_v[b];
+  const unsigned long long ku = ks_u[b], kv = ks_v[b];
+  double ulp;
+  const double tb = wb_edge(b, &ulp);
+  const double w = wb_edge(b + 1, nullptr) - tb;
+  edges[b] = tb;
+  if (b == WB_BINS - 1) edges[WB_BINS] = tb + w;
+  const bool d_ge0 = Cu * nv - (Cv + cv) * nu >= 0;  // D >= 0 on the whole bin (|.| < 2^62)
+  const bool d_le0 = (Cu + cu) * nv - Cv * nu <= 0;  // D <= 0 on the whole bin
   double acc = 0.0;
-  long long au = 0, av = 0, nonfin = 0;
-  uint8_t fl[PER];
-  for (int q = 0; q < PER; ++q) {
-    const int b = b0 + q;
-    const long long cu = (long long)cnt_u[b], cv = (long long)cnt_v[b];
-    double ulp;
-    const double tb = wb_edge(b, &ulp);
-    const double w = wb_edge(b + 1, nullptr) - tb;
-    edges[b] = tb;
-    if (b == WB_BINS - 1) edges[WB_BINS] = tb + w;
-    if ((b < 32 || b >= WB_BINS - 32) && (cu | cv)) nonfin += cu + cv;
-    const bool d_ge0 = Cu * nv - (Cv + cv) * nu >= 0;  // D >= 0 on the whole bin (|.| < 2^62)
-    const bool d_le0 = (Cu + cu) * nv - Cv * nu <= 0;  // D <= 0 on the whole bin
-    fl[q] = 0;
-    if (d_ge0 || d_le0) {
-      if ((cu | cv) || Cu * nv != Cv * nu) {
-        const double a = ((double)(Cu + cu) * w - (double)ks_u[b] * ulp) / dnu;
-        const double c = ((double)(Cv + cv) * w - (double)ks_v[b] * ulp) / dnv;
-        acc += fabs(a - c);
-      }
-    } else {
-      fl[q] = 1;
-      au += cu, av += cv;
-    }
-    flags[b] = fl[q];
-    Cu += cu, Cv += cv;
+  const bool amb = !(d_ge0 || d_le0);
+  if (!amb && ((cu | cv) || Cu * nv != Cv * nu)) {
+    const double a = ((double)(Cu + cu) * w - (double)ku * ulp) / (double)nu;
+    const double c = ((double)(Cv + cv) * w - (double)kv * ulp) / (double)nv;
+    acc = fabs(a - c);
   }
-  __syncthreads();
-  sc[0][t] = au, sc[1][t] = av, sc[2][t] = nonfin, sd[t] = acc;
-  __syncthreads();
-  scan2(0, 1);
-  // skip tables: values below bin b in resolved bins = C_b - (ambiguous values below b)
-  long long ambu = sc[0][t] - au, ambv = sc[1][t] - av;
-  Cu -= tot_u, Cv -= tot_v;  // back to the count below bin b0
-  for (int q = 0; q < PER; ++q) {
-    const int b = b0 + q;
-    skip_u[b] = Cu - ambu, skip_v[b] = Cv - ambv;
-    const long long cu = (long long)cnt_u[b], cv = (long long)cnt_v[b];
-    if (fl[q]) ambu += cu, ambv += cv;
-    Cu += cu, Cv += cv;
+  flags[b] = amb ? 1 : 0;
+  if (amb) {  // integer atomics: order-independent
+    atomicAdd(reinterpret_cast<unsigned long long*>(&res->amb_u), (unsigned long long)cu);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&res->amb_v), (unsigned long long)cv);
   }
-  if (t == 1023) skip_u[WB_BINS] = Cu - ambu, skip_v[WB_BINS] = Cv - ambv;
-  // fixed-order reductions
-  for (int o = 512; o > 0; o >>= 1) {
+  if ((b < 32 || b >= WB_BINS - 32) && (cu | cv))
+    atomicAdd(reinterpret_cast<unsigned long long*>(&res->nonfinite), (unsigned long long)(cu + cv));
+  sd[t] = acc;
+  for (int o = T / 2; o > 0; o >>= 1) {  // fixed-order tree: deterministic
     __syncthreads();
-    if (t < o) sd[t] += sd[t + o], sc[2][t] += sc[2][t + o];
+    if (t < o) sd[t] += sd[t + o];
   }
-  if (t == 0) {
-    res->resolved = sd[0];
-    res->amb_u = sc[0][1023];
-    res->amb_v = sc[1][1023];
-    res->nonfinite = sc[2][0];
-  }
+  if (t == 0) res->parts[blockIdx.x] = sd[0];
 }
 
 // values whose bin is flagged -> out (order arbitrary: they are sorted next)
@@ -416,7 +439,7 @@ cdf_integral_binned_kernel(const float* __restrict__ U, int64_t nu, const float*
 }
 
 struct WsLayout {
-  size_t u, ut, v, vt, scratch, parts, splits, result, tables, flags, skips, edges, bres, cursors, total;
+  size_t u, ut, v, vt, scratch, parts, splits, result, tables, bres, pre, flags, skips, edges, cursors, total;
   int64_t blocks;
 };
 
@@ -436,10 +459,11 @@ WsLayout layout(int64_t nu, int64_t nv) {
   L.splits = o; o += al(sizeof(int64_t) * (size_t)L.blocks);
   L.result = o; o += 256;
   L.tables = o; o += al(sizeof(unsigned long long) * 4 * WB_BINS);  // cnt_u, ks_u, cnt_v, ks_v
+  L.bres = o; o += al(sizeof(BinnedResult));                        // zeroed with the tables
+  L.pre = o; o += al(sizeof(long long) * 2 * WB_BINS);
   L.flags = o; o += al(WB_BINS);
   L.skips = o; o += al(sizeof(long long) * 2 * (WB_BINS + 1));
   L.edges = o; o += al(sizeof(double) * (WB_BINS + 1));
-  L.bres = o; o += 256;
   L.cursors = o; o += 256;
   L.total = o;
   return L;
@@ -457,13 +481,13 @@ namespace {
 int bin_moments_launch(const float* x, int64_t n, unsigned long long* cnt, unsigned long long* ks,
                        cudaStream_t st) {
   static bool attr_set = false;
-  constexpr int SMEM = 3 * WB_BINS * (int)sizeof(uint32_t);
+  constexpr int SMEM = 2 * WB_BINS * (int)sizeof(uint32_t);
   if (!attr_set) {
     UQ_CUDA(cudaFuncSetAttribute(bin_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SMEM));
     attr_set = true;
   }
-  // one block per SM; more only to keep a block's 9-bit partial sums below 2^32
+  // one block per SM; more only to keep a block below BM_MAX_PER_BLOCK values
   int64_t blocks = (n + (int64_t)BM_THREADS * 16 - 1) / ((int64_t)BM_THREADS * 16);
   if (blocks > 148) blocks = 148;
   const int64_t need = (n + BM_MAX_PER_BLOCK - 1) / BM_MAX_PER_BLOCK;
@@ -501,6 +525,85 @@ int sort_and_integrate(float* du, float* dut, int64_t nu, float* dv, float* dvt,
 
 }  // namespace
 
+namespace {
+
+struct BinTables {
+  unsigned long long *cnt_u, *ks_u, *cnt_v, *ks_v;
+};
+BinTables tables_at(unsigned long long* t) { return {t, t + WB_BINS, t + 2 * WB_BINS, t + 3 * WB_BINS}; }
+
+// tables (already complete, e.g. all-reduced over ranks) -> flags, edges, prefix counts and the
+// host copy of BinnedResult; synchronises the stream.  `bres` must be zeroed.
+int resolve_bins(const BinTables& T, int64_t nu, int64_t nv, char* b, const WsLayout& L,
+                 uint8_t* flags, BinnedResult* h, double* resolved, cudaStream_t st) {
+  long long* pre_u = reinterpret_cast<long long*>(b + L.pre);
+  long long* pre_v = pre_u + WB_BINS;
+  double* edges = reinterpret_cast<double*>(b + L.edges);
+  BinnedResult* bres = reinterpret_cast<BinnedResult*>(b + L.bres);
+  bin_scan_kernel<<<SCAN_BLOCKS, 1024, 0, st>>>(T.cnt_u, T.cnt_v, nullptr, nullptr, nullptr, pre_u, pre_v);
+  UQ_LAUNCH_CHECK();
+  bin_contrib_kernel<<<RS_BLOCKS, WB_BINS / RS_BLOCKS, 0, st>>>(
+      T.cnt_u, T.ks_u, T.cnt_v, T.ks_v, pre_u, pre_v, (long long)nu, (long long)nv, flags, edges,
+      bres);
+  UQ_LAUNCH_CHECK();
+  UQ_CUDA(cudaMemcpyAsync(h, bres, sizeof(*h), cudaMemcpyDeviceToHost, st));
+  UQ_CUDA(cudaStreamSynchronize(st));
+  *resolved = 0.0;
+  for (int q = 0; q < RS_BLOCKS; ++q) *resolved += h->parts[q];  // fixed order
+  return UQ_OK;
+}
+
+// Exact integral over the ambiguous bins.  du / dv hold the (unsorted) ambiguous values and are
+// clobbered; pre / edges / flags come from resolve_bins on the same workspace.  Synchronises.
+int ambiguous_exact(const BinTables& T, const uint8_t* flags, float* du, float* dut, int64_t amb_u,
+                    float* dv, float* dvt, int64_t amb_v, int64_t nu, int64_t nv, char* b,
+                    const WsLayout& L, double* exact_host, cudaStream_t st) {
+  long long* pre_u = reinterpret_cast<long long*>(b + L.pre);
+  long long* pre_v = pre_u + WB_BINS;
+  long long* skip_u = reinterpret_cast<long long*>(b + L.skips);
+  long long* skip_v = skip_u + WB_BINS + 1;
+  double* edges = reinterpret_cast<double*>(b + L.edges);
+  double* result = reinterpret_cast<double*>(b + L.result);
+  bin_scan_kernel<<<SCAN_BLOCKS, 1024, 0, st>>>(T.cnt_u, T.cnt_v, flags, pre_u, pre_v, skip_u, skip_v);
+  UQ_LAUNCH_CHECK();
+  float *su = du, *sv = dv;
+  int rc;
+  if (amb_u > 0) {
+    rc = radix_sort_f32(du, dut, amb_u, b + L.scratch, radix_sort_scratch_bytes(amb_u), &su, st);
+    if (rc != UQ_OK) return rc;
+  }
+  if (amb_v > 0) {
+    rc = radix_sort_f32(dv, dvt, amb_v, b + L.scratch, radix_sort_scratch_bytes(amb_v), &sv, st);
+    if (rc != UQ_OK) return rc;
+  }
+  const int64_t amb = amb_u + amb_v;
+  const int64_t blocks = (amb + MRG_TILE - 1) / MRG_TILE;
+  int64_t* splits = reinterpret_cast<int64_t*>(b + L.splits);
+  double* parts = reinterpret_cast<double*>(b + L.parts);
+  merge_partition_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, st>>>(su, amb_u, sv, amb_v,
+                                                                           blocks, splits);
+  UQ_LAUNCH_CHECK();
+  cdf_integral_binned_kernel<<<(unsigned)blocks, MRG_THREADS, 0, st>>>(
+      su, amb_u, sv, amb_v, skip_u, skip_v, edges, nu, nv, splits, parts);
+  UQ_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 1024, 0, st>>>(parts, blocks, result);
+  UQ_LAUNCH_CHECK();
+  UQ_CUDA(cudaMemcpyAsync(exact_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
+  UQ_CUDA(cudaStreamSynchronize(st));
+  return UQ_OK;
+}
+
+int compact_launch(const float* x, int64_t n, const uint8_t* flags, float* out,
+                   unsigned long long* cursor, cudaStream_t st) {
+  const int64_t tile = 256 * 16;
+  compact_flagged_kernel<<<(unsigned)((n + tile - 1) / tile), 256, 0, st>>>(x, n, flags, out,
+                                                                            cursor);
+  UQ_LAUNCH_CHECK();
+  return UQ_OK;
+}
+
+}  // namespace
+
 // method: UQ_WASSERSTEIN_AUTO / _SORT / _BINNED (binned even when most values are ambiguous).
 // info_host (may be NULL): {method used, ambiguous u values, ambiguous v values}.
 int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, int method,
@@ -521,68 +624,34 @@ int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, int m
   if (info_host) info_host[0] = UQ_WASSERSTEIN_SORT, info_host[1] = nu, info_host[2] = nv;
 
   if (method != UQ_WASSERSTEIN_SORT) {
-    unsigned long long* tables = reinterpret_cast<unsigned long long*>(b + L.tables);
-    unsigned long long *cnt_u = tables, *ks_u = tables + WB_BINS, *cnt_v = tables + 2 * WB_BINS,
-                       *ks_v = tables + 3 * WB_BINS;
+    const BinTables T = tables_at(reinterpret_cast<unsigned long long*>(b + L.tables));
     uint8_t* flags = reinterpret_cast<uint8_t*>(b + L.flags);
-    long long* skip_u = reinterpret_cast<long long*>(b + L.skips);
-    long long* skip_v = skip_u + WB_BINS + 1;
-    double* edges = reinterpret_cast<double*>(b + L.edges);
-    BinnedResult* bres = reinterpret_cast<BinnedResult*>(b + L.bres);
-    UQ_CUDA(cudaMemsetAsync(tables, 0, sizeof(unsigned long long) * 4 * WB_BINS, st));
-    int rc = bin_moments_launch(u, nu, cnt_u, ks_u, st);
+    UQ_CUDA(cudaMemsetAsync(b + L.tables, 0, L.pre - L.tables, st));  // tables + BinnedResult
+    int rc = bin_moments_launch(u, nu, T.cnt_u, T.ks_u, st);
     if (rc != UQ_OK) return rc;
-    rc = bin_moments_launch(v, nv, cnt_v, ks_v, st);
+    rc = bin_moments_launch(v, nv, T.cnt_v, T.ks_v, st);
     if (rc != UQ_OK) return rc;
-    bin_resolve_kernel<<<1, 1024, 0, st>>>(cnt_u, ks_u, cnt_v, ks_v, (long long)nu, (long long)nv,
-                                           flags, skip_u, skip_v, edges, bres);
-    UQ_LAUNCH_CHECK();
     BinnedResult h;
-    UQ_CUDA(cudaMemcpyAsync(&h, bres, sizeof(h), cudaMemcpyDeviceToHost, st));
-    UQ_CUDA(cudaStreamSynchronize(st));
+    double resolved;
+    rc = resolve_bins(T, nu, nv, b, L, flags, &h, &resolved, st);
+    if (rc != UQ_OK) return rc;
     const int64_t amb = h.amb_u + h.amb_v;
     const bool use = h.nonfinite == 0 &&
                      (method == UQ_WASSERSTEIN_BINNED || amb <= (nu + nv) / 2);
     if (use) {
       if (info_host) info_host[0] = UQ_WASSERSTEIN_BINNED, info_host[1] = h.amb_u, info_host[2] = h.amb_v;
-      if (amb == 0) {
-        *out_host = h.resolved;
-        return UQ_OK;
-      }
-      // exact pass over the ambiguous bins: compact -> sort -> clipped merge integral
-      unsigned long long* cursors = reinterpret_cast<unsigned long long*>(b + L.cursors);
-      UQ_CUDA(cudaMemsetAsync(cursors, 0, 2 * sizeof(unsigned long long), st));
-      const int64_t tile = 256 * 16;
-      compact_flagged_kernel<<<(unsigned)((nu + tile - 1) / tile), 256, 0, st>>>(u, nu, flags, du,
-                                                                                 cursors);
-      UQ_LAUNCH_CHECK();
-      compact_flagged_kernel<<<(unsigned)((nv + tile - 1) / tile), 256, 0, st>>>(v, nv, flags, dv,
-                                                                                 cursors + 1);
-      UQ_LAUNCH_CHECK();
-      float *su = du, *sv = dv;
-      if (h.amb_u > 0) {
-        rc = radix_sort_f32(du, dut, h.amb_u, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
-        if (rc != UQ_OK) return rc;
-      }
-      if (h.amb_v > 0) {
-        rc = radix_sort_f32(dv, dvt, h.amb_v, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
-        if (rc != UQ_OK) return rc;
-      }
-      const int64_t blocks = (amb + MRG_TILE - 1) / MRG_TILE;
-      int64_t* splits = reinterpret_cast<int64_t*>(b + L.splits);
-      double* parts = reinterpret_cast<double*>(b + L.parts);
-      merge_partition_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, st>>>(
-          su, h.amb_u, sv, h.amb_v, blocks, splits);
-      UQ_LAUNCH_CHECK();
-      cdf_integral_binned_kernel<<<(unsigned)blocks, MRG_THREADS, 0, st>>>(
-          su, h.amb_u, sv, h.amb_v, skip_u, skip_v, edges, nu, nv, splits, parts);
-      UQ_LAUNCH_CHECK();
-      sum_partials_kernel<<<1, 1024, 0, st>>>(parts, blocks, result);
-      UQ_LAUNCH_CHECK();
       double exact = 0.0;
-      UQ_CUDA(cudaMemcpyAsync(&exact, result, sizeof(double), cudaMemcpyDeviceToHost, st));
-      UQ_CUDA(cudaStreamSynchronize(st));
-      *out_host = h.resolved + exact;
+      if (amb > 0) {
+        unsigned long long* cursors = reinterpret_cast<unsigned long long*>(b + L.cursors);
+        UQ_CUDA(cudaMemsetAsync(cursors, 0, 2 * sizeof(unsigned long long), st));
+        rc = compact_launch(u, nu, flags, du, cursors, st);
+        if (rc != UQ_OK) return rc;
+        rc = compact_launch(v, nv, flags, dv, cursors + 1, st);
+        if (rc != UQ_OK) return rc;
+        rc = ambiguous_exact(T, flags, du, dut, h.amb_u, dv, dvt, h.amb_v, nu, nv, b, L, &exact, st);
+        if (rc != UQ_OK) return rc;
+      }
+      *out_host = resolved + exact;
       return UQ_OK;
     }
   }
@@ -594,6 +663,82 @@ int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, int m
   UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
   UQ_CUDA(cudaStreamSynchronize(st));
   return UQ_OK;
+}
+
+// ---- per-rank steps of the sharded binned method (nnueehcs_b200.distributed) --------------------
+
+int bin_moments_accumulate(const float* x, int64_t n, unsigned long long* cnt,
+                           unsigned long long* ksum, cudaStream_t st) {
+  return bin_moments_launch(x, n, cnt, ksum, st);
+}
+
+// tables = [cnt_u | ks_u | cnt_v | ks_v] of the WHOLE samples.  out_host = {sum of the resolved
+// bins, ambiguous u values, ambiguous v values, values in inf/NaN bins}; flags_out[bin] = ambiguous.
+int wasserstein_from_bins(const unsigned long long* tables, int64_t nu_total, int64_t nv_total,
+                          uint8_t* flags_out, double* out_host, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+  const WsLayout L = layout(1, 1);
+  UQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, UQ_ERR_WORKSPACE,
+             "wasserstein_from_bins needs %zu workspace bytes, got %zu", L.total, ws_bytes);
+  char* b = static_cast<char*>(ws);
+  const BinTables T = tables_at(const_cast<unsigned long long*>(tables));
+  UQ_CUDA(cudaMemsetAsync(b + L.bres, 0, sizeof(BinnedResult), st));
+  BinnedResult h;
+  double resolved;
+  const int rc = resolve_bins(T, nu_total, nv_total, b, L, flags_out, &h, &resolved, st);
+  if (rc != UQ_OK) return rc;
+  out_host[0] = resolved;
+  out_host[1] = (double)h.amb_u;
+  out_host[2] = (double)h.amb_v;
+  out_host[3] = (double)h.nonfinite;
+  return UQ_OK;
+}
+
+int compact_flagged(const float* x, int64_t n, const uint8_t* flags, float* out,
+                    int64_t* count_host, void* ws, size_t ws_bytes, cudaStream_t st) {
+  UQ_REQUIRE(ws != nullptr && ws_bytes >= 8, UQ_ERR_WORKSPACE, "compact_flagged: workspace too small");
+  unsigned long long* cursor = static_cast<unsigned long long*>(ws);
+  UQ_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+  const int rc = compact_launch(x, n, flags, out, cursor, st);
+  if (rc != UQ_OK) return rc;
+  unsigned long long c = 0;
+  UQ_CUDA(cudaMemcpyAsync(&c, cursor, sizeof(c), cudaMemcpyDeviceToHost, st));
+  UQ_CUDA(cudaStreamSynchronize(st));
+  *count_host = (int64_t)c;
+  return UQ_OK;
+}
+
+// Exact part: u_amb / v_amb = every ambiguous value of the whole samples (any order, left
+// untouched), tables as above.  Writes the integral over the ambiguous bins.
+int wasserstein_ambiguous(const float* u_amb, int64_t nu_amb, const float* v_amb, int64_t nv_amb,
+                          const unsigned long long* tables, int64_t nu_total, int64_t nv_total,
+                          double* out_host, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const WsLayout L = layout(nu_amb > 0 ? nu_amb : 1, nv_amb > 0 ? nv_amb : 1);
+  UQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, UQ_ERR_WORKSPACE,
+             "wasserstein_ambiguous needs %zu workspace bytes, got %zu", L.total, ws_bytes);
+  UQ_REQUIRE(nu_amb + nv_amb >= 1 && nu_amb + nv_amb < ((int64_t)1 << 31), UQ_ERR_INVALID,
+             "wasserstein_ambiguous: %lld values", (long long)(nu_amb + nv_amb));
+  char* b = static_cast<char*>(ws);
+  float* du = reinterpret_cast<float*>(b + L.u);
+  float* dut = reinterpret_cast<float*>(b + L.ut);
+  float* dv = reinterpret_cast<float*>(b + L.v);
+  float* dvt = reinterpret_cast<float*>(b + L.vt);
+  uint8_t* flags = reinterpret_cast<uint8_t*>(b + L.flags);
+  const BinTables T = tables_at(const_cast<unsigned long long*>(tables));
+  UQ_CUDA(cudaMemsetAsync(b + L.bres, 0, sizeof(BinnedResult), st));
+  BinnedResult h;
+  double resolved;
+  int rc = resolve_bins(T, nu_total, nv_total, b, L, flags, &h, &resolved, st);
+  if (rc != UQ_OK) return rc;
+  UQ_REQUIRE(h.amb_u == nu_amb && h.amb_v == nv_amb, UQ_ERR_INVALID,
+             "wasserstein_ambiguous: got %lld + %lld values, the tables say %lld + %lld",
+             (long long)nu_amb, (long long)nv_amb, h.amb_u, h.amb_v);
+  if (nu_amb > 0)
+    UQ_CUDA(cudaMemcpyAsync(du, u_amb, sizeof(float) * (size_t)nu_amb, cudaMemcpyDeviceToDevice, st));
+  if (nv_amb > 0)
+    UQ_CUDA(cudaMemcpyAsync(dv, v_amb, sizeof(float) * (size_t)nv_amb, cudaMemcpyDeviceToDevice, st));
+  return ambiguous_exact(T, flags, du, dut, nu_amb, dv, dvt, nv_amb, nu_total, nv_total, b, L,
+                         out_host, st);
 }
 
 // One value range of a sample-sorted (multi-GPU) Wasserstein: this rank holds every u and v

@@ -370,6 +370,72 @@ def partition_by_bin(x: torch.Tensor, bin_to_part: torch.Tensor, part_counts: Se
     return out
 
 
+def bin_moments(x: torch.Tensor, tables: torch.Tensor, row: int) -> None:
+    """Adds shard ``x`` to ``tables[row]`` (counts per key bin) and ``tables[row + 1]`` (sum of the
+    low 18 key bits per bin); ``tables`` = int64 [4, key_bins()] on x's device."""
+    lib = _lib.load()
+    x = _flat_f32(x, "x")
+    _require_cuda(tables, "tables")
+    if tables.dtype != torch.int64 or tuple(tables.shape) != (4, key_bins()) \
+            or not tables.is_contiguous():
+        raise ValueError("tables must be a contiguous int64 [4, key_bins()] tensor")
+    if x.numel() == 0:
+        return
+    with torch.cuda.device(x.device):
+        _lib.check(lib.uq_bin_moments(x.data_ptr(), x.numel(), tables[row].data_ptr(),
+                                      tables[row + 1].data_ptr(), _stream_ptr(x.device)))
+
+
+def wasserstein_from_bins(tables: torch.Tensor, nu_total: int, nv_total: int) -> dict:
+    """Resolved part of the Wasserstein integral from complete (all-reduced) bin tables."""
+    lib = _lib.load()
+    _require_cuda(tables, "tables")
+    dev = tables.device
+    flags = torch.empty(key_bins(), dtype=torch.uint8, device=dev)
+    out = (C.c_double * 4)()
+    with torch.cuda.device(dev):
+        wsb = int(lib.uq_wasserstein_workspace_bytes(1, 1))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _lib.check(lib.uq_wasserstein_from_bins(tables.data_ptr(), int(nu_total), int(nv_total),
+                                                flags.data_ptr(), out, ws.data_ptr(), wsb,
+                                                _stream_ptr(dev)))
+    return {"resolved": float(out[0]), "amb_u": int(out[1]), "amb_v": int(out[2]),
+            "nonfinite": int(out[3]), "flags": flags}
+
+
+def compact_flagged(x: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
+    """The values of ``x`` whose key bin is flagged (order arbitrary)."""
+    lib = _lib.load()
+    x = _flat_f32(x, "x")
+    if x.numel() == 0:
+        return x
+    out = torch.empty_like(x)
+    cnt = C.c_int64()
+    with torch.cuda.device(x.device):
+        ws = torch.empty(256, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.uq_compact_flagged(x.data_ptr(), x.numel(), flags.data_ptr(),
+                                          out.data_ptr(), C.byref(cnt), ws.data_ptr(), 256,
+                                          _stream_ptr(x.device)))
+    return out[:cnt.value]
+
+
+def wasserstein_ambiguous(u_amb: torch.Tensor, v_amb: torch.Tensor, tables: torch.Tensor,
+                          nu_total: int, nv_total: int) -> float:
+    """Exact integral over the ambiguous bins from all their values (any order)."""
+    lib = _lib.load()
+    u_amb, v_amb = _flat_f32(u_amb, "u_amb"), _flat_f32(v_amb, "v_amb")
+    out = C.c_double()
+    dev = tables.device
+    with torch.cuda.device(dev):
+        wsb = int(lib.uq_wasserstein_workspace_bytes(max(u_amb.numel(), 1), max(v_amb.numel(), 1)))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _lib.check(lib.uq_wasserstein_ambiguous(
+            u_amb.data_ptr() if u_amb.numel() else None, u_amb.numel(),
+            v_amb.data_ptr() if v_amb.numel() else None, v_amb.numel(), tables.data_ptr(),
+            int(nu_total), int(nv_total), C.byref(out), ws.data_ptr(), wsb, _stream_ptr(dev)))
+    return float(out.value)
+
+
 def wasserstein_1d_range(u: torch.Tensor, v: torch.Tensor, u_below: int, v_below: int,
                          nu_total: int, nv_total: int) -> Tuple[float, float, float]:
     """(partial integral, first merged value, last merged value) of one value range."""

@@ -346,6 +346,30 @@ def bin_resolve(cu, ku, cv, kv) -> dict:
             "amb_u": int(amb_u[-1]), "amb_v": int(amb_v[-1]), "t": t}
 
 
+def wasserstein_ambiguous(u_amb, v_amb, cu, ku, cv, kv) -> float:
+    """Exact integral over the ambiguous bins from all their values (bin tables of the whole
+    samples give the ranks below each bin)."""
+    r = bin_resolve(cu, ku, cv, kv)
+    t, flags = r["t"], r["flags"]
+    nu, nv = float(cu.sum()), float(cv.sum())
+    u = np.asarray(u_amb, dtype=np.float32).ravel()
+    v = np.asarray(v_amb, dtype=np.float32).ravel()
+    bu = (_keys(u) >> np.uint32(18)).astype(np.int64)
+    bv = (_keys(v) >> np.uint32(18)).astype(np.int64)
+    total = 0.0
+    for b in np.nonzero(flags)[0]:
+        xu = np.sort(u[bu == b].astype(np.float64))
+        xv = np.sort(v[bv == b].astype(np.float64))
+        allv = np.sort(np.concatenate([xu, xv]), kind="mergesort")
+        pts = np.concatenate([[t[b]], allv, [t[b + 1]]])
+        ru = np.concatenate([[0], np.searchsorted(xu, allv, side="right")])
+        rv = np.concatenate([[0], np.searchsorted(xv, allv, side="right")])
+        cb, db = int(cu[:b].sum()), int(cv[:b].sum())
+        d = (cb + ru) / nu - (db + rv) / nv
+        total += float(np.sum(np.abs(d) * np.diff(pts)))
+    return total
+
+
 def wasserstein_1d_binned(u, v) -> float:
     u = np.asarray(u, dtype=np.float32).ravel()
     v = np.asarray(v, dtype=np.float32).ravel()
@@ -354,17 +378,44 @@ def wasserstein_1d_binned(u, v) -> float:
     r = bin_resolve(cu, ku, cv, kv)
     total = r["resolved"]
     if r["amb_u"] + r["amb_v"]:
-        t, flags = r["t"], r["flags"]
-        nu, nv = float(u.size), float(v.size)
-        bu, bv = (_keys(u) >> np.uint32(18)).astype(np.int64), (_keys(v) >> np.uint32(18)).astype(np.int64)
-        for b in np.nonzero(flags)[0]:
-            xu = np.sort(u[bu == b].astype(np.float64))
-            xv = np.sort(v[bv == b].astype(np.float64))
-            allv = np.sort(np.concatenate([xu, xv]), kind="mergesort")
-            pts = np.concatenate([[t[b]], allv, [t[b + 1]]])
-            ru = np.concatenate([[0], np.searchsorted(xu, allv, side="right")])
-            rv = np.concatenate([[0], np.searchsorted(xv, allv, side="right")])
-            cb, db = int(cu[:b].sum()), int(cv[:b].sum())
-            d = (cb + ru) / nu - (db + rv) / nv
-            total += float(np.sum(np.abs(d) * np.diff(pts)))
+        flags = r["flags"].astype(bool)
+        total += wasserstein_ambiguous(u[flags[key_bin(u + np.float32(0.0))]],
+                                       v[flags[key_bin(v + np.float32(0.0))]], cu, ku, cv, kv)
     return float(total)
+
+
+def _np_bin_moments(x, tables, row):
+    import torch
+    if x.numel() == 0:
+        return
+    c, k = bin_moments(x.detach().cpu().numpy())
+    tables[row] += torch.from_numpy(c)
+    tables[row + 1] += torch.from_numpy(k)
+
+
+def _np_from_bins(tables, nu_total, nv_total):
+    import torch
+    t = tables.cpu().numpy()
+    assert int(t[0].sum()) == nu_total and int(t[2].sum()) == nv_total
+    r = bin_resolve(t[0], t[1], t[2], t[3])
+    nonfinite = int(t[0][:32].sum() + t[0][-32:].sum() + t[2][:32].sum() + t[2][-32:].sum())
+    return {"resolved": float(r["resolved"]), "amb_u": r["amb_u"], "amb_v": r["amb_v"],
+            "nonfinite": nonfinite, "flags": torch.from_numpy(r["flags"])}
+
+
+def _np_compact_flagged(x, flags):
+    import torch
+    a = x.detach().cpu().numpy().ravel()
+    keep = flags.cpu().numpy().astype(bool)[key_bin(a + np.float32(0.0))]
+    return torch.from_numpy(a[keep].copy())
+
+
+def _np_ambiguous(u_amb, v_amb, tables, nu_total, nv_total):
+    t = tables.cpu().numpy()
+    return wasserstein_ambiguous(u_amb.cpu().numpy(), v_amb.cpu().numpy(), t[0], t[1], t[2], t[3])
+
+
+NumpyShardBackend.bin_moments = staticmethod(_np_bin_moments)
+NumpyShardBackend.wasserstein_from_bins = staticmethod(_np_from_bins)
+NumpyShardBackend.compact_flagged = staticmethod(_np_compact_flagged)
+NumpyShardBackend.wasserstein_ambiguous = staticmethod(_np_ambiguous)

@@ -34,6 +34,9 @@ def _samples(case):
     elif case == "ties":           # heavy ties, identical values in both samples, negatives
         u = rng.integers(-3, 4, 3000).astype(np.float32) * 0.5
         v = rng.integers(-1, 6, 2000).astype(np.float32) * 0.5
+    elif case == "crossing":       # CDFs cross: a few ambiguous bins travel, the rest resolves
+        u = rng.normal(0.0, 1.0, 5000).astype(np.float32)
+        v = rng.normal(0.3, 2.0, 3500).astype(np.float32)
     else:                          # disjoint supports: one rank's range may hold a single sample
         u = rng.uniform(0.0, 1.0, 2500).astype(np.float32)
         v = rng.uniform(5.0, 6.0, 2500).astype(np.float32)
@@ -52,14 +55,17 @@ def _worker(rank, world, port, case, out_dir):
         if rank == world - 1:
             ul = torch.cat([ul, torch.from_numpy(u[0::world][-7:].copy())])
         vl = torch.from_numpy(v[rank::world].copy())
-        w = nd.wasserstein_1d_sharded(ul, vl, backend=metrics_oracle.NumpyShardBackend)
-        j = nd.kde_jsd_sharded(ul, vl, 512, backend=metrics_oracle.NumpyShardBackend)
-        torch.save({"w": w, "j": j}, os.path.join(out_dir, f"rank{rank}.pt"))
+        be = metrics_oracle.NumpyShardBackend
+        info = {m: {} for m in ("auto", "binned", "sort")}
+        w = {m: nd.wasserstein_1d_sharded(ul, vl, backend=be, method=m, info=info[m])
+             for m in info}
+        j = nd.kde_jsd_sharded(ul, vl, 512, backend=be)
+        torch.save({"w": w, "j": j, "info": info}, os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["gamma", "ties", "disjoint"])
+@pytest.mark.parametrize("case", ["gamma", "ties", "crossing", "disjoint"])
 def test_sharded_metrics_match_unsharded_oracle(tmp_path, case):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
@@ -67,8 +73,17 @@ def test_sharded_metrics_match_unsharded_oracle(tmp_path, case):
     w_ref = metrics_oracle.wasserstein_1d(u, v)
     j_ref = metrics_oracle.pdf_jsd(u, v, 512)
     for r in range(world):
-        got = torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"))
-        assert abs(got["w"] - w_ref) <= 1e-12 * max(1.0, abs(w_ref)), (case, got["w"], w_ref)
+        got = torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"), weights_only=False)
+        for m, w in got["w"].items():
+            assert abs(w - w_ref) <= 1e-12 * max(1.0, abs(w_ref)), (case, m, w, w_ref)
+        info = got["info"]
+        assert info["sort"]["method"] == "sort" and info["binned"]["method"] == "binned"
+        assert info["sort"]["exchanged_values"] == u.size + v.size
+        if case in ("gamma", "disjoint"):   # every bin resolves: nothing but the tables is exchanged
+            assert info["auto"] == {"method": "binned", "exchanged_values": 0}
+        if case == "crossing":
+            assert info["auto"]["method"] == "binned"
+            assert 0 < info["auto"]["exchanged_values"] < (u.size + v.size) // 4
         assert abs(got["j"] - j_ref) <= 5e-8 * max(1.0, abs(j_ref)), (case, got["j"], j_ref)
 
 

@@ -270,6 +270,47 @@ def test_wasserstein_ranges_compose_to_the_full_distance():
     assert abs(total - ref) <= 1e-10 * ref
 
 
+@pytest.mark.parametrize("case", ["gamma_id_vs_ood", "crossing_cdfs", "same_distribution",
+                                  "wide_range_signed_zero"])
+def test_binned_wasserstein_steps_match_numpy_stand_ins(case):
+    """uq_bin_moments / uq_wasserstein_from_bins / uq_compact_flagged / uq_wasserstein_ambiguous
+    (the per-rank steps of the sharded binned method) against oracle.metrics_oracle, shard-wise."""
+    u, v = _binned_cases()[case]
+    tables = torch.zeros((4, ops.key_bins()), dtype=torch.int64, device=DEV)
+    cut_u, cut_v = u.size // 3, v.size // 2
+    for part in (u[:cut_u], u[cut_u:]):          # two shards accumulate into the same tables
+        ops.bin_moments(_dev(part), tables, 0)
+    for part in (v[:cut_v], v[cut_v:]):
+        ops.bin_moments(_dev(part), tables, 2)
+    cu, ku = metrics_oracle.bin_moments(u)
+    cv, kv = metrics_oracle.bin_moments(v)
+    t = tables.cpu().numpy()
+    assert np.array_equal(t[0], cu) and np.array_equal(t[1], ku)
+    assert np.array_equal(t[2], cv) and np.array_equal(t[3], kv)
+    book = metrics_oracle.bin_resolve(cu, ku, cv, kv)
+    r = ops.wasserstein_from_bins(tables, u.size, v.size)
+    assert (r["amb_u"], r["amb_v"], r["nonfinite"]) == (book["amb_u"], book["amb_v"], 0)
+    assert np.array_equal(r["flags"].cpu().numpy(), book["flags"])
+    assert r["resolved"] == pytest.approx(book["resolved"], rel=1e-12, abs=1e-300)
+    au = torch.cat([ops.compact_flagged(_dev(u[:cut_u]), r["flags"]),
+                    ops.compact_flagged(_dev(u[cut_u:]), r["flags"])])
+    av = ops.compact_flagged(_dev(v), r["flags"])
+    fl = book["flags"].astype(bool)
+    assert np.array_equal(np.sort(au.cpu().numpy()), np.sort(u[fl[metrics_oracle.key_bin(u + np.float32(0))]]))
+    assert av.numel() == book["amb_v"]
+    ref = metrics_oracle.wasserstein_1d(u, v)
+    if au.numel() + av.numel():
+        exact = ops.wasserstein_ambiguous(au, av, tables, u.size, v.size)
+        assert exact == pytest.approx(
+            metrics_oracle.wasserstein_ambiguous(au.cpu().numpy(), av.cpu().numpy(), cu, ku, cv, kv),
+            rel=1e-11, abs=1e-300)
+        with pytest.raises(ValueError, match="the tables say"):
+            ops.wasserstein_ambiguous(au[:-1], av, tables, u.size, v.size)
+    else:
+        exact = 0.0
+    assert r["resolved"] + exact == pytest.approx(ref, rel=1e-11)
+
+
 def test_kde_grid_accumulate_and_jsd_match_oracle():
     u, v = _gamma_pair(30_000, 20_000)
     G = 2000
@@ -307,6 +348,19 @@ def test_sharded_metrics_single_rank_group():
         j_ref = metrics_oracle.pdf_jsd(u, v, 2000)
         assert abs(w - w_ref) <= 1e-10 * w_ref
         assert abs(j - j_ref) <= 2e-5 * j_ref
+        for m in ("binned", "sort"):
+            info = {}
+            assert abs(nd.wasserstein_1d_sharded(tu, tv, method=m, info=info) - w_ref) <= 1e-10 * w_ref
+            assert info["method"] == m
+        # crossing CDFs: some bins are ambiguous and their values go through the gather
+        rng = np.random.default_rng(9)
+        a = torch.from_numpy(rng.normal(0, 1, 90_000).astype(np.float32)).to(DEV)
+        b = torch.from_numpy(rng.normal(0.3, 2, 60_000).astype(np.float32)).to(DEV)
+        info = {}
+        w2 = nd.wasserstein_1d_sharded(a, b, info=info)
+        assert info["method"] == "binned" and 0 < info["exchanged_values"] < 40_000
+        ref2 = metrics_oracle.wasserstein_1d(a.cpu().numpy(), b.cpu().numpy())
+        assert abs(w2 - ref2) <= 1e-10 * ref2
     finally:
         if created:
             dist.destroy_process_group()

@@ -47,6 +47,10 @@ def main():
         u = shard(args.check_n, 2, 0.05, 1, rank, world, dev)
         v = shard(args.check_n * 3 // 4, 3, 0.08, 2, rank, world, dev)
         w = nd.wasserstein_1d_sharded(u, v)
+        w_sort = nd.wasserstein_1d_sharded(u, v, method="sort")
+        # a second ID-like sample: almost every bin is ambiguous, 'binned' must still be exact
+        v2 = shard(args.check_n * 3 // 4, 2, 0.05, 3, rank, world, dev)
+        w2 = {m: nd.wasserstein_1d_sharded(u, v2, method=m) for m in ("binned", "sort", "auto")}
         j = nd.kde_jsd_sharded(u, v, 2000)
         sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([u.numel(), v.numel()], device=dev))
@@ -62,9 +66,11 @@ def main():
             fv = np.concatenate([gv[r][:int(sizes[r][1])].cpu().numpy() for r in range(world)])
             w_ref = metrics_oracle.wasserstein_1d(fu, fv)
             j_ref = metrics_oracle.pdf_jsd(fu[:40000], fv[:30000], 2000) if False else None
-            ok = abs(w - w_ref) <= 1e-10 * w_ref
+            ok = abs(w - w_ref) <= 1e-10 * w_ref and abs(w_sort - w_ref) <= 1e-10 * w_ref
+            ok = ok and max(w2.values()) - min(w2.values()) <= 1e-10 * w2["sort"]
             print(json.dumps({"check": "wasserstein_1d_sharded", "world": world, "got": w,
-                              "oracle": w_ref, "ok": bool(ok)}), flush=True)
+                              "got_sort_method": w_sort, "oracle": w_ref,
+                              "same_distribution_by_method": w2, "ok": bool(ok)}), flush=True)
             from nnueehcs_b200 import ops
             j1 = ops.kde_jsd(torch.from_numpy(fu).to(dev), torch.from_numpy(fv).to(dev), 2000)
             print(json.dumps({"check": "kde_jsd_sharded", "world": world, "got": j,
@@ -74,7 +80,10 @@ def main():
 
     u = shard(args.values, 2, 0.05, 11, rank, world, dev)
     v = shard(args.values, 3, 0.08, 12, rank, world, dev)
-    for name, fn in (("wasserstein_1d_sharded", lambda: nd.wasserstein_1d_sharded(u, v)),
+    winfo = {}
+    for name, fn in (("wasserstein_1d_sharded", lambda: nd.wasserstein_1d_sharded(u, v, info=winfo)),
+                     ("wasserstein_1d_sharded[sort]",
+                      lambda: nd.wasserstein_1d_sharded(u, v, method="sort")),
                      ("kde_jsd_sharded", lambda: nd.kde_jsd_sharded(u, v, args.grid))):
         val = fn()
         dist.barrier()
@@ -92,6 +101,7 @@ def main():
             ms = float(t.item())
             print(json.dumps({"metric": name, "n_gpus": world, "values": 2 * args.values, "ms": ms,
                               "values_per_s": 2 * args.values / (ms * 1e-3), "result": val,
+                              "info": winfo if name == "wasserstein_1d_sharded" else None,
                               "algorithmic_GBps": 2 * args.values * 4 / (ms * 1e-3) / 1e9}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
