@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UQ_ABI_VERSION 1
+#define UQ_ABI_VERSION 2
 
 /* status codes */
 #define UQ_OK 0
@@ -38,6 +38,10 @@ extern "C" {
 #define UQ_MODE_ENSEMBLE 0   /* EnsembleModel.forward      nnueehcs/models.py:99-108  */
 #define UQ_MODE_MC_DROPOUT 1 /* MCDropoutModel.forward     nnueehcs/models.py:147-163 */
 #define UQ_MODE_DELTA_UQ 2   /* DeltaUQMLP.forward         nnueehcs/models.py:313-341 */
+#define UQ_MODE_PAGER 3      /* PAGERMLP._score_samples    nnueehcs/models.py:396-429: roles of
+                                sample and anchor swapped, P[n][k] = net(cat(a_k - x_n, x_n));
+                                out0 = mean_k P[n][k], out1 = max_k |P[n][k] - Y_k|, raised to
+                                score_floor[n] when given (torch.maximum at models.py:389-390) */
 
 /* arithmetic the MLP stack runs in */
 #define UQ_PREC_FP32 0 /* CUDA-core FFMA, fp32 accumulate: the 1e-5 parity mode            */
@@ -85,6 +89,9 @@ typedef struct uq_forward_args {
                            order) a block [total_members][n][width_l] of bytes (0/1), blocks
                            concatenated in layer order. */
   const float* anchors; /* Delta-UQ anchors [total_members][d_in] (d_in = net input / 2) */
+  const float* anchor_targets; /* PAGER: anchors_Y [total_members][d_out] (models.py:440-449) */
+  const float* score_floor;    /* PAGER: [n][d_out] or NULL -- the Delta-UQ std the conformal
+                                  score is maximised with */
 } uq_forward_args;
 
 /* -- library ------------------------------------------------------------------------------ */

@@ -10,8 +10,9 @@ import os
 
 from .build import LIB_PATH
 
+ABI_VERSION = 2
 UQ_OK, UQ_ERR_INVALID, UQ_ERR_CUDA, UQ_ERR_UNSUPPORTED, UQ_ERR_WORKSPACE = 0, 1, 2, 3, 4
-MODE_ENSEMBLE, MODE_MC_DROPOUT, MODE_DELTA_UQ = 0, 1, 2
+MODE_ENSEMBLE, MODE_MC_DROPOUT, MODE_DELTA_UQ, MODE_PAGER = 0, 1, 2, 3
 PREC_FP32, PREC_BF16 = 0, 1
 OUT_MEAN_STD, OUT_MOMENTS = 0, 1
 WASSERSTEIN_AUTO, WASSERSTEIN_SORT, WASSERSTEIN_BINNED = 0, 1, 2
@@ -63,6 +64,8 @@ class ForwardArgs(C.Structure):
         ("philox_offset", C.c_uint64),
         ("masks", C.c_void_p),
         ("anchors", C.c_void_p),
+        ("anchor_targets", C.c_void_p),
+        ("score_floor", C.c_void_p),
     ]
 
 
@@ -146,7 +149,7 @@ def load() -> C.CDLL:
                  "uq_forward_host", "uq_moments_merge", "uq_philox_keep_masks",
                  "uq_wasserstein_1d", "uq_kde_jsd"):
         getattr(lib, name).restype = C.c_int
-    if lib.uq_abi_version() != 1:
+    if lib.uq_abi_version() != ABI_VERSION:
         raise RuntimeError("nnueehcs_b200: ABI version mismatch between _lib.py and the library")
     _lib = lib
     return lib

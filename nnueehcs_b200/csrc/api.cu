@@ -181,7 +181,7 @@ static int check_args(const uq_model_t* m, const float* x, int64_t n, const uq_f
              "uq_forward: need n >= 1 and non-NULL x/out pointers (n = %lld)", (long long)n);
   UQ_REQUIRE(n < ((int64_t)1 << 31), UQ_ERR_INVALID, "uq_forward: n = %lld exceeds 2^31-1",
              (long long)n);
-  UQ_REQUIRE(a->mode >= UQ_MODE_ENSEMBLE && a->mode <= UQ_MODE_DELTA_UQ, UQ_ERR_INVALID,
+  UQ_REQUIRE(a->mode >= UQ_MODE_ENSEMBLE && a->mode <= UQ_MODE_PAGER, UQ_ERR_INVALID,
              "uq_forward: unknown mode %d", a->mode);
   UQ_REQUIRE(a->precision == UQ_PREC_FP32 || a->precision == UQ_PREC_BF16, UQ_ERR_INVALID,
              "uq_forward: unknown precision %d", a->precision);
@@ -202,10 +202,17 @@ static int check_args(const uq_model_t* m, const float* x, int64_t n, const uq_f
     UQ_REQUIRE(a->dropout_p >= 0.0 && a->dropout_p < 1.0, UQ_ERR_INVALID,
                "dropout_p must be in [0, 1), got %g", a->dropout_p);
   }
-  if (a->mode == UQ_MODE_DELTA_UQ) {
+  if (a->mode == UQ_MODE_DELTA_UQ || a->mode == UQ_MODE_PAGER) {
     UQ_REQUIRE(a->anchors != nullptr, UQ_ERR_INVALID, "Delta-UQ: anchors pointer is NULL");
     UQ_REQUIRE(m->d_in % 2 == 0, UQ_ERR_INVALID,
                "Delta-UQ: network input width %d is not 2 * d_in", m->d_in);
+  }
+  if (a->mode == UQ_MODE_PAGER) {
+    UQ_REQUIRE(a->anchor_targets != nullptr, UQ_ERR_INVALID,
+               "PAGER: anchor_targets (anchors_Y) pointer is NULL");
+    UQ_REQUIRE(a->output == UQ_OUT_MEAN_STD, UQ_ERR_INVALID,
+               "PAGER: the conformal score is a max over anchors, not a moment (output must be "
+               "UQ_OUT_MEAN_STD; K-shards combine with an element-wise max)");
   }
   return UQ_OK;
 }
@@ -240,7 +247,8 @@ int uq_forward_host(const uq_model_t* model, const float* x_host, int64_t n,
   UQ_REQUIRE(model && args && x_host && out0_host && out1_host && n >= 1, UQ_ERR_INVALID,
              "uq_forward_host: NULL argument or n < 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int d_x = (args->mode == UQ_MODE_DELTA_UQ) ? model->d_in / 2 : model->d_in;
+  const int d_x = (args->mode == UQ_MODE_DELTA_UQ || args->mode == UQ_MODE_PAGER)
+                      ? model->d_in / 2 : model->d_in;
   const size_t xb = sizeof(float) * (size_t)n * d_x;
   const size_t ob = sizeof(float) * (size_t)n * model->d_out;
   const size_t wsb = uq_forward_workspace_bytes(model, n, args);

@@ -70,6 +70,9 @@ struct TcPlan {
   // the columns that multiply x; the anchor enters as a per-anchor bias (see tc_forward)
   __nv_bfloat16* image_delta = nullptr;
   int k0_delta = 0;
+  // PAGER variant: W0 [a - x; x] + b0 = (W0b - W0a) x + (b0 + W0a a), so layer 0 holds the column
+  // differences and the anchor again enters as a per-anchor bias
+  __nv_bfloat16* image_pager = nullptr;
 };
 
 }  // namespace uq

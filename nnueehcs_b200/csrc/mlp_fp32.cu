@@ -193,8 +193,10 @@ linear_small_out_kernel(const float* __restrict__ A, int64_t a_member_stride, in
 
 // Delta-UQ input assembly: in[z][m] = cat(x[m] - a_k, a_k)   (oracle/uq_oracle.py restatement of
 // deltaUQ_MLP.create_anchored_batch; parity unpinned).
+// PAGER (swap = 1): the anchor is the input and the sample the anchor, in = cat(a_k - x[m], x[m])
+// (PAGERMLP._anchored_predictions, models.py:396-424).
 __global__ void delta_input_kernel(const float* __restrict__ x, const float* __restrict__ anchors,
-                                   float* __restrict__ out, int M, int d, int member0) {
+                                   float* __restrict__ out, int M, int d, int member0, int swap) {
   const int z = blockIdx.z;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * d) return;
@@ -202,8 +204,28 @@ __global__ void delta_input_kernel(const float* __restrict__ x, const float* __r
   const int c = (int)(i - m * d);
   const float a = anchors[(int64_t)(member0 + z) * d + c];
   float* o = out + ((int64_t)z * M + m) * (2 * d);
-  o[c] = x[i] - a;
-  o[d + c] = a;
+  o[c] = swap ? a - x[i] : x[i] - a;
+  o[d + c] = swap ? x[i] : a;
+}
+
+// PAGER: out0 = mean over anchors of the predictions, out1 = max_k |P[k] - Y_k| (float32 like the
+// reference's torch.abs / torch.max), raised to floor[i] when given (torch.maximum, :389-390).
+__global__ void finalize_pager_kernel(const float* __restrict__ slab, int64_t member_stride, int K,
+                                      int64_t len, int d_out, const float* __restrict__ targets,
+                                      const float* __restrict__ floor_, float* __restrict__ out0,
+                                      float* __restrict__ out1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  const int o = (int)(i % d_out);
+  double s = 0.0;
+  float mx = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float y = slab[(int64_t)k * member_stride + i];
+    s += (double)y;
+    mx = fmaxf(mx, fabsf(y - targets[(int64_t)k * d_out + o]));
+  }
+  out0[i] = (float)(s / (double)K);
+  out1[i] = floor_ ? fmaxf(mx, floor_[i]) : mx;
 }
 
 // (mean, std) or (mean, M2) over the member axis of slab[K][M*out]; float64 accumulation.
@@ -288,12 +310,13 @@ int fp32_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_
       int64_t in_stride = 0;
       int ld_in = m->d_in;
       int cur = 0;
-      if (a->mode == UQ_MODE_DELTA_UQ) {
+      if (a->mode == UQ_MODE_DELTA_UQ || a->mode == UQ_MODE_PAGER) {
         const int d = m->d_in / 2;
         in = x + s0 * d;
         const int64_t tot = (int64_t)M * d;
         dim3 grid((unsigned)((tot + 255) / 256), 1, G);
-        delta_input_kernel<<<grid, 256, 0, st>>>(in, a->anchors, act[0], M, d, gm0);
+        delta_input_kernel<<<grid, 256, 0, st>>>(in, a->anchors, act[0], M, d, gm0,
+                                                 a->mode == UQ_MODE_PAGER ? 1 : 0);
         UQ_LAUNCH_CHECK();
         in = act[0];
         in_stride = (int64_t)M * m->d_in;
@@ -367,6 +390,13 @@ int fp32_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_
     }
     {
       const int64_t len = (int64_t)M * m->d_out;
+      if (a->mode == UQ_MODE_PAGER) {
+        finalize_pager_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(
+            slab, len, K, len, m->d_out, a->anchor_targets + (size_t)a->member_begin * m->d_out,
+            a->score_floor ? a->score_floor + s0 * m->d_out : nullptr, out0 + s0 * m->d_out,
+            out1 + s0 * m->d_out);
+        UQ_LAUNCH_CHECK();
+      } else
       finalize_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(
           slab, len, K, len, out0 + s0 * m->d_out, out1 + s0 * m->d_out,
           a->output == UQ_OUT_MOMENTS ? 1 : 0);

@@ -153,19 +153,31 @@ static int split_factor(const TcPlan& t) { return split_factor_of(t.d_in); }
 
 // Delta-UQ: bias0[k][h] = b0'[h] + sum_i (W0'[h][dx + i] - W0'[h][i]) a_k[i]   (W0', b0' = layer 0
 // with eval-BatchNorm folded), so that  W0' [x - a_k; a_k] + b0' = W0'[:, :dx] x + bias0[k]
+// PAGER (pager = 1) swaps the roles:  W0' [a_k - x; a... x] = (W0'[:, dx:] - W0'[:, :dx]) x + bias0[k]
+// with bias0[k][h] = b0'[h] + sum_i W0'[h][i] a_k[i].
 __global__ void delta_bias_kernel(const float* __restrict__ w0, const float* __restrict__ alpha,
                                   const float* __restrict__ bias_folded,
                                   const float* __restrict__ anchors, int H, int dx, int n_anchors,
-                                  int anchor_begin, float* __restrict__ out) {
+                                  int anchor_begin, int pager, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_anchors * H) return;
   const int h = i % H, k = anchor_begin + i / H;
   const float sc = alpha ? alpha[h] : 1.0f;
   float acc = bias_folded[h];
-  for (int j = 0; j < dx; ++j)
-    acc = fmaf((w0[(int64_t)h * 2 * dx + dx + j] - w0[(int64_t)h * 2 * dx + j]) * sc,
-               anchors[(int64_t)k * dx + j], acc);
+  for (int j = 0; j < dx; ++j) {
+    const float wa = w0[(int64_t)h * 2 * dx + j], wb = w0[(int64_t)h * 2 * dx + dx + j];
+    acc = fmaf((pager ? wa : wb - wa) * sc, anchors[(int64_t)k * dx + j], acc);
+  }
   out[(int64_t)k * H + h] = acc;
+}
+
+// [H][dx] column differences W0[:, dx:] - W0[:, :dx] (the PAGER image's layer 0)
+__global__ void column_diff_kernel(const float* __restrict__ w0, int H, int dx,
+                                   float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * dx) return;
+  const int h = i / dx, j = i % dx;
+  out[i] = w0[(int64_t)h * 2 * dx + dx + j] - w0[(int64_t)h * 2 * dx + j];
 }
 
 int tc_pack(uq_model* m, cudaStream_t st) {
@@ -209,6 +221,22 @@ int tc_pack(uq_model* m, cudaStream_t st) {
         t.image_delta, l0.w, l0.has_bn ? l0.alpha : nullptr, 0, dx, l0.in, H, t.n_tile, NH, KC,
         t.k0_delta, split_factor_of(dx), stage_elems, 0);
     UQ_LAUNCH_CHECK();
+    // PAGER image: layer 0 = column differences, everything else shared with the Delta-UQ image
+    void *pp = nullptr, *diff = nullptr;
+    UQ_CUDA(cudaMalloc(&pp, member_elems * sizeof(__nv_bfloat16)));
+    m->allocations.push_back(pp);
+    UQ_CUDA(cudaMalloc(&diff, sizeof(float) * (size_t)H * dx));
+    m->allocations.push_back(diff);
+    t.image_pager = static_cast<__nv_bfloat16*>(pp);
+    UQ_CUDA(cudaMemcpyAsync(pp, pd, member_elems * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice,
+                            st));
+    UQ_CUDA(cudaMemsetAsync(pp, 0, (size_t)NH * t.stage_bytes, st));
+    column_diff_kernel<<<(H * dx + 255) / 256, 256, 0, st>>>(l0.w, H, dx, static_cast<float*>(diff));
+    UQ_LAUNCH_CHECK();
+    pack_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        t.image_pager, static_cast<const float*>(diff), l0.has_bn ? l0.alpha : nullptr, 0, dx, dx, H,
+        t.n_tile, NH, KC, t.k0_delta, split_factor_of(dx), stage_elems, 0);
+    UQ_LAUNCH_CHECK();
   }
   for (int l = 0; l < m->n_layers; ++l) {
     const Layer& ly = m->layers[l];
@@ -243,6 +271,7 @@ static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a)
   const int64_t units = (n + rows - 1) / rows;
   int splits = 1;
   if (a->output == UQ_OUT_MOMENTS) return 1;  // a K-shard hands raw moments to the caller
+  if (a->mode == UQ_MODE_PAGER) return 1;      // the max over anchors is not a moment merge
   // few sample tiles but many members/passes: also spread the member axis over the 74 SM pairs
   while (units * splits < 148 && a->member_count / (splits * 2) >= 4 && splits < 64) splits *= 2;
   return splits;
@@ -252,7 +281,7 @@ size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a
   const int splits = choose_splits(m, n, a);
   size_t b = 256;  // error flag
   if (splits > 1) b += 2 * (size_t)splits * (size_t)n * m->d_out * sizeof(float) + 512;
-  if (a->mode == UQ_MODE_DELTA_UQ)  // per-anchor layer-0 bias [total_members][H]
+  if (a->mode == UQ_MODE_DELTA_UQ || a->mode == UQ_MODE_PAGER)  // per-anchor layer-0 bias [K][H]
     b += (((size_t)a->total_members * m->tc.hidden * sizeof(float)) + 255) & ~(size_t)255;
   return b;
 }
@@ -268,7 +297,9 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.x = x;
   p.n = n;
   p.d_in = m->d_in;
-  p.d_x = (a->mode == UQ_MODE_DELTA_UQ) ? m->d_in / 2 : m->d_in;
+  const bool anchored = a->mode == UQ_MODE_DELTA_UQ || a->mode == UQ_MODE_PAGER;
+  const bool pager = a->mode == UQ_MODE_PAGER;
+  p.d_x = anchored ? m->d_in / 2 : m->d_in;
   p.mode = a->mode;
   p.n_tiles = (int)((n + TILE_M - 1) / TILE_M);
   p.splits = choose_splits(m, n, a);
@@ -310,7 +341,8 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
     p.part_m2 = reinterpret_cast<float*>(wsb + 256 + part);
   }
   UQ_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(unsigned int), st));
-  if (a->mode == UQ_MODE_DELTA_UQ) {
+  if (pager) p.targets = a->anchor_targets, p.score_floor = a->score_floor;
+  if (anchored) {
     // anchors -> per-anchor layer-0 bias; the kernels then see plain x (d_in / 2 inputs), shared
     // weights and no per-member input rebuild
     UQ_REQUIRE(t.image_delta != nullptr, UQ_ERR_UNSUPPORTED,
@@ -324,11 +356,11 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
     const int total = a->member_count * t.hidden;
     delta_bias_kernel<<<(total + 255) / 256, 256, 0, st>>>(
         l0.w, l0.has_bn ? l0.alpha : nullptr, l0.bias_folded, a->anchors, t.hidden, dx,
-        a->member_count, a->member_begin, bias0);
+        a->member_count, a->member_begin, pager ? 1 : 0, bias0);
     UQ_LAUNCH_CHECK();
     p.bias[0] = bias0;
     p.bias0_per_member = 1;
-    p.image = reinterpret_cast<const uint8_t*>(t.image_delta);
+    p.image = reinterpret_cast<const uint8_t*>(pager ? t.image_pager : t.image_delta);
     p.d_in = dx;
     p.K0 = t.k0_delta;
     p.split_s = split_factor_of(dx);

@@ -460,9 +460,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
               y += ld_shared_f32(xb + (uint32_t)(((j * ROWS + row) * DOUT + o) * 4));
             y += __ldg(bl + o);
             if (p.last_relu) y = fmaxf(y, 0.f);
-            const float dlt = y - wf_mean[o];
-            wf_mean[o] += dlt * inv_n;
-            wf_m2[o] = fmaf(dlt, y - wf_mean[o], wf_m2[o]);
+            member_fold(p, kg, o, y, inv_n, wf_mean[o], wf_m2[o]);
           }
         }
       }
@@ -477,8 +475,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
               p.part_m2[(size_t)split * (size_t)p.n * p.d_out + idx] = wf_m2[o];
             } else {
               p.out0[idx] = wf_mean[o];
-              p.out1[idx] =
-                  (p.output == UQ_OUT_MOMENTS) ? wf_m2[o] : sqrtf(wf_m2[o] / (wf_n - 1.f));
+              p.out1[idx] = second_output(p, wf_m2[o], wf_n, idx);
             }
           }
         }

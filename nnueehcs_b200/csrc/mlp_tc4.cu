@@ -435,9 +435,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           for (int j = 0; j < OWN; ++j) {
             float y = dot[j] + bl;
             if (p.last_relu) y = fmaxf(y, 0.f);
-            const float dlt = y - wf_mean[j];
-            wf_mean[j] += dlt * inv_n;
-            wf_m2[j] = fmaf(dlt, y - wf_mean[j], wf_m2[j]);
+            member_fold(p, kg, 0, y, inv_n, wf_mean[j], wf_m2[j]);
           }
         }
       }
@@ -451,7 +449,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
             p.part_m2[(size_t)split * (size_t)p.n + grow] = wf_m2[j];
           } else {
             p.out0[grow] = wf_mean[j];
-            p.out1[grow] = (p.output == UQ_OUT_MOMENTS) ? wf_m2[j] : sqrtf(wf_m2[j] / (wf_n - 1.f));
+            p.out1[grow] = second_output(p, wf_m2[j], wf_n, grow);
           }
         }
       }

@@ -164,6 +164,22 @@ __device__ __forceinline__ void epi_block2(const uint32_t (&acc)[NC], const floa
   if (!LAST) epi_store<NC / 2>(packed, a_dst, piece0, rx);
 }
 
+// One member's output y of one row folded into the row's running state over the member axis:
+// Welford (mean, M2), or -- PAGER -- (mean, max |y - Y_k|) in the same two registers.
+__device__ __forceinline__ void member_fold(const TcParams& p, int kg, int o, float y, float inv_n,
+                                            float& mean, float& m2) {
+  const float dlt = y - mean;
+  mean += dlt * inv_n;
+  if (p.targets) m2 = fmaxf(m2, fabsf(y - __ldg(p.targets + (size_t)kg * p.d_out + o)));
+  else m2 = fmaf(dlt, y - mean, m2);
+}
+
+// what goes to out1 for one output element
+__device__ __forceinline__ float second_output(const TcParams& p, float m2, float n, int64_t idx) {
+  if (p.targets) return p.score_floor ? fmaxf(m2, __ldg(p.score_floor + idx)) : m2;
+  return (p.output == UQ_OUT_MOMENTS) ? m2 : sqrtf(m2 / (n - 1.f));
+}
+
 template <int THREADS>
 __device__ __forceinline__ void epi_bar_sync_n() {
   asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");

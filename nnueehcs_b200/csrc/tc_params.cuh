@@ -38,6 +38,8 @@ struct TcParams {
   PhiloxKey key;
   const uint8_t* masks;               // injected base
   const float* anchors;               // [total_members][d_x]
+  const float* targets;               // PAGER: [total_members][d_out]; the second moment slot then
+  const float* score_floor;           //   holds max_k |y_k - target_k| (>= score_floor[n] at the end)
   float* out0;
   float* out1;
   int output;                         // UQ_OUT_*

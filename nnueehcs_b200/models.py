@@ -305,11 +305,84 @@ def _out_of_scope(name):
         def __init__(self, *a, **k):
             raise NotImplementedError(
                 f"{name} is outside the hot path this package accelerates (SURVEY.md section 8: "
-                "KDE / KNN-KDE / PAGER wrappers are 'next' rows); use the reference class")
+                "KDE / KNN-KDE wrappers are 'next' rows); use the reference class")
     _Unsupported.__name__ = name
     return _Unsupported
 
 
 KDEMLPModel = _out_of_scope("KDEMLPModel")
 KNNKDEMLPModel = _out_of_scope("KNNKDEMLPModel")
-PAGERMLP = _out_of_scope("PAGERMLP")
+
+
+class PAGERMLP(DeltaUQMLP):
+    """Delta-UQ + anchor-consistency (conformal) score, reference models.py:376-468.
+
+    ``forward(x, return_ue=True)`` returns ``(mu, max(std, score))`` where ``mu, std`` are the
+    Delta-UQ mean/std over the anchors and ``score[n] = max_k |net(cat(a_k - x_n, x_n)) - Y_k|``
+    (``_score_samples`` / ``_anchored_predictions``, :396-429: the roles of sample and anchor are
+    swapped).  Both are one fused launch each; the second one takes the first one's ``std`` as a
+    floor, so the ``[N, K]`` prediction matrix and the ``torch.maximum`` never materialise.
+    PARITY-UNPINNED like ``DeltaUQMLP`` (the anchoring lives in the absent ``deltauq`` package).
+    The conformal pass runs every anchor on every rank (K is small); only the Delta-UQ pass
+    follows ``uq_shard``."""
+
+    def __init__(self, base_model, estimator='std', anchored_batch_size=None, num_anchors=5,
+                 vectorize=False, **kwargs):
+        super().__init__(base_model, estimator=estimator, num_anchors=num_anchors,
+                         anchored_batch_size=anchored_batch_size, **kwargs)
+        self.vectorize = vectorize   # loop and vectorised branches of :398-424 compute the same
+        self.register_buffer('_anchors_Y', None)
+
+    def forward(self, x, return_ue=False):
+        res = super().forward(x, return_ue)
+        if not return_ue or self.training or self._anchors is None:
+            return res
+        if self._anchors_Y is None:
+            raise ValueError("PAGER anchors_Y not set yet")
+        mu, std = res
+        packed = self._packed([self.net], x.device)
+        _, score = packed.forward(x, "pager", total_members=int(self.num_anchors),
+                                  precision=self.uq_precision, anchors=self._anchors.to(x.device),
+                                  targets=self._anchors_Y.to(x.device), score_floor=std)
+        return mu, score.to(std.dtype)
+
+    def _score_samples(self, x, anchors_X, anchors_Y):
+        """Conformal score alone (reference :426-429), shape ``[N, 1]``."""
+        ops._require_cuda(x, "x")
+        packed = self._packed([self.net], x.device)
+        k = anchors_X.shape[0]
+        _, score = packed.forward(x, "pager", total_members=int(k), precision=self.uq_precision,
+                                  anchors=anchors_X.to(x.device), targets=anchors_Y.to(x.device))
+        return score
+
+    @property
+    def anchors_Y(self):
+        return self._anchors_Y
+
+    @anchors_Y.setter
+    def anchors_Y(self, value):
+        self._anchors_Y = value.detach().clone()
+
+    class PAGERGetAnchorsCallback(_Callback):
+        """Inputs AND targets of the first ``num_anchors`` training rows (reference :451-468)."""
+
+        def __init__(self):
+            super().__init__()
+            self._anchor_X, self._anchor_Y = [], []
+            self._epochs = 0
+
+        def on_validation_epoch_start(self, trainer, pl_module):
+            if self._epochs == 0 and len(self._anchor_X) > 0:
+                k = pl_module.num_anchors
+                pl_module.anchors = torch.cat(self._anchor_X)[0:k].detach().clone()
+                pl_module.anchors_Y = torch.cat(self._anchor_Y)[0:k].detach().clone()
+            self._epochs += 1
+
+        def on_train_batch_end(self, trainer, pl_module, outputs, batch, batch_idx):
+            bs = batch[0].shape[0]
+            if self._epochs == 0 and bs * len(self._anchor_X) < pl_module.num_anchors:
+                self._anchor_X.append(batch[0].detach())
+                self._anchor_Y.append(batch[1].detach())
+
+    def get_callbacks(self):
+        return [PAGERMLP.PAGERGetAnchorsCallback()]

@@ -17,7 +17,7 @@ from .extract import (Block, _f32_cuda, dropout_widths, split_blocks, structure_
 _PREC = {"fp32": _lib.PREC_FP32, "float32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16,
          "bfloat16": _lib.PREC_BF16}
 _MODE = {"ensemble": _lib.MODE_ENSEMBLE, "mc_dropout": _lib.MODE_MC_DROPOUT,
-         "delta_uq": _lib.MODE_DELTA_UQ}
+         "delta_uq": _lib.MODE_DELTA_UQ, "pager": _lib.MODE_PAGER}
 
 
 def _stream_ptr(device) -> int:
@@ -131,10 +131,13 @@ class PackedModel:
                 dropout_p: float = 0.0, dropout_active: bool = True, seed: int = 0,
                 offset: int = 0, masks: Optional[torch.Tensor] = None,
                 anchors: Optional[torch.Tensor] = None,
-                output: str = "mean_std") -> Tuple[torch.Tensor, torch.Tensor]:
-        """(mean, std) -- or (mean, M2) with ``output='moments'`` -- of shape ``[n, d_out]``."""
+                output: str = "mean_std", targets: Optional[torch.Tensor] = None,
+                score_floor: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(mean, std) -- or (mean, M2) with ``output='moments'`` -- of shape ``[n, d_out]``.
+        ``mode='pager'``: (mean over anchors of the swapped-role predictions, conformal score
+        ``max_k |P[n, k] - targets[k]|`` raised to ``score_floor`` when given)."""
         _require_cuda(x, "x")
-        d_x = self.d_in // 2 if mode == "delta_uq" else self.d_in
+        d_x = self.d_in // 2 if mode in ("delta_uq", "pager") else self.d_in
         if x.dim() != 2 or x.shape[1] != d_x:
             raise ValueError(f"x must be [n, {d_x}], got {tuple(x.shape)}")
         if x.shape[0] == 0:
@@ -154,6 +157,20 @@ class PackedModel:
             anchors = anchors.detach().to(torch.float32).contiguous()
             if anchors.dim() != 2 or anchors.shape[1] != d_x or anchors.shape[0] < total_members:
                 raise ValueError(f"anchors must be [>= {total_members}, {d_x}]")
+        if mode == "pager":
+            if targets is None:
+                raise ValueError("PAGER needs the anchors' targets (anchors_Y)")
+            _require_cuda(targets, "targets")
+            targets = targets.detach().to(torch.float32).reshape(-1, self.d_out).contiguous()
+            if targets.shape[0] < total_members:
+                raise ValueError(f"targets must be [>= {total_members}, {self.d_out}]")
+            if score_floor is not None:
+                _require_cuda(score_floor, "score_floor")
+                score_floor = score_floor.detach().to(torch.float32).contiguous()
+                if tuple(score_floor.shape) != (x.shape[0], self.d_out):
+                    raise ValueError(f"score_floor must be [{x.shape[0]}, {self.d_out}]")
+        elif targets is not None or score_floor is not None:
+            raise ValueError("targets / score_floor only apply to mode='pager'")
         if precision not in _PREC:
             raise ValueError(f"unknown precision {precision!r} (use 'fp32' or 'bf16')")
         count = int(total_members - member_begin if member_count is None else member_count)
@@ -162,7 +179,7 @@ class PackedModel:
             int(self._handle.value), xf, _MODE[mode], _PREC[precision],
             _lib.OUT_MOMENTS if output == "moments" else _lib.OUT_MEAN_STD, int(member_begin),
             count, int(total_members), bool(dropout_active), float(dropout_p),
-            _as_i64(seed), _as_i64(offset), masks, anchors, int(self.d_out))
+            _as_i64(seed), _as_i64(offset), masks, anchors, int(self.d_out), targets, score_floor)
 
     def forward_host(self, x_host: torch.Tensor, out0_host: torch.Tensor, out1_host: torch.Tensor,
                      mode: str, *, total_members: int, precision: str = "fp32",
@@ -467,7 +484,9 @@ def _as_i64(v: int) -> int:
 def _op_uq_forward(handle: int, x: torch.Tensor, mode: int, precision: int, output: int,
                    member_begin: int, member_count: int, total_members: int,
                    dropout_active: bool, dropout_p: float, seed: int, offset: int,
-                   masks: Optional[torch.Tensor], anchors: Optional[torch.Tensor], d_out: int
+                   masks: Optional[torch.Tensor], anchors: Optional[torch.Tensor], d_out: int,
+                   targets: Optional[torch.Tensor] = None,
+                   score_floor: Optional[torch.Tensor] = None
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     a = _lib.ForwardArgs()
@@ -479,6 +498,8 @@ def _op_uq_forward(handle: int, x: torch.Tensor, mode: int, precision: int, outp
     a.philox_offset = offset & 0xFFFFFFFFFFFFFFFF
     a.masks = masks.data_ptr() if masks is not None else None
     a.anchors = anchors.data_ptr() if anchors is not None else None
+    a.anchor_targets = targets.data_ptr() if targets is not None else None
+    a.score_floor = score_floor.data_ptr() if score_floor is not None else None
     n, dev = x.shape[0], x.device
     h = C.c_void_p(handle)
     with torch.cuda.device(dev):
@@ -533,7 +554,8 @@ OP_NAMESPACE = "nnueehcs_b200"
 OP_SCHEMAS = {
     "uq_forward": "(int handle, Tensor x, int mode, int precision, int output, int member_begin, "
                   "int member_count, int total_members, bool dropout_active, float dropout_p, "
-                  "int seed, int offset, Tensor? masks, Tensor? anchors, int d_out) "
+                  "int seed, int offset, Tensor? masks, Tensor? anchors, int d_out, "
+                  "Tensor? targets=None, Tensor? score_floor=None) "
                   "-> (Tensor, Tensor)",
     "moments_merge": "(Tensor means, Tensor m2s, float[] counts) -> (Tensor, Tensor)",
     "wasserstein_1d": "(Tensor u, Tensor v, int method=0) -> float",

@@ -262,6 +262,104 @@ def test_delta_uq_wrapper():
     assert_close_ref(std, g["std"], 2e-5, scale_ref=g["mean"], what="delta wrapper std")
 
 
+# ---- PAGER (anchoring parity-unpinned like Delta-UQ) -----------------------------------
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pager_matches_reference_class_golden(precision):
+    """uq_forward(mode=UQ_MODE_PAGER) against the outputs of the reference's own PAGERMLP
+    (tests/golden/make_golden_pager.py) and the oracle restatement."""
+    g = load_golden("pager_small.npz")
+    k = int(g["k"])
+    net = nets_from_golden(g, 1, arch=delta_arch(golden_arch(g)))[0]
+    packed = ops.PackedModel([net], DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    anchors = torch.from_numpy(g["anchors"]).to(DEV)
+    ys = torch.from_numpy(g["anchors_y"]).to(DEV)
+    mu, std = packed.forward(x, "delta_uq", total_members=k, precision=precision, anchors=anchors)
+    pmean, conformal = packed.forward(x, "pager", total_members=k, precision=precision,
+                                      anchors=anchors, targets=ys)
+    _, score = packed.forward(x, "pager", total_members=k, precision=precision, anchors=anchors,
+                              targets=ys, score_floor=std)
+    assert torch.equal(score, torch.maximum(conformal, std))   # the fused floor IS torch.maximum
+    ref_pred, ref_score, ref_conf = uq_oracle.pager_forward(
+        net, torch.from_numpy(g["x"]), torch.from_numpy(g["anchors"]),
+        torch.from_numpy(g["anchors_y"]), k)
+    if precision == "fp32":
+        assert_close_ref(mu, g["pred"], 2e-5, what="pager pred")
+        assert_close_ref(conformal, g["conformal"], RTOL32, scale_ref=g["pred"], what="conformal")
+        assert_close_ref(score, g["score"], 2e-5, scale_ref=g["pred"], what="pager score")
+        assert_close_ref(conformal, ref_conf, RTOL32, scale_ref=ref_pred, what="conformal/oracle")
+    else:
+        scale = float(np.abs(g["pred"]).max())
+        e_c = float((conformal.cpu() - ref_conf).abs().max())
+        e_s = float((score.cpu() - ref_score).abs().max())
+        print(f"[bf16 pager] max|conformal err| = {e_c:.3e}, max|score err| = {e_s:.3e}, "
+              f"scale {scale:.3e}")
+        assert e_c <= 3e-2 * scale and e_s <= 6e-2 * scale
+    # the by-product mean is the mean over anchors of the swapped-role predictions
+    with torch.no_grad():
+        cols = [uq_oracle.sequential_forward(
+            net, torch.cat([torch.from_numpy(g["anchors"])[j:j + 1] - torch.from_numpy(g["x"]),
+                            torch.from_numpy(g["x"])], dim=1)) for j in range(k)]
+    ref_pmean = torch.stack(cols).mean(0)
+    tol = RTOL32 if precision == "fp32" else 3e-2
+    assert float((pmean.cpu() - ref_pmean).abs().max()) <= tol * float(ref_pmean.abs().max()) + 1e-7
+
+
+def test_pager_wrapper_drop_in_and_errors():
+    from nnueehcs_b200.model_builder import PAGERModelBuilder
+    g = load_golden("pager_small.npz")
+    k = int(g["k"])
+    model = PAGERModelBuilder(golden_arch(g), {"estimator": "std", "num_anchors": k}).build()
+    ref_net = nets_from_golden(g, 1, arch=delta_arch(golden_arch(g)))[0]
+    model.net.load_state_dict(ref_net.state_dict())
+    model.anchors = torch.from_numpy(g["anchors"])
+    model.to(DEV)
+    model.eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with torch.no_grad():
+        with pytest.raises(ValueError, match="anchors_Y not set"):
+            model(x, return_ue=True)
+        model.anchors_Y = torch.from_numpy(g["anchors_y"]).to(DEV)
+        pred, score = model(x, return_ue=True)
+        only = model(x)
+        conf = model._score_samples(x, model.anchors, model.anchors_Y)
+    assert_close_ref(pred, g["pred"], 2e-5, what="pager wrapper pred")
+    assert_close_ref(only, g["pred_only"], 2e-5, what="pager wrapper pred (no ue)")
+    assert_close_ref(score, g["score"], 2e-5, scale_ref=g["pred"], what="pager wrapper score")
+    assert_close_ref(conf, g["conformal"], 2e-5, scale_ref=g["pred"], what="pager wrapper conformal")
+    packed = model._packed([model.net], x.device)
+    with pytest.raises(ValueError, match="anchors_Y"):
+        packed.forward(x, "pager", total_members=k, anchors=model.anchors)
+    with pytest.raises(ValueError, match="only apply to mode='pager'"):
+        packed.forward(x, "delta_uq", total_members=k, anchors=model.anchors,
+                       targets=model.anchors_Y)
+    with pytest.raises(ValueError, match="max over anchors"):
+        packed.forward(x, "pager", total_members=k, anchors=model.anchors,
+                       targets=model.anchors_Y, output="moments")
+
+
+def test_pager_narrow_and_wide_kernels_bf16():
+    """The same fold runs in all three fused kernels: 6x128 (four-slot kernel), 3x256 (pair
+    kernel), 2x768 (wide kernel); ragged N, K = 7 anchors."""
+    for width, depth, n in ((128, 6, 1000), (256, 3, 700), (768, 2, 300)):
+        torch.manual_seed(width)
+        net = build_network(delta_arch(_wide_arch(5, width, depth, 1))).eval()
+        x, anchors, ys = torch.rand(n, 5), torch.rand(7, 5), torch.rand(7, 1) * 0.2
+        packed = ops.PackedModel([net], DEV)
+        assert packed.supports_bf16
+        _, conf = packed.forward(x.to(DEV), "pager", total_members=7, precision="bf16",
+                                 anchors=anchors.to(DEV), targets=ys.to(DEV))
+        _, conf32 = packed.forward(x.to(DEV), "pager", total_members=7, precision="fp32",
+                                   anchors=anchors.to(DEV), targets=ys.to(DEV))
+        ref_pred, _, ref_conf = uq_oracle.pager_forward(net, x, anchors, ys, 7)
+        scale = float(ref_pred.abs().max()) + float(ys.abs().max())
+        assert_close_ref(conf32, ref_conf, RTOL32, scale_ref=ref_pred, what=f"pager fp32 {width}")
+        err = float((conf.cpu() - ref_conf).abs().max())
+        print(f"[bf16 pager {depth}x{width}] max|conformal err| = {err:.3e} of scale {scale:.3e}")
+        assert err <= 3e-2 * scale
+
+
 # ---- K-axis shards, tails, errors ---------------------------------------------------------------------
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

@@ -159,6 +159,34 @@ def test_delta_uq_builder_doubles_inputs(descr):
     assert model.anchors.shape == (5, 16) and "_anchors" in dict(model.named_buffers())
 
 
+def test_pager_builder_and_wrapper_contract(descr):
+    """reference tests/test_model_builder.py:215-237 (input doubling, num_anchors) + the wrapper's
+    buffers, callbacks and loud failure off the GPU."""
+    from nnueehcs_b200.model_builder import PAGERModelBuilder
+    from nnueehcs_b200.models import PAGERMLP
+    b = PAGERModelBuilder(descr["architecture_mlp"], {"estimator": "std", "num_anchors": 4})
+    model = b.build()
+    assert isinstance(model, PAGERMLP) and isinstance(model, DeltaUQMLP)
+    assert model.net[0].in_features == 32 and model.num_anchors == 4
+    assert b.get_info().num_inputs() == 32 and b.get_info().get_estimator() == "std"
+    model.anchors = torch.randn(4, 16)
+    model.anchors_Y = torch.randn(4, 5)
+    bufs = dict(model.named_buffers())
+    assert "_anchors" in bufs and "_anchors_Y" in bufs
+    cb = model.get_callbacks()[0]
+    for i in range(3):
+        cb.on_train_batch_end(None, model, None, (torch.full((2, 16), float(i)),
+                                                  torch.full((2, 5), float(10 + i))), i)
+    cb.on_validation_epoch_start(None, model)
+    assert model.anchors.shape == (4, 16) and model.anchors_Y.shape == (4, 5)
+    assert float(model.anchors_Y[2, 0]) == 11.0          # rows 2-3 come from the second batch
+    model.train()
+    assert model(torch.randn(6, 16)).shape == (6, 5)      # training forward: stock torch
+    model.eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.randn(6, 16), return_ue=True)
+
+
 def test_out_of_scope_wrappers_say_so(descr):
     with pytest.raises(NotImplementedError, match="outside the hot path"):
         KDEModelBuilder(descr["architecture_mlp"], {"bandwidth": "scott"}).build()
@@ -280,7 +308,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     raw = ctypes.CDLL(path)
     for name in declared:
         assert hasattr(raw, name), f"{name} not exported"
-    assert lib.uq_abi_version() == 1
+    assert lib.uq_abi_version() == _lib.ABI_VERSION == 2
     lib.uq_launch_count_reset()
     assert lib.uq_launch_count() == 0
 
@@ -289,9 +317,10 @@ def test_abi_struct_layouts_match_header():
     # uq_layer_desc: 2 x int32, 6 pointers, float, 2 x int32 -> 72 bytes on LP64
     assert ctypes.sizeof(_lib.LayerDesc) == 72
     assert _lib.LayerDesc.weight.offset == 8 and _lib.LayerDesc.bn_eps.offset == 56
-    # uq_forward_args: 8 x int32, double, 2 x uint64, 2 pointers -> 72 bytes
-    assert ctypes.sizeof(_lib.ForwardArgs) == 72
+    # uq_forward_args (ABI 2): 8 x int32, double, 2 x uint64, 4 pointers -> 88 bytes
+    assert ctypes.sizeof(_lib.ForwardArgs) == 88
     assert _lib.ForwardArgs.dropout_p.offset == 32 and _lib.ForwardArgs.masks.offset == 56
+    assert _lib.ForwardArgs.anchor_targets.offset == 72 and _lib.ForwardArgs.score_floor.offset == 80
 
 
 def test_argument_errors_surface_as_python_exceptions_without_a_gpu():
