@@ -40,6 +40,7 @@ WORKLOADS = {
     # configs[3] of BASELINE.json (MC dropout, 1000 passes x 8-layer width-1024 MLP) on a
     # 64 k-sample slice of its 16 M samples, and the same net without dropout
     "mcdropout_1000x1024_64k": ("mc_dropout", 5, [1024] * 7, 1, 1000, 1 << 16, 0.2),
+    "mcdropout_1000x1024_1M": ("mc_dropout", 5, [1024] * 7, 1, 1000, 1 << 20, 0.2),
     "ensemble8x1024_256k": ("ensemble", 5, [1024] * 7, 1, 8, 1 << 18, 0.0),
     # the binomial-options surrogate as a 32-member ensemble (same flops as deltauq32_binomial_4M)
     "ensemble32x128_4M": ("ensemble", 5, [128] * 6, 1, 32, 1 << 22, 0.0),
@@ -276,7 +277,19 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator comes up; stdout
+        # carries exactly one JSON line, so the banner goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     wl = args.workload
     mode, d_in, widths, d_out, k, n, p = WORKLOADS[wl]
@@ -386,7 +399,8 @@ def run_gpu(args):
         timed_s = total_ms * 1e-3
         peak_kind = "sustained" if timed_s >= 2.0 else "burst"
         peak = peaks[peak_kind]
-        achieved = F * n * k / (kernel_ms * 1e-3) / 1e12
+        # per-GPU rate: an ensemble rank runs its own k members, a K-sharded job k / world of them
+        achieved = F * n * (k if mode == "ensemble" else k / world) / (kernel_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
@@ -395,7 +409,8 @@ def run_gpu(args):
         line = {
             "metric": "uq_sample_passes_per_sec", "value": value, "unit": "sample*members/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True,
+            "scaling": "weak" if mode == "ensemble" else "strong", "vs_baseline": None,
             "dtype": precision if precision == "bf16" else "f32", "data": "synthetic",
             "config": config_dict(wl, world),
             "e2e": {"value": e2e_value, "unit": "sample*members/s",

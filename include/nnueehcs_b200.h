@@ -237,6 +237,18 @@ int uq_wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t 
                             void* stream);
 
 
+/*    uq_kde_density replaces the input-density score of KDEMLPModel.forward
+      (nnueehcs/models.py:209-222): -exp(KernelDensity(bandwidth, kernel='gaussian')
+      .fit(fit).score_samples(x)) -- the negated d-dimensional Gaussian KDE of the `m` fitted rows
+      at each of the `n` query rows.  fit: [m][d], x: [n][d] float32 row-major on device;
+      bandwidth: sklearn's bandwidth_ (for 'scott': m^(-1/(d+4)), uq_kde_scott_bandwidth);
+      out: [n] float64 on device (the reference returns a float64 tensor).  Asynchronous. */
+double uq_kde_scott_bandwidth(int64_t m, int32_t d);
+size_t uq_kde_density_workspace_bytes(int64_t n, int64_t m);
+int uq_kde_density(const float* fit, int64_t m, const float* x, int64_t n, int32_t d,
+                   double bandwidth, double* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 /*    Per-rank steps of the sharded BINNED Wasserstein (no counterpart in the reference).
       uq_bin_moments ADDS one shard to the caller-zeroed tables cnt / ksum (uint64 [uq_key_bins()]
       each, device): values per key bin and the sum of their low 18 key bits.  The four tables

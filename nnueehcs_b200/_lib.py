@@ -29,6 +29,7 @@ EXPORTS = (
     "uq_kde_grid_accumulate", "uq_jsd_from_grids", "uq_key_bins", "uq_key_histogram",
     "uq_partition_by_bin", "uq_wasserstein_1d_range",
     "uq_score_metrics_workspace_bytes", "uq_score_metrics",
+    "uq_kde_scott_bandwidth", "uq_kde_density_workspace_bytes", "uq_kde_density",
     "uq_bin_moments", "uq_wasserstein_from_bins", "uq_compact_flagged", "uq_wasserstein_ambiguous",
 )
 
@@ -129,6 +130,12 @@ def load() -> C.CDLL:
     lib.uq_partition_by_bin.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     lib.uq_wasserstein_1d_range.argtypes = [vp, i64, vp, i64, i64, i64, i64, i64, C.POINTER(dbl),
                                             vp, sz, vp]
+    lib.uq_kde_scott_bandwidth.argtypes = [i64, i32]
+    lib.uq_kde_scott_bandwidth.restype = dbl
+    lib.uq_kde_density_workspace_bytes.argtypes = [i64, i64]
+    lib.uq_kde_density_workspace_bytes.restype = sz
+    lib.uq_kde_density.argtypes = [vp, i64, vp, i64, i32, dbl, vp, vp, sz, vp]
+    lib.uq_kde_density.restype = C.c_int
     lib.uq_bin_moments.argtypes = [vp, i64, vp, vp, vp]
     lib.uq_wasserstein_from_bins.argtypes = [vp, i64, i64, vp, C.POINTER(dbl), vp, sz, vp]
     lib.uq_compact_flagged.argtypes = [vp, i64, vp, vp, C.POINTER(i64), vp, sz, vp]

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <math.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -385,6 +387,26 @@ int uq_wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t 
              UQ_ERR_INVALID, "uq_wasserstein_1d_range: inconsistent counts");
   return wasserstein_1d_range(u, nu, v, nv, u_below, v_below, nu_total, nv_total, out_host,
                               workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+double uq_kde_scott_bandwidth(int64_t m, int32_t d) {
+  // sklearn.neighbors.KernelDensity.fit: bandwidth_ = n_samples ** (-1 / (n_features + 4))
+  return (m < 1 || d < 1) ? 0.0 : pow((double)m, -1.0 / ((double)d + 4.0));
+}
+
+size_t uq_kde_density_workspace_bytes(int64_t n, int64_t m) {
+  return kde_density_workspace_bytes(n, m);
+}
+
+int uq_kde_density(const float* fit, int64_t m, const float* x, int64_t n, int32_t d,
+                   double bandwidth, double* out, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  UQ_REQUIRE(fit && x && out && m >= 1 && n >= 1, UQ_ERR_INVALID,
+             "uq_kde_density: NULL argument, no fitted rows or no query rows");
+  UQ_REQUIRE(n < ((int64_t)1 << 31) && m < ((int64_t)1 << 31), UQ_ERR_INVALID,
+             "uq_kde_density: too many rows");
+  return kde_density(fit, m, x, n, d, bandwidth, out, workspace, workspace_bytes,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int uq_bin_moments(const float* x, int64_t n, uint64_t* cnt, uint64_t* ksum, void* stream) {

@@ -305,12 +305,73 @@ def _out_of_scope(name):
         def __init__(self, *a, **k):
             raise NotImplementedError(
                 f"{name} is outside the hot path this package accelerates (SURVEY.md section 8: "
-                "KDE / KNN-KDE wrappers are 'next' rows); use the reference class")
+                "KNN-KDE needs the absent third-party `kde` package); use the reference class")
     _Unsupported.__name__ = name
     return _Unsupported
 
 
-KDEMLPModel = _out_of_scope("KDEMLPModel")
+
+
+class KDEMLPModel(MLPModel):
+    """MLP + input-density uncertainty score, reference models.py:191-240.
+
+    ``fit_kde(data)`` keeps a random ``train_fit_prop`` share of the training inputs (on their
+    device) and sklearn's 'scott' bandwidth ``m ** (-1 / (d + 4))``; ``forward(x, return_ue=True)``
+    returns ``(pred, dens)`` with ``dens = -exp(KernelDensity.score_samples(x))`` as a float64
+    ``[N]`` tensor, computed by ``uq_kde_density`` on the GPU (the reference copies ``x`` to the
+    host and walks a KD-tree per call).  ``rtol`` is kept for API parity: sklearn stops refining
+    at ``rtol / 10000`` relative, the kernel adds every term."""
+
+    def __init__(self, base_model, bandwidth='scott', rtol=0.1, train_fit_prop=1.0, **kwargs):
+        super().__init__(base_model, **kwargs)
+        if bandwidth != 'scott' and not isinstance(bandwidth, (int, float)):
+            raise ValueError(f"bandwidth must be 'scott' or a number, got {bandwidth!r} "
+                             "('silverman' is not built)")
+        self.bandwidth = bandwidth
+        self.rtol = rtol / 10000
+        self.kde = None
+        self.train_fit_prop = train_fit_prop
+        self.register_buffer('_kde_data', None)
+
+    def fit_kde(self, data):
+        idx = torch.randperm(len(data))[:int(self.train_fit_prop * len(data))]
+        kept = data[idx.to(data.device)].detach().to(torch.float32).contiguous()
+        self._kde_data = kept
+        m, d = kept.shape
+        self.kde = {"bandwidth_": float(self.bandwidth) if self.bandwidth != 'scott'
+                    else ops.kde_scott_bandwidth(m, d), "n_fit": m}
+
+    def forward(self, x, return_ue=False):
+        if return_ue and self.kde is None:
+            raise ValueError("KDE not fitted yet")
+        pred = super().forward(x)
+        if return_ue:
+            ops._require_cuda(x, "x")
+            dens = ops.kde_density(self._kde_data.to(x.device), x, self.kde["bandwidth_"])
+            return pred, dens
+        return pred
+
+    class KDEFitCallback(_Callback):
+        """Fits the KDE on the inputs of the first training epoch (reference models.py:224-238)."""
+
+        def __init__(self):
+            super().__init__()
+            self._train_data_to_fit = []
+            self._epochs = 0
+
+        def on_train_epoch_end(self, trainer, pl_module):
+            if self._epochs == 0:
+                pl_module.fit_kde(torch.cat(self._train_data_to_fit))
+            self._epochs += 1
+
+        def on_train_batch_end(self, trainer, pl_module, outputs, batch, batch_idx):
+            if self._epochs == 0:
+                self._train_data_to_fit.append(batch[0])
+
+    def get_callbacks(self):
+        return [KDEMLPModel.KDEFitCallback()]
+
+
 KNNKDEMLPModel = _out_of_scope("KNNKDEMLPModel")
 
 

@@ -276,6 +276,34 @@ def kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000) -> float:
     return float(torch.ops.nnueehcs_b200.kde_jsd(u, v, int(num_points)))
 
 
+def kde_scott_bandwidth(m: int, d: int) -> float:
+    """sklearn ``KernelDensity(bandwidth='scott').fit(X).bandwidth_`` for X of shape [m, d]."""
+    return float(_lib.load().uq_kde_scott_bandwidth(int(m), int(d)))
+
+
+def kde_density(fit: torch.Tensor, x: torch.Tensor, bandwidth: float) -> torch.Tensor:
+    """``-exp(KernelDensity(bandwidth).fit(fit).score_samples(x))`` as a float64 [n] device tensor
+    (KDEMLPModel.forward's uncertainty score, reference models.py:209-222)."""
+    lib = _lib.load()
+    _require_cuda(fit, "fit")
+    _require_cuda(x, "x")
+    if fit.dim() != 2 or x.dim() != 2 or fit.shape[1] != x.shape[1]:
+        raise ValueError(f"fit [m, d] and x [n, d] must agree in d, got {tuple(fit.shape)} and "
+                         f"{tuple(x.shape)}")
+    if fit.shape[0] == 0 or x.shape[0] == 0:
+        raise ValueError("kde_density needs at least one fitted row and one query row")
+    fit = fit.detach().to(torch.float32).contiguous()
+    x = x.detach().to(torch.float32).contiguous()
+    n, m, d = x.shape[0], fit.shape[0], x.shape[1]
+    out = torch.empty(n, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        wsb = int(lib.uq_kde_density_workspace_bytes(n, m))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.uq_kde_density(fit.data_ptr(), m, x.data_ptr(), n, d, float(bandwidth),
+                                      out.data_ptr(), ws.data_ptr(), wsb, _stream_ptr(x.device)))
+    return out
+
+
 def score_metrics(id_scores: torch.Tensor, ood_scores: torch.Tensor, *, percentile_q: float = 95.0,
                   target_tpr: float = 0.95, tnr_reversed: bool = False,
                   classifier_percentile: float = 0.95, classifier_reversed: bool = False) -> dict:

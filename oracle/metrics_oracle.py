@@ -419,3 +419,29 @@ NumpyShardBackend.bin_moments = staticmethod(_np_bin_moments)
 NumpyShardBackend.wasserstein_from_bins = staticmethod(_np_from_bins)
 NumpyShardBackend.compact_flagged = staticmethod(_np_compact_flagged)
 NumpyShardBackend.wasserstein_ambiguous = staticmethod(_np_ambiguous)
+
+
+# ----------------------------------------------------------------------------------------------
+# KDEMLPModel's input-density score (nnueehcs/models.py:191-222): sklearn KernelDensity restated.
+# Pinned by tests/golden/kde_density.npz (outputs of the reference's own KDEMLPModel + sklearn).
+# ----------------------------------------------------------------------------------------------
+
+def scott_bandwidth_sklearn(m: int, d: int) -> float:
+    """sklearn/neighbors/_kde.py, KernelDensity.fit: bandwidth_ = n_samples ** (-1 / (n_features + 4))."""
+    return float(m) ** (-1.0 / (d + 4))
+
+
+def kde_neg_density(fit: np.ndarray, x: np.ndarray, bandwidth: float, block: int = 256) -> np.ndarray:
+    """``-exp(KernelDensity(bandwidth=h, kernel='gaussian').fit(fit).score_samples(x))`` in float64:
+    log-density = logsumexp(-|x - y|^2 / (2 h^2)) - log(m) - d log(h) - d/2 log(2 pi)."""
+    fit = np.asarray(fit, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    m, d = fit.shape
+    out = np.empty(x.shape[0])
+    log_norm = -np.log(m) - d * np.log(bandwidth) - 0.5 * d * np.log(2.0 * np.pi)
+    for i in range(0, x.shape[0], block):
+        d2 = ((x[i:i + block, None, :] - fit[None, :, :]) ** 2).sum(-1)
+        e = -0.5 * d2 / bandwidth ** 2
+        mx = e.max(axis=1, keepdims=True)
+        out[i:i + block] = (mx[:, 0] + np.log(np.exp(e - mx).sum(axis=1))) + log_norm
+    return -np.exp(out)

@@ -418,3 +418,84 @@ def test_score_metrics_large_against_oracle_and_mirror_classes():
     assert abs(rv["specificity"] - float((u > thr).mean())) < 1e-4
     with pytest.raises(ValueError, match="between 0 and 1"):
         ops.score_metrics(a, b, target_tpr=2.0)
+
+
+# ---- KDEMLPModel's input-density score --------------------------------------------
+
+KDE_RTOL = 2e-5   # sklearn's own tree pruning is rtol 1e-5; the kernel sums float32 MUFU.EX2 terms
+
+
+@pytest.mark.parametrize("tag", ["binomial5", "d2_half", "d12"])
+def test_kde_density_matches_reference_class_golden(tag):
+    g = load_golden("kde_density.npz")
+    fit, x, h = g[f"{tag}.fit"], g[f"{tag}.x"], float(g[f"{tag}.bandwidth"])
+    assert ops.kde_scott_bandwidth(*fit.shape) == pytest.approx(h, rel=1e-15)
+    got = ops.kde_density(_dev(fit), _dev(x), h)
+    assert got.dtype == torch.float64 and tuple(got.shape) == (x.shape[0],)
+    got = got.cpu().numpy()
+    ref = metrics_oracle.kde_neg_density(fit, x, h)
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref)
+    print(f"[kde_density {tag}] max rel err vs float64 oracle {np.max(err / np.maximum(np.abs(ref), 1e-300)):.2e}")
+    assert np.all(err <= KDE_RTOL * np.abs(ref) + 1e-12 * scale)
+    assert np.all(np.abs(got - g[f"{tag}.dens"]) <= 2 * KDE_RTOL * np.abs(ref) + 1e-12 * scale)
+    assert got[-1] == 0.0          # far query: every term underflows, as in the reference
+
+
+def test_kde_density_fit_splits_ragged_sizes_and_errors():
+    """Few query rows x many fitted rows (the fitted rows are split over blocks), ragged tiles."""
+    rng = np.random.default_rng(4)
+    for n, m, d in ((7, 70_001, 5), (1025, 4097, 3), (1, 1, 8), (3000, 513, 1)):
+        fit = rng.random((m, d)).astype(np.float32)
+        x = (rng.random((n, d)) * 1.5 - 0.25).astype(np.float32)
+        h = metrics_oracle.scott_bandwidth_sklearn(m, d)
+        got = ops.kde_density(_dev(fit), _dev(x), h).cpu().numpy()
+        ref = metrics_oracle.kde_neg_density(fit, x, h)
+        assert np.all(np.abs(got - ref) <= KDE_RTOL * np.abs(ref) + 1e-12 * np.abs(ref).max()), (n, m, d)
+    a = torch.rand(10, 5, device=DEV)
+    with pytest.raises(ValueError, match="agree in d"):
+        ops.kde_density(a, a[:, :4], 0.3)
+    with pytest.raises(ValueError, match="at least one"):
+        ops.kde_density(a[:0], a, 0.3)
+    with pytest.raises(ValueError, match="supported: 1..32"):
+        ops.kde_density(torch.rand(10, 40, device=DEV), torch.rand(4, 40, device=DEV), 0.3)
+    with pytest.raises(ValueError, match="bandwidth must be positive"):
+        ops.kde_density(a, a, 0.0)
+
+
+def test_kde_wrapper_drop_in():
+    from nnueehcs_b200.model_builder import KDEModelBuilder
+    import yaml as _yaml
+    g = load_golden("kde_density.npz")
+    tag = "binomial5"
+    arch = _yaml.safe_load(str(g[f"{tag}.arch_yaml"]))
+    model = KDEModelBuilder(arch, {"bandwidth": "scott", "rtol": 0.1, "train_fit_prop": 1.0}).build()
+    model.model.load_state_dict({k[len(f"{tag}.m0."):]: torch.from_numpy(g[k]) for k in g.files
+                                 if k.startswith(f"{tag}.m0.")})
+    model.to(DEV)
+    model.eval()
+    fit = torch.from_numpy(g[f"{tag}.fit"]).to(DEV)
+    model.fit_kde(fit)                       # train_fit_prop = 1: a permutation of the same rows
+    assert model.kde["bandwidth_"] == pytest.approx(float(g[f"{tag}.bandwidth"]), rel=1e-15)
+    with torch.no_grad():
+        pred, dens = model(torch.from_numpy(g[f"{tag}.x"]).to(DEV), return_ue=True)
+    np.testing.assert_allclose(pred.cpu().numpy(), g[f"{tag}.pred"], rtol=1e-5, atol=1e-6)
+    ref = g[f"{tag}.dens"]
+    assert np.all(np.abs(dens.cpu().numpy() - ref) <= 2 * KDE_RTOL * np.abs(ref) + 1e-12)
+    # a state_dict round trip keeps the fitted rows (they are a buffer)
+    assert "_kde_data" in model.state_dict()
+
+
+def test_kde_density_property_at_scale():
+    """1 M queries x 100 k fitted rows (1e11 Gaussian terms): the density of the fitted sample
+    integrates to ~1 over its support and a permutation of the fitted rows changes nothing
+    beyond float64 summation order."""
+    g = torch.Generator(device=DEV).manual_seed(0)
+    fit = torch.rand(100_000, 5, device=DEV, generator=g)
+    x = torch.rand(1 << 20, 5, device=DEV, generator=g) * 3.0 - 1.0    # uniform on [-1, 2]^5
+    h = ops.kde_scott_bandwidth(*fit.shape)
+    d1 = ops.kde_density(fit, x, h)
+    d2 = ops.kde_density(fit[torch.randperm(fit.shape[0], device=DEV)], x, h)
+    assert float((d1 - d2).abs().max()) <= 1e-6 * float(d1.abs().max())
+    integral = float(-d1.mean()) * 3.0 ** 5          # Monte-Carlo integral over the box
+    assert integral == pytest.approx(1.0, abs=0.05)   # Monte-Carlo error of 1 M samples ~ 1 %

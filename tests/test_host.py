@@ -188,8 +188,33 @@ def test_pager_builder_and_wrapper_contract(descr):
 
 
 def test_out_of_scope_wrappers_say_so(descr):
+    from nnueehcs_b200.model_builder import KNNKDEModelBuilder
     with pytest.raises(NotImplementedError, match="outside the hot path"):
-        KDEModelBuilder(descr["architecture_mlp"], {"bandwidth": "scott"}).build()
+        KNNKDEModelBuilder(descr["architecture_mlp"], {"bandwidth": "scott", "k": 10}).build()
+
+
+def test_kde_builder_and_wrapper_contract(descr):
+    """KDEMLPModel mirror (reference models.py:191-240): fit on a train_fit_prop share, sklearn's
+    scott bandwidth, errors before the fit, the fit callback, no CPU path for the score."""
+    from nnueehcs_b200.models import KDEMLPModel
+    model = KDEModelBuilder(descr["architecture_mlp"],
+                            {"bandwidth": "scott", "rtol": 0.1, "train_fit_prop": 0.5}).build()
+    assert isinstance(model, KDEMLPModel) and isinstance(model, MLPModel)
+    assert model.rtol == pytest.approx(1e-5) and model.kde is None
+    x = torch.randn(6, 16)
+    assert model(x).shape == (6, 5)
+    with pytest.raises(ValueError, match="KDE not fitted yet"):
+        model(x, return_ue=True)
+    cb = model.get_callbacks()[0]
+    for i in range(4):
+        cb.on_train_batch_end(None, model, None, (torch.randn(25, 16), None), i)
+    cb.on_train_epoch_end(None, model)
+    assert model._kde_data.shape == (50, 16) and "_kde_data" in dict(model.named_buffers())
+    assert model.kde["bandwidth_"] == pytest.approx(50 ** (-1 / 20))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(x, return_ue=True)
+    with pytest.raises(ValueError, match="bandwidth must be"):
+        KDEModelBuilder(descr["architecture_mlp"], {"bandwidth": "silverman"}).build()
 
 
 def test_split_blocks_vocabulary(descr):

@@ -85,6 +85,18 @@ def main():
         if name == "kde_jsd":
             line["gaussian_terms_equivalent_per_s"] = total * args.grid / (mean_ms * 1e-3)
         print(json.dumps(line), flush=True)
+    # KDEMLPModel's input-density score: 1 M queries x 100 k fitted rows, d = 5
+    g = torch.Generator(device=dev).manual_seed(7)
+    fit = torch.rand(100_000, 5, device=dev, generator=g)
+    xq = torch.rand(1 << 20, 5, device=dev, generator=g)
+    h = ops.kde_scott_bandwidth(*fit.shape)
+    mean_ms, best_ms = time_gpu(lambda: ops.kde_density(fit, xq, h), max(2, args.steps // 2))
+    pairs = fit.shape[0] * xq.shape[0]
+    print(json.dumps({"metric": "kde_density", "queries": xq.shape[0], "fitted_rows": fit.shape[0],
+                      "d": 5, "ms": mean_ms, "best_ms": best_ms,
+                      "gaussian_terms_per_s": pairs / (mean_ms * 1e-3),
+                      "bound": "FP32 + MUFU pipes (N x M terms of 2d + 2 FP32 ops and one ex2)"}),
+          flush=True)
     if args.cpu:
         from oracle import metrics_oracle
         un, vn = u[:5_000_000].cpu().numpy(), v[:5_000_000].cpu().numpy()
