@@ -26,7 +26,6 @@ namespace {
 
 constexpr int KDE_THREADS = 256;
 constexpr int KDE_CHUNK = 2048;      // sorted samples per block
-constexpr int KDE_GP = 4;            // grid points per thread per pass
 constexpr int KDE_SUB = 256;         // float32 accumulation run before flushing to float64
 constexpr double KDE_Z = 9.0;        // truncation in kernel standard deviations
 constexpr int STAT_BLOCKS = 296;
@@ -96,6 +95,42 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// One pass over the staged chunk for GP grid points per thread (columns jb + g * 256 + tid).
+template <int GP>
+__device__ __forceinline__ void kde_pass(const float* sx, int jb, int jlo, int jhi, double step_s,
+                                         double* __restrict__ out) {
+  float b[GP];
+  double acc64[GP];
+#pragma unroll
+  for (int g = 0; g < GP; ++g) {
+    const int j = jb + g * KDE_THREADS + threadIdx.x;
+    b[g] = (float)((double)(j - jlo) * step_s);
+    acc64[g] = 0.0;
+  }
+  for (int s0 = 0; s0 < KDE_CHUNK; s0 += KDE_SUB) {
+    float acc[GP];
+#pragma unroll
+    for (int g = 0; g < GP; ++g) acc[g] = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < KDE_SUB; i += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(&sx[s0 + i]);  // warp-broadcast
+#pragma unroll
+      for (int g = 0; g < GP; ++g) {
+        const float d0 = a.x - b[g], d1 = a.y - b[g], d2 = a.z - b[g], d3 = a.w - b[g];
+        acc[g] += ex2_approx(-d0 * d0) + ex2_approx(-d1 * d1) +
+                  (ex2_approx(-d2 * d2) + ex2_approx(-d3 * d3));
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < GP; ++g) acc64[g] += (double)acc[g];
+  }
+#pragma unroll
+  for (int g = 0; g < GP; ++g) {
+    const int j = jb + g * KDE_THREADS + threadIdx.x;
+    if (j <= jhi && acc64[g] != 0.0) atomicAdd(&out[j], acc64[g]);
+  }
+}
+
 // blockIdx.x < chunks_u : chunk of the first sample, else of the second
 __global__ void __launch_bounds__(KDE_THREADS)
 kde_eval_kernel(const float* __restrict__ us, int64_t nu, const float* __restrict__ vs, int64_t nv,
@@ -129,38 +164,16 @@ kde_eval_kernel(const float* __restrict__ us, int64_t nu, const float* __restric
   }
   __syncthreads();
 
+  // passes of GP grid points per thread; GP follows what is left of the window, so a ~480-point
+  // window costs 512 point-columns of MUFU work, not 1024
   const double step_s = p.step * scale;
-  for (int jb = jlo; jb <= jhi; jb += KDE_THREADS * KDE_GP) {
-    float b[KDE_GP];
-    double acc64[KDE_GP];
-#pragma unroll
-    for (int g = 0; g < KDE_GP; ++g) {
-      const int j = jb + g * KDE_THREADS + threadIdx.x;
-      b[g] = (float)((double)(j - jlo) * step_s);
-      acc64[g] = 0.0;
-    }
-    for (int s0 = 0; s0 < KDE_CHUNK; s0 += KDE_SUB) {
-      float acc[KDE_GP];
-#pragma unroll
-      for (int g = 0; g < KDE_GP; ++g) acc[g] = 0.f;
-#pragma unroll 4
-      for (int i = 0; i < KDE_SUB; i += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(&sx[s0 + i]);  // warp-broadcast
-#pragma unroll
-        for (int g = 0; g < KDE_GP; ++g) {
-          const float d0 = a.x - b[g], d1 = a.y - b[g], d2 = a.z - b[g], d3 = a.w - b[g];
-          acc[g] += ex2_approx(-d0 * d0) + ex2_approx(-d1 * d1) +
-                    (ex2_approx(-d2 * d2) + ex2_approx(-d3 * d3));
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < KDE_GP; ++g) acc64[g] += (double)acc[g];
-    }
-#pragma unroll
-    for (int g = 0; g < KDE_GP; ++g) {
-      const int j = jb + g * KDE_THREADS + threadIdx.x;
-      if (j <= jhi && acc64[g] != 0.0) atomicAdd(&out[j], acc64[g]);
-    }
+  int jb = jlo;
+  while (jb <= jhi) {
+    const int rem = jhi - jb + 1;
+    if (rem > 3 * KDE_THREADS) kde_pass<4>(sx, jb, jlo, jhi, step_s, out), jb += 4 * KDE_THREADS;
+    else if (rem > 2 * KDE_THREADS) kde_pass<3>(sx, jb, jlo, jhi, step_s, out), jb += 3 * KDE_THREADS;
+    else if (rem > KDE_THREADS) kde_pass<2>(sx, jb, jlo, jhi, step_s, out), jb += 2 * KDE_THREADS;
+    else kde_pass<1>(sx, jb, jlo, jhi, step_s, out), jb += KDE_THREADS;
   }
 }
 
