@@ -171,6 +171,18 @@ int uq_wasserstein_1d_ex(const float* u, int64_t nu, const float* v, int64_t nv,
 size_t uq_kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int32_t grid_pts);
 int uq_kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
                double* out_host, void* workspace, size_t workspace_bytes, void* stream);
+/*    Same with the method spelled out (uq_kde_jsd = UQ_KDE_AUTO).  WINDOW: the samples are
+      sorted and every chunk adds exp() terms to the grid points within 9 bandwidths (every term of
+      scipy's sum above 3e-18 of the peak).  MOMENTS: bins of width h/4, six moments per bin from one
+      pass over the sample, Hermite series on the grid -- independent of N x grid work, JS distance
+      within 1e-9 relative of WINDOW; needs (max - min) / (h/4) <= 8192.  AUTO = MOMENTS when it
+      applies.  *method_used (host, may be NULL) receives what ran. */
+#define UQ_KDE_AUTO 0
+#define UQ_KDE_WINDOW 1
+#define UQ_KDE_MOMENTS 2
+int uq_kde_jsd_ex(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
+                  int32_t method, double* out_host, int32_t* method_used, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* -- score consumers: the rest of what nnueehcs/evaluation.py derives
       from the two score vectors, from one pair of device sorts.  Replaces MeanScoreEvaluation /

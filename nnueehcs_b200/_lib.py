@@ -16,6 +16,7 @@ MODE_ENSEMBLE, MODE_MC_DROPOUT, MODE_DELTA_UQ, MODE_PAGER = 0, 1, 2, 3
 PREC_FP32, PREC_BF16 = 0, 1
 OUT_MEAN_STD, OUT_MOMENTS = 0, 1
 WASSERSTEIN_AUTO, WASSERSTEIN_SORT, WASSERSTEIN_BINNED = 0, 1, 2
+KDE_AUTO, KDE_WINDOW, KDE_MOMENTS = 0, 1, 2
 
 # every symbol include/nnueehcs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
@@ -24,7 +25,7 @@ EXPORTS = (
     "uq_forward_workspace_bytes", "uq_forward", "uq_forward_host", "uq_moments_merge",
     "uq_philox_keep_masks", "uq_wasserstein_workspace_bytes", "uq_wasserstein_1d",
     "uq_wasserstein_1d_ex",
-    "uq_kde_jsd_workspace_bytes", "uq_kde_jsd",
+    "uq_kde_jsd_workspace_bytes", "uq_kde_jsd", "uq_kde_jsd_ex",
     "uq_sample_stats_workspace_bytes", "uq_sample_stats", "uq_kde_grid_workspace_bytes",
     "uq_kde_grid_accumulate", "uq_jsd_from_grids", "uq_key_bins", "uq_key_histogram",
     "uq_partition_by_bin", "uq_wasserstein_1d_range",
@@ -119,6 +120,9 @@ def load() -> C.CDLL:
     lib.uq_kde_jsd_workspace_bytes.argtypes = [i64, i64, i32]
     lib.uq_kde_jsd_workspace_bytes.restype = sz
     lib.uq_kde_jsd.argtypes = [vp, i64, vp, i64, i32, C.POINTER(dbl), vp, sz, vp]
+    lib.uq_kde_jsd_ex.argtypes = [vp, i64, vp, i64, i32, i32, C.POINTER(dbl), C.POINTER(i32), vp, sz,
+                                  vp]
+    lib.uq_kde_jsd_ex.restype = C.c_int
     lib.uq_sample_stats_workspace_bytes.restype = sz
     lib.uq_sample_stats.argtypes = [vp, i64, C.POINTER(dbl), vp, sz, vp]
     lib.uq_kde_grid_workspace_bytes.argtypes = [i64]

@@ -353,8 +353,24 @@ int uq_kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int32_t g
              (long long)nv);
   UQ_REQUIRE(grid_pts >= 2 && grid_pts <= (1 << 20), UQ_ERR_INVALID,
              "uq_kde_jsd: grid_pts %d outside [2, 2^20]", grid_pts);
-  return kde_jsd(u, nu, v, nv, grid_pts, out_host, workspace, workspace_bytes,
-                 static_cast<cudaStream_t>(stream));
+  return kde_jsd(u, nu, v, nv, grid_pts, UQ_KDE_AUTO, out_host, nullptr, workspace,
+                 workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int uq_kde_jsd_ex(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
+                  int32_t method, double* out_host, int32_t* method_used, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(out_host != nullptr, UQ_ERR_INVALID, "uq_kde_jsd_ex: out is NULL");
+  UQ_REQUIRE(u && v && nu >= 2 && nv >= 2, UQ_ERR_INVALID,
+             "uq_kde_jsd_ex: each sample needs at least 2 values (got %lld, %lld)", (long long)nu,
+             (long long)nv);
+  UQ_REQUIRE(grid_pts >= 2 && grid_pts <= (1 << 20), UQ_ERR_INVALID,
+             "uq_kde_jsd_ex: grid_pts %d outside [2, 2^20]", grid_pts);
+  int used = 0;
+  const int rc = kde_jsd(u, nu, v, nv, grid_pts, method, out_host, &used, workspace,
+                         workspace_bytes, static_cast<cudaStream_t>(stream));
+  if (method_used) *method_used = used;
+  return rc;
 }
 
 size_t uq_kde_grid_workspace_bytes(int64_t n) { return kde_grid_workspace_bytes(n); }

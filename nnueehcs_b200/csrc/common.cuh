@@ -132,7 +132,7 @@ size_t kde_density_workspace_bytes(int64_t n, int64_t m);
 int kde_density(const float* fit, int64_t m, const float* x, int64_t n, int d, double bandwidth,
                 double* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int grid_pts);
-int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
-            double* out_host, void* ws, size_t ws_bytes, cudaStream_t st);
+int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts, int method,
+            double* out_host, int* method_used_host, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace uq

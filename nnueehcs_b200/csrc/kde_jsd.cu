@@ -16,7 +16,19 @@
 // cancellation), one MUFU.EX2 per pair, flushed to float64 every 256 terms.  Each block adds its
 // window's partial sums to the float64 grid with atomics; a last block turns the two grids into
 // the JS distance.
+//
+// Moment method (default when it applies; uq_kde_jsd_ex's `method`): no sort and no N x G work.
+// The value range is cut into bins of width h/4; for a value at offset eps*h from its bin centre c
+//   exp(-((g - c)/h - eps)^2 / 2) = K(z) * exp(z eps - eps^2/2) = K(z) * sum_m He_m(z) eps^m / m!,
+// z = (g - c)/h, so the kernel sum at every grid point follows from six numbers per bin -- the
+// count and sum eps^m, m = 1..5 -- gathered in ONE pass over the sample (bin_moments-style
+// block-private shared-memory tables, six shared atomics per value), and a [grid point x 77 bins]
+// evaluation in float64 that no longer depends on N.  |eps| <= 1/8: the truncated series moves
+// the Jensen-Shannon distance by <= 1e-9 relative on every distribution pair tried (the oracle
+// tests state 2e-5).  Needs (max - min) / (h/4) <= 8192 bins (shared memory); else the window
+// method above runs.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sort.cuh"
@@ -177,6 +189,126 @@ kde_eval_kernel(const float* __restrict__ us, int64_t nu, const float* __restric
   }
 }
 
+// ---- moment method ---------------------------------------------------------------------------------
+
+constexpr int KM_PER_H = 4;          // bins per bandwidth
+constexpr int KM_ORDER = 5;          // highest eps power kept
+constexpr int KM_WORDS = KM_ORDER + 1;
+constexpr int KM_MAX_BINS = 8192;    // 8192 x 6 x 4 B = 192 KB of shared memory
+constexpr int KM_THREADS = 1024;
+
+// One pass over a sample: per bin the count and sum eps^m (m = 1..5), block-private in shared
+// memory (float32: a block adds a few thousand terms per bin), flushed to float64 global tables
+// [bin][6] with one atomic per non-empty word.
+__global__ void __launch_bounds__(KM_THREADS, 1)
+kde_moments_kernel(const float* __restrict__ x, int64_t n, double lo, double inv_w, int nb,
+                   double* __restrict__ tables) {
+  extern __shared__ uint32_t km_sh[];
+  uint32_t* cnt = km_sh;                                            // [nb]
+  float* mom = reinterpret_cast<float*>(km_sh + nb);                // [KM_ORDER][nb]
+  for (int i = threadIdx.x; i < KM_WORDS * nb; i += KM_THREADS) km_sh[i] = 0;
+  __syncthreads();
+  auto add = [&](float v) {
+    const double t = ((double)v - lo) * inv_w;                      // float64: bin offsets stay exact
+    int b = (int)t;
+    b = b < 0 ? 0 : (b >= nb ? nb - 1 : b);
+    const float e = (float)((t - (double)b - 0.5) * (1.0 / KM_PER_H));
+    const float e2 = e * e;
+    atomicAdd(&cnt[b], 1u);
+    atomicAdd(&mom[b], e);
+    atomicAdd(&mom[nb + b], e2);
+    atomicAdd(&mom[2 * nb + b], e2 * e);
+    atomicAdd(&mom[3 * nb + b], e2 * e2);
+    atomicAdd(&mom[4 * nb + b], e2 * e2 * e);
+  };
+  const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
+  const int64_t n4 = (n - head) / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  const int64_t gtid = (int64_t)blockIdx.x * KM_THREADS + threadIdx.x;
+  const int64_t gstride = (int64_t)gridDim.x * KM_THREADS;
+  if (gtid < head) add(__ldg(x + gtid));
+  int64_t i = gtid;
+  for (; i + gstride < n4; i += 2 * gstride) {
+    const float4 a0 = __ldg(x4 + i), a1 = __ldg(x4 + i + gstride);
+    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
+    add(a1.x); add(a1.y); add(a1.z); add(a1.w);
+  }
+  for (; i < n4; i += gstride) {
+    const float4 a0 = __ldg(x4 + i);
+    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
+  }
+  const int64_t tail0 = head + 4 * n4;
+  if (tail0 + gtid < n) add(__ldg(x + tail0 + gtid));
+  __syncthreads();
+  for (int b = threadIdx.x; b < nb; b += KM_THREADS) {
+    const uint32_t c = cnt[b];
+    if (c) {
+      atomicAdd(&tables[(size_t)b * KM_WORDS], (double)c);
+#pragma unroll
+      for (int m = 0; m < KM_ORDER; ++m)
+        atomicAdd(&tables[(size_t)b * KM_WORDS + 1 + m], (double)mom[m * nb + b]);
+    }
+  }
+}
+
+// grid[j] += sum over the bins within KDE_Z bandwidths of K(z) * sum_m He_m(z) M_m / m!
+__global__ void __launch_bounds__(256)
+kde_eval_bins_kernel(const double* __restrict__ tables, int nb, double lo, double w, double h,
+                     double grid_lo, double grid_step, int grid_pts, double* __restrict__ grid) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= grid_pts) return;
+  const double g = grid_lo + (double)j * grid_step;
+  const double reach = KDE_Z * h + 0.5 * w;
+  int b0 = (int)floor((g - reach - lo) / w), b1 = (int)floor((g + reach - lo) / w);
+  b0 = b0 < 0 ? 0 : b0;
+  b1 = b1 >= nb ? nb - 1 : b1;
+  double acc = 0.0;
+  for (int b = b0; b <= b1; ++b) {
+    const double* T = tables + (size_t)b * KM_WORDS;
+    const double c = T[0];
+    if (c == 0.0) continue;
+    const double z = (g - (lo + ((double)b + 0.5) * w)) / h;
+    const double z2 = z * z;
+    const double he2 = z2 - 1.0, he3 = z * (z2 - 3.0), he4 = z2 * (z2 - 6.0) + 3.0,
+                 he5 = z * (z2 * (z2 - 10.0) + 15.0);
+    const double series = c + z * T[1] + he2 * T[2] * (1.0 / 2.0) + he3 * T[3] * (1.0 / 6.0) +
+                          he4 * T[4] * (1.0 / 24.0) + he5 * T[5] * (1.0 / 120.0);
+    acc += exp(-0.5 * z2) * series;
+  }
+  grid[j] += acc;
+}
+
+// number of bins the moment method needs for one sample on [lo, hi], or 0 if it does not apply
+int km_bins(double lo, double hi, double h) {
+  if (!(h > 0.0) || !(hi >= lo)) return 0;
+  const double nb = floor((hi - lo) / (h / KM_PER_H)) + 1.0;
+  return nb <= (double)KM_MAX_BINS ? (int)nb : 0;
+}
+
+// adds the kernel sums of sample x (bandwidth h) to grid[grid_pts] = linspace(lo, hi); tables:
+// KM_MAX_BINS * KM_WORDS doubles of scratch
+int km_accumulate(const float* x, int64_t n, double lo, double hi, double h, int nb, int grid_pts,
+                  double* grid, double* tables, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    UQ_CUDA(cudaFuncSetAttribute(kde_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 KM_MAX_BINS * KM_WORDS * (int)sizeof(uint32_t)));
+    attr_set = true;
+  }
+  const double w = h / KM_PER_H;
+  UQ_CUDA(cudaMemsetAsync(tables, 0, sizeof(double) * (size_t)nb * KM_WORDS, st));
+  int64_t blocks = (n + (int64_t)KM_THREADS * 8 - 1) / ((int64_t)KM_THREADS * 8);
+  if (blocks > 148) blocks = 148;
+  if (blocks < 1) blocks = 1;
+  kde_moments_kernel<<<(unsigned)blocks, KM_THREADS, (size_t)nb * KM_WORDS * sizeof(uint32_t), st>>>(
+      x, n, lo, 1.0 / w, nb, tables);
+  UQ_LAUNCH_CHECK();
+  kde_eval_bins_kernel<<<(grid_pts + 255) / 256, 256, 0, st>>>(
+      tables, nb, lo, w, h, lo, (hi - lo) / (double)(grid_pts - 1), grid_pts, grid);
+  UQ_LAUNCH_CHECK();
+  return UQ_OK;
+}
+
 // scipy.spatial.distance.jensenshannon on the two raw kernel-sum vectors
 __global__ void __launch_bounds__(1024)
 jsd_kernel(const double* __restrict__ pdf, int grid_pts, double* __restrict__ result) {
@@ -211,7 +343,7 @@ jsd_kernel(const double* __restrict__ pdf, int grid_pts, double* __restrict__ re
 }
 
 struct WsLayout {
-  size_t u, ut, v, vt, scratch, partials, params, pdf, result, total;
+  size_t u, ut, v, vt, scratch, partials, params, pdf, result, tables, stats, total;
 };
 
 WsLayout layout(int64_t nu, int64_t nv, int grid_pts) {
@@ -228,6 +360,8 @@ WsLayout layout(int64_t nu, int64_t nv, int grid_pts) {
   L.params = o; o += al(sizeof(KdeParams));
   L.pdf = o; o += al(sizeof(double) * 2 * (size_t)grid_pts);
   L.result = o; o += 256;
+  L.tables = o; o += al(sizeof(double) * KM_MAX_BINS * KM_WORDS);
+  L.stats = o; o += al(uq_sample_stats_workspace_bytes());
   L.total = o;
   return L;
 }
@@ -239,12 +373,48 @@ size_t kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int grid_pts) {
   return layout(nu, nv, grid_pts).total;
 }
 
-int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts, double* out_host,
-            void* ws, size_t ws_bytes, cudaStream_t st) {
+// method: UQ_KDE_AUTO / UQ_KDE_WINDOW (sorted samples, 9-sigma windows) / UQ_KDE_MOMENTS.
+// method_used_host (may be NULL) receives the method that ran.
+int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts, int method,
+            double* out_host, int* method_used_host, void* ws, size_t ws_bytes, cudaStream_t st) {
   const WsLayout L = layout(nu, nv, grid_pts);
   UQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, UQ_ERR_WORKSPACE,
              "kde_jsd needs %zu workspace bytes, got %zu", L.total, ws_bytes);
+  UQ_REQUIRE(method >= UQ_KDE_AUTO && method <= UQ_KDE_MOMENTS, UQ_ERR_INVALID,
+             "kde_jsd: unknown method %d", method);
   char* b = static_cast<char*>(ws);
+  if (method_used_host) *method_used_host = UQ_KDE_WINDOW;
+  if (method != UQ_KDE_WINDOW && nu >= 2 && nv >= 2) {
+    // scipy.stats.gaussian_kde: h = sqrt(unbiased variance) * n^(-1/5); grid = linspace(min, max)
+    double su[4], sv[4];
+    int rc = uq_sample_stats(u, nu, su, b + L.stats, uq_sample_stats_workspace_bytes(), st);
+    if (rc != UQ_OK) return rc;
+    rc = uq_sample_stats(v, nv, sv, b + L.stats, uq_sample_stats_workspace_bytes(), st);
+    if (rc != UQ_OK) return rc;
+    const double hu = sqrt(su[3] / (double)(nu - 1)) * pow((double)nu, -0.2);
+    const double hv = sqrt(sv[3] / (double)(nv - 1)) * pow((double)nv, -0.2);
+    const double lo = su[0] < sv[0] ? su[0] : sv[0], hi = su[1] > sv[1] ? su[1] : sv[1];
+    const int nbu = km_bins(lo, hi, hu), nbv = km_bins(lo, hi, hv);
+    if (nbu > 0 && nbv > 0 && isfinite(lo) && isfinite(hi)) {
+      double* pdf = reinterpret_cast<double*>(b + L.pdf);
+      double* tables = reinterpret_cast<double*>(b + L.tables);
+      double* result = reinterpret_cast<double*>(b + L.result);
+      UQ_CUDA(cudaMemsetAsync(pdf, 0, sizeof(double) * 2 * (size_t)grid_pts, st));
+      rc = km_accumulate(u, nu, lo, hi, hu, nbu, grid_pts, pdf, tables, st);
+      if (rc != UQ_OK) return rc;
+      rc = km_accumulate(v, nv, lo, hi, hv, nbv, grid_pts, pdf + grid_pts, tables, st);
+      if (rc != UQ_OK) return rc;
+      jsd_kernel<<<1, 1024, 0, st>>>(pdf, grid_pts, result);
+      UQ_LAUNCH_CHECK();
+      UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
+      UQ_CUDA(cudaStreamSynchronize(st));
+      if (method_used_host) *method_used_host = UQ_KDE_MOMENTS;
+      return UQ_OK;
+    }
+    UQ_REQUIRE(method != UQ_KDE_MOMENTS, UQ_ERR_UNSUPPORTED,
+               "kde_jsd: the moment method needs (max - min) / (h / %d) <= %d bins and h > 0 "
+               "(range %g, bandwidths %g / %g)", KM_PER_H, KM_MAX_BINS, hi - lo, hu, hv);
+  }
   float* du = reinterpret_cast<float*>(b + L.u);
   float* dut = reinterpret_cast<float*>(b + L.ut);
   float* dv = reinterpret_cast<float*>(b + L.v);
@@ -284,7 +454,8 @@ int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts
 size_t kde_grid_workspace_bytes(int64_t n) {
   if (n < 1) return 0;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  return 2 * al(sizeof(float) * (size_t)n) + al(radix_sort_scratch_bytes(n)) + al(sizeof(KdeParams));
+  return 2 * al(sizeof(float) * (size_t)n) + al(radix_sort_scratch_bytes(n)) + al(sizeof(KdeParams)) +
+         al(sizeof(double) * KM_MAX_BINS * KM_WORDS);
 }
 
 // Adds this shard's Gaussian kernel sums to `grid` (float64 [grid_pts], device).  The grid
@@ -303,6 +474,11 @@ int kde_grid_accumulate(const float* x, int64_t n, double lo, double hi, double 
   float* dt = reinterpret_cast<float*>(b + al(sizeof(float) * (size_t)n));
   char* scratch = b + 2 * al(sizeof(float) * (size_t)n);
   KdeParams* params = reinterpret_cast<KdeParams*>(scratch + al(radix_sort_scratch_bytes(n)));
+  if (const int nb = getenv("UQ_KDE_WINDOW_ONLY") ? 0 : km_bins(lo, hi, bandwidth)) {
+    // moment method: one pass over the shard, then a [grid x 77 bins] evaluation (no sort)
+    double* tables = reinterpret_cast<double*>(reinterpret_cast<char*>(params) + al(sizeof(KdeParams)));
+    return km_accumulate(x, n, lo, hi, bandwidth, nb, grid_pts, grid, tables, st);
+  }
   UQ_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
   float* sx = nullptr;
   int rc = radix_sort_f32(dx, dt, n, scratch, radix_sort_scratch_bytes(n), &sx, st);

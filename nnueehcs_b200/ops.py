@@ -269,11 +269,31 @@ def wasserstein_1d_info(u: torch.Tensor, v: torch.Tensor, method: str = "auto") 
             "sorted_u": int(info[1]), "sorted_v": int(info[2])}
 
 
-def kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000) -> float:
+_KMETHOD = {"auto": _lib.KDE_AUTO, "window": _lib.KDE_WINDOW, "moments": _lib.KDE_MOMENTS}
+
+
+def kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000, method: str = "auto"
+            ) -> float:
     """``JensenShannonEvaluation.pdf_jsd(u, v, num_points)`` for float32 device samples."""
+    u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
+    if method not in _KMETHOD:
+        raise ValueError(f"unknown KDE method {method!r} (auto, window, moments)")
+    return float(torch.ops.nnueehcs_b200.kde_jsd(u, v, int(num_points), _KMETHOD[method]))
+
+
+def kde_jsd_info(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000, method: str = "auto"
+                 ) -> dict:
+    """Same value plus which method ran."""
     lib = _lib.load()
     u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
-    return float(torch.ops.nnueehcs_b200.kde_jsd(u, v, int(num_points)))
+    out, used = C.c_double(), C.c_int32()
+    with torch.cuda.device(u.device):
+        wsb = int(lib.uq_kde_jsd_workspace_bytes(u.numel(), v.numel(), num_points))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
+        _lib.check(lib.uq_kde_jsd_ex(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), num_points,
+                                     _KMETHOD[method], C.byref(out), C.byref(used), ws.data_ptr(),
+                                     wsb, _stream_ptr(u.device)))
+    return {"value": float(out.value), "method": "moments" if used.value == 2 else "window"}
 
 
 def kde_scott_bandwidth(m: int, d: int) -> float:
@@ -567,14 +587,15 @@ def _op_wasserstein_1d(u: torch.Tensor, v: torch.Tensor, method: int = 0) -> flo
     return float(out.value)
 
 
-def _op_kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int) -> float:
+def _op_kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int, method: int = 0) -> float:
     lib = _lib.load()
     out = C.c_double()
     with torch.cuda.device(u.device):
         wsb = int(lib.uq_kde_jsd_workspace_bytes(u.numel(), v.numel(), num_points))
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
-        _lib.check(lib.uq_kde_jsd(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), num_points,
-                                  C.byref(out), ws.data_ptr(), wsb, _stream_ptr(u.device)))
+        _lib.check(lib.uq_kde_jsd_ex(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), num_points,
+                                     method, C.byref(out), None, ws.data_ptr(), wsb,
+                                     _stream_ptr(u.device)))
     return float(out.value)
 
 
@@ -587,7 +608,7 @@ OP_SCHEMAS = {
                   "-> (Tensor, Tensor)",
     "moments_merge": "(Tensor means, Tensor m2s, float[] counts) -> (Tensor, Tensor)",
     "wasserstein_1d": "(Tensor u, Tensor v, int method=0) -> float",
-    "kde_jsd": "(Tensor u, Tensor v, int num_points) -> float",
+    "kde_jsd": "(Tensor u, Tensor v, int num_points, int method=0) -> float",
 }
 _OP_IMPLS = {"uq_forward": _op_uq_forward, "moments_merge": _op_moments_merge,
              "wasserstein_1d": _op_wasserstein_1d, "kde_jsd": _op_kde_jsd}

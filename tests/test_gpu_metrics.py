@@ -206,6 +206,66 @@ def test_metric_classes_drop_in():
     assert two["wasserstein_distance"] == pytest.approx(float(g["wasserstein"]), rel=1e-12)
 
 
+def _kde_cases():
+    rng = np.random.default_rng(21)
+    return {
+        "gamma_id_vs_ood": (rng.gamma(2.0, 0.05, 9000), rng.gamma(3.0, 0.08, 7000)),
+        "separated_normals": (rng.normal(0, 1, 8000), rng.normal(6, 0.5, 5000)),
+        "bimodal_vs_wide": (np.concatenate([rng.normal(0, 0.1, 4000), rng.normal(5, 0.1, 4000)]),
+                            rng.normal(2.5, 1, 6000)),
+        "lognormal": (rng.lognormal(0, 1.0, 8000), rng.lognormal(0.5, 0.7, 8000)),
+        "tiny": (rng.random(2), rng.random(3) + 0.5),
+    }
+
+
+@pytest.mark.parametrize("case", sorted(_kde_cases()))
+def test_kde_jsd_moment_method_equals_window_method_and_oracle(case):
+    """The one-pass moment method against the window method (every exp term within 9 bandwidths)
+    and the float64 oracle of scipy's arithmetic; the two device methods agree far tighter than
+    either does with float64 (their difference is the truncated Hermite series, <= 1e-8)."""
+    u, v = (a.astype(np.float32) for a in _kde_cases()[case])
+    G = 3000
+    ref = metrics_oracle.pdf_jsd(u, v, G)
+    mom = ops.kde_jsd_info(_dev(u), _dev(v), G, "moments")
+    win = ops.kde_jsd_info(_dev(u), _dev(v), G, "window")
+    auto = ops.kde_jsd_info(_dev(u), _dev(v), G, "auto")
+    assert mom["method"] == "moments" and win["method"] == "window" and auto["method"] == "moments"
+    print(f"[kde_jsd {case}] oracle {ref:.12f} moments {mom['value']:.12f} window {win['value']:.12f}")
+    assert mom["value"] == pytest.approx(ref, rel=JSD_RTOL)
+    assert win["value"] == pytest.approx(ref, rel=JSD_RTOL)
+    assert mom["value"] == pytest.approx(win["value"], rel=2e-6)
+    assert auto["value"] == pytest.approx(mom["value"], rel=1e-7)   # float atomics: order varies
+
+
+def test_kde_jsd_moment_method_falls_back_when_bins_do_not_fit():
+    rng = np.random.default_rng(2)
+    u = rng.normal(0, 1, 200_000).astype(np.float32)
+    u[0] = 3.0e4                      # one far outlier: (max - min) / (h / 4) >> 8192 bins
+    v = rng.normal(0.5, 1, 150_000).astype(np.float32)
+    info = ops.kde_jsd_info(_dev(u), _dev(v), 2000, "auto")
+    assert info["method"] == "window" and np.isfinite(info["value"])
+    with pytest.raises(ValueError, match="moment method needs"):
+        ops.kde_jsd(_dev(u), _dev(v), 2000, "moments")
+    with pytest.raises(ValueError, match="unknown KDE method"):
+        ops.kde_jsd(_dev(u), _dev(v), 2000, "fft")
+
+
+def test_kde_jsd_methods_agree_at_scale():
+    """BASELINE configs[4] shape on one GPU (50 M + 50 M, 20 000 grid points)."""
+    n = 50_000_000
+    g = torch.Generator(device=DEV).manual_seed(0)
+    u = torch.empty(n, device=DEV).exponential_(1.0, generator=g)
+    u = (u + torch.empty(n, device=DEV).exponential_(1.0, generator=g)) * 0.05
+    v = torch.zeros(n, device=DEV)
+    for _ in range(3):
+        v += torch.empty(n, device=DEV).exponential_(1.0, generator=g)
+    v *= 0.08
+    mom = ops.kde_jsd_info(u, v, 20000, "moments")
+    win = ops.kde_jsd_info(u, v, 20000, "window")
+    assert mom["method"] == "moments" and win["method"] == "window"
+    assert mom["value"] == pytest.approx(win["value"], rel=2e-6)
+
+
 # ---- per-rank steps of the sharded metrics (each CUDA step against its numpy stand-in) ----------
 
 def _gamma_pair(nu, nv, seed=3):

@@ -67,7 +67,8 @@ def main():
     for name, fn in (("wasserstein_1d", lambda: ops.wasserstein_1d(u, v)),
                      ("wasserstein_1d[sort]", lambda: ops.wasserstein_1d(u, v, "sort")),
                      ("wasserstein_1d[same distribution, auto]", lambda: ops.wasserstein_1d(u, same)),
-                     ("kde_jsd", lambda: ops.kde_jsd(u, v, args.grid))):
+                     ("kde_jsd", lambda: ops.kde_jsd(u, v, args.grid)),
+                     ("kde_jsd[window]", lambda: ops.kde_jsd(u, v, args.grid, "window"))):
         ops.reset_launch_count()
         val = fn()
         launches = ops.launch_count()
@@ -82,7 +83,9 @@ def main():
                                            "sort" if "[sort]" in name else "auto")
             line["method"] = info["method"]
             line["values_sorted"] = info["sorted_u"] + info["sorted_v"]
-        if name == "kde_jsd":
+        if name.startswith("kde_jsd"):
+            line["method"] = ops.kde_jsd_info(u, v, args.grid,
+                                              "window" if "[window]" in name else "auto")["method"]
             line["gaussian_terms_equivalent_per_s"] = total * args.grid / (mean_ms * 1e-3)
         print(json.dumps(line), flush=True)
     # KDEMLPModel's input-density score: 1 M queries x 100 k fitted rows, d = 5
