@@ -198,28 +198,46 @@ constexpr int KM_MAX_BINS = 8192;    // 8192 x 6 x 4 B = 192 KB of shared memory
 constexpr int KM_THREADS = 1024;
 
 // One pass over a sample: per bin the count and sum eps^m (m = 1..5), block-private in shared
-// memory (float32: a block adds a few thousand terms per bin), flushed to float64 global tables
-// [bin][6] with one atomic per non-empty word.
+// memory, flushed to float64 global tables [bin][6].  A float atomicAdd on shared memory is a CAS
+// loop in SASS (ATOMS.CAST.SPIN; first version: 440 us per 50 M values), so the moments are
+// accumulated in fixed point with native 32-bit ATOMS.ADD: term_m = (eps^m + o_m) * S_m with
+// o_m = 2 * 8^-m (keeps it positive; |eps| <= 1/8) and S_m = 2^19 * 8^m, i.e. 2^19 .. 3 * 2^19 per
+// term, converted with the 2^23 magic-number add (FADD + LOP instead of a quarter-rate F2I).  A
+// word wraps at most once per 2730 adds; the add that sees the wrap (old + term < old) credits
+// 2^32 / S_m to the global table directly.  The offset c * o_m leaves at the flush (exact: the
+// count is an integer).
+__device__ __forceinline__ uint32_t km_fixed(float term) {   // 0 <= term < 2^23, round to nearest
+  return __float_as_uint(term + 8388608.0f) & 0x7FFFFFu;
+}
+
 __global__ void __launch_bounds__(KM_THREADS, 1)
 kde_moments_kernel(const float* __restrict__ x, int64_t n, double lo, double inv_w, int nb,
                    double* __restrict__ tables) {
   extern __shared__ uint32_t km_sh[];
-  uint32_t* cnt = km_sh;                                            // [nb]
-  float* mom = reinterpret_cast<float*>(km_sh + nb);                // [KM_ORDER][nb]
+  uint32_t* cnt = km_sh;                       // [nb]
+  uint32_t* mom = km_sh + nb;                  // [KM_ORDER][nb]
   for (int i = threadIdx.x; i < KM_WORDS * nb; i += KM_THREADS) km_sh[i] = 0;
   __syncthreads();
+  constexpr float S1 = 4194304.f, S2 = S1 * 8.f, S3 = S2 * 8.f, S4 = S3 * 8.f, S5 = S4 * 8.f;
+  auto bump = [&](int m, int b, float e_m, float scale, float offset_scaled, double wrap_credit) {
+    const uint32_t term = km_fixed(fmaf(e_m, scale, offset_scaled));
+    const uint32_t old = atomicAdd(&mom[m * nb + b], term);
+    if (old + term < old) atomicAdd(&tables[(size_t)b * KM_WORDS + 1 + m], wrap_credit);
+  };
   auto add = [&](float v) {
     const double t = ((double)v - lo) * inv_w;                      // float64: bin offsets stay exact
     int b = (int)t;
     b = b < 0 ? 0 : (b >= nb ? nb - 1 : b);
-    const float e = (float)((t - (double)b - 0.5) * (1.0 / KM_PER_H));
+    float e = (float)((t - (double)b - 0.5) * (1.0 / KM_PER_H));
+    e = fminf(fmaxf(e, -0.126f), 0.126f);      // |eps| <= 1/8 by construction; keeps every term in (0, 2^21)
     const float e2 = e * e;
     atomicAdd(&cnt[b], 1u);
-    atomicAdd(&mom[b], e);
-    atomicAdd(&mom[nb + b], e2);
-    atomicAdd(&mom[2 * nb + b], e2 * e);
-    atomicAdd(&mom[3 * nb + b], e2 * e2);
-    atomicAdd(&mom[4 * nb + b], e2 * e2 * e);
+    // o_m * S_m = 2 * 8^-m * 2^19 * 8^m = 2^20 for every m
+    bump(0, b, e, S1, 1048576.f, 4294967296.0 / S1);
+    bump(1, b, e2, S2, 1048576.f, 4294967296.0 / S2);
+    bump(2, b, e2 * e, S3, 1048576.f, 4294967296.0 / S3);
+    bump(3, b, e2 * e2, S4, 1048576.f, 4294967296.0 / S4);
+    bump(4, b, e2 * e2 * e, S5, 1048576.f, 4294967296.0 / S5);
   };
   const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
   const int64_t n4 = (n - head) / 4;
@@ -240,42 +258,51 @@ kde_moments_kernel(const float* __restrict__ x, int64_t n, double lo, double inv
   const int64_t tail0 = head + 4 * n4;
   if (tail0 + gtid < n) add(__ldg(x + tail0 + gtid));
   __syncthreads();
+  const double inv_s[KM_ORDER] = {1.0 / S1, 1.0 / S2, 1.0 / S3, 1.0 / S4, 1.0 / S5};
   for (int b = threadIdx.x; b < nb; b += KM_THREADS) {
     const uint32_t c = cnt[b];
     if (c) {
       atomicAdd(&tables[(size_t)b * KM_WORDS], (double)c);
 #pragma unroll
-      for (int m = 0; m < KM_ORDER; ++m)
-        atomicAdd(&tables[(size_t)b * KM_WORDS + 1 + m], (double)mom[m * nb + b]);
+      for (int m = 0; m < KM_ORDER; ++m)  // (low word - c * 2^20) / S_m; the wraps were credited
+        atomicAdd(&tables[(size_t)b * KM_WORDS + 1 + m],
+                  ((double)mom[m * nb + b] - (double)c * 1048576.0) * inv_s[m]);
     }
   }
 }
 
 // grid[j] += sum over the bins within KDE_Z bandwidths of K(z) * sum_m He_m(z) M_m / m!
+// Eight lanes share a grid point (each takes every eighth bin of the ~77 in reach) and combine
+// with shuffles in a fixed order: 625 blocks instead of 79, a 10-step dependent chain instead of 77.
+constexpr int KE_LANES = 8;
 __global__ void __launch_bounds__(256)
 kde_eval_bins_kernel(const double* __restrict__ tables, int nb, double lo, double w, double h,
                      double grid_lo, double grid_step, int grid_pts, double* __restrict__ grid) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= grid_pts) return;
-  const double g = grid_lo + (double)j * grid_step;
-  const double reach = KDE_Z * h + 0.5 * w;
-  int b0 = (int)floor((g - reach - lo) / w), b1 = (int)floor((g + reach - lo) / w);
-  b0 = b0 < 0 ? 0 : b0;
-  b1 = b1 >= nb ? nb - 1 : b1;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = tid / KE_LANES, part = tid % KE_LANES;
   double acc = 0.0;
-  for (int b = b0; b <= b1; ++b) {
-    const double* T = tables + (size_t)b * KM_WORDS;
-    const double c = T[0];
-    if (c == 0.0) continue;
-    const double z = (g - (lo + ((double)b + 0.5) * w)) / h;
-    const double z2 = z * z;
-    const double he2 = z2 - 1.0, he3 = z * (z2 - 3.0), he4 = z2 * (z2 - 6.0) + 3.0,
-                 he5 = z * (z2 * (z2 - 10.0) + 15.0);
-    const double series = c + z * T[1] + he2 * T[2] * (1.0 / 2.0) + he3 * T[3] * (1.0 / 6.0) +
-                          he4 * T[4] * (1.0 / 24.0) + he5 * T[5] * (1.0 / 120.0);
-    acc += exp(-0.5 * z2) * series;
+  if (j < grid_pts) {
+    const double g = grid_lo + (double)j * grid_step;
+    const double reach = KDE_Z * h + 0.5 * w;
+    int b0 = (int)floor((g - reach - lo) / w), b1 = (int)floor((g + reach - lo) / w);
+    b0 = b0 < 0 ? 0 : b0;
+    b1 = b1 >= nb ? nb - 1 : b1;
+    for (int b = b0 + part; b <= b1; b += KE_LANES) {
+      const double* T = tables + (size_t)b * KM_WORDS;
+      const double c = T[0];
+      if (c == 0.0) continue;
+      const double z = (g - (lo + ((double)b + 0.5) * w)) / h;
+      const double z2 = z * z;
+      const double he2 = z2 - 1.0, he3 = z * (z2 - 3.0), he4 = z2 * (z2 - 6.0) + 3.0,
+                   he5 = z * (z2 * (z2 - 10.0) + 15.0);
+      const double series = c + z * T[1] + he2 * T[2] * (1.0 / 2.0) + he3 * T[3] * (1.0 / 6.0) +
+                            he4 * T[4] * (1.0 / 24.0) + he5 * T[5] * (1.0 / 120.0);
+      acc += exp(-0.5 * z2) * series;
+    }
   }
-  grid[j] += acc;
+#pragma unroll
+  for (int o = KE_LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, KE_LANES);
+  if (j < grid_pts && part == 0) grid[j] += acc;
 }
 
 // number of bins the moment method needs for one sample on [lo, hi], or 0 if it does not apply
@@ -303,7 +330,7 @@ int km_accumulate(const float* x, int64_t n, double lo, double hi, double h, int
   kde_moments_kernel<<<(unsigned)blocks, KM_THREADS, (size_t)nb * KM_WORDS * sizeof(uint32_t), st>>>(
       x, n, lo, 1.0 / w, nb, tables);
   UQ_LAUNCH_CHECK();
-  kde_eval_bins_kernel<<<(grid_pts + 255) / 256, 256, 0, st>>>(
+  kde_eval_bins_kernel<<<(grid_pts * KE_LANES + 255) / 256, 256, 0, st>>>(
       tables, nb, lo, w, h, lo, (hi - lo) / (double)(grid_pts - 1), grid_pts, grid);
   UQ_LAUNCH_CHECK();
   return UQ_OK;

@@ -22,21 +22,45 @@ __device__ __forceinline__ uint32_t key_bin(float x) {
   return k >> 18;
 }
 
-// per-block (min, max, sum(x - x0), sum((x - x0)^2)) in float64, x0 = x[0]
+// per-block (min, max, sum(x - x0), sum((x - x0)^2)) in float64, x0 = x[0].  float4 loads, four
+// in flight per thread (the scalar-load version ran at 2.1 TB/s: 4 KB in flight per SM); min / max
+// stay in float32 (exact), only the two sums are float64.
 __global__ void __launch_bounds__(256)
 shard_stats_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ partials) {
   __shared__ double sh[4][8];
-  const double x0 = (double)x[0];
-  double s1 = 0.0, s2 = 0.0, mn = x0, mx = x0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const double v = (double)__ldg(x + i);
-    const double d = v - x0;
+  const float x0f = x[0];
+  const double x0 = (double)x0f;
+  double s1 = 0.0, s2 = 0.0;
+  float mnf = x0f, mxf = x0f;
+  auto add = [&](float v) {
+    const double d = (double)v - x0;
     s1 += d;
-    s2 += d * d;
-    mn = fmin(mn, v);
-    mx = fmax(mx, v);
+    s2 = fma(d, d, s2);
+    mnf = fminf(mnf, v);
+    mxf = fmaxf(mxf, v);
+  };
+  const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
+  const int64_t n4 = (n - head) / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  if (gtid < head) add(__ldg(x + gtid));
+  int64_t i = gtid;
+  for (; i + 3 * gstride < n4; i += 4 * gstride) {
+    const float4 a0 = __ldg(x4 + i), a1 = __ldg(x4 + i + gstride);
+    const float4 a2 = __ldg(x4 + i + 2 * gstride), a3 = __ldg(x4 + i + 3 * gstride);
+    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
+    add(a1.x); add(a1.y); add(a1.z); add(a1.w);
+    add(a2.x); add(a2.y); add(a2.z); add(a2.w);
+    add(a3.x); add(a3.y); add(a3.z); add(a3.w);
   }
+  for (; i < n4; i += gstride) {
+    const float4 a0 = __ldg(x4 + i);
+    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
+  }
+  const int64_t tail0 = head + 4 * n4;
+  if (tail0 + gtid < n) add(__ldg(x + tail0 + gtid));
+  double mn = (double)mnf, mx = (double)mxf;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s1 += __shfl_down_sync(0xffffffffu, s1, o);
