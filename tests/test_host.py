@@ -414,3 +414,10 @@ def test_custom_ops_are_registered_for_cuda_only():
         ns.kde_jsd(torch.rand(8), torch.rand(8), 100)
     with pytest.raises(NotImplementedError):
         ns.moments_merge(torch.rand(2, 8), torch.rand(2, 8), [1.0, 1.0])
+
+
+def test_graft_entry_build_runs_on_cpu():
+    """The driver's "does it build" check: compiles (or reuses) the library, loads it through the
+    C ABI, checks the ABI version against the binding, imports the package and the oracle."""
+    import __graft_entry__ as entry
+    entry.build()
