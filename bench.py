@@ -262,6 +262,47 @@ def measured_peaks():
             "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
+def metric_kernel_lines(dev, peaks, n=50_000_000, steps=5):
+    """BASELINE.json's metric also asks for the metric kernels' GB/s: ID-vs-OOD Wasserstein and
+    KDE Jensen-Shannon over 50 M + 50 M synthetic uncertainty scores (configs[4] on one GPU),
+    resident in HBM, timed with CUDA events around the public op; GB/s = the algorithmic 4 B per
+    value over the call time, next to the measured HBM peak."""
+    from nnueehcs_b200 import ops
+
+    def gamma(shape, scale, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        u = torch.rand((shape, n), generator=g, device=dev).clamp_min_(1e-12)
+        return (-torch.log(u)).sum(0).mul_(scale).contiguous()
+
+    u, v = gamma(2, 0.05, 0), gamma(3, 0.08, 1)
+    hbm = peaks.get("hbm")
+    out = {}
+    for name, fn, info in (
+            ("wasserstein_1d", lambda: ops.wasserstein_1d(u, v), lambda: ops.wasserstein_1d_info(u, v)),
+            ("kde_jsd", lambda: ops.kde_jsd(u, v, 20000), lambda: ops.kde_jsd_info(u, v, 20000))):
+        for _ in range(3):
+            val = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ops.reset_launch_count()
+        e0.record()
+        for _ in range(steps):
+            val = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = ops.launch_count() // steps
+        ms = e0.elapsed_time(e1) / steps
+        gbs = 2 * n * 4 / (ms * 1e-3) / 1e9
+        out[name] = {"values": 2 * n, "ms": ms, "values_per_s": 2 * n / (ms * 1e-3),
+                     "algorithmic_GBps": gbs, "hbm_peak_GBps": hbm,
+                     "frac_of_hbm_peak": gbs / hbm if hbm else None, "result": val,
+                     "method": info()["method"], "gpu_launches_per_call": int(launches),
+                     "data": "synthetic Gamma(2, 0.05) vs Gamma(3, 0.08) scores, float32, in HBM"}
+    del u, v
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     from nnueehcs_b200 import ops
@@ -426,6 +467,8 @@ def run_gpu(args):
                          "frac_of_sustained": achieved / peaks["sustained"]},
             "wall_s_timed_region": wall,
         }
+        if world == 1 and wl == DEFAULT_WORKLOAD and not args.no_metric_kernels:
+            line["metric_kernels"] = metric_kernel_lines(dev, peaks)
         if world == 1 and not args.no_cpu_baseline:
             sample_n = cpu_sample_size(wl)
             cpu_model = build_model(wl)
@@ -451,6 +494,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-metric-kernels", action="store_true",
+                    help="skip the Wasserstein / KDE-JS kernel timings added to the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
