@@ -92,6 +92,62 @@ class KShard:
         return ops.moments_merge(means.contiguous(), m2s.contiguous(), counts)
 
 
+class NShard:
+    """Sample-axis sharding of the fused forward (the alternative to the
+    K axis, for K smaller than the number of GPUs).  Every rank holds the same ``x`` and the whole
+    model, runs ALL members on its contiguous slice of the rows, and one all-gather of the
+    ``[mean | second output]`` rows rebuilds the full result on every rank -- no moment algebra.
+    Set ``model.uq_shard = NShard()`` on a mirror wrapper, exactly like ``KShard``.
+
+    Native MC-dropout masks are drawn per (pass, layer, row of the CALL), so each rank shifts the
+    Philox offset by its rank to keep the slices' streams distinct; the bits therefore depend on the
+    sharding (they do not under ``KShard``).  Injected masks are indexed by global row and are not
+    supported here."""
+
+    def __init__(self, group: Optional["dist.ProcessGroup"] = None):
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("NShard needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def rows(self, n: int, rank: Optional[int] = None) -> Tuple[int, int]:
+        return split_range(n, self.world, self.rank if rank is None else rank)
+
+    def gather_rows(self, local: torch.Tensor, n: int) -> torch.Tensor:
+        """``local``: this rank's ``[count, ...]`` rows -> the full ``[n, ...]`` tensor (rank order)."""
+        cap = (n + self.world - 1) // self.world
+        pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        flat = torch.empty(self.world * pad.numel(), dtype=pad.dtype, device=pad.device)
+        if pad.is_cuda:
+            dist.all_gather_into_tensor(flat, pad.reshape(-1), group=self.group)
+        else:  # gloo (CPU tests)
+            dist.all_gather(list(flat.view(self.world, -1).unbind(0)), pad.reshape(-1),
+                            group=self.group)
+        parts = flat.view((self.world,) + tuple(pad.shape))
+        return torch.cat([parts[r, :self.rows(n, r)[1]] for r in range(self.world)], dim=0)
+
+    def forward(self, packed: "ops.PackedModel", x: torch.Tensor, mode: str, *, total_members: int,
+                precision: str = "fp32", **kw) -> Tuple[torch.Tensor, torch.Tensor]:
+        if kw.get("masks") is not None:
+            raise ValueError("NShard: injected dropout masks are indexed by global row; use KShard")
+        n = x.shape[0]
+        begin, count = self.rows(n)
+        if mode == "mc_dropout":
+            kw["offset"] = int(kw.get("offset", 0)) + self.rank
+        if kw.get("score_floor") is not None:
+            kw["score_floor"] = kw["score_floor"][begin:begin + count]
+        if count > 0:
+            first, second = packed.forward(x[begin:begin + count], mode,
+                                           total_members=total_members, precision=precision, **kw)
+            local = torch.stack([first, second], dim=1)              # [count, 2, d_out]
+        else:
+            local = torch.zeros((0, 2, packed.d_out), dtype=torch.float32, device=x.device)
+        full = self.gather_rows(local, n)
+        return full[:, 0].contiguous(), full[:, 1].contiguous()
+
+
 # ------------------------------------------------------------------------------------------------
 # Sharded distribution metrics (BASELINE.json configs[4]: 100 M scores over 8 GPUs)
 # ------------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from nnueehcs_b200.distributed import KShard, split_range
+from nnueehcs_b200.distributed import KShard, NShard, split_range
 from oracle import uq_oracle
 from tests.util import load_golden, nets_from_golden
 
@@ -82,3 +82,51 @@ def test_gloo_world2_exchange_and_merge(tmp_path):
     b = torch.load(tmp_path / "rank1.pt")
     # every rank ends with the same merged result
     assert torch.equal(a["mean"], b["mean"]) and torch.equal(a["std"], b["std"])
+
+
+class _OraclePacked:
+    """Stand-in for ops.PackedModel on CPU: the oracle's ensemble forward (test infrastructure)."""
+
+    def __init__(self, nets):
+        self.nets, self.d_out, self.calls = nets, 1, []
+
+    def forward(self, x, mode, *, total_members, precision="fp32", **kw):
+        self.calls.append((tuple(x.shape), mode, total_members, dict(kw)))
+        return uq_oracle.ensemble_forward(self.nets, x)
+
+
+def _nshard_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = load_golden("ensemble_bn.npz")
+        k = int(g["k"])
+        packed = _OraclePacked(nets_from_golden(g, k))
+        x = torch.from_numpy(g["x"])[:157]            # 157 rows over 2 ranks -> 79 + 78
+        shard = NShard()
+        assert shard.rows(157) == split_range(157, world, rank)
+        mean, std = shard.forward(packed, x, "ensemble", total_members=k)
+        assert packed.calls[0][0] == (shard.rows(157)[1], x.shape[1])   # only its own rows ran
+        ref_mean, ref_std = uq_oracle.ensemble_forward(packed.nets, x)
+        assert torch.allclose(mean, ref_mean, rtol=0, atol=1e-7)
+        assert torch.allclose(std, ref_std, rtol=0, atol=1e-7)
+        # MC dropout: the Philox offset is shifted by the rank; injected masks are refused
+        shard.forward(packed, x, "mc_dropout", total_members=k, offset=10)
+        assert packed.calls[-1][3]["offset"] == 10 + rank
+        with pytest.raises(ValueError, match="indexed by global row"):
+            shard.forward(packed, x, "mc_dropout", total_members=k, masks=torch.zeros(1))
+        # fewer rows than ranks: one rank holds nothing and still takes part in the gather
+        tiny_mean, _ = shard.forward(packed, x[:1], "ensemble", total_members=k)
+        assert tiny_mean.shape == (1, 1) and torch.allclose(tiny_mean, ref_mean[:1], atol=1e-7)
+        torch.save({"mean": mean}, os.path.join(out_dir, f"nrank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_sample_axis_shard(tmp_path):
+    mp.spawn(_nshard_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(tmp_path / "nrank0.pt")
+    b = torch.load(tmp_path / "nrank1.pt")
+    assert torch.equal(a["mean"], b["mean"])

@@ -12,6 +12,8 @@ bf16 mode : stated tolerance ``|got-ref| <= 3e-2 * max|ref|`` for the mean and
             ``<= 6e-2 * max|ref_std| + 3e-2 * max|ref_mean|`` for the std (bf16 has 8 mantissa bits;
             activations and weights are rounded once per layer).  Measured errors are printed.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -598,3 +600,37 @@ def test_narrow_kernel_many_passes_member_splits():
     mm, ss = ops.moments_merge(torch.stack([lo[0], hi[0]]), torch.stack([lo[1], hi[1]]), [24, 40])
     assert float((mm - a[0]).abs().max()) <= 1e-5 * float(a[0].abs().max())
     assert float((ss - a[1]).abs().max()) <= 1e-3 * float(a[1].abs().max())
+
+
+def test_shard_objects_on_a_single_rank_nccl_group():
+    """World-size-1 NCCL group: KShard and NShard degenerate to the plain forward (the N > 1 logic is
+    covered by the gloo tests and by bench.py --gpus N / tools/dist_metrics_check.py on real GPUs)."""
+    import socket
+    import torch.distributed as dist
+    from nnueehcs_b200.distributed import KShard, NShard
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=DEV)
+    try:
+        g = load_golden("ensemble_bn.npz")
+        k = int(g["k"])
+        model = EnsembleModelBuilder(golden_arch(g), {"num_models": k}).build()
+        for m, ref in zip(model.models, nets_from_golden(g, k)):
+            m.load_state_dict(ref.state_dict())
+        model.to(DEV).eval()
+        x = torch.from_numpy(g["x"]).to(DEV)
+        with torch.no_grad():
+            plain = model(x, return_ue=True)
+            for shard in (KShard(), NShard()):
+                model.uq_shard = shard
+                got = model(x, return_ue=True)
+                assert_close_ref(got[0], plain[0], 1e-6, what=type(shard).__name__ + " mean")
+                assert_close_ref(got[1], plain[1], 1e-5, scale_ref=plain[0],
+                                 what=type(shard).__name__ + " std")
+        model.uq_shard = None
+        assert_close_ref(plain[0], g["mean"], RTOL32, what="mean")
+    finally:
+        if created:
+            dist.destroy_process_group()
