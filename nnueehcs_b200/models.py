@@ -22,7 +22,6 @@ from __future__ import annotations
 import copy
 import os
 import sys
-import warnings
 from typing import Optional, Sequence
 
 import torch

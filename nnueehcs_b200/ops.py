@@ -217,7 +217,6 @@ def philox_keep_masks(n: int, widths: Sequence[int], total_members: int, dropout
 def moments_merge(means: torch.Tensor, m2s: torch.Tensor, counts: Sequence[float]
                   ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Chan-merge ``[S, ...]`` shard moments into (mean, unbiased std) of shape ``[...]``."""
-    lib = _lib.load()
     _require_cuda(means, "means")
     _require_cuda(m2s, "m2s")
     means = means.contiguous()
