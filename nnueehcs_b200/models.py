@@ -383,8 +383,8 @@ class PAGERMLP(DeltaUQMLP):
     swapped).  Both are one fused launch each; the second one takes the first one's ``std`` as a
     floor, so the ``[N, K]`` prediction matrix and the ``torch.maximum`` never materialise.
     PARITY-UNPINNED like ``DeltaUQMLP`` (the anchoring lives in the absent ``deltauq`` package).
-    The conformal pass runs every anchor on every rank (K is small); only the Delta-UQ pass
-    follows ``uq_shard``."""
+    With ``uq_shard = KShard()`` the anchors of both passes are split over the ranks; the conformal
+    shards combine with one element-wise max all-reduce."""
 
     def __init__(self, base_model, estimator='std', anchored_batch_size=None, num_anchors=5,
                  vectorize=False, **kwargs):
@@ -401,9 +401,22 @@ class PAGERMLP(DeltaUQMLP):
             raise ValueError("PAGER anchors_Y not set yet")
         mu, std = res
         packed = self._packed([self.net], x.device)
-        _, score = packed.forward(x, "pager", total_members=int(self.num_anchors),
-                                  precision=self.uq_precision, anchors=self._anchors.to(x.device),
-                                  targets=self._anchors_Y.to(x.device), score_floor=std)
+        k = int(self.num_anchors)
+        kw = dict(total_members=k, precision=self.uq_precision, anchors=self._anchors.to(x.device),
+                  targets=self._anchors_Y.to(x.device), score_floor=std.to(torch.float32))
+        shard = self.__dict__.get("uq_shard")
+        if shard is not None and hasattr(shard, "split"):
+            # anchors sharded over the ranks (KShard): the conformal score is a max over anchors,
+            # so the shards combine with ONE element-wise max all-reduce
+            import torch.distributed as dist
+            begin, count = shard.split(k)
+            if count > 0:
+                _, score = packed.forward(x, "pager", member_begin=begin, member_count=count, **kw)
+            else:
+                score = kw["score_floor"].clone()
+            dist.all_reduce(score, op=dist.ReduceOp.MAX, group=shard.group)
+        else:
+            _, score = packed.forward(x, "pager", **kw)
         return mu, score.to(std.dtype)
 
     def _score_samples(self, x, anchors_X, anchors_Y):

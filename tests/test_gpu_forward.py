@@ -631,6 +631,51 @@ def test_shard_objects_on_a_single_rank_nccl_group():
                                  what=type(shard).__name__ + " std")
         model.uq_shard = None
         assert_close_ref(plain[0], g["mean"], RTOL32, what="mean")
+        # PAGER with the anchors on the K-shard path (conformal shards combine with a max)
+        from nnueehcs_b200.model_builder import PAGERModelBuilder
+        pg = load_golden("pager_small.npz")
+        pk = int(pg["k"])
+        pm = PAGERModelBuilder(golden_arch(pg), {"estimator": "std", "num_anchors": pk}).build()
+        pm.net.load_state_dict(nets_from_golden(pg, 1, arch=delta_arch(golden_arch(pg)))[0].state_dict())
+        pm.anchors = torch.from_numpy(pg["anchors"])
+        pm.anchors_Y = torch.from_numpy(pg["anchors_y"])
+        pm.to(DEV).eval()
+        pm.uq_shard = KShard()
+        with torch.no_grad():
+            pred, score = pm(torch.from_numpy(pg["x"]).to(DEV), return_ue=True)
+        assert_close_ref(pred, pg["pred"], 2e-5, what="sharded pager pred")
+        assert_close_ref(score, pg["score"], 2e-5, scale_ref=pg["pred"], what="sharded pager score")
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pager_multi_output_and_anchor_prefix(precision):
+    """d_out = 3 (targets are indexed [anchor][output]; the multi-output epilogue of the pair
+    kernel), more anchor rows stored than num_anchors uses, and a K-range call that covers only the
+    last anchors (member_begin > 0: targets / per-anchor biases are indexed by the GLOBAL id)."""
+    torch.manual_seed(3)
+    net = build_network(delta_arch(_wide_arch(4, 128, 3, 3))).eval()
+    x, anchors, ys = torch.rand(500, 4), torch.rand(9, 4), torch.rand(9, 3) * 0.3
+    k = 6
+    packed = ops.PackedModel([net], DEV)
+    _, conf = packed.forward(x.to(DEV), "pager", total_members=k, precision=precision,
+                             anchors=anchors.to(DEV), targets=ys.to(DEV))
+    with torch.no_grad():
+        cols = [uq_oracle.sequential_forward(net, torch.cat([anchors[j:j + 1] - x, x], dim=1))
+                for j in range(k)]
+    p = torch.stack(cols)                                            # [K, N, 3]
+    ref = (p - ys[:k].unsqueeze(1)).abs().max(dim=0)[0]
+    tol = RTOL32 if precision == "fp32" else 3e-2
+    scale = float(p.abs().max()) + float(ys.abs().max())
+    assert float((conf.cpu() - ref).abs().max()) <= tol * scale
+    # anchors [2, 6) only: max over the last four anchors
+    _, tail = packed.forward(x.to(DEV), "pager", total_members=k, member_begin=2, member_count=4,
+                             precision=precision, anchors=anchors.to(DEV), targets=ys.to(DEV))
+    ref_tail = (p[2:] - ys[2:k].unsqueeze(1)).abs().max(dim=0)[0]
+    assert float((tail.cpu() - ref_tail).abs().max()) <= tol * scale
+    # ... so K-shards of the conformal score combine with an element-wise max
+    _, head = packed.forward(x.to(DEV), "pager", total_members=k, member_begin=0, member_count=2,
+                             precision=precision, anchors=anchors.to(DEV), targets=ys.to(DEV))
+    assert torch.equal(torch.maximum(head, tail), conf)
