@@ -124,6 +124,8 @@ int wasserstein_ambiguous(const float* u_amb, int64_t nu_amb, const float* v_amb
 int wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv, int64_t u_below,
                          int64_t v_below, int64_t nu_total, int64_t nv_total, double* out_host,
                          void* ws, size_t ws_bytes, cudaStream_t st);
+int sample_stats_multi(const float* const* xs, const int64_t* ns, int count, double* out_host,
+                       void* workspace, cudaStream_t st);
 size_t kde_grid_workspace_bytes(int64_t n);
 int kde_grid_accumulate(const float* x, int64_t n, double lo, double hi, double bandwidth,
                         int grid_pts, double* grid, void* ws, size_t ws_bytes, cudaStream_t st);

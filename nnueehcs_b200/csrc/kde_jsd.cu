@@ -388,7 +388,7 @@ WsLayout layout(int64_t nu, int64_t nv, int grid_pts) {
   L.pdf = o; o += al(sizeof(double) * 2 * (size_t)grid_pts);
   L.result = o; o += 256;
   L.tables = o; o += al(sizeof(double) * KM_MAX_BINS * KM_WORDS);
-  L.stats = o; o += al(uq_sample_stats_workspace_bytes());
+  L.stats = o; o += al(2 * uq_sample_stats_workspace_bytes());
   L.total = o;
   return L;
 }
@@ -413,11 +413,12 @@ int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts
   if (method_used_host) *method_used_host = UQ_KDE_WINDOW;
   if (method != UQ_KDE_WINDOW && nu >= 2 && nv >= 2) {
     // scipy.stats.gaussian_kde: h = sqrt(unbiased variance) * n^(-1/5); grid = linspace(min, max)
-    double su[4], sv[4];
-    int rc = uq_sample_stats(u, nu, su, b + L.stats, uq_sample_stats_workspace_bytes(), st);
+    double stats[8];
+    const float* xs[2] = {u, v};
+    const int64_t ns[2] = {nu, nv};
+    int rc = sample_stats_multi(xs, ns, 2, stats, b + L.stats, st);  // one synchronisation
     if (rc != UQ_OK) return rc;
-    rc = uq_sample_stats(v, nv, sv, b + L.stats, uq_sample_stats_workspace_bytes(), st);
-    if (rc != UQ_OK) return rc;
+    const double *su = stats, *sv = stats + 4;
     const double hu = sqrt(su[3] / (double)(nu - 1)) * pow((double)nu, -0.2);
     const double hv = sqrt(sv[3] / (double)(nv - 1)) * pow((double)nv, -0.2);
     const double lo = su[0] < sv[0] ? su[0] : sv[0], hi = su[1] > sv[1] ? su[1] : sv[1];

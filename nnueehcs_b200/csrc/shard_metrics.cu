@@ -134,6 +134,40 @@ partition_kernel(const float* __restrict__ x, int64_t n, const uint8_t* __restri
 }
 
 }  // namespace
+
+// (min, max, mean, M2) of one or two device samples with ONE stream synchronisation.
+// out_host: 4 doubles per sample; workspace: uq_sample_stats_workspace_bytes() per sample.
+int sample_stats_multi(const float* const* xs, const int64_t* ns, int count, double* out_host,
+                       void* workspace, cudaStream_t st) {
+  static thread_local double h[2][4 * STAT_BLOCKS];
+  float x0f[2] = {0.f, 0.f};
+  double* partials = static_cast<double*>(workspace);
+  for (int s = 0; s < count; ++s) {
+    shard_stats_kernel<<<STAT_BLOCKS, 256, 0, st>>>(xs[s], ns[s], partials + (size_t)s * 4 * STAT_BLOCKS);
+    UQ_LAUNCH_CHECK();
+  }
+  for (int s = 0; s < count; ++s) {
+    UQ_CUDA(cudaMemcpyAsync(h[s], partials + (size_t)s * 4 * STAT_BLOCKS, sizeof(h[s]),
+                            cudaMemcpyDeviceToHost, st));
+    UQ_CUDA(cudaMemcpyAsync(&x0f[s], xs[s], sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  UQ_CUDA(cudaStreamSynchronize(st));
+  for (int s = 0; s < count; ++s) {
+    double s1 = 0.0, s2 = 0.0, mn = h[s][2], mx = h[s][3];
+    for (int b = 0; b < STAT_BLOCKS; ++b) {
+      s1 += h[s][4 * b], s2 += h[s][4 * b + 1];
+      if (h[s][4 * b + 2] < mn) mn = h[s][4 * b + 2];
+      if (h[s][4 * b + 3] > mx) mx = h[s][4 * b + 3];
+    }
+    const double dn = (double)ns[s];
+    out_host[4 * s + 0] = mn;
+    out_host[4 * s + 1] = mx;
+    out_host[4 * s + 2] = (double)x0f[s] + s1 / dn;   // mean
+    out_host[4 * s + 3] = s2 - s1 * s1 / dn;          // M2 = sum (x - mean)^2
+  }
+  return UQ_OK;
+}
+
 }  // namespace uq
 
 using namespace uq;
@@ -149,27 +183,7 @@ int uq_sample_stats(const float* x, int64_t n, double* out_host, void* workspace
   UQ_REQUIRE(x && out_host && n >= 1, UQ_ERR_INVALID, "uq_sample_stats: NULL argument or n < 1");
   UQ_REQUIRE(workspace && workspace_bytes >= uq_sample_stats_workspace_bytes(), UQ_ERR_WORKSPACE,
              "uq_sample_stats: workspace too small");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double* partials = static_cast<double*>(workspace);
-  shard_stats_kernel<<<STAT_BLOCKS, 256, 0, st>>>(x, n, partials);
-  UQ_LAUNCH_CHECK();
-  static thread_local double h[4 * STAT_BLOCKS];
-  float x0f = 0.f;
-  UQ_CUDA(cudaMemcpyAsync(h, partials, sizeof(h), cudaMemcpyDeviceToHost, st));
-  UQ_CUDA(cudaMemcpyAsync(&x0f, x, sizeof(float), cudaMemcpyDeviceToHost, st));
-  UQ_CUDA(cudaStreamSynchronize(st));
-  double s1 = 0.0, s2 = 0.0, mn = h[2], mx = h[3];
-  for (int b = 0; b < STAT_BLOCKS; ++b) {
-    s1 += h[4 * b], s2 += h[4 * b + 1];
-    if (h[4 * b + 2] < mn) mn = h[4 * b + 2];
-    if (h[4 * b + 3] > mx) mx = h[4 * b + 3];
-  }
-  const double dn = (double)n;
-  out_host[0] = mn;
-  out_host[1] = mx;
-  out_host[2] = (double)x0f + s1 / dn;   // mean
-  out_host[3] = s2 - s1 * s1 / dn;       // M2 = sum (x - mean)^2
-  return UQ_OK;
+  return sample_stats_multi(&x, &n, 1, out_host, workspace, static_cast<cudaStream_t>(stream));
 }
 
 int uq_key_histogram(const float* x, int64_t n, uint32_t* hist, void* stream) {
