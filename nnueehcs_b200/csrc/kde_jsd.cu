@@ -336,41 +336,87 @@ int km_accumulate(const float* x, int64_t n, double lo, double hi, double h, int
   return UQ_OK;
 }
 
-// scipy.spatial.distance.jensenshannon on the two raw kernel-sum vectors
-__global__ void __launch_bounds__(1024)
-jsd_kernel(const double* __restrict__ pdf, int grid_pts, double* __restrict__ result) {
-  __shared__ double sh[2][1024];
+// scipy.spatial.distance.jensenshannon on the two raw kernel-sum vectors, two launches of
+// JSD_BLOCKS blocks (one block doing all 20 000 float64 logs took 34 us): per-block sums of each
+// vector, then per-block sums of p log(p/m) and q log(q/m) with the totals rebuilt from the
+// block sums in a fixed order; the last block to finish (ticket counter) adds the per-block terms
+// in a fixed order and writes the distance.  Deterministic.
+constexpr int JSD_BLOCKS = 80;
+constexpr int JSD_THREADS = 256;
+constexpr size_t JSD_SCRATCH_BYTES = sizeof(double) * 4 * JSD_BLOCKS + 256;  // sums | terms | ticket
+
+__device__ __forceinline__ void jsd_block_reduce2(double& a, double& b, double (*sh)[JSD_THREADS]) {
   const int t = threadIdx.x;
-  const double* pu = pdf;
-  const double* pv = pdf + grid_pts;
-  double a = 0.0, b = 0.0;
-  for (int j = t; j < grid_pts; j += 1024) a += pu[j], b += pv[j];
-  sh[0][t] = a; sh[1][t] = b;
+  sh[0][t] = a, sh[1][t] = b;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
+  for (int o = JSD_THREADS / 2; o > 0; o >>= 1) {
     if (t < o) sh[0][t] += sh[0][t + o], sh[1][t] += sh[1][t + o];
     __syncthreads();
   }
-  const double su = sh[0][0], sv = sh[1][0];
+  a = sh[0][0], b = sh[1][0];
   __syncthreads();
+}
+
+__global__ void __launch_bounds__(JSD_THREADS)
+jsd_sums_kernel(const double* __restrict__ pdf, int grid_pts, double* __restrict__ scratch) {
+  __shared__ double sh[2][JSD_THREADS];
+  const int per = (grid_pts + JSD_BLOCKS - 1) / JSD_BLOCKS;
+  const int j0 = blockIdx.x * per, j1 = min(grid_pts, j0 + per);
+  double a = 0.0, b = 0.0;
+  for (int j = j0 + threadIdx.x; j < j1; j += JSD_THREADS) a += pdf[j], b += pdf[grid_pts + j];
+  jsd_block_reduce2(a, b, sh);
+  if (threadIdx.x == 0) scratch[2 * blockIdx.x] = a, scratch[2 * blockIdx.x + 1] = b;
+}
+
+__global__ void __launch_bounds__(JSD_THREADS)
+jsd_terms_kernel(const double* __restrict__ pdf, int grid_pts, double* __restrict__ scratch,
+                 double* __restrict__ result) {
+  __shared__ double sh[2][JSD_THREADS];
+  __shared__ bool last;
+  double* terms = scratch + 2 * JSD_BLOCKS;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 4 * JSD_BLOCKS);
+  double su = 0.0, sv = 0.0;
+  for (int k = 0; k < JSD_BLOCKS; ++k) su += scratch[2 * k], sv += scratch[2 * k + 1];
+  const int per = (grid_pts + JSD_BLOCKS - 1) / JSD_BLOCKS;
+  const int j0 = blockIdx.x * per, j1 = min(grid_pts, j0 + per);
   double left = 0.0, right = 0.0;
-  for (int j = t; j < grid_pts; j += 1024) {
-    const double p = pu[j] / su, q = pv[j] / sv;
+  for (int j = j0 + threadIdx.x; j < j1; j += JSD_THREADS) {
+    const double p = pdf[j] / su, q = pdf[grid_pts + j] / sv;
     const double m = (p + q) / 2.0;
     if (p > 0.0 && m > 0.0) left += p * log(p / m);
     if (q > 0.0 && m > 0.0) right += q * log(q / m);
   }
-  sh[0][t] = left; sh[1][t] = right;
-  __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if (t < o) sh[0][t] += sh[0][t + o], sh[1][t] += sh[1][t + o];
-    __syncthreads();
+  jsd_block_reduce2(left, right, sh);
+  if (threadIdx.x == 0) {
+    terms[2 * blockIdx.x] = left, terms[2 * blockIdx.x + 1] = right;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == (unsigned int)(JSD_BLOCKS - 1);
   }
-  if (t == 0) *result = sqrt((sh[0][0] + sh[1][0]) / 2.0);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double l = 0.0, r = 0.0;
+    for (int k = 0; k < JSD_BLOCKS; ++k) {
+      l += reinterpret_cast<volatile double*>(terms)[2 * k];
+      r += reinterpret_cast<volatile double*>(terms)[2 * k + 1];
+    }
+    *result = sqrt((l + r) / 2.0);
+    *ticket = 0;  // ready for the next call on this scratch
+  }
+}
+
+// scratch: JSD_SCRATCH_BYTES, its ticket word zero on first use (zeroed here)
+int jsd_launch(const double* pdf, int grid_pts, double* scratch, double* result, cudaStream_t st) {
+  UQ_CUDA(cudaMemsetAsync(scratch + 4 * JSD_BLOCKS, 0, 8, st));
+  jsd_sums_kernel<<<JSD_BLOCKS, JSD_THREADS, 0, st>>>(pdf, grid_pts, scratch);
+  UQ_LAUNCH_CHECK();
+  jsd_terms_kernel<<<JSD_BLOCKS, JSD_THREADS, 0, st>>>(pdf, grid_pts, scratch, result);
+  UQ_LAUNCH_CHECK();
+  return UQ_OK;
 }
 
 struct WsLayout {
-  size_t u, ut, v, vt, scratch, partials, params, pdf, result, tables, stats, total;
+  size_t u, ut, v, vt, scratch, partials, params, pdf, result, tables, stats, jsd, total;
 };
 
 WsLayout layout(int64_t nu, int64_t nv, int grid_pts) {
@@ -389,6 +435,7 @@ WsLayout layout(int64_t nu, int64_t nv, int grid_pts) {
   L.result = o; o += 256;
   L.tables = o; o += al(sizeof(double) * KM_MAX_BINS * KM_WORDS);
   L.stats = o; o += al(2 * uq_sample_stats_workspace_bytes());
+  L.jsd = o; o += al(JSD_SCRATCH_BYTES);
   L.total = o;
   return L;
 }
@@ -432,8 +479,8 @@ int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts
       if (rc != UQ_OK) return rc;
       rc = km_accumulate(v, nv, lo, hi, hv, nbv, grid_pts, pdf + grid_pts, tables, st);
       if (rc != UQ_OK) return rc;
-      jsd_kernel<<<1, 1024, 0, st>>>(pdf, grid_pts, result);
-      UQ_LAUNCH_CHECK();
+      rc = jsd_launch(pdf, grid_pts, reinterpret_cast<double*>(b + L.jsd), result, st);
+      if (rc != UQ_OK) return rc;
       UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
       UQ_CUDA(cudaStreamSynchronize(st));
       if (method_used_host) *method_used_host = UQ_KDE_MOMENTS;
@@ -471,8 +518,8 @@ int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts
   kde_eval_kernel<<<(unsigned)(chunks_u + chunks_v), KDE_THREADS, 0, st>>>(
       su, nu, sv, nv, chunks_u, grid_pts, params, pdf);
   UQ_LAUNCH_CHECK();
-  jsd_kernel<<<1, 1024, 0, st>>>(pdf, grid_pts, result);
-  UQ_LAUNCH_CHECK();
+  rc = jsd_launch(pdf, grid_pts, reinterpret_cast<double*>(b + L.jsd), result, st);
+  if (rc != UQ_OK) return rc;
   UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
   UQ_CUDA(cudaStreamSynchronize(st));
   return UQ_OK;
@@ -527,14 +574,15 @@ int kde_grid_accumulate(const float* x, int64_t n, double lo, double hi, double 
 
 // Jensen-Shannon distance of two raw kernel-sum vectors ([2][grid_pts] float64, device)
 int jsd_from_grids(const double* grids, int grid_pts, double* out_host, cudaStream_t st) {
-  double* result = nullptr;
-  UQ_CUDA(cudaMallocAsync((void**)&result, sizeof(double), st));
-  jsd_kernel<<<1, 1024, 0, st>>>(grids, grid_pts, result);
-  count_launch();
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st);
-  cudaFreeAsync(result, st);
+  char* buf = nullptr;
+  UQ_CUDA(cudaMallocAsync((void**)&buf, JSD_SCRATCH_BYTES + 256, st));
+  double* result = reinterpret_cast<double*>(buf);
+  double* scratch = reinterpret_cast<double*>(buf + 256);
+  int rc = jsd_launch(grids, grid_pts, scratch, result, st);
+  cudaError_t e = cudaSuccess;
+  if (rc == UQ_OK) e = cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(buf, st);
+  if (rc != UQ_OK) return rc;
   if (e != cudaSuccess) return cuda_fail(e, "jsd_from_grids", __FILE__, __LINE__);
   UQ_CUDA(cudaStreamSynchronize(st));
   return UQ_OK;
