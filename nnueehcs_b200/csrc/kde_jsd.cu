@@ -219,11 +219,6 @@ kde_moments_kernel(const float* __restrict__ x, int64_t n, double lo, double inv
   for (int i = threadIdx.x; i < KM_WORDS * nb; i += KM_THREADS) km_sh[i] = 0;
   __syncthreads();
   constexpr float S1 = 4194304.f, S2 = S1 * 8.f, S3 = S2 * 8.f, S4 = S3 * 8.f, S5 = S4 * 8.f;
-  auto bump = [&](int m, int b, float e_m, float scale, float offset_scaled, double wrap_credit) {
-    const uint32_t term = km_fixed(fmaf(e_m, scale, offset_scaled));
-    const uint32_t old = atomicAdd(&mom[m * nb + b], term);
-    if (old + term < old) atomicAdd(&tables[(size_t)b * KM_WORDS + 1 + m], wrap_credit);
-  };
   auto add = [&](float v) {
     const double t = ((double)v - lo) * inv_w;                      // float64: bin offsets stay exact
     int b = (int)t;
@@ -231,13 +226,28 @@ kde_moments_kernel(const float* __restrict__ x, int64_t n, double lo, double inv
     float e = (float)((t - (double)b - 0.5) * (1.0 / KM_PER_H));
     e = fminf(fmaxf(e, -0.126f), 0.126f);      // |eps| <= 1/8 by construction; keeps every term in (0, 2^21)
     const float e2 = e * e;
-    atomicAdd(&cnt[b], 1u);
     // o_m * S_m = 2 * 8^-m * 2^19 * 8^m = 2^20 for every m
-    bump(0, b, e, S1, 1048576.f, 4294967296.0 / S1);
-    bump(1, b, e2, S2, 1048576.f, 4294967296.0 / S2);
-    bump(2, b, e2 * e, S3, 1048576.f, 4294967296.0 / S3);
-    bump(3, b, e2 * e2, S4, 1048576.f, 4294967296.0 / S4);
-    bump(4, b, e2 * e2 * e, S5, 1048576.f, 4294967296.0 / S5);
+    const uint32_t t1 = km_fixed(fmaf(e, S1, 1048576.f));
+    const uint32_t t2 = km_fixed(fmaf(e2, S2, 1048576.f));
+    const uint32_t t3 = km_fixed(fmaf(e2 * e, S3, 1048576.f));
+    const uint32_t t4 = km_fixed(fmaf(e2 * e2, S4, 1048576.f));
+    const uint32_t t5 = km_fixed(fmaf(e2 * e2 * e, S5, 1048576.f));
+    uint32_t* cell = mom + b;
+    atomicAdd(&cnt[b], 1u);
+    const uint32_t o1 = atomicAdd(cell, t1);
+    const uint32_t o2 = atomicAdd(cell + nb, t2);
+    const uint32_t o3 = atomicAdd(cell + 2 * nb, t3);
+    const uint32_t o4 = atomicAdd(cell + 3 * nb, t4);
+    const uint32_t o5 = atomicAdd(cell + 4 * nb, t5);
+    // a word wraps at most once per 2730 adds: one test for all five, the credits in the rare branch
+    if ((o1 + t1 < o1) | (o2 + t2 < o2) | (o3 + t3 < o3) | (o4 + t4 < o4) | (o5 + t5 < o5)) {
+      double* T = tables + (size_t)b * KM_WORDS + 1;
+      if (o1 + t1 < o1) atomicAdd(T + 0, 4294967296.0 / S1);
+      if (o2 + t2 < o2) atomicAdd(T + 1, 4294967296.0 / S2);
+      if (o3 + t3 < o3) atomicAdd(T + 2, 4294967296.0 / S3);
+      if (o4 + t4 < o4) atomicAdd(T + 3, 4294967296.0 / S4);
+      if (o5 + t5 < o5) atomicAdd(T + 4, 4294967296.0 / S5);
+    }
   };
   const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
   const int64_t n4 = (n - head) / 4;
