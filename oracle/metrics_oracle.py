@@ -445,3 +445,49 @@ def kde_neg_density(fit: np.ndarray, x: np.ndarray, bandwidth: float, block: int
         mx = e.max(axis=1, keepdims=True)
         out[i:i + block] = (mx[:, 0] + np.log(np.exp(e - mx).sum(axis=1))) + log_norm
     return -np.exp(out)
+
+
+# ----------------------------------------------------------------------------------------------
+# Moment form of the KDE sums (csrc/kde_jsd.cu, "moments" method).  Not part of the reference: a
+# numpy stand-in of the product's default path, itself checked against pdf_jsd above (scipy's
+# arithmetic).  Bins of width h / 4; a value at offset eps * h from its bin centre c contributes
+#   exp(-((g - c)/h - eps)^2 / 2) = K(z) exp(z eps - eps^2 / 2) = K(z) sum_m He_m(z) eps^m / m!
+# (z = (g - c)/h, He_m the probabilists' Hermite polynomials), so the sum over a bin's values needs
+# only the bin's count and sum eps^m, m = 1..5.
+# ----------------------------------------------------------------------------------------------
+
+KM_PER_H, KM_ORDER, KM_MAX_BINS = 4, 5, 8192
+
+
+def kde_sums_moments(x: np.ndarray, lo: float, hi: float, h: float, num_points: int) -> np.ndarray:
+    """Raw Gaussian kernel sums of ``x`` on ``linspace(lo, hi, num_points)`` via per-bin moments."""
+    import math
+    x = np.asarray(x, dtype=np.float64).ravel()
+    w = h / KM_PER_H
+    nb = int(np.floor((hi - lo) / w)) + 1
+    if nb > KM_MAX_BINS:
+        raise ValueError("the moment method needs (max - min) / (h / 4) <= 8192 bins")
+    b = np.clip(((x - lo) / w).astype(np.int64), 0, nb - 1)
+    eps = (x - (lo + (b + 0.5) * w)) / h
+    mom = np.stack([np.bincount(b, weights=eps ** m, minlength=nb) / math.factorial(m)
+                    for m in range(KM_ORDER + 1)])
+    centres = lo + (np.arange(nb) + 0.5) * w
+    grid = np.linspace(lo, hi, num_points)
+    out = np.zeros(num_points)
+    for j0 in range(0, num_points, 1024):
+        z = (grid[j0:j0 + 1024, None] - centres[None, :]) / h
+        he = [np.ones_like(z), z]
+        for m in range(2, KM_ORDER + 1):
+            he.append(z * he[-1] - (m - 1) * he[-2])
+        series = sum(he[m] * mom[m][None, :] for m in range(KM_ORDER + 1))
+        out[j0:j0 + 1024] = (np.where(np.abs(z) <= 9.0 + 0.5 / KM_PER_H, np.exp(-0.5 * z * z), 0.0)
+                             * series).sum(axis=1)
+    return out
+
+
+def pdf_jsd_moments(dist1: np.ndarray, dist2: np.ndarray, num_points: int = 20000) -> float:
+    a = np.asarray(dist1, dtype=np.float64).ravel()
+    c = np.asarray(dist2, dtype=np.float64).ravel()
+    lo, hi = float(min(a.min(), c.min())), float(max(a.max(), c.max()))
+    return jensenshannon(kde_sums_moments(a, lo, hi, scott_bandwidth(a), num_points),
+                         kde_sums_moments(c, lo, hi, scott_bandwidth(c), num_points))
