@@ -18,7 +18,6 @@ Behavioural notes checked against the reference:
 """
 from __future__ import annotations
 
-import collections
 import copy
 import types
 
@@ -28,82 +27,84 @@ from .models import (DeltaUQMLP, EnsembleModel, KDEMLPModel, KNNKDEMLPModel, MCD
                      MLPModel, PAGERMLP)
 
 
-class LayerBuilder(object):
-    """Resolve layer names against one or more namespaces (``torch.nn.__dict__`` by default)."""
+class LayerBuilder:
+    """Callable ``builder(name, *args, **kwargs) -> nn.Module`` that looks ``name`` up in an ordered
+    list of namespaces (``torch.nn.__dict__`` by default; earlier namespaces shadow later ones).
+    Same call / ``add_namespace`` interface as the reference's class of this name."""
 
     def __init__(self, *namespaces):
-        self._namespace = collections.ChainMap(*namespaces)
+        self._spaces = list(namespaces)
+
+    def _lookup(self, name):
+        for space in self._spaces:
+            if name in space:
+                return space[name]
+        raise KeyError(name)
 
     def __call__(self, name, *args, **kwargs):
         try:
-            return self._namespace[name](*args, **kwargs)
-        except Exception as e:
-            raise e.__class__(str(e), name, args, kwargs) from e
+            return self._lookup(name)(*args, **kwargs)
+        except Exception as err:  # keep the exception type, add what was being built
+            raise type(err)(str(err), name, args, kwargs) from err
 
     def add_namespace(self, namespace, index=-1):
-        if index >= 0:
-            maps = self._namespace.maps
-            maps.insert(index, namespace)
-            self._namespace = collections.ChainMap(*maps)
-        else:
-            self._namespace = self._namespace.new_child(namespace)
+        """``index >= 0``: insert at that search position; otherwise the new namespace is searched
+        first."""
+        self._spaces.insert(index if index >= 0 else 0, namespace)
 
 
 def build_network(architecture, builder=LayerBuilder(torch.nn.__dict__)):
     """``[{LayerName: {args: [...], **kwargs}}, ...]`` -> ``nn.Sequential`` (the YAML format of
-    examples/*/config.yaml; each list entry is a single-key dict)."""
-    layers = []
-    for block in copy.deepcopy(architecture):
-        assert len(block) == 1
-        (name, kwargs), = block.items()
-        kwargs = dict(kwargs or {})
-        args = kwargs.pop("args", [])
-        layers.append(builder(name, *args, **kwargs))
-    return torch.nn.Sequential(*layers)
+    examples/*/config.yaml; each list entry is a single-key dict).  The caller's description is
+    left untouched."""
+    modules = []
+    for entry in architecture:
+        if len(entry) != 1:
+            raise AssertionError(f"one layer per list entry expected, got keys {list(entry)}")
+        (layer_name, spec), = entry.items()
+        options = copy.deepcopy(spec) if spec else {}
+        positional = options.pop("args", [])
+        modules.append(builder(layer_name, *positional, **options))
+    return torch.nn.Sequential(*modules)
 
 
 class InfoGrabbBase:
+    """What the drivers ask about an architecture description: kind, depth, input width.  The
+    width lives in the first layer's first positional argument (``Linear`` / ``Conv2d``)."""
+    first_layer = None   # set by the two concrete grabbers
+
     def __init__(self, descr):
         self.descr = descr
 
     def num_layers(self):
         return len(self.descr)
 
-
-class CNNInfoGrabber(InfoGrabbBase):
-    def is_cnn(self):
-        return True
-
     def is_mlp(self):
-        return False
+        return self.first_layer == 'Linear'
+
+    def is_cnn(self):
+        return self.first_layer == 'Conv2d'
 
     def num_inputs(self):
-        return self.descr[0]['Conv2d']['args'][0]
+        return self.descr[0][self.first_layer]['args'][0]
 
     def set_num_inputs(self, num_inputs):
-        self.descr[0]['Conv2d']['args'][0] = num_inputs
+        self.descr[0][self.first_layer]['args'][0] = num_inputs
+
+
+class CNNInfoGrabber(InfoGrabbBase):
+    first_layer = 'Conv2d'
 
 
 class MLPInfoGrabber(InfoGrabbBase):
-    def is_mlp(self):
-        return True
-
-    def is_cnn(self):
-        return False
-
-    def num_inputs(self):
-        return self.descr[0]['Linear']['args'][0]
-
-    def set_num_inputs(self, num_inputs):
-        self.descr[0]['Linear']['args'][0] = num_inputs
+    first_layer = 'Linear'
 
 
 class ModelInfo:
     @classmethod
     def get_info_grabber(cls, model_descr):
-        if 'Conv2d' in model_descr[0]:
-            return CNNInfoGrabber(model_descr)
-        return MLPInfoGrabber(model_descr)
+        grabber = CNNInfoGrabber if 'Conv2d' in model_descr[0] else MLPInfoGrabber
+        return grabber(model_descr)
 
 
 def _attach(info, **getters):
