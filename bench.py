@@ -469,7 +469,10 @@ def run_gpu(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "peak_source": peaks["source"], "kernel": kernel_name(widths, d_out)
-                         if precision == "bf16" else "sgemm_tn_kernel (fp32 CUDA cores)",
+                         if precision == "bf16" else
+                         ("uq_mlp_tcx_kernel (fp32 parity: scaled fp16 x 2 split on tcgen05, 3 MMAs "
+                          "per K step)" if packed.fp32_on_tensor_cores
+                          else "sgemm_tn_kernel (fp32 CUDA cores)"),
                          "flops_per_unit": F, "kernel_ms": kernel_ms,
                          "frac_of_sustained": achieved / peaks["sustained"]},
             "wall_s_timed_region": wall,

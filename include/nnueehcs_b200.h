@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UQ_ABI_VERSION 2
+#define UQ_ABI_VERSION 3
 
 /* status codes */
 #define UQ_OK 0
@@ -44,8 +44,13 @@ extern "C" {
                                 score_floor[n] when given (torch.maximum at models.py:389-390) */
 
 /* arithmetic the MLP stack runs in */
-#define UQ_PREC_FP32 0 /* CUDA-core FFMA, fp32 accumulate: the 1e-5 parity mode            */
+#define UQ_PREC_FP32 0 /* the 1e-5 parity mode.  Runs on the tensor cores as a scaled fp16 x 2 split
+                          (three tcgen05 kind::f16 MMAs per K step into fp32 TMEM accumulators,
+                          per-product error <= 7e-7) when uq_model_supports_fp32_tc(), else as
+                          UQ_PREC_FP32_FFMA                                                  */
 #define UQ_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the throughput mode */
+#define UQ_PREC_FP32_FFMA 2 /* CUDA-core FFMA, fp32 accumulate, one grouped SGEMM per layer: any
+                               layer shape; the cross-check of the two modes above           */
 
 /* what uq_forward writes */
 #define UQ_OUT_MEAN_STD 0 /* out0 = mean, out1 = unbiased std (what evaluation.py consumes)   */
@@ -113,6 +118,10 @@ int uq_model_create(uq_model_t** out, int32_t n_members, int32_t n_layers,
 int uq_model_destroy(uq_model_t* model);
 /* 1 if the bf16 tcgen05 path supports this model's shapes, else 0 (reason in uq_last_error) */
 int uq_model_supports_bf16(const uq_model_t* model);
+/* 1 if UQ_PREC_FP32 runs on the tensor cores for this model (equal hidden widths, multiple of 64,
+   <= 512, at most 21 network inputs), else 0 (reason in uq_last_error) and UQ_PREC_FP32 is the
+   CUDA-core path */
+int uq_model_supports_fp32_tc(const uq_model_t* model);
 
 /* -- the forward: K x net(x) -> stack -> mean(0), std(0), fused.
       x: [n, d_in] float32 row-major on device.  out0/out1: [n, d_out] float32 on device.

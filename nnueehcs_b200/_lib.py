@@ -10,10 +10,10 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 UQ_OK, UQ_ERR_INVALID, UQ_ERR_CUDA, UQ_ERR_UNSUPPORTED, UQ_ERR_WORKSPACE = 0, 1, 2, 3, 4
 MODE_ENSEMBLE, MODE_MC_DROPOUT, MODE_DELTA_UQ, MODE_PAGER = 0, 1, 2, 3
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP32_FFMA = 0, 1, 2
 OUT_MEAN_STD, OUT_MOMENTS = 0, 1
 WASSERSTEIN_AUTO, WASSERSTEIN_SORT, WASSERSTEIN_BINNED = 0, 1, 2
 KDE_AUTO, KDE_WINDOW, KDE_MOMENTS = 0, 1, 2
@@ -21,7 +21,7 @@ KDE_AUTO, KDE_WINDOW, KDE_MOMENTS = 0, 1, 2
 # every symbol include/nnueehcs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "uq_abi_version", "uq_last_error", "uq_launch_count", "uq_launch_count_reset",
-    "uq_model_create", "uq_model_destroy", "uq_model_supports_bf16",
+    "uq_model_create", "uq_model_destroy", "uq_model_supports_bf16", "uq_model_supports_fp32_tc",
     "uq_forward_workspace_bytes", "uq_forward", "uq_forward_host", "uq_moments_merge",
     "uq_philox_keep_masks", "uq_wasserstein_workspace_bytes", "uq_wasserstein_1d",
     "uq_wasserstein_1d_ex",
@@ -104,6 +104,8 @@ def load() -> C.CDLL:
     lib.uq_model_create.argtypes = [C.POINTER(vp), i32, i32, C.POINTER(LayerDesc), vp]
     lib.uq_model_destroy.argtypes = [vp]
     lib.uq_model_supports_bf16.argtypes = [vp]
+    lib.uq_model_supports_fp32_tc.argtypes = [vp]
+    lib.uq_model_supports_fp32_tc.restype = C.c_int
     lib.uq_forward_workspace_bytes.argtypes = [vp, i64, C.POINTER(ForwardArgs)]
     lib.uq_forward_workspace_bytes.restype = sz
     lib.uq_forward.argtypes = [vp, vp, i64, C.POINTER(ForwardArgs), vp, vp, vp, sz,

@@ -156,6 +156,8 @@ int uq_model_create(uq_model_t** out, int32_t n_members, int32_t n_layers,
   if (rc == UQ_OK) {
     tc_plan(m);
     if (m->tc.ok) rc = tc_pack(m, st);
+    tcx_plan(m);
+    if (rc == UQ_OK && m->tc.x_ok) rc = tcx_pack(m, st);
   }
   if (rc == UQ_OK) {
     // the caller may free its tensors once this returns
@@ -176,6 +178,13 @@ int uq_model_supports_bf16(const uq_model_t* model) {
   return model->tc.ok ? 1 : 0;
 }
 
+int uq_model_supports_fp32_tc(const uq_model_t* model) {
+  if (!model) return 0;
+  if (!model->tc.x_ok)
+    set_error("fp32 tensor-core split path unavailable: %s", model->tc.x_why_not.c_str());
+  return model->tc.x_ok ? 1 : 0;
+}
+
 static int check_args(const uq_model_t* m, const float* x, int64_t n, const uq_forward_args* a,
                       const float* out0, const float* out1) {
   UQ_REQUIRE(m && a, UQ_ERR_INVALID, "uq_forward: NULL model or args");
@@ -185,7 +194,9 @@ static int check_args(const uq_model_t* m, const float* x, int64_t n, const uq_f
              (long long)n);
   UQ_REQUIRE(a->mode >= UQ_MODE_ENSEMBLE && a->mode <= UQ_MODE_PAGER, UQ_ERR_INVALID,
              "uq_forward: unknown mode %d", a->mode);
-  UQ_REQUIRE(a->precision == UQ_PREC_FP32 || a->precision == UQ_PREC_BF16, UQ_ERR_INVALID,
+  UQ_REQUIRE(a->precision == UQ_PREC_FP32 || a->precision == UQ_PREC_BF16 ||
+                 a->precision == UQ_PREC_FP32_FFMA,
+             UQ_ERR_INVALID,
              "uq_forward: unknown precision %d", a->precision);
   UQ_REQUIRE(a->output == UQ_OUT_MEAN_STD || a->output == UQ_OUT_MOMENTS, UQ_ERR_INVALID,
              "uq_forward: unknown output kind %d", a->output);
@@ -222,8 +233,10 @@ static int check_args(const uq_model_t* m, const float* x, int64_t n, const uq_f
 size_t uq_forward_workspace_bytes(const uq_model_t* model, int64_t n,
                                   const uq_forward_args* args) {
   if (!model || !args || n < 1) return 0;
-  return args->precision == UQ_PREC_BF16 ? tc_workspace_bytes(model, n, args)
-                                         : fp32_workspace_bytes(model, n, args);
+  if (args->precision == UQ_PREC_BF16) return tc_workspace_bytes(model, n, args, false);
+  if (args->precision == UQ_PREC_FP32 && model->tc.x_ok)
+    return tc_workspace_bytes(model, n, args, true);
+  return fp32_workspace_bytes(model, n, args);
 }
 
 int uq_forward(const uq_model_t* model, const float* x, int64_t n, const uq_forward_args* args,
@@ -235,7 +248,10 @@ int uq_forward(const uq_model_t* model, const float* x, int64_t n, const uq_forw
   if (args->precision == UQ_PREC_BF16) {
     UQ_REQUIRE(model->tc.ok, UQ_ERR_UNSUPPORTED, "bf16 path unavailable for this model: %s",
                model->tc.why_not.c_str());
-    rc = tc_forward(model, x, n, args, out0, out1, workspace, workspace_bytes, st);
+    rc = tc_forward(model, x, n, args, out0, out1, workspace, workspace_bytes, st, false);
+  } else if (args->precision == UQ_PREC_FP32 && model->tc.x_ok) {
+    // the 1e-5 parity mode on the tensor cores (scaled fp16 x 2 split, mlp_tcx.cu)
+    rc = tc_forward(model, x, n, args, out0, out1, workspace, workspace_bytes, st, true);
   } else {
     rc = fp32_forward(model, x, n, args, out0, out1, workspace, workspace_bytes, st);
   }

@@ -73,6 +73,19 @@ struct TcPlan {
   // PAGER variant: W0 [a - x; x] + b0 = (W0b - W0a) x + (b0 + W0a a), so layer 0 holds the column
   // differences and the anchor again enters as a per-anchor bias
   __nv_bfloat16* image_pager = nullptr;
+  // fp32-parity split mode (mlp_tcx.cu): fp16 hi/lo images of the power-of-two scaled weights and
+  // the per-(member, layer) statistics the kernel's row scaling needs
+  bool x_ok = false;
+  std::string x_why_not;
+  int x_n_tile = 0;                // MMA N per stage
+  size_t x_stage_bytes = 0;        // [x_n_tile x 64] fp16
+  int x_stages_per_member = 0;
+  uint16_t* x_image = nullptr;        // [K][x_stages_per_member][x_stage_bytes]
+  uint16_t* x_image_delta = nullptr;  // layer 0 = the columns that multiply x (Delta-UQ)
+  uint16_t* x_image_pager = nullptr;  // layer 0 = column differences (PAGER)
+  float* x_stats = nullptr;           // [K][n_mma_layers][4]
+  float* x_stats_delta = nullptr;     // [1][n_mma_layers][4]
+  float* x_stats_pager = nullptr;
 };
 
 }  // namespace uq
@@ -98,9 +111,15 @@ int fp32_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_
 // bf16 tcgen05 path (mlp_tc.cu)
 void tc_plan(uq_model* m);  // fills m->tc.ok / geometry (no allocation)
 int tc_pack(uq_model* m, cudaStream_t st);
-size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a);
+// split = true: the fp32-parity split mode (mlp_tcx.cu) instead of the bf16 kernels
+size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a,
+                          bool split = false);
 int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_args* a,
-               float* out0, float* out1, void* ws, size_t ws_bytes, cudaStream_t st);
+               float* out0, float* out1, void* ws, size_t ws_bytes, cudaStream_t st,
+               bool split = false);
+// fp32-parity split mode, host side (mlp_tcx.cu)
+void tcx_plan(uq_model* m);  // fills m->tc.x_ok (needs tc_plan first)
+int tcx_pack(uq_model* m, cudaStream_t st);
 
 // moments (moments.cu)
 int moments_merge(const float* means, const float* m2s, const double* counts, int n_shards,

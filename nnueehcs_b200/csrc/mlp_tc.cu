@@ -264,10 +264,11 @@ int tc_pack(uq_model* m, cudaStream_t st) {
   return UQ_OK;
 }
 
-static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a) {
+static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a, bool split) {
   // sample rows one cluster (CTA pair) works on at a time
   const bool narrow = tc4_supported(m->tc.hidden, dout_pad(m->tc.d_out)) && !getenv("UQ_TC_NO_SLOTS");
-  const int64_t rows = m->tc.hidden > 512 ? TILE_M : narrow ? tc4_rows_per_unit() : 2 * TILE_M;
+  const int64_t rows = split ? tcx_rows_per_unit()
+                       : m->tc.hidden > 512 ? TILE_M : narrow ? tc4_rows_per_unit() : 2 * TILE_M;
   const int64_t units = (n + rows - 1) / rows;
   int splits = 1;
   if (a->output == UQ_OUT_MOMENTS) return 1;  // a K-shard hands raw moments to the caller
@@ -277,21 +278,41 @@ static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a)
   return splits;
 }
 
-size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a) {
-  const int splits = choose_splits(m, n, a);
+size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a, bool split) {
+  const int splits = choose_splits(m, n, a, split);
   size_t b = 256;  // error flag
   if (splits > 1) b += 2 * (size_t)splits * (size_t)n * m->d_out * sizeof(float) + 512;
-  if (a->mode == UQ_MODE_DELTA_UQ || a->mode == UQ_MODE_PAGER)  // per-anchor layer-0 bias [K][H]
+  if (a->mode == UQ_MODE_DELTA_UQ || a->mode == UQ_MODE_PAGER) {  // per-anchor layer-0 bias [K][H]
     b += (((size_t)a->total_members * m->tc.hidden * sizeof(float)) + 255) & ~(size_t)255;
+    if (split) b += (((size_t)a->total_members * sizeof(float)) + 255) & ~(size_t)255;  // max |bias0[k]|
+  }
   return b;
 }
 
+// max |v[k][:]| of every row k in [begin, begin + count): the per-anchor term of the split mode's
+// output bound (mlp_tcx.cu)
+__global__ void row_absmax_kernel(const float* __restrict__ v, int H, int begin,
+                                  float* __restrict__ out) {
+  const int k = begin + blockIdx.x;
+  float m = 0.f;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) m = fmaxf(m, fabsf(v[(int64_t)k * H + h]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    out[k] = m;
+  }
+}
+
 int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_args* a,
-               float* out0, float* out1, void* ws, size_t ws_bytes, cudaStream_t st) {
+               float* out0, float* out1, void* ws, size_t ws_bytes, cudaStream_t st, bool split) {
   const TcPlan& t = m->tc;
-  const size_t need = tc_workspace_bytes(m, n, a);
+  const size_t need = tc_workspace_bytes(m, n, a, split);
   UQ_REQUIRE(ws != nullptr && ws_bytes >= need, UQ_ERR_WORKSPACE,
-             "bf16 forward needs %zu workspace bytes, got %zu", need, ws_bytes);
+             "tensor-core forward needs %zu workspace bytes, got %zu", need, ws_bytes);
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.x = x;
@@ -302,7 +323,7 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.d_x = anchored ? m->d_in / 2 : m->d_in;
   p.mode = a->mode;
   p.n_tiles = (int)((n + TILE_M - 1) / TILE_M);
-  p.splits = choose_splits(m, n, a);
+  p.splits = choose_splits(m, n, a, split);
   p.member_begin = a->member_begin;
   p.member_count = a->member_count;
   p.total_members = a->total_members;
@@ -313,6 +334,13 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.stages_per_member = t.stages_per_member;
   p.shared_weights = (a->mode != UQ_MODE_ENSEMBLE) ? 1 : 0;
   p.image = reinterpret_cast<const uint8_t*>(t.image);
+  if (split) {  // fp32-parity split mode: its own image, three input segments always
+    p.K0 = ((3 * t.d_in + 15) / 16) * 16 + 16;   // + the all-zero step (see mlp_tcx.cu)
+    p.split_s = 3;
+    p.stages_per_member = t.x_stages_per_member;
+    p.image = reinterpret_cast<const uint8_t*>(t.x_image);
+    p.lstats = t.x_stats;
+  }
   const bool mc = (a->mode == UQ_MODE_MC_DROPOUT) && a->dropout_active;
   for (int l = 0; l < t.n_mma_layers; ++l) {
     p.bias[l] = m->layers[l].bias_folded;
@@ -364,6 +392,17 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
     p.d_in = dx;
     p.K0 = t.k0_delta;
     p.split_s = split_factor_of(dx);
+    if (split) {
+      float* bmax0 = reinterpret_cast<float*>(
+          wsb + off + ((((size_t)a->total_members * t.hidden * sizeof(float)) + 255) & ~(size_t)255));
+      row_absmax_kernel<<<a->member_count, 128, 0, st>>>(bias0, t.hidden, a->member_begin, bmax0);
+      UQ_LAUNCH_CHECK();
+      p.bmax0 = bmax0;
+      p.image = reinterpret_cast<const uint8_t*>(pager ? t.x_image_pager : t.x_image_delta);
+      p.lstats = pager ? t.x_stats_pager : t.x_stats_delta;
+      p.K0 = ((3 * dx + 15) / 16) * 16 + 16;
+      p.split_s = 3;
+    }
     p.mode = UQ_MODE_MC_DROPOUT;   // shared weights, members differ only in bias0
     p.anchors = nullptr;
   }
@@ -378,9 +417,10 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
 #endif
 
   const bool narrow = tc4_supported(t.hidden, dout_pad(t.d_out)) && !getenv("UQ_TC_NO_SLOTS");
-  const int rc = t.hidden > 512 ? tc3_launch(p, t.hidden, dout_pad(t.d_out), st)
-                 : narrow       ? tc4_launch(p, t.hidden, st)
-                                : tc2_launch(p, t.hidden, dout_pad(t.d_out), st);
+  const int rc = split           ? tcx_launch(p, t.hidden, dout_pad(t.d_out), st)
+                 : t.hidden > 512 ? tc3_launch(p, t.hidden, dout_pad(t.d_out), st)
+                 : narrow         ? tc4_launch(p, t.hidden, st)
+                                  : tc2_launch(p, t.hidden, dout_pad(t.d_out), st);
   if (rc != UQ_OK) return rc;
 #ifdef UQ_TC_TRACE
   if (d_trace) {  // bring-up aid: dump CTA 0's event timeline as CSV (role, kind, index, clock)

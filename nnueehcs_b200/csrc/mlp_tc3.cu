@@ -458,7 +458,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int j = 0; j < 3; ++j)
               y += ld_shared_f32(xb + (uint32_t)(((j * ROWS + row) * DOUT + o) * 4));
-            y += __ldg(bl + o);
+            y = fmaf(y, final_dropout_scale(p), __ldg(bl + o));
             if (p.last_relu) y = fmaxf(y, 0.f);
             member_fold(p, kg, o, y, inv_n, wf_mean[o], wf_m2[o]);
           }

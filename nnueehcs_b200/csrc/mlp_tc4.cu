@@ -433,7 +433,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           const float bl = __ldg(p.b_last + wslot);
 #pragma unroll
           for (int j = 0; j < OWN; ++j) {
-            float y = dot[j] + bl;
+            float y = fmaf(dot[j], final_dropout_scale(p), bl);
             if (p.last_relu) y = fmaxf(y, 0.f);
             member_fold(p, kg, 0, y, inv_n, wf_mean[j], wf_m2[j]);
           }

@@ -174,6 +174,13 @@ __device__ __forceinline__ void member_fold(const TcParams& p, int kg, int o, fl
   else m2 = fmaf(dlt, y - mean, m2);
 }
 
+// 1 / (1 - p) of a Dropout that sits between the last hidden activation and the final Linear (the
+// reference's MC-dropout builder never puts one there, model_builder.py:257-262, but a hand-built
+// nn.Sequential may): the final dot product sees masked, unscaled activations
+__device__ __forceinline__ float final_dropout_scale(const TcParams& p) {
+  return (((p.dropout_mask >> (p.L_mma - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
+}
+
 // what goes to out1 for one output element
 __device__ __forceinline__ float second_output(const TcParams& p, float m2, float n, int64_t idx) {
   if (p.targets) return p.score_floor ? fmaxf(m2, __ldg(p.score_floor + idx)) : m2;

@@ -46,6 +46,9 @@ struct TcParams {
   float* part_mean;                   // [splits][n*d_out] when splits > 1
   float* part_m2;
   unsigned int* error_flag;
+  // fp32-parity split mode (mlp_tcx.cu) only:
+  const float* lstats;                // [K or 1][L_mma][4] = {1/C, max_n |w_n|_2, max |bias|, C}
+  const float* bmax0;                 // [total_members] max |bias0[k]| (Delta-UQ / PAGER) or null
   unsigned long long* trace;          // -DUQ_TC_TRACE builds only: [3 roles][TRACE_LEN][2] of CTA 0
 };
 
@@ -61,5 +64,10 @@ bool tc3_supported(int hidden);
 int tc4_launch(const tc::TcParams& p, int hidden, cudaStream_t st);
 bool tc4_supported(int hidden, int dout_pad);
 int tc4_rows_per_unit();
+// mlp_tcx.cu: fp32-parity mode on the tensor cores (scaled fp16 x 2 split, 64 rows per CTA),
+// hidden widths 64 .. 512; its own weight image (tcx_pack)
+int tcx_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st);
+bool tcx_supported(int hidden);
+int tcx_rows_per_unit();
 
 }  // namespace uq

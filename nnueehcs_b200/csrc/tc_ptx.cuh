@@ -161,6 +161,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Same for A = B = F16 (the fp32-parity split mode, mlp_tcx.cu): format fields [7,10) / [10,13) = 0.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -15,7 +15,7 @@ from . import _lib
 from .extract import (Block, _f32_cuda, dropout_widths, split_blocks, structure_signature)
 
 _PREC = {"fp32": _lib.PREC_FP32, "float32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16,
-         "bfloat16": _lib.PREC_BF16}
+         "bfloat16": _lib.PREC_BF16, "fp32_ffma": _lib.PREC_FP32_FFMA}
 _MODE = {"ensemble": _lib.MODE_ENSEMBLE, "mc_dropout": _lib.MODE_MC_DROPOUT,
          "delta_uq": _lib.MODE_DELTA_UQ, "pager": _lib.MODE_PAGER}
 
@@ -73,6 +73,10 @@ class PackedModel:
         self._lib = lib
         self.supports_bf16 = bool(lib.uq_model_supports_bf16(handle))
         self.bf16_reason = "" if self.supports_bf16 else lib.uq_last_error().decode()
+        # True: precision='fp32' runs as the tensor-core split kernel; False: CUDA-core FFMA
+        self.fp32_on_tensor_cores = bool(lib.uq_model_supports_fp32_tc(handle))
+        self.fp32_tc_reason = ("" if self.fp32_on_tensor_cores
+                               else lib.uq_last_error().decode())
         del keep  # uq_model_create synchronised its stream: our staging copies may go
 
     @staticmethod
@@ -112,7 +116,8 @@ class PackedModel:
         a = _lib.ForwardArgs()
         a.mode = _MODE[mode]
         if precision not in _PREC:
-            raise ValueError(f"unknown precision {precision!r} (use 'fp32' or 'bf16')")
+            raise ValueError(f"unknown precision {precision!r} (use 'fp32', 'bf16' or "
+                             "'fp32_ffma')")
         a.precision = _PREC[precision]
         a.output = _lib.OUT_MOMENTS if output == "moments" else _lib.OUT_MEAN_STD
         a.member_begin = int(member_begin)
@@ -172,7 +177,8 @@ class PackedModel:
         elif targets is not None or score_floor is not None:
             raise ValueError("targets / score_floor only apply to mode='pager'")
         if precision not in _PREC:
-            raise ValueError(f"unknown precision {precision!r} (use 'fp32' or 'bf16')")
+            raise ValueError(f"unknown precision {precision!r} (use 'fp32', 'bf16' or "
+                             "'fp32_ffma')")
         count = int(total_members - member_begin if member_count is None else member_count)
         # the registered custom op (torch.ops.nnueehcs_b200.uq_forward, CUDA dispatch key only)
         return torch.ops.nnueehcs_b200.uq_forward(

@@ -333,7 +333,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     raw = ctypes.CDLL(path)
     for name in declared:
         assert hasattr(raw, name), f"{name} not exported"
-    assert lib.uq_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.uq_abi_version() == _lib.ABI_VERSION == 3
     lib.uq_launch_count_reset()
     assert lib.uq_launch_count() == 0
 
