@@ -3,12 +3,14 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
 
-Workload at N = 1 (``configs[1]`` of BASELINE.json): binomial-options deep ensemble,
+Workload (``configs[1]`` of BASELINE.json): binomial-options deep ensemble,
 16 members x (5 -> 512 -> 512 -> 512 -> 1, Linear+BatchNorm1d+ReLU), 1 M synthetic samples,
 bf16 tcgen05 mode.  One step = one ``model(x, return_ue=True)`` over the whole batch.
-At N > 1 (one rank per GPU, launched by torchrun) the member axis is sharded: every rank owns 16
-more members (weak scaling: 16 N members in total), reduces them to per-sample (mean, M2) in the
-fused kernel, and the shards are combined with one NCCL all-gather + Chan merge per step.
+At N > 1 (one rank per GPU, launched by torchrun) the SAME job is sharded over the member axis
+(strong scaling: 16 members in total, 16 / N per rank, each rank holding only its members'
+weights): every rank reduces its members to per-sample (mean, M2) in the fused kernel and the
+shards are combined reduce-scatter style over NCCL/NVLink (all-to-all of row slices, local Chan
+merge, all-gather of the finished (mean, std) slices; ``distributed.KShard.combine``).
 
 The JSON line follows the driver's contract: ``value`` is whole-job sample.members/s with inputs
 resident in HBM; ``e2e`` is the same metric through the wrapper API with pinned HOST buffers
@@ -82,13 +84,16 @@ def randomise_bn(net, seed):
             m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
 
 
-def build_model(workload, member_offset=0):
+def build_model(workload, member_offset=0, member_count=None):
     """Random-init model of the named architecture through the builder mirror (the reference's
-    own construction path, model_builder.py:219-275); BN running stats randomised (seed 1+i)."""
+    own construction path, model_builder.py:219-275); BN running stats randomised (seed 1+i).
+    ``member_offset`` / ``member_count``: the slice of an ensemble's members one rank owns (member
+    i is seeded 42 + i, as model_builder.py:229 does, whichever rank holds it)."""
     from nnueehcs_b200 import model_builder as mb
     mode, d_in, widths, d_out, k, n, p = WORKLOADS[workload]
     if mode == "ensemble":
         arch = mlp_arch(d_in, widths, d_out)
+        k = k if member_count is None else member_count
         builder = mb.EnsembleModelBuilder(arch, {"num_models": k})
         model = builder.build()
         if member_offset:  # other ranks own other members: seeds 42 + offset + i
@@ -181,7 +186,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "uq_sample_passes_per_sec", "value": rate,
         "unit": "sample*members/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(wl, 1, sample_note=f"{sample_n} of {n} samples per step"),
         "cpu_baseline": {"value": rate, "unit": "sample*members/s", "cores": cores,
@@ -198,9 +203,11 @@ def run_reference(args):
 def config_dict(wl, n_gpus, sample_note=None):
     mode, d_in, widths, d_out, k, n, p = WORKLOADS[wl]
     cfg = {"workload": wl, "mode": mode, "arch": f"{d_in}->" + "->".join(map(str, widths)) + f"->{d_out}",
-           "members_per_gpu": k, "members_total": k * n_gpus if mode == "ensemble" else k,
+           "members_per_gpu": k / n_gpus, "members_total": k,
            "samples": n, "dropout_p": p,
-           "parallelism": f"member-axis shards x{n_gpus}, one all-gather of (mean, M2) per step",
+           "parallelism": f"member-axis shards x{n_gpus} of the same job (strong scaling); per step "
+                          "one all-to-all of (mean, M2) row slices, a local Chan merge and an "
+                          "all-gather of the (mean, std) slices",
            "l2": f"inputs rotated over {N_ROTATE} device buffers (> 126 MB L2 with weights)"}
     if sample_note:
         cfg["cpu_sample"] = sample_note
@@ -310,10 +317,73 @@ def metric_kernel_lines(dev, peaks, n=50_000_000, steps=5):
     return out
 
 
+def parity_check(wl, packed_forward, x_dev, rows=4096):
+    """bench.py checks its own output: the first ``rows`` rows of a forward against the CPU oracle
+    (reference arithmetic), before anything is timed.  Returns the worst error of mean and std
+    in the test-suite's units: fp32 in units of the 1e-5 tolerance (<= 1 passes), bf16 as a
+    fraction of scale = max|mean| + max|std| (tests allow 1e-2)."""
+    from oracle import uq_oracle  # the checker, never the thing measured
+    mode, d_in, widths, d_out, k, n, p = WORKLOADS[wl]
+    if mode != "ensemble":
+        return None
+    cpu_model = build_model(wl)
+    xs = x_dev[:rows].cpu()
+    ref_mean, ref_std = uq_oracle.ensemble_forward(list(cpu_model.models), xs)
+    out = {}
+    for prec, (mean, std) in packed_forward.items():
+        mean, std = mean[:rows].double().cpu(), std[:rows].double().cpu()
+        ms, ss = float(ref_mean.abs().max()), float(ref_std.abs().max())
+        e_mean, e_std = (mean - ref_mean).abs(), (std - ref_std).abs()
+        if prec == "bf16":
+            out[prec] = {"max_err_of_scale": max(float(e_mean.max()), float(e_std.max())) / (ms + ss),
+                         "allowed": 1e-2}
+        else:
+            tol_m = 1e-5 * ref_mean.abs() + 1e-5 * ms
+            tol_s = 1e-5 * ref_std.abs() + 1e-5 * ms
+            out[prec] = {"max_err_in_units_of_1e-5_tolerance":
+                         max(float((e_mean / tol_m).max()), float((e_std / tol_s).max())),
+                         "allowed": 1.0}
+    out["rows"] = rows
+    out["oracle"] = "oracle.uq_oracle.ensemble_forward (torch CPU, reference arithmetic)"
+    return out
+
+
+def gpu_eager_baseline(wl, dev, x, steps=2):
+    """Informational: what a reference user has today on the same B200 -- the reference's own eager
+    fp32 loop (models.py:103-107: stack([m(x) for m in models]), mean(0), std(0)) run by stock
+    torch on the GPU (cuBLAS SGEMM, TF32 off).  Not the product path and not the target."""
+    mode, d_in, widths, d_out, k, n, p = WORKLOADS[wl]
+    if mode != "ensemble":
+        return None
+    model = build_model(wl).to(dev)
+    nets = list(model.models)
+
+    def fwd():
+        with torch.no_grad():
+            outputs = torch.stack([m(x) for m in nets])
+            return outputs.mean(0), outputs.std(0)
+
+    fwd()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fwd()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, nets
+    torch.cuda.empty_cache()
+    return {"value": n * k / (ms * 1e-3), "unit": "sample*members/s", "ms_per_step": ms,
+            "what": "stock torch eager fp32 EnsembleModel loop on the same GPU (cuBLAS; the "
+                    "reference's models.py:103-107 as its authors run it on A100s)",
+            "steps": steps}
+
+
 def run_gpu(args):
     import torch.distributed as dist
     from nnueehcs_b200 import ops
-    from nnueehcs_b200.distributed import KShard
+    from nnueehcs_b200.distributed import KShard, split_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -342,7 +412,12 @@ def run_gpu(args):
     wl = args.workload
     mode, d_in, widths, d_out, k, n, p = WORKLOADS[wl]
     precision = args.precision
-    model = build_model(wl, member_offset=rank * k if mode == "ensemble" else 0)
+    # strong scaling: the job (k members / passes / anchors over n samples) is fixed; an ensemble
+    # rank builds and packs only the members it owns
+    own_begin, own_count = split_range(k, world, rank) if mode == "ensemble" else (0, k)
+    if mode == "ensemble" and own_count == 0:
+        raise RuntimeError(f"{world} ranks but only {k} ensemble members")
+    model = build_model(wl, member_offset=own_begin, member_count=own_count)
     model.to(dev)
     model.eval()
     model.uq_precision = precision
@@ -353,7 +428,6 @@ def run_gpu(args):
     if precision == "bf16" and not packed.supports_bf16:
         raise RuntimeError(f"bf16 path unavailable: {packed.bf16_reason}")
 
-    xs_host = [synth_x(n, d_in, s).pin_memory() for s in range(2)]
     xs = [synth_x(n, d_in, s).to(dev) for s in range(N_ROTATE)]
     kw = {}
     if mode == "mc_dropout":
@@ -361,17 +435,34 @@ def run_gpu(args):
     if mode == "delta_uq":
         kw = dict(anchors=model.anchors.to(dev))
 
-    def step(x):
+    def step(x, prec=precision):
         if shard is not None and mode == "ensemble":
-            return shard.forward_owned(packed, x, mode, local_members=k, precision=precision, **kw)
+            return shard.forward_owned(packed, x, mode, local_members=own_count, precision=prec,
+                                       **kw)
         if shard is not None:
-            return shard.forward(packed, x, mode, total_members=k, precision=precision, **kw)
-        return packed.forward(x, mode, total_members=k, precision=precision, **kw)
+            return shard.forward(packed, x, mode, total_members=k, precision=prec, **kw)
+        return packed.forward(x, mode, total_members=k, precision=prec, **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- the bench verifies its own output before timing anything -----------------------------
+    parity = None
+    if mode == "ensemble":
+        outs = {precision: step(xs[0])}
+        if world == 1 and precision == "bf16" and packed.fp32_on_tensor_cores:
+            outs["fp32"] = step(xs[0], "fp32")
+        torch.cuda.synchronize()
+        if rank == 0:
+            parity = parity_check(wl, outs, xs[0])
+            for prec, r in parity.items():
+                if isinstance(r, dict):
+                    worst = [v for key, v in r.items() if key.startswith("max_err")][0]
+                    if not worst <= r["allowed"]:
+                        raise RuntimeError(f"bench.py parity check failed ({prec}): {r}")
+        del outs
 
     steps, warmup = args.steps, max(3, args.warmup)
     for i in range(warmup):
@@ -404,34 +495,72 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    units_per_step = n * k * (world if mode == "ensemble" else 1)
+    units_per_step = n * k          # the whole job, whatever the number of ranks
     value = units_per_step * steps / (total_ms * 1e-3)
 
-    # ---- end-to-end through the wrapper API with pinned HOST buffers ---------------------------
-    model.uq_shard = None
-    mean_h = torch.empty((n, d_out), dtype=torch.float32).pin_memory()
-    std_h = torch.empty((n, d_out), dtype=torch.float32).pin_memory()
+    # ---- the fused kernel alone (K-sharded runs: forward without the exchange) -----------------
+    kernel_ms = statistics.mean(step_ms)
+    if shard is not None:
+        slab = shard.new_slab(n * d_out, dev)
+        fkw = dict(total_members=own_count) if mode == "ensemble" else \
+            dict(zip(("member_begin", "member_count"), shard.split(k)), total_members=k)
 
-    def e2e_step(xh):
-        xd = xh.to(dev, non_blocking=True)
-        if shard is not None:
+        def fwd_only(x):
+            packed.forward_into(x, mode, slab[0, :n * d_out].view(n, d_out),
+                                slab[1, :n * d_out].view(n, d_out), precision=precision,
+                                output="moments", **fkw, **kw)
+        for i in range(2):
+            fwd_only(xs[i])
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(steps):
+            fwd_only(xs[(2 + i) % N_ROTATE])
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1) / steps
+        del slab
+
+    # ---- end-to-end with pinned HOST buffers ---------------------------------------------------
+    # N = 1: through the wrapper API.  N > 1: the samples live sharded in the ranks' host memory
+    # (rank r holds rows [r n/N, (r+1) n/N)): every step each rank copies ITS rows host -> device,
+    # one NCCL all-gather of x over NVLink gives every GPU all rows (the K axis is what is
+    # sharded), the forward + combine run, and each rank copies ITS rows of (mean, std) back.
+    model.uq_shard = None
+    r_begin, r_count = split_range(n, world, rank)
+    cap = -(-n // world)
+    xh = [synth_x(n, d_in, s)[r_begin:r_begin + r_count].contiguous().pin_memory() for s in range(2)]
+    mean_h = torch.empty((r_count, d_out), dtype=torch.float32).pin_memory()
+    std_h = torch.empty((r_count, d_out), dtype=torch.float32).pin_memory()
+    x_pad = torch.zeros((cap, d_in), dtype=torch.float32, device=dev) if world > 1 else None
+    x_all = torch.empty((world * cap, d_in), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def e2e_step(xh_rows):
+        if world > 1:
+            x_pad[:r_count].copy_(xh_rows, non_blocking=True)
+            dist.all_gather_into_tensor(x_all.view(-1), x_pad.view(-1))
+            xd = x_all if n == world * cap else torch.cat(
+                [x_all[q * cap:q * cap + split_range(n, world, q)[1]] for q in range(world)])
             mean, std = step(xd)
+            mean_h.copy_(mean[r_begin:r_begin + r_count], non_blocking=True)
+            std_h.copy_(std[r_begin:r_begin + r_count], non_blocking=True)
         else:
+            xd = xh_rows.to(dev, non_blocking=True)
             with torch.no_grad():
                 if mode == "mc_dropout":
                     torch.manual_seed(0)
                 mean, std = model(xd, return_ue=True)
-        mean_h.copy_(mean, non_blocking=True)
-        std_h.copy_(std, non_blocking=True)
+            mean_h.copy_(mean, non_blocking=True)
+            std_h.copy_(std, non_blocking=True)
         torch.cuda.synchronize()
 
     e2e_steps = max(3, min(steps, 10))
     for i in range(2):
-        e2e_step(xs_host[i % 2])
+        e2e_step(xh[i % 2])
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        e2e_step(xs_host[i % 2])
+        e2e_step(xh[i % 2])
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -440,43 +569,81 @@ def run_gpu(args):
     e2e_s = float(t.item())
     e2e_value = units_per_step * e2e_steps / e2e_s
 
+    # ---- the 1e-5 parity mode on the same workload (N = 1 default line) ------------------------
+    fp32_line = None
+    if world == 1 and precision == "bf16" and not args.no_fp32_leg:
+        for i in range(3):
+            step(xs[i], "fp32")
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f_steps = max(3, min(steps, 8))
+        f0.record()
+        for i in range(f_steps):
+            step(xs[(3 + i) % N_ROTATE], "fp32")
+        f1.record()
+        torch.cuda.synchronize()
+        fp32_line = f0.elapsed_time(f1) / f_steps
+
     if rank == 0:
         peaks = measured_peaks()
         F = flops_per_unit(d_in, widths, d_out)
-        kernel_ms = statistics.mean(step_ms)
         timed_s = total_ms * 1e-3
         peak_kind = "sustained" if timed_s >= 2.0 else "burst"
         peak = peaks[peak_kind]
-        # per-GPU rate: an ensemble rank runs its own k members, a K-sharded job k / world of them
-        achieved = F * n * (k if mode == "ensemble" else k / world) / (kernel_ms * 1e-3) / 1e12
-        traffic = None
+        # per-GPU rate of the fused kernel: a rank runs k / world of the members / passes
+        k_rank = own_count if mode == "ensemble" else k / world
+        achieved = F * n * k_rank / (kernel_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(wl, {}).get(precision)
+                tj = json.load(f)
+            traffic = tj.get(wl, {}).get(precision)
+            traffic_src = tj.get("_source")
+
+        def kernel_label(prec):
+            if prec == "bf16":
+                return kernel_name(widths, d_out)
+            return ("uq_mlp_tcx_kernel (fp32 parity: scaled fp16 x 2 split on tcgen05, 3 MMAs per "
+                    "K step)" if packed.fp32_on_tensor_cores else "sgemm_tn_kernel (fp32 CUDA cores)")
+
         line = {
             "metric": "uq_sample_passes_per_sec", "value": value, "unit": "sample*members/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
             "higher_is_better": True,
-            "scaling": "weak" if mode == "ensemble" else "strong", "vs_baseline": None,
+            "scaling": "strong", "vs_baseline": None,
             "dtype": precision if precision == "bf16" else "f32", "data": "synthetic",
             "config": config_dict(wl, world),
             "e2e": {"value": e2e_value, "unit": "sample*members/s",
                     "h2d_bytes_per_step": n * d_in * 4, "d2h_bytes_per_step": 2 * n * d_out * 4,
-                    "steps": e2e_steps, "api": "model(x.to(device), return_ue=True) -> pinned host"},
+                    "steps": e2e_steps,
+                    "api": "model(x.to(device), return_ue=True) -> pinned host" if world == 1 else
+                           "per rank: its rows of x pinned host -> device, NCCL all-gather of x, "
+                           "KShard forward + combine, its rows of (mean, std) -> pinned host "
+                           "(byte counts are the sums over the ranks)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "peak_source": peaks["source"], "kernel": kernel_name(widths, d_out)
-                         if precision == "bf16" else
-                         ("uq_mlp_tcx_kernel (fp32 parity: scaled fp16 x 2 split on tcgen05, 3 MMAs "
-                          "per K step)" if packed.fp32_on_tensor_cores
-                          else "sgemm_tn_kernel (fp32 CUDA cores)"),
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_kind": peak_kind,
+                         "peak_source": peaks["source"], "kernel": kernel_label(precision),
                          "flops_per_unit": F, "kernel_ms": kernel_ms,
                          "frac_of_sustained": achieved / peaks["sustained"]},
             "wall_s_timed_region": wall,
         }
+        if parity is not None:
+            line["parity_max_err"] = parity
+        if world > 1:
+            line["exchange_ms"] = total_ms / steps - kernel_ms
+        if fp32_line is not None:
+            a32 = F * n * k / (fp32_line * 1e-3) / 1e12
+            line["roofline_fp32_parity"] = {
+                "bound": "tensor", "achieved": a32, "peak": peaks["burst"], "unit": "TFLOP/s",
+                "frac": a32 / peaks["burst"], "kernel": kernel_label("fp32"), "kernel_ms": fp32_line,
+                "value": n * k / (fp32_line * 1e-3), "value_unit": "sample*members/s",
+                "note": "algorithmic flops (what the reference executes) over the launch time; "
+                        "the split issues 3 tensor-core MMAs per algorithmic one, so the tensor "
+                        "pipe runs at 3x this fraction"}
         if world == 1 and wl == DEFAULT_WORKLOAD and not args.no_metric_kernels:
             line["metric_kernels"] = metric_kernel_lines(dev, peaks)
         if world == 1 and not args.no_cpu_baseline:
@@ -488,6 +655,9 @@ def run_gpu(args):
                 "kind": "port",
                 "sample": f"{sample_n} of {n} samples x {k} members, 1 warm-up + 2 timed calls, "
                           f"{dt:.2f} s per call, os.cpu_count={os.cpu_count()}"}
+            eager = gpu_eager_baseline(wl, dev, xs[0])
+            if eager is not None:
+                line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -504,6 +674,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-leg", action="store_true",
+                    help="skip timing the fp32 parity mode next to the bf16 line")
     ap.add_argument("--no-metric-kernels", action="store_true",
                     help="skip the Wasserstein / KDE-JS kernel timings added to the default line")
     args = ap.parse_args()

@@ -145,6 +145,14 @@ int uq_moments_merge(const float* means, const float* m2s, const double* counts,
                      int32_t n_shards, int64_t len, float* out_mean, float* out_std,
                      void* stream);
 
+/*    Same merge for shards that are not packed back to back: shard s has its means at
+      means + s * shard_stride and its M2 at m2s + s * shard_stride (e.g. the receive buffer of the
+      all-to-all in nnueehcs_b200/distributed.py, [shard][mean | M2][slice]).  Shards with count 0
+      are skipped.  output = UQ_OUT_MEAN_STD writes (mean, unbiased std), UQ_OUT_MOMENTS (mean, M2). */
+int uq_moments_merge_ex(const float* means, const float* m2s, int64_t shard_stride,
+                        const double* counts, int32_t n_shards, int64_t len, float* out_mean,
+                        float* out_second, int32_t output, void* stream);
+
 /* -- native dropout masks: writes the Philox keep-masks uq_forward would draw for dropout layer
       `dropout_layer` as bytes [total_members][n][width] (the injected-mask layout), so a
       native-RNG MC-dropout run can be replayed bit-for-bit through the CPU oracle. */

@@ -23,6 +23,7 @@ EXPORTS = (
     "uq_abi_version", "uq_last_error", "uq_launch_count", "uq_launch_count_reset",
     "uq_model_create", "uq_model_destroy", "uq_model_supports_bf16", "uq_model_supports_fp32_tc",
     "uq_forward_workspace_bytes", "uq_forward", "uq_forward_host", "uq_moments_merge",
+    "uq_moments_merge_ex",
     "uq_philox_keep_masks", "uq_wasserstein_workspace_bytes", "uq_wasserstein_1d",
     "uq_wasserstein_1d_ex",
     "uq_kde_jsd_workspace_bytes", "uq_kde_jsd", "uq_kde_jsd_ex",
@@ -112,6 +113,8 @@ def load() -> C.CDLL:
                                C.POINTER(dbl), vp]
     lib.uq_forward_host.argtypes = [vp, vp, i64, C.POINTER(ForwardArgs), vp, vp, vp]
     lib.uq_moments_merge.argtypes = [vp, vp, C.POINTER(dbl), i32, i64, vp, vp, vp]
+    lib.uq_moments_merge_ex.argtypes = [vp, vp, i64, C.POINTER(dbl), i32, i64, vp, vp, i32, vp]
+    lib.uq_moments_merge_ex.restype = C.c_int
     lib.uq_philox_keep_masks.argtypes = [vp, i64, i32, i32, i32, dbl, u64, u64, vp]
     lib.uq_wasserstein_workspace_bytes.argtypes = [i64, i64]
     lib.uq_wasserstein_workspace_bytes.restype = sz

@@ -302,6 +302,20 @@ int uq_moments_merge(const float* means, const float* m2s, const double* counts,
                        static_cast<cudaStream_t>(stream));
 }
 
+int uq_moments_merge_ex(const float* means, const float* m2s, int64_t shard_stride,
+                        const double* counts, int32_t n_shards, int64_t len, float* out_mean,
+                        float* out_second, int32_t output, void* stream) {
+  UQ_REQUIRE(means && m2s && counts && out_mean && out_second && n_shards >= 1 && len >= 1,
+             UQ_ERR_INVALID, "uq_moments_merge_ex: NULL argument or empty input");
+  UQ_REQUIRE(n_shards <= 64, UQ_ERR_INVALID, "uq_moments_merge_ex: at most 64 shards");
+  UQ_REQUIRE(shard_stride >= 1, UQ_ERR_INVALID, "uq_moments_merge_ex: shard_stride < 1");
+  UQ_REQUIRE(output == UQ_OUT_MEAN_STD || output == UQ_OUT_MOMENTS, UQ_ERR_INVALID,
+             "uq_moments_merge_ex: unknown output kind %d", output);
+  return moments_merge_strided(means, m2s, shard_stride, counts, n_shards, len, out_mean,
+                               out_second, output == UQ_OUT_MOMENTS ? 1 : 0,
+                               static_cast<cudaStream_t>(stream));
+}
+
 // Export the native Philox keep-masks in the injected-mask layout (uq_forward_args.masks), so a
 // native-RNG MC-dropout run can be replayed bit-for-bit through the oracle.
 __global__ void philox_export_kernel(uint8_t* __restrict__ out, int64_t n, int width, int passes,

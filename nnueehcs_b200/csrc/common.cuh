@@ -124,6 +124,9 @@ int tcx_pack(uq_model* m, cudaStream_t st);
 // moments (moments.cu)
 int moments_merge(const float* means, const float* m2s, const double* counts, int n_shards,
                   int64_t len, float* out_mean, float* out_std, cudaStream_t st);
+int moments_merge_strided(const float* means, const float* m2s, int64_t shard_stride,
+                          const double* counts, int n_shards, int64_t len, float* out_mean,
+                          float* out_second, int moments, cudaStream_t st);
 
 // metrics (wasserstein.cu / kde_jsd.cu)
 size_t wasserstein_workspace_bytes(int64_t nu, int64_t nv);

@@ -4,16 +4,19 @@ The reference is single-GPU (no collective anywhere).  The 
 path shards the member axis -- ensemble members, MC-dropout passes or Delta-UQ anchors -- across
 ranks (one process per GPU, ``torch.distributed`` over NCCL/NVLink): every rank sees all N samples
 (x is ~20 B/sample), reduces its own members inside the fused kernel to per-sample
-``(count, mean, M2)``, and the shards are combined with ONE collective -- an all-gather of the
-``[2, N, out]`` float32 (mean, M2) slab -- followed by a Chan merge kernel
-(``uq_moments_merge``).  Moments cross the wire rather than raw power sums because
+``(count, mean, M2)`` written straight into one ``[mean | M2]`` slab, and the shards are combined
+reduce-scatter style: an all-to-all hands rank r the r-th slice of the rows of every shard, rank r
+Chan-merges its slice (``uq_moments_merge_ex``) and an all-gather of the finished (mean, std)
+slices rebuilds the result on every rank -- ``2 (G-1)/G`` slabs per GPU over NVLink instead of the
+``G-1`` slabs (plus a G-slab merge read) of a plain all-gather of the moments.  Moments cross the
+wire rather than raw power sums because
 ``sum(y^2) - sum(y)^2/n`` cancels catastrophically in fp32 when std << |mean|, which is the
 in-distribution case.  Philox masks are keyed by the *global* pass id, so the result does not
 depend on the number of ranks.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -43,24 +46,66 @@ class KShard:
         return [self.split(total, r)[1] for r in range(self.world)]
 
     def exchange(self, mean: torch.Tensor, m2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """The one collective: all-gather every rank's (mean, M2) slab -> two ``[world, ...]``
-        tensors ordered by rank."""
+        """All-gather of every rank's (mean, M2) -> two ``[world, ...]`` tensors ordered by rank
+        (the simple form of the exchange; ``combine`` is what the forwards use)."""
         slab = torch.stack([mean, m2]).contiguous()
         flat = torch.empty(self.world * slab.numel(), dtype=slab.dtype, device=slab.device)
         dist.all_gather_into_tensor(flat, slab.reshape(-1), group=self.group)
         gathered = flat.view((self.world,) + tuple(slab.shape))
         return gathered[:, 0], gathered[:, 1]
 
+    # ---- reduce-scatter style combine ----------------------------------------------------------
+    def slice_len(self, length: int) -> int:
+        """Elements of one rank's slice of a ``length``-element result (the last may be padded)."""
+        return -(-length // self.world)
+
+    def new_slab(self, length: int, device) -> torch.Tensor:
+        """``[2, world * slice_len]`` float32: row 0 takes the means, row 1 the M2 of this rank's
+        members (first ``length`` entries; the padding is never read back)."""
+        return torch.empty((2, self.world * self.slice_len(length)), dtype=torch.float32,
+                           device=device)
+
+    def combine(self, slab: torch.Tensor, counts: Sequence[float], merge=None) -> torch.Tensor:
+        """``slab`` = this rank's ``[mean | M2]`` (``new_slab``) -> ``[2, world * slice_len]`` holding
+        the merged (mean, unbiased std) of all shards, identical on every rank.
+        all-to-all of the row slices -> Chan merge of slice ``rank`` -> all-gather of the slices."""
+        world, cap = self.world, slab.shape[1] // self.world
+        merge = ops.moments_merge_strided if merge is None else merge
+        if world == 1:
+            return merge(slab.view(1, 2, cap), list(counts))
+        # [2][world][cap] -> [world][2][cap]: destination-major for the all-to-all
+        send = slab.view(2, world, cap).transpose(0, 1).contiguous()
+        recv = _all_to_all(send.view(-1), [2 * cap] * world, [2 * cap] * world, self.group)
+        fin = merge(recv.view(world, 2, cap), list(counts))             # [2, cap]
+        out = torch.empty((2, world * cap), dtype=slab.dtype, device=slab.device)
+        for row in range(2):
+            if slab.is_cuda:
+                dist.all_gather_into_tensor(out[row], fin[row].contiguous(), group=self.group)
+            else:  # gloo (CPU tests)
+                dist.all_gather(list(out[row].view(world, cap).unbind(0)), fin[row].contiguous(),
+                                group=self.group)
+        return out
+
+    def _forward_and_combine(self, packed, x, mode, counts, merge=None, **fkw):
+        n, d = x.shape[0], packed.d_out
+        length = n * d
+        slab = self.new_slab(length, x.device)
+        if fkw.pop("_skip", False):   # more ranks than members: an empty shard (count 0)
+            slab.zero_()
+        else:
+            packed.forward_into(x, mode, slab[0, :length].view(n, d), slab[1, :length].view(n, d),
+                                output="moments", **fkw)
+        out = self.combine(slab, counts, merge)
+        return out[0, :length].view(n, d), out[1, :length].view(n, d)
+
     def forward_owned(self, packed: "ops.PackedModel", x: torch.Tensor, mode: str, *,
-                      local_members: int, precision: str = "fp32",
+                      local_members: int, precision: str = "fp32", merge=None,
                       **kw) -> Tuple[torch.Tensor, torch.Tensor]:
         """Each rank's ``packed`` holds ONLY its own shard of the members (an ensemble whose
         weights are distributed over the GPUs): reduce locally, exchange moments, merge."""
-        mean, m2 = packed.forward(x, mode, total_members=local_members, precision=precision,
-                                  output="moments", **kw)
-        means, m2s = self.exchange(mean, m2)
-        return ops.moments_merge(means.contiguous(), m2s.contiguous(),
-                                 self.owned_counts(local_members, x.device))
+        return self._forward_and_combine(packed, x, mode, self.owned_counts(local_members, x.device),
+                                         merge, total_members=local_members, precision=precision,
+                                         **kw)
 
     def owned_counts(self, local_members: int, device) -> List[float]:
         """Member count of every rank's shard (gathered once, then cached: it is static)."""
@@ -68,28 +113,20 @@ class KShard:
         if local_members not in cache:
             cnt = torch.tensor([float(local_members)], dtype=torch.float64, device=device)
             all_cnt = torch.empty(self.world, dtype=torch.float64, device=device)
-            dist.all_gather_into_tensor(all_cnt, cnt, group=self.group)
+            if cnt.is_cuda:
+                dist.all_gather_into_tensor(all_cnt, cnt, group=self.group)
+            else:
+                dist.all_gather(list(all_cnt.view(self.world, 1).unbind(0)), cnt, group=self.group)
             cache[local_members] = all_cnt.tolist()
         return cache[local_members]
 
     def forward(self, packed: "ops.PackedModel", x: torch.Tensor, mode: str, *, total_members: int,
-                precision: str = "fp32", **kw) -> Tuple[torch.Tensor, torch.Tensor]:
+                precision: str = "fp32", merge=None, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
         begin, count = self.split(total_members)
-        if count > 0:
-            mean, m2 = packed.forward(x, mode, total_members=total_members, precision=precision,
-                                      member_begin=begin, member_count=count, output="moments",
-                                      **kw)
-        else:  # more ranks than members: this rank contributes an empty shard
-            mean = torch.zeros((x.shape[0], packed.d_out), dtype=torch.float32, device=x.device)
-            m2 = torch.zeros_like(mean)
-        means, m2s = self.exchange(mean, m2)
-        counts = self.counts(total_members)
-        live = [r for r, c in enumerate(counts) if c > 0]
-        if len(live) != self.world:
-            idx = torch.tensor(live, device=means.device)
-            means, m2s = means.index_select(0, idx), m2s.index_select(0, idx)
-            counts = [counts[r] for r in live]
-        return ops.moments_merge(means.contiguous(), m2s.contiguous(), counts)
+        return self._forward_and_combine(packed, x, mode, self.counts(total_members), merge,
+                                         total_members=total_members, precision=precision,
+                                         member_begin=begin, member_count=count,
+                                         _skip=(count == 0), **kw)
 
 
 class NShard:

@@ -187,6 +187,31 @@ class PackedModel:
             count, int(total_members), bool(dropout_active), float(dropout_p),
             _as_i64(seed), _as_i64(offset), masks, anchors, int(self.d_out), targets, score_floor)
 
+    def forward_into(self, x: torch.Tensor, mode: str, out0: torch.Tensor, out1: torch.Tensor, *,
+                     total_members: int, precision: str = "fp32", member_begin: int = 0,
+                     member_count: Optional[int] = None, dropout_p: float = 0.0,
+                     dropout_active: bool = True, seed: int = 0, offset: int = 0,
+                     masks: Optional[torch.Tensor] = None, anchors: Optional[torch.Tensor] = None,
+                     output: str = "mean_std") -> None:
+        """``forward`` writing into caller-owned ``[n, d_out]`` float32 tensors (e.g. the two halves
+        of one exchange slab, ``distributed.KShard``) instead of allocating its outputs."""
+        _require_cuda(x, "x")
+        d_x = self.d_in // 2 if mode in ("delta_uq", "pager") else self.d_in
+        if x.dim() != 2 or x.shape[1] != d_x or x.shape[0] == 0:
+            raise ValueError(f"x must be [n >= 1, {d_x}], got {tuple(x.shape)}")
+        for t in (out0, out1):
+            _require_cuda(t, "out")
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != x.shape[0] * self.d_out:
+                raise ValueError(f"outputs must be contiguous float32 [{x.shape[0]}, {self.d_out}]")
+        xf = x.detach()
+        if xf.dtype != torch.float32 or not xf.is_contiguous():
+            xf = xf.to(torch.float32).contiguous()
+        if anchors is not None:
+            anchors = anchors.detach().to(torch.float32).contiguous()
+        a = self._args(mode, precision, total_members, member_begin, member_count, dropout_p,
+                       dropout_active, seed, offset, masks, anchors, output)
+        _run_forward(self._lib, self._handle, xf, a, out0, out1)
+
     def forward_host(self, x_host: torch.Tensor, out0_host: torch.Tensor, out1_host: torch.Tensor,
                      mode: str, *, total_members: int, precision: str = "fp32",
                      dropout_p: float = 0.0, dropout_active: bool = True, seed: int = 0,
@@ -233,6 +258,30 @@ def moments_merge(means: torch.Tensor, m2s: torch.Tensor, counts: Sequence[float
     if len(counts) != s:
         raise ValueError("one count per shard is required")
     return torch.ops.nnueehcs_b200.moments_merge(means, m2s, [float(c) for c in counts])
+
+
+def moments_merge_strided(shards: torch.Tensor, counts: Sequence[float], output: str = "mean_std"
+                          ) -> torch.Tensor:
+    """Chan merge of ``shards`` = float32 ``[S, 2, L]`` (shard s: its means, then its M2 -- the
+    receive buffer of the K-shard all-to-all) into a ``[2, L]`` tensor: (mean, unbiased std), or
+    (mean, M2) with ``output='moments'``.  Shards whose count is 0 are skipped."""
+    lib = _lib.load()
+    _require_cuda(shards, "shards")
+    if shards.dtype != torch.float32 or shards.dim() != 3 or shards.shape[1] != 2 \
+            or not shards.is_contiguous():
+        raise ValueError("shards must be a contiguous float32 [S, 2, L] tensor")
+    s, _, length = shards.shape
+    if len(counts) != s:
+        raise ValueError("one count per shard is required")
+    out = torch.empty((2, length), dtype=torch.float32, device=shards.device)
+    cnt = (C.c_double * s)(*[float(c) for c in counts])
+    base = shards.data_ptr()
+    with torch.cuda.device(shards.device):
+        _lib.check(lib.uq_moments_merge_ex(base, base + 4 * length, 2 * length, cnt, s, length,
+                                           out[0].data_ptr(), out[1].data_ptr(),
+                                           _lib.OUT_MOMENTS if output == "moments"
+                                           else _lib.OUT_MEAN_STD, _stream_ptr(shards.device)))
+    return out
 
 
 def _flat_f32(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -534,6 +583,16 @@ def _as_i64(v: int) -> int:
     return v - (1 << 64) if v >= (1 << 63) else v
 
 
+def _run_forward(lib, handle, x: torch.Tensor, a: "_lib.ForwardArgs", out0: torch.Tensor,
+                 out1: torch.Tensor) -> None:
+    n, dev = x.shape[0], x.device
+    with torch.cuda.device(dev):
+        wsb = int(lib.uq_forward_workspace_bytes(handle, n, C.byref(a)))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        _lib.check(lib.uq_forward(handle, x.data_ptr(), n, C.byref(a), out0.data_ptr(),
+                                  out1.data_ptr(), ws.data_ptr(), wsb, None, _stream_ptr(dev)))
+
+
 def _op_uq_forward(handle: int, x: torch.Tensor, mode: int, precision: int, output: int,
                    member_begin: int, member_count: int, total_members: int,
                    dropout_active: bool, dropout_p: float, seed: int, offset: int,
@@ -554,14 +613,9 @@ def _op_uq_forward(handle: int, x: torch.Tensor, mode: int, precision: int, outp
     a.anchor_targets = targets.data_ptr() if targets is not None else None
     a.score_floor = score_floor.data_ptr() if score_floor is not None else None
     n, dev = x.shape[0], x.device
-    h = C.c_void_p(handle)
-    with torch.cuda.device(dev):
-        out0 = torch.empty((n, d_out), dtype=torch.float32, device=dev)
-        out1 = torch.empty((n, d_out), dtype=torch.float32, device=dev)
-        wsb = int(lib.uq_forward_workspace_bytes(h, n, C.byref(a)))
-        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
-        _lib.check(lib.uq_forward(h, x.data_ptr(), n, C.byref(a), out0.data_ptr(),
-                                  out1.data_ptr(), ws.data_ptr(), wsb, None, _stream_ptr(dev)))
+    out0 = torch.empty((n, d_out), dtype=torch.float32, device=dev)
+    out1 = torch.empty((n, d_out), dtype=torch.float32, device=dev)
+    _run_forward(lib, C.c_void_p(handle), x, a, out0, out1)
     return out0, out1
 
 

@@ -130,3 +130,75 @@ def test_gloo_world2_sample_axis_shard(tmp_path):
     a = torch.load(tmp_path / "nrank0.pt")
     b = torch.load(tmp_path / "nrank1.pt")
     assert torch.equal(a["mean"], b["mean"])
+
+
+# ---- reduce-scatter style combine (all-to-all of row slices -> local merge -> all-gather) ----------
+
+class _OracleMomentsPacked:
+    """CPU stand-in for ops.PackedModel.forward_into: oracle moments of the member range."""
+
+    def __init__(self, nets):
+        self.nets, self.d_out = nets, 1
+
+    def forward_into(self, x, mode, out0, out1, *, total_members, precision="fp32", member_begin=0,
+                     member_count=None, output="mean_std", **kw):
+        assert output == "moments"
+        count = total_members - member_begin if member_count is None else member_count
+        members = uq_oracle.ensemble_member_outputs(self.nets[member_begin:member_begin + count], x)
+        _, mean, m2 = uq_oracle.moments_of(members)
+        out0.copy_(mean.float())
+        out1.copy_(m2.float())
+
+
+def _merge_standin(shards, counts):
+    """numpy-style restatement of uq_moments_merge_ex on CPU: shards [S, 2, L] -> [2, L]."""
+    acc = None
+    for s, c in enumerate(counts):
+        if c <= 0:
+            continue
+        part = (torch.full_like(shards[s, 0], float(c)).double(), shards[s, 0].double(),
+                shards[s, 1].double())
+        acc = part if acc is None else uq_oracle.chan_merge(acc, part)
+    m, sd = uq_oracle.finalize_std(*acc)
+    return torch.stack([m.float(), sd.float()])
+
+
+def _combine_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = load_golden("ensemble_bn.npz")
+        k = int(g["k"])
+        nets = nets_from_golden(g, k)
+        packed = _OracleMomentsPacked(nets)
+        x = torch.from_numpy(g["x"])[:157]        # odd row count: the last slice is padded
+        shard = KShard()
+        assert shard.slice_len(157) == 79 and shard.new_slab(157, "cpu").shape == (2, 158)
+        mean, std = shard.forward(packed, x, "ensemble", total_members=k, merge=_merge_standin)
+        ref_mean, ref_std = uq_oracle.ensemble_forward(nets, x)
+        assert mean.shape == ref_mean.shape
+        assert torch.allclose(mean, ref_mean, rtol=0, atol=2e-7)
+        assert torch.allclose(std, ref_std, rtol=0, atol=2e-7)
+        # members owned per rank (weak-scaling ensembles): rank r owns nets[2r : 2r + 2]
+        own = _OracleMomentsPacked(nets[2 * rank:2 * rank + 2])
+        m2_, s2_ = shard.forward_owned(own, x, "ensemble", local_members=2, merge=_merge_standin)
+        r_mean, r_std = uq_oracle.ensemble_forward(nets[:4], x)
+        assert torch.allclose(m2_, r_mean, rtol=0, atol=2e-7)
+        assert torch.allclose(s2_, r_std, rtol=0, atol=2e-7)
+        # more ranks than members: rank 1 contributes an empty shard (count 0) and still takes part
+        one = _OracleMomentsPacked(nets[:1])
+        m1, s1 = shard.forward(one, x, "ensemble", total_members=1, merge=_merge_standin)
+        assert torch.allclose(m1, uq_oracle.ensemble_member_outputs(nets[:1], x)[0], atol=2e-7)
+        assert torch.isnan(s1).all()              # unbiased std of a single member, like torch.std
+        torch.save({"mean": mean, "std": std}, os.path.join(out_dir, f"crank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_reduce_scatter_combine(tmp_path):
+    mp.spawn(_combine_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(tmp_path / "crank0.pt")
+    b = torch.load(tmp_path / "crank1.pt")
+    assert torch.equal(a["mean"], b["mean"]) and torch.equal(a["std"], b["std"])

@@ -11,11 +11,10 @@ fp32 mode : north_star's 1e-5 relative, read as ``|got-ref| <= 1e-5*|ref| + 1e-5
             ``precision='fp32'`` is the tensor-core split kernel (csrc/mlp_tcx.cu) wherever the model
             is eligible and the CUDA-core path otherwise; ``'fp32_ffma'`` forces the CUDA-core path.
             Both are held to the same 1e-5.
-bf16 mode : stated tolerance, per test, about 5x the measured worst case (printed): the mean within
-            ``tol_mean * max|ref_mean|``, the std within ``tol_std * max|ref_std|`` -- relative to the
-            std's OWN scale.  Defaults 2e-3 / 1e-2 fit nets up to 6 x 128 (measured 1e-4 .. 4e-4 of
-            scale); wide / deep nets state their own (bf16 rounds weights and activations to 8 bits
-            once per layer, the error grows with width and depth: 1.1e-2 at 3 x 512).
+bf16 mode : stated tolerance (``_bf16_check``): mean and std within ``1e-2 * scale`` with
+            ``scale = max|ref_mean| + max|ref_std|`` (the size of one member's output; measured worst
+            case 2.3e-3 .. 4.3e-3), and the std within ``5e-2`` of its own scale (measured <= 2.2e-2).
+            bf16 rounds weights and activations to 8 bits once per layer.  Measured errors are printed.
 """
 import os
 
@@ -38,19 +37,27 @@ RTOL32 = 1e-5
 FP32_MODES = ["fp32", "fp32_ffma"]
 
 
-def _bf16_check(mean, std, ref_mean, ref_std, what, tol_mean=2e-3, tol_std=1e-2):
+def _bf16_check(mean, std, ref_mean, ref_std, what, tol=1e-2, tol_std=5e-2):
+    """bf16 tolerance.  The natural unit is the magnitude of one member's output, taken as
+    ``scale = max|ref_mean| + max|ref_std|``: both errors must stay within ``tol * scale`` (measured
+    worst case over every bf16 test: 2.3e-3, and 4.3e-3 for identical passes whose std is 0 -- the
+    bound is 2.5-5x that; a mis-addressed K chunk is an error of >= 1/8 of scale), and the std
+    additionally within ``tol_std`` of its OWN scale (measured 1e-3 .. 2.2e-2; the largest values
+    belong to anchored nets whose spread is 16x smaller than their mean)."""
     mean, std = mean.double().cpu(), std.double().cpu()
     ref_mean, ref_std = torch.as_tensor(ref_mean).double(), torch.as_tensor(ref_std).double()
     ms, ss = float(ref_mean.abs().max()), float(ref_std.abs().max())
+    scale = ms + ss
     e_mean = float((mean - ref_mean).abs().max())
     e_std = float((std - ref_std).abs().max())
-    print(f"[bf16 {what}] max|mean err| = {e_mean:.3e} ({e_mean / ms:.3e} of scale), "
-          f"max|std err| = {e_std:.3e} ({e_std / max(ss, 1e-30):.3e} of std scale)")
-    assert e_mean <= tol_mean * ms, f"{what}: bf16 mean error {e_mean / ms:.3e} of scale > {tol_mean}"
-    # a std that is identically ~0 (identical passes) is checked against the mean scale instead
-    floor = 1e-6 * ms
-    assert e_std <= tol_std * ss + floor, \
-        f"{what}: bf16 std error {e_std / max(ss, 1e-30):.3e} of std scale > {tol_std}"
+    print(f"[bf16 {what}] max|mean err| = {e_mean:.3e} ({e_mean / scale:.3e} of scale), "
+          f"max|std err| = {e_std:.3e} ({e_std / scale:.3e} of scale, "
+          f"{e_std / max(ss, 1e-30):.3e} of std scale)")
+    assert e_mean <= tol * scale, f"{what}: bf16 mean error {e_mean / scale:.3e} of scale > {tol}"
+    assert e_std <= tol * scale, f"{what}: bf16 std error {e_std / scale:.3e} of scale > {tol}"
+    if ss > 1e-3 * ms:   # identical passes have std == 0: nothing relative to check
+        assert e_std <= tol_std * ss, \
+            f"{what}: bf16 std error {e_std / ss:.3e} of std scale > {tol_std}"
 
 
 # ---- ensemble -----------------------------------------------------------------------------------
@@ -808,7 +815,7 @@ def test_baseline_config1_ensemble16x512():
     assert_close_ref(mean, ref_mean, RTOL32, what="cfg1 fp32 mean")
     assert_close_ref(std, ref_std, RTOL32, scale_ref=ref_mean, what="cfg1 fp32 std")
     mean, std = packed.forward(x.to(DEV), "ensemble", total_members=k, precision="bf16")
-    _bf16_check(mean, std, ref_mean, ref_std, "cfg1 bf16", tol_mean=5e-2, tol_std=2e-1)
+    _bf16_check(mean, std, ref_mean, ref_std, "cfg1 bf16")
     model = EnsembleModelBuilder(_wide_arch(5, 512, 3, 1), {"num_models": k}).build()
     for m, ref in zip(model.models, nets):
         m.load_state_dict(ref.state_dict())
@@ -841,7 +848,7 @@ def test_baseline_config2_deltauq_32_anchors_6x128():
     assert_close_ref(std, ref_std, RTOL32, scale_ref=ref_mean, what="cfg2 fp32 std")
     mean, std = packed.forward(x.to(DEV), "delta_uq", total_members=k, precision="bf16",
                                anchors=anchors.to(DEV))
-    _bf16_check(mean, std, ref_mean, ref_std, "cfg2 bf16", tol_mean=5e-2, tol_std=2e-1)
+    _bf16_check(mean, std, ref_mean, ref_std, "cfg2 bf16")
     model = DeltaUQMLPModelBuilder(_wide_arch(5, 128, 6, 1), {"estimator": "std", "num_anchors": k,
                                                               "anchored_batch_size": 4096}).build()
     model.net.load_state_dict(net.state_dict())
@@ -872,7 +879,7 @@ def test_baseline_config3_mcdropout_8x1024_philox_replay():
     assert_close_ref(std, ref_std, RTOL32, scale_ref=ref_mean, what="cfg3 fp32 std")
     mean, std = packed.forward(x_cpu.to(DEV), "mc_dropout", total_members=passes, precision="bf16",
                                dropout_p=p, seed=seed)
-    _bf16_check(mean, std, ref_mean, ref_std, "cfg3 bf16", tol_mean=5e-2, tol_std=2e-1)
+    _bf16_check(mean, std, ref_mean, ref_std, "cfg3 bf16")
     model = MCDropoutModelBuilder(_wide_arch(5, 1024, 7, 1), {"num_samples": passes,
                                                               "dropout_percent": p}).build()
     model.model.load_state_dict(net.state_dict())
