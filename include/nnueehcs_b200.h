@@ -115,6 +115,15 @@ void uq_launch_count_reset(void);
       call's stream work has completed. */
 int uq_model_create(uq_model_t** out, int32_t n_members, int32_t n_layers,
                     const uq_layer_desc* layers, void* stream);
+/*    Same with flags.  UQ_MODEL_ANCHOR_FIRST: in UQ_MODE_DELTA_UQ / UQ_MODE_PAGER the network input
+      of a sample x and an anchor a is cat([a, x - a]) -- the channel order of the public `deltauq`
+      package (deltaUQ_MLP.create_anchored_batch: torch.cat([A, diff], axis=1)) that the reference
+      subclasses (nnueehcs/models.py:288) -- instead of cat([x - a, a]) (flags = 0, what
+      uq_model_create packs).  The two differ by a swap of the first Linear's column halves; a
+      checkpoint trained with the reference stack needs the flag.  Other modes ignore it. */
+#define UQ_MODEL_ANCHOR_FIRST 1
+int uq_model_create_ex(uq_model_t** out, int32_t n_members, int32_t n_layers,
+                       const uq_layer_desc* layers, int32_t flags, void* stream);
 int uq_model_destroy(uq_model_t* model);
 /* 1 if the bf16 tcgen05 path supports this model's shapes, else 0 (reason in uq_last_error) */
 int uq_model_supports_bf16(const uq_model_t* model);

@@ -15,13 +15,14 @@ UQ_OK, UQ_ERR_INVALID, UQ_ERR_CUDA, UQ_ERR_UNSUPPORTED, UQ_ERR_WORKSPACE = 0, 1,
 MODE_ENSEMBLE, MODE_MC_DROPOUT, MODE_DELTA_UQ, MODE_PAGER = 0, 1, 2, 3
 PREC_FP32, PREC_BF16, PREC_FP32_FFMA = 0, 1, 2
 OUT_MEAN_STD, OUT_MOMENTS = 0, 1
+MODEL_ANCHOR_FIRST = 1
 WASSERSTEIN_AUTO, WASSERSTEIN_SORT, WASSERSTEIN_BINNED = 0, 1, 2
 KDE_AUTO, KDE_WINDOW, KDE_MOMENTS = 0, 1, 2
 
 # every symbol include/nnueehcs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "uq_abi_version", "uq_last_error", "uq_launch_count", "uq_launch_count_reset",
-    "uq_model_create", "uq_model_destroy", "uq_model_supports_bf16", "uq_model_supports_fp32_tc",
+    "uq_model_create", "uq_model_create_ex", "uq_model_destroy", "uq_model_supports_bf16", "uq_model_supports_fp32_tc",
     "uq_forward_workspace_bytes", "uq_forward", "uq_forward_host", "uq_moments_merge",
     "uq_moments_merge_ex",
     "uq_philox_keep_masks", "uq_wasserstein_workspace_bytes", "uq_wasserstein_1d",
@@ -103,6 +104,8 @@ def load() -> C.CDLL:
     lib.uq_launch_count.restype = u64
     lib.uq_launch_count_reset.restype = None
     lib.uq_model_create.argtypes = [C.POINTER(vp), i32, i32, C.POINTER(LayerDesc), vp]
+    lib.uq_model_create_ex.argtypes = [C.POINTER(vp), i32, i32, C.POINTER(LayerDesc), i32, vp]
+    lib.uq_model_create_ex.restype = C.c_int
     lib.uq_model_destroy.argtypes = [vp]
     lib.uq_model_supports_bf16.argtypes = [vp]
     lib.uq_model_supports_fp32_tc.argtypes = [vp]
@@ -161,7 +164,7 @@ def load() -> C.CDLL:
     for name in ("uq_sample_stats", "uq_kde_grid_accumulate", "uq_jsd_from_grids",
                  "uq_key_histogram", "uq_partition_by_bin", "uq_wasserstein_1d_range"):
         getattr(lib, name).restype = C.c_int
-    for name in ("uq_model_create", "uq_model_destroy", "uq_model_supports_bf16", "uq_forward",
+    for name in ("uq_model_create", "uq_model_create_ex", "uq_model_destroy", "uq_model_supports_bf16", "uq_forward",
                  "uq_forward_host", "uq_moments_merge", "uq_philox_keep_masks",
                  "uq_wasserstein_1d", "uq_kde_jsd"):
         getattr(lib, name).restype = C.c_int

@@ -75,7 +75,14 @@ int uq_model_destroy(uq_model_t* model) {
 
 int uq_model_create(uq_model_t** out, int32_t n_members, int32_t n_layers,
                     const uq_layer_desc* layers, void* stream) {
+  return uq_model_create_ex(out, n_members, n_layers, layers, 0, stream);
+}
+
+int uq_model_create_ex(uq_model_t** out, int32_t n_members, int32_t n_layers,
+                       const uq_layer_desc* layers, int32_t flags, void* stream) {
   UQ_REQUIRE(out != nullptr, UQ_ERR_INVALID, "uq_model_create: out is NULL");
+  UQ_REQUIRE((flags & ~UQ_MODEL_ANCHOR_FIRST) == 0, UQ_ERR_INVALID,
+             "uq_model_create_ex: unknown flags 0x%x", flags);
   *out = nullptr;
   UQ_REQUIRE(n_members >= 1 && n_layers >= 1 && layers != nullptr, UQ_ERR_INVALID,
              "uq_model_create: need >= 1 member and >= 1 Linear layer");
@@ -105,6 +112,7 @@ int uq_model_create(uq_model_t** out, int32_t n_members, int32_t n_layers,
   cudaGetDevice(&m->device);
   m->n_members = n_members;
   m->n_layers = n_layers;
+  m->anchor_first = (flags & UQ_MODEL_ANCHOR_FIRST) != 0;
   m->d_in = layers[0].in_features;
   m->d_out = layers[n_layers - 1].out_features;
   m->layers.resize(n_layers);

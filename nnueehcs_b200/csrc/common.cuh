@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,24 @@ void count_launch(int n = 1);
       return (code);                  \
     }                                 \
   } while (0)
+
+// One-time, PER-DEVICE opt-in of a kernel to more than 48 KB of dynamic shared memory
+// (cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: a process
+// that uses cuda:0 and then cuda:1 must set it on both).  Thread-safe; devices >= 64 set it on
+// every call.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+};
+template <class Kernel>
+inline int smem_opt_in(Kernel kernel, int bytes, PerDeviceOnce& once) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+  if (bit && (once.done.load(std::memory_order_acquire) & bit)) return UQ_OK;
+  UQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (bit) once.done.fetch_or(bit, std::memory_order_release);
+  return UQ_OK;
+}
 
 // ---- packed model ------------------------------------------------------------------------------
 struct Layer {
@@ -96,6 +115,7 @@ struct uq_model {
   int n_layers = 0;
   int d_in = 0, d_out = 0, max_width = 0;
   int n_dropout = 0;
+  bool anchor_first = false;   // UQ_MODEL_ANCHOR_FIRST: anchored input = cat([a, x - a])
   std::vector<uq::Layer> layers;
   std::vector<void*> allocations;
   uq::TcPlan tc;

@@ -326,12 +326,9 @@ int km_bins(double lo, double hi, double h) {
 // KM_MAX_BINS * KM_WORDS doubles of scratch
 int km_accumulate(const float* x, int64_t n, double lo, double hi, double h, int nb, int grid_pts,
                   double* grid, double* tables, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    UQ_CUDA(cudaFuncSetAttribute(kde_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 KM_MAX_BINS * KM_WORDS * (int)sizeof(uint32_t)));
-    attr_set = true;
-  }
+  static PerDeviceOnce opted;
+  if (int rc = smem_opt_in(kde_moments_kernel, KM_MAX_BINS * KM_WORDS * (int)sizeof(uint32_t), opted))
+    return rc;
   const double w = h / KM_PER_H;
   UQ_CUDA(cudaMemsetAsync(tables, 0, sizeof(double) * (size_t)nb * KM_WORDS, st));
   int64_t blocks = (n + (int64_t)KM_THREADS * 8 - 1) / ((int64_t)KM_THREADS * 8);

@@ -195,8 +195,11 @@ linear_small_out_kernel(const float* __restrict__ A, int64_t a_member_stride, in
 // deltaUQ_MLP.create_anchored_batch; parity unpinned).
 // PAGER (swap = 1): the anchor is the input and the sample the anchor, in = cat(a_k - x[m], x[m])
 // (PAGERMLP._anchored_predictions, models.py:396-424).
+// anchor_first: the halves in the other order, cat(a_k, x[m] - a_k) / cat(x[m], a_k - x[m])
+// (UQ_MODEL_ANCHOR_FIRST: the public deltauq package's channel order).
 __global__ void delta_input_kernel(const float* __restrict__ x, const float* __restrict__ anchors,
-                                   float* __restrict__ out, int M, int d, int member0, int swap) {
+                                   float* __restrict__ out, int M, int d, int member0, int swap,
+                                   int anchor_first) {
   const int z = blockIdx.z;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * d) return;
@@ -204,8 +207,9 @@ __global__ void delta_input_kernel(const float* __restrict__ x, const float* __r
   const int c = (int)(i - m * d);
   const float a = anchors[(int64_t)(member0 + z) * d + c];
   float* o = out + ((int64_t)z * M + m) * (2 * d);
-  o[c] = swap ? a - x[i] : x[i] - a;
-  o[d + c] = swap ? x[i] : a;
+  const int diff_at = anchor_first ? d : 0, base_at = anchor_first ? 0 : d;
+  o[diff_at + c] = swap ? a - x[i] : x[i] - a;
+  o[base_at + c] = swap ? x[i] : a;
 }
 
 // PAGER: out0 = mean over anchors of the predictions, out1 = max_k |P[k] - Y_k| (float32 like the
@@ -316,7 +320,8 @@ int fp32_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_
         const int64_t tot = (int64_t)M * d;
         dim3 grid((unsigned)((tot + 255) / 256), 1, G);
         delta_input_kernel<<<grid, 256, 0, st>>>(in, a->anchors, act[0], M, d, gm0,
-                                                 a->mode == UQ_MODE_PAGER ? 1 : 0);
+                                                 a->mode == UQ_MODE_PAGER ? 1 : 0,
+                                                 m->anchor_first ? 1 : 0);
         UQ_LAUNCH_CHECK();
         in = act[0];
         in_stride = (int64_t)M * m->d_in;

@@ -155,29 +155,33 @@ static int split_factor(const TcPlan& t) { return split_factor_of(t.d_in); }
 // with eval-BatchNorm folded), so that  W0' [x - a_k; a_k] + b0' = W0'[:, :dx] x + bias0[k]
 // PAGER (pager = 1) swaps the roles:  W0' [a_k - x; a... x] = (W0'[:, dx:] - W0'[:, :dx]) x + bias0[k]
 // with bias0[k][h] = b0'[h] + sum_i W0'[h][i] a_k[i].
+// diff_at: first column of the half of W0 that multiplies the difference (0, or dx with
+// UQ_MODEL_ANCHOR_FIRST); "W0a" above is that half, "W0b" the other one.
 __global__ void delta_bias_kernel(const float* __restrict__ w0, const float* __restrict__ alpha,
                                   const float* __restrict__ bias_folded,
                                   const float* __restrict__ anchors, int H, int dx, int n_anchors,
-                                  int anchor_begin, int pager, float* __restrict__ out) {
+                                  int anchor_begin, int pager, int diff_at,
+                                  float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_anchors * H) return;
   const int h = i % H, k = anchor_begin + i / H;
   const float sc = alpha ? alpha[h] : 1.0f;
   float acc = bias_folded[h];
   for (int j = 0; j < dx; ++j) {
-    const float wa = w0[(int64_t)h * 2 * dx + j], wb = w0[(int64_t)h * 2 * dx + dx + j];
+    const float wa = w0[(int64_t)h * 2 * dx + diff_at + j];
+    const float wb = w0[(int64_t)h * 2 * dx + (dx - diff_at) + j];
     acc = fmaf((pager ? wa : wb - wa) * sc, anchors[(int64_t)k * dx + j], acc);
   }
   out[(int64_t)k * H + h] = acc;
 }
 
 // [H][dx] column differences W0[:, dx:] - W0[:, :dx] (the PAGER image's layer 0)
-__global__ void column_diff_kernel(const float* __restrict__ w0, int H, int dx,
+__global__ void column_diff_kernel(const float* __restrict__ w0, int H, int dx, int diff_at,
                                    float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * dx) return;
   const int h = i / dx, j = i % dx;
-  out[i] = w0[(int64_t)h * 2 * dx + dx + j] - w0[(int64_t)h * 2 * dx + j];
+  out[i] = w0[(int64_t)h * 2 * dx + (dx - diff_at) + j] - w0[(int64_t)h * 2 * dx + diff_at + j];
 }
 
 int tc_pack(uq_model* m, cudaStream_t st) {
@@ -217,9 +221,10 @@ int tc_pack(uq_model* m, cudaStream_t st) {
     const Layer& l0 = m->layers[0];
     const int dx = l0.in / 2;
     const int64_t total = (int64_t)NH * t.n_tile * 8;
+    const int diff_at = m->anchor_first ? dx : 0;
     pack_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        t.image_delta, l0.w, l0.has_bn ? l0.alpha : nullptr, 0, dx, l0.in, H, t.n_tile, NH, KC,
-        t.k0_delta, split_factor_of(dx), stage_elems, 0);
+        t.image_delta, l0.w + diff_at, l0.has_bn ? l0.alpha : nullptr, 0, dx, l0.in, H, t.n_tile,
+        NH, KC, t.k0_delta, split_factor_of(dx), stage_elems, 0);
     UQ_LAUNCH_CHECK();
     // PAGER image: layer 0 = column differences, everything else shared with the Delta-UQ image
     void *pp = nullptr, *diff = nullptr;
@@ -231,7 +236,8 @@ int tc_pack(uq_model* m, cudaStream_t st) {
     UQ_CUDA(cudaMemcpyAsync(pp, pd, member_elems * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice,
                             st));
     UQ_CUDA(cudaMemsetAsync(pp, 0, (size_t)NH * t.stage_bytes, st));
-    column_diff_kernel<<<(H * dx + 255) / 256, 256, 0, st>>>(l0.w, H, dx, static_cast<float*>(diff));
+    column_diff_kernel<<<(H * dx + 255) / 256, 256, 0, st>>>(l0.w, H, dx, diff_at,
+                                                              static_cast<float*>(diff));
     UQ_LAUNCH_CHECK();
     pack_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         t.image_pager, static_cast<const float*>(diff), l0.has_bn ? l0.alpha : nullptr, 0, dx, dx, H,
@@ -384,7 +390,7 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
     const int total = a->member_count * t.hidden;
     delta_bias_kernel<<<(total + 255) / 256, 256, 0, st>>>(
         l0.w, l0.has_bn ? l0.alpha : nullptr, l0.bias_folded, a->anchors, t.hidden, dx,
-        a->member_count, a->member_begin, pager ? 1 : 0, bias0);
+        a->member_count, a->member_begin, pager ? 1 : 0, m->anchor_first ? dx : 0, bias0);
     UQ_LAUNCH_CHECK();
     p.bias[0] = bias0;
     p.bias0_per_member = 1;

@@ -659,7 +659,7 @@ int launch_tc2(const TcParams& p, cudaStream_t st) {
   auto kern = uq_mlp_tc2_kernel<H, DOUT, NG>;
   // per-device launch geometry of this instantiation, queried once (the occupancy query and the
   // attribute call cost tens of microseconds, which shows on millisecond-sized forwards)
-  static int cached_clusters[16] = {0};
+  static std::atomic<int> cached_clusters[64];   // zero-initialised; races only repeat the query
   int dev = 0;
   cudaGetDevice(&dev);
   const int64_t units = (int64_t)((p.n_tiles + 1) / 2) * p.splits;
@@ -675,7 +675,7 @@ int launch_tc2(const TcParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int max_clusters = dev >= 0 && dev < 16 ? cached_clusters[dev] : 0;
+  int max_clusters = dev >= 0 && dev < 64 ? cached_clusters[dev].load(std::memory_order_acquire) : 0;
   if (max_clusters == 0) {
     UQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
     int sms = 148;
@@ -687,7 +687,7 @@ int launch_tc2(const TcParams& p, cudaStream_t st) {
         active < max_clusters)
       max_clusters = active;
     (void)cudaGetLastError();
-    if (dev >= 0 && dev < 16) cached_clusters[dev] = max_clusters;
+    if (dev >= 0 && dev < 64) cached_clusters[dev].store(max_clusters, std::memory_order_release);
   }
   const int clusters = (int)(units < (int64_t)max_clusters ? units : (int64_t)max_clusters);
   cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);

@@ -904,12 +904,12 @@ void tcx_plan(uq_model* m) {
 }
 
 // the [H][dx] column differences of tc_pack's PAGER image are recomputed here (tiny)
-__global__ void column_diff_x_kernel(const float* __restrict__ w0, int H, int dx,
+__global__ void column_diff_x_kernel(const float* __restrict__ w0, int H, int dx, int diff_at,
                                      float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * dx) return;
   const int h = i / dx, j = i % dx;
-  out[i] = w0[(int64_t)h * 2 * dx + dx + j] - w0[(int64_t)h * 2 * dx + j];
+  out[i] = w0[(int64_t)h * 2 * dx + (dx - diff_at) + j] - w0[(int64_t)h * 2 * dx + diff_at + j];
 }
 
 // needs tc_pack to have run (bias_folded)
@@ -978,16 +978,18 @@ int tcx_pack(uq_model* m, cudaStream_t st) {
     for (void* dst : {sd, sp})
       UQ_CUDA(cudaMemcpyAsync(dst, stats, sizeof(float) * (size_t)L * STAT_FLOATS,
                               cudaMemcpyDeviceToDevice, st));
-    // Delta-UQ: the dx columns of W0 that multiply x
-    layer_stats_kernel<<<1, 256, 0, st>>>(l0.w, l0.has_bn ? l0.alpha : nullptr, l0.bias_folded,
-                                          l0.out, dx, l0.in, 0, L, 0, t.x_stats_delta);
+    // Delta-UQ: the dx columns of W0 that multiply x (the half that sees the difference)
+    const int diff_at = m->anchor_first ? dx : 0;
+    layer_stats_kernel<<<1, 256, 0, st>>>(l0.w + diff_at, l0.has_bn ? l0.alpha : nullptr,
+                                          l0.bias_folded, l0.out, dx, l0.in, 0, L, 0,
+                                          t.x_stats_delta);
     UQ_LAUNCH_CHECK();
     pack_image_x_kernel<<<(unsigned)((total0 + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<__half*>(pd), l0.w, l0.has_bn ? l0.alpha : nullptr, t.x_stats_delta, 0,
-        dx, l0.in, t.x_n_tile, n_tiles, KC, k0d, stage_elems, 0);
+        reinterpret_cast<__half*>(pd), l0.w + diff_at, l0.has_bn ? l0.alpha : nullptr,
+        t.x_stats_delta, 0, dx, l0.in, t.x_n_tile, n_tiles, KC, k0d, stage_elems, 0);
     UQ_LAUNCH_CHECK();
     // PAGER: the column differences W0[:, dx:] - W0[:, :dx]
-    column_diff_x_kernel<<<(H * dx + 255) / 256, 256, 0, st>>>(l0.w, H, dx,
+    column_diff_x_kernel<<<(H * dx + 255) / 256, 256, 0, st>>>(l0.w, H, dx, diff_at,
                                                               static_cast<float*>(diff));
     UQ_LAUNCH_CHECK();
     layer_stats_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(diff),

@@ -189,12 +189,8 @@ int uq_sample_stats(const float* x, int64_t n, double* out_host, void* workspace
 int uq_key_histogram(const float* x, int64_t n, uint32_t* hist, void* stream) {
   UQ_REQUIRE(x && hist && n >= 1, UQ_ERR_INVALID, "uq_key_histogram: NULL argument or n < 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    UQ_CUDA(cudaFuncSetAttribute(key_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 KEY_BINS * (int)sizeof(uint32_t)));
-    attr_set = true;
-  }
+  static PerDeviceOnce opted;
+  if (int rc = smem_opt_in(key_histogram_kernel, KEY_BINS * (int)sizeof(uint32_t), opted)) return rc;
   int64_t blocks = (n + 512 * 32 - 1) / (512 * 32);
   if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;

@@ -480,13 +480,9 @@ namespace {
 
 int bin_moments_launch(const float* x, int64_t n, unsigned long long* cnt, unsigned long long* ks,
                        cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceOnce opted;
   constexpr int SMEM = 2 * WB_BINS * (int)sizeof(uint32_t);
-  if (!attr_set) {
-    UQ_CUDA(cudaFuncSetAttribute(bin_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SMEM));
-    attr_set = true;
-  }
+  if (int rc = smem_opt_in(bin_moments_kernel, SMEM, opted)) return rc;
   // one block per SM; more only to keep a block below BM_MAX_PER_BLOCK values
   int64_t blocks = (n + (int64_t)BM_THREADS * 16 - 1) / ((int64_t)BM_THREADS * 16);
   if (blocks > 148) blocks = 148;

@@ -88,9 +88,15 @@ def _f32_cuda(t: Optional[torch.Tensor], device, keep: list) -> Optional[torch.T
 
 
 def tensors_version(nets: Sequence[nn.Sequential]):
-    """Cheap cache key: identity + in-place version of every parameter and buffer."""
+    """Cache key of the packed weights: for every parameter and buffer its Python identity, storage
+    address, in-place version, dtype and device -- plus the module structure (a ReLU swapped out or
+    a Dropout removed changes what is packed without touching a tensor).  What no cheap key can see
+    -- ``param.data.mul_()`` (every ``.data`` is a fresh alias with its own version counter) or a
+    write through a raw pointer -- is what ``WrappedModelBase.invalidate_packed()`` is for."""
     key = []
     for net in nets:
+        key.append(tuple((name, type(mod).__name__, getattr(mod, "p", None))
+                         for name, mod in net.named_modules()))
         for t in list(net.parameters()) + list(net.buffers()):
-            key.append((t.data_ptr(), t._version, t.dtype, str(t.device)))
+            key.append((id(t), t.data_ptr(), t._version, t.dtype, str(t.device)))
     return tuple(key)

@@ -119,14 +119,37 @@ class WrappedModelBase(_Base):
     # (.to()), or after unpickling -- the reference checkpoints whole modules with torch.save
     # (training.py:54-65) and reloads them with torch.load (examples/bo_driven/bo.py:409).
     def _packed(self, nets: Sequence[nn.Sequential], device: torch.device) -> ops.PackedModel:
-        key = (str(device), tensors_version(nets))
+        anchor_first = bool(getattr(self, "anchor_first", True))
+        key = (str(device), tensors_version(nets), anchor_first)
         cache = self.__dict__.get("_uq_cache")
         if cache is None or cache[0] != key:
             if cache is not None:
                 cache[1].close()
-            cache = (key, ops.PackedModel(nets, device))
+            cache = (key, ops.PackedModel(nets, device, anchor_first=anchor_first))
             self.__dict__["_uq_cache"] = cache
         return cache[1]
+
+    def invalidate_packed(self) -> None:
+        """Drop the packed-weight cache explicitly (it is rebuilt on the next eval-mode forward).
+        The cache key follows parameter identity, versions and module structure; call this after
+        an edit it cannot see."""
+        cache = self.__dict__.get("_uq_cache")
+        if cache is not None:
+            cache[1].close()
+        self.__dict__["_uq_cache"] = None
+
+    def _shared_seed(self, seed: int, device) -> int:
+        """Under a shard every rank must key Philox with the SAME seed, whatever its own CPU
+        generator holds (``manual_seed(base + rank)`` is a common setup): rank 0's seed is
+        broadcast over the shard's group."""
+        shard = self.__dict__.get("uq_shard")
+        if shard is None or getattr(shard, "world", 1) <= 1:
+            return seed
+        import torch.distributed as dist
+        t = torch.tensor([seed], dtype=torch.int64, device=device)
+        dist.broadcast(t, src=dist.get_global_rank(shard.group, 0) if shard.group is not None else 0,
+                       group=shard.group)
+        return int(t.item())
 
     def __getstate__(self):
         state = dict(self.__dict__)
@@ -202,7 +225,7 @@ class MCDropoutModel(WrappedModelBase):
         ops._require_cuda(x, "x")
         packed = self._packed([self.model], x.device)
         # Philox stream keyed from torch's CPU generator: reproducible under torch.manual_seed
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        seed = self._shared_seed(int(torch.randint(0, 2 ** 62, (1,)).item()), x.device)
         mean, std = self._fused(packed, x, "mc_dropout", int(self.num_samples),
                                 dropout_p=float(self.dropout_percent),
                                 dropout_active=self._dropout_live(), seed=seed,
@@ -230,8 +253,15 @@ class MLPModel(WrappedModelBase):
 class DeltaUQMLP(WrappedModelBase):
     """Anchored (Delta-UQ) MLP.  The reference subclasses the third-party ``deltaUQ_MLP``
     (models.py:288); that package is absent from the reference tree, so the anchoring scheme here
-    follows the published method -- the network sees ``cat([x - a, a], dim=1)`` -- and is
-    PARITY-UNPINNED."""
+    follows the published method and is PARITY-UNPINNED.
+
+    ``anchor_first`` (class attribute, default True): the network sees ``cat([a, x - a], dim=1)``,
+    the channel order of the public ``deltauq`` package (``create_anchored_batch``:
+    ``torch.cat([A, diff], axis=1)``), so a first-Linear weight trained with the reference stack
+    means the same thing here.  Set it to False on an instance whose checkpoint was trained with
+    the other order, ``cat([x - a, a])``."""
+
+    anchor_first = True
 
     def __init__(self, base_model, estimator='std', num_anchors=5, anchored_batch_size=None,
                  **kwargs):
@@ -252,7 +282,9 @@ class DeltaUQMLP(WrappedModelBase):
         return loss
 
     def _anchored_torch(self, x, anchors_per_row):
-        return self.net(torch.cat([x - anchors_per_row, anchors_per_row], dim=1))
+        parts = ([anchors_per_row, x - anchors_per_row] if self.anchor_first
+                 else [x - anchors_per_row, anchors_per_row])
+        return self.net(torch.cat(parts, dim=1))
 
     def forward(self, x, return_ue=False):
         if self.training or self._anchors is None:
@@ -378,7 +410,7 @@ class PAGERMLP(DeltaUQMLP):
     """Delta-UQ + anchor-consistency (conformal) score, reference models.py:376-468.
 
     ``forward(x, return_ue=True)`` returns ``(mu, max(std, score))`` where ``mu, std`` are the
-    Delta-UQ mean/std over the anchors and ``score[n] = max_k |net(cat(a_k - x_n, x_n)) - Y_k|``
+    Delta-UQ mean/std over the anchors and ``score[n] = max_k |net(cat(x_n, a_k - x_n)) - Y_k|``
     (``_score_samples`` / ``_anchored_predictions``, :396-429: the roles of sample and anchor are
     swapped).  Both are one fused launch each; the second one takes the first one's ``std`` as a
     floor, so the ``[N, K]`` prediction matrix and the ``torch.maximum`` never materialise.

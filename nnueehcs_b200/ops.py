@@ -42,7 +42,13 @@ def reset_launch_count() -> None:
 class PackedModel:
     """Device-resident packed weights of K structurally identical MLPs (``uq_model_t``)."""
 
-    def __init__(self, nets: Sequence[nn.Sequential], device: torch.device):
+    def __init__(self, nets: Sequence[nn.Sequential], device: torch.device,
+                 anchor_first: bool = True):
+        """``anchor_first`` only matters for ``mode='delta_uq'`` / ``'pager'``: True (default) is the
+        public ``deltauq`` package's network input ``cat([anchor, x - anchor])``; False is
+        ``cat([x - anchor, anchor])``, the order ``uq_forward`` evaluates natively.  The two differ
+        by a swap of the first Linear's column halves (``UQ_MODEL_ANCHOR_FIRST``); the other modes
+        do not look at the flag."""
         lib = _lib.load()
         device = torch.device(device)
         if device.type != "cuda":
@@ -59,16 +65,19 @@ class PackedModel:
         self.d_out = sig[-1][1]
         self.dropout_widths = dropout_widths(all_blocks[0])
         self.device = device
+        self.anchor_first = bool(anchor_first)
         keep: list = []
         descs = (_lib.LayerDesc * (self.n_members * self.n_layers))()
         for k, blocks in enumerate(all_blocks):
             for l, blk in enumerate(blocks):
                 d = descs[k * self.n_layers + l]
                 self._fill(d, blk, device, keep)
+
         handle = C.c_void_p()
         with torch.cuda.device(device):
-            _lib.check(lib.uq_model_create(C.byref(handle), self.n_members, self.n_layers, descs,
-                                           _stream_ptr(device)))
+            _lib.check(lib.uq_model_create_ex(C.byref(handle), self.n_members, self.n_layers, descs,
+                                              _lib.MODEL_ANCHOR_FIRST if self.anchor_first else 0,
+                                              _stream_ptr(device)))
         self._handle = handle
         self._lib = lib
         self.supports_bf16 = bool(lib.uq_model_supports_bf16(handle))

@@ -192,6 +192,11 @@ def _combine_worker(rank, world, port, out_dir):
         m1, s1 = shard.forward(one, x, "ensemble", total_members=1, merge=_merge_standin)
         assert torch.allclose(m1, uq_oracle.ensemble_member_outputs(nets[:1], x)[0], atol=2e-7)
         assert torch.isnan(s1).all()              # unbiased std of a single member, like torch.std
+        # MC-dropout seeds: every rank keys Philox with rank 0's seed, whatever its own generator holds
+        from nnueehcs_b200.models import MCDropoutModel
+        mc = MCDropoutModel(nets[0], num_samples=4, dropout_percent=0.2)
+        mc.uq_shard = shard
+        assert mc._shared_seed(1000 + rank, "cpu") == 1000
         torch.save({"mean": mean, "std": std}, os.path.join(out_dir, f"crank{rank}.pt"))
     finally:
         dist.destroy_process_group()

@@ -322,8 +322,8 @@ def test_pager_matches_reference_class_golden(precision):
     # the by-product mean is the mean over anchors of the swapped-role predictions
     with torch.no_grad():
         cols = [uq_oracle.sequential_forward(
-            net, torch.cat([torch.from_numpy(g["anchors"])[j:j + 1] - torch.from_numpy(g["x"]),
-                            torch.from_numpy(g["x"])], dim=1)) for j in range(k)]
+            net, uq_oracle.anchored_input(torch.from_numpy(g["anchors"])[j:j + 1].expand(
+                g["x"].shape[0], -1), torch.from_numpy(g["x"]))) for j in range(k)]
     ref_pmean = torch.stack(cols).mean(0)
     tol = RTOL32 if precision != "bf16" else 3e-2
     assert float((pmean.cpu() - ref_pmean).abs().max()) <= tol * float(ref_pmean.abs().max()) + 1e-7
@@ -684,8 +684,9 @@ def test_pager_multi_output_and_anchor_prefix(precision):
     _, conf = packed.forward(x.to(DEV), "pager", total_members=k, precision=precision,
                              anchors=anchors.to(DEV), targets=ys.to(DEV))
     with torch.no_grad():
-        cols = [uq_oracle.sequential_forward(net, torch.cat([anchors[j:j + 1] - x, x], dim=1))
-                for j in range(k)]
+        cols = [uq_oracle.sequential_forward(
+            net, uq_oracle.anchored_input(anchors[j:j + 1].expand(x.shape[0], -1), x))
+            for j in range(k)]
     p = torch.stack(cols)                                            # [K, N, 3]
     ref = (p - ys[:k].unsqueeze(1)).abs().max(dim=0)[0]
     tol = RTOL32 if precision == "fp32" else 3e-2

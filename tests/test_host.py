@@ -243,6 +243,30 @@ def test_tensors_version_tracks_inplace_updates():
     with torch.no_grad():
         net[0].weight.add_(1.0)
     assert k0 != extract.tensors_version([net])
+    # a replaced parameter and a structural edit change the key (an edit through the .data
+    # alias cannot be seen by any version counter: invalidate_packed() is the explicit way)
+    k2 = extract.tensors_version([net])
+    net[0].bias = nn.Parameter(net[0].bias.detach().clone())
+    k3 = extract.tensors_version([net])
+    assert k3 != k2
+    net.append(nn.ReLU())
+    assert extract.tensors_version([net]) != k3
+
+
+def test_invalidate_packed_and_shared_seed_without_a_shard():
+    class _Handle:
+        closed = False
+
+        def close(self):
+            self.closed = True
+
+    model = EnsembleModel([nn.Sequential(nn.Linear(3, 1))])
+    h = _Handle()
+    model.__dict__["_uq_cache"] = ("key", h)
+    model.invalidate_packed()
+    assert h.closed and model.__dict__["_uq_cache"] is None
+    model.invalidate_packed()                      # idempotent
+    assert model._shared_seed(1234, "cpu") == 1234  # no shard: the rank's own seed
 
 
 def test_eval_forward_requires_cuda_and_never_falls_back(descr):
