@@ -571,7 +571,8 @@ def run_gpu(args):
 
     # ---- the 1e-5 parity mode on the same workload (N = 1 default line) ------------------------
     fp32_line = None
-    if world == 1 and precision == "bf16" and not args.no_fp32_leg:
+    if world == 1 and precision == "bf16" and not args.no_fp32_leg and \
+            (wl == DEFAULT_WORKLOAD or args.fp32_leg):
         for i in range(3):
             step(xs[i], "fp32")
         torch.cuda.synchronize()
@@ -674,6 +675,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fp32-leg", action="store_true",
+                    help="time the fp32 parity mode for a non-default workload as well")
     ap.add_argument("--no-fp32-leg", action="store_true",
                     help="skip timing the fp32 parity mode next to the bf16 line")
     ap.add_argument("--no-metric-kernels", action="store_true",

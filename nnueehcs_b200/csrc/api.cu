@@ -328,17 +328,17 @@ int uq_moments_merge_ex(const float* means, const float* m2s, int64_t shard_stri
 // native-RNG MC-dropout run can be replayed bit-for-bit through the oracle.
 __global__ void philox_export_kernel(uint8_t* __restrict__ out, int64_t n, int width, int passes,
                                      int layer, uq::PhiloxKey key, uint32_t thr16) {
-  const int64_t groups = (width + 7) / 8;
+  const int64_t groups = (width + 31) / 32;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)passes * n * groups;
   if (i >= total) return;
   const int64_t g = i % groups;
   const int64_t s = (i / groups) % n;
   const int64_t p = i / (groups * n);
-  const uint32_t m = uq::dropout_keep8(key, thr16, (uint32_t)p, (uint32_t)layer, (uint32_t)s,
-                                       (uint32_t)g);
-  uint8_t* o = out + (p * n + s) * width + g * 8;
-  for (int b = 0; b < 8 && g * 8 + b < width; ++b) o[b] = (m >> b) & 1u;
+  const uint32_t m = uq::dropout_keep32(key, thr16, (uint32_t)p, (uint32_t)layer, (uint32_t)s,
+                                        (uint32_t)g);
+  uint8_t* o = out + (p * n + s) * width + g * 32;
+  for (int b = 0; b < 32 && g * 32 + b < width; ++b) o[b] = (m >> b) & 1u;
 }
 
 int uq_philox_keep_masks(uint8_t* out, int64_t n, int32_t width, int32_t total_members,
@@ -348,7 +348,7 @@ int uq_philox_keep_masks(uint8_t* out, int64_t n, int32_t width, int32_t total_m
              UQ_ERR_INVALID, "uq_philox_keep_masks: bad argument");
   uq::PhiloxKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32),
                     (uint32_t)(offset & 0xffffffffu)};
-  const int64_t total = (int64_t)total_members * n * ((width + 7) / 8);
+  const int64_t total = (int64_t)total_members * n * ((width + 31) / 32);
   philox_export_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
                          static_cast<cudaStream_t>(stream)>>>(
       out, n, width, total_members, dropout_layer, key, uq::dropout_thr16((float)dropout_p));

@@ -144,6 +144,14 @@ sgemm_tn_kernel(const float* __restrict__ A, int64_t a_member_stride, int lda,
     const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (gm >= M) continue;
     const int64_t sample = ep.sample0 + gm;
+    // native masks: the thread's two runs of four columns sit in one 32-feature group each
+    uint32_t keep_lo = 0, keep_hi = 0;
+    if (ep.drop_mode == 2) {
+      keep_lo = dropout_keep32(ep.key, ep.thr16, pass, (uint32_t)ep.drop_layer, (uint32_t)sample,
+                               (uint32_t)((n0 + tx * 4) >> 5));
+      keep_hi = dropout_keep32(ep.key, ep.thr16, pass, (uint32_t)ep.drop_layer, (uint32_t)sample,
+                               (uint32_t)((n0 + 64 + tx * 4) >> 5));
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
@@ -156,8 +164,7 @@ sgemm_tn_kernel(const float* __restrict__ A, int64_t a_member_stride, int lda,
         const uint8_t keep = ep.mask[((int64_t)pass * ep.n_total + sample) * N + gn];
         v = v * (keep ? ep.drop_scale : 0.f);
       } else if (ep.drop_mode == 2) {
-        const bool keep = dropout_keep1(ep.key, ep.thr16, pass, (uint32_t)ep.drop_layer,
-                                        (uint32_t)sample, (uint32_t)gn);
+        const bool keep = ((j < 4 ? keep_lo : keep_hi) >> (gn & 31)) & 1u;
         v = v * (keep ? ep.drop_scale : 0.f);
       }
       C[(int64_t)gm * ldc + gn] = v;

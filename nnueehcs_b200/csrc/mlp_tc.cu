@@ -279,8 +279,19 @@ static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a,
   int splits = 1;
   if (a->output == UQ_OUT_MOMENTS) return 1;  // a K-shard hands raw moments to the caller
   if (a->mode == UQ_MODE_PAGER) return 1;      // the max over anchors is not a moment merge
-  // few sample tiles but many members/passes: also spread the member axis over the 74 SM pairs
-  while (units * splits < 148 && a->member_count / (splits * 2) >= 4 && splits < 64) splits *= 2;
+  // Split the member axis over clusters as well when that shortens the schedule: one launch is
+  // ceil(units * s / 74) rounds of the 74 SM pairs, a round costs members / s member-forwards plus
+  // a fixed per-unit part (input staging, Welford write-back; ~half a member-forward).  Few sample
+  // tiles with many passes spread out (10 units x 100 passes -> 7 splits = 70 of the 74 pairs, one
+  // round), and a ragged last round
+  // is evened out (256 units x 1000 passes: 4 rounds -> 7 half-rounds, -12 %).
+  double best = 0.0;
+  for (int s = 1; s <= 64; ++s) {
+    if (s > 1 && a->member_count / s < 4) break;
+    const double rounds = (double)((units * s + 73) / 74);
+    const double cost = rounds * ((double)((a->member_count + s - 1) / s) + 0.5);
+    if (s == 1 || cost < best * 0.97) best = cost, splits = s;   // a split must buy >= 3 %
+  }
   return splits;
 }
 

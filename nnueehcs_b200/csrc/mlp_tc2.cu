@@ -115,43 +115,64 @@ __device__ __forceinline__ void drain_trace(const DrainCtx& cx, unsigned kind, u
 #define UQ_DTRACE(kind, c)
 #endif
 
+// Keep-mask words of this warp's blocks of one layer-step: word 2 i + b = block b of the warp's
+// i-th chunk.  They depend on (pass, layer, row, feature) only, not on the activations, so the
+// epilogue computes them BEFORE it waits for the layer's MMAs -- Philox4x32-10 costs ~11
+// instructions per element, 5600 issue cycles per layer-step at H = 512, which used to sit between
+// "layer accumulated" and "first chunk released" (49 % of peak with dropout, 74 % without).
+template <int H, int NG>
+struct KeepWords {
+  static constexpr int CPW = (H / CHUNK_K + NG - 1) / NG;   // chunks per warp
+  uint32_t w[2 * CPW];
+};
+
+template <int H, int NG>
+__device__ __forceinline__ void compute_keep_words(const TcParams& p, const DrainCtx& cx,
+                                                   KeepWords<H, NG>& kw) {
+  constexpr int KC = H / CHUNK_K;
+#pragma unroll
+  for (int i = 0; i < KeepWords<H, NG>::CPW; ++i) {
+    const int c = cx.grp + NG * i;
+    if (c < KC) {
+      kw.w[2 * i] = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, c * CHUNK_K, cx.mask_layer, H);
+      kw.w[2 * i + 1] =
+          keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, c * CHUNK_K + 32, cx.mask_layer, H);
+    }
+  }
+}
+
 // Drain this warp's chunks of one layer-step.  NG == 2: 8 epilogue warps, TMEM loads run one
 // 32-column block ahead in a second register buffer.  NG == 4: 16 epilogue warps (4 per
 // scheduler) hide the tcgen05.ld / LDS latencies by thread-level parallelism instead, within the
 // 112-register budget that 18 warps leave.
 template <int H, int DOUT, int NG, bool RELU, bool DROP, bool LAST>
 __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx, int c_begin,
-                                           float (&dot)[DOUT]) {
+                                           const KeepWords<H, NG>& kw, float (&dot)[DOUT]) {
   constexpr int KC = H / CHUNK_K;
   if (NG == 2) {
     uint32_t acc0[32], acc1[32];
     if (c_begin < KC) tmem_ld32(cx.lane_addr + (uint32_t)(c_begin * CHUNK_K), acc0);
-#pragma unroll 1
-    for (int c = c_begin; c < KC; c += NG) {
+    auto chunk = [&](int c, uint32_t keep0, uint32_t keep1) {
       const int col0 = c * CHUNK_K;
       const uint32_t a_dst = cx.a_row + (uint32_t)c * CHUNK_BYTES;
-      uint32_t keep = 0xffffffffu;
       float4 bv[8];
       // ---- block 0 (columns col0 .. col0+31) ----
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
-      if (DROP) keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
       UQ_DTRACE(10, c);
       tmem_ld_wait();
       UQ_DTRACE(11, c);
       tmem_ld32(cx.lane_addr + (uint32_t)(col0 + 32), acc1);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep, cx.in_scale, a_dst, 0, cx.rx,
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep0, cx.in_scale, a_dst, 0, cx.rx,
                                             cx.wl_s + col0, cx.wl_g + col0, dot);
       UQ_DTRACE(12, c);
       // ---- block 1 (columns col0+32 .. col0+63) ----
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
         bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0 + 32)[j4];
-      if (DROP)
-        keep = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0 + 32, cx.mask_layer, H);
       tmem_ld_wait();
       if (c + NG < KC) tmem_ld32(cx.lane_addr + (uint32_t)(col0 + NG * CHUNK_K), acc0);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep, cx.in_scale, a_dst, 4, cx.rx,
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep1, cx.in_scale, a_dst, 4, cx.rx,
                                             cx.wl_s + col0 + 32, cx.wl_g + col0 + 32, dot);
       UQ_DTRACE(13, c);
       // chunk c: accumulator columns drained (+ A chunk rewritten) -> release to the MMA warp
@@ -161,6 +182,16 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
       __syncwarp();
       if (cx.lane == 0) mbar_arrive_cluster(cx.chunk_bar0 + 8 * c);
       UQ_DTRACE(15, c);
+    };
+    if (DROP) {   // unrolled: the precomputed keep words are indexed statically
+#pragma unroll
+      for (int i = 0; i < KeepWords<H, NG>::CPW; ++i) {
+        const int c = c_begin + NG * i;
+        if (c < KC) chunk(c, kw.w[2 * i], kw.w[2 * i + 1]);
+      }
+    } else {
+#pragma unroll 1
+      for (int c = c_begin; c < KC; c += NG) chunk(c, 0xffffffffu, 0xffffffffu);
     }
   } else {
 #pragma unroll 1
@@ -194,7 +225,10 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
 // ------------------------------------------------------------------------------------------------
 // the fused kernel (one cluster = two CTAs = two sample tiles)
 // ------------------------------------------------------------------------------------------------
-template <int H, int DOUT, int NG>
+// MC: the launch has live dropout (MC-dropout passes).  The dropout-free instantiation carries no
+// mask code at all -- the headline ensemble kernel keeps its 162 registers and zero spills whatever
+// the dropout path needs (keep words live across the layer barrier wait).
+template <int H, int DOUT, int NG, bool MC>
 __global__ void __launch_bounds__(Geo2<H, DOUT, NG>::NUM_THREADS, 1)
 uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
   using G = Geo2<H, DOUT, NG>;
@@ -519,7 +553,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           const bool last = (l == p.L_mma - 1);
           const bool relu = (p.relu_mask >> l) & 1u;
           const bool has_drop = (p.dropout_mask >> l) & 1u;
-          const int drop = has_drop ? p.drop_mode : 0;
+          const int drop = (MC && has_drop) ? p.drop_mode : 0;
 
           if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 0, g); }
           // ---- publish this step's bias (+ w_last) in smem, prefetch the next step's ------------
@@ -565,12 +599,15 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
 #endif
 #define UQ_STEP_DISPATCH(CALL_TTT, CALL_TFT, CALL_FTT, CALL_FFT, CALL_TTF, CALL_TFF, CALL_FTF, CALL_FFF) \
   if (last) {                                                                                      \
-    if (relu) { if (drop) { CALL_TTT; } else { CALL_TFT; } }                                       \
-    else { if (drop) { CALL_FTT; } else { CALL_FFT; } }                                            \
+    if (relu) { if (MC && drop) { CALL_TTT; } else { CALL_TFT; } }                                 \
+    else { if (MC && drop) { CALL_FTT; } else { CALL_FFT; } }                                      \
   } else {                                                                                         \
-    if (relu) { if (drop) { CALL_TTF; } else { CALL_TFF; } }                                       \
-    else { if (drop) { CALL_FTF; } else { CALL_FFF; } }                                            \
+    if (relu) { if (MC && drop) { CALL_TTF; } else { CALL_TFF; } }                                 \
+    else { if (MC && drop) { CALL_FTF; } else { CALL_FFF; } }                                      \
   }
+          // keep masks of this step while the layer's MMAs still run (see KeepWords)
+          KeepWords<H, NG> kw;
+          if (MC && NG == 2 && drop) compute_keep_words<H, NG>(p, cx, kw);
           // one lane polls the layer barrier, the rest of the warp parks on the warp barrier
           if (lane == 0) mbar_wait(bars + BAR_D_FULL, g & 1, p.error_flag, 5);
           __syncwarp();
@@ -581,14 +618,14 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           if (last && have_next) publish_x(ntile, p.member_begin + nk);
 
           const int c_begin = grp;
-          UQ_STEP_DISPATCH((drain_step<H, DOUT, NG, true, true, true>(p, cx, c_begin, dot)),
-                           (drain_step<H, DOUT, NG, true, false, true>(p, cx, c_begin, dot)),
-                           (drain_step<H, DOUT, NG, false, true, true>(p, cx, c_begin, dot)),
-                           (drain_step<H, DOUT, NG, false, false, true>(p, cx, c_begin, dot)),
-                           (drain_step<H, DOUT, NG, true, true, false>(p, cx, c_begin, dot)),
-                           (drain_step<H, DOUT, NG, true, false, false>(p, cx, c_begin, dot)),
-                           (drain_step<H, DOUT, NG, false, true, false>(p, cx, c_begin, dot)),
-                           (drain_step<H, DOUT, NG, false, false, false>(p, cx, c_begin, dot)))
+          UQ_STEP_DISPATCH((drain_step<H, DOUT, NG, true, MC, true>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, true, false, true>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, false, MC, true>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, false, false, true>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, true, MC, false>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, true, false, false>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, false, MC, false>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, false, false, false>(p, cx, c_begin, kw, dot)))
           if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 2, g); }
           if (has_drop) {
             if (p.masks) mask_layer += (size_t)p.total_members * (size_t)p.n * (size_t)H;
@@ -653,10 +690,10 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-template <int H, int DOUT, int NG>
-int launch_tc2(const TcParams& p, cudaStream_t st) {
+template <int H, int DOUT, int NG, bool MC>
+int launch_tc2_mc(const TcParams& p, cudaStream_t st) {
   using G = Geo2<H, DOUT, NG>;
-  auto kern = uq_mlp_tc2_kernel<H, DOUT, NG>;
+  auto kern = uq_mlp_tc2_kernel<H, DOUT, NG, MC>;
   // per-device launch geometry of this instantiation, queried once (the occupancy query and the
   // attribute call cost tens of microseconds, which shows on millisecond-sized forwards)
   static std::atomic<int> cached_clusters[64];   // zero-initialised; races only repeat the query
@@ -694,6 +731,12 @@ int launch_tc2(const TcParams& p, cudaStream_t st) {
   UQ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   UQ_LAUNCH_CHECK();
   return UQ_OK;
+}
+
+template <int H, int DOUT, int NG>
+int launch_tc2(const TcParams& p, cudaStream_t st) {
+  const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
+  return mc ? launch_tc2_mc<H, DOUT, NG, true>(p, st) : launch_tc2_mc<H, DOUT, NG, false>(p, st);
 }
 
 template <int DOUT, int NG>

@@ -76,49 +76,85 @@ constexpr uint32_t B3_D_FULL = 256;
 constexpr uint32_t B3_X_READY = 264;    //           leader only: 2 warps of each CTA
 constexpr uint32_t B3_TMEM_PTR = 272;
 
+// Keep-mask words of this warp's blocks of one layer-step, computed BEFORE the warp waits for the
+// layer's MMAs (they do not depend on the activations; see mlp_tc2.cu: KeepWords).  Word
+// 4 i + 2 e + b = block b of chunk e of the warp's i-th N tile.
+template <int H, int DOUT>
+struct KeepWords3 {
+  static constexpr int TPW = (Geo3<H, DOUT>::NTILES + NG - 1) / NG;   // N tiles per warp
+  uint32_t w[4 * TPW];
+};
+
+template <int H, int DOUT>
+__device__ __forceinline__ void compute_keep_words3(const TcParams& p, int grp, int ch, int drop,
+                                                    int kg, int drop_ord, int64_t grow,
+                                                    const uint8_t* mask_layer,
+                                                    KeepWords3<H, DOUT>& kw) {
+  using G = Geo3<H, DOUT>;
+#pragma unroll
+  for (int i = 0; i < KeepWords3<H, DOUT>::TPW; ++i) {
+    const int j = grp + NG * i;
+    if (j < G::NTILES) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col0 = (G::CPT * j + 2 * ch + e) * CHUNK_K;
+        kw.w[4 * i + 2 * e] = keep_bits32(p, drop, kg, drop_ord, grow, col0, mask_layer, H);
+        kw.w[4 * i + 2 * e + 1] = keep_bits32(p, drop, kg, drop_ord, grow, col0 + 32, mask_layer, H);
+      }
+    }
+  }
+}
+
 template <int H, int DOUT, bool RELU, bool DROP, bool LAST>
 __device__ __forceinline__ void drain3(const TcParams& p, uint32_t lane_addr, uint32_t a_row, int rx,
                                        int grp, int ch, int lane, uint32_t chunk_bar0,
                                        const float* bias_s, const float* wl_s, const float* wl_g,
-                                       int drop, int kg, int drop_ord, int64_t grow,
-                                       const uint8_t* mask_layer, float in_scale,
+                                       const KeepWords3<H, DOUT>& kw, float in_scale,
                                        float (&dot)[DOUT]) {
   using G = Geo3<H, DOUT>;
   uint32_t acc0[32], acc1[32];
   // this warp's chunks, in order: for j = grp, grp + 2, ...: c = CPT j + 2 ch + {0, 1}
-  int j = grp;
-  if (j < G::NTILES) tmem_ld32(lane_addr + (uint32_t)(j * G::TCOLS), acc0);
-#pragma unroll 1
-  for (; j < G::NTILES; j += NG) {
-#pragma unroll 1
-    for (int e = 0; e < 2; ++e) {
-      const int c = G::CPT * j + 2 * ch + e;
-      const int col0 = c * CHUNK_K;                                  // feature index
-      const uint32_t tcol = (uint32_t)(j * G::TCOLS + e * CHUNK_K);  // TMEM column of this chunk
-      const uint32_t a_dst = a_row + (uint32_t)c * CHUNK3_BYTES;
-      uint32_t keep = 0xffffffffu;
-      float4 bv[8];
+  if (grp < G::NTILES) tmem_ld32(lane_addr + (uint32_t)(grp * G::TCOLS), acc0);
+  auto chunk = [&](int j, int e, uint32_t keep0, uint32_t keep1) {
+    const int c = G::CPT * j + 2 * ch + e;
+    const int col0 = c * CHUNK_K;                                  // feature index
+    const uint32_t tcol = (uint32_t)(j * G::TCOLS + e * CHUNK_K);  // TMEM column of this chunk
+    const uint32_t a_dst = a_row + (uint32_t)c * CHUNK3_BYTES;
+    float4 bv[8];
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0)[j4];
-      if (DROP) keep = keep_bits32(p, drop, kg, drop_ord, grow, col0, mask_layer, H);
-      tmem_ld_wait();
-      tmem_ld32(lane_addr + tcol + 32, acc1);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep, in_scale, a_dst, 0, rx,
-                                                wl_s + col0, wl_g + col0, dot);
+    for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0)[j4];
+    tmem_ld_wait();
+    tmem_ld32(lane_addr + tcol + 32, acc1);
+    epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep0, in_scale, a_dst, 0, rx,
+                                              wl_s + col0, wl_g + col0, dot);
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
-      if (DROP) keep = keep_bits32(p, drop, kg, drop_ord, grow, col0 + 32, mask_layer, H);
-      tmem_ld_wait();
-      // next chunk of this warp: e == 0 -> same tile, next 64 TMEM columns; else tile j + NG
-      if (e == 0) tmem_ld32(lane_addr + tcol + CHUNK_K, acc0);
-      else if (j + NG < G::NTILES) tmem_ld32(lane_addr + (uint32_t)((j + NG) * G::TCOLS), acc0);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep, in_scale, a_dst, 4, rx,
-                                                wl_s + col0 + 32, wl_g + col0 + 32, dot);
-      tc_fence_before();
-      if (!LAST) fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(chunk_bar0 + 8 * c);
+    for (int j4 = 0; j4 < 8; ++j4)
+      bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
+    tmem_ld_wait();
+    // next chunk of this warp: e == 0 -> same tile, next 64 TMEM columns; else tile j + NG
+    if (e == 0) tmem_ld32(lane_addr + tcol + CHUNK_K, acc0);
+    else if (j + NG < G::NTILES) tmem_ld32(lane_addr + (uint32_t)((j + NG) * G::TCOLS), acc0);
+    epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep1, in_scale, a_dst, 4, rx,
+                                              wl_s + col0 + 32, wl_g + col0 + 32, dot);
+    tc_fence_before();
+    if (!LAST) fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(chunk_bar0 + 8 * c);
+  };
+  if (DROP) {   // unrolled: the precomputed keep words are indexed statically
+#pragma unroll
+    for (int i = 0; i < KeepWords3<H, DOUT>::TPW; ++i) {
+      const int j = grp + NG * i;
+      if (j < G::NTILES) {
+        chunk(j, 0, kw.w[4 * i], kw.w[4 * i + 1]);
+        chunk(j, 1, kw.w[4 * i + 2], kw.w[4 * i + 3]);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int j = grp; j < G::NTILES; j += NG) {
+#pragma unroll 1
+      for (int e = 0; e < 2; ++e) chunk(j, e, 0xffffffffu, 0xffffffffu);
     }
   }
 }
@@ -415,6 +451,9 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
           if (last && have_next && use_stash && (ntile != tile))
             build_x(ntile, p.member_begin + nk, true);
 
+          // keep masks of this step while the layer's MMAs still run
+          KeepWords3<H, DOUT> kw;
+          if (drop) compute_keep_words3<H, DOUT>(p, grp, ch, drop, kg, drop_ord, grow, mask_layer, kw);
           if (lane == 0) mbar_wait(bars + B3_D_FULL, g & 1, p.error_flag, 5);
           __syncwarp();
           tc_fence_after();
@@ -425,7 +464,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
               (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
 #define UQ_DRAIN3(R, D, L)                                                                       \
   drain3<H, DOUT, R, D, L>(p, lane_addr, a_row, rx, grp, ch, lane, chunk_bar0, aux, aux + H, wl_g, \
-                           drop, kg, drop_ord, grow, mask_layer, in_scale, dot)
+                           kw, in_scale, dot)
           if (last) {
             if (relu) { if (drop) UQ_DRAIN3(true, true, true); else UQ_DRAIN3(true, false, true); }
             else { if (drop) UQ_DRAIN3(false, true, true); else UQ_DRAIN3(false, false, true); }

@@ -70,6 +70,7 @@ struct GeoX {
   static constexpr int CPT = NT / CHUNK_K;               // chunks per N tile
   static constexpr int TCOLS = NT / 2;                   // TMEM columns per N tile
   static constexpr int BPT = TCOLS / 32;                 // 32-column drain blocks per (tile, half)
+  static constexpr int BLOCKS_PER_WARP = (NTILES * BPT + NG - 1) / NG;
   static constexpr int ACC_COLS = H / 2;                 // TMEM columns of one accumulator tile set
   static constexpr int NEED_COLS = H;                    // main tiles, then correction tiles
   static constexpr int TMEM_COLS =
@@ -240,12 +241,11 @@ template <int H, int DOUT, bool RELU, bool DROP, bool LAST>
 __device__ __forceinline__ void drain_x(const TcParams& p, uint32_t lane_addr, uint32_t a_row,
                                         int rx, int grp, int ch, int lane, uint32_t chunk_bar0,
                                         const float* bias_s, const float* wl_s, const float* wl_g,
-                                        int drop, int kg, int drop_ord, int64_t grow,
-                                        const uint8_t* mask_layer, float rs, float s_out,
-                                        float (&dot)[DOUT], float& ss) {
+                                        const uint32_t (&keepw)[GeoX<H, DOUT>::BLOCKS_PER_WARP],
+                                        float rs, float s_out, float (&dot)[DOUT], float& ss) {
   using G = GeoX<H, DOUT>;
   constexpr int NBLK = G::NTILES * G::BPT;             // blocks of this column half, all tiles
-  constexpr int TOTAL = (NBLK + NG - 1) / NG;          // upper bound of blocks per warp
+  constexpr int TOTAL = G::BLOCKS_PER_WARP;            // upper bound of blocks per warp
   // i-th block of this warp: t = grp + NG i  ->  tile j = t / BPT, block b = t % BPT; only the
   // tail can be missing (t >= NBLK), so "next block exists" is a plain bound check
   auto valid = [&](int i) { return grp + NG * i < NBLK; };
@@ -264,7 +264,6 @@ __device__ __forceinline__ void drain_x(const TcParams& p, uint32_t lane_addr, u
     tmem_ld16(lane_addr + (uint32_t)G::ACC_COLS + col, c);
   };
   if (valid(0)) issue(0);
-  uint32_t keep = 0xffffffffu;
 #pragma unroll
   for (int u = 0; u < 2 * TOTAL; ++u) {
     const int i = u >> 1, h = u & 1;
@@ -274,7 +273,7 @@ __device__ __forceinline__ void drain_x(const TcParams& p, uint32_t lane_addr, u
     const int piece0 = ((f0 & 63) >> 3) + 2 * h;
     const uint32_t a1_dst = a_row + (uint32_t)cidx * CHUNKX_BYTES;
     const uint32_t a2_dst = a1_dst + (uint32_t)G::KC * CHUNKX_BYTES;
-    if (DROP && h == 0) keep = keep_bits32(p, drop, kg, drop_ord, grow, f0, mask_layer, H);
+    const uint32_t keep = DROP ? keepw[i] : 0xffffffffu;
     float a[16];
     tmem_ld_wait();
 #pragma unroll
@@ -639,6 +638,19 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
             pow2_scale(bound, s_out, s_inv);
           }
 
+          // keep masks of this step (they do not depend on the activations) while the layer's
+          // MMAs still run: word i = the warp's i-th block (see drain_x)
+          uint32_t keepw[G::BLOCKS_PER_WARP];
+          if (drop) {
+#pragma unroll
+            for (int i = 0; i < G::BLOCKS_PER_WARP; ++i) {
+              const int t = grp + NG * i;
+              if (t < G::NTILES * G::BPT)
+                keepw[i] = keep_bits32(p, drop, kg, drop_ord, grow,
+                                       (t / G::BPT) * G::NT + ch * G::TCOLS + 32 * (t % G::BPT),
+                                       mask_layer, H);
+            }
+          }
           if (lane == 0) mbar_wait(bars + BX_D_FULL, g & 1, p.error_flag, 5);
           __syncwarp();
           tc_fence_after();
@@ -648,7 +660,7 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
           float ss = 0.f;
 #define UQ_DRAINX(R, D, L)                                                                        \
   drain_x<H, DOUT, R, D, L>(p, lane_addr, a_row, rx, grp, ch, lane, chunk_bar0, aux, aux + H, wl_g, \
-                            drop, kg, drop_ord, grow, mask_layer, rs, s_out, dot, ss)
+                            keepw, rs, s_out, dot, ss)
           if (last) {
             if (relu) { if (drop) UQ_DRAINX(true, true, true); else UQ_DRAINX(true, false, true); }
             else { if (drop) UQ_DRAINX(false, true, true); else UQ_DRAINX(false, false, true); }
