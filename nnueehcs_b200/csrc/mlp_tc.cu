@@ -273,7 +273,8 @@ int tc_pack(uq_model* m, cudaStream_t st) {
 static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a, bool split) {
   // sample rows one cluster (CTA pair) works on at a time
   const bool narrow = tc4_supported(m->tc.hidden, dout_pad(m->tc.d_out)) && !getenv("UQ_TC_NO_SLOTS");
-  const int64_t rows = split ? tcx_rows_per_unit()
+  const bool narrow_x = tcx4_supported(m->tc.hidden, dout_pad(m->tc.d_out)) && !getenv("UQ_TC_NO_SLOTS");
+  const int64_t rows = split ? (narrow_x ? tcx4_rows_per_unit() : tcx_rows_per_unit())
                        : m->tc.hidden > 512 ? TILE_M : narrow ? tc4_rows_per_unit() : 2 * TILE_M;
   const int64_t units = (n + rows - 1) / rows;
   int splits = 1;
@@ -434,7 +435,9 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
 #endif
 
   const bool narrow = tc4_supported(t.hidden, dout_pad(t.d_out)) && !getenv("UQ_TC_NO_SLOTS");
-  const int rc = split           ? tcx_launch(p, t.hidden, dout_pad(t.d_out), st)
+  const bool narrow_x = tcx4_supported(t.hidden, dout_pad(t.d_out)) && !getenv("UQ_TC_NO_SLOTS");
+  const int rc = split && narrow_x ? tcx4_launch(p, t.hidden, st)
+                 : split          ? tcx_launch(p, t.hidden, dout_pad(t.d_out), st)
                  : t.hidden > 512 ? tc3_launch(p, t.hidden, dout_pad(t.d_out), st)
                  : narrow         ? tc4_launch(p, t.hidden, st)
                                   : tc2_launch(p, t.hidden, dout_pad(t.d_out), st);

@@ -69,5 +69,10 @@ int tc4_rows_per_unit();
 int tcx_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st);
 bool tcx_supported(int hidden);
 int tcx_rows_per_unit();
+// mlp_tcx4.cu: the same split mode with four 64-row tile slots per CTA for hidden widths 64 / 128,
+// d_out 1 (the reference's own 6 x 128 architecture); same weight image
+int tcx4_launch(const tc::TcParams& p, int hidden, cudaStream_t st);
+bool tcx4_supported(int hidden, int dout_pad);
+int tcx4_rows_per_unit();
 
 }  // namespace uq
