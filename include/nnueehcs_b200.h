@@ -86,7 +86,9 @@ typedef struct uq_forward_args {
   int32_t member_count; /*   of this call; full range = [0, K)                            */
   int32_t total_members; /* K of the whole job (Philox pass ids and anchors index by global id) */
   int32_t dropout_active; /* 0: "dropout-off" parity case (P identical passes) */
-  int32_t reserved0;
+  int32_t row_base;     /* native Philox masks only: global index of x's first row, so that a rank
+                           that runs a slice [row_base, row_base + n) of the samples draws the same
+                           bits as the unsharded call (0 for a whole-batch call)              */
   double dropout_p;     /* MCDropoutModel.dropout_percent (models.py:132-134) */
   uint64_t philox_seed; /* native masks: Philox4x32-10 keyed by seed, counter =     */
   uint64_t philox_offset; /*   (global pass id, dropout layer, sample, feature group)  */

@@ -62,7 +62,7 @@ class ForwardArgs(C.Structure):
         ("member_count", C.c_int32),
         ("total_members", C.c_int32),
         ("dropout_active", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("row_base", C.c_int32),
         ("dropout_p", C.c_double),
         ("philox_seed", C.c_uint64),
         ("philox_offset", C.c_uint64),

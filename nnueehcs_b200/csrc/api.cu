@@ -219,6 +219,7 @@ static int check_args(const uq_model_t* m, const float* x, int64_t n, const uq_f
     UQ_REQUIRE(m->n_members == 1, UQ_ERR_INVALID,
                "MC-dropout / Delta-UQ need a single packed network, got %d", m->n_members);
   }
+  UQ_REQUIRE(a->row_base >= 0, UQ_ERR_INVALID, "uq_forward: row_base %d < 0", a->row_base);
   if (a->mode == UQ_MODE_MC_DROPOUT && a->dropout_active) {
     UQ_REQUIRE(a->dropout_p >= 0.0 && a->dropout_p < 1.0, UQ_ERR_INVALID,
                "dropout_p must be in [0, 1), got %g", a->dropout_p);

@@ -29,7 +29,8 @@ struct Epilogue {
   int drop_mode;       // 0 none, 1 injected byte masks, 2 native philox
   const uint8_t* mask; // injected: base of this dropout layer's [total_members][n_total][N] block
   int64_t n_total;     // samples of the whole call (mask row stride)
-  int64_t sample0;     // global index of this chunk's first sample
+  int64_t sample0;     // index (inside this call) of this chunk's first sample
+  int64_t philox_row0; // global index of the call's first row (Philox sample counter)
   int pass0;           // global id of this launch's first member (blockIdx.z = 0)
   int drop_layer;      // dropout layer ordinal (philox counter)
   float drop_scale;    // fl32(1 / fl32(1-p))
@@ -147,9 +148,10 @@ sgemm_tn_kernel(const float* __restrict__ A, int64_t a_member_stride, int lda,
     // native masks: the thread's two runs of four columns sit in one 32-feature group each
     uint32_t keep_lo = 0, keep_hi = 0;
     if (ep.drop_mode == 2) {
-      keep_lo = dropout_keep32(ep.key, ep.thr16, pass, (uint32_t)ep.drop_layer, (uint32_t)sample,
+      const uint32_t prow = (uint32_t)(sample + ep.philox_row0);
+      keep_lo = dropout_keep32(ep.key, ep.thr16, pass, (uint32_t)ep.drop_layer, prow,
                                (uint32_t)((n0 + tx * 4) >> 5));
-      keep_hi = dropout_keep32(ep.key, ep.thr16, pass, (uint32_t)ep.drop_layer, (uint32_t)sample,
+      keep_hi = dropout_keep32(ep.key, ep.thr16, pass, (uint32_t)ep.drop_layer, prow,
                                (uint32_t)((n0 + 64 + tx * 4) >> 5));
     }
 #pragma unroll
@@ -361,6 +363,7 @@ int fp32_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_
           ep.mask = nullptr;
           ep.n_total = n;
           ep.sample0 = s0;
+          ep.philox_row0 = a->row_base;
           ep.pass0 = gm0;
           ep.drop_layer = drop_ord;
           ep.drop_scale = drop_scale;

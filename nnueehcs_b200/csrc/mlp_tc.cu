@@ -280,12 +280,28 @@ static int choose_splits(const uq_model* m, int64_t n, const uq_forward_args* a,
   int splits = 1;
   if (a->output == UQ_OUT_MOMENTS) return 1;  // a K-shard hands raw moments to the caller
   if (a->mode == UQ_MODE_PAGER) return 1;      // the max over anchors is not a moment merge
-  // Split the member axis over clusters as well when that shortens the schedule: one launch is
+  // (1) Ensembles whose weights exceed the L2 (each die caches its own copy: ~63 MB): cut the
+  // members into ~32 MB groups, which mlp_tc3.cu / mlp_tcx.cu walk split-major -- every cluster on
+  // the same group at the same time (ensemble8x1024_256k: 2.86 GB of DRAM reads per launch and
+  // 26.7 ms -> 22.7 ms).
+  const bool group_kernel = split ? !narrow_x : m->tc.hidden > 512;   // mlp_tcx.cu / mlp_tc3.cu
+  if (group_kernel && a->mode == UQ_MODE_ENSEMBLE) {
+    const double member_mb = split
+        ? (double)m->tc.x_stages_per_member * (double)m->tc.x_stage_bytes / 1048576.0
+        : (double)m->tc.stages_per_member * (double)m->tc.stage_bytes / 1048576.0;
+    if (member_mb * a->member_count > 48.0) {
+      int s = (int)((member_mb * a->member_count + 31.9) / 32.0);
+      if (s > a->member_count) s = a->member_count;
+      if (s > 64) s = 64;
+      if (s > 1 && units >= 74) return s;
+    }
+  }
+  // (2) Split the member axis over clusters when that shortens the schedule: one launch is
   // ceil(units * s / 74) rounds of the 74 SM pairs, a round costs members / s member-forwards plus
   // a fixed per-unit part (input staging, Welford write-back; ~half a member-forward).  Few sample
   // tiles with many passes spread out (10 units x 100 passes -> 7 splits = 70 of the 74 pairs, one
-  // round), and a ragged last round
-  // is evened out (256 units x 1000 passes: 4 rounds -> 7 half-rounds, -12 %).
+  // round), and a ragged last round is evened out (256 units x 1000 passes: 4 rounds -> 7
+  // half-rounds, -12 %).
   double best = 0.0;
   for (int s = 1; s <= 64; ++s) {
     if (s > 1 && a->member_count / s < 4) break;
@@ -335,6 +351,7 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   memset(&p, 0, sizeof(p));
   p.x = x;
   p.n = n;
+  p.row_base = a->row_base;
   p.d_in = m->d_in;
   const bool anchored = a->mode == UQ_MODE_DELTA_UQ || a->mode == UQ_MODE_PAGER;
   const bool pager = a->mode == UQ_MODE_PAGER;
@@ -342,6 +359,11 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.mode = a->mode;
   p.n_tiles = (int)((n + TILE_M - 1) / TILE_M);
   p.splits = choose_splits(m, n, a, split);
+  {
+    const bool nx = tcx4_supported(t.hidden, dout_pad(t.d_out)) && !getenv("UQ_TC_NO_SLOTS");
+    const bool group_kernel = split ? !nx : t.hidden > 512;
+    p.split_major = (group_kernel && a->mode == UQ_MODE_ENSEMBLE && p.splits > 1) ? 1 : 0;
+  }
   p.member_begin = a->member_begin;
   p.member_count = a->member_count;
   p.total_members = a->total_members;

@@ -185,7 +185,15 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
   const int n_tiles = (int)((p.n + ROWS - 1) / ROWS);
-  const int n_units = ((n_tiles + 1) >> 1) * p.splits;
+  const int n_tp = (n_tiles + 1) >> 1;             // tile pairs
+  const int n_units = n_tp * p.splits;
+  // unit -> (member split, tile pair).  Tile-major (default): a cluster's consecutive units walk
+  // the splits of one tile pair.  Split-major (p.split_major): all clusters work on the tile pairs
+  // of split 0 first, then of split 1, ... so that only one split's weights are live in L2 at a
+  // time -- 8 members x 14.7 MB of a 7 x 1024 ensemble do not fit the 2 x 63 MB L2 and were
+  // re-read from HBM every round (2.86 GB of DRAM reads per launch against 125 MB of weights).
+  auto unit_split = [&](int unit) { return p.split_major ? unit / n_tp : unit % p.splits; };
+  auto unit_tp = [&](int unit) { return p.split_major ? unit % n_tp : unit / p.splits; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -209,7 +217,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
       uint32_t slot = 0, phase = 0;
       const size_t member_bytes = (size_t)p.stages_per_member * STAGE_BYTES;
       for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
-        const int split = unit % p.splits;
+        const int split = unit_split(unit);
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
         for (int k = mb; k < me; ++k) {
@@ -232,7 +240,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
       uint32_t slot = 0, phase = 0;
       const uint32_t full0 = mapa_shared(bars + B3_W_FULL, 0);
       for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
-        const int split = unit % p.splits;
+        const int split = unit_split(unit);
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
         const int n_stages = (me - mb) * p.stages_per_member;
@@ -280,7 +288,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
           mbar_wait_cluster_inline(bars + B3_CHUNK + 8 * (CPT * nt + i), prev_par, p.error_flag, 3);
     };
     for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
-      const int split = unit % p.splits;
+      const int split = unit_split(unit);
       const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
       const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
       for (int k = mb; k < me; ++k, ++xm) {
@@ -399,7 +407,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
 
     bool first_step = true;
     for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
-      const int tile = 2 * (unit / p.splits) + (int)rank, split = unit % p.splits;
+      const int tile = 2 * unit_tp(unit) + (int)rank, split = unit_split(unit);
       const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
       const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
       const int64_t grow = (int64_t)tile * ROWS + row;
@@ -429,8 +437,8 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
         if (nk >= me) {
           const int nunit = unit + n_clusters;
           have_next = nunit < n_units;
-          ntile = 2 * (nunit / p.splits) + (int)rank;
-          nk = (int)(((int64_t)p.member_count * (nunit % p.splits)) / p.splits);
+          ntile = 2 * unit_tp(nunit) + (int)rank;
+          nk = (int)(((int64_t)p.member_count * unit_split(nunit)) / p.splits);
         }
 
         for (int l = 0; l < p.L_mma; ++l, ++g) {

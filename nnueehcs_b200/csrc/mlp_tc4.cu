@@ -72,34 +72,35 @@ constexpr uint32_t B4_X_READY = 192;    // TS x 8 B   leader only: 4 warps of ea
 constexpr uint32_t B4_TMEM_PTR = 224;
 
 // drain all chunks of one slot (this warp: 32 rows of it)
+// keepw: the keep-mask words of the slot's 2 KC blocks, computed by the caller BEFORE it waits for
+// the slot's MMAs (they do not depend on the activations; several independent Philox chains in
+// flight hide each other's latency -- with two warps per scheduler a single chain does not)
 template <int H, bool RELU, bool DROP, bool LAST>
-__device__ __forceinline__ void drain4(const TcParams& p, uint32_t lane_addr, uint32_t a_row, int rx,
-                                       const float* bias_s, const float* wl_s, int drop,
-                                       int kg, int drop_ord, int64_t grow,
-                                       const uint8_t* mask_layer, float in_scale, float (&dot)[1]) {
+__device__ __forceinline__ void drain4(uint32_t lane_addr, uint32_t a_row, int rx,
+                                       const float* bias_s, const float* wl_s,
+                                       const uint32_t (&keepw)[2 * (H / CHUNK_K)], float in_scale,
+                                       float (&dot)[1]) {
   constexpr int KC = H / CHUNK_K;
   uint32_t acc0[32], acc1[32];
   tmem_ld32(lane_addr, acc0);
-#pragma unroll 1
+#pragma unroll
   for (int c = 0; c < KC; ++c) {
     const int col0 = c * CHUNK_K;
     const uint32_t a_dst = a_row + (uint32_t)c * CHUNK_BYTES;
-    uint32_t keep = 0xffffffffu;
     float4 bv[8];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0)[j4];
-    if (DROP) keep = keep_bits32(p, drop, kg, drop_ord, grow, col0, mask_layer, H);
     tmem_ld_wait();
     tmem_ld32(lane_addr + (uint32_t)(col0 + 32), acc1);
-    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc0, bv, keep, in_scale, a_dst, 0, rx, wl_s + col0,
-                                           wl_s + col0, dot);
+    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc0, bv, DROP ? keepw[2 * c] : 0xffffffffu, in_scale,
+                                           a_dst, 0, rx, wl_s + col0, wl_s + col0, dot);
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
-    if (DROP) keep = keep_bits32(p, drop, kg, drop_ord, grow, col0 + 32, mask_layer, H);
     tmem_ld_wait();
     if (c + 1 < KC) tmem_ld32(lane_addr + (uint32_t)(col0 + CHUNK_K), acc0);
-    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc1, bv, keep, in_scale, a_dst, 4, rx,
-                                           wl_s + col0 + 32, wl_s + col0 + 32, dot);
+    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc1, bv, DROP ? keepw[2 * c + 1] : 0xffffffffu,
+                                           in_scale, a_dst, 4, rx, wl_s + col0 + 32,
+                                           wl_s + col0 + 32, dot);
   }
 }
 
@@ -390,6 +391,13 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll 1   // one copy of the drain code for all slots (it is ~1.5 k instructions)
           for (int t = grp; t < TS; t += NG4) {
             float dslot[1] = {0.f};
+            const int64_t grow = (int64_t)tile_of(unit, t) * TILE_M + row;
+            uint32_t keepw[2 * KC];
+            if (drop) {
+#pragma unroll
+              for (int b = 0; b < 2 * KC; ++b)
+                keepw[b] = keep_bits32(p, drop, kg, drop_ord, grow, 32 * b, mask_layer, H);
+            }
             if (lane == 0) mbar_wait(bars + B4_D_FULL + 8 * t, g & 1, p.error_flag, 5);
             __syncwarp();
             tc_fence_after();
@@ -397,10 +405,8 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
 
             const uint32_t lane_addr = lane_addr0 + (uint32_t)(t * H);
             const uint32_t a_row = a_row0 + (uint32_t)(t * G::A_SLOT_BYTES);
-            const int64_t grow = (int64_t)tile_of(unit, t) * TILE_M + row;
-#define UQ_DRAIN4(R, D, L)                                                                        \
-  drain4<H, R, D, L>(p, lane_addr, a_row, rx, aux, aux + H, drop, kg, drop_ord, grow,             \
-                     mask_layer, in_scale, dslot)
+#define UQ_DRAIN4(R, D, L) \
+  drain4<H, R, D, L>(lane_addr, a_row, rx, aux, aux + H, keepw, in_scale, dslot)
             if (last) {
               if (relu) { if (drop) UQ_DRAIN4(true, true, true); else UQ_DRAIN4(true, false, true); }
               else { if (drop) UQ_DRAIN4(false, true, true); else UQ_DRAIN4(false, false, true); }

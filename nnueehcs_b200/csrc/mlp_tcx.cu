@@ -189,7 +189,12 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
   const int n_tiles = (int)((p.n + ROWS - 1) / ROWS);
-  const int n_units = ((n_tiles + 1) >> 1) * p.splits;
+  const int n_tp = (n_tiles + 1) >> 1;             // tile pairs
+  const int n_units = n_tp * p.splits;
+  // unit -> (member split, tile pair); split-major keeps one member group's weights L2-resident
+  // (see mlp_tc3.cu)
+  auto unit_split = [&](int unit) { return p.split_major ? unit / n_tp : unit % p.splits; };
+  auto unit_tp = [&](int unit) { return p.split_major ? unit % n_tp : unit / p.splits; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -213,7 +218,7 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
       uint32_t slot = 0, phase = 0;
       const size_t member_bytes = (size_t)p.stages_per_member * STAGE_BYTES;
       for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
-        const int split = unit % p.splits;
+        const int split = unit_split(unit);
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
         for (int k = mb; k < me; ++k) {
@@ -236,7 +241,7 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
       uint32_t slot = 0, phase = 0;
       const uint32_t full0 = mapa_shared(bars + BX_W_FULL, 0);
       for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
-        const int split = unit % p.splits;
+        const int split = unit_split(unit);
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
         const int n_stages = (me - mb) * p.stages_per_member;
@@ -286,7 +291,7 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
           mbar_wait_cluster_inline(bars + BX_CHUNK + 8 * (CPT * nt + i), prev_par, p.error_flag, 3);
     };
     for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
-      const int split = unit % p.splits;
+      const int split = unit_split(unit);
       const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
       const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
       for (int k = mb; k < me; ++k, ++xm) {
@@ -430,7 +435,7 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
 
     bool first_step = true;
     for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++ucount) {
-      const int tile = 2 * (unit / p.splits) + (int)rank, split = unit % p.splits;
+      const int tile = 2 * unit_tp(unit) + (int)rank, split = unit_split(unit);
       const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
       const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
       const int64_t grow = (int64_t)tile * ROWS + row;
@@ -462,8 +467,8 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
         if (nk >= me) {
           const int nunit = unit + n_clusters;
           have_next = nunit < n_units;
-          ntile = 2 * (nunit / p.splits) + (int)rank;
-          nk = (int)(((int64_t)p.member_count * (nunit % p.splits)) / p.splits);
+          ntile = 2 * unit_tp(nunit) + (int)rank;
+          nk = (int)(((int64_t)p.member_count * unit_split(nunit)) / p.splits);
         }
         const bool next_unit = (k + 1 >= me);   // the next member belongs to the next unit
 

@@ -62,8 +62,8 @@ __device__ __forceinline__ uint32_t keep_bits32(const TcParams& p, int drop, int
                                                 int H) {
   uint32_t keep = 0;
   if (drop == 2) {
-    keep = dropout_keep32(p.key, p.thr16, (uint32_t)kg, (uint32_t)drop_ord, (uint32_t)grow,
-                          (uint32_t)(col0 >> 5));
+    keep = dropout_keep32(p.key, p.thr16, (uint32_t)kg, (uint32_t)drop_ord,
+                          (uint32_t)(grow + p.row_base), (uint32_t)(col0 >> 5));
   } else if (grow < p.n) {
     const uint4* mrow = reinterpret_cast<const uint4*>(
         mask_layer + ((size_t)kg * (size_t)p.n + (size_t)grow) * H + col0);

@@ -16,11 +16,13 @@ constexpr int TRACE_ROLES = 6;
 struct TcParams {
   const float* x;        // [n][d_x]
   int64_t n;
+  int64_t row_base;      // global index of row 0 (Philox sample counter = row_base + row)
   int d_x;               // features of x (d_in, or d_in/2 for Delta-UQ)
   int d_in;              // network input features
   int mode;
   int n_tiles;
   int splits;            // member-axis splits (partial moments when > 1)
+  int split_major;       // mlp_tc3.cu / mlp_tcx.cu: unit order (split, tile pair), not (tile pair, split)
   int member_begin, member_count, total_members;
   int K0, split_s, L_mma, d_out;
   int stages_per_member;

@@ -136,10 +136,10 @@ class NShard:
     ``[mean | second output]`` rows rebuilds the full result on every rank -- no moment algebra.
     Set ``model.uq_shard = NShard()`` on a mirror wrapper, exactly like ``KShard``.
 
-    Native MC-dropout masks are drawn per (pass, layer, row of the CALL), so each rank shifts the
-    Philox offset by its rank to keep the slices' streams distinct; the bits therefore depend on the
-    sharding (they do not under ``KShard``).  Injected masks are indexed by global row and are not
-    supported here."""
+    Native MC-dropout masks are a function of (pass, layer, GLOBAL row, feature): each rank passes
+    the global index of its first row (``row_base``), so the bits -- and the result -- do not depend
+    on the number of ranks, exactly as under ``KShard``.  Injected masks are laid out for the whole
+    batch and are not supported here."""
 
     def __init__(self, group: Optional["dist.ProcessGroup"] = None):
         if not dist.is_available() or not dist.is_initialized():
@@ -172,7 +172,7 @@ class NShard:
         n = x.shape[0]
         begin, count = self.rows(n)
         if mode == "mc_dropout":
-            kw["offset"] = int(kw.get("offset", 0)) + self.rank
+            kw["row_base"] = begin
         if kw.get("score_floor") is not None:
             kw["score_floor"] = kw["score_floor"][begin:begin + count]
         if count > 0:

@@ -121,7 +121,8 @@ class PackedModel:
 
     # ------------------------------------------------------------------------------------------
     def _args(self, mode, precision, total_members, member_begin, member_count, dropout_p,
-              dropout_active, seed, offset, masks, anchors, output) -> "_lib.ForwardArgs":
+              dropout_active, seed, offset, masks, anchors, output, row_base=0
+              ) -> "_lib.ForwardArgs":
         a = _lib.ForwardArgs()
         a.mode = _MODE[mode]
         if precision not in _PREC:
@@ -133,6 +134,7 @@ class PackedModel:
         a.member_count = int(total_members - member_begin if member_count is None else member_count)
         a.total_members = int(total_members)
         a.dropout_active = 1 if dropout_active else 0
+        a.row_base = int(row_base)
         a.dropout_p = float(dropout_p)
         a.philox_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         a.philox_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
@@ -146,7 +148,8 @@ class PackedModel:
                 offset: int = 0, masks: Optional[torch.Tensor] = None,
                 anchors: Optional[torch.Tensor] = None,
                 output: str = "mean_std", targets: Optional[torch.Tensor] = None,
-                score_floor: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                score_floor: Optional[torch.Tensor] = None, row_base: int = 0
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
         """(mean, std) -- or (mean, M2) with ``output='moments'`` -- of shape ``[n, d_out]``.
         ``mode='pager'``: (mean over anchors of the swapped-role predictions, conformal score
         ``max_k |P[n, k] - targets[k]|`` raised to ``score_floor`` when given)."""
@@ -194,7 +197,8 @@ class PackedModel:
             int(self._handle.value), xf, _MODE[mode], _PREC[precision],
             _lib.OUT_MOMENTS if output == "moments" else _lib.OUT_MEAN_STD, int(member_begin),
             count, int(total_members), bool(dropout_active), float(dropout_p),
-            _as_i64(seed), _as_i64(offset), masks, anchors, int(self.d_out), targets, score_floor)
+            _as_i64(seed), _as_i64(offset), masks, anchors, int(self.d_out), targets, score_floor,
+            int(row_base))
 
     def forward_into(self, x: torch.Tensor, mode: str, out0: torch.Tensor, out1: torch.Tensor, *,
                      total_members: int, precision: str = "fp32", member_begin: int = 0,
@@ -607,11 +611,12 @@ def _op_uq_forward(handle: int, x: torch.Tensor, mode: int, precision: int, outp
                    dropout_active: bool, dropout_p: float, seed: int, offset: int,
                    masks: Optional[torch.Tensor], anchors: Optional[torch.Tensor], d_out: int,
                    targets: Optional[torch.Tensor] = None,
-                   score_floor: Optional[torch.Tensor] = None
+                   score_floor: Optional[torch.Tensor] = None, row_base: int = 0
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     a = _lib.ForwardArgs()
     a.mode, a.precision, a.output = mode, precision, output
+    a.row_base = row_base
     a.member_begin, a.member_count, a.total_members = member_begin, member_count, total_members
     a.dropout_active = 1 if dropout_active else 0
     a.dropout_p = dropout_p
@@ -672,7 +677,7 @@ OP_SCHEMAS = {
     "uq_forward": "(int handle, Tensor x, int mode, int precision, int output, int member_begin, "
                   "int member_count, int total_members, bool dropout_active, float dropout_p, "
                   "int seed, int offset, Tensor? masks, Tensor? anchors, int d_out, "
-                  "Tensor? targets=None, Tensor? score_floor=None) "
+                  "Tensor? targets=None, Tensor? score_floor=None, int row_base=0) "
                   "-> (Tensor, Tensor)",
     "moments_merge": "(Tensor means, Tensor m2s, float[] counts) -> (Tensor, Tensor)",
     "wasserstein_1d": "(Tensor u, Tensor v, int method=0) -> float",

@@ -112,9 +112,11 @@ def _nshard_worker(rank, world, port, out_dir):
         ref_mean, ref_std = uq_oracle.ensemble_forward(packed.nets, x)
         assert torch.allclose(mean, ref_mean, rtol=0, atol=1e-7)
         assert torch.allclose(std, ref_std, rtol=0, atol=1e-7)
-        # MC dropout: the Philox offset is shifted by the rank; injected masks are refused
+        # MC dropout: Philox is keyed by the GLOBAL row (row_base = first row of the rank's slice);
+        # injected masks are refused
         shard.forward(packed, x, "mc_dropout", total_members=k, offset=10)
-        assert packed.calls[-1][3]["offset"] == 10 + rank
+        assert packed.calls[-1][3]["offset"] == 10
+        assert packed.calls[-1][3]["row_base"] == shard.rows(157)[0]
         with pytest.raises(ValueError, match="indexed by global row"):
             shard.forward(packed, x, "mc_dropout", total_members=k, masks=torch.zeros(1))
         # fewer rows than ranks: one rank holds nothing and still takes part in the gather

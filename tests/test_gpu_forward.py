@@ -890,3 +890,45 @@ def test_baseline_config3_mcdropout_8x1024_philox_replay():
     with torch.no_grad():
         w_mean, w_std = model(x_cpu.to(DEV), return_ue=True)
     assert torch.isfinite(w_mean).all() and float(w_std.min()) > 0.0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp32_ffma", "bf16"])
+def test_native_masks_do_not_depend_on_sample_sharding(precision):
+    """A rank that runs rows [b, e) of the batch with row_base = b draws the bits of the whole-batch
+    call (Philox counters use the GLOBAL row), so an N-sharded MC-dropout run reproduces the
+    single-GPU result bit for bit."""
+    g = load_golden("mcdropout_binomial.npz")
+    p, passes, seed = 0.2, 10, 99
+    net = nets_from_golden(g, 1, arch=mc_arch_with_dropout(golden_arch(g), p))[0]
+    packed = ops.PackedModel([net], DEV)
+    x = torch.rand(333, 5, generator=torch.Generator().manual_seed(4)).to(DEV)
+    full = packed.forward(x, "mc_dropout", total_members=passes, precision=precision, dropout_p=p,
+                          seed=seed)
+    for b, e in ((0, 100), (100, 333), (64, 65)):
+        part = packed.forward(x[b:e], "mc_dropout", total_members=passes, precision=precision,
+                              dropout_p=p, seed=seed, row_base=b)
+        assert torch.equal(part[0], full[0][b:e]) and torch.equal(part[1], full[1][b:e])
+    other = packed.forward(x[100:333], "mc_dropout", total_members=passes, precision=precision,
+                           dropout_p=p, seed=seed)          # row_base 0: different rows' bits
+    assert not torch.equal(other[1], full[1][100:333])
+
+
+def test_wide_ensemble_split_major_member_groups():
+    """A wide ensemble whose weights exceed the L2 (24 members x 2.1 MB) is cut into member groups
+    that mlp_tc3.cu walks split-major (all clusters on the same group at a time) and Chan-merges;
+    the result must equal the oracle like any other bf16 forward."""
+    k, n = 24, 9600
+    nets = _baseline_nets(5, 1024, 2, k)
+    x = torch.rand(n, 5, generator=torch.Generator().manual_seed(0))
+    packed = ops.PackedModel(nets, DEV)
+    mean, std = packed.forward(x.to(DEV), "ensemble", total_members=k, precision="bf16")
+    ref_mean, ref_std = uq_oracle.ensemble_forward(nets, x)
+    _bf16_check(mean, std, ref_mean, ref_std, "split-major wide ensemble")
+    # the same forward as two K-shards (no member groups inside a moments call) merges to it
+    a = packed.forward(x.to(DEV), "ensemble", total_members=k, precision="bf16", member_begin=0,
+                       member_count=10, output="moments")
+    b = packed.forward(x.to(DEV), "ensemble", total_members=k, precision="bf16", member_begin=10,
+                       member_count=14, output="moments")
+    mm, ss = ops.moments_merge(torch.stack([a[0], b[0]]), torch.stack([a[1], b[1]]), [10, 14])
+    assert float((mm - mean).abs().max()) <= 1e-5 * float(mean.abs().max())
+    assert float((ss - std).abs().max()) <= 1e-4 * float(std.abs().max())
