@@ -108,6 +108,9 @@ const char* uq_last_error(void);
    gpu_launches) */
 uint64_t uq_launch_count(void);
 void uq_launch_count_reset(void);
+/* diagnostics: microseconds the five phases (statistics, fine-bin pass, fold, grid evaluation,
+   JS terms) of this thread's last single-launch uq_kde_jsd took on the current device */
+int uq_kde_jsd_phase_us(double* out5);
 
 /* -- model packing: replaces the weight walk the wrappers do implicitly through
       nn.Sequential.__call__ (models.py:103,156-158).  `layers` is

@@ -22,6 +22,7 @@ KDE_AUTO, KDE_WINDOW, KDE_MOMENTS = 0, 1, 2
 # every symbol include/nnueehcs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "uq_abi_version", "uq_last_error", "uq_launch_count", "uq_launch_count_reset",
+    "uq_kde_jsd_phase_us",
     "uq_model_create", "uq_model_create_ex", "uq_model_destroy", "uq_model_supports_bf16", "uq_model_supports_fp32_tc",
     "uq_forward_workspace_bytes", "uq_forward", "uq_forward_host", "uq_moments_merge",
     "uq_moments_merge_ex",

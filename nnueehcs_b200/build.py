@@ -46,9 +46,23 @@ def _fingerprint() -> str:
     files.append(os.path.join(INCLUDE, "nnueehcs_b200.h"))
     for p in files:
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())   # not the checkout root: the stamp travels
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _object_fingerprint(src, extra_flags) -> str:
+    """One translation unit: its source, every header of csrc/ + the public header, the flags."""
+    h = hashlib.sha256()
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
+            if not f.endswith(".cu") and os.path.isfile(os.path.join(CSRC, f))]
+    deps += [os.path.join(INCLUDE, "nnueehcs_b200.h"), src]
+    for p in deps:
+        with open(p, "rb") as f:
+            h.update(os.path.basename(p).encode())
+            h.update(f.read())
+    h.update(" ".join([*NVCC_FLAGS, *extra_flags]).encode())
     return h.hexdigest()
 
 
@@ -79,6 +93,11 @@ def _build_variant(suffix, extra_flags, verbose) -> str:
 
     def compile_one(src):
         obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + suffix + ".o")
+        fp, fp_path = _object_fingerprint(src, extra_flags), obj[:-2] + ".stamp"
+        if os.path.exists(obj) and os.path.exists(fp_path):
+            with open(fp_path) as f:
+                if f.read().strip() == fp:
+                    return obj   # unchanged translation unit
         cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", INCLUDE, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -87,6 +106,8 @@ def _build_variant(suffix, extra_flags, verbose) -> str:
             f.write(r.stderr)
         if verbose:
             sys.stderr.write(r.stderr)
+        with open(fp_path, "w") as f:
+            f.write(fp)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:

@@ -27,6 +27,26 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 void count_launch(int n) { g_launches += (uint64_t)n; }
 
+int result_slot(void** host_ptr, void** dev_ptr) {
+  static thread_local void* slots[64] = {nullptr};
+  static thread_local void* dslots[64] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  UQ_REQUIRE(dev >= 0 && dev < 64, UQ_ERR_UNSUPPORTED, "result_slot: device %d >= 64", dev);
+  if (!slots[dev]) {
+    void* p = nullptr;
+    UQ_CUDA(cudaHostAlloc(&p, 256, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(p, 0, 256);
+    void* d = nullptr;
+    UQ_CUDA(cudaHostGetDevicePointer(&d, p, 0));
+    slots[dev] = p;
+    dslots[dev] = d;
+  }
+  *host_ptr = slots[dev];
+  *dev_ptr = dslots[dev];
+  return UQ_OK;
+}
+
 namespace {
 
 // eval-mode BatchNorm1d as ATen's CPU kernel factors it: alpha = weight / sqrt(var + eps),
@@ -61,6 +81,10 @@ int uq_abi_version(void) { return UQ_ABI_VERSION; }
 const char* uq_last_error(void) { return g_err; }
 uint64_t uq_launch_count(void) { return g_launches; }
 void uq_launch_count_reset(void) { g_launches = 0; }
+int uq_kde_jsd_phase_us(double* out5) {
+  UQ_REQUIRE(out5 != nullptr, UQ_ERR_INVALID, "uq_kde_jsd_phase_us: out is NULL");
+  return kde_jsd_fused_phase_us(out5);
+}
 
 int uq_model_destroy(uq_model_t* model) {
   if (!model) return UQ_OK;

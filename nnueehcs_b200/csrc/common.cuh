@@ -57,6 +57,58 @@ inline int smem_opt_in(Kernel kernel, int bytes, PerDeviceOnce& once) {
   return UQ_OK;
 }
 
+// ---- single-launch metric kernels: grid barrier, co-resident grid size, mapped result slot ------
+// A metric that used to be 4-8 dependent launches runs as ONE cooperative launch whose phases are
+// separated by this barrier (cooperative launch guarantees co-residency, so spinning is safe).
+// `counter` is zeroed before the launch; barrier number k (1, 2, ...) waits for k * gridDim.x
+// arrivals.  Release on arrive / acquire on the poll make every block's earlier global writes and
+// atomics visible to every block's later reads.
+#ifdef __CUDACC__
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int k) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int target = k * gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+#endif
+
+// Largest grid of `threads`-thread blocks with `smem` dynamic bytes that is co-resident on the
+// current device (cached per device like the shared-memory opt-in).
+struct PerDeviceInt {
+  std::atomic<int> v[64];
+  PerDeviceInt() { for (auto& a : v) a.store(0); }
+};
+template <class Kernel>
+inline int coop_grid_limit(Kernel kernel, int threads, size_t smem, PerDeviceInt& cache, int* out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64) {
+    const int c = cache.v[dev].load(std::memory_order_acquire);
+    if (c > 0) { *out = c; return UQ_OK; }
+  }
+  int per_sm = 0, sms = 0, coop = 0;
+  UQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  UQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  UQ_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  UQ_REQUIRE(coop && per_sm * sms >= 1, UQ_ERR_UNSUPPORTED,
+             "device %d cannot run the single-launch metric kernel (cooperative launch %d, "
+             "%d blocks/SM)", dev, coop, per_sm);
+  *out = per_sm * sms;
+  if (dev >= 0 && dev < 64) cache.v[dev].store(*out, std::memory_order_release);
+  return UQ_OK;
+}
+
+// 256 bytes of mapped pinned host memory per (thread, device): a metric kernel's last block writes
+// the scalar result record straight into it, so the call ends with a stream synchronisation
+// instead of a D2H copy + synchronisation.  Lives until process exit.
+int result_slot(void** host_ptr, void** dev_ptr);
+
 // ---- packed model ------------------------------------------------------------------------------
 struct Layer {
   int in = 0, out = 0;
@@ -175,6 +227,11 @@ int jsd_from_grids(const double* grids, int grid_pts, double* out_host, cudaStre
 size_t kde_density_workspace_bytes(int64_t n, int64_t m);
 int kde_density(const float* fit, int64_t m, const float* x, int64_t n, int d, double bandwidth,
                 double* out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t kde_jsd_fused_workspace_bytes(int64_t nu, int64_t nv, int grid_pts);
+int kde_jsd_fused(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                  double* out_host, int* status_host, double* info_host, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+int kde_jsd_fused_phase_us(double* out5);
 size_t kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int grid_pts);
 int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts, int method,
             double* out_host, int* method_used_host, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -21,12 +21,11 @@
 // The value range is cut into bins of width h/4; for a value at offset eps*h from its bin centre c
 //   exp(-((g - c)/h - eps)^2 / 2) = K(z) * exp(z eps - eps^2/2) = K(z) * sum_m He_m(z) eps^m / m!,
 // z = (g - c)/h, so the kernel sum at every grid point follows from six numbers per bin -- the
-// count and sum eps^m, m = 1..5 -- gathered in ONE pass over the sample (bin_moments-style
-// block-private shared-memory tables, six shared atomics per value), and a [grid point x 77 bins]
-// evaluation in float64 that no longer depends on N.  |eps| <= 1/8: the truncated series moves
-// the Jensen-Shannon distance by <= 1e-9 relative on every distribution pair tried (the oracle
-// tests state 2e-5).  Needs (max - min) / (h/4) <= 8192 bins (shared memory); else the window
-// method above runs.
+// count and sum eps^m, m = 1..5 -- and a [grid point x 77 bins] evaluation in float64 that no
+// longer depends on N.  uq_kde_jsd runs this as ONE cooperative launch (csrc/kde_fused.cu: three
+// shared atomics per value on finer bins, folded into the six moments).  The six-atomic kernel
+// below (kde_moments_kernel) serves the sharded path (kde_grid_accumulate), where bandwidth and
+// range come from the all-reduced statistics.
 #include <math.h>
 #include <stdlib.h>
 
@@ -423,7 +422,7 @@ int jsd_launch(const double* pdf, int grid_pts, double* scratch, double* result,
 }
 
 struct WsLayout {
-  size_t u, ut, v, vt, scratch, partials, params, pdf, result, tables, stats, jsd, total;
+  size_t u, ut, v, vt, scratch, partials, params, pdf, result, jsd, fused, fused_bytes, total;
 };
 
 WsLayout layout(int64_t nu, int64_t nv, int grid_pts) {
@@ -440,9 +439,9 @@ WsLayout layout(int64_t nu, int64_t nv, int grid_pts) {
   L.params = o; o += al(sizeof(KdeParams));
   L.pdf = o; o += al(sizeof(double) * 2 * (size_t)grid_pts);
   L.result = o; o += 256;
-  L.tables = o; o += al(sizeof(double) * KM_MAX_BINS * KM_WORDS);
-  L.stats = o; o += al(2 * uq_sample_stats_workspace_bytes());
   L.jsd = o; o += al(JSD_SCRATCH_BYTES);
+  L.fused_bytes = kde_jsd_fused_workspace_bytes(nu, nv, grid_pts);   // 0 if the device cannot run it
+  L.fused = o; o += al(L.fused_bytes);
   L.total = o;
   return L;
 }
@@ -466,36 +465,25 @@ int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts
   char* b = static_cast<char*>(ws);
   if (method_used_host) *method_used_host = UQ_KDE_WINDOW;
   if (method != UQ_KDE_WINDOW && nu >= 2 && nv >= 2) {
-    // scipy.stats.gaussian_kde: h = sqrt(unbiased variance) * n^(-1/5); grid = linspace(min, max)
-    double stats[8];
-    const float* xs[2] = {u, v};
-    const int64_t ns[2] = {nu, nv};
-    int rc = sample_stats_multi(xs, ns, 2, stats, b + L.stats, st);  // one synchronisation
-    if (rc != UQ_OK) return rc;
-    const double *su = stats, *sv = stats + 4;
-    const double hu = sqrt(su[3] / (double)(nu - 1)) * pow((double)nu, -0.2);
-    const double hv = sqrt(sv[3] / (double)(nv - 1)) * pow((double)nv, -0.2);
-    const double lo = su[0] < sv[0] ? su[0] : sv[0], hi = su[1] > sv[1] ? su[1] : sv[1];
-    const int nbu = km_bins(lo, hi, hu), nbv = km_bins(lo, hi, hv);
-    if (nbu > 0 && nbv > 0 && isfinite(lo) && isfinite(hi)) {
-      double* pdf = reinterpret_cast<double*>(b + L.pdf);
-      double* tables = reinterpret_cast<double*>(b + L.tables);
-      double* result = reinterpret_cast<double*>(b + L.result);
-      UQ_CUDA(cudaMemsetAsync(pdf, 0, sizeof(double) * 2 * (size_t)grid_pts, st));
-      rc = km_accumulate(u, nu, lo, hi, hu, nbu, grid_pts, pdf, tables, st);
+    // the single-launch moment method (kde_fused.cu); it declines (status 2) when the range
+    // exceeds ~4000 bandwidths, a bandwidth is zero or a value is not finite
+    UQ_REQUIRE(L.fused_bytes > 0 || method != UQ_KDE_MOMENTS, UQ_ERR_UNSUPPORTED,
+               "kde_jsd: this device cannot run the moment method's cooperative launch");
+    if (L.fused_bytes > 0) {
+      int status = 0;
+      double info[6];
+      const int rc = kde_jsd_fused(u, nu, v, nv, grid_pts, out_host, &status, info, b + L.fused,
+                                   L.fused_bytes, st);
       if (rc != UQ_OK) return rc;
-      rc = km_accumulate(v, nv, lo, hi, hv, nbv, grid_pts, pdf + grid_pts, tables, st);
-      if (rc != UQ_OK) return rc;
-      rc = jsd_launch(pdf, grid_pts, reinterpret_cast<double*>(b + L.jsd), result, st);
-      if (rc != UQ_OK) return rc;
-      UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
-      UQ_CUDA(cudaStreamSynchronize(st));
-      if (method_used_host) *method_used_host = UQ_KDE_MOMENTS;
-      return UQ_OK;
+      if (status == 1) {
+        if (method_used_host) *method_used_host = UQ_KDE_MOMENTS;
+        return UQ_OK;
+      }
+      UQ_REQUIRE(method != UQ_KDE_MOMENTS, UQ_ERR_UNSUPPORTED,
+                 "kde_jsd: the moment method needs (max - min) <= 4000 bandwidths, h > 0 and "
+                 "finite values (range %g, bandwidths %g / %g)", info[3] - info[2], info[0],
+                 info[1]);
     }
-    UQ_REQUIRE(method != UQ_KDE_MOMENTS, UQ_ERR_UNSUPPORTED,
-               "kde_jsd: the moment method needs (max - min) / (h / %d) <= %d bins and h > 0 "
-               "(range %g, bandwidths %g / %g)", KM_PER_H, KM_MAX_BINS, hi - lo, hu, hv);
   }
   float* du = reinterpret_cast<float*>(b + L.u);
   float* dut = reinterpret_cast<float*>(b + L.ut);

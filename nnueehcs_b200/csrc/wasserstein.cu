@@ -26,6 +26,8 @@
 // coalesced loads, each thread merges 8 consecutive positions sequentially, and the partial sums
 // go through warp shuffles to one float64 per block; a last single-block kernel adds the block
 // partials in a fixed order (deterministic result).
+#include <string.h>
+
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -146,7 +148,7 @@ constexpr int WB_BINS = 16384;      // == KEY_BINS of shard_metrics.cu (top 14 k
 constexpr int WB_LOW_BITS = 18;
 constexpr uint32_t WB_LOW_MASK = (1u << WB_LOW_BITS) - 1u;
 constexpr int BM_THREADS = 1024;
-constexpr int64_t BM_MAX_PER_BLOCK = (int64_t)1 << 19;  // H = count * 4096 + carries < 2^32 with margin
+constexpr int64_t BM_MAX_PER_BLOCK = (int64_t)1 << 19;  // values per block between flushes (16-bit event counts)
 
 __device__ __forceinline__ uint32_t wb_key(float x) {
   const uint32_t b = __float_as_uint(x + 0.0f);  // -0.0 -> +0.0: one bin for the value zero
@@ -168,55 +170,103 @@ __device__ __forceinline__ double wb_edge(int b, double* ulp) {
   return pos ? mag : -mag;
 }
 
-// One pass over a sample: block-private shared-memory tables, two native 32-bit shared atomics
-// per value (64-bit shared atomics are a CAS loop): L[b] += low 18 key bits (mod 2^32) and
-// H[b] += 4096, + 1 more when the L add wrapped.  So H = count * 4096 + carries and the integer
-// offset sum is carries * 2^32 + L; a block sees at most 2^20 values, which keeps
-// carries < 64 and H below 2^32.  Flushed with one 64-bit reduction per non-empty bin and table.
-__global__ void __launch_bounds__(BM_THREADS, 1)
-bin_moments_kernel(const float* __restrict__ x, int64_t n, unsigned long long* __restrict__ cnt,
-                   unsigned long long* __restrict__ ksum) {
-  extern __shared__ uint32_t bm_sh[];
-  uint32_t* H = bm_sh;
-  uint32_t* L = bm_sh + WB_BINS;
-  for (int i = threadIdx.x; i < 2 * WB_BINS; i += BM_THREADS) bm_sh[i] = 0;
-  __syncthreads();
-  auto add = [&](float v) {
-    const uint32_t k = wb_key(v);
-    const uint32_t b = k >> WB_LOW_BITS, low = k & WB_LOW_MASK;
-    const uint32_t old = atomicAdd(&L[b], low);
-    atomicAdd(&H[b], 4096u + ((old + low) < old ? 1u : 0u));
-  };
+// One pass over a sample: block-private shared-memory tables and ONE native 32-bit shared atomic
+// per value (64-bit shared atomics are a CAS loop, and the first version's two 32-bit atomics per
+// value -- offset sum, then count + carry -- were what bounded the kernel: ~17 us per atomic per
+// value at 50 M values).  W[b] += 2^24 + low 18 key bits: the low 24 bits of W collect the offset
+// sum K mod 2^24, the high 8 bits (count + low-field carries) mod 2^8.  The returned old word
+// tells the adding thread whether ITS add carried out of the low field or wrapped the word; only
+// then (about one add in 85) a second atomic records the event in the side word S[b] (carries in
+// the low half, wraps in the high half).  So  K = carries 2^24 + (W & 0xFFFFFF)  and
+// count = wraps 2^8 + (W >> 24) - carries, exactly.  A block sees at most 2^19 values between
+// flushes, which keeps carries <= 8192 and wraps <= 2080 (16 bits each).  Flushed with one 64-bit
+// reduction per non-empty bin and table.
+constexpr int BM_SMEM = 2 * WB_BINS * (int)sizeof(uint32_t);
+
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// rare path of bm_add: did this add carry out of the low field / wrap the word?
+__device__ __forceinline__ void bm_event(uint32_t addr, uint32_t old, uint32_t inc) {
+  const uint32_t nw = old + inc;
+  const bool carry = (nw & 0xFFFFFFu) < (inc & 0xFFFFFFu), wrap = nw < old;
+  if (carry | wrap) reds_add(addr + WB_BINS * 4, (carry ? 1u : 0u) + (wrap ? 65536u : 0u));
+}
+
+// One value.  The pass is bound by the INT32 pipe (64 lanes per clock and SM, half the FP32
+// rate: ncu showed sm__pipe_alu at 67 % with ATOMS wavefronts at 30 %), so the count of integer
+// instructions is what matters: key (SHF + LOP3), bin (SHF), increment (LOP3), address (IMAD, FMA
+// pipe), the atomic, and a two-LOP3 test of the returned word that only says "the low field was
+// within 2^18 of full, or the high field within 2 of full" (necessary for a carry / wrap; true
+// for one add in 40) before the exact test of bm_event.
+__device__ __forceinline__ void bm_add(float v, uint32_t w_base) {
+  const uint32_t b = __float_as_uint(v + 0.0f);   // -0.0 -> +0.0: one bin for the value zero
+  const uint32_t k = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+  const uint32_t addr = w_base + ((k >> WB_LOW_BITS) << 2);
+  const uint32_t inc = (k & WB_LOW_MASK) | (1u << 24);
+  const uint32_t old = atoms_add(addr, inc);
+  if (((~old & 0x00FC0000u) == 0u) | ((~old & 0xFE000000u) == 0u)) bm_event(addr, old, inc);
+}
+
+// this block's grid-stride share of x[0 .. n); w_base = shared-memory address of W (S follows)
+__device__ __forceinline__ void bm_accumulate(const float* __restrict__ x, int64_t n,
+                                              uint32_t w_base) {
   // scalar head up to 16-byte alignment, float4 body (4 loads in flight per thread), scalar tail
   const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
   const int64_t n4 = (n - head) / 4;
   const float4* x4 = reinterpret_cast<const float4*>(x + head);
   const int64_t gtid = (int64_t)blockIdx.x * BM_THREADS + threadIdx.x;
   const int64_t gstride = (int64_t)gridDim.x * BM_THREADS;
-  if (gtid < head) add(__ldg(x + gtid));
+  if (gtid < head) bm_add(__ldg(x + gtid), w_base);
   int64_t i = gtid;
   for (; i + 3 * gstride < n4; i += 4 * gstride) {
     const float4 a0 = __ldg(x4 + i), a1 = __ldg(x4 + i + gstride);
     const float4 a2 = __ldg(x4 + i + 2 * gstride), a3 = __ldg(x4 + i + 3 * gstride);
-    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
-    add(a1.x); add(a1.y); add(a1.z); add(a1.w);
-    add(a2.x); add(a2.y); add(a2.z); add(a2.w);
-    add(a3.x); add(a3.y); add(a3.z); add(a3.w);
+    bm_add(a0.x, w_base); bm_add(a0.y, w_base); bm_add(a0.z, w_base); bm_add(a0.w, w_base);
+    bm_add(a1.x, w_base); bm_add(a1.y, w_base); bm_add(a1.z, w_base); bm_add(a1.w, w_base);
+    bm_add(a2.x, w_base); bm_add(a2.y, w_base); bm_add(a2.z, w_base); bm_add(a2.w, w_base);
+    bm_add(a3.x, w_base); bm_add(a3.y, w_base); bm_add(a3.z, w_base); bm_add(a3.w, w_base);
   }
   for (; i < n4; i += gstride) {
     const float4 a0 = __ldg(x4 + i);
-    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
+    bm_add(a0.x, w_base); bm_add(a0.y, w_base); bm_add(a0.z, w_base); bm_add(a0.w, w_base);
   }
   const int64_t tail0 = head + 4 * n4;
-  if (tail0 + gtid < n) add(__ldg(x + tail0 + gtid));
+  if (tail0 + gtid < n) bm_add(__ldg(x + tail0 + gtid), w_base);
+}
+
+// adds the block-private tables to the global ones and leaves them zeroed
+__device__ __forceinline__ void bm_flush(uint32_t* W, uint32_t* S, unsigned long long* cnt,
+                                         unsigned long long* ksum) {
   __syncthreads();
   for (int b = threadIdx.x; b < WB_BINS; b += BM_THREADS) {
-    const uint32_t h = H[b];
-    if (h) {
-      atomicAdd(&cnt[b], (unsigned long long)(h >> 12));
-      atomicAdd(&ksum[b], ((unsigned long long)(h & 4095u) << 32) + (unsigned long long)L[b]);
+    const uint32_t w = W[b], s = S[b];
+    if (w | s) {
+      const uint32_t carries = s & 0xFFFFu, wraps = s >> 16;
+      atomicAdd(&cnt[b], (unsigned long long)((wraps << 8) + (w >> 24) - carries));
+      atomicAdd(&ksum[b], ((unsigned long long)carries << 24) + (unsigned long long)(w & 0xFFFFFFu));
+      W[b] = 0;
+      S[b] = 0;
     }
   }
+  __syncthreads();
+}
+
+// the pass as a kernel of its own: the sharded method's per-rank step (uq_bin_moments)
+__global__ void __launch_bounds__(BM_THREADS, 1)
+bin_moments_kernel(const float* __restrict__ x, int64_t n, unsigned long long* __restrict__ cnt,
+                   unsigned long long* __restrict__ ksum) {
+  extern __shared__ __align__(16) uint32_t bm_sh[];
+  for (int i = threadIdx.x; i < 2 * WB_BINS; i += BM_THREADS) bm_sh[i] = 0;
+  __syncthreads();
+  bm_accumulate(x, n, (uint32_t)__cvta_generic_to_shared(bm_sh));
+  bm_flush(bm_sh, bm_sh + WB_BINS, cnt, ksum);
 }
 
 constexpr int RS_BLOCKS = 64;  // bin_contrib_kernel: 64 blocks x 256 threads, one bin per thread
@@ -335,6 +385,125 @@ bin_contrib_kernel(const unsigned long long* __restrict__ cnt_u,
   if (t == 0) res->parts[blockIdx.x] = sd[0];
 }
 
+// ---- the binned method as ONE cooperative launch ----------------------------------------------
+// Phase 1: every block accumulates its grid-stride share of u, flushes, then of v, flushes (the
+// block-private tables of bin_moments_kernel; a block never holds more than BM_MAX_PER_BLOCK
+// values between flushes).  Grid barrier.  Phase 2: the 64 units of bin_contrib_kernel (256 bins
+// each) are dealt to the blocks; a unit first adds up the counts of the bins below it (coalesced,
+// <= 16 loads per thread), scans its own 256 bins and evaluates the sign tests and contributions
+// with the arithmetic of bin_contrib_kernel (same fixed-order tree, so the result is bit-identical
+// to the three-kernel path).  The last block to finish adds the 64 unit sums in a fixed order and
+// writes the result record into mapped host memory.
+struct FusedCtl {
+  unsigned int barrier, ticket;
+};
+struct FusedRecord {     // what the host reads after the stream synchronisation
+  double resolved;
+  long long amb_u, amb_v, nonfinite;
+};
+
+__global__ void __launch_bounds__(BM_THREADS, 1)
+wasserstein_binned_fused_kernel(const float* __restrict__ u, int64_t nu,
+                                const float* __restrict__ v, int64_t nv,
+                                unsigned long long* __restrict__ tables,  // cnt_u|ks_u|cnt_v|ks_v
+                                long long* __restrict__ pre_u, long long* __restrict__ pre_v,
+                                uint8_t* __restrict__ flags, double* __restrict__ edges,
+                                BinnedResult* __restrict__ res, FusedCtl* __restrict__ ctl,
+                                FusedRecord* __restrict__ record) {
+  extern __shared__ __align__(16) uint32_t bm_sh[];
+  __shared__ long long scan_sm[64];
+  __shared__ double sd[WB_BINS / RS_BLOCKS];
+  __shared__ bool last;
+  uint32_t* H = bm_sh;              // main words
+  uint32_t* L = bm_sh + WB_BINS;    // side words (carry / wrap events)
+  unsigned long long* cnt_u = tables;
+  unsigned long long* ks_u = tables + WB_BINS;
+  unsigned long long* cnt_v = tables + 2 * WB_BINS;
+  unsigned long long* ks_v = tables + 3 * WB_BINS;
+  const int t = threadIdx.x;
+
+  // ---- phase 1
+  const uint32_t w_base = (uint32_t)__cvta_generic_to_shared(bm_sh);
+  for (int i = t; i < 2 * WB_BINS; i += BM_THREADS) bm_sh[i] = 0;
+  __syncthreads();
+  const int64_t round = (int64_t)gridDim.x * BM_MAX_PER_BLOCK;  // values per flush round (x 4 | round)
+  for (int64_t r0 = 0; r0 < nu; r0 += round) {
+    bm_accumulate(u + r0, min(round, nu - r0), w_base);
+    bm_flush(H, L, cnt_u, ks_u);
+  }
+  for (int64_t r0 = 0; r0 < nv; r0 += round) {
+    bm_accumulate(v + r0, min(round, nv - r0), w_base);
+    bm_flush(H, L, cnt_v, ks_v);
+  }
+  grid_barrier(&ctl->barrier, 1);
+
+  // ---- phase 2
+  constexpr int T = WB_BINS / RS_BLOCKS;  // 256 bins per unit
+  for (int j = blockIdx.x; j < RS_BLOCKS; j += gridDim.x) {
+    long long sa = 0, sb = 0;
+    for (int i = t; i < j * T; i += BM_THREADS)
+      sa += (long long)__ldcg(cnt_u + i), sb += (long long)__ldcg(cnt_v + i);
+    const int b = j * T + t;
+    long long cu = 0, cv = 0;
+    if (t < T) cu = (long long)__ldcg(cnt_u + b), cv = (long long)__ldcg(cnt_v + b);
+    long long ea, eb, base_a, base_b, ta, tb;
+    block_scan_pair(sa, sb, ea, eb, base_a, base_b, scan_sm);
+    block_scan_pair(cu, cv, ea, eb, ta, tb, scan_sm);
+    double acc = 0.0;
+    if (t < T) {
+      const long long Cu = base_a + ea, Cv = base_b + eb;
+      pre_u[b] = Cu;
+      pre_v[b] = Cv;
+      const unsigned long long ku = __ldcg(ks_u + b), kv = __ldcg(ks_v + b);
+      double ulp;
+      const double tb0 = wb_edge(b, &ulp);
+      const double w = wb_edge(b + 1, nullptr) - tb0;
+      edges[b] = tb0;
+      if (b == WB_BINS - 1) edges[WB_BINS] = tb0 + w;
+      const bool d_ge0 = Cu * nv - (Cv + cv) * nu >= 0;
+      const bool d_le0 = (Cu + cu) * nv - Cv * nu <= 0;
+      const bool amb = !(d_ge0 || d_le0);
+      if (!amb && ((cu | cv) || Cu * nv != Cv * nu)) {
+        const double a = ((double)(Cu + cu) * w - (double)ku * ulp) / (double)nu;
+        const double c = ((double)(Cv + cv) * w - (double)kv * ulp) / (double)nv;
+        acc = fabs(a - c);
+      }
+      flags[b] = amb ? 1 : 0;
+      if (amb) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&res->amb_u), (unsigned long long)cu);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&res->amb_v), (unsigned long long)cv);
+      }
+      if ((b < 32 || b >= WB_BINS - 32) && (cu | cv))
+        atomicAdd(reinterpret_cast<unsigned long long*>(&res->nonfinite),
+                  (unsigned long long)(cu + cv));
+      sd[t] = acc;
+    }
+    for (int o = T / 2; o > 0; o >>= 1) {  // the fixed-order tree of bin_contrib_kernel
+      __syncthreads();
+      if (t < o) sd[t] += sd[t + o];
+    }
+    if (t == 0) res->parts[j] = sd[0];
+    __syncthreads();
+  }
+
+  // ---- the last block to finish phase 2 writes the record
+  if (t == 0) {
+    __threadfence();
+    last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && t == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (int q = 0; q < RS_BLOCKS; ++q) s += __ldcg(&res->parts[q]);  // fixed order
+    record->resolved = s;
+    record->amb_u = __ldcg(&res->amb_u);
+    record->amb_v = __ldcg(&res->amb_v);
+    record->nonfinite = __ldcg(&res->nonfinite);
+    __threadfence_system();
+  }
+}
+
 // values whose bin is flagged -> out (order arbitrary: they are sorted next)
 __global__ void __launch_bounds__(256)
 compact_flagged_kernel(const float* __restrict__ x, int64_t n, const uint8_t* __restrict__ flags,
@@ -439,7 +608,7 @@ cdf_integral_binned_kernel(const float* __restrict__ U, int64_t nu, const float*
 }
 
 struct WsLayout {
-  size_t u, ut, v, vt, scratch, parts, splits, result, tables, bres, pre, flags, skips, edges, cursors, total;
+  size_t u, ut, v, vt, scratch, parts, splits, result, tables, bres, ctl, pre, flags, skips, edges, cursors, total;
   int64_t blocks;
 };
 
@@ -460,6 +629,7 @@ WsLayout layout(int64_t nu, int64_t nv) {
   L.result = o; o += 256;
   L.tables = o; o += al(sizeof(unsigned long long) * 4 * WB_BINS);  // cnt_u, ks_u, cnt_v, ks_v
   L.bres = o; o += al(sizeof(BinnedResult));                        // zeroed with the tables
+  L.ctl = o; o += 256;                                              // barrier + ticket, zeroed too
   L.pre = o; o += al(sizeof(long long) * 2 * WB_BINS);
   L.flags = o; o += al(WB_BINS);
   L.skips = o; o += al(sizeof(long long) * 2 * (WB_BINS + 1));
@@ -481,7 +651,7 @@ namespace {
 int bin_moments_launch(const float* x, int64_t n, unsigned long long* cnt, unsigned long long* ks,
                        cudaStream_t st) {
   static PerDeviceOnce opted;
-  constexpr int SMEM = 2 * WB_BINS * (int)sizeof(uint32_t);
+  constexpr int SMEM = BM_SMEM;
   if (int rc = smem_opt_in(bin_moments_kernel, SMEM, opted)) return rc;
   // one block per SM; more only to keep a block below BM_MAX_PER_BLOCK values
   int64_t blocks = (n + (int64_t)BM_THREADS * 16 - 1) / ((int64_t)BM_THREADS * 16);
@@ -600,6 +770,45 @@ int compact_launch(const float* x, int64_t n, const uint8_t* flags, float* out,
 
 }  // namespace
 
+namespace {
+
+// tables, BinnedResult and the control words are zeroed, the fused kernel runs, the stream is
+// synchronised; *h = the record its last block wrote into mapped host memory
+int binned_fused(const float* u, int64_t nu, const float* v, int64_t nv, char* b, const WsLayout& L,
+                 FusedRecord* h, cudaStream_t st) {
+  static PerDeviceOnce opted;
+  static PerDeviceInt grid_cache;
+  constexpr int SMEM = BM_SMEM;
+  if (int rc = smem_opt_in(wasserstein_binned_fused_kernel, SMEM, opted)) return rc;
+  int grid = 0;
+  if (int rc = coop_grid_limit(wasserstein_binned_fused_kernel, BM_THREADS, SMEM, grid_cache, &grid))
+    return rc;
+  void *slot_h = nullptr, *slot_d = nullptr;
+  if (int rc = result_slot(&slot_h, &slot_d)) return rc;
+  unsigned long long* tables = reinterpret_cast<unsigned long long*>(b + L.tables);
+  long long* pre_u = reinterpret_cast<long long*>(b + L.pre);
+  long long* pre_v = pre_u + WB_BINS;
+  uint8_t* flags = reinterpret_cast<uint8_t*>(b + L.flags);
+  double* edges = reinterpret_cast<double*>(b + L.edges);
+  BinnedResult* bres = reinterpret_cast<BinnedResult*>(b + L.bres);
+  FusedCtl* ctl = reinterpret_cast<FusedCtl*>(b + L.ctl);
+  FusedRecord* record = static_cast<FusedRecord*>(slot_d);
+  static_cast<FusedRecord*>(slot_h)->nonfinite = -1;   // the kernel overwrites it with a count
+  UQ_CUDA(cudaMemsetAsync(b + L.tables, 0, L.pre - L.tables, st));
+  void* args[] = {(void*)&u, (void*)&nu, (void*)&v, (void*)&nv, (void*)&tables, (void*)&pre_u,
+                  (void*)&pre_v, (void*)&flags, (void*)&edges, (void*)&bres, (void*)&ctl,
+                  (void*)&record};
+  UQ_CUDA(cudaLaunchCooperativeKernel((const void*)wasserstein_binned_fused_kernel, dim3(grid),
+                                      dim3(BM_THREADS), args, SMEM, st));
+  UQ_LAUNCH_CHECK();
+  UQ_CUDA(cudaStreamSynchronize(st));
+  memcpy(h, slot_h, sizeof(*h));
+  UQ_REQUIRE(h->nonfinite >= 0, UQ_ERR_CUDA, "wasserstein: the kernel left no result record");
+  return UQ_OK;
+}
+
+}  // namespace
+
 // method: UQ_WASSERSTEIN_AUTO / _SORT / _BINNED (binned even when most values are ambiguous).
 // info_host (may be NULL): {method used, ambiguous u values, ambiguous v values}.
 int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, int method,
@@ -622,15 +831,10 @@ int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, int m
   if (method != UQ_WASSERSTEIN_SORT) {
     const BinTables T = tables_at(reinterpret_cast<unsigned long long*>(b + L.tables));
     uint8_t* flags = reinterpret_cast<uint8_t*>(b + L.flags);
-    UQ_CUDA(cudaMemsetAsync(b + L.tables, 0, L.pre - L.tables, st));  // tables + BinnedResult
-    int rc = bin_moments_launch(u, nu, T.cnt_u, T.ks_u, st);
+    FusedRecord h;
+    int rc = binned_fused(u, nu, v, nv, b, L, &h, st);  // one memset + one launch + one sync
     if (rc != UQ_OK) return rc;
-    rc = bin_moments_launch(v, nv, T.cnt_v, T.ks_v, st);
-    if (rc != UQ_OK) return rc;
-    BinnedResult h;
-    double resolved;
-    rc = resolve_bins(T, nu, nv, b, L, flags, &h, &resolved, st);
-    if (rc != UQ_OK) return rc;
+    const double resolved = h.resolved;
     const int64_t amb = h.amb_u + h.amb_v;
     const bool use = h.nonfinite == 0 &&
                      (method == UQ_WASSERSTEIN_BINNED || amb <= (nu + nv) / 2);

@@ -24,6 +24,28 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _on_device:
+    """``torch.cuda.device(dev)`` without the set/restore round trip when ``dev`` is already the
+    current device (the usual case: one process per GPU) -- a few microseconds per call, which is
+    a visible share of a 100-microsecond metric call."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device: torch.device):
+        self.idx = device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _require_cuda(t: torch.Tensor, what: str) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(
@@ -599,7 +621,7 @@ def _as_i64(v: int) -> int:
 def _run_forward(lib, handle, x: torch.Tensor, a: "_lib.ForwardArgs", out0: torch.Tensor,
                  out1: torch.Tensor) -> None:
     n, dev = x.shape[0], x.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         wsb = int(lib.uq_forward_workspace_bytes(handle, n, C.byref(a)))
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
         _lib.check(lib.uq_forward(handle, x.data_ptr(), n, C.byref(a), out0.data_ptr(),
@@ -651,7 +673,7 @@ def _op_moments_merge(means: torch.Tensor, m2s: torch.Tensor, counts: Sequence[f
 def _op_wasserstein_1d(u: torch.Tensor, v: torch.Tensor, method: int = 0) -> float:
     lib = _lib.load()
     out = C.c_double()
-    with torch.cuda.device(u.device):
+    with _on_device(u.device):
         wsb = int(lib.uq_wasserstein_workspace_bytes(u.numel(), v.numel()))
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
         _lib.check(lib.uq_wasserstein_1d_ex(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
@@ -663,7 +685,7 @@ def _op_wasserstein_1d(u: torch.Tensor, v: torch.Tensor, method: int = 0) -> flo
 def _op_kde_jsd(u: torch.Tensor, v: torch.Tensor, num_points: int, method: int = 0) -> float:
     lib = _lib.load()
     out = C.c_double()
-    with torch.cuda.device(u.device):
+    with _on_device(u.device):
         wsb = int(lib.uq_kde_jsd_workspace_bytes(u.numel(), v.numel(), num_points))
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
         _lib.check(lib.uq_kde_jsd_ex(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), num_points,

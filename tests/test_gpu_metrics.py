@@ -250,6 +250,36 @@ def test_kde_jsd_moment_method_falls_back_when_bins_do_not_fit():
         ops.kde_jsd(_dev(u), _dev(v), 2000, "fft")
 
 
+def test_kde_jsd_wide_range_uses_coarser_fine_bins():
+    """(max - min) = 1400 bandwidths: the single-launch kernel (csrc/kde_fused.cu) has room for
+    two fine bins per coarse bin instead of 64."""
+    rng = np.random.default_rng(5)
+    u = rng.normal(0, 1, 200_000).astype(np.float32)
+    u[0] = 120.0
+    v = rng.normal(0.5, 1, 150_000).astype(np.float32)
+    mom = ops.kde_jsd_info(_dev(u), _dev(v), 2000, "moments")
+    win = ops.kde_jsd_info(_dev(u), _dev(v), 2000, "window")
+    assert mom["method"] == "moments" and win["method"] == "window"
+    assert mom["value"] == pytest.approx(win["value"], rel=2e-6)
+
+
+def test_kde_jsd_single_launch_is_reproducible_and_counts_one_launch():
+    u, v = _gamma_pair(300_000, 200_000, seed=9)
+    du, dv = _dev(u), _dev(v)
+    first = ops.kde_jsd(du, dv, 20000)
+    ops.reset_launch_count()
+    again = ops.kde_jsd(du, dv, 20000)
+    assert ops.launch_count() == 1          # one cooperative launch (plus a memset)
+    assert again == first                   # fixed-order reductions, no float atomics
+    ops.reset_launch_count()
+    w = ops.wasserstein_1d(du, dv)
+    assert ops.launch_count() == 1
+    assert w == pytest.approx(metrics_oracle.wasserstein_1d(u, v), rel=1e-12)
+    # unaligned views and odd sizes go through the same kernel
+    ref = metrics_oracle.pdf_jsd(u[1:70_001], v[3:50_000], 1500)
+    assert ops.kde_jsd(du[1:70_001], dv[3:50_000], 1500) == pytest.approx(ref, rel=JSD_RTOL)
+
+
 def test_kde_jsd_methods_agree_at_scale():
     """BASELINE configs[4] shape on one GPU (50 M + 50 M, 20 000 grid points)."""
     n = 50_000_000
