@@ -78,6 +78,38 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 }
 #endif
 
+#ifdef __CUDACC__
+// A block's grid-stride share of x[0 .. n), one call of add(float) per value: scalar head up to
+// 16-byte alignment, float4 body with four loads in flight per thread, scalar tail.  (A software-
+// pipelined variant -- the next batch's loads issued before the current batch is processed --
+// and a TMA-fed shared-memory ring were both measured and were not faster: the metric passes
+// are bound by shared-memory atomic wavefronts, see DESIGN.md.)
+template <int THREADS, class F>
+__device__ __forceinline__ void for_each_value(const float* __restrict__ x, int64_t n, F&& add) {
+  const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
+  const int64_t n4 = (n - head) / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  const int64_t gtid = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  const int64_t gstride = (int64_t)gridDim.x * THREADS;
+  if (gtid < head) add(__ldg(x + gtid));
+  int64_t i = gtid;
+  for (; i + 3 * gstride < n4; i += 4 * gstride) {
+    const float4 a0 = __ldg(x4 + i), a1 = __ldg(x4 + i + gstride);
+    const float4 a2 = __ldg(x4 + i + 2 * gstride), a3 = __ldg(x4 + i + 3 * gstride);
+    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
+    add(a1.x); add(a1.y); add(a1.z); add(a1.w);
+    add(a2.x); add(a2.y); add(a2.z); add(a2.w);
+    add(a3.x); add(a3.y); add(a3.z); add(a3.w);
+  }
+  for (; i < n4; i += gstride) {
+    const float4 a0 = __ldg(x4 + i);
+    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
+  }
+  const int64_t tail0 = head + 4 * n4;
+  if (tail0 + gtid < n) add(__ldg(x + tail0 + gtid));
+}
+#endif
+
 // Largest grid of `threads`-thread blocks with `smem` dynamic bytes that is co-resident on the
 // current device (cached per device like the shared-memory opt-in).
 struct PerDeviceInt {

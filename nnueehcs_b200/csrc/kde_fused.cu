@@ -130,27 +130,7 @@ __device__ __forceinline__ void kf_stats(const float* __restrict__ x, int64_t n,
     mnf = fminf(mnf, v);
     mxf = fmaxf(mxf, v);
   };
-  const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
-  const int64_t n4 = (n - head) / 4;
-  const float4* x4 = reinterpret_cast<const float4*>(x + head);
-  const int64_t gtid = (int64_t)blockIdx.x * KF_THREADS + threadIdx.x;
-  const int64_t gstride = (int64_t)gridDim.x * KF_THREADS;
-  if (gtid < head) add(__ldg(x + gtid));
-  int64_t i = gtid;
-  for (; i + 3 * gstride < n4; i += 4 * gstride) {
-    const float4 a0 = __ldg(x4 + i), a1 = __ldg(x4 + i + gstride);
-    const float4 a2 = __ldg(x4 + i + 2 * gstride), a3 = __ldg(x4 + i + 3 * gstride);
-    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
-    add(a1.x); add(a1.y); add(a1.z); add(a1.w);
-    add(a2.x); add(a2.y); add(a2.z); add(a2.w);
-    add(a3.x); add(a3.y); add(a3.z); add(a3.w);
-  }
-  for (; i < n4; i += gstride) {
-    const float4 a0 = __ldg(x4 + i);
-    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
-  }
-  const int64_t tail0 = head + 4 * n4;
-  if (tail0 + gtid < n) add(__ldg(x + tail0 + gtid));
+  for_each_value<KF_THREADS>(x, n, add);
   // NaN must survive the min / max (fminf drops it): fold it into the sums, which the
   // applicability test looks at
   kf_block_sum2(s1, s2, sh);
@@ -184,68 +164,52 @@ __device__ __forceinline__ void kf_reds_add(uint32_t addr, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
 }
 
-// rare path of kf_add: did this add carry out of W1's low field / wrap W1?
-__device__ __forceinline__ void kf_event(uint32_t addr, uint32_t old, uint32_t inc) {
+// rare path of kf_add: did this add carry out of W2's low field / wrap W2?
+__device__ __forceinline__ void kf_event2(uint32_t addr, uint32_t old, uint32_t inc) {
   const uint32_t nw = old + inc;
-  const bool carry = (nw & 0xFFFFFFu) < (inc & 0xFFFFFFu), wrap = nw < old;
+  const bool carry = (nw & 0x3FFFFFu) < (inc & 0x3FFFFFu), wrap = nw < old;
   if (carry | wrap)
-    kf_reds_add<2 * KF_MAX_FINE * 4>(addr, (carry ? 1u : 0u) + (wrap ? 65536u : 0u));
+    kf_reds_add<2 * KF_MAX_FINE * 4>(addr, (carry ? 1u << 8 : 0u) + (wrap ? 1u << 20 : 0u));
 }
 
-// phase 2, one value: two to three native shared atomics on three words per fine bin
-//   W1 += 2^24 + t1 : low 24 bits = sum t1 mod 2^24, high 8 bits = (count + low-field carries)
-//        mod 2^8 -- count and first moment in ONE atomic (the packing of wasserstein.cu);
-//   W2 += t2        : never wraps (<= 2^19 values per block and slab);
-//   SD += carry + (wrap << 16), only from the add whose returned old word shows that it carried
-//        out of W1's low field or wrapped W1.
+// phase 2, one value: two native shared atomics on the value's fine bin
+//   W1 += t1,          t1 = e 2^18 + 2^17 in [0, 2^18]: wraps at most once per 2^14 adds;
+//   W2 += 2^22 + t2,   t2 = e^2 2^14 in [0, 2^12]: low 22 bits = sum t2 mod 2^22, high 10 bits =
+//                      (count + low-field carries) mod 2^10 -- count and second moment in ONE
+//                      atomic; packing the count with the SMALL increment keeps the carry / wrap
+//                      events rare (three adds in 1000: packed with t1 they fired in every second
+//                      warp and cost more instructions than they saved);
+//   SD += wrap of W1 | carry of W2 << 8 | wrap of W2 << 20, only from the add whose returned
+//                      old word shows the event.
 // The first version of this pass spent 45 instructions per value and was issue-bound (ncu: INT32
 // pipe), so everything here is shaped to stay off the integer pipe:
 //   * bin index = round(t + 1/2) by the 2^23 magic-number add -- no quarter-rate F2I / I2F; the
 //     bin grid starts one fine bin below the minimum, so the index is never negative and the
 //     rounding remainder e is in [-1/2, 1/2] by construction -- no clamps;
 //   * the word address is one IMAD on the raw float bits (4 * (bits - 0x4B000000) mod 2^32);
-//   * the increments are produced directly as bit patterns by FMAs whose result exponent is
-//     chosen for it: 2^-125 + t1 2^-148 has the bits 0x01000000 + t1, and e^2 2^-135 is the
-//     denormal with the bits round(e^2 2^14) (gradual underflow rounds to nearest);
-//   * the returned word is only tested for "low field within 2^18 of full or high field within 2
-//     of full" (two LOP3) before the exact test in kf_event.
+//   * the increments are produced directly as bit patterns by FMAs with denormal results
+//     (gradual underflow rounds to nearest at 2^-149): m 2^-149 has the bits m;
+//   * a returned word is only tested for "a field is within one increment of full" (LOP3)
+//     before the exact test.
 __device__ __forceinline__ void kf_add(float v, float lo_f, float inv_wf, uint32_t w_rel) {
   const float a = fmaf(v - lo_f, inv_wf, 0.5f);           // t + 1/2, t = position in fine bins >= 0
   const float tf = a + 8388608.0f;                        // bits 0x4B000000 + round(t + 1/2)
   const float e = a - (tf - 8388608.0f);                  // offset from that bin's centre
   const uint32_t addr = __float_as_uint(tf) * 4u + w_rel; // w_rel = &W1[0] - 4 * 0x4B000000
-  const uint32_t inc = __float_as_uint(fmaf(e, 0x1p-130f, 0x1.04p-125f));   // 2^24 + e 2^18 + 2^17
-  const uint32_t t2 = __float_as_uint((e * e) * 0x1p-135f);                 // e^2 2^14
-  const uint32_t o1 = kf_atoms_add(addr, inc);
-  kf_reds_add<KF_MAX_FINE * 4>(addr, t2);
-  if (((~o1 & 0x00FC0000u) == 0u) | ((~o1 & 0xFE000000u) == 0u)) kf_event(addr, o1, inc);
+  const uint32_t inc1 = __float_as_uint(fmaf(e, 0x1p-131f, 0x1p-132f));      // e 2^18 + 2^17
+  const uint32_t inc2 = __float_as_uint(fmaf(e * e, 0x1p-135f, 0x1p-127f));  // 2^22 + e^2 2^14
+  const uint32_t o1 = kf_atoms_add(addr, inc1);
+  const uint32_t o2 = kf_atoms_add(addr + KF_MAX_FINE * 4, inc2);
+  if ((~o1 & 0xFFFC0000u) == 0u)
+    if (o1 + inc1 < o1) kf_reds_add<2 * KF_MAX_FINE * 4>(addr, 1u);
+  if (((~o2 & 0x003FF000u) == 0u) | ((~o2 & 0xFF800000u) == 0u))
+    kf_event2(addr, o2, inc2);
 }
 
 // this block's grid-stride share of x[0 .. n)
 __device__ __forceinline__ void kf_accumulate(const float* __restrict__ x, int64_t n, float lo_f,
                                               float inv_wf, uint32_t w_rel) {
-  const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
-  const int64_t n4 = (n - head) / 4;
-  const float4* x4 = reinterpret_cast<const float4*>(x + head);
-  const int64_t gtid = (int64_t)blockIdx.x * KF_THREADS + threadIdx.x;
-  const int64_t gstride = (int64_t)gridDim.x * KF_THREADS;
-  auto add = [&](float v) { kf_add(v, lo_f, inv_wf, w_rel); };
-  if (gtid < head) add(__ldg(x + gtid));
-  int64_t i = gtid;
-  for (; i + 3 * gstride < n4; i += 4 * gstride) {
-    const float4 a0 = __ldg(x4 + i), a1 = __ldg(x4 + i + gstride);
-    const float4 a2 = __ldg(x4 + i + 2 * gstride), a3 = __ldg(x4 + i + 3 * gstride);
-    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
-    add(a1.x); add(a1.y); add(a1.z); add(a1.w);
-    add(a2.x); add(a2.y); add(a2.z); add(a2.w);
-    add(a3.x); add(a3.y); add(a3.z); add(a3.w);
-  }
-  for (; i < n4; i += gstride) {
-    const float4 a0 = __ldg(x4 + i);
-    add(a0.x); add(a0.y); add(a0.z); add(a0.w);
-  }
-  const int64_t tail0 = head + 4 * n4;
-  if (tail0 + gtid < n) add(__ldg(x + tail0 + gtid));
+  for_each_value<KF_THREADS>(x, n, [&](float v) { kf_add(v, lo_f, inv_wf, w_rel); });
 }
 
 __global__ void __launch_bounds__(KF_THREADS, 1)
@@ -380,19 +344,19 @@ kde_jsd_fused_kernel(const float* __restrict__ u, int64_t nu, const float* __res
         for (int it = t; it < nfine * parts; it += KF_THREADS) {
           const int part = it / nfine, fi = it - part * nfine;
           const uint32_t* p = slab0 + c0 * fpc + fi;
-          unsigned long long top = 0, low = 0, sq = 0, carries = 0, wraps = 0;
+          unsigned long long t1 = 0, top = 0, low = 0, wraps1 = 0, carries2 = 0, wraps2 = 0;
 #pragma unroll 4
           for (int b = part; b < nslabs; b += parts) {
             const uint32_t* q = p + (size_t)b * (KF_WORDS * KF_MAX_FINE);
             const uint32_t w1 = __ldcg(q), w2 = __ldcg(q + nbf), sd = __ldcg(q + 2 * nbf);
-            top += w1 >> 24, low += w1 & 0xFFFFFFu, sq += w2;
-            carries += sd & 0xFFFFu, wraps += sd >> 16;
+            t1 += w1, top += w2 >> 22, low += w2 & 0x3FFFFFu;
+            wraps1 += sd & 0xFFu, carries2 += (sd >> 8) & 0xFFFu, wraps2 += sd >> 20;
           }
           // integer sums: the order of the shared atomics does not matter
-          atomicAdd(&sums[fi], (wraps << 8) + top);       // count + carries
-          atomicAdd(&sums[nfine + fi], carries);
-          atomicAdd(&sums[2 * nfine + fi], low);
-          atomicAdd(&sums[3 * nfine + fi], sq);
+          atomicAdd(&sums[fi], (wraps2 << 10) + top);              // count + carries2
+          atomicAdd(&sums[nfine + fi], carries2);
+          atomicAdd(&sums[2 * nfine + fi], (wraps1 << 32) + t1);   // sum t1
+          atomicAdd(&sums[3 * nfine + fi], low);                   // sum t2 - carries2 2^22
         }
       }
       __syncthreads();
@@ -407,8 +371,8 @@ kde_jsd_fused_kernel(const float* __restrict__ u, int64_t nu, const float* __res
           const unsigned long long carries = sums[nfine + fi];
           const double c = (double)(sums[fi] - carries);
           if (c == 0.0) continue;
-          const double s1 = ((double)((carries << 24) + sums[2 * nfine + fi]) - c * 131072.0) * inv_s1;
-          const double s2 = (double)sums[3 * nfine + fi] * inv_s2;
+          const double s1 = ((double)sums[2 * nfine + fi] - c * 131072.0) * inv_s1;
+          const double s2 = (double)((carries << 22) + sums[3 * nfine + fi]) * inv_s2;
           const double S[KF_CW] = {c, s1, s2, 0.6 * A * A * s1, c * (A * A * A * A / 5.0),
                                    (3.0 / 7.0) * A * A * A * A * s1};
           const double d = ((double)i - 0.5 * (double)(fpc - 1)) / (double)fph;

@@ -170,17 +170,20 @@ __device__ __forceinline__ double wb_edge(int b, double* ulp) {
   return pos ? mag : -mag;
 }
 
-// One pass over a sample: block-private shared-memory tables and ONE native 32-bit shared atomic
-// per value (64-bit shared atomics are a CAS loop, and the first version's two 32-bit atomics per
-// value -- offset sum, then count + carry -- were what bounded the kernel: ~17 us per atomic per
-// value at 50 M values).  W[b] += 2^24 + low 18 key bits: the low 24 bits of W collect the offset
-// sum K mod 2^24, the high 8 bits (count + low-field carries) mod 2^8.  The returned old word
-// tells the adding thread whether ITS add carried out of the low field or wrapped the word; only
-// then (about one add in 85) a second atomic records the event in the side word S[b] (carries in
-// the low half, wraps in the high half).  So  K = carries 2^24 + (W & 0xFFFFFF)  and
-// count = wraps 2^8 + (W >> 24) - carries, exactly.  A block sees at most 2^19 values between
-// flushes, which keeps carries <= 8192 and wraps <= 2080 (16 bits each).  Flushed with one 64-bit
-// reduction per non-empty bin and table.
+// One pass over a sample: block-private shared-memory tables, two native 32-bit shared-memory
+// operations per value and as few instructions around them as possible -- ncu showed the pass
+// bound by instruction issue / the INT32 pipe (64 lanes per clock and SM), not by HBM (40 %) or
+// by the ATOMS wavefronts (36 %):
+//   L[b] += low 18 key bits   (atom with return: the adding thread sees whether ITS add wrapped
+//                              the word -- possible only when the old word's top 14 bits were all
+//                              ones, one add in 16384 -- and then credits 2^20 to H[b]);
+//   H[b] += 1                 (red, fire and forget; immediate address offset).
+// So count = H & 0xFFFFF and the offset sum K = (H >> 20) 2^32 + L, exactly; a block sees at most
+// 2^19 values between flushes (count < 2^20, at most 32 wraps).  History: two dependent atomics
+// with the carry computed for every value (55.6 us per 50 M values), one packed atomic with the
+// count in the top byte (same time: its carry / wrap test fired in every second warp and cost
+// more instructions than the second atomic), this (see DESIGN.md for the numbers).  Flushed with
+// one 64-bit reduction per non-empty bin and table.
 constexpr int BM_SMEM = 2 * WB_BINS * (int)sizeof(uint32_t);
 
 __device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
@@ -188,71 +191,43 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
   return old;
 }
+template <int OFF>
 __device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
-  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
 }
 
-// rare path of bm_add: did this add carry out of the low field / wrap the word?
-__device__ __forceinline__ void bm_event(uint32_t addr, uint32_t old, uint32_t inc) {
-  const uint32_t nw = old + inc;
-  const bool carry = (nw & 0xFFFFFFu) < (inc & 0xFFFFFFu), wrap = nw < old;
-  if (carry | wrap) reds_add(addr + WB_BINS * 4, (carry ? 1u : 0u) + (wrap ? 65536u : 0u));
-}
-
-// One value.  The pass is bound by the INT32 pipe (64 lanes per clock and SM, half the FP32
-// rate: ncu showed sm__pipe_alu at 67 % with ATOMS wavefronts at 30 %), so the count of integer
-// instructions is what matters: key (SHF + LOP3), bin (SHF), increment (LOP3), address (IMAD, FMA
-// pipe), the atomic, and a two-LOP3 test of the returned word that only says "the low field was
-// within 2^18 of full, or the high field within 2 of full" (necessary for a carry / wrap; true
-// for one add in 40) before the exact test of bm_event.
-__device__ __forceinline__ void bm_add(float v, uint32_t w_base) {
+// key = bits ^ (sign ? 0xFFFFFFFF : 0x80000000); bin = key >> 18, low = key & 0x3FFFF.  The sign
+// mask and the word address are IMAD.HI (FMA pipe) instead of shifts (INT32 pipe).
+__device__ __forceinline__ void bm_add(float v, uint32_t l_base) {
   const uint32_t b = __float_as_uint(v + 0.0f);   // -0.0 -> +0.0: one bin for the value zero
-  const uint32_t k = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
-  const uint32_t addr = w_base + ((k >> WB_LOW_BITS) << 2);
-  const uint32_t inc = (k & WB_LOW_MASK) | (1u << 24);
-  const uint32_t old = atoms_add(addr, inc);
-  if (((~old & 0x00FC0000u) == 0u) | ((~old & 0xFE000000u) == 0u)) bm_event(addr, old, inc);
+  uint32_t sign, addr;
+  asm("mul.hi.s32 %0, %1, 1;" : "=r"(sign) : "r"(b));                     // b < 0 ? ~0 : 0
+  const uint32_t k = b ^ (sign | 0x80000000u);
+  asm("mad.hi.u32 %0, %1, 65536, %2;" : "=r"(addr) : "r"(k & 0xFFFC0000u), "r"(l_base));
+  const uint32_t low = k & WB_LOW_MASK;
+  const uint32_t old = atoms_add(addr, low);
+  reds_add<WB_BINS * 4>(addr, 1u);
+  if ((~old & 0xFFFC0000u) == 0u)                  // necessary for a wrap; exact test inside
+    if (old + low < old) reds_add<WB_BINS * 4>(addr, 1u << 20);
 }
 
-// this block's grid-stride share of x[0 .. n); w_base = shared-memory address of W (S follows)
+// this block's grid-stride share of x[0 .. n); l_base = shared-memory address of L (H follows)
 __device__ __forceinline__ void bm_accumulate(const float* __restrict__ x, int64_t n,
                                               uint32_t w_base) {
-  // scalar head up to 16-byte alignment, float4 body (4 loads in flight per thread), scalar tail
-  const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / 4);
-  const int64_t n4 = (n - head) / 4;
-  const float4* x4 = reinterpret_cast<const float4*>(x + head);
-  const int64_t gtid = (int64_t)blockIdx.x * BM_THREADS + threadIdx.x;
-  const int64_t gstride = (int64_t)gridDim.x * BM_THREADS;
-  if (gtid < head) bm_add(__ldg(x + gtid), w_base);
-  int64_t i = gtid;
-  for (; i + 3 * gstride < n4; i += 4 * gstride) {
-    const float4 a0 = __ldg(x4 + i), a1 = __ldg(x4 + i + gstride);
-    const float4 a2 = __ldg(x4 + i + 2 * gstride), a3 = __ldg(x4 + i + 3 * gstride);
-    bm_add(a0.x, w_base); bm_add(a0.y, w_base); bm_add(a0.z, w_base); bm_add(a0.w, w_base);
-    bm_add(a1.x, w_base); bm_add(a1.y, w_base); bm_add(a1.z, w_base); bm_add(a1.w, w_base);
-    bm_add(a2.x, w_base); bm_add(a2.y, w_base); bm_add(a2.z, w_base); bm_add(a2.w, w_base);
-    bm_add(a3.x, w_base); bm_add(a3.y, w_base); bm_add(a3.z, w_base); bm_add(a3.w, w_base);
-  }
-  for (; i < n4; i += gstride) {
-    const float4 a0 = __ldg(x4 + i);
-    bm_add(a0.x, w_base); bm_add(a0.y, w_base); bm_add(a0.z, w_base); bm_add(a0.w, w_base);
-  }
-  const int64_t tail0 = head + 4 * n4;
-  if (tail0 + gtid < n) bm_add(__ldg(x + tail0 + gtid), w_base);
+  for_each_value<BM_THREADS>(x, n, [&](float v) { bm_add(v, w_base); });
 }
 
 // adds the block-private tables to the global ones and leaves them zeroed
-__device__ __forceinline__ void bm_flush(uint32_t* W, uint32_t* S, unsigned long long* cnt,
+__device__ __forceinline__ void bm_flush(uint32_t* L, uint32_t* H, unsigned long long* cnt,
                                          unsigned long long* ksum) {
   __syncthreads();
   for (int b = threadIdx.x; b < WB_BINS; b += BM_THREADS) {
-    const uint32_t w = W[b], s = S[b];
-    if (w | s) {
-      const uint32_t carries = s & 0xFFFFu, wraps = s >> 16;
-      atomicAdd(&cnt[b], (unsigned long long)((wraps << 8) + (w >> 24) - carries));
-      atomicAdd(&ksum[b], ((unsigned long long)carries << 24) + (unsigned long long)(w & 0xFFFFFFu));
-      W[b] = 0;
-      S[b] = 0;
+    const uint32_t h = H[b];
+    if (h) {
+      atomicAdd(&cnt[b], (unsigned long long)(h & 0xFFFFFu));
+      atomicAdd(&ksum[b], ((unsigned long long)(h >> 20) << 32) + (unsigned long long)L[b]);
+      H[b] = 0;
+      L[b] = 0;
     }
   }
   __syncthreads();
@@ -414,8 +389,8 @@ wasserstein_binned_fused_kernel(const float* __restrict__ u, int64_t nu,
   __shared__ long long scan_sm[64];
   __shared__ double sd[WB_BINS / RS_BLOCKS];
   __shared__ bool last;
-  uint32_t* H = bm_sh;              // main words
-  uint32_t* L = bm_sh + WB_BINS;    // side words (carry / wrap events)
+  uint32_t* L = bm_sh;              // offset sums
+  uint32_t* H = bm_sh + WB_BINS;    // counts (+ 2^20 per wrap of L)
   unsigned long long* cnt_u = tables;
   unsigned long long* ks_u = tables + WB_BINS;
   unsigned long long* cnt_v = tables + 2 * WB_BINS;
@@ -429,11 +404,11 @@ wasserstein_binned_fused_kernel(const float* __restrict__ u, int64_t nu,
   const int64_t round = (int64_t)gridDim.x * BM_MAX_PER_BLOCK;  // values per flush round (x 4 | round)
   for (int64_t r0 = 0; r0 < nu; r0 += round) {
     bm_accumulate(u + r0, min(round, nu - r0), w_base);
-    bm_flush(H, L, cnt_u, ks_u);
+    bm_flush(L, H, cnt_u, ks_u);
   }
   for (int64_t r0 = 0; r0 < nv; r0 += round) {
     bm_accumulate(v + r0, min(round, nv - r0), w_base);
-    bm_flush(H, L, cnt_v, ks_v);
+    bm_flush(L, H, cnt_v, ks_v);
   }
   grid_barrier(&ctl->barrier, 1);
 
