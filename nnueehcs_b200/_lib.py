@@ -34,6 +34,7 @@ EXPORTS = (
     "uq_partition_by_bin", "uq_wasserstein_1d_range",
     "uq_score_metrics_workspace_bytes", "uq_score_metrics",
     "uq_kde_scott_bandwidth", "uq_kde_density_workspace_bytes", "uq_kde_density",
+    "uq_sort_workspace_bytes", "uq_sort_f32",
     "uq_bin_moments", "uq_wasserstein_from_bins", "uq_compact_flagged", "uq_wasserstein_ambiguous",
 )
 
@@ -157,6 +158,10 @@ def load() -> C.CDLL:
     for name in ("uq_bin_moments", "uq_wasserstein_from_bins", "uq_compact_flagged",
                  "uq_wasserstein_ambiguous"):
         getattr(lib, name).restype = C.c_int
+    lib.uq_sort_workspace_bytes.argtypes = [i64]
+    lib.uq_sort_workspace_bytes.restype = sz
+    lib.uq_sort_f32.argtypes = [vp, i64, vp, vp, sz, vp]
+    lib.uq_sort_f32.restype = C.c_int
     lib.uq_score_metrics_workspace_bytes.argtypes = [i64, i64]
     lib.uq_score_metrics_workspace_bytes.restype = sz
     lib.uq_score_metrics.argtypes = [vp, i64, vp, i64, C.POINTER(ScoreRequest),

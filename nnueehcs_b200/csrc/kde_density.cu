@@ -115,13 +115,71 @@ kde_density_kernel(const float* __restrict__ fit, int64_t m, const float* __rest
   }
 }
 
+// Queries whose kernel sum is so small that float32 terms flushed to zero (below 2^-126) could
+// matter are listed for the float64 pass below: with s >= m 2^-100 the at most m lost terms are
+// below 2^-26 of the sum; anything smaller is re-done.  (The reference keeps such far-OOD scores
+// apart down to 1e-308 -- score_samples works in log space -- and every score consumer ranks them.)
 __global__ void kde_density_finish_kernel(const double* __restrict__ partial, int splits, int64_t n,
-                                          double scale, double* __restrict__ out) {
+                                          double scale, double rescue_below,
+                                          double* __restrict__ out,
+                                          unsigned long long* __restrict__ n_far,
+                                          int64_t* __restrict__ far_rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
   for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * n + i];
   out[i] = -s * scale;
+  if (s < rescue_below) far_rows[atomicAdd(n_far, 1ull)] = i;
+}
+
+// Far queries, one block each, in float64 and in log space: every thread folds its share of the
+// fitted rows into a running (max exponent, sum of exp(e - max)) pair, the pairs are merged in a
+// fixed order, and dens = -exp(log_norm + max) * sum -- which underflows to -0.0 only where the
+// reference's exp(score_samples) does.  Terms more than 45 below the running maximum (4e-20 of
+// it) are skipped without evaluating exp.
+constexpr int KF_THREADS_FAR = 256;
+__global__ void __launch_bounds__(KF_THREADS_FAR)
+kde_density_far_kernel(const float* __restrict__ fit, int64_t m, const float* __restrict__ x, int d,
+                       double neg_half_inv_h2, double log_norm,
+                       const unsigned long long* __restrict__ n_far,
+                       const int64_t* __restrict__ far_rows, double* __restrict__ out) {
+  __shared__ double sh_m[KF_THREADS_FAR], sh_s[KF_THREADS_FAR];
+  __shared__ float xs[KD_MAX_D];
+  const unsigned long long count = *n_far;
+  for (unsigned long long q = blockIdx.x; q < count; q += gridDim.x) {
+    const int64_t row = far_rows[q];
+    __syncthreads();
+    if (threadIdx.x < d) xs[threadIdx.x] = x[row * d + threadIdx.x];
+    __syncthreads();
+    double mx = -1.0e300, sum = 0.0;
+    for (int64_t j = threadIdx.x; j < m; j += KF_THREADS_FAR) {
+      double s2 = 0.0;
+      for (int i = 0; i < d; ++i) {
+        const double df = (double)xs[i] - (double)__ldg(fit + j * d + i);
+        s2 = fma(df, df, s2);
+      }
+      const double e = s2 * neg_half_inv_h2;
+      if (e > mx) {
+        sum = (mx - e > -45.0 ? sum * exp(mx - e) : 0.0) + 1.0;
+        mx = e;
+      } else if (e - mx > -45.0) {
+        sum += exp(e - mx);
+      }
+    }
+    sh_m[threadIdx.x] = mx, sh_s[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = KF_THREADS_FAR / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        const double ma = sh_m[threadIdx.x], mb = sh_m[threadIdx.x + o];
+        const double sa = sh_s[threadIdx.x], sb = sh_s[threadIdx.x + o];
+        const double mm = ma > mb ? ma : mb;
+        sh_s[threadIdx.x] = sa * exp(ma - mm) + sb * exp(mb - mm);   // empty shares: s = 0
+        sh_m[threadIdx.x] = mm;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[row] = -exp(log_norm + sh_m[0]) * sh_s[0];
+  }
 }
 
 int choose_splits(int64_t n, int64_t m) {
@@ -146,9 +204,16 @@ int launch(const float* fit, int64_t m, const float* x, int64_t n, int d, float 
 
 }  // namespace
 
+namespace {
+size_t partial_bytes(int64_t n, int64_t m) {
+  return (sizeof(double) * (size_t)choose_splits(n, m) * (size_t)n + 255) & ~(size_t)255;
+}
+}  // namespace
+
+// [partial sums | far-query counter | far-query rows]
 size_t kde_density_workspace_bytes(int64_t n, int64_t m) {
   if (n < 1 || m < 1) return 0;
-  return sizeof(double) * (size_t)choose_splits(n, m) * (size_t)n + 256;
+  return partial_bytes(n, m) + 256 + sizeof(int64_t) * (size_t)n;
 }
 
 int kde_density(const float* fit, int64_t m, const float* x, int64_t n, int d, double bandwidth,
@@ -179,8 +244,18 @@ int kde_density(const float* fit, int64_t m, const float* x, int64_t n, int d, d
   // normalisation of sklearn's Gaussian kernel and the 1/M of score_samples, float64
   const double log_norm = -(double)d * log(bandwidth) - 0.5 * (double)d * log(2.0 * M_PI) -
                           log((double)m);
-  kde_density_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, splits, n,
-                                                                         exp(log_norm), out);
+  char* wsb = static_cast<char*>(ws);
+  unsigned long long* n_far = reinterpret_cast<unsigned long long*>(wsb + partial_bytes(n, m));
+  int64_t* far_rows = reinterpret_cast<int64_t*>(wsb + partial_bytes(n, m) + 256);
+  UQ_CUDA(cudaMemsetAsync(n_far, 0, sizeof(unsigned long long), st));
+  kde_density_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+      partial, splits, n, exp(log_norm), (double)m * 7.888609052210118e-31 /* m 2^-100 */, out,
+      n_far, far_rows);
+  UQ_LAUNCH_CHECK();
+  // far queries (none for in-distribution inputs: the blocks read the counter and leave)
+  int64_t far_blocks = n < 148 * 8 ? n : 148 * 8;
+  kde_density_far_kernel<<<(unsigned)far_blocks, KF_THREADS_FAR, 0, st>>>(
+      fit, m, x, d, -0.5 / (bandwidth * bandwidth), log_norm, n_far, far_rows, out);
   UQ_LAUNCH_CHECK();
   return UQ_OK;
 }

@@ -1,9 +1,11 @@
 // Stable LSD radix sort (8-bit digits, 4 passes) of float32 keys: upsweep histogram ->
 // single-block spine scan -> downsweep scatter.  Each block owns a contiguous key range, so the
-// spine is only 256 x (#blocks) counters; inside a tile, ranks come from warp-wide
-// __match_any_sync multisplit (stable: lanes, rounds, warps, tiles and blocks are all visited in
-// key order), loads are fully coalesced and the scattered 4-byte stores of one digit land in a
-// run that the 126 MB L2 merges before write-back.
+// spine is only 256 x (#blocks) counters; inside a tile, ranks come from lane-private byte
+// counters in shared memory (stable: items, lanes, warps, tiles and blocks are all visited in key
+// order), the tile is staged in sorted order in shared memory, and the 4-byte stores of one
+// digit land in a run that the 126 MB L2 merges before write-back.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -12,9 +14,8 @@ namespace {
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys
 constexpr int RADIX = 256;
+constexpr int MAX_SORT_BLOCKS = 148 * 2;   // <= SPINE_THREADS: one spine row is one block scan
 
 __device__ __forceinline__ uint32_t f2key(uint32_t b) {
   return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
@@ -25,17 +26,17 @@ __device__ __forceinline__ uint32_t key2f(uint32_t k) {
 
 template <bool FIRST>
 __global__ void __launch_bounds__(SORT_THREADS)
-upsweep_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int64_t tiles_per_block,
-               uint32_t* __restrict__ spine, int num_blocks) {
+upsweep_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int64_t keys_per_block,
+               uint32_t* __restrict__ spine, int num_blocks, uint32_t* __restrict__ digit_totals) {
   __shared__ uint32_t wh[SORT_WARPS][RADIX];
   const int t = threadIdx.x, w = t >> 5;
   for (int i = t; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&wh[0][0])[i] = 0;
   __syncthreads();
-  const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * SORT_TILE;
-  int64_t end = begin + tiles_per_block * SORT_TILE;
+  const int64_t begin = (int64_t)blockIdx.x * keys_per_block;
+  int64_t end = begin + keys_per_block;
   if (end > n) end = n;
   // 128-bit loads over the aligned bulk of the range
-  const int64_t vbeg = begin / 4, vend = end / 4;   // begin is a multiple of 4096
+  const int64_t vbeg = begin / 4, vend = end / 4;   // begin is a multiple of the tile size
   const uint4* k4 = reinterpret_cast<const uint4*>(keys);
   for (int64_t i = vbeg + t; i < vend; i += SORT_THREADS) {
     const uint4 v = k4[i];
@@ -56,204 +57,346 @@ upsweep_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int64_t 
 #pragma unroll
     for (int ww = 0; ww < SORT_WARPS; ++ww) s += wh[ww][d];
     spine[(int64_t)d * num_blocks + blockIdx.x] = s;
+    if (s) atomicAdd(digit_totals + d, s);   // whole-array count of digit d (zeroed per sort)
   }
 }
 
-// exclusive scan of the digit-major spine, one block of 1024 threads walking it in coalesced
-// 4096-element slabs (uint4 per thread) with a running carry
-__global__ void __launch_bounds__(1024) spine_scan_kernel(uint32_t* __restrict__ spine, int total) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_s;
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < total; base += 4096) {
-    const uint32_t carry = carry_s;   // written by warp 0 between the two barriers below
-    const int i0 = base + t * 4;
-    uint32_t v[4] = {0, 0, 0, 0};
-    if (i0 + 3 < total) {
-      const uint4 q = *reinterpret_cast<const uint4*>(spine + i0);
-      v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
-    } else {
+// exclusive scan of the digit-major spine: block d scans digit d's row (one counter per upsweep
+// block, at most SPINE_THREADS of them) and starts it at the number of keys with a smaller digit,
+// which it gets from the 256 whole-array digit totals the upsweep accumulated.  (One block walking
+// all 256 x 291 counters took 24 us per pass, a tenth of the downsweep.)
+constexpr int SPINE_THREADS = 320;
+static_assert(MAX_SORT_BLOCKS <= SPINE_THREADS && RADIX <= SPINE_THREADS, "one row, one block");
+__global__ void __launch_bounds__(SPINE_THREADS)
+spine_scan_kernel(uint32_t* __restrict__ spine, int num_blocks,
+                  const uint32_t* __restrict__ digit_totals) {
+  __shared__ uint32_t warp_sums[SPINE_THREADS / 32];
+  __shared__ uint32_t below_s[SPINE_THREADS / 32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, d = blockIdx.x;
+  uint32_t below = (t < d) ? digit_totals[t] : 0u;   // d < RADIX <= SPINE_THREADS
+  const uint32_t v = t < num_blocks ? spine[(int64_t)d * num_blocks + t] : 0u;
+  uint32_t incl = v;
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (i0 + e < total) v[e] = spine[i0 + e];
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_down_sync(0xffffffffu, below, o);
+  if (lane == 31) warp_sums[w] = incl;
+  if (lane == 0) below_s[w] = below;
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int ww = 0; ww < SPINE_THREADS / 32; ++ww) {
+    base += below_s[ww];
+    if (ww < w) base += warp_sums[ww];
+  }
+  if (t < num_blocks) spine[(int64_t)d * num_blocks + t] = base + incl - v;
+}
+
+// ---- downsweep: lane-private byte counters --------------------------------------------------------
+// A warp owns ITEMS * 32 consecutive keys of the tile and each LANE owns ITEMS consecutive keys of
+// those, so "key order" is (warp, lane, item).  Ranking needs no warp collectives at all:
+//   count   every lane bumps its own byte counter cnt[digit][lane] once per key (the old value is
+//           the key's rank among the lane's earlier keys with that digit; <= ITEMS <= 32);
+//   scan    lane L takes the digit rows L, L + 32, ... : the 32 lane counters of a row are eight
+//           words; an exclusive prefix inside each word is one IMAD (x * 0x01010100, <= 96 so no
+//           byte overflows), the prefix over the words is a DP4A chain; the byte prefixes go back
+//           in place, the eight word bases into a 16-bit table, the row total to the block scan;
+//   rank    position in the tile = block offset of (digit, warp) + word base + byte prefix + rank
+//           in the lane: three shared loads per key.
+// The ballot version of this kernel (nine VOTEs and ~60 instructions per 32 keys and round, every
+// round waiting for the previous one's counter update) issued 106 warp instructions per 32 keys
+// and ran at 0.39 keys per clock and SM; this one issues ~35.
+// Shared-memory layout of a warp's counters: byte (digit d, lane l) sits at
+// (l >> 4) * 4096 + d * 16 + (l & 15), i.e. two planes of 16-byte rows, so the scan's 128-bit row
+// loads of consecutive lanes are consecutive (conflict-free) and the counting step collides only
+// when two of the eight lanes that share a bank hold different digits with equal d mod 8.
+template <int ITEMS>
+struct Down {
+  static constexpr int TILE = SORT_THREADS * ITEMS;
+  static constexpr int CNT_BYTES = SORT_WARPS * 8192;            // aliased by the staged tile
+  static constexpr int BASE_OFF = CNT_BYTES;                     // u16 [warp][256][8]
+  static constexpr int WOFF_OFF = BASE_OFF + SORT_WARPS * 4096;  // u16 [warp][256]
+  static constexpr int DBASE_OFF = WOFF_OFF + SORT_WARPS * 512;  // u32 [256]
+  static constexpr int GDELTA_OFF = DBASE_OFF + 1024;            // u32 [256]
+  static constexpr int WTOT_OFF = GDELTA_OFF + 1024;             // u32 [warps]
+  static constexpr int SMEM = WTOT_OFF + SORT_WARPS * 4;
+  static_assert(TILE * 4 <= CNT_BYTES, "staged tile must fit the counter area");
+  static_assert(ITEMS % 4 == 0 && ITEMS <= 32, "byte counters: at most 32 keys per lane");
+};
+
+// One tile.  FULL = every key of the tile exists (all tiles but the last one of the array): no
+// per-key validity tests anywhere.
+template <int ITEMS, bool FIRST, bool LAST, bool FULL>
+__device__ __forceinline__ void downsweep_tile(const uint32_t* __restrict__ in,
+                                               uint32_t* __restrict__ out, int64_t tile0,
+                                               int64_t end, int shift, unsigned char* smem) {
+  using D = Down<ITEMS>;
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  unsigned char* cnt_w = smem + w * 8192;
+  uint32_t* staged = reinterpret_cast<uint32_t*>(smem);
+  unsigned short* base_w = reinterpret_cast<unsigned short*>(smem + D::BASE_OFF + w * 4096);
+  unsigned short* woff = reinterpret_cast<unsigned short*>(smem + D::WOFF_OFF);
+  unsigned short* woff_w = woff + w * RADIX;
+  uint32_t* digit_base = reinterpret_cast<uint32_t*>(smem + D::DBASE_OFF);
+  uint32_t* gdelta = reinterpret_cast<uint32_t*>(smem + D::GDELTA_OFF);
+  uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + D::WTOT_OFF);
+  const uint32_t lane_off = (uint32_t)(lane >> 4) * 4096u + (uint32_t)(lane & 15);
+
+  // ---- keys: lane l owns keys [l * ITEMS, (l + 1) * ITEMS) of the warp's run.  Loading them
+  // straight from global memory (128-bit loads ITEMS * 4 bytes apart) costs one L1 wavefront per
+  // lane and load -- a quarter of all the LSU wavefronts of this LSU-bound kernel -- so the warp
+  // loads its run coalesced (4 wavefronts per load) and transposes it through its own counter
+  // area: rows of ITEMS keys padded by 16 bytes, so both the coalesced stores and the per-lane
+  // 128-bit loads are conflict-free.
+  uint32_t key[ITEMS];
+  const int64_t wbase = tile0 + (int64_t)w * (32 * ITEMS);
+  const int64_t lbase = wbase + (int64_t)lane * ITEMS;
+  int nvalid = ITEMS;
+  if (FULL) {
+    constexpr int ROW = ITEMS * 4 + 16;
+    const uint4* src = reinterpret_cast<const uint4*>(in + wbase);
+    uint4 v[ITEMS / 4];
+#pragma unroll
+    for (int r = 0; r < ITEMS / 4; ++r) v[r] = __ldg(src + r * 32 + lane);
+#pragma unroll
+    for (int r = 0; r < ITEMS / 4; ++r) {
+      const int e = 128 * r + 4 * lane;            // first of the four keys, within the warp's run
+      const int o = e / ITEMS;                     // owner lane
+      *reinterpret_cast<uint4*>(cnt_w + o * ROW + (e - o * ITEMS) * 4) = v[r];
     }
-    const uint32_t s = v[0] + v[1] + v[2] + v[3];
-    uint32_t incl = s;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < ITEMS / 4; ++q) {
+      const uint4 k4 = *reinterpret_cast<const uint4*>(cnt_w + lane * ROW + q * 16);
+      key[4 * q + 0] = k4.x, key[4 * q + 1] = k4.y, key[4 * q + 2] = k4.z, key[4 * q + 3] = k4.w;
+    }
+    __syncwarp();
+  } else {
+    const int64_t left = end - lbase;
+    nvalid = left >= ITEMS ? ITEMS : (left > 0 ? (int)left : 0);
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) key[r] = r < nvalid ? __ldg(in + lbase + r) : 0u;
+  }
+  if (FIRST) {
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) key[r] = f2key(key[r]);
+  }
+  // ---- zero this warp's counters (conflict-free 128-bit stores)
+  {
+    uint4* z = reinterpret_cast<uint4*>(cnt_w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[lane + 32 * i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncwarp();
+  // ---- count: rk = rank among the lane's earlier keys with the same digit
+  uint32_t rk[ITEMS];
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const uint32_t d = (key[r] >> shift) & 0xFFu;
+    rk[r] = 0;
+    if (FULL || r < nvalid) {
+      unsigned char* c = cnt_w + d * 16u + lane_off;
+      const uint32_t old = *c;
+      *c = (unsigned char)(old + 1u);
+      rk[r] = old;
+    }
+  }
+  __syncwarp();
+  // ---- scan the 32 lane counters of each digit row
+#pragma unroll
+  for (int i = 0; i < RADIX / 32; ++i) {
+    const int d = lane + 32 * i;
+    uint4* rowa = reinterpret_cast<uint4*>(cnt_w + d * 16);
+    uint4* rowb = reinterpret_cast<uint4*>(cnt_w + 4096 + d * 16);
+    const uint4 a = *rowa, b = *rowb;
+    const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t base[8], pre[8];
+    uint32_t run = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      base[j] = run;
+      pre[j] = x[j] * 0x01010100u;
+      run = __dp4a(x[j], 0x01010101u, run);
+    }
+    *rowa = make_uint4(pre[0], pre[1], pre[2], pre[3]);
+    *rowb = make_uint4(pre[4], pre[5], pre[6], pre[7]);
+    reinterpret_cast<uint4*>(base_w)[d] =
+        make_uint4(base[0] | (base[1] << 16), base[2] | (base[3] << 16),
+                   base[4] | (base[5] << 16), base[6] | (base[7] << 16));
+    woff_w[d] = (unsigned short)run;
+  }
+  __syncthreads();
+  // ---- thread t == digit t: where each (digit, warp) run starts in the tile and in `out`
+  {
+    uint32_t c[SORT_WARPS];
+    uint32_t total = 0;
+#pragma unroll
+    for (int ww = 0; ww < SORT_WARPS; ++ww) {
+      c[ww] = woff[ww * RADIX + t];
+      total += c[ww];
+    }
+    uint32_t incl = total;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += y;
     }
-    if (lane == 31) warp_sums[w] = incl;
+    if (lane == 31) warp_tot[w] = incl;
     __syncthreads();
-    if (w == 0) {
-      const uint32_t ws = warp_sums[lane];
-      uint32_t wi = ws;
+    uint32_t before = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += y;
-      }
-      warp_sums[lane] = wi - ws;
-      if (lane == 31) carry_s = carry + wi;   // read by everyone only after the next barrier
-    }
-    __syncthreads();
-    uint32_t run = carry + warp_sums[w] + incl - s;
-    uint32_t o4[4];
+    for (int ww = 0; ww < SORT_WARPS; ++ww)
+      if (ww < w) before += warp_tot[ww];
+    const uint32_t off = before + incl - total;   // first tile-local position of digit t
+    // the start of (digit t, warp ww)'s run goes into that warp's eight word bases of the digit
+    // (packed 16-bit adds, no carries: base + start < 2^14), so ranking needs no third table
+    uint32_t run = off;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      o4[e] = run;
-      run += v[e];
+    for (int ww = 0; ww < SORT_WARPS; ++ww) {
+      uint4* bp = reinterpret_cast<uint4*>(smem + D::BASE_OFF + ww * 4096) + t;
+      uint4 bv = *bp;
+      const uint32_t add = run * 0x00010001u;
+      bv.x += add, bv.y += add, bv.z += add, bv.w += add;
+      *bp = bv;
+      run += c[ww];
     }
-    if (i0 + 3 < total) {
-      *reinterpret_cast<uint4*>(spine + i0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (i0 + e < total) spine[i0 + e] = o4[e];
-    }
-    __syncthreads();   // warp_sums / carry_s are rewritten by the next slab
+    gdelta[t] = digit_base[t] - off;              // global position = gdelta[d] + local position
+    digit_base[t] += total;
   }
-}
-
-// 4 blocks per SM (<= 64 registers): the ranking rounds are a chain of dependent warp-collectives
-// and shared-memory updates, so the kernel is latency-bound and wants warps, not registers
-template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(SORT_THREADS, 4)
-downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n, int shift,
-                 int64_t tiles_per_block, const uint32_t* __restrict__ spine, int num_blocks) {
-  __shared__ uint32_t digit_base[RADIX];   // running global position of each digit's next key
-  __shared__ uint32_t tile_off[RADIX];     // first tile-local position of each digit
-  __shared__ uint32_t gdelta[RADIX];
-  __shared__ uint32_t warp_tot[SORT_WARPS];
-  __shared__ uint32_t wh[SORT_WARPS][RADIX];
-  __shared__ uint32_t staged[SORT_TILE];   // the tile in sorted order
-  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int d = t; d < RADIX; d += SORT_THREADS)
-    digit_base[d] = spine[(int64_t)d * num_blocks + blockIdx.x];
-  const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * SORT_TILE;
-  int64_t end = begin + tiles_per_block * SORT_TILE;
-  if (end > n) end = n;
-
-  for (int64_t tile0 = begin; tile0 < end; tile0 += SORT_TILE) {
-    for (int i = t; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&wh[0][0])[i] = 0;
-    __syncthreads();
-    uint32_t key[SORT_ITEMS];
-    uint32_t rank[SORT_ITEMS];
-    const int64_t wbase = tile0 + (int64_t)w * 32 * SORT_ITEMS;
-    // all 16 loads of the tile are issued before any of them is consumed: inside the ranking loop
-    // the warp-synchronous steps would otherwise serialise one HBM round trip per round
+  __syncthreads();
+  // ---- rank: tile-local destination of every key
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
-      const int64_t idx = wbase + r * 32 + lane;
-      uint32_t k = 0xFFFFFFFFu;
-      if (idx < end) k = FIRST ? f2key(__ldg(in + idx)) : __ldg(in + idx);
-      key[r] = k;
-    }
+  for (int r = 0; r < ITEMS; ++r) {
+    const uint32_t d = (key[r] >> shift) & 0xFFu;
+    rk[r] += (uint32_t)cnt_w[d * 16u + lane_off] + (uint32_t)base_w[d * 8u + (lane >> 2)];
+  }
+  __syncthreads();   // every warp is done with the counters: the staged tile takes their place
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
-      const int64_t idx = wbase + r * 32 + lane;
-      const bool valid = idx < end;
-      const uint32_t k = key[r];
-      // lanes holding the same digit, from nine ballots (one per digit bit + validity).
-      // MATCH.ANY does the same in one instruction but runs on the ADU pipe at ~64 cycles per
-      // warp on sm_100 (ncu: ADU 57 % busy, kernel 10x off the HBM roofline); ballots and LOP3s
-      // issue at full rate.
+  for (int r = 0; r < ITEMS; ++r)
+    if (FULL || r < nvalid) staged[rk[r]] = key[r];
+  __syncthreads();
+  // ---- consecutive threads write consecutive addresses of a digit's run
+  if (FULL) {
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+      const int i = t + r * SORT_THREADS;
+      const uint32_t k = staged[i];
       const uint32_t d = (k >> shift) & 0xFFu;
-      uint32_t peers = __ballot_sync(0xffffffffu, valid);
-      if (!valid) peers = ~peers;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? bal : ~bal;
-      }
-      const int leader = __ffs(peers) - 1;
-      uint32_t old = 0;
-      if (valid && lane == leader) {
-        old = wh[w][d];
-        wh[w][d] = old + __popc(peers);
-      }
-      old = __shfl_sync(0xffffffffu, old, leader);
-      rank[r] = old + __popc(peers & lt_mask);
-      __syncwarp();
+      out[gdelta[d] + (uint32_t)i] = LAST ? key2f(k) : k;
     }
-    __syncthreads();
-    // thread t == digit t: offsets of the warps inside the digit's run, the digit's run inside the
-    // tile (block-wide exclusive scan), and where that run goes in global memory
-    {
-      uint32_t run = 0;
-#pragma unroll
-      for (int ww = 0; ww < SORT_WARPS; ++ww) {
-        const uint32_t c = wh[ww][t];
-        wh[ww][t] = run;
-        run += c;
-      }
-      uint32_t incl = run;   // digits-in-tile inclusive scan
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      if (lane == 31) warp_tot[w] = incl;
-      __syncthreads();
-      uint32_t before = 0;
-#pragma unroll
-      for (int ww = 0; ww < SORT_WARPS; ++ww)
-        if (ww < w) before += warp_tot[ww];
-      const uint32_t off = before + incl - run;   // first tile-local position of digit t
-      tile_off[t] = off;
-      gdelta[t] = digit_base[t] - off;            // global position = gdelta[d] + local position
-      digit_base[t] += run;
-    }
-    __syncthreads();
-    // keys go to their tile-local sorted position in shared memory first ...
-#pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
-      const int64_t idx = wbase + r * 32 + lane;
-      if (idx < end) {
-        const uint32_t d = (key[r] >> shift) & 0xFFu;
-        staged[tile_off[d] + wh[w][d] + rank[r]] = key[r];
-      }
-    }
-    __syncthreads();
-    // ... so that consecutive threads write consecutive addresses of a digit's run: a warp's store
-    // touches a few sectors instead of 32 (the direct scatter was LSU-sector bound)
-    const int tile_n = (int)((end - tile0) < (int64_t)SORT_TILE ? (end - tile0) : (int64_t)SORT_TILE);
-#pragma unroll 4
+  } else {
+    const int tile_n = (int)(end - tile0);
     for (int i = t; i < tile_n; i += SORT_THREADS) {
       const uint32_t k = staged[i];
       const uint32_t d = (k >> shift) & 0xFFu;
       out[gdelta[d] + (uint32_t)i] = LAST ? key2f(k) : k;
     }
-    __syncthreads();
+  }
+  __syncthreads();
+}
+
+template <int ITEMS, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SORT_THREADS, 2)
+downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n, int shift,
+                 int64_t tiles_per_block, const uint32_t* __restrict__ spine, int num_blocks) {
+  using D = Down<ITEMS>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t* digit_base = reinterpret_cast<uint32_t*>(smem + D::DBASE_OFF);
+  // SORT_THREADS == RADIX: thread t owns digit t's running output position
+  digit_base[threadIdx.x] = spine[(int64_t)threadIdx.x * num_blocks + blockIdx.x];
+  const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * D::TILE;
+  int64_t end = begin + tiles_per_block * D::TILE;
+  if (end > n) end = n;
+  for (int64_t tile0 = begin; tile0 < end; tile0 += D::TILE) {
+    if (tile0 + D::TILE <= end)
+      downsweep_tile<ITEMS, FIRST, LAST, true>(in, out, tile0, end, shift, smem);
+    else
+      downsweep_tile<ITEMS, FIRST, LAST, false>(in, out, tile0, end, shift, smem);
   }
 }
 
 struct SortPlan {
+  int items;                 // keys per lane and tile: 16 or 32
   int num_blocks;
   int64_t tiles_per_block;
+  int64_t tile() const { return (int64_t)SORT_THREADS * items; }
 };
 
+// 32 keys per lane (8192-key tiles: the row scan is paid once per 1024 keys of a warp and a
+// digit's run in the output is twice as long) unless the array is too short to give every SM two
+// blocks of them; UQ_SORT_ITEMS=16|32 overrides (A/B runs).
 SortPlan sort_plan(int64_t n) {
-  const int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-  int64_t nb = tiles < 148 * 4 ? tiles : 148 * 4;
-  if (nb < 1) nb = 1;
+  static const int forced = [] {
+    const char* e = getenv("UQ_SORT_ITEMS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 16 || v == 32) ? v : 0;
+  }();
   SortPlan p;
+  p.items = forced ? forced : (n >= (int64_t)148 * 2 * SORT_THREADS * 32 ? 32 : 16);
+  const int64_t tiles = (n + p.tile() - 1) / p.tile();
+  int64_t nb = tiles < MAX_SORT_BLOCKS ? tiles : MAX_SORT_BLOCKS;   // two resident blocks per SM, one wave
+  if (nb < 1) nb = 1;
   p.tiles_per_block = (tiles + nb - 1) / nb;
   p.num_blocks = (int)((tiles + p.tiles_per_block - 1) / p.tiles_per_block);
   if (p.num_blocks < 1) p.num_blocks = 1;
   return p;
 }
 
+template <int ITEMS>
+int sort_passes(uint32_t* a, uint32_t* b, int64_t n, const SortPlan& p, uint32_t* spine,
+                uint32_t* digit_totals, cudaStream_t st) {
+  static PerDeviceOnce opted[3];
+  constexpr int SMEM = Down<ITEMS>::SMEM;
+  if (int rc = smem_opt_in(downsweep_kernel<ITEMS, true, false>, SMEM, opted[0])) return rc;
+  if (int rc = smem_opt_in(downsweep_kernel<ITEMS, false, false>, SMEM, opted[1])) return rc;
+  if (int rc = smem_opt_in(downsweep_kernel<ITEMS, false, true>, SMEM, opted[2])) return rc;
+  const int64_t per_block = p.tiles_per_block * p.tile();
+  UQ_CUDA(cudaMemsetAsync(digit_totals, 0, 4 * RADIX * sizeof(uint32_t), st));
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = pass * 8;
+    uint32_t* totals = digit_totals + pass * RADIX;
+    if (pass == 0)
+      upsweep_kernel<true><<<p.num_blocks, SORT_THREADS, 0, st>>>(a, n, shift, per_block, spine,
+                                                                p.num_blocks, totals);
+    else
+      upsweep_kernel<false><<<p.num_blocks, SORT_THREADS, 0, st>>>(a, n, shift, per_block, spine,
+                                                                 p.num_blocks, totals);
+    UQ_LAUNCH_CHECK();
+    spine_scan_kernel<<<RADIX, SPINE_THREADS, 0, st>>>(spine, p.num_blocks, totals);
+    UQ_LAUNCH_CHECK();
+    if (pass == 0)
+      downsweep_kernel<ITEMS, true, false><<<p.num_blocks, SORT_THREADS, SMEM, st>>>(
+          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
+    else if (pass == 3)
+      downsweep_kernel<ITEMS, false, true><<<p.num_blocks, SORT_THREADS, SMEM, st>>>(
+          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
+    else
+      downsweep_kernel<ITEMS, false, false><<<p.num_blocks, SORT_THREADS, SMEM, st>>>(
+          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
+    UQ_LAUNCH_CHECK();
+    uint32_t* s = a;
+    a = b;
+    b = s;
+  }
+  return UQ_OK;
+}
+
+}  // namespace
+
+namespace {
+// spine for either tile size (the plan can be overridden at run time)
+size_t spine_bytes(int64_t n) {
+  const int64_t tiles = (n + SORT_THREADS * 16 - 1) / (SORT_THREADS * 16);
+  const int64_t nb = tiles < MAX_SORT_BLOCKS ? (tiles < 1 ? 1 : tiles) : MAX_SORT_BLOCKS;
+  return (((size_t)RADIX * (size_t)nb * sizeof(uint32_t)) + 255) & ~(size_t)255;
+}
 }  // namespace
 
 size_t radix_sort_scratch_bytes(int64_t n) {
-  const SortPlan p = sort_plan(n);
-  return (((size_t)RADIX * p.num_blocks * sizeof(uint32_t)) + 255) & ~(size_t)255;
+  return spine_bytes(n) + 4 * RADIX * sizeof(uint32_t);   // + the digit totals of the four passes
 }
 
 int radix_sort_f32(float* keys, float* tmp, int64_t n, void* scratch, size_t scratch_bytes,
@@ -262,37 +405,47 @@ int radix_sort_f32(float* keys, float* tmp, int64_t n, void* scratch, size_t scr
              "radix sort: n = %lld outside [1, 2^31)", (long long)n);
   UQ_REQUIRE(scratch && scratch_bytes >= radix_sort_scratch_bytes(n), UQ_ERR_WORKSPACE,
              "radix sort: scratch too small");
+  UQ_REQUIRE(((uintptr_t)keys & 15) == 0 && ((uintptr_t)tmp & 15) == 0, UQ_ERR_INVALID,
+             "radix sort: key buffers must be 16-byte aligned");
   const SortPlan p = sort_plan(n);
   uint32_t* spine = static_cast<uint32_t*>(scratch);
   uint32_t* a = reinterpret_cast<uint32_t*>(keys);
   uint32_t* b = reinterpret_cast<uint32_t*>(tmp);
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = pass * 8;
-    if (pass == 0)
-      upsweep_kernel<true><<<p.num_blocks, SORT_THREADS, 0, st>>>(a, n, shift, p.tiles_per_block,
-                                                                spine, p.num_blocks);
-    else
-      upsweep_kernel<false><<<p.num_blocks, SORT_THREADS, 0, st>>>(a, n, shift, p.tiles_per_block,
-                                                                 spine, p.num_blocks);
-    UQ_LAUNCH_CHECK();
-    spine_scan_kernel<<<1, 1024, 0, st>>>(spine, RADIX * p.num_blocks);
-    UQ_LAUNCH_CHECK();
-    if (pass == 0)
-      downsweep_kernel<true, false><<<p.num_blocks, SORT_THREADS, 0, st>>>(
-          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
-    else if (pass == 3)
-      downsweep_kernel<false, true><<<p.num_blocks, SORT_THREADS, 0, st>>>(
-          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
-    else
-      downsweep_kernel<false, false><<<p.num_blocks, SORT_THREADS, 0, st>>>(
-          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
-    UQ_LAUNCH_CHECK();
-    uint32_t* s = a;
-    a = b;
-    b = s;
-  }
-  *sorted = reinterpret_cast<float*>(a);  // 4 passes: result is back in `keys`
+  uint32_t* totals = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + spine_bytes(n));
+  const int rc = p.items == 32 ? sort_passes<32>(a, b, n, p, spine, totals, st)
+                               : sort_passes<16>(a, b, n, p, spine, totals, st);
+  if (rc != UQ_OK) return rc;
+  *sorted = keys;  // 4 passes: the result is back in `keys`
   return UQ_OK;
 }
 
 }  // namespace uq
+
+// ---- C ABI: the sort on its own (tests, tools/bench_metrics.py) -------------------------------------
+namespace {
+size_t sort_al(size_t b) { return (b + 255) & ~(size_t)255; }
+}  // namespace
+
+size_t uq_sort_workspace_bytes(int64_t n) {
+  if (n < 1) return 0;
+  return sort_al(sizeof(float) * (size_t)n) + sort_al(uq::radix_sort_scratch_bytes(n));
+}
+
+int uq_sort_f32(const float* x, int64_t n, float* out, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  UQ_REQUIRE(x && out && n >= 1, UQ_ERR_INVALID, "uq_sort_f32: NULL argument or n < 1");
+  UQ_REQUIRE(workspace && workspace_bytes >= uq_sort_workspace_bytes(n), UQ_ERR_WORKSPACE,
+             "uq_sort_f32: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* w = static_cast<char*>(workspace);
+  float* tmp = reinterpret_cast<float*>(w);
+  if (out != x)
+    UQ_CUDA(cudaMemcpyAsync(out, x, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  float* sorted = nullptr;
+  const int rc = uq::radix_sort_f32(out, tmp, n, w + sort_al(sizeof(float) * (size_t)n),
+                                    uq::radix_sort_scratch_bytes(n), &sorted, st);
+  if (rc != UQ_OK) return rc;
+  if (sorted != out)
+    UQ_CUDA(cudaMemcpyAsync(out, sorted, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  return UQ_OK;
+}

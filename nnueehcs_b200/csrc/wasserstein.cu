@@ -38,6 +38,39 @@ constexpr int MRG_THREADS = 256;
 constexpr int MRG_ITEMS = 8;
 constexpr int MRG_TILE = MRG_THREADS * MRG_ITEMS;  // merged positions per block
 
+__device__ __forceinline__ int merge_path_smem(const float* U, int nu, const float* V, int nv, int k) {
+  int lo = k > nv ? k - nv : 0;
+  int hi = k < nu ? k : nu;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (U[mid] <= V[k - mid - 1]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// |a / na - b / nb| for ranks a <= na, b <= nb.  scipy divides each rank by its sample size in
+// float64 and subtracts (two roundings of 1.1e-16 each on numbers near 1, so its difference
+// carries an ABSOLUTE error of ~1e-16); here the difference is the exact integer a nb - b na
+// times one rounded reciprocal: closer to the true value, and no float64 division per merged
+// element (two of them were 60 % of the integral kernel's instructions).  Sample sizes of 2^31
+// and more (sharded totals) keep scipy's form.
+struct CdfScale {
+  long long na, nb;
+  double dna, dnb, inv;
+  bool exact;
+};
+__device__ __forceinline__ CdfScale cdf_scale(long long na, long long nb) {
+  CdfScale s;
+  s.na = na, s.nb = nb, s.dna = (double)na, s.dnb = (double)nb;
+  s.exact = na < (1ll << 31) && nb < (1ll << 31);
+  s.inv = 1.0 / (s.dna * s.dnb);
+  return s;
+}
+__device__ __forceinline__ double cdf_gap(const CdfScale& s, long long a, long long b) {
+  if (s.exact) return fabs((double)(a * s.nb - b * s.na)) * s.inv;
+  return fabs((double)a / s.dna - (double)b / s.dnb);
+}
+
 // number of u's among the first k merged elements (u before v on ties)
 __device__ __forceinline__ int64_t merge_path(const float* __restrict__ U, int64_t nu,
                                               const float* __restrict__ V, int64_t nv, int64_t k) {
@@ -50,19 +83,33 @@ __device__ __forceinline__ int64_t merge_path(const float* __restrict__ U, int64
   return lo;
 }
 
-__device__ __forceinline__ int merge_path_smem(const float* U, int nu, const float* V, int nv, int k) {
-  int lo = k > nv ? k - nv : 0;
-  int hi = k < nu ? k : nu;
+// The same split found by a whole warp, 33-ary: every lane probes one point of the range and a
+// ballot finds the first failing probe, so a 50 M-value range closes in 6 rounds of one load
+// instead of 26 dependent ones.  (Used once per persistent block.  As a replacement of the
+// one-thread search for EVERY tile boundary it was slower -- 83 us against 34 for 48 829 splits:
+// the probes of a round touch 64 distinct sectors.)
+__device__ __forceinline__ int64_t merge_path_warp(const float* __restrict__ U, int64_t nu,
+                                                   const float* __restrict__ V, int64_t nv,
+                                                   int64_t k) {
+  const int lane = threadIdx.x & 31;
+  int64_t lo = k > nv ? k - nv : 0;
+  int64_t hi = k < nu ? k : nu;
+  // the answer is in [lo, hi]; pred(mid) = U[mid] <= V[k - mid - 1] holds exactly for mid < answer
   while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (U[mid] <= V[k - mid - 1]) lo = mid + 1; else hi = mid;
+    const int64_t span = hi - lo;
+    const int64_t mid = lo + (span * (lane + 1)) / 33;   // lo <= mid < hi, non-decreasing in lane
+    const bool pred = U[mid] <= V[k - mid - 1];
+    const int c = __popc(__ballot_sync(0xffffffffu, pred));   // the true probes are a prefix
+    const int64_t mid_last_true = __shfl_sync(0xffffffffu, mid, c > 0 ? c - 1 : 0);
+    const int64_t mid_first_false = __shfl_sync(0xffffffffu, mid, c < 32 ? c : 31);
+    if (c > 0) lo = mid_last_true + 1;
+    if (c < 32) hi = mid_first_false;
   }
-  return lo;
+  return lo < hi ? lo : hi;   // lo > hi only if NaNs break the monotone order
 }
 
-// merge-path split of every block boundary k = b * MRG_TILE, one thread each: done up front so the
-// ~25 dependent global loads of a binary search are paid once in parallel instead of serially by
-// thread 0 of each of the ~50 k integral blocks (that cost 0.6 of the kernel's 0.97 ms)
+// merge-path split of every block boundary k = b * MRG_TILE of the binned integral, one thread
+// each, done up front so the ~25 dependent global loads of a search are paid once in parallel
 __global__ void __launch_bounds__(256)
 merge_partition_kernel(const float* __restrict__ U, int64_t nu, const float* __restrict__ V,
                        int64_t nv, int64_t blocks, int64_t* __restrict__ splits) {
@@ -71,49 +118,114 @@ merge_partition_kernel(const float* __restrict__ U, int64_t nu, const float* __r
   splits[b] = merge_path(U, nu, V, nv, b * MRG_TILE);
 }
 
-__global__ void __launch_bounds__(MRG_THREADS)
+// A block's two input runs (at most MRG_TILE + 1 values each) into shared memory with every
+// global load in flight before the first store: as a plain strided loop the 2 x 9 rounds each
+// waited a full L2 round trip, which was most of a block's life.
+__device__ __forceinline__ void stage_runs(const float* __restrict__ U, int lu,
+                                           const float* __restrict__ V, int lv, float* su,
+                                           float* sv) {
+  constexpr int R = MRG_ITEMS + 1;   // MRG_TILE + 1 values = MRG_ITEMS rounds of the block + 1
+  const int t = threadIdx.x;
+  float ru[R], rv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = t + r * MRG_THREADS;
+    ru[r] = i < lu ? __ldg(U + i) : 0.f;
+    rv[r] = i < lv ? __ldg(V + i) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = t + r * MRG_THREADS;
+    if (i < lu) su[i] = ru[r];
+    if (i < lv) sv[i] = rv[r];
+  }
+}
+
+// The integral of |F_u - F_v| over the merged sorted samples.  Persistent blocks: block b owns a
+// contiguous range of MRG_TILE-position tiles, finds the merge-path split of its first tile with
+// one warp-cooperative search and gets every later split for free (a tile ends where the next one
+// starts), so there is no partition pass; a thread keeps its partial sum in a register across all
+// its tiles.  Inside a tile every thread merges MRG_ITEMS consecutive positions from shared
+// memory; the runs are closed by sentinels (NaN after u, +inf after v: "u[i] <= v[j]" is then the
+// whole take-u test, ties and exhausted runs included), the value is widened to float64 once per
+// element, and the rank difference a nb - b na is carried as an exactly-updated float64 (DBL:
+// na nb < 2^53) instead of being rebuilt from two 64-bit products per element.
+constexpr int MRG_PAD = 16;
+
+template <bool DBL>
+__device__ __forceinline__ double merge_tile(const float* su, int lu, const float* sv, int lv,
+                                             int ka, int kb, long long rank_u0, long long rank_v0,
+                                             const CdfScale& cs, int* i_at_kb) {
+  int i = merge_path_smem(su, lu, sv, lv, ka);
+  int j = ka - i;
+  float a = su[i], b = sv[j];
+  bool tu = a <= b;                      // merged element ka
+  double cur = (double)(tu ? a : b);
+  i += tu ? 1 : 0, j += tu ? 0 : 1;
+  a = su[i], b = sv[j];
+  long long ru = rank_u0 + i, rv = rank_v0 + j;
+  double dd = DBL ? (double)(ru * cs.nb - rv * cs.na) : 0.0;
+  const double up = cs.dnb, down = -cs.dna;
+  double acc = 0.0;
+#pragma unroll
+  for (int q = 0; q < MRG_ITEMS; ++q) {
+    if (ka + q < kb) {
+      tu = a <= b;                       // merged element ka + q + 1 (exists: kb <= total - 1)
+      const double nxt = (double)(tu ? a : b);
+      const double gap = DBL ? fabs(dd) : cdf_gap(cs, ru, rv);
+      acc = fma(gap, nxt - cur, acc);
+      cur = nxt;
+      if (tu) { ++i; a = su[i]; } else { ++j; b = sv[j]; }
+      if (DBL) dd += tu ? up : down; else { ru += tu ? 1 : 0; rv += tu ? 0 : 1; }
+    }
+  }
+  *i_at_kb = i - (tu ? 1 : 0);           // u's among the first kb merged elements of the tile
+  return DBL ? acc * cs.inv : acc;
+}
+
+__global__ void __launch_bounds__(MRG_THREADS, 4)
 cdf_integral_kernel(const float* __restrict__ U, int64_t nu, const float* __restrict__ V,
                     int64_t nv, int64_t u_below, int64_t v_below, int64_t nu_total,
-                    int64_t nv_total, const int64_t* __restrict__ splits,
-                    double* __restrict__ block_partials) {
-  __shared__ float su[MRG_TILE + 1];
-  __shared__ float sv[MRG_TILE + 1];
+                    int64_t nv_total, int64_t tiles, double* __restrict__ block_partials) {
+  __shared__ float su[MRG_TILE + MRG_PAD];
+  __shared__ float sv[MRG_TILE + MRG_PAD];
   __shared__ double warp_part[MRG_THREADS / 32];
+  __shared__ long long split_s;
   const int64_t total = nu + nv;
-  const int64_t k0 = (int64_t)blockIdx.x * MRG_TILE;           // first merged index of the block
-  int64_t k1 = k0 + MRG_TILE;                                   // contributions k in [k0, k1)
-  if (k1 > total - 1) k1 = total - 1;
   const int t = threadIdx.x;
-  const int64_t i0 = splits[blockIdx.x], j0 = k0 - i0;
-  const int len = (int)(k1 - k0);
-  const int lu = (int)((nu - i0) < (int64_t)(len + 1) ? (nu - i0) : (int64_t)(len + 1));
-  const int lv = (int)((nv - j0) < (int64_t)(len + 1) ? (nv - j0) : (int64_t)(len + 1));
-  for (int i = t; i < lu; i += MRG_THREADS) su[i] = U[i0 + i];
-  for (int i = t; i < lv; i += MRG_THREADS) sv[i] = V[j0 + i];
+  const int64_t tile_begin = (tiles * blockIdx.x) / gridDim.x;
+  const int64_t tile_end = (tiles * (blockIdx.x + 1)) / gridDim.x;
+  if (t < 32) {
+    const int64_t s0 = merge_path_warp(U, nu, V, nv, tile_begin * MRG_TILE);
+    if (t == 0) split_s = s0;
+  }
   __syncthreads();
-
+  const CdfScale cs = cdf_scale(nu_total, nv_total);
+  const bool dbl = cs.dna * cs.dnb < 9007199254740992.0;   // 2^53: the rank difference is exact
   double acc = 0.0;
-  const int ka = t * MRG_ITEMS;
-  if (ka < len) {
-    const int kb = (ka + MRG_ITEMS) < len ? (ka + MRG_ITEMS) : len;
-    int i = merge_path_smem(su, lu, sv, lv, ka);
-    int j = ka - i;
-    // consume merged element ka
-    float cur;
-    if (j >= lv || (i < lu && su[i] <= sv[j])) cur = su[i++]; else cur = sv[j++];
-    for (int k = ka; k < kb; ++k) {
-      // next merged element (exists: k <= total - 2)
-      float nxt;
-      const bool take_u = (j >= lv) || (i < lu && su[i] <= sv[j]);
-      nxt = take_u ? su[i] : sv[j];
-      const double delta = (double)nxt - (double)cur;  // exact: scipy widens to float64 first
-      // numpy: idx / size in float64
-      const double cu = (double)(u_below + i0 + i) / (double)nu_total;
-      const double cv = (double)(v_below + j0 + j) / (double)nv_total;
-      acc += fabs(cu - cv) * delta;
-      if (take_u) ++i; else ++j;
-      cur = nxt;
+  for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+    const int64_t i0 = split_s;
+    const int64_t k0 = tile * MRG_TILE, j0 = k0 - i0;
+    int64_t k1 = k0 + MRG_TILE;                     // contributions k in [k0, k1)
+    if (k1 > total - 1) k1 = total - 1;
+    const int len = (int)(k1 - k0);
+    const int lu = (int)((nu - i0) < (int64_t)(len + 1) ? (nu - i0) : (int64_t)(len + 1));
+    const int lv = (int)((nv - j0) < (int64_t)(len + 1) ? (nv - j0) : (int64_t)(len + 1));
+    stage_runs(U + i0, lu, V + j0, lv, su, sv);
+    if (t < MRG_PAD) {
+      if (lu + t < MRG_TILE + MRG_PAD) su[lu + t] = __int_as_float(0x7fc00000);   // NaN
+      if (lv + t < MRG_TILE + MRG_PAD) sv[lv + t] = __int_as_float(0x7f800000);   // +inf
     }
+    __syncthreads();
+    const int ka = t * MRG_ITEMS;
+    if (ka < len) {
+      const int kb = (ka + MRG_ITEMS) < len ? (ka + MRG_ITEMS) : len;
+      int i_at_kb;
+      acc += dbl ? merge_tile<true>(su, lu, sv, lv, ka, kb, u_below + i0, v_below + j0, cs, &i_at_kb)
+                 : merge_tile<false>(su, lu, sv, lv, ka, kb, u_below + i0, v_below + j0, cs, &i_at_kb);
+      if (kb == len) split_s = i0 + i_at_kb;        // exactly one thread: the next tile's split
+    }
+    __syncthreads();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -124,6 +236,12 @@ cdf_integral_kernel(const float* __restrict__ U, int64_t nu, const float* __rest
     for (int w = 0; w < MRG_THREADS / 32; ++w) s += warp_part[w];
     block_partials[blockIdx.x] = s;
   }
+}
+
+// persistent grid of cdf_integral_kernel for `tiles` tiles (four resident blocks per SM)
+inline unsigned integral_grid(int64_t tiles) {
+  const int64_t cap = 148 * 4;
+  return (unsigned)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -529,11 +647,10 @@ cdf_integral_binned_kernel(const float* __restrict__ U, int64_t nu, const float*
   const int len = (int)(k1 - k0);
   const int lu = (int)((nu - i0) < (int64_t)(len + 1) ? (nu - i0) : (int64_t)(len + 1));
   const int lv = (int)((nv - j0) < (int64_t)(len + 1) ? (nv - j0) : (int64_t)(len + 1));
-  for (int i = t; i < lu; i += MRG_THREADS) su[i] = U[i0 + i];
-  for (int i = t; i < lv; i += MRG_THREADS) sv[i] = V[j0 + i];
+  stage_runs(U + i0, lu, V + j0, lv, su, sv);
   __syncthreads();
 
-  const double dnu = (double)nu_total, dnv = (double)nv_total;
+  const CdfScale cs = cdf_scale(nu_total, nv_total);
   double acc = 0.0;
   const int ka = t * MRG_ITEMS;
   if (ka < len) {
@@ -554,8 +671,7 @@ cdf_integral_binned_kernel(const float* __restrict__ U, int64_t nu, const float*
       const int b = (int)(wb_key(cur) >> WB_LOW_BITS);
       const long long ou = __ldg(skip_u + b) + i0, ov = __ldg(skip_v + b) + j0;
       if (b != pb) {
-        const double d = (double)(ou + i) / dnu - (double)(ov + j) / dnv;
-        acc += fabs(d) * ((double)cur - __ldg(edges + b));
+        acc += cdf_gap(cs, ou + i, ov + j) * ((double)cur - __ldg(edges + b));
       }
       if (take_u) ++i; else ++j;
       double seg;
@@ -566,8 +682,7 @@ cdf_integral_binned_kernel(const float* __restrict__ U, int64_t nu, const float*
         same = (int)(wb_key(nxt) >> WB_LOW_BITS) == b;
       }
       seg = same ? (double)nxt - (double)cur : __ldg(edges + b + 1) - (double)cur;
-      const double d = (double)(ou + i) / dnu - (double)(ov + j) / dnv;
-      acc += fabs(d) * seg;
+      acc += cdf_gap(cs, ou + i, ov + j) * seg;
       pb = b;
     }
   }
@@ -649,14 +764,11 @@ int sort_and_integrate(float* du, float* dut, int64_t nu, float* dv, float* dvt,
   rc = radix_sort_f32(dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
   if (rc != UQ_OK) return rc;
   if (nu + nv - 1 > 0) {
-    int64_t* splits = reinterpret_cast<int64_t*>(b + L.splits);
-    merge_partition_kernel<<<(unsigned)((L.blocks + 255) / 256), 256, 0, st>>>(su, nu, sv, nv,
-                                                                               L.blocks, splits);
+    const unsigned grid = integral_grid(L.blocks);
+    cdf_integral_kernel<<<grid, MRG_THREADS, 0, st>>>(su, nu, sv, nv, 0, 0, nu, nv, L.blocks,
+                                                      parts);
     UQ_LAUNCH_CHECK();
-    cdf_integral_kernel<<<(unsigned)L.blocks, MRG_THREADS, 0, st>>>(su, nu, sv, nv, 0, 0, nu, nv,
-                                                                    splits, parts);
-    UQ_LAUNCH_CHECK();
-    sum_partials_kernel<<<1, 1024, 0, st>>>(parts, L.blocks, result);
+    sum_partials_kernel<<<1, 1024, 0, st>>>(parts, grid, result);
     UQ_LAUNCH_CHECK();
   } else {
     UQ_CUDA(cudaMemsetAsync(result, 0, sizeof(double), st));
@@ -948,14 +1060,11 @@ int wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv,
   }
   if (nu + nv - 1 > 0) {
     const int64_t blocks = (nu + nv - 1 + MRG_TILE - 1) / MRG_TILE;
-    int64_t* splits = reinterpret_cast<int64_t*>(b + L.splits);
-    merge_partition_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, st>>>(su, nu, sv, nv, blocks,
-                                                                             splits);
+    const unsigned grid = integral_grid(blocks);
+    cdf_integral_kernel<<<grid, MRG_THREADS, 0, st>>>(su, nu, sv, nv, u_below, v_below, nu_total,
+                                                      nv_total, blocks, parts);
     UQ_LAUNCH_CHECK();
-    cdf_integral_kernel<<<(unsigned)blocks, MRG_THREADS, 0, st>>>(su, nu, sv, nv, u_below, v_below,
-                                                                  nu_total, nv_total, splits, parts);
-    UQ_LAUNCH_CHECK();
-    sum_partials_kernel<<<1, 1024, 0, st>>>(parts, blocks, result);
+    sum_partials_kernel<<<1, 1024, 0, st>>>(parts, grid, result);
     UQ_LAUNCH_CHECK();
   } else {
     UQ_CUDA(cudaMemsetAsync(result, 0, sizeof(double), st));

@@ -358,6 +358,23 @@ def wasserstein_1d_info(u: torch.Tensor, v: torch.Tensor, method: str = "auto") 
             "sorted_u": int(info[1]), "sorted_v": int(info[2])}
 
 
+def sort_f32(x: torch.Tensor) -> torch.Tensor:
+    """``x`` sorted ascending (a new float32 tensor): the radix sort behind the SORT Wasserstein
+    method, the score metrics and the WINDOW KDE, on its own.  Ordering = the float32 bit patterns'
+    (what ``np.sort`` gives, with ``-0.0`` before ``+0.0`` and NaNs last)."""
+    lib = _lib.load()
+    x = _flat_f32(x, "x")
+    out = torch.empty_like(x)
+    if x.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        wsb = int(lib.uq_sort_workspace_bytes(x.numel()))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.uq_sort_f32(x.data_ptr(), x.numel(), out.data_ptr(), ws.data_ptr(), wsb,
+                                   _stream_ptr(x.device)))
+    return out
+
+
 _KMETHOD = {"auto": _lib.KDE_AUTO, "window": _lib.KDE_WINDOW, "moments": _lib.KDE_MOMENTS}
 
 

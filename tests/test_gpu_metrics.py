@@ -532,6 +532,24 @@ def test_kde_density_matches_reference_class_golden(tag):
     assert got[-1] == 0.0          # far query: every term underflows, as in the reference
 
 
+@pytest.mark.parametrize("tag", ["far5", "far2"])
+def test_kde_density_far_queries_keep_their_order(tag):
+    """Far-OOD queries (reference densities 1e-38 ... 1e-318, where a float32 kernel sum has
+    flushed to zero) are re-done in float64 log space: equal to the float64 oracle at the same
+    tolerance as near queries, to the reference's own KDEMLPModel within ITS far-field error
+    (tree pruning, 6e-5 measured), and ranked like the reference ranks them."""
+    g = load_golden("kde_density_far.npz")
+    fit, x, h = g[f"{tag}.fit"], g[f"{tag}.x"], float(g[f"{tag}.bandwidth"])
+    got = ops.kde_density(_dev(fit), _dev(x), h).cpu().numpy()
+    ref = metrics_oracle.kde_neg_density(fit, x, h)
+    gold = g[f"{tag}.dens"]
+    np.testing.assert_allclose(got, ref, rtol=KDE_RTOL, atol=1e-300)
+    np.testing.assert_allclose(got, gold, rtol=2e-4, atol=1e-300)
+    assert np.array_equal(got == 0, gold == 0)
+    big = np.abs(gold) > 1e-290                  # away from float64 denormals: strict order kept
+    assert np.array_equal(np.argsort(got[big], kind="stable"), np.argsort(gold[big], kind="stable"))
+
+
 def test_kde_density_fit_splits_ragged_sizes_and_errors():
     """Few query rows x many fitted rows (the fitted rows are split over blocks), ragged tiles."""
     rng = np.random.default_rng(4)
@@ -611,3 +629,51 @@ def test_wasserstein_methods_on_random_bit_patterns():
         for method in ("sort", "binned", "auto"):
             got = ops.wasserstein_1d(_dev(u), _dev(v), method)
             assert got == pytest.approx(ref, rel=1e-11), (trial, method)
+
+
+# ---- the radix sort on its own ----------------------------------------------------------------------
+
+def _sort_ref(x):
+    """np.sort on the order-preserving integer keys (bit-pattern order: -0.0 < +0.0, NaNs last)."""
+    b = x.view(np.uint32)
+    k = np.where(b >> 31, ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+    k.sort()
+    return np.where(k >> 31, k & np.uint32(0x7FFFFFFF), ~k).astype(np.uint32)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 4095, 4096, 4097, 8191, 8193, 70001, 1 << 20,
+                               2_424_833, 2_424_832 + 8192 * 3 + 17])
+def test_radix_sort_bit_exact(n):
+    rng = np.random.default_rng(n)
+    kinds = [rng.standard_normal(n).astype(np.float32),
+             rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32),
+             np.round(rng.gamma(2.0, 0.05, n), 2).astype(np.float32),        # heavy ties
+             np.full(n, 1.5, np.float32)]                                     # one digit everywhere
+    kinds[1][np.isnan(kinds[1])] = np.float32(np.inf)   # NaN payloads: compare everything else
+    for x in kinds:
+        if n > 3:
+            x[:3] = np.array([0.0, -0.0, -np.inf], np.float32)
+        got = ops.sort_f32(_dev(x)).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), _sort_ref(x))
+
+
+def test_radix_sort_both_tile_sizes():
+    """8192-key tiles (32 keys per lane) and 4096-key tiles give the same bits; UQ_SORT_ITEMS is
+    read once per process, so the forced sizes run in subprocesses."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, torch, zlib; from nnueehcs_b200 import ops;"
+            "x = torch.from_numpy(np.random.default_rng(5).standard_normal(3_000_017)"
+            ".astype(np.float32)).cuda();"
+            "print(zlib.crc32(ops.sort_f32(x).cpu().numpy().tobytes()))")
+    import os
+    outs = []
+    for items in ("16", "32"):
+        env = dict(os.environ, UQ_SORT_ITEMS=items)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip().splitlines()[-1])
+    x = np.random.default_rng(5).standard_normal(3_000_017).astype(np.float32)
+    import zlib
+    assert outs[0] == outs[1] == str(zlib.crc32(_sort_ref(x).tobytes()))

@@ -87,6 +87,22 @@ def main():
                                               "window" if "[window]" in name else "auto")["method"]
             line["gaussian_terms_equivalent_per_s"] = total * args.grid / (mean_ms * 1e-3)
         print(json.dumps(line), flush=True)
+    # the radix sort on its own: 36 B of HBM traffic per key is what a 4-pass LSD sort with a
+    # separate histogram read moves (4 x (4 read + 4 write) + 4 x 4 upsweep read = 48 here)
+    lib = ops._lib.load()
+    out = torch.empty_like(u)
+    wsb = int(lib.uq_sort_workspace_bytes(u.numel()))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def sort_only():
+        ops._lib.check(lib.uq_sort_f32(u.data_ptr(), u.numel(), out.data_ptr(), ws.data_ptr(), wsb, st))
+    mean_ms, best_ms = time_gpu(sort_only, args.steps)
+    ok = bool((out[1:] >= out[:-1]).all().item())
+    print(json.dumps({"metric": "radix_sort_f32", "keys": u.numel(), "ms": mean_ms, "best_ms": best_ms,
+                      "keys_per_s": u.numel() / (mean_ms * 1e-3), "sorted": ok,
+                      "includes": "one device-to-device copy of the input (the sort is in place)",
+                      "items_per_lane": os.environ.get("UQ_SORT_ITEMS", "auto")}), flush=True)
     # KDEMLPModel's input-density score: 1 M queries x 100 k fitted rows, d = 5
     g = torch.Generator(device=dev).manual_seed(7)
     fit = torch.rand(100_000, 5, device=dev, generator=g)
