@@ -291,12 +291,30 @@ def metric_kernel_lines(dev, peaks, n=50_000_000, steps=5):
     u, v = gamma(2, 0.05, 0), gamma(3, 0.08, 1)
     hbm = peaks.get("hbm")
     out = {}
-    for name, fn, info in (
-            ("wasserstein_1d", lambda: ops.wasserstein_1d(u, v), lambda: ops.wasserstein_1d_info(u, v)),
-            ("kde_jsd", lambda: ops.kde_jsd(u, v, 20000), lambda: ops.kde_jsd_info(u, v, 20000))):
+    for name, fn, info, enqueue in (
+            ("wasserstein_1d", lambda: ops.wasserstein_1d(u, v), lambda: ops.wasserstein_1d_info(u, v),
+             lambda: ops.wasserstein_1d_async(u, v)),
+            ("kde_jsd", lambda: ops.kde_jsd(u, v, 20000), lambda: ops.kde_jsd_info(u, v, 20000),
+             lambda: ops.kde_jsd_async(u, v, 20000))):
         for _ in range(3):
             val = fn()
         torch.cuda.synchronize()
+        # device time per call with the host out of the loop: `steps` calls enqueued back to back
+        # through the enqueue / finish API (uq_*_enqueue: memset + one launch each, no
+        # synchronisation), one synchronisation at the end.  This is the kernel's launch duration
+        # the roofline fraction refers to; "ms" below is what a caller of the synchronous op sees
+        # (launch latency, the stream synchronisation and the Python / ctypes hop included).
+        pend = [enqueue() for _ in range(2)]
+        vals = [p.result() for p in pend]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pend = [enqueue() for _ in range(steps)]
+        e1.record()
+        torch.cuda.synchronize()
+        ms_dev = e0.elapsed_time(e1) / steps
+        vals = [p.result() for p in pend]
+        assert all(x == val for x in vals), (name, vals, val)
+        del pend
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ops.reset_launch_count()
         e0.record()
@@ -307,9 +325,16 @@ def metric_kernel_lines(dev, peaks, n=50_000_000, steps=5):
         launches = ops.launch_count() // steps
         ms = e0.elapsed_time(e1) / steps
         gbs = 2 * n * 4 / (ms * 1e-3) / 1e9
+        gbs_dev = 2 * n * 4 / (ms_dev * 1e-3) / 1e9
         out[name] = {"values": 2 * n, "ms": ms, "values_per_s": 2 * n / (ms * 1e-3),
                      "algorithmic_GBps": gbs, "hbm_peak_GBps": hbm,
-                     "frac_of_hbm_peak": gbs / hbm if hbm else None, "result": val,
+                     "frac_of_hbm_peak": gbs / hbm if hbm else None,
+                     "ms_device": ms_dev, "algorithmic_GBps_device": gbs_dev,
+                     "frac_of_hbm_peak_device": gbs_dev / hbm if hbm else None,
+                     "device_timing": "calls enqueued back to back (uq_*_enqueue), one "
+                                      "synchronisation at the end; results equal the synchronous "
+                                      "calls' bit for bit",
+                     "result": val,
                      "method": info()["method"], "gpu_launches_per_call": int(launches),
                      "data": "synthetic Gamma(2, 0.05) vs Gamma(3, 0.08) scores, float32, in HBM"}
     del u, v

@@ -196,6 +196,29 @@ int uq_wasserstein_1d_ex(const float* u, int64_t nu, const float* v, int64_t nv,
                          double* out_host, int64_t* info_host, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/*    Enqueue / finish forms of the two distribution metrics: the same results without a stream
+      synchronisation inside the call, so that a caller that needs several metrics of the same
+      score vectors (the reference's evaluate() loop over its metric list,
+      nnueehcs/evaluation.py:122-144) pays ONE synchronisation for all of them.
+      enqueue: the single-launch method's memset + kernel on `stream`; `record` is caller-owned
+      MAPPED PINNED host memory of UQ_METRIC_RECORD_BYTES (cudaHostAlloc / torch pin_memory) that
+      the kernel's last block fills in.  The inputs must stay untouched until finish; the
+      workspace may be handed to further enqueue calls on the SAME stream (each call zeroes what
+      it needs, in stream order).  finish (after the caller has synchronised `stream`): reads the
+      record; where the single-launch method does not apply (ambiguous bins, inf / NaN, a range
+      beyond ~4000 bandwidths) it runs the synchronous call from scratch. */
+#define UQ_METRIC_RECORD_BYTES 256
+int uq_wasserstein_1d_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, void* record,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int uq_wasserstein_1d_finish(const float* u, int64_t nu, const float* v, int64_t nv,
+                             const void* record, double* out_host, int64_t* info_host,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int uq_kde_jsd_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
+                       void* record, void* workspace, size_t workspace_bytes, void* stream);
+int uq_kde_jsd_finish(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
+                      const void* record, double* out_host, int32_t* method_used, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /*    uq_kde_jsd replaces JensenShannonEvaluation.pdf_jsd (nnueehcs/evaluation.py:268-276):
       Scott-bandwidth Gaussian KDE of each sample on a shared `grid_pts`-point linspace between
       the joint min and max, then the Jensen-Shannon distance of the two pdf vectors. */

@@ -18,6 +18,7 @@ OUT_MEAN_STD, OUT_MOMENTS = 0, 1
 MODEL_ANCHOR_FIRST = 1
 WASSERSTEIN_AUTO, WASSERSTEIN_SORT, WASSERSTEIN_BINNED = 0, 1, 2
 KDE_AUTO, KDE_WINDOW, KDE_MOMENTS = 0, 1, 2
+METRIC_RECORD_BYTES = 256
 
 # every symbol include/nnueehcs_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
@@ -35,6 +36,8 @@ EXPORTS = (
     "uq_score_metrics_workspace_bytes", "uq_score_metrics",
     "uq_kde_scott_bandwidth", "uq_kde_density_workspace_bytes", "uq_kde_density",
     "uq_sort_workspace_bytes", "uq_sort_f32",
+    "uq_wasserstein_1d_enqueue", "uq_wasserstein_1d_finish", "uq_kde_jsd_enqueue",
+    "uq_kde_jsd_finish",
     "uq_bin_moments", "uq_wasserstein_from_bins", "uq_compact_flagged", "uq_wasserstein_ambiguous",
 )
 
@@ -157,6 +160,15 @@ def load() -> C.CDLL:
                                              sz, vp]
     for name in ("uq_bin_moments", "uq_wasserstein_from_bins", "uq_compact_flagged",
                  "uq_wasserstein_ambiguous"):
+        getattr(lib, name).restype = C.c_int
+    lib.uq_wasserstein_1d_enqueue.argtypes = [vp, i64, vp, i64, vp, vp, sz, vp]
+    lib.uq_wasserstein_1d_finish.argtypes = [vp, i64, vp, i64, vp, C.POINTER(dbl), C.POINTER(i64),
+                                             vp, sz, vp]
+    lib.uq_kde_jsd_enqueue.argtypes = [vp, i64, vp, i64, i32, vp, vp, sz, vp]
+    lib.uq_kde_jsd_finish.argtypes = [vp, i64, vp, i64, i32, vp, C.POINTER(dbl), C.POINTER(i32),
+                                      vp, sz, vp]
+    for name in ("uq_wasserstein_1d_enqueue", "uq_wasserstein_1d_finish", "uq_kde_jsd_enqueue",
+                 "uq_kde_jsd_finish"):
         getattr(lib, name).restype = C.c_int
     lib.uq_sort_workspace_bytes.argtypes = [i64]
     lib.uq_sort_workspace_bytes.restype = sz

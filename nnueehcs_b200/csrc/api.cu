@@ -404,6 +404,42 @@ int uq_wasserstein_1d_ex(const float* u, int64_t nu, const float* v, int64_t nv,
                         static_cast<cudaStream_t>(stream));
 }
 
+int uq_wasserstein_1d_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, void* record,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(u && v && nu >= 1 && nv >= 1, UQ_ERR_INVALID,
+             "uq_wasserstein_1d_enqueue: Distribution can't be empty.");
+  return wasserstein_1d_enqueue(u, nu, v, nv, record, workspace, workspace_bytes,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int uq_wasserstein_1d_finish(const float* u, int64_t nu, const float* v, int64_t nv,
+                             const void* record, double* out_host, int64_t* info_host,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(u && v && record && out_host && nu >= 1 && nv >= 1, UQ_ERR_INVALID,
+             "uq_wasserstein_1d_finish: NULL argument or empty distribution");
+  return wasserstein_1d_finish(u, nu, v, nv, record, out_host, info_host, workspace,
+                               workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int uq_kde_jsd_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
+                       void* record, void* workspace, size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(u && v && nu >= 2 && nv >= 2, UQ_ERR_INVALID,
+             "uq_kde_jsd_enqueue: each sample needs at least 2 values (got %lld, %lld)",
+             (long long)nu, (long long)nv);
+  UQ_REQUIRE(grid_pts >= 2, UQ_ERR_INVALID, "uq_kde_jsd_enqueue: grid_pts must be >= 2");
+  return kde_jsd_enqueue(u, nu, v, nv, grid_pts, record, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int uq_kde_jsd_finish(const float* u, int64_t nu, const float* v, int64_t nv, int32_t grid_pts,
+                      const void* record, double* out_host, int32_t* method_used, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  UQ_REQUIRE(u && v && record && out_host && nu >= 2 && nv >= 2 && grid_pts >= 2, UQ_ERR_INVALID,
+             "uq_kde_jsd_finish: NULL argument, fewer than 2 values or fewer than 2 grid points");
+  return kde_jsd_finish(u, nu, v, nv, grid_pts, record, out_host, method_used, workspace,
+                        workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 size_t uq_kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int32_t grid_pts) {
   return kde_jsd_workspace_bytes(nu, nv, grid_pts);
 }

@@ -264,6 +264,19 @@ int kde_jsd_fused(const float* u, int64_t nu, const float* v, int64_t nv, int gr
                   double* out_host, int* status_host, double* info_host, void* ws, size_t ws_bytes,
                   cudaStream_t st);
 int kde_jsd_fused_phase_us(double* out5);
+int kde_jsd_fused_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                          void* record, void* ws, size_t ws_bytes, cudaStream_t st);
+int kde_jsd_fused_read(const void* record, double* out_host);
+int kde_jsd_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                    void* record, void* ws, size_t ws_bytes, cudaStream_t st);
+int kde_jsd_finish(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                   const void* record, double* out_host, int* method_used_host, void* ws,
+                   size_t ws_bytes, cudaStream_t st);
+int wasserstein_1d_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, void* record,
+                           void* ws, size_t ws_bytes, cudaStream_t st);
+int wasserstein_1d_finish(const float* u, int64_t nu, const float* v, int64_t nv,
+                          const void* record, double* out_host, int64_t* info_host, void* ws,
+                          size_t ws_bytes, cudaStream_t st);
 size_t kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int grid_pts);
 int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts, int method,
             double* out_host, int* method_used_host, void* ws, size_t ws_bytes, cudaStream_t st);

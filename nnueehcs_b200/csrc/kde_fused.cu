@@ -552,12 +552,11 @@ size_t kde_jsd_fused_workspace_bytes(int64_t nu, int64_t nv, int grid_pts) {
   return kf_layout(nu, nv, grid_pts, grid).total;
 }
 
-// One memset + one cooperative launch + one stream synchronisation.  *status_host = 1: *out_host
-// holds the distance; 2: the kernel declined (range / bandwidth / non-finite data) and nothing
-// was computed.  info_host (may be NULL): {h_u, h_v, lo, hi, fine bins u, fine bins v}.
-int kde_jsd_fused(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
-                  double* out_host, int* status_host, double* info_host, void* ws, size_t ws_bytes,
-                  cudaStream_t st) {
+// memset + cooperative launch; the last block writes the KfRecord to `record_dev`.  No
+// synchronisation.
+namespace {
+int kde_jsd_fused_launch(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                         KfRecord* record_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
   int grid = 0;
   if (int rc = kf_grid(&grid)) return rc;
   const KfLayout L = kf_layout(nu, nv, grid_pts, grid);
@@ -565,8 +564,6 @@ int kde_jsd_fused(const float* u, int64_t nu, const float* v, int64_t nv, int gr
              "kde_jsd_fused needs %zu workspace bytes, got %zu", L.total, ws_bytes);
   UQ_REQUIRE(nu >= 2 && nv >= 2 && grid_pts >= 2, UQ_ERR_INVALID,
              "kde_jsd_fused: each sample needs at least 2 values and the grid 2 points");
-  void *slot_h = nullptr, *slot_d = nullptr;
-  if (int rc = result_slot(&slot_h, &slot_d)) return rc;
   char* b = static_cast<char*>(ws);
   KfWs w;
   w.partials = reinterpret_cast<double*>(b + L.partials);
@@ -576,13 +573,28 @@ int kde_jsd_fused(const float* u, int64_t nu, const float* v, int64_t nv, int gr
   w.blocksums = reinterpret_cast<double*>(b + L.blocksums);
   w.terms = reinterpret_cast<double*>(b + L.terms);
   w.ctl = reinterpret_cast<KfCtl*>(b + L.ctl);
-  w.record = static_cast<KfRecord*>(slot_d);
-  static_cast<KfRecord*>(slot_h)->status = 0;
+  w.record = record_dev;
   UQ_CUDA(cudaMemsetAsync(b + L.zeroed, 0, L.zeroed_end - L.zeroed, st));
   void* args[] = {(void*)&u, (void*)&nu, (void*)&v, (void*)&nv, (void*)&grid_pts, (void*)&w};
   UQ_CUDA(cudaLaunchCooperativeKernel((const void*)kde_jsd_fused_kernel, dim3(grid),
                                       dim3(KF_THREADS), args, KF_SMEM, st));
   UQ_LAUNCH_CHECK();
+  return UQ_OK;
+}
+}  // namespace
+
+// One memset + one cooperative launch + one stream synchronisation.  *status_host = 1: *out_host
+// holds the distance; 2: the kernel declined (range / bandwidth / non-finite data) and nothing
+// was computed.  info_host (may be NULL): {h_u, h_v, lo, hi, fine bins u, fine bins v}.
+int kde_jsd_fused(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                  double* out_host, int* status_host, double* info_host, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  void *slot_h = nullptr, *slot_d = nullptr;
+  if (int rc = result_slot(&slot_h, &slot_d)) return rc;
+  static_cast<KfRecord*>(slot_h)->status = 0;
+  if (int rc = kde_jsd_fused_launch(u, nu, v, nv, grid_pts, static_cast<KfRecord*>(slot_d), ws,
+                                    ws_bytes, st))
+    return rc;
   UQ_CUDA(cudaStreamSynchronize(st));
   KfRecord rec;
   memcpy(&rec, slot_h, sizeof(rec));
@@ -595,6 +607,26 @@ int kde_jsd_fused(const float* u, int64_t nu, const float* v, int64_t nv, int gr
     info_host[4] = (double)rec.nbf[0], info_host[5] = (double)rec.nbf[1];
   }
   return UQ_OK;
+}
+
+// enqueue-only form (see wasserstein_1d_enqueue): `record` = caller-owned mapped pinned host
+// memory; kde_jsd_fused_read returns 1 (distance in *out_host), 2 (declined) or 0 (no record yet)
+int kde_jsd_fused_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                          void* record, void* ws, size_t ws_bytes, cudaStream_t st) {
+  void* record_dev = nullptr;
+  UQ_REQUIRE(record && cudaHostGetDevicePointer(&record_dev, record, 0) == cudaSuccess,
+             UQ_ERR_INVALID, "kde_jsd enqueue: the record must be mapped pinned host memory");
+  static_assert(sizeof(KfRecord) <= UQ_METRIC_RECORD_BYTES, "record size");
+  static_cast<KfRecord*>(record)->status = 0;
+  return kde_jsd_fused_launch(u, nu, v, nv, grid_pts, static_cast<KfRecord*>(record_dev), ws,
+                              ws_bytes, st);
+}
+
+int kde_jsd_fused_read(const void* record, double* out_host) {
+  KfRecord rec;
+  memcpy(&rec, record, sizeof(rec));
+  *out_host = rec.jsd;
+  return rec.status;
 }
 
 // diagnostics: microseconds block 0 spent in phases 1..5 of this thread's last kde_jsd_fused call

@@ -453,6 +453,36 @@ size_t kde_jsd_workspace_bytes(int64_t nu, int64_t nv, int grid_pts) {
   return layout(nu, nv, grid_pts).total;
 }
 
+// enqueue / finish (see wasserstein_1d_enqueue): the single-launch moment method without a
+// synchronisation inside the call; finish falls back to the synchronous call when the kernel
+// declined (range / bandwidth / non-finite data) or the device cannot run it.
+int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts, int method,
+            double* out_host, int* method_used_host, void* ws, size_t ws_bytes, cudaStream_t st);
+
+int kde_jsd_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                    void* record, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const WsLayout L = layout(nu, nv, grid_pts);
+  UQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, UQ_ERR_WORKSPACE,
+             "kde_jsd needs %zu workspace bytes, got %zu", L.total, ws_bytes);
+  UQ_REQUIRE(record != nullptr, UQ_ERR_INVALID, "kde_jsd enqueue: record is NULL");
+  if (L.fused_bytes == 0) {          // finish will run the synchronous call
+    memset(record, 0, UQ_METRIC_RECORD_BYTES);
+    return UQ_OK;
+  }
+  return kde_jsd_fused_enqueue(u, nu, v, nv, grid_pts, record, static_cast<char*>(ws) + L.fused,
+                               L.fused_bytes, st);
+}
+
+int kde_jsd_finish(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
+                   const void* record, double* out_host, int* method_used_host, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  if (kde_jsd_fused_read(record, out_host) == 1) {
+    if (method_used_host) *method_used_host = UQ_KDE_MOMENTS;
+    return UQ_OK;
+  }
+  return kde_jsd(u, nu, v, nv, grid_pts, UQ_KDE_AUTO, out_host, method_used_host, ws, ws_bytes, st);
+}
+
 // method: UQ_KDE_AUTO / UQ_KDE_WINDOW (sorted samples, 9-sigma windows) / UQ_KDE_MOMENTS.
 // method_used_host (may be NULL) receives the method that ran.
 int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts, int method,
@@ -493,12 +523,10 @@ int kde_jsd(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts
   KdeParams* params = reinterpret_cast<KdeParams*>(b + L.params);
   double* pdf = reinterpret_cast<double*>(b + L.pdf);
   double* result = reinterpret_cast<double*>(b + L.result);
-  UQ_CUDA(cudaMemcpyAsync(du, u, sizeof(float) * (size_t)nu, cudaMemcpyDeviceToDevice, st));
-  UQ_CUDA(cudaMemcpyAsync(dv, v, sizeof(float) * (size_t)nv, cudaMemcpyDeviceToDevice, st));
   float *su = nullptr, *sv = nullptr;
-  int rc = radix_sort_f32(du, dut, nu, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
+  int rc = radix_sort_f32_copy(u, du, dut, nu, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
   if (rc != UQ_OK) return rc;
-  rc = radix_sort_f32(dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
+  rc = radix_sort_f32_copy(v, dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
   if (rc != UQ_OK) return rc;
   stats_kernel<<<STAT_BLOCKS, 256, 0, st>>>(su, nu, partials);
   UQ_LAUNCH_CHECK();
@@ -549,9 +577,8 @@ int kde_grid_accumulate(const float* x, int64_t n, double lo, double hi, double 
     double* tables = reinterpret_cast<double*>(reinterpret_cast<char*>(params) + al(sizeof(KdeParams)));
     return km_accumulate(x, n, lo, hi, bandwidth, nb, grid_pts, grid, tables, st);
   }
-  UQ_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
   float* sx = nullptr;
-  int rc = radix_sort_f32(dx, dt, n, scratch, radix_sort_scratch_bytes(n), &sx, st);
+  int rc = radix_sort_f32_copy(x, dx, dt, n, scratch, radix_sort_scratch_bytes(n), &sx, st);
   if (rc != UQ_OK) return rc;
   KdeParams hp;
   hp.lo = lo;

@@ -221,12 +221,12 @@ int uq_score_metrics(const float* id_scores, int64_t n_id, const float* ood_scor
   double* partials = reinterpret_cast<double*>(w + L.partials);
   unsigned long long* acc = reinterpret_cast<unsigned long long*>(w + L.acc);
   uq_score_result* result = reinterpret_cast<uq_score_result*>(w + L.result);
-  UQ_CUDA(cudaMemcpyAsync(da, id_scores, sizeof(float) * (size_t)n_id, cudaMemcpyDeviceToDevice, st));
-  UQ_CUDA(cudaMemcpyAsync(db, ood_scores, sizeof(float) * (size_t)n_ood, cudaMemcpyDeviceToDevice, st));
   float *sa = nullptr, *sb = nullptr;
-  int rc = radix_sort_f32(da, dat, n_id, w + L.scratch, radix_sort_scratch_bytes(n_id), &sa, st);
+  int rc = radix_sort_f32_copy(id_scores, da, dat, n_id, w + L.scratch,
+                               radix_sort_scratch_bytes(n_id), &sa, st);
   if (rc != UQ_OK) return rc;
-  rc = radix_sort_f32(db, dbt, n_ood, w + L.scratch, radix_sort_scratch_bytes(n_ood), &sb, st);
+  rc = radix_sort_f32_copy(ood_scores, db, dbt, n_ood, w + L.scratch,
+                           radix_sort_scratch_bytes(n_ood), &sb, st);
   if (rc != UQ_OK) return rc;
   sum_kernel<<<SUM_BLOCKS, 256, 0, st>>>(sa, n_id, partials);
   UQ_LAUNCH_CHECK();

@@ -345,9 +345,10 @@ SortPlan sort_plan(int64_t n) {
   return p;
 }
 
+// pass 0: src -> b, then b -> a, a -> b, b -> a: the result is in `a`; src may be `a` itself
 template <int ITEMS>
-int sort_passes(uint32_t* a, uint32_t* b, int64_t n, const SortPlan& p, uint32_t* spine,
-                uint32_t* digit_totals, cudaStream_t st) {
+int sort_passes(const uint32_t* src, uint32_t* a, uint32_t* b, int64_t n, const SortPlan& p,
+                uint32_t* spine, uint32_t* digit_totals, cudaStream_t st) {
   static PerDeviceOnce opted[3];
   constexpr int SMEM = Down<ITEMS>::SMEM;
   if (int rc = smem_opt_in(downsweep_kernel<ITEMS, true, false>, SMEM, opted[0])) return rc;
@@ -355,31 +356,32 @@ int sort_passes(uint32_t* a, uint32_t* b, int64_t n, const SortPlan& p, uint32_t
   if (int rc = smem_opt_in(downsweep_kernel<ITEMS, false, true>, SMEM, opted[2])) return rc;
   const int64_t per_block = p.tiles_per_block * p.tile();
   UQ_CUDA(cudaMemsetAsync(digit_totals, 0, 4 * RADIX * sizeof(uint32_t), st));
+  const uint32_t* in = src;
+  uint32_t* out = b;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = pass * 8;
     uint32_t* totals = digit_totals + pass * RADIX;
     if (pass == 0)
-      upsweep_kernel<true><<<p.num_blocks, SORT_THREADS, 0, st>>>(a, n, shift, per_block, spine,
+      upsweep_kernel<true><<<p.num_blocks, SORT_THREADS, 0, st>>>(in, n, shift, per_block, spine,
                                                                 p.num_blocks, totals);
     else
-      upsweep_kernel<false><<<p.num_blocks, SORT_THREADS, 0, st>>>(a, n, shift, per_block, spine,
+      upsweep_kernel<false><<<p.num_blocks, SORT_THREADS, 0, st>>>(in, n, shift, per_block, spine,
                                                                  p.num_blocks, totals);
     UQ_LAUNCH_CHECK();
     spine_scan_kernel<<<RADIX, SPINE_THREADS, 0, st>>>(spine, p.num_blocks, totals);
     UQ_LAUNCH_CHECK();
     if (pass == 0)
       downsweep_kernel<ITEMS, true, false><<<p.num_blocks, SORT_THREADS, SMEM, st>>>(
-          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
+          in, out, n, shift, p.tiles_per_block, spine, p.num_blocks);
     else if (pass == 3)
       downsweep_kernel<ITEMS, false, true><<<p.num_blocks, SORT_THREADS, SMEM, st>>>(
-          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
+          in, out, n, shift, p.tiles_per_block, spine, p.num_blocks);
     else
       downsweep_kernel<ITEMS, false, false><<<p.num_blocks, SORT_THREADS, SMEM, st>>>(
-          a, b, n, shift, p.tiles_per_block, spine, p.num_blocks);
+          in, out, n, shift, p.tiles_per_block, spine, p.num_blocks);
     UQ_LAUNCH_CHECK();
-    uint32_t* s = a;
-    a = b;
-    b = s;
+    in = out;
+    out = (out == b) ? a : b;
   }
   return UQ_OK;
 }
@@ -399,24 +401,34 @@ size_t radix_sort_scratch_bytes(int64_t n) {
   return spine_bytes(n) + 4 * RADIX * sizeof(uint32_t);   // + the digit totals of the four passes
 }
 
-int radix_sort_f32(float* keys, float* tmp, int64_t n, void* scratch, size_t scratch_bytes,
-                   float** sorted, cudaStream_t st) {
+int radix_sort_f32_copy(const float* src, float* keys, float* tmp, int64_t n, void* scratch,
+                        size_t scratch_bytes, float** sorted, cudaStream_t st) {
   UQ_REQUIRE(n >= 1 && n < ((int64_t)1 << 31), UQ_ERR_INVALID,
              "radix sort: n = %lld outside [1, 2^31)", (long long)n);
   UQ_REQUIRE(scratch && scratch_bytes >= radix_sort_scratch_bytes(n), UQ_ERR_WORKSPACE,
              "radix sort: scratch too small");
   UQ_REQUIRE(((uintptr_t)keys & 15) == 0 && ((uintptr_t)tmp & 15) == 0, UQ_ERR_INVALID,
              "radix sort: key buffers must be 16-byte aligned");
+  if (src != keys && ((uintptr_t)src & 15) != 0) {   // e.g. a tensor slice: copy, then in place
+    UQ_CUDA(cudaMemcpyAsync(keys, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    src = keys;
+  }
   const SortPlan p = sort_plan(n);
   uint32_t* spine = static_cast<uint32_t*>(scratch);
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
   uint32_t* a = reinterpret_cast<uint32_t*>(keys);
   uint32_t* b = reinterpret_cast<uint32_t*>(tmp);
   uint32_t* totals = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + spine_bytes(n));
-  const int rc = p.items == 32 ? sort_passes<32>(a, b, n, p, spine, totals, st)
-                               : sort_passes<16>(a, b, n, p, spine, totals, st);
+  const int rc = p.items == 32 ? sort_passes<32>(s32, a, b, n, p, spine, totals, st)
+                               : sort_passes<16>(s32, a, b, n, p, spine, totals, st);
   if (rc != UQ_OK) return rc;
-  *sorted = keys;  // 4 passes: the result is back in `keys`
+  *sorted = keys;  // 4 passes: the result is in `keys`
   return UQ_OK;
+}
+
+int radix_sort_f32(float* keys, float* tmp, int64_t n, void* scratch, size_t scratch_bytes,
+                   float** sorted, cudaStream_t st) {
+  return radix_sort_f32_copy(keys, keys, tmp, n, scratch, scratch_bytes, sorted, st);
 }
 
 }  // namespace uq
@@ -439,11 +451,9 @@ int uq_sort_f32(const float* x, int64_t n, float* out, void* workspace, size_t w
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* w = static_cast<char*>(workspace);
   float* tmp = reinterpret_cast<float*>(w);
-  if (out != x)
-    UQ_CUDA(cudaMemcpyAsync(out, x, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
   float* sorted = nullptr;
-  const int rc = uq::radix_sort_f32(out, tmp, n, w + sort_al(sizeof(float) * (size_t)n),
-                                    uq::radix_sort_scratch_bytes(n), &sorted, st);
+  const int rc = uq::radix_sort_f32_copy(x, out, tmp, n, w + sort_al(sizeof(float) * (size_t)n),
+                                         uq::radix_sort_scratch_bytes(n), &sorted, st);
   if (rc != UQ_OK) return rc;
   if (sorted != out)
     UQ_CUDA(cudaMemcpyAsync(out, sorted, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));

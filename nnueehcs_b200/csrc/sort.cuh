@@ -14,4 +14,9 @@ size_t radix_sort_scratch_bytes(int64_t n);
 int radix_sort_f32(float* keys, float* tmp, int64_t n, void* scratch, size_t scratch_bytes,
                    float** sorted, cudaStream_t st);
 
+// Same sort of the `n` floats at `src`, which is only read (pass 0 reads it directly: no copy
+// unless `src` is not 16-byte aligned).  The result ends up in `keys`; src == keys is allowed.
+int radix_sort_f32_copy(const float* src, float* keys, float* tmp, int64_t n, void* scratch,
+                        size_t scratch_bytes, float** sorted, cudaStream_t st);
+
 }  // namespace uq

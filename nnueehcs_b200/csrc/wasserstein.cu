@@ -754,14 +754,15 @@ int bin_moments_launch(const float* x, int64_t n, unsigned long long* cnt, unsig
   return UQ_OK;
 }
 
-// The sort method on device buffers that already hold copies of the samples.
-int sort_and_integrate(float* du, float* dut, int64_t nu, float* dv, float* dvt, int64_t nv,
-                       char* b, const WsLayout& L, double* result, cudaStream_t st) {
+// The sort method: sorted copies of u and v in the workspace buffers (the inputs are only read).
+int sort_and_integrate(const float* u, float* du, float* dut, int64_t nu, const float* v, float* dv,
+                       float* dvt, int64_t nv, char* b, const WsLayout& L, double* result,
+                       cudaStream_t st) {
   double* parts = reinterpret_cast<double*>(b + L.parts);
   float *su = nullptr, *sv = nullptr;
-  int rc = radix_sort_f32(du, dut, nu, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
+  int rc = radix_sort_f32_copy(u, du, dut, nu, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
   if (rc != UQ_OK) return rc;
-  rc = radix_sort_f32(dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
+  rc = radix_sort_f32_copy(v, dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
   if (rc != UQ_OK) return rc;
   if (nu + nv - 1 > 0) {
     const unsigned grid = integral_grid(L.blocks);
@@ -859,10 +860,11 @@ int compact_launch(const float* x, int64_t n, const uint8_t* flags, float* out,
 
 namespace {
 
-// tables, BinnedResult and the control words are zeroed, the fused kernel runs, the stream is
-// synchronised; *h = the record its last block wrote into mapped host memory
-int binned_fused(const float* u, int64_t nu, const float* v, int64_t nv, char* b, const WsLayout& L,
-                 FusedRecord* h, cudaStream_t st) {
+// tables, BinnedResult and the control words are zeroed and the fused kernel is launched; its last
+// block writes the FusedRecord to `record` (device-visible: mapped pinned host memory).  No
+// synchronisation.
+int binned_fused_launch(const float* u, int64_t nu, const float* v, int64_t nv, char* b,
+                        const WsLayout& L, FusedRecord* record, cudaStream_t st) {
   static PerDeviceOnce opted;
   static PerDeviceInt grid_cache;
   constexpr int SMEM = BM_SMEM;
@@ -870,8 +872,6 @@ int binned_fused(const float* u, int64_t nu, const float* v, int64_t nv, char* b
   int grid = 0;
   if (int rc = coop_grid_limit(wasserstein_binned_fused_kernel, BM_THREADS, SMEM, grid_cache, &grid))
     return rc;
-  void *slot_h = nullptr, *slot_d = nullptr;
-  if (int rc = result_slot(&slot_h, &slot_d)) return rc;
   unsigned long long* tables = reinterpret_cast<unsigned long long*>(b + L.tables);
   long long* pre_u = reinterpret_cast<long long*>(b + L.pre);
   long long* pre_v = pre_u + WB_BINS;
@@ -879,8 +879,6 @@ int binned_fused(const float* u, int64_t nu, const float* v, int64_t nv, char* b
   double* edges = reinterpret_cast<double*>(b + L.edges);
   BinnedResult* bres = reinterpret_cast<BinnedResult*>(b + L.bres);
   FusedCtl* ctl = reinterpret_cast<FusedCtl*>(b + L.ctl);
-  FusedRecord* record = static_cast<FusedRecord*>(slot_d);
-  static_cast<FusedRecord*>(slot_h)->nonfinite = -1;   // the kernel overwrites it with a count
   UQ_CUDA(cudaMemsetAsync(b + L.tables, 0, L.pre - L.tables, st));
   void* args[] = {(void*)&u, (void*)&nu, (void*)&v, (void*)&nv, (void*)&tables, (void*)&pre_u,
                   (void*)&pre_v, (void*)&flags, (void*)&edges, (void*)&bres, (void*)&ctl,
@@ -888,6 +886,17 @@ int binned_fused(const float* u, int64_t nu, const float* v, int64_t nv, char* b
   UQ_CUDA(cudaLaunchCooperativeKernel((const void*)wasserstein_binned_fused_kernel, dim3(grid),
                                       dim3(BM_THREADS), args, SMEM, st));
   UQ_LAUNCH_CHECK();
+  return UQ_OK;
+}
+
+// the synchronous form: this thread's mapped result slot, one stream synchronisation
+int binned_fused(const float* u, int64_t nu, const float* v, int64_t nv, char* b, const WsLayout& L,
+                 FusedRecord* h, cudaStream_t st) {
+  void *slot_h = nullptr, *slot_d = nullptr;
+  if (int rc = result_slot(&slot_h, &slot_d)) return rc;
+  static_cast<FusedRecord*>(slot_h)->nonfinite = -1;   // the kernel overwrites it with a count
+  if (int rc = binned_fused_launch(u, nu, v, nv, b, L, static_cast<FusedRecord*>(slot_d), st))
+    return rc;
   UQ_CUDA(cudaStreamSynchronize(st));
   memcpy(h, slot_h, sizeof(*h));
   UQ_REQUIRE(h->nonfinite >= 0, UQ_ERR_CUDA, "wasserstein: the kernel left no result record");
@@ -895,6 +904,42 @@ int binned_fused(const float* u, int64_t nu, const float* v, int64_t nv, char* b
 }
 
 }  // namespace
+
+// ---- enqueue / finish: the same metric without a synchronisation inside the call ----------------
+// enqueue = the one-pass binned method's memset + launch on `st`; `record` is caller-owned mapped
+// pinned host memory (>= UQ_METRIC_RECORD_BYTES) that the kernel's last block fills in.  After the
+// caller has synchronised the stream, finish reads the record: if every bin was resolved from
+// the tables (the ID-vs-OOD case) the distance is there; otherwise (ambiguous bins, inf / NaN)
+// the synchronous call runs.  Several metrics can so be in flight behind ONE synchronisation.
+int wasserstein_1d_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, void* record,
+                           void* ws, size_t ws_bytes, cudaStream_t st) {
+  const WsLayout L = layout(nu, nv);
+  UQ_REQUIRE(ws != nullptr && ws_bytes >= L.total, UQ_ERR_WORKSPACE,
+             "wasserstein needs %zu workspace bytes, got %zu", L.total, ws_bytes);
+  UQ_REQUIRE(nu + nv < ((int64_t)1 << 31), UQ_ERR_INVALID, "wasserstein: too many values");
+  void* record_dev = nullptr;
+  UQ_REQUIRE(record && cudaHostGetDevicePointer(&record_dev, record, 0) == cudaSuccess,
+             UQ_ERR_INVALID, "wasserstein enqueue: the record must be mapped pinned host memory");
+  static_assert(sizeof(FusedRecord) <= UQ_METRIC_RECORD_BYTES, "record size");
+  static_cast<FusedRecord*>(record)->nonfinite = -1;
+  return binned_fused_launch(u, nu, v, nv, static_cast<char*>(ws), L,
+                             static_cast<FusedRecord*>(record_dev), st);
+}
+
+int wasserstein_1d_finish(const float* u, int64_t nu, const float* v, int64_t nv,
+                          const void* record, double* out_host, int64_t* info_host, void* ws,
+                          size_t ws_bytes, cudaStream_t st) {
+  FusedRecord h;
+  memcpy(&h, record, sizeof(h));
+  UQ_REQUIRE(h.nonfinite >= 0, UQ_ERR_INVALID,
+             "wasserstein finish: no result record (synchronise the stream of the enqueue first)");
+  if (h.nonfinite == 0 && h.amb_u + h.amb_v == 0) {
+    *out_host = h.resolved;
+    if (info_host) info_host[0] = UQ_WASSERSTEIN_BINNED, info_host[1] = 0, info_host[2] = 0;
+    return UQ_OK;
+  }
+  return wasserstein_1d(u, nu, v, nv, UQ_WASSERSTEIN_AUTO, out_host, info_host, ws, ws_bytes, st);
+}
 
 // method: UQ_WASSERSTEIN_AUTO / _SORT / _BINNED (binned even when most values are ambiguous).
 // info_host (may be NULL): {method used, ambiguous u values, ambiguous v values}.
@@ -943,9 +988,7 @@ int wasserstein_1d(const float* u, int64_t nu, const float* v, int64_t nv, int m
     }
   }
 
-  UQ_CUDA(cudaMemcpyAsync(du, u, sizeof(float) * (size_t)nu, cudaMemcpyDeviceToDevice, st));
-  UQ_CUDA(cudaMemcpyAsync(dv, v, sizeof(float) * (size_t)nv, cudaMemcpyDeviceToDevice, st));
-  const int rc = sort_and_integrate(du, dut, nu, dv, dvt, nv, b, L, result, st);
+  const int rc = sort_and_integrate(u, du, dut, nu, v, dv, dvt, nv, b, L, result, st);
   if (rc != UQ_OK) return rc;
   UQ_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
   UQ_CUDA(cudaStreamSynchronize(st));
@@ -1049,13 +1092,11 @@ int wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t nv,
   float *su = du, *sv = dv;
   int rc;
   if (nu > 0) {
-    UQ_CUDA(cudaMemcpyAsync(du, u, sizeof(float) * (size_t)nu, cudaMemcpyDeviceToDevice, st));
-    rc = radix_sort_f32(du, dut, nu, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
+    rc = radix_sort_f32_copy(u, du, dut, nu, b + L.scratch, radix_sort_scratch_bytes(nu), &su, st);
     if (rc != UQ_OK) return rc;
   }
   if (nv > 0) {
-    UQ_CUDA(cudaMemcpyAsync(dv, v, sizeof(float) * (size_t)nv, cudaMemcpyDeviceToDevice, st));
-    rc = radix_sort_f32(dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
+    rc = radix_sort_f32_copy(v, dv, dvt, nv, b + L.scratch, radix_sort_scratch_bytes(nv), &sv, st);
     if (rc != UQ_OK) return rc;
   }
   if (nu + nv - 1 > 0) {

@@ -358,6 +358,101 @@ def wasserstein_1d_info(u: torch.Tensor, v: torch.Tensor, method: str = "auto") 
             "sorted_u": int(info[1]), "sorted_v": int(info[2])}
 
 
+class PendingMetric:
+    """A distribution metric enqueued on the current stream by ``wasserstein_1d_async`` /
+    ``kde_jsd_async`` (``uq_*_enqueue``): nothing has been synchronised yet.  ``result()``
+    synchronises that stream once (a no-op for every further pending metric of the same stream)
+    and returns the float; the rare inputs the single-launch kernels do not cover (ambiguous
+    bins, inf / NaN, a range beyond ~4000 bandwidths) run the synchronous call there."""
+    __slots__ = ("kind", "u", "v", "num_points", "record", "ws", "wsb", "stream", "_value")
+
+    def __init__(self, kind, u, v, num_points, record, ws, wsb, stream):
+        self.kind, self.u, self.v, self.num_points = kind, u, v, num_points
+        self.record, self.ws, self.wsb, self.stream = record, ws, wsb, stream
+        self._value = None
+
+    def result(self) -> float:
+        if self._value is None:
+            lib = _lib.load()
+            self.stream.synchronize()
+            out = C.c_double()
+            u, v = self.u, self.v
+            with _on_device(u.device):
+                if self.kind == "wasserstein":
+                    _lib.check(lib.uq_wasserstein_1d_finish(
+                        u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), self.record.data_ptr(),
+                        C.byref(out), None, self.ws.data_ptr(), self.wsb, self.stream.cuda_stream))
+                else:
+                    _lib.check(lib.uq_kde_jsd_finish(
+                        u.data_ptr(), u.numel(), v.data_ptr(), v.numel(), self.num_points,
+                        self.record.data_ptr(), C.byref(out), None, self.ws.data_ptr(), self.wsb,
+                        self.stream.cuda_stream))
+            self._value = float(out.value)
+            _free_records.append(self.record)
+            self.u = self.v = self.ws = self.record = None     # release the buffers
+        return self._value
+
+
+_free_records: list = []     # pinned 256-byte result records, recycled by PendingMetric.result()
+_async_ws: dict = {}         # (device index, stream) -> workspace shared by the enqueued metrics
+
+
+def _metric_record() -> torch.Tensor:
+    # pinned host memory is device-mapped under unified addressing
+    if _free_records:
+        return _free_records.pop()
+    return torch.zeros(_lib.METRIC_RECORD_BYTES, dtype=torch.uint8, pin_memory=True)
+
+
+def _shared_metric_ws(device: torch.device, stream, nbytes: int) -> torch.Tensor:
+    """ONE workspace per (device, stream) for all enqueued metrics: calls on a stream run in order,
+    each begins by zeroing its tables, and the only later reader (``uq_*_finish`` falling back to
+    the synchronous path) recomputes everything after the stream has been synchronised -- so
+    metrics in flight do not need a workspace each (0.8 GB at 50 M + 50 M values)."""
+    key = (device.index, stream.cuda_stream)
+    ws = _async_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _async_ws.pop(key, None)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _async_ws[key] = ws
+    return ws
+
+
+def wasserstein_1d_async(u: torch.Tensor, v: torch.Tensor) -> PendingMetric:
+    """``wasserstein_1d(u, v)`` enqueued on the current stream, not synchronised
+    (``uq_wasserstein_1d_enqueue``); ``.result()`` gives the float."""
+    lib = _lib.load()
+    u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
+    if u.numel() == 0 or v.numel() == 0:
+        raise ValueError("Distribution can't be empty.")
+    record = _metric_record()
+    with _on_device(u.device):
+        stream = torch.cuda.current_stream(u.device)
+        wsb = int(lib.uq_wasserstein_workspace_bytes(u.numel(), v.numel()))
+        ws = _shared_metric_ws(u.device, stream, wsb)
+        _lib.check(lib.uq_wasserstein_1d_enqueue(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
+                                                 record.data_ptr(), ws.data_ptr(), wsb,
+                                                 stream.cuda_stream))
+    return PendingMetric("wasserstein", u, v, 0, record, ws, wsb, stream)
+
+
+def kde_jsd_async(u: torch.Tensor, v: torch.Tensor, num_points: int = 20000) -> PendingMetric:
+    """``kde_jsd(u, v, num_points)`` enqueued on the current stream, not synchronised
+    (``uq_kde_jsd_enqueue``); ``.result()`` gives the float."""
+    lib = _lib.load()
+    u, v = _flat_f32(u, "u"), _flat_f32(v, "v")
+    record = _metric_record()
+    with _on_device(u.device):
+        stream = torch.cuda.current_stream(u.device)
+        wsb = int(lib.uq_kde_jsd_workspace_bytes(u.numel(), v.numel(), int(num_points)))
+        ws = _shared_metric_ws(u.device, stream, wsb)
+        _lib.check(lib.uq_kde_jsd_enqueue(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
+                                          int(num_points), record.data_ptr(), ws.data_ptr(), wsb,
+                                          stream.cuda_stream))
+    return PendingMetric("kde_jsd", u, v, int(num_points), record, ws, wsb, stream)
+
+
 def sort_f32(x: torch.Tensor) -> torch.Tensor:
     """``x`` sorted ascending (a new float32 tensor): the radix sort behind the SORT Wasserstein
     method, the score metrics and the WINDOW KDE, on its own.  Ordering = the float32 bit patterns'

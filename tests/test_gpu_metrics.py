@@ -655,6 +655,10 @@ def test_radix_sort_bit_exact(n):
             x[:3] = np.array([0.0, -0.0, -np.inf], np.float32)
         got = ops.sort_f32(_dev(x)).cpu().numpy()
         assert np.array_equal(got.view(np.uint32), _sort_ref(x))
+    if n > 8:   # a slice that is not 16-byte aligned (copied before pass 0 instead of read in place)
+        x = kinds[0]
+        got = ops.sort_f32(_dev(x)[1:]).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), _sort_ref(x[1:].copy()))
 
 
 def test_radix_sort_both_tile_sizes():
@@ -677,3 +681,51 @@ def test_radix_sort_both_tile_sizes():
     x = np.random.default_rng(5).standard_normal(3_000_017).astype(np.float32)
     import zlib
     assert outs[0] == outs[1] == str(zlib.crc32(_sort_ref(x).tobytes()))
+
+
+# ---- enqueue / finish forms ---------------------------------------------------------------------------
+
+def test_enqueued_metrics_equal_the_synchronous_calls():
+    """uq_*_enqueue / uq_*_finish: several metrics in flight behind one synchronisation, the same
+    kernels -> the same bits; inputs the single-launch kernels do not cover fall back inside
+    finish (same-distribution samples: every bin ambiguous; inf: scipy's route)."""
+    rng = np.random.default_rng(21)
+    u = _dev(rng.gamma(2.0, 0.05, 300_001).astype(np.float32))
+    v = _dev(rng.gamma(3.0, 0.08, 200_003).astype(np.float32))
+    same = _dev(rng.gamma(2.0, 0.05, 250_000).astype(np.float32))
+    pend = [ops.wasserstein_1d_async(u, v), ops.kde_jsd_async(u, v, 20000),
+            ops.wasserstein_1d_async(u, same), ops.kde_jsd_async(v, same, 5000),
+            ops.wasserstein_1d_async(v, u)]
+    got = [p.result() for p in pend]
+    assert got[0] == ops.wasserstein_1d(u, v)
+    assert got[1] == ops.kde_jsd(u, v, 20000)
+    assert got[2] == ops.wasserstein_1d(u, same)          # fallback: ambiguous bins
+    assert got[3] == ops.kde_jsd(v, same, 5000)
+    assert got[4] == got[0]
+    assert got[0] == pytest.approx(metrics_oracle.wasserstein_1d(u.cpu().numpy(), v.cpu().numpy()),
+                                   rel=1e-11)
+    assert pend[0].result() == got[0]                      # idempotent
+    w = u.clone()
+    w[5] = float("inf")
+    assert ops.wasserstein_1d_async(w, v).result() == ops.wasserstein_1d(w, v)
+    wide = torch.cat([u, u.new_tensor([1e9])])            # range beyond 4000 bandwidths: KDE declines
+    assert ops.kde_jsd_async(wide, v, 2000).result() == ops.kde_jsd(wide, v, 2000)
+    with pytest.raises(ValueError, match="can't be empty"):
+        ops.wasserstein_1d_async(u[:0], v)
+
+
+def test_metric_evaluator_reads_distance_metrics_behind_one_synchronisation():
+    class Scores(torch.nn.Module):
+        def forward(self, x, return_ue=False):
+            return x, x[:, 0].abs()
+
+    rng = np.random.default_rng(3)
+    xi = _dev(rng.gamma(2.0, 0.05, (50_000, 1)).astype(np.float32))
+    xo = _dev(rng.gamma(3.0, 0.08, (40_000, 1)).astype(np.float32))
+    ev = evaluation.get_uncertainty_evaluator(["wasserstein_distance", "jensen_shannon_distance",
+                                               "auroc"])
+    r = ev.evaluate(Scores(), (xi, None), (xo, None))
+    assert r["wasserstein_distance"] == ops.wasserstein_1d(xi[:, 0], xo[:, 0])
+    assert r["jensen_shannon_distance"] == ops.kde_jsd(xi[:, 0], xo[:, 0], 20000)
+    assert isinstance(r["wasserstein_distance"], float) and "auroc" in r
+    assert list(r)[:2] == ["wasserstein_distance", "jensen_shannon_distance"]

@@ -87,6 +87,25 @@ def main():
                                               "window" if "[window]" in name else "auto")["method"]
             line["gaussian_terms_equivalent_per_s"] = total * args.grid / (mean_ms * 1e-3)
         print(json.dumps(line), flush=True)
+    # device time per call of the two single-launch metrics, host out of the loop (enqueue / finish)
+    for name, enq in (("wasserstein_1d[enqueued]", lambda: ops.wasserstein_1d_async(u, v)),
+                      ("kde_jsd[enqueued]", lambda: ops.kde_jsd_async(u, v, args.grid))):
+        [p.result() for p in [enq() for _ in range(2)]]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pend = [enq() for _ in range(args.steps)]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        vals = [p.result() for p in pend]
+        gbs = total * 4 / (ms * 1e-3) / 1e9
+        print(json.dumps({"metric": name, "result": vals[0], "values": total, "ms": ms,
+                          "values_per_s": total / (ms * 1e-3),
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                                       "frac": gbs / hbm, "algorithmic_bytes": total * 4,
+                                       "peak_source": src},
+                          "timing": f"{args.steps} calls enqueued back to back, one synchronisation"}),
+              flush=True)
     # the radix sort on its own: 36 B of HBM traffic per key is what a 4-pass LSD sort with a
     # separate histogram read moves (4 x (4 read + 4 write) + 4 x 4 upsweep read = 48 here)
     lib = ops._lib.load()
