@@ -98,33 +98,45 @@ spine_scan_kernel(uint32_t* __restrict__ spine, int num_blocks,
 // ---- downsweep: lane-private byte counters --------------------------------------------------------
 // A warp owns ITEMS * 32 consecutive keys of the tile and each LANE owns ITEMS consecutive keys of
 // those, so "key order" is (warp, lane, item).  Ranking needs no warp collectives at all:
-//   count   every lane bumps its own byte counter cnt[digit][lane] once per key (the old value is
-//           the key's rank among the lane's earlier keys with that digit; <= ITEMS <= 32);
-//   scan    lane L takes the digit rows L, L + 32, ... : the 32 lane counters of a row are eight
-//           words; an exclusive prefix inside each word is one IMAD (x * 0x01010100, <= 96 so no
-//           byte overflows), the prefix over the words is a DP4A chain; the byte prefixes go back
-//           in place, the eight word bases into a 16-bit table, the row total to the block scan;
-//   rank    position in the tile = block offset of (digit, warp) + word base + byte prefix + rank
-//           in the lane: three shared loads per key.
+//   count   every lane bumps its own byte counter of the key's digit (the old value is the key's
+//           rank among the lane's earlier keys with that digit; <= ITEMS <= 32).  The counters of
+//           lane l live in shared-memory bank l -- word (digit >> 2) * 32 + l, byte digit & 3 -- so
+//           the read-modify-write of 32 random digits is ONE wavefront each way (in a [digit][lane]
+//           byte matrix it was ~2.8: the kernel is bound by the LSU data pipe, 82 % busy, and half
+//           of its shared-memory wavefronts were bank conflicts);
+//   scan 1  one lane per (digit row j = digit >> 2, group g of four lanes): the four words of the
+//           group (one 128-bit load) are four lanes x four digits of byte counts; their running
+//           byte-wise sum is the exclusive prefix inside the group (<= 96: no byte overflows),
+//           stored back in place; the group's total goes to the row's group-total slot;
+//   scan 1b one lane per row: the eight group totals of a row added up -> the warp's count of the
+//           row's four digits, for the block-wide scan (thread t = digit t) that follows;
+//   scan 2  one lane per row again: the eight group totals turned into 16-bit exclusive bases that
+//           start at the block offset of (digit, warp), two digits per word: base[j][g] = (digits
+//           4j and 4j+2 | digits 4j+1 and 4j+3);
+//   rank    position in the tile = group base + byte prefix + rank in the lane: two shared loads
+//           per key, one of them conflict-free.
 // The ballot version of this kernel (nine VOTEs and ~60 instructions per 32 keys and round, every
 // round waiting for the previous one's counter update) issued 106 warp instructions per 32 keys
-// and ran at 0.39 keys per clock and SM; this one issues ~35.
-// Shared-memory layout of a warp's counters: byte (digit d, lane l) sits at
-// (l >> 4) * 4096 + d * 16 + (l & 15), i.e. two planes of 16-byte rows, so the scan's 128-bit row
-// loads of consecutive lanes are consecutive (conflict-free) and the counting step collides only
-// when two of the eight lanes that share a bank hold different digits with equal d mod 8.
+// and ran at 0.39 keys per clock and SM.
+// Base rows are 64 bytes of data in 80-byte slots: the stride of 20 words makes the 128-bit row
+// accesses of eight consecutive lanes hit eight different bank quads.  A row's group totals sit in
+// the last 32 bytes of its own slot (16 of them overlap the data: scan 2 has the totals in
+// registers before it writes the bases).
 template <int ITEMS>
 struct Down {
   static constexpr int TILE = SORT_THREADS * ITEMS;
   static constexpr int CNT_BYTES = SORT_WARPS * 8192;            // aliased by the staged tile
-  static constexpr int BASE_OFF = CNT_BYTES;                     // u16 [warp][256][8]
-  static constexpr int WOFF_OFF = BASE_OFF + SORT_WARPS * 4096;  // u16 [warp][256]
+  static constexpr int BROW = 80;                                // bytes per base row slot
+  static constexpr int BASE_BYTES = 64 * BROW;                   // per warp
+  static constexpr int BASE_OFF = CNT_BYTES;
+  static constexpr int WOFF_OFF = BASE_OFF + SORT_WARPS * BASE_BYTES;  // u16 [warp][256]
   static constexpr int DBASE_OFF = WOFF_OFF + SORT_WARPS * 512;  // u32 [256]
   static constexpr int GDELTA_OFF = DBASE_OFF + 1024;            // u32 [256]
   static constexpr int WTOT_OFF = GDELTA_OFF + 1024;             // u32 [warps]
   static constexpr int SMEM = WTOT_OFF + SORT_WARPS * 4;
   static_assert(TILE * 4 <= CNT_BYTES, "staged tile must fit the counter area");
   static_assert(ITEMS % 4 == 0 && ITEMS <= 32, "byte counters: at most 32 keys per lane");
+  static_assert(2 * (SMEM + 1024) <= 233472, "two blocks per SM");
 };
 
 // One tile.  FULL = every key of the tile exists (all tiles but the last one of the array): no
@@ -137,13 +149,17 @@ __device__ __forceinline__ void downsweep_tile(const uint32_t* __restrict__ in,
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
   unsigned char* cnt_w = smem + w * 8192;
   uint32_t* staged = reinterpret_cast<uint32_t*>(smem);
-  unsigned short* base_w = reinterpret_cast<unsigned short*>(smem + D::BASE_OFF + w * 4096);
+  unsigned char* base_w = smem + D::BASE_OFF + w * D::BASE_BYTES;
   unsigned short* woff = reinterpret_cast<unsigned short*>(smem + D::WOFF_OFF);
   unsigned short* woff_w = woff + w * RADIX;
   uint32_t* digit_base = reinterpret_cast<uint32_t*>(smem + D::DBASE_OFF);
   uint32_t* gdelta = reinterpret_cast<uint32_t*>(smem + D::GDELTA_OFF);
   uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + D::WTOT_OFF);
-  const uint32_t lane_off = (uint32_t)(lane >> 4) * 4096u + (uint32_t)(lane & 15);
+  // counter byte of (digit d, this lane): cnt_w + (d >> 2) * 128 + (d & 3) + lane * 4
+  const uint32_t lane_off = (uint32_t)lane * 4u;
+  // 16-bit group base of (digit d, this lane's group): base_w + (d >> 2) * BROW + (d & 1) * 4 +
+  // ((d >> 1) & 1) * 2 + (lane >> 2) * 8
+  const uint32_t group_off = (uint32_t)(lane >> 2) * 8u;
 
   // ---- keys: lane l owns keys [l * ITEMS, (l + 1) * ITEMS) of the warp's run.  Loading them
   // straight from global memory (128-bit loads ITEMS * 4 bytes apart) costs one L1 wavefront per
@@ -198,35 +214,40 @@ __device__ __forceinline__ void downsweep_tile(const uint32_t* __restrict__ in,
     const uint32_t d = (key[r] >> shift) & 0xFFu;
     rk[r] = 0;
     if (FULL || r < nvalid) {
-      unsigned char* c = cnt_w + d * 16u + lane_off;
+      unsigned char* c = cnt_w + ((d >> 2) * 128u + (d & 3u) + lane_off);
       const uint32_t old = *c;
       *c = (unsigned char)(old + 1u);
       rk[r] = old;
     }
   }
   __syncwarp();
-  // ---- scan the 32 lane counters of each digit row
+  // ---- scan 1: exclusive prefix inside every group of four lanes, group totals
 #pragma unroll
-  for (int i = 0; i < RADIX / 32; ++i) {
-    const int d = lane + 32 * i;
-    uint4* rowa = reinterpret_cast<uint4*>(cnt_w + d * 16);
-    uint4* rowb = reinterpret_cast<uint4*>(cnt_w + 4096 + d * 16);
-    const uint4 a = *rowa, b = *rowb;
-    const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t base[8], pre[8];
-    uint32_t run = 0;
+  for (int it = 0; it < 16; ++it) {
+    const int item = lane + 32 * it;               // (row j, group g) = (item >> 3, item & 7)
+    uint4* grp = reinterpret_cast<uint4*>(cnt_w) + item;   // words 4g .. 4g+3 of row j
+    const uint4 c = *grp;
+    const uint32_t e2 = c.x + c.y, e3 = e2 + c.z;
+    *grp = make_uint4(0u, c.x, e2, e3);
+    *reinterpret_cast<uint32_t*>(base_w + (item >> 3) * D::BROW + 48 + (item & 7) * 4) = e3 + c.w;
+  }
+  __syncwarp();
+  // ---- scan 1b: this warp's count of every digit
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      base[j] = run;
-      pre[j] = x[j] * 0x01010100u;
-      run = __dp4a(x[j], 0x01010101u, run);
+  for (int i = 0; i < 2; ++i) {
+    const int j = lane + 32 * i;
+    const uint4 ga = *reinterpret_cast<const uint4*>(base_w + j * D::BROW + 48);
+    const uint4 gb = *reinterpret_cast<const uint4*>(base_w + j * D::BROW + 64);
+    const uint32_t g8[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    uint32_t lo = 0, hi = 0;                       // digits (4j, 4j+2) and (4j+1, 4j+3), 16 bits each
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      lo += g8[g] & 0x00FF00FFu;
+      hi += (g8[g] >> 8) & 0x00FF00FFu;
     }
-    *rowa = make_uint4(pre[0], pre[1], pre[2], pre[3]);
-    *rowb = make_uint4(pre[4], pre[5], pre[6], pre[7]);
-    reinterpret_cast<uint4*>(base_w)[d] =
-        make_uint4(base[0] | (base[1] << 16), base[2] | (base[3] << 16),
-                   base[4] | (base[5] << 16), base[6] | (base[7] << 16));
-    woff_w[d] = (unsigned short)run;
+    // woff_w[4j .. 4j+3] = counts of digits 4j, 4j+1, 4j+2, 4j+3
+    *reinterpret_cast<uint2*>(woff_w + 4 * j) =
+        make_uint2((lo & 0xFFFFu) | (hi << 16), (lo >> 16) | (hi & 0xFFFF0000u));
   }
   __syncthreads();
   // ---- thread t == digit t: where each (digit, warp) run starts in the tile and in `out`
@@ -251,27 +272,47 @@ __device__ __forceinline__ void downsweep_tile(const uint32_t* __restrict__ in,
     for (int ww = 0; ww < SORT_WARPS; ++ww)
       if (ww < w) before += warp_tot[ww];
     const uint32_t off = before + incl - total;   // first tile-local position of digit t
-    // the start of (digit t, warp ww)'s run goes into that warp's eight word bases of the digit
-    // (packed 16-bit adds, no carries: base + start < 2^14), so ranking needs no third table
     uint32_t run = off;
 #pragma unroll
     for (int ww = 0; ww < SORT_WARPS; ++ww) {
-      uint4* bp = reinterpret_cast<uint4*>(smem + D::BASE_OFF + ww * 4096) + t;
-      uint4 bv = *bp;
-      const uint32_t add = run * 0x00010001u;
-      bv.x += add, bv.y += add, bv.z += add, bv.w += add;
-      *bp = bv;
+      woff[ww * RADIX + t] = (unsigned short)run;
       run += c[ww];
     }
     gdelta[t] = digit_base[t] - off;              // global position = gdelta[d] + local position
     digit_base[t] += total;
   }
   __syncthreads();
+  // ---- scan 2: 16-bit group bases that start at the (digit, warp) run's offset in the tile
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = lane + 32 * i;
+    unsigned char* row = base_w + j * D::BROW;
+    const uint4 ga = *reinterpret_cast<const uint4*>(row + 48);
+    const uint4 gb = *reinterpret_cast<const uint4*>(row + 64);
+    const uint2 st = *reinterpret_cast<const uint2*>(woff_w + 4 * j);   // starts of digits 4j..4j+3
+    uint32_t lo = (st.x & 0xFFFFu) | (st.y << 16);          // digits 4j, 4j+2
+    uint32_t hi = (st.x >> 16) | (st.y & 0xFFFF0000u);      // digits 4j+1, 4j+3
+    const uint32_t g8[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    uint32_t b[16];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      b[2 * g] = lo, b[2 * g + 1] = hi;
+      lo += g8[g] & 0x00FF00FFu;
+      hi += (g8[g] >> 8) & 0x00FF00FFu;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(row + 16 * q) = make_uint4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+  }
+  __syncwarp();
   // ---- rank: tile-local destination of every key
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
     const uint32_t d = (key[r] >> shift) & 0xFFu;
-    rk[r] += (uint32_t)cnt_w[d * 16u + lane_off] + (uint32_t)base_w[d * 8u + (lane >> 2)];
+    const uint32_t j = d >> 2;
+    rk[r] += (uint32_t)cnt_w[j * 128u + (d & 3u) + lane_off] +
+             (uint32_t)*reinterpret_cast<const unsigned short*>(
+                 base_w + j * D::BROW + (d & 1u) * 4u + (d & 2u) + group_off);
   }
   __syncthreads();   // every warp is done with the counters: the staged tile takes their place
 #pragma unroll
