@@ -337,6 +337,31 @@ def metric_kernel_lines(dev, peaks, n=50_000_000, steps=5):
                      "result": val,
                      "method": info()["method"], "gpu_launches_per_call": int(launches),
                      "data": "synthetic Gamma(2, 0.05) vs Gamma(3, 0.08) scores, float32, in HBM"}
+    # scipy's own route (two radix sorts + a merge-path integral): the fallback of the binned
+    # method and the engine of uq_score_metrics; and the sort on its own
+    for name, fn in (("wasserstein_1d_sort", lambda: ops.wasserstein_1d(u, v, "sort")),
+                     ("radix_sort_f32", lambda: ops.sort_f32(u))):
+        for _ in range(2):
+            val = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            val = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        nvals = 2 * n if name.startswith("wasserstein") else n
+        out[name] = {"values": nvals, "ms": ms, "values_per_s": nvals / (ms * 1e-3),
+                     "algorithmic_GBps": nvals * 4 / (ms * 1e-3) / 1e9, "hbm_peak_GBps": hbm,
+                     "frac_of_hbm_peak": nvals * 4 / (ms * 1e-3) / 1e9 / hbm if hbm else None}
+        if name.startswith("wasserstein"):
+            out[name]["result"] = val
+            out[name]["equals_binned"] = bool(abs(val - out["wasserstein_1d"]["result"])
+                                              <= 1e-11 * abs(val))
+        else:
+            out[name]["sorted"] = bool((val[1:] >= val[:-1]).all().item())
+        del val
     del u, v
     torch.cuda.empty_cache()
     return out
