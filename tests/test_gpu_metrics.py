@@ -661,6 +661,28 @@ def test_radix_sort_bit_exact(n):
         assert np.array_equal(got.view(np.uint32), _sort_ref(x[1:].copy()))
 
 
+def test_radix_sort_at_baseline_size_properties():
+    """50 M keys (BASELINE configs[4]'s per-sample size), beyond what numpy sorts in seconds:
+    size-independent properties -- sorted, the same multiset (sum and xor of the bit patterns), idempotent --
+    and equality with torch.sort of the same GPU (a library sort, the checker here)."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(50_000_000, generator=g, device=DEV) * torch.rand(50_000_000, generator=g, device=DEV)
+    x[:5] = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), 1e-42], device=DEV)
+    y = ops.sort_f32(x)
+    assert bool((y[1:] >= y[:-1]).all())
+    xi, yi = x.view(torch.int32), y.view(torch.int32)
+    assert int(xi.to(torch.int64).sum()) == int(yi.to(torch.int64).sum())
+    def xor_all(t):
+        while t.numel() > 1:
+            h = t.numel() // 2
+            t = torch.cat([t[:h] ^ t[h:2 * h], t[2 * h:]])
+        return int(t[0])
+    assert xor_all(xi.clone()) == xor_all(yi.clone())
+    assert torch.equal(ops.sort_f32(y).view(torch.int32), yi)
+    ref = torch.sort(x).values
+    assert torch.equal(ref, y)          # values equal everywhere (-0.0 == +0.0 under this comparison)
+
+
 def test_radix_sort_both_tile_sizes():
     """8192-key tiles (32 keys per lane) and 4096-key tiles give the same bits; UQ_SORT_ITEMS is
     read once per process, so the forced sizes run in subprocesses."""

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_metrics.py -x -q > gpurun_out/pytest_metrics.log 2>&1
 echo "pytest metrics exit $?"; tail -5 gpurun_out/pytest_metrics.log
-timeout 600 python tools/bench_metrics.py --steps 5 > gpurun_out/metrics_50M.jsonl 2> gpurun_out/metrics_50M.err
+timeout 600 python tools/bench_metrics.py --steps 10 > gpurun_out/metrics_50M.jsonl 2> gpurun_out/metrics_50M.err
 echo "bench_metrics exit $?"
 python - <<PY
 import json
