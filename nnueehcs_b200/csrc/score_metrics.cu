@@ -51,25 +51,114 @@ sum_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ partials
   }
 }
 
-// Mann-Whitney: sum over OOD scores of (#ID < v) + (#ID <= v)  (= 2U, exact in uint64)
-__global__ void __launch_bounds__(256)
-auroc_kernel(const float* __restrict__ id_sorted, int64_t n_id, const float* __restrict__ ood,
-             int64_t n_ood, unsigned long long* __restrict__ acc) {
-  __shared__ unsigned long long sh[8];
-  unsigned long long s = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ood;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = __ldg(ood + i);
-    s += (unsigned long long)(lower_bound_f(id_sorted, n_id, v) + upper_bound_f(id_sorted, n_id, v));
+// Mann-Whitney: sum over OOD scores v of (#ID < v) + (#ID <= v)  (= 2U, exact in uint64).
+// Both arrays are sorted, so the counts are read off a MERGE instead of two 26-step binary
+// searches per OOD score (2.1 ms at 50 M + 50 M): with ties broken "ID first" the number of ID
+// scores merged before an OOD score v is #ID <= v, with ties broken "OOD first" it is #ID < v --
+// one launch per rule.  Persistent blocks own contiguous ranges of 2048-position tiles of the
+// merged sequence; the first split of a range comes from one warp-cooperative 33-ary search, every
+// later one from where the previous tile ended; a thread finds its 8-position diagonal in shared
+// memory and merges sequentially (the structure of wasserstein.cu's cdf_integral_kernel).
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+template <bool ID_FIRST>
+__device__ __forceinline__ bool takes_id(float a, float b) { return ID_FIRST ? a <= b : a < b; }
+
+// number of ID scores among the first k merged elements
+template <bool ID_FIRST>
+__device__ __forceinline__ int64_t split_warp(const float* __restrict__ A, int64_t na,
+                                              const float* __restrict__ B, int64_t nb, int64_t k) {
+  const int lane = threadIdx.x & 31;
+  int64_t lo = k > nb ? k - nb : 0;
+  int64_t hi = k < na ? k : na;
+  while (lo < hi) {   // takes_id(A[mid], B[k - mid - 1]) holds exactly for mid < answer
+    const int64_t span = hi - lo;
+    const int64_t mid = lo + (span * (lane + 1)) / 33;
+    const bool pred = takes_id<ID_FIRST>(A[mid], B[k - mid - 1]);
+    const int c = __popc(__ballot_sync(0xffffffffu, pred));
+    const int64_t last_true = __shfl_sync(0xffffffffu, mid, c > 0 ? c - 1 : 0);
+    const int64_t first_false = __shfl_sync(0xffffffffu, mid, c < 32 ? c : 31);
+    if (c > 0) lo = last_true + 1;
+    if (c < 32) hi = first_false;
+  }
+  return lo < hi ? lo : hi;
+}
+template <bool ID_FIRST>
+__device__ __forceinline__ int split_smem(const float* A, int na, const float* B, int nb, int k) {
+  int lo = k > nb ? k - nb : 0;
+  int hi = k < na ? k : na;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (takes_id<ID_FIRST>(A[mid], B[k - mid - 1])) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <bool ID_FIRST>
+__global__ void __launch_bounds__(RS_THREADS, 4)
+rank_sum_kernel(const float* __restrict__ A /*sorted ID*/, int64_t na,
+                const float* __restrict__ B /*sorted OOD*/, int64_t nb, int64_t tiles,
+                unsigned long long* __restrict__ acc) {
+  __shared__ float sa[RS_TILE + 1];
+  __shared__ float sb[RS_TILE + 1];
+  __shared__ unsigned long long warp_part[RS_THREADS / 32];
+  __shared__ long long split_s;
+  const int64_t total = na + nb;
+  const int t = threadIdx.x;
+  const int64_t tile_begin = (tiles * blockIdx.x) / gridDim.x;
+  const int64_t tile_end = (tiles * (blockIdx.x + 1)) / gridDim.x;
+  if (t < 32) {
+    const int64_t s0 = split_warp<ID_FIRST>(A, na, B, nb, tile_begin * RS_TILE);
+    if (t == 0) split_s = s0;
+  }
+  __syncthreads();
+  unsigned long long sum = 0;
+  for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+    const int64_t i0 = split_s;
+    const int64_t k0 = tile * RS_TILE, j0 = k0 - i0;
+    const int len = (int)((total - k0) < (int64_t)RS_TILE ? (total - k0) : (int64_t)RS_TILE);
+    const int la = (int)((na - i0) < (int64_t)len ? (na - i0) : (int64_t)len);
+    const int lb = (int)((nb - j0) < (int64_t)len ? (nb - j0) : (int64_t)len);
+    {
+      float ra[RS_ITEMS], rb[RS_ITEMS];   // every global load in flight before the first store
+#pragma unroll
+      for (int r = 0; r < RS_ITEMS; ++r) {
+        const int i = t + r * RS_THREADS;
+        ra[r] = i < la ? __ldg(A + i0 + i) : 0.f;
+        rb[r] = i < lb ? __ldg(B + j0 + i) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < RS_ITEMS; ++r) {
+        const int i = t + r * RS_THREADS;
+        sa[i] = ra[r];
+        sb[i] = rb[r];
+      }
+    }
+    __syncthreads();
+    const int ka = t * RS_ITEMS;
+    if (ka < len) {
+      const int kb = (ka + RS_ITEMS) < len ? (ka + RS_ITEMS) : len;
+      int i = split_smem<ID_FIRST>(sa, la, sb, lb, ka);
+      int j = ka - i;
+      for (int k = ka; k < kb; ++k) {
+        const bool id = (j >= lb) || (i < la && takes_id<ID_FIRST>(sa[i], sb[j]));
+        if (id) ++i;
+        else { sum += (unsigned long long)(i0 + i); ++j; }   // ID scores merged before this OOD score
+      }
+      if (kb == len) split_s = i0 + i;            // exactly one thread: the next tile's split
+    }
+    __syncthreads();
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+  if ((t & 31) == 0) warp_part[t >> 5] = sum;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long t = 0;
-    for (int w = 0; w < 8; ++w) t += sh[w];
-    atomicAdd(acc, t);
+  if (t == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < RS_THREADS / 32; ++w) s += warp_part[w];
+    if (s) atomicAdd(acc, s);
   }
 }
 
@@ -231,9 +320,11 @@ int uq_score_metrics(const float* id_scores, int64_t n_id, const float* ood_scor
   sum_kernel<<<SUM_BLOCKS, 256, 0, st>>>(sa, n_id, partials);
   UQ_LAUNCH_CHECK();
   UQ_CUDA(cudaMemsetAsync(acc, 0, sizeof(unsigned long long), st));
-  int64_t blocks = (n_ood + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  auroc_kernel<<<(unsigned)blocks, 256, 0, st>>>(sa, n_id, sb, n_ood, acc);
+  const int64_t tiles = (n_id + n_ood + RS_TILE - 1) / RS_TILE;
+  const unsigned grid = (unsigned)(tiles < 148 * 4 ? tiles : 148 * 4);
+  rank_sum_kernel<true><<<grid, RS_THREADS, 0, st>>>(sa, n_id, sb, n_ood, tiles, acc);   // #ID <= v
+  UQ_LAUNCH_CHECK();
+  rank_sum_kernel<false><<<grid, RS_THREADS, 0, st>>>(sa, n_id, sb, n_ood, tiles, acc);  // #ID < v
   UQ_LAUNCH_CHECK();
   score_scalar_kernel<<<1, 32, 0, st>>>(sa, n_id, sb, n_ood, *req, partials, acc, result);
   UQ_LAUNCH_CHECK();
