@@ -614,8 +614,11 @@ int kde_jsd_fused(const float* u, int64_t nu, const float* v, int64_t nv, int gr
 int kde_jsd_fused_enqueue(const float* u, int64_t nu, const float* v, int64_t nv, int grid_pts,
                           void* record, void* ws, size_t ws_bytes, cudaStream_t st) {
   void* record_dev = nullptr;
-  UQ_REQUIRE(record && cudaHostGetDevicePointer(&record_dev, record, 0) == cudaSuccess,
-             UQ_ERR_INVALID, "kde_jsd enqueue: the record must be mapped pinned host memory");
+  if (!record || cudaHostGetDevicePointer(&record_dev, record, 0) != cudaSuccess) {
+    (void)cudaGetLastError();   // the failed query must not show up in the next launch check
+    set_error("kde_jsd enqueue: the record must be mapped pinned host memory");
+    return UQ_ERR_INVALID;
+  }
   static_assert(sizeof(KfRecord) <= UQ_METRIC_RECORD_BYTES, "record size");
   static_cast<KfRecord*>(record)->status = 0;
   return kde_jsd_fused_launch(u, nu, v, nv, grid_pts, static_cast<KfRecord*>(record_dev), ws,

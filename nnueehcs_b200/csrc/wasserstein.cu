@@ -918,8 +918,11 @@ int wasserstein_1d_enqueue(const float* u, int64_t nu, const float* v, int64_t n
              "wasserstein needs %zu workspace bytes, got %zu", L.total, ws_bytes);
   UQ_REQUIRE(nu + nv < ((int64_t)1 << 31), UQ_ERR_INVALID, "wasserstein: too many values");
   void* record_dev = nullptr;
-  UQ_REQUIRE(record && cudaHostGetDevicePointer(&record_dev, record, 0) == cudaSuccess,
-             UQ_ERR_INVALID, "wasserstein enqueue: the record must be mapped pinned host memory");
+  if (!record || cudaHostGetDevicePointer(&record_dev, record, 0) != cudaSuccess) {
+    (void)cudaGetLastError();   // the failed query must not show up in the next launch check
+    set_error("wasserstein enqueue: the record must be mapped pinned host memory");
+    return UQ_ERR_INVALID;
+  }
   static_assert(sizeof(FusedRecord) <= UQ_METRIC_RECORD_BYTES, "record size");
   static_cast<FusedRecord*>(record)->nonfinite = -1;
   return binned_fused_launch(u, nu, v, nv, static_cast<char*>(ws), L,

@@ -734,6 +734,26 @@ def test_enqueued_metrics_equal_the_synchronous_calls():
     assert ops.kde_jsd_async(wide, v, 2000).result() == ops.kde_jsd(wide, v, 2000)
     with pytest.raises(ValueError, match="can't be empty"):
         ops.wasserstein_1d_async(u[:0], v)
+    # the record must be mapped pinned host memory: pageable memory is refused, not written to
+    import ctypes
+    from nnueehcs_b200 import _lib
+    lib = _lib.load()
+    wsb = int(lib.uq_wasserstein_workspace_bytes(u.numel(), v.numel()))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    pageable = (ctypes.c_uint8 * 256)()
+    rc = lib.uq_wasserstein_1d_enqueue(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
+                                       ctypes.addressof(pageable), ws.data_ptr(), wsb,
+                                       torch.cuda.current_stream().cuda_stream)
+    assert rc == _lib.UQ_ERR_INVALID and b"pinned" in lib.uq_last_error()
+    torch.cuda.synchronize()
+    # finish before the kernel has written the record is an error, not a wrong number
+    rec = torch.zeros(256, dtype=torch.uint8, pin_memory=True)
+    rec.view(torch.int64)[3] = -1        # what enqueue writes before the launch
+    out = ctypes.c_double()
+    rc = lib.uq_wasserstein_1d_finish(u.data_ptr(), u.numel(), v.data_ptr(), v.numel(),
+                                      rec.data_ptr(), ctypes.byref(out), None, ws.data_ptr(), wsb,
+                                      torch.cuda.current_stream().cuda_stream)
+    assert rc == _lib.UQ_ERR_INVALID and b"synchronise" in lib.uq_last_error()
 
 
 def test_metric_evaluator_reads_distance_metrics_behind_one_synchronisation():
