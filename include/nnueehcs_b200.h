@@ -241,7 +241,7 @@ int uq_kde_jsd_ex(const float* u, int64_t nu, const float* v, int64_t nv, int32_
 /*    The ascending sort underneath the SORT method, uq_score_metrics and the WINDOW KDE, on its
       own: what np.sort does inside scipy's _cdf_distance (behind nnueehcs/evaluation.py:182) and
       np.percentile (evaluation.py:292-381).  Stable 4-pass LSD radix sort of the float32 bit
-      patterns (-0.0 before +0.0, NaNs with the sign bit clear last).  x, out: [n] float32 device,
+      patterns (-0.0 before +0.0; every NaN last, as np.sort puts them, returned as 0x7FFFFFFF).  x, out: [n] float32 device,
       16-byte aligned, out == x allowed; asynchronous on `stream`. */
 size_t uq_sort_workspace_bytes(int64_t n);
 int uq_sort_f32(const float* x, int64_t n, float* out, void* workspace, size_t workspace_bytes,

@@ -17,7 +17,10 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX = 256;
 constexpr int MAX_SORT_BLOCKS = 148 * 2;   // <= SPINE_THREADS: one spine row is one block scan
 
+// order-preserving key of a float32 bit pattern; every NaN (either sign, any payload) becomes the
+// largest key, so NaNs sort last as np.sort puts them (and come back as 0x7FFFFFFF)
 __device__ __forceinline__ uint32_t f2key(uint32_t b) {
+  if ((b & 0x7FFFFFFFu) > 0x7F800000u) return 0xFFFFFFFFu;
   return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
 }
 __device__ __forceinline__ uint32_t key2f(uint32_t k) {

@@ -38,12 +38,17 @@ constexpr int MRG_THREADS = 256;
 constexpr int MRG_ITEMS = 8;
 constexpr int MRG_TILE = MRG_THREADS * MRG_ITEMS;  // merged positions per block
 
+// a <= b in the order the radix sort leaves the arrays in: NaNs (canonicalised by the sort) after
+// everything else, all NaNs equal.  A plain "a <= b" is false for any NaN, which would merge a
+// sample's NaNs AFTER the other sample's sentinel and turn scipy's nan (nan in, nan out) into inf.
+__device__ __forceinline__ bool le_total(float a, float b) { return (a <= b) || (b != b); }
+
 __device__ __forceinline__ int merge_path_smem(const float* U, int nu, const float* V, int nv, int k) {
   int lo = k > nv ? k - nv : 0;
   int hi = k < nu ? k : nu;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (U[mid] <= V[k - mid - 1]) lo = mid + 1; else hi = mid;
+    if (le_total(U[mid], V[k - mid - 1])) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
@@ -78,7 +83,7 @@ __device__ __forceinline__ int64_t merge_path(const float* __restrict__ U, int64
   int64_t hi = k < nu ? k : nu;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
-    if (U[mid] <= V[k - mid - 1]) lo = mid + 1; else hi = mid;
+    if (le_total(U[mid], V[k - mid - 1])) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
@@ -98,7 +103,7 @@ __device__ __forceinline__ int64_t merge_path_warp(const float* __restrict__ U, 
   while (lo < hi) {
     const int64_t span = hi - lo;
     const int64_t mid = lo + (span * (lane + 1)) / 33;   // lo <= mid < hi, non-decreasing in lane
-    const bool pred = U[mid] <= V[k - mid - 1];
+    const bool pred = le_total(U[mid], V[k - mid - 1]);
     const int c = __popc(__ballot_sync(0xffffffffu, pred));   // the true probes are a prefix
     const int64_t mid_last_true = __shfl_sync(0xffffffffu, mid, c > 0 ? c - 1 : 0);
     const int64_t mid_first_false = __shfl_sync(0xffffffffu, mid, c < 32 ? c : 31);
@@ -146,8 +151,8 @@ __device__ __forceinline__ void stage_runs(const float* __restrict__ U, int lu,
 // one warp-cooperative search and gets every later split for free (a tile ends where the next one
 // starts), so there is no partition pass; a thread keeps its partial sum in a register across all
 // its tiles.  Inside a tile every thread merges MRG_ITEMS consecutive positions from shared
-// memory; the runs are closed by sentinels (NaN after u, +inf after v: "u[i] <= v[j]" is then the
-// whole take-u test, ties and exhausted runs included), the value is widened to float64 once per
+// memory; the runs are closed by NaN sentinels (see merge_tile: no index tests for exhausted runs
+// in the common case, and real NaNs merge last as they do in scipy), the value is widened to float64 once per
 // element, and the rank difference a nb - b na is carried as an exactly-updated float64 (DBL:
 // na nb < 2^53) instead of being rebuilt from two 64-bit products per element.
 constexpr int MRG_PAD = 16;
@@ -159,7 +164,9 @@ __device__ __forceinline__ double merge_tile(const float* su, int lu, const floa
   int i = merge_path_smem(su, lu, sv, lv, ka);
   int j = ka - i;
   float a = su[i], b = sv[j];
-  bool tu = a <= b;                      // merged element ka
+  // both runs end in a NaN sentinel: "a <= b, or b is a NaN and u is not exhausted" is the whole
+  // take-u test -- real NaNs merge last (u's before v's), an exhausted run never wins
+  bool tu = (a <= b) || ((b != b) && i < lu);   // merged element ka
   double cur = (double)(tu ? a : b);
   i += tu ? 1 : 0, j += tu ? 0 : 1;
   a = su[i], b = sv[j];
@@ -170,7 +177,7 @@ __device__ __forceinline__ double merge_tile(const float* su, int lu, const floa
 #pragma unroll
   for (int q = 0; q < MRG_ITEMS; ++q) {
     if (ka + q < kb) {
-      tu = a <= b;                       // merged element ka + q + 1 (exists: kb <= total - 1)
+      tu = (a <= b) || ((b != b) && i < lu);   // merged element ka + q + 1 (exists: kb <= total - 1)
       const double nxt = (double)(tu ? a : b);
       const double gap = DBL ? fabs(dd) : cdf_gap(cs, ru, rv);
       acc = fma(gap, nxt - cur, acc);
@@ -209,12 +216,16 @@ cdf_integral_kernel(const float* __restrict__ U, int64_t nu, const float* __rest
     int64_t k1 = k0 + MRG_TILE;                     // contributions k in [k0, k1)
     if (k1 > total - 1) k1 = total - 1;
     const int len = (int)(k1 - k0);
-    const int lu = (int)((nu - i0) < (int64_t)(len + 1) ? (nu - i0) : (int64_t)(len + 1));
-    const int lv = (int)((nv - j0) < (int64_t)(len + 1) ? (nv - j0) : (int64_t)(len + 1));
+    int lu = (int)((nu - i0) < (int64_t)(len + 1) ? (nu - i0) : (int64_t)(len + 1));
+    int lv = (int)((nv - j0) < (int64_t)(len + 1) ? (nv - j0) : (int64_t)(len + 1));
+    // NaN scores compare false either way, so a merge over them can run past the end of v (the
+    // result is NaN, as scipy's is); the run lengths must stay valid array extents regardless
+    if (lu < 0) lu = 0;
+    if (lv < 0) lv = 0;
     stage_runs(U + i0, lu, V + j0, lv, su, sv);
     if (t < MRG_PAD) {
       if (lu + t < MRG_TILE + MRG_PAD) su[lu + t] = __int_as_float(0x7fc00000);   // NaN
-      if (lv + t < MRG_TILE + MRG_PAD) sv[lv + t] = __int_as_float(0x7f800000);   // +inf
+      if (lv + t < MRG_TILE + MRG_PAD) sv[lv + t] = __int_as_float(0x7fc00000);   // NaN
     }
     __syncthreads();
     const int ka = t * MRG_ITEMS;

@@ -121,6 +121,18 @@ def test_wasserstein_binned_unaligned_views_and_nonfinite_fallback():
     info = ops.wasserstein_1d_info(w, base_v, "binned")
     assert info["method"] == "sort"            # inf / NaN: scipy's route decides what comes out
     assert info["value"] == ops.wasserstein_1d(w, base_v, "sort")
+    # scipy: inf - inf inside the integral -> nan
+    import math
+    for bad_at in ((17,), (0, 5000, 100002)):
+        wn = base_u.clone()
+        wn[list(bad_at)] = float("nan")
+        for m in ("auto", "sort"):
+            assert math.isnan(ops.wasserstein_1d(wn, base_v, m)), (bad_at, m)   # as scipy: nan in, nan out
+            assert math.isnan(ops.wasserstein_1d(base_v, wn, m)), (bad_at, m)
+        assert math.isnan(ops.wasserstein_1d_async(wn, base_v).result())
+    # and the library is still healthy afterwards
+    ref = metrics_oracle.wasserstein_1d(base_u.cpu().numpy(), base_v.cpu().numpy())
+    assert ops.wasserstein_1d(base_u, base_v, "sort") == pytest.approx(ref, rel=1e-11)
 
 
 def test_wasserstein_binned_at_scale():
@@ -659,6 +671,23 @@ def test_radix_sort_bit_exact(n):
         x = kinds[0]
         got = ops.sort_f32(_dev(x)[1:]).cpu().numpy()
         assert np.array_equal(got.view(np.uint32), _sort_ref(x[1:].copy()))
+
+
+def test_radix_sort_puts_every_nan_last():
+    """np.sort's convention: NaNs of either sign and any payload after +inf (they come back as one
+    canonical NaN); everything else in bit-pattern order."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(100_003).astype(np.float32)
+    bits = x.view(np.uint32)
+    bits[5] = 0x7FC00000          # quiet NaN
+    bits[77] = 0xFFC00000         # negative quiet NaN
+    bits[4096] = 0x7F800001       # signalling NaN, small payload
+    bits[99_999] = 0xFFFFFFFF     # negative NaN, full payload
+    x[10], x[11] = np.inf, -np.inf
+    got = ops.sort_f32(_dev(x)).cpu().numpy()
+    assert np.isnan(got[-4:]).all() and not np.isnan(got[:-4]).any()
+    assert np.array_equal(got[:-4].view(np.uint32), _sort_ref(x[~np.isnan(x)].copy()))
+    assert got[-5] == np.inf and got[0] == -np.inf
 
 
 def test_radix_sort_at_baseline_size_properties():
