@@ -319,6 +319,9 @@ int uq_wasserstein_1d_range(const float* u, int64_t nu, const float* v, int64_t 
       bandwidth: sklearn's bandwidth_ (for 'scott': m^(-1/(d+4)), uq_kde_scott_bandwidth);
       out: [n] float64 on device (the reference returns a float64 tensor).  Asynchronous. */
 double uq_kde_scott_bandwidth(int64_t m, int32_t d);
+/*    sklearn's other named rule, bandwidth='silverman' (the reference's KDE search space offers
+      both, examples/bo_driven/config_kde.yaml:385-390): (m (d + 2) / 4)^(-1/(d+4)). */
+double uq_kde_silverman_bandwidth(int64_t m, int32_t d);
 size_t uq_kde_density_workspace_bytes(int64_t n, int64_t m);
 int uq_kde_density(const float* fit, int64_t m, const float* x, int64_t n, int32_t d,
                    double bandwidth, double* out, void* workspace, size_t workspace_bytes,

@@ -34,7 +34,8 @@ EXPORTS = (
     "uq_kde_grid_accumulate", "uq_jsd_from_grids", "uq_key_bins", "uq_key_histogram",
     "uq_partition_by_bin", "uq_wasserstein_1d_range",
     "uq_score_metrics_workspace_bytes", "uq_score_metrics",
-    "uq_kde_scott_bandwidth", "uq_kde_density_workspace_bytes", "uq_kde_density",
+    "uq_kde_scott_bandwidth", "uq_kde_silverman_bandwidth", "uq_kde_density_workspace_bytes",
+    "uq_kde_density",
     "uq_sort_workspace_bytes", "uq_sort_f32",
     "uq_wasserstein_1d_enqueue", "uq_wasserstein_1d_finish", "uq_kde_jsd_enqueue",
     "uq_kde_jsd_finish",
@@ -149,6 +150,8 @@ def load() -> C.CDLL:
                                             vp, sz, vp]
     lib.uq_kde_scott_bandwidth.argtypes = [i64, i32]
     lib.uq_kde_scott_bandwidth.restype = dbl
+    lib.uq_kde_silverman_bandwidth.argtypes = [i64, i32]
+    lib.uq_kde_silverman_bandwidth.restype = dbl
     lib.uq_kde_density_workspace_bytes.argtypes = [i64, i64]
     lib.uq_kde_density_workspace_bytes.restype = sz
     lib.uq_kde_density.argtypes = [vp, i64, vp, i64, i32, dbl, vp, vp, sz, vp]

@@ -509,6 +509,13 @@ double uq_kde_scott_bandwidth(int64_t m, int32_t d) {
   return (m < 1 || d < 1) ? 0.0 : pow((double)m, -1.0 / ((double)d + 4.0));
 }
 
+double uq_kde_silverman_bandwidth(int64_t m, int32_t d) {
+  // sklearn.neighbors.KernelDensity.fit:
+  // bandwidth_ = (n_samples * (n_features + 2) / 4) ** (-1 / (n_features + 4))
+  return (m < 1 || d < 1) ? 0.0
+                          : pow((double)m * ((double)d + 2.0) / 4.0, -1.0 / ((double)d + 4.0));
+}
+
 size_t uq_kde_density_workspace_bytes(int64_t n, int64_t m) {
   return kde_density_workspace_bytes(n, m);
 }

@@ -347,7 +347,8 @@ class KDEMLPModel(MLPModel):
     """MLP + input-density uncertainty score, reference models.py:191-240.
 
     ``fit_kde(data)`` keeps a random ``train_fit_prop`` share of the training inputs (on their
-    device) and sklearn's 'scott' bandwidth ``m ** (-1 / (d + 4))``; ``forward(x, return_ue=True)``
+    device) and sklearn's 'scott' (``m ** (-1 / (d + 4))``) or 'silverman' bandwidth;
+    ``forward(x, return_ue=True)``
     returns ``(pred, dens)`` with ``dens = -exp(KernelDensity.score_samples(x))`` as a float64
     ``[N]`` tensor, computed by ``uq_kde_density`` on the GPU (the reference copies ``x`` to the
     host and walks a KD-tree per call).  ``rtol`` is kept for API parity: sklearn stops refining
@@ -355,9 +356,9 @@ class KDEMLPModel(MLPModel):
 
     def __init__(self, base_model, bandwidth='scott', rtol=0.1, train_fit_prop=1.0, **kwargs):
         super().__init__(base_model, **kwargs)
-        if bandwidth != 'scott' and not isinstance(bandwidth, (int, float)):
-            raise ValueError(f"bandwidth must be 'scott' or a number, got {bandwidth!r} "
-                             "('silverman' is not built)")
+        if bandwidth not in ('scott', 'silverman') and not isinstance(bandwidth, (int, float)):
+            raise ValueError(f"bandwidth must be 'scott', 'silverman' or a number, got "
+                             f"{bandwidth!r}")
         self.bandwidth = bandwidth
         self.rtol = rtol / 10000
         self.kde = None
@@ -369,8 +370,9 @@ class KDEMLPModel(MLPModel):
         kept = data[idx.to(data.device)].detach().to(torch.float32).contiguous()
         self._kde_data = kept
         m, d = kept.shape
-        self.kde = {"bandwidth_": float(self.bandwidth) if self.bandwidth != 'scott'
-                    else ops.kde_scott_bandwidth(m, d), "n_fit": m}
+        rules = {'scott': ops.kde_scott_bandwidth, 'silverman': ops.kde_silverman_bandwidth}
+        h = rules[self.bandwidth](m, d) if self.bandwidth in rules else float(self.bandwidth)
+        self.kde = {"bandwidth_": h, "n_fit": m}
 
     def forward(self, x, return_ue=False):
         if return_ue and self.kde is None:

@@ -502,6 +502,11 @@ def kde_scott_bandwidth(m: int, d: int) -> float:
     return float(_lib.load().uq_kde_scott_bandwidth(int(m), int(d)))
 
 
+def kde_silverman_bandwidth(m: int, d: int) -> float:
+    """sklearn ``KernelDensity(bandwidth='silverman').fit(X).bandwidth_`` for X of shape [m, d]."""
+    return float(_lib.load().uq_kde_silverman_bandwidth(int(m), int(d)))
+
+
 def kde_density(fit: torch.Tensor, x: torch.Tensor, bandwidth: float) -> torch.Tensor:
     """``-exp(KernelDensity(bandwidth).fit(fit).score_samples(x))`` as a float64 [n] device tensor
     (KDEMLPModel.forward's uncertainty score, reference models.py:209-222)."""

@@ -431,6 +431,12 @@ def scott_bandwidth_sklearn(m: int, d: int) -> float:
     return float(m) ** (-1.0 / (d + 4))
 
 
+def silverman_bandwidth_sklearn(m: int, d: int) -> float:
+    """sklearn/neighbors/_kde.py, KernelDensity.fit, bandwidth='silverman':
+    bandwidth_ = (n_samples * (n_features + 2) / 4) ** (-1 / (n_features + 4))."""
+    return (float(m) * (d + 2) / 4.0) ** (-1.0 / (d + 4))
+
+
 def kde_neg_density(fit: np.ndarray, x: np.ndarray, bandwidth: float, block: int = 256) -> np.ndarray:
     """``-exp(KernelDensity(bandwidth=h, kernel='gaussian').fit(fit).score_samples(x))`` in float64:
     log-density = logsumexp(-|x - y|^2 / (2 h^2)) - log(m) - d log(h) - d/2 log(2 pi)."""

@@ -21,11 +21,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from tests.golden.make_golden import mlp_arch, ref_builder, ref_models  # noqa: E402
 
 
-def make_case(out, tag, d, m, seed):
+def make_case(out, tag, d, m, seed, bandwidth="scott"):
     import sklearn
     arch = mlp_arch(d, [16], 1, False)
     torch.manual_seed(seed)
-    model = ref_builder.KDEModelBuilder(arch, {"bandwidth": "scott", "rtol": 0.1,
+    model = ref_builder.KDEModelBuilder(arch, {"bandwidth": bandwidth, "rtol": 0.1,
                                                "train_fit_prop": 1.0}).build()
     assert isinstance(model, ref_models.KDEMLPModel)
     g = torch.Generator().manual_seed(seed)
@@ -56,7 +56,9 @@ def make_case(out, tag, d, m, seed):
 
 if __name__ == "__main__":
     torch.set_num_threads(1)
-    out = {"tags": np.array(["far5", "far2"])}
+    out = {"tags": np.array(["far5", "far2", "silverman3"])}
     make_case(out, "far5", 5, 2000, 10)
     make_case(out, "far2", 2, 700, 11)
+    # bandwidth='silverman' (examples/bo_driven/config_kde.yaml:385-390 offers both rules)
+    make_case(out, "silverman3", 3, 900, 12, "silverman")
     np.savez_compressed(os.path.join(HERE, "kde_density_far.npz"), **out)

@@ -544,7 +544,7 @@ def test_kde_density_matches_reference_class_golden(tag):
     assert got[-1] == 0.0          # far query: every term underflows, as in the reference
 
 
-@pytest.mark.parametrize("tag", ["far5", "far2"])
+@pytest.mark.parametrize("tag", ["far5", "far2", "silverman3"])
 def test_kde_density_far_queries_keep_their_order(tag):
     """Far-OOD queries (reference densities 1e-38 ... 1e-318, where a float32 kernel sum has
     flushed to zero) are re-done in float64 log space: equal to the float64 oracle at the same
@@ -560,6 +560,26 @@ def test_kde_density_far_queries_keep_their_order(tag):
     assert np.array_equal(got == 0, gold == 0)
     big = np.abs(gold) > 1e-290                  # away from float64 denormals: strict order kept
     assert np.array_equal(np.argsort(got[big], kind="stable"), np.argsort(gold[big], kind="stable"))
+
+
+def test_kde_wrapper_silverman_bandwidth():
+    """bandwidth='silverman' (the reference's KDE search space offers both rules,
+    examples/bo_driven/config_kde.yaml:385-390) through the wrapper, against the reference class."""
+    from nnueehcs_b200.model_builder import KDEModelBuilder
+    g = load_golden("kde_density_far.npz")
+    fit, x = g["silverman3.fit"], g["silverman3.x"]
+    arch = [{"Linear": {"args": [3, 16]}}, {"ReLU": {"inplace": True}}, {"Linear": {"args": [16, 1]}}]
+    model = KDEModelBuilder(arch, {"bandwidth": "silverman", "rtol": 0.1, "train_fit_prop": 1.0}).build()
+    model.to(DEV).eval()
+    model.fit_kde(torch.from_numpy(fit).to(DEV))
+    assert model.kde["bandwidth_"] == pytest.approx(float(g["silverman3.bandwidth"]), rel=1e-15)
+    assert ops.kde_silverman_bandwidth(*fit.shape) == pytest.approx(
+        metrics_oracle.silverman_bandwidth_sklearn(*fit.shape), rel=1e-15)
+    with torch.no_grad():
+        _, dens = model(torch.from_numpy(x).to(DEV), return_ue=True)
+    np.testing.assert_allclose(dens.cpu().numpy(), g["silverman3.dens"], rtol=2e-4, atol=1e-300)
+    with pytest.raises(ValueError, match="'scott', 'silverman' or a number"):
+        KDEModelBuilder(arch, {"bandwidth": "epanechnikov"}).build()
 
 
 def test_kde_density_fit_splits_ragged_sizes_and_errors():

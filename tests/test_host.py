@@ -214,7 +214,10 @@ def test_kde_builder_and_wrapper_contract(descr):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(x, return_ue=True)
     with pytest.raises(ValueError, match="bandwidth must be"):
-        KDEModelBuilder(descr["architecture_mlp"], {"bandwidth": "silverman"}).build()
+        KDEModelBuilder(descr["architecture_mlp"], {"bandwidth": "epanechnikov"}).build()
+    sil = KDEModelBuilder(descr["architecture_mlp"], {"bandwidth": "silverman"}).build()
+    sil.fit_kde(torch.randn(50, 16))        # sklearn: (n (d + 2) / 4) ** (-1 / (d + 4))
+    assert sil.kde["bandwidth_"] == pytest.approx((50 * 18 / 4) ** (-1 / 20))
 
 
 def test_split_blocks_vocabulary(descr):
