@@ -17,8 +17,10 @@ result keys as the reference; what changes is underneath:
   result (two device sorts + binary searches) instead of numpy / sklearn / a Python loop over every
   unique score.
 
-Runtime / throughput / memory metrics and the Euclidean distance are not built: asking the
-factories for them raises ``ValueError`` naming the metric.
+The host-side metrics around the same calls -- ``EuclideanEvaluation`` (``:205-227``),
+``MaxMemoryUsageEvaluation`` and the runtime / throughput classes (``:383-516``; the last one is the
+reference's own definition of UQ throughput) -- are mirrored as plain host code so that a
+reference config moves over unchanged.
 """
 from __future__ import annotations
 
@@ -391,6 +393,173 @@ class PercentileBasedClassifier(ClassificationMetric):
         return f'percentile_classification{suffix}'
 
 
+# ------------------------------------------------------------------------------------------------
+# Host-side metrics around the same calls (reference ``evaluation.py:205-227, 383-516``): nothing to
+# accelerate, but the reference's configs name them (``uncertainty_estimating_throughput`` is the
+# BO objective of examples/bo_driven/config*.yaml, and the reference's own definition of UQ
+# throughput), so a config moves over unchanged.  Same names, result keys, objectives and timing
+# protocol: wall clock around each call with a device synchronisation before the clock stops.
+# ------------------------------------------------------------------------------------------------
+
+class EuclideanEvaluation(UncertaintyEvaluationMetric):
+    """Mean L2 distance between paired ID / OOD score rows (reference ``evaluation.py:205-227``)."""
+    name = "euclidean_distance"
+
+    def _evaluate_uncertainties(self, id_ue, ood_ue) -> dict:
+        if id_ue.dimensions != ood_ue.dimensions:
+            raise ValueError("Uncertainty estimates must have the same dimensions")
+        diff = np.asarray(id_ue.data) - np.asarray(ood_ue.data)
+        return {self.name: float(np.mean(np.sqrt(np.sum(diff ** 2, axis=-1))))}
+
+    @classmethod
+    def get_objectives(cls):
+        return [{"name": cls.name, "type": "maximize"}]
+
+    @classmethod
+    def get_metrics(cls):
+        return [cls.name]
+
+    def get_name(self):
+        return self.name
+
+
+def _device_sync() -> None:
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+class MaxMemoryUsageEvaluation(EvaluationMetric):
+    """Peak torch-allocator bytes (MiB) of one UQ forward over ID + OOD inputs (reference
+    ``evaluation.py:383-411``).  The fused kernels take their workspaces from torch's caching
+    allocator, so the number includes them."""
+    name = "max_memory_usage"
+
+    def evaluate(self, model, id_data: tuple, ood_data: tuple) -> dict:
+        import gc
+        model.eval()
+        with torch.no_grad():
+            torch.cuda.empty_cache()
+            gc.collect()
+            torch.cuda.reset_peak_memory_stats()
+            model(torch.cat([id_data[0], ood_data[0]]), return_ue=True)
+            peak = torch.cuda.max_memory_allocated()
+        return {self.name: peak / float(1 << 20)}
+
+    def get_objectives(self):
+        return [{"name": self.name, "type": "minimize"}]
+
+    def get_metrics(self):
+        return [self.name]
+
+    def get_name(self):
+        return self.name
+
+
+class RuntimeEvaluation(EvaluationMetric):
+    """``num_warmup`` untimed + ``num_trials`` timed calls on the concatenated ID + OOD inputs
+    (reference ``evaluation.py:413-461``); subclasses choose the call."""
+    name = "runtime"
+
+    def __init__(self, num_trials: int = 20, num_warmup: int = 5):
+        self.num_trials = num_trials
+        self.num_warmup = num_warmup
+
+    @classmethod
+    def from_config(cls, config: dict):
+        return cls(num_trials=config.get('trials', 20), num_warmup=config.get('warmup', 5))
+
+    def evaluate(self, model, id_data: tuple, ood_data: tuple) -> dict:
+        raise NotImplementedError("Cannot call evaluate on base class")
+
+    def _call(self, model, data):
+        raise NotImplementedError
+
+    def _seconds_per_call(self, model, id_data, ood_data) -> np.ndarray:
+        import time
+        model.eval()
+        data = torch.cat([id_data[0], ood_data[0]])
+        seconds = np.zeros(self.num_trials)
+        with torch.no_grad():
+            for _ in range(self.num_warmup):
+                self._call(model, data)
+            for i in range(self.num_trials):
+                t0 = time.time()
+                self._call(model, data)
+                _device_sync()
+                seconds[i] = time.time() - t0
+        return seconds
+
+    def _runtime(self, model, id_data, ood_data) -> dict:
+        s = self._seconds_per_call(model, id_data, ood_data)
+        return {'runtime': float(np.mean(s)), 'runtime_std': float(np.std(s))}
+
+    @classmethod
+    def get_objectives(cls):
+        return [{"name": cls.name, "type": "minimize"}]
+
+    @classmethod
+    def get_metrics(cls):
+        return [cls.name, 'runtime_std']
+
+    def get_name(self):
+        return self.name
+
+
+class BaseModelRuntimeEvaluation(RuntimeEvaluation):
+    name = "base_model_runtime"
+
+    def _call(self, model, data):
+        return model(data)
+
+    def evaluate(self, model, id_data: tuple, ood_data: tuple) -> dict:
+        return self._runtime(model, id_data, ood_data)
+
+
+class UncertaintyEstimatingRuntimeEvaluation(RuntimeEvaluation):
+    name = "uncertainty_estimating_runtime"
+
+    def _call(self, model, data):
+        return model(data, return_ue=True)
+
+    def evaluate(self, model, id_data: tuple, ood_data: tuple) -> dict:
+        return self._runtime(model, id_data, ood_data)
+
+
+class BaseModelThroughputEvaluation(RuntimeEvaluation):
+    """Samples per second of the plain forward: mean and std over the trials of
+    ``total_samples / seconds`` (reference ``evaluation.py:475-492``)."""
+    name = "base_model_throughput"
+
+    def _call(self, model, data):
+        return model(data)
+
+    def evaluate(self, model, id_data: tuple, ood_data: tuple) -> dict:
+        seconds = self._seconds_per_call(model, id_data, ood_data)
+        rate = (id_data[0].shape[0] + ood_data[0].shape[0]) / seconds
+        return {self.name: float(np.mean(rate)), 'throughput_std': float(np.std(rate))}
+
+
+class UncertaintyEstimatingThroughputEvaluation(BaseModelThroughputEvaluation):
+    """The reference's own definition of UQ throughput (``evaluation.py:494-516``): samples per
+    second of ``model(x, return_ue=True)``."""
+    name = "uncertainty_estimating_throughput"
+
+    def _call(self, model, data):
+        return model(data, return_ue=True)
+
+    @classmethod
+    def get_objectives(cls):
+        return [{"name": cls.name, "type": "maximize"}]
+
+    @classmethod
+    def get_metrics(cls):
+        return [cls.name]
+
+    @classmethod
+    def get_name(cls):
+        return cls.name
+
+
 class MetricEvaluator:
     """Unified evaluator over several metrics (reference ``evaluation.py:666-697``).
 
@@ -455,10 +624,8 @@ class MetricEvaluator:
 _DISTANCE_METRICS = {
     WassersteinEvaluation.name: WassersteinEvaluation,
     JensenShannonEvaluation.name: JensenShannonEvaluation,
+    EuclideanEvaluation.name: EuclideanEvaluation,
 }
-# names the reference's factories also know (evaluation.py:700-812) but that are not built here
-_NOT_BUILT = ("euclidean_distance", "runtime", "uncertainty_estimating_runtime",
-              "uncertainty_estimating_throughput", "base_model_throughput", "max_memory_usage")
 
 
 def _create_single_evaluator(metric_config: dict) -> EvaluationMetric:
@@ -480,9 +647,17 @@ def _create_single_evaluator(metric_config: dict) -> EvaluationMetric:
         return PercentileScoreEvaluation.from_config(metric_config)
     if name == 'auroc':
         return AUROC()
-    if name in _NOT_BUILT:
-        raise ValueError(f"metric '{name}' is not built in nnueehcs_b200 (outside the accelerated "
-                         "hot path); use the reference's evaluator for it")
+    if name == 'runtime':
+        kwargs = {}
+        if 'trials' in metric_config:
+            kwargs['num_trials'] = metric_config['trials']
+        if 'warmup' in metric_config:
+            kwargs['num_warmup'] = metric_config['warmup']
+        return BaseModelRuntimeEvaluation(**kwargs)
+    if name == 'uncertainty_estimating_runtime':
+        return UncertaintyEstimatingRuntimeEvaluation()
+    if name == 'uncertainty_estimating_throughput':
+        return UncertaintyEstimatingThroughputEvaluation.from_config(metric_config)
     raise ValueError(f"Invalid metric type: {name}")
 
 
@@ -510,6 +685,17 @@ def get_evaluator(config) -> MetricEvaluator:
             metrics.append(PercentileBasedClassifier(c['threshold'], c.get('reversed', False)))
         elif name == 'tnr_at_tpr':
             metrics.append(TNRatTPX.from_config(c))
-        else:
+        elif name == 'runtime':
+            metrics.append(BaseModelRuntimeEvaluation.from_config(c))
+        elif name == 'uncertainty_estimating_runtime':
+            metrics.append(UncertaintyEstimatingRuntimeEvaluation.from_config(c))
+        elif name == 'base_model_throughput':
+            metrics.append(BaseModelThroughputEvaluation.from_config(c))
+        elif name == 'uncertainty_estimating_throughput':
+            metrics.append(UncertaintyEstimatingThroughputEvaluation.from_config(c))
+        elif name == 'max_memory_usage':
+            metrics.append(MaxMemoryUsageEvaluation())
+        elif name in ('mean_score', 'max_score', 'percentile_score', 'auroc'):
             metrics.append(_create_single_evaluator(c))
+        # other names: skipped, as the reference's get_evaluator does (evaluation.py:700-743)
     return MetricEvaluator(metrics)

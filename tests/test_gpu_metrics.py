@@ -820,3 +820,21 @@ def test_metric_evaluator_reads_distance_metrics_behind_one_synchronisation():
     assert r["jensen_shannon_distance"] == ops.kde_jsd(xi[:, 0], xo[:, 0], 20000)
     assert isinstance(r["wasserstein_distance"], float) and "auroc" in r
     assert list(r)[:2] == ["wasserstein_distance", "jensen_shannon_distance"]
+
+
+def test_runtime_throughput_and_memory_metrics_on_a_uq_model():
+    """The reference's own throughput definition (evaluation.py:494-516) and its memory metric
+    (:383-411) over the fused MC-dropout forward."""
+    from nnueehcs_b200 import model_builder as mb
+    arch = [{"Linear": {"args": [5, 128]}}, {"ReLU": {"inplace": True}},
+            {"Linear": {"args": [128, 128]}}, {"ReLU": {"inplace": True}}, {"Linear": {"args": [128, 1]}}]
+    torch.manual_seed(0)
+    model = mb.MCDropoutModelBuilder(arch, {"num_samples": 20, "dropout_percent": 0.2}).build().to(DEV)
+    idd, ood = (torch.rand(3000, 5, device=DEV), None), (torch.rand(2000, 5, device=DEV) + 0.5, None)
+    ev = evaluation.get_evaluator([{"name": "uncertainty_estimating_throughput", "trials": 3, "warmup": 2},
+                                   {"name": "uncertainty_estimating_runtime", "trials": 2, "warmup": 0},
+                                   {"name": "max_memory_usage"}, {"name": "wasserstein"}])
+    r = ev.evaluate(model, idd, ood)
+    assert r["uncertainty_estimating_throughput"] > 1e4 and r["throughput_std"] >= 0
+    assert 0 < r["runtime"] < 1.0 and r["max_memory_usage"] > 0
+    assert r["wasserstein_distance"] >= 0

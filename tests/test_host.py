@@ -220,6 +220,86 @@ def test_kde_builder_and_wrapper_contract(descr):
     assert sil.kde["bandwidth_"] == pytest.approx((50 * 18 / 4) ** (-1 / 20))
 
 
+def test_runtime_and_throughput_metrics_protocol():
+    """Reference evaluation.py:413-516: warm-ups untimed, every timed trial is one call on the
+    concatenated ID + OOD inputs; runtime = mean / std of the seconds, throughput = mean / std of
+    samples / seconds; the UQ variants call model(x, return_ue=True)."""
+    calls = []
+
+    class Fake(torch.nn.Module):
+        def forward(self, x, return_ue=False):
+            calls.append((x.shape[0], return_ue, self.training))
+            return (x, x[:, 0]) if return_ue else x
+
+    idd, ood = (torch.zeros(30, 2), None), (torch.ones(12, 2), None)
+    m = Fake().train()
+    r = evaluation.UncertaintyEstimatingRuntimeEvaluation(num_trials=3, num_warmup=2).evaluate(m, idd, ood)
+    assert set(r) == {"runtime", "runtime_std"} and r["runtime"] > 0 and r["runtime_std"] >= 0
+    assert calls == [(42, True, False)] * 5          # eval mode, 2 warm-ups + 3 trials
+    calls.clear()
+    r = evaluation.BaseModelThroughputEvaluation(num_trials=2, num_warmup=0).evaluate(m, idd, ood)
+    assert set(r) == {"base_model_throughput", "throughput_std"} and calls == [(42, False, False)] * 2
+    assert r["base_model_throughput"] > 0
+    r = evaluation.UncertaintyEstimatingThroughputEvaluation.from_config({"trials": 2, "warmup": 1}) \
+        .evaluate(m, idd, ood)
+    assert set(r) == {"uncertainty_estimating_throughput", "throughput_std"}
+    assert evaluation.UncertaintyEstimatingThroughputEvaluation.get_objectives() == [
+        {"name": "uncertainty_estimating_throughput", "type": "maximize"}]
+    assert evaluation.BaseModelRuntimeEvaluation.get_metrics() == ["base_model_runtime", "runtime_std"]
+    with pytest.raises(NotImplementedError):
+        evaluation.RuntimeEvaluation().evaluate(m, idd, ood)
+    # EuclideanEvaluation: mean over rows of the L2 norm of the paired difference
+    a = evaluation.UncertaintyEstimate(torch.tensor([[3.0, 4.0], [0.0, 0.0]]))
+    b = evaluation.UncertaintyEstimate(torch.tensor([[0.0, 0.0], [6.0, 8.0]]))
+    assert evaluation.EuclideanEvaluation()._evaluate_uncertainties(a, b) == {"euclidean_distance": 7.5}
+
+
+def test_host_side_metrics_have_the_reference_interface():
+    """Where /root/reference is present (the authoring container): the mirrored host-side metric
+    classes expose the reference's names, result keys, objectives, metric lists and factory
+    behaviour (evaluation.py:205-227, :383-516, :700-812)."""
+    from oracle import shims
+    if not shims.reference_available():
+        pytest.skip("reference tree not present")
+    _, _, ref = shims.import_reference()
+
+    class Fake(torch.nn.Module):
+        def forward(self, x, return_ue=False):
+            return (x, x[:, 0]) if return_ue else x
+
+    idd, ood = (torch.rand(20, 3), None), (torch.rand(20, 3), None)
+    for cls_name in ("BaseModelRuntimeEvaluation", "UncertaintyEstimatingRuntimeEvaluation",
+                     "BaseModelThroughputEvaluation", "UncertaintyEstimatingThroughputEvaluation"):
+        mine, theirs = getattr(evaluation, cls_name), getattr(ref, cls_name)
+        assert mine.name == theirs.name
+        assert mine.get_objectives() == theirs.get_objectives()
+        assert mine.get_metrics() == theirs.get_metrics()
+        a, b = mine(num_trials=2, num_warmup=1), theirs(num_trials=2, num_warmup=1)
+        assert a.get_name() == b.get_name()
+        if torch.cuda.is_available():      # the reference synchronises the device unconditionally
+            assert set(a.evaluate(Fake(), idd, ood)) == set(b.evaluate(Fake(), idd, ood))
+    assert evaluation.MaxMemoryUsageEvaluation.name == ref.MaxMemoryUsageEvaluation.name
+    assert (evaluation.MaxMemoryUsageEvaluation().get_objectives()
+            == ref.MaxMemoryUsageEvaluation().get_objectives())
+    ua = torch.rand(17, 4)
+    ub = torch.rand(17, 4)
+    got = evaluation.EuclideanEvaluation()._evaluate_uncertainties(
+        evaluation.UncertaintyEstimate(ua), evaluation.UncertaintyEstimate(ub))
+    exp = ref.EuclideanEvaluation()._evaluate_uncertainties(ref.UncertaintyEstimate(ua),
+                                                            ref.UncertaintyEstimate(ub))
+    assert got == exp
+    cfg = [{"name": "uncertainty_estimating_throughput", "trials": 3, "warmup": 2},
+           {"name": "runtime", "trials": 4}, {"name": "max_memory_usage"}, {"name": "mean_score"}]
+    mine, theirs = evaluation.get_evaluator(cfg), ref.get_evaluator(cfg)
+    assert [type(m).__name__ for m in mine.metrics] == [type(m).__name__ for m in theirs.metrics]
+    assert [(getattr(m, "num_trials", None), getattr(m, "num_warmup", None)) for m in mine.metrics] \
+        == [(getattr(m, "num_trials", None), getattr(m, "num_warmup", None)) for m in theirs.metrics]
+    ucfg = [{"name": "runtime", "trials": 4}, "uncertainty_estimating_runtime", "euclidean_distance",
+            {"name": "uncertainty_estimating_throughput", "warmup": 1}]
+    mine, theirs = evaluation.get_uncertainty_evaluator(ucfg), ref.get_uncertainty_evaluator(ucfg)
+    assert [type(m).__name__ for m in mine.metrics] == [type(m).__name__ for m in theirs.metrics]
+
+
 def test_split_blocks_vocabulary(descr):
     net = MCDropoutModelBuilder(descr["architecture_mlp4"], descr["mc_dropout_model"]).build().model
     blocks = extract.split_blocks(net)
@@ -308,8 +388,21 @@ def test_evaluator_factories():
     assert ev.get_training_objectives()[0] == {"name": "wasserstein_distance", "type": "maximize"}
     assert isinstance(evaluation.get_evaluator({"name": "wasserstein"}).metrics[0],
                       evaluation.WassersteinEvaluation)
-    with pytest.raises(ValueError, match="not built"):
-        evaluation.get_uncertainty_evaluator("runtime")
+    # the host-side metrics the reference's configs name (evaluation.py:383-516, :205-227)
+    ev = evaluation.get_uncertainty_evaluator(
+        [{"name": "runtime", "trials": 3, "warmup": 1}, "uncertainty_estimating_runtime",
+         {"name": "uncertainty_estimating_throughput", "trials": 4}, "euclidean_distance"])
+    assert [type(m).__name__ for m in ev.metrics] == [
+        "BaseModelRuntimeEvaluation", "UncertaintyEstimatingRuntimeEvaluation",
+        "UncertaintyEstimatingThroughputEvaluation", "EuclideanEvaluation"]
+    assert (ev.metrics[0].num_trials, ev.metrics[0].num_warmup) == (3, 1)
+    assert (ev.metrics[2].num_trials, ev.metrics[2].num_warmup) == (4, 5)
+    ev = evaluation.get_evaluator([{"name": "uncertainty_estimating_throughput", "trials": 2},
+                                   {"name": "base_model_throughput"}, {"name": "max_memory_usage"},
+                                   {"name": "runtime"}, {"name": "no_such_metric"}])
+    assert [m.get_name() for m in ev.metrics] == [
+        "uncertainty_estimating_throughput", "base_model_throughput", "max_memory_usage",
+        "base_model_runtime"]      # unknown names are skipped by this factory, as in the reference
     ev = evaluation.get_uncertainty_evaluator(
         ["auroc", "mean_score", "max_score", {"name": "percentile_score", "percentile": 90.0},
          {"name": "tnr_at_tpr", "target_tpr": 0.95},
