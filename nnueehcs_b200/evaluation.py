@@ -180,8 +180,17 @@ class JensenShannonEvaluation(UncertaintyEvaluationMetric):
     def _average_js_distance(self, p1, p2) -> float:
         if isinstance(p1, torch.Tensor) and (p1.dim() == 1 or (p1.dim() == 2 and p1.shape[1] == 1)):
             return self.pdf_jsd(p1.reshape(-1), p2.reshape(-1))
-        raise ValueError("JensenShannonEvaluation: only 1-D (or [N, 1]) uncertainty scores are on "
-                         "the accelerated path")
+        if isinstance(p1, torch.Tensor) and isinstance(p2, torch.Tensor) and p1.dim() == 2:
+            # [N, d > 1] scores: the reference's other branch (evaluation.py:263-266) -- the mean
+            # over rows of scipy's jensenshannon(p1[i], p2[i]) on the raw score rows.  N x d scalar
+            # work with no kernel behind it in the reference either: done on the host.
+            a = p1.detach().cpu().numpy().astype(np.float64)
+            b = p2.detach().cpu().numpy().astype(np.float64)
+            if a.shape != b.shape:
+                raise ValueError(f"operands could not be broadcast together with shapes "
+                                 f"{a.shape} {b.shape}")
+            return float(np.mean(_jensenshannon_rows(a, b)))
+        raise ValueError("JensenShannonEvaluation: scores must be a 1-D or 2-D tensor")
 
     def _enqueue_uncertainties(self, id_ue, ood_ue):
         """See ``WassersteinEvaluation._enqueue_uncertainties``."""
@@ -209,6 +218,26 @@ class JensenShannonEvaluation(UncertaintyEvaluationMetric):
 
     def get_name(self):
         return self.name
+
+
+def _jensenshannon_rows(p: np.ndarray, q: np.ndarray) -> np.ndarray:
+    """``scipy.spatial.distance.jensenshannon(p[i], q[i])`` for every row (natural log): rows
+    normalised to sum 1, m = (p + q) / 2, sqrt((KL(p || m) + KL(q || m)) / 2), with scipy's
+    ``rel_entr`` conventions (0 where p == 0 and m >= 0, inf where a term is undefined)."""
+    p = p / p.sum(axis=1, keepdims=True)
+    q = q / q.sum(axis=1, keepdims=True)
+    m = (p + q) / 2.0
+
+    def rel_entr(x, y):
+        out = np.full(x.shape, np.inf)
+        pos = (x > 0) & (y > 0)
+        out[pos] = x[pos] * np.log(x[pos] / y[pos])
+        out[(x == 0) & (y >= 0)] = 0.0
+        out[np.isnan(x) | np.isnan(y)] = np.nan
+        return out
+
+    js = rel_entr(p, m).sum(axis=1) + rel_entr(q, m).sum(axis=1)
+    return np.sqrt(js / 2.0)
 
 
 def _scores_1d(ue: UncertaintyEstimate) -> torch.Tensor:

@@ -248,6 +248,15 @@ def test_runtime_and_throughput_metrics_protocol():
     assert evaluation.BaseModelRuntimeEvaluation.get_metrics() == ["base_model_runtime", "runtime_std"]
     with pytest.raises(NotImplementedError):
         evaluation.RuntimeEvaluation().evaluate(m, idd, ood)
+    # JensenShannonEvaluation on [N, d > 1] scores: mean of jensenshannon(p[i], q[i]) over rows
+    from oracle import metrics_oracle
+    rng = np.random.default_rng(0)
+    pa, pb = rng.random((7, 5)).astype(np.float32), rng.random((7, 5)).astype(np.float32)
+    exp = np.mean([metrics_oracle.jensenshannon(pa[i], pb[i]) for i in range(7)])
+    got = evaluation.JensenShannonEvaluation()._evaluate_uncertainties(
+        evaluation.UncertaintyEstimate(torch.from_numpy(pa)),
+        evaluation.UncertaintyEstimate(torch.from_numpy(pb)))["jensen_shannon_distance"]
+    assert got == pytest.approx(exp, rel=1e-12)
     # EuclideanEvaluation: mean over rows of the L2 norm of the paired difference
     a = evaluation.UncertaintyEstimate(torch.tensor([[3.0, 4.0], [0.0, 0.0]]))
     b = evaluation.UncertaintyEstimate(torch.tensor([[0.0, 0.0], [6.0, 8.0]]))
@@ -288,6 +297,15 @@ def test_host_side_metrics_have_the_reference_interface():
     exp = ref.EuclideanEvaluation()._evaluate_uncertainties(ref.UncertaintyEstimate(ua),
                                                             ref.UncertaintyEstimate(ub))
     assert got == exp
+    # JensenShannonEvaluation on [N, d > 1] scores: mean of scipy's jensenshannon over the rows
+    pa, pb = torch.rand(9, 4) + 0.1, torch.rand(9, 4) + 0.1
+    pa[0, 1] = 0.0
+    got = evaluation.JensenShannonEvaluation()._evaluate_uncertainties(
+        evaluation.UncertaintyEstimate(pa), evaluation.UncertaintyEstimate(pb))
+    exp = ref.JensenShannonEvaluation()._evaluate_uncertainties(ref.UncertaintyEstimate(pa),
+                                                                ref.UncertaintyEstimate(pb))
+    assert got["jensen_shannon_distance"] == pytest.approx(float(exp["jensen_shannon_distance"]),
+                                                           rel=1e-6)
     cfg = [{"name": "uncertainty_estimating_throughput", "trials": 3, "warmup": 2},
            {"name": "runtime", "trials": 4}, {"name": "max_memory_usage"}, {"name": "mean_score"}]
     mine, theirs = evaluation.get_evaluator(cfg), ref.get_evaluator(cfg)
