@@ -10,6 +10,7 @@ import os
 import pickle
 import re
 
+import numpy as np
 import pytest
 import torch
 import torch.nn as nn
