@@ -13,8 +13,9 @@ all become one call into ``libnnueehcs_b200.so`` (``ops.PackedModel.forward``). 
 fallback: an eval-mode forward on a non-CUDA tensor raises ``RuntimeError``.
 
 Knobs that do not exist in the reference (all optional, attributes on the wrapper):
-``uq_precision``  ``'fp32'`` (default; CUDA-core FFMA, the 1e-5 parity mode) or ``'bf16'``
-                  (tcgen05 tensor-core mode); default overridable with ``NNUEEHCS_B200_PRECISION``.
+``uq_precision``  ``'fp32'`` (default; the 1e-5 parity mode: scaled fp16 x 2 split on tcgen05,
+                  CUDA-core FFMA for shapes the split kernels do not cover) or ``'bf16'`` (tcgen05
+                  tensor-core mode); default overridable with ``NNUEEHCS_B200_PRECISION``.
 ``uq_shard``      optional ``distributed.KShard`` -- shard members/passes/anchors over ranks.
 """
 from __future__ import annotations

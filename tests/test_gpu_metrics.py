@@ -838,3 +838,41 @@ def test_runtime_throughput_and_memory_metrics_on_a_uq_model():
     assert r["uncertainty_estimating_throughput"] > 1e4 and r["throughput_std"] >= 0
     assert 0 < r["runtime"] < 1.0 and r["max_memory_usage"] > 0
     assert r["wasserstein_distance"] >= 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """dynamic shared-memory opt-ins are per device.  Every kernel family runs on
+    cuda:0 first and then on cuda:1 in the same process; the results must be identical."""
+    from nnueehcs_b200 import model_builder as mb
+    rng = np.random.default_rng(11)
+    u = rng.gamma(2.0, 0.05, 3_000_017).astype(np.float32)
+    v = rng.gamma(3.0, 0.08, 2_500_003).astype(np.float32)
+    arch = [{"Linear": {"args": [5, 128]}}, {"BatchNorm1d": {"args": [128]}}, {"ReLU": {"inplace": True}},
+            {"Linear": {"args": [128, 128]}}, {"ReLU": {"inplace": True}}, {"Linear": {"args": [128, 1]}}]
+    torch.manual_seed(3)
+    model = mb.EnsembleModelBuilder(arch, {"num_models": 4}).build().eval()
+    x = torch.rand(5000, 5)
+    out = []
+    for idx in (0, 1):
+        dev = torch.device("cuda", idx)
+        ud, vd = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
+        with torch.cuda.device(dev):
+            pend = [ops.wasserstein_1d_async(ud, vd), ops.kde_jsd_async(ud, vd, 5000)]
+            res = [ops.wasserstein_1d(ud, vd), ops.wasserstein_1d(ud, vd, "sort"),
+                   ops.kde_jsd(ud, vd, 5000), ops.kde_jsd(ud[:200_000], vd[:200_000], 2000, "window"),
+                   ops.score_metrics(ud, vd)["auroc"], [p.result() for p in pend],
+                   ops.sort_f32(ud).cpu().numpy().tobytes(),
+                   ops.kde_density(torch.rand(3000, 5, generator=torch.Generator().manual_seed(1)).to(dev),
+                                   x[:512].to(dev), 0.3).cpu().numpy().tobytes()]
+            model.to(dev)
+            with torch.no_grad():
+                for prec in ("fp32", "bf16"):
+                    model.uq_precision = prec
+                    mean, std = model(x.to(dev), return_ue=True)
+                    res.append((mean.cpu().numpy().tobytes(), std.cpu().numpy().tobytes()))
+        out.append(res)
+    # the window KDE adds into its grid with float64 atomics: last-digit differences between runs
+    assert out[0][3] == pytest.approx(out[1][3], rel=1e-12)
+    out[0][3] = out[1][3] = None
+    assert out[0] == out[1]
