@@ -167,6 +167,9 @@ struct TcPlan {
   int n_tile = 0;                // MMA N per stage (H if H <= 256 else 256)
   int stages_per_member = 0;
   __nv_bfloat16* image = nullptr;  // [K][stages_per_member][stage_bytes]
+  // bias stages of mlp_tc2.cu's bias-in-the-MMA variant: [K][n_mma_layers][H / n_tile] stages whose
+  // K columns 0..2 hold the folded bias of the stage's N rows as bf16 hi + mid + lo
+  __nv_bfloat16* bias_image = nullptr;
   float* w_last = nullptr;         // [K][d_out][H] fp32 (dropout scale NOT folded; see kernel)
   float* b_last = nullptr;         // [K][d_out]
   // Delta-UQ variant of the image (single network with an even input width): layer 0 holds only

@@ -80,6 +80,31 @@ __global__ void fold_bias_kernel(const float* __restrict__ bias, const float* __
   out[i] = b;
 }
 
+// Bias stages of mlp_tc2.cu's bias-in-the-MMA variant: stage (k, l, nh) is a zeroed [n_tile x 64]
+// SW128 stage whose row r carries the folded bias of output feature nh * n_tile + r as three bf16
+// pieces (hi + mid + lo == the fp32 bias to 24 bits) in K columns 0..2; the kernel multiplies it by
+// an all-ones A tile as one K = 16 step, which leaves acc + bias in the accumulator.
+__global__ void pack_bias_image_kernel(__nv_bfloat16* __restrict__ image,
+                                       const float* __restrict__ bias_folded, int K, int l,
+                                       int L_mma, int H, int n_tile, size_t stage_elems) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * H) return;
+  const int k = i / H, n = i % H;
+  const int nh = n / n_tile, r = n % n_tile;
+  const int NH = H / n_tile;
+  const float b = bias_folded[(size_t)k * H + n];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+  const float r1 = b - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  uint8_t* dst = reinterpret_cast<uint8_t*>(image + ((size_t)(k * L_mma + l) * NH + nh) * stage_elems) +
+                 sw128_offset(r, 0);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+  d[0] = hi;
+  d[1] = mid;
+  d[2] = lo;
+}
+
 // padded outputs of the last Linear: zero rows / zero bias beyond d_out
 __global__ void pad_last_kernel(const float* __restrict__ w, const float* __restrict__ b,
                                 float* __restrict__ w_out, float* __restrict__ b_out, int K,
@@ -252,6 +277,19 @@ int tc_pack(uq_model* m, cudaStream_t st) {
                                                      ly.bias_folded, n);
     UQ_LAUNCH_CHECK();
   }
+  if (tc2_supported(H)) {   // bias stages (mlp_tc2.cu, bias-in-the-MMA variant)
+    void* pb = nullptr;
+    const size_t bias_elems = (size_t)K * t.n_mma_layers * NH * stage_elems;
+    UQ_CUDA(cudaMalloc(&pb, bias_elems * sizeof(__nv_bfloat16)));
+    m->allocations.push_back(pb);
+    t.bias_image = static_cast<__nv_bfloat16*>(pb);
+    UQ_CUDA(cudaMemsetAsync(pb, 0, bias_elems * sizeof(__nv_bfloat16), st));
+    for (int l = 0; l < t.n_mma_layers; ++l) {
+      pack_bias_image_kernel<<<(K * H + 255) / 256, 256, 0, st>>>(
+          t.bias_image, m->layers[l].bias_folded, K, l, t.n_mma_layers, H, t.n_tile, stage_elems);
+      UQ_LAUNCH_CHECK();
+    }
+  }
   // last Linear, padded to the kernel's compile-time output count
   const Layer& last = m->layers[m->n_layers - 1];
   const int dpad = dout_pad(t.d_out);
@@ -374,6 +412,10 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.stages_per_member = t.stages_per_member;
   p.shared_weights = (a->mode != UQ_MODE_ENSEMBLE) ? 1 : 0;
   p.image = reinterpret_cast<const uint8_t*>(t.image);
+  // the bias rides in the MMA only where the epilogue's accumulator scale is 1 (no live dropout)
+  // and the layer-0 bias is the packed one (no anchors); mlp_tc2.cu checks the rest
+  p.bias_image = (!split && a->mode != UQ_MODE_DELTA_UQ && a->mode != UQ_MODE_PAGER)
+                     ? reinterpret_cast<const uint8_t*>(t.bias_image) : nullptr;
   if (split) {  // fp32-parity split mode: its own image, three input segments always
     p.K0 = ((3 * t.d_in + 15) / 16) * 16 + 16;   // + the all-zero step (see mlp_tcx.cu)
     p.split_s = 3;

@@ -44,7 +44,9 @@ constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
 
 // NG = epilogue warp groups (4 warps each, one per TMEM lane quarter); group j drains the
 // activation chunks c with c % NG == j.
-template <int H, int DOUT, int NG>
+// BIAS: the folded bias is accumulated by the tensor core (one extra K = 16 MMA per layer and
+// accumulator half: an all-ones A tile against a bias stage of the ring), not added by the epilogue.
+template <int H, int DOUT, int NG, bool BIAS = false>
 struct Geo2 {
   static constexpr int EPI_THREADS = NG * 128;
   static constexpr int NUM_THREADS = 64 + EPI_THREADS;
@@ -57,17 +59,20 @@ struct Geo2 {
   static constexpr int STAGE_BYTES = NT * 128;           // whole stage [NT x 64] bf16 in the image
   static constexpr int HALF_BYTES = STAGE_BYTES / 2;     // what one CTA of the pair loads
   static constexpr int A_BYTES = KC * CHUNK_BYTES;
-  static constexpr int AUX_FLOATS = (DOUT == 1 ? 2 : 1) * H;   // bias [+ w_last] of one step
+  static constexpr int WL_OFF = BIAS ? 0 : H;                  // w_last inside a step's aux block
+  static constexpr int AUX_FLOATS = WL_OFF + (DOUT == 1 ? H : 0);   // [bias] [+ w_last] of one step
+  static constexpr int ONES_BYTES = BIAS ? CONST_TILE_BYTES : 0;
   static constexpr int AUX_BYTES = 2 * AUX_FLOATS * 4;         // double-buffered by step parity
   static constexpr int XCHG_BYTES = 2 * (NG - 1) * TILE_M * DOUT * 4;
   static constexpr int XS_BYTES = TILE_M * 64;   // stash of the next layer-0 A rows (K0 <= 32)
   static constexpr int MISC_BYTES =
       1024 /*align slack*/ + 256 /*barriers*/ + XCHG_BYTES + XS_BYTES;
-  static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES;
+  static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES - ONES_BYTES;
   static constexpr int NS_RAW = BUDGET / HALF_BYTES;
   static constexpr int NSTAGES = NS_RAW > 8 ? 8 : NS_RAW;
   static_assert(NSTAGES >= 2, "not enough shared memory for a weight ring");
-  static constexpr int SMEM_BYTES = A_BYTES + NSTAGES * HALF_BYTES + AUX_BYTES + MISC_BYTES;
+  static constexpr int SMEM_BYTES =
+      A_BYTES + NSTAGES * HALF_BYTES + ONES_BYTES + AUX_BYTES + MISC_BYTES;
   __host__ __device__ static constexpr int hi(int nh) { return ((nh + 1) * NT + CHUNK_K - 1) / CHUNK_K - 1; }
 };
 
@@ -145,7 +150,7 @@ __device__ __forceinline__ void compute_keep_words(const TcParams& p, const Drai
 // 32-column block ahead in a second register buffer.  NG == 4: 16 epilogue warps (4 per
 // scheduler) hide the tcgen05.ld / LDS latencies by thread-level parallelism instead, within the
 // 112-register budget that 18 warps leave.
-template <int H, int DOUT, int NG, bool RELU, bool DROP, bool LAST>
+template <int H, int DOUT, int NG, bool RELU, bool DROP, bool LAST, bool BIAS = false>
 __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx, int c_begin,
                                            const KeepWords<H, NG>& kw, float (&dot)[DOUT]) {
   constexpr int KC = H / CHUNK_K;
@@ -157,22 +162,26 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
       const uint32_t a_dst = cx.a_row + (uint32_t)c * CHUNK_BYTES;
       float4 bv[8];
       // ---- block 0 (columns col0 .. col0+31) ----
+      if (!BIAS) {
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
+        for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
+      }
       UQ_DTRACE(10, c);
       tmem_ld_wait();
       UQ_DTRACE(11, c);
       tmem_ld32(cx.lane_addr + (uint32_t)(col0 + 32), acc1);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep0, cx.in_scale, a_dst, 0, cx.rx,
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST, BIAS>(acc0, bv, keep0, cx.in_scale, a_dst, 0, cx.rx,
                                             cx.wl_s + col0, cx.wl_g + col0, dot);
       UQ_DTRACE(12, c);
       // ---- block 1 (columns col0+32 .. col0+63) ----
+      if (!BIAS) {
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0 + 32)[j4];
+        for (int j4 = 0; j4 < 8; ++j4)
+          bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0 + 32)[j4];
+      }
       tmem_ld_wait();
       if (c + NG < KC) tmem_ld32(cx.lane_addr + (uint32_t)(col0 + NG * CHUNK_K), acc0);
-      epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep1, cx.in_scale, a_dst, 4, cx.rx,
+      epi_block2<H, DOUT, 32, RELU, DROP, LAST, BIAS>(acc1, bv, keep1, cx.in_scale, a_dst, 4, cx.rx,
                                             cx.wl_s + col0 + 32, cx.wl_g + col0 + 32, dot);
       UQ_DTRACE(13, c);
       // chunk c: accumulator columns drained (+ A chunk rewritten) -> release to the MMA warp
@@ -228,10 +237,11 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
 // MC: the launch has live dropout (MC-dropout passes).  The dropout-free instantiation carries no
 // mask code at all -- the headline ensemble kernel keeps its 162 registers and zero spills whatever
 // the dropout path needs (keep words live across the layer barrier wait).
-template <int H, int DOUT, int NG, bool MC>
-__global__ void __launch_bounds__(Geo2<H, DOUT, NG>::NUM_THREADS, 1)
+template <int H, int DOUT, int NG, bool MC, bool BIAS = false>
+__global__ void __launch_bounds__(Geo2<H, DOUT, NG, BIAS>::NUM_THREADS, 1)
 uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
-  using G = Geo2<H, DOUT, NG>;
+  static_assert(!BIAS || (!MC && NG == 2 && DOUT == 1), "bias-in-the-MMA variant: NG 2, d_out 1, no dropout");
+  using G = Geo2<H, DOUT, NG, BIAS>;
   constexpr int EPI_THREADS = G::EPI_THREADS;
   constexpr int KC = G::KC, NH = G::NH, NT = G::NT, NS = G::NSTAGES;
   constexpr uint32_t STAGE_BYTES = G::STAGE_BYTES, HALF_BYTES = G::HALF_BYTES;
@@ -243,7 +253,8 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                  // KC chunks of 16 KB
   uint8_t* w_smem = smem + G::A_BYTES;                     // NS half-stages
-  float* aux_smem = reinterpret_cast<float*>(w_smem + NS * HALF_BYTES);  // [2][AUX_FLOATS]
+  uint8_t* ones_smem = w_smem + NS * HALF_BYTES;           // BIAS: constant-1 A tile (bf16)
+  float* aux_smem = reinterpret_cast<float*>(ones_smem + G::ONES_BYTES);  // [2][AUX_FLOATS]
   uint8_t* bar_smem = reinterpret_cast<uint8_t*>(aux_smem) + G::AUX_BYTES;
   const uint32_t xchg = smem_u32(bar_smem + 256);  // [2][NG-1][128][DOUT] dot exchange (floats)
   const uint32_t xstash = xchg + G::XCHG_BYTES;    // [K0/8 pieces][128 rows] x 16 B
@@ -285,6 +296,11 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(bars + BAR_TMEM_PTR, (uint32_t)G::TMEM_COLS);
+  if (BIAS) {   // the all-ones A tile of the bias MMAs (read by the tensor core: async proxy)
+    for (int i = threadIdx.x; i < G::ONES_BYTES / 4; i += G::NUM_THREADS)
+      reinterpret_cast<uint32_t*>(ones_smem)[i] = 0x3F803F80u;   // bf16 (1.0, 1.0)
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -304,13 +320,26 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           const uint8_t* src =
               p.image + (p.shared_weights ? 0 : (size_t)(p.member_begin + k) * member_bytes) +
               rank * HALF_BYTES;
-          for (int s = 0; s < p.stages_per_member; ++s) {
+          auto load = [&](const uint8_t* from) {
             mbar_wait(bars + BAR_W_EMPTY + 8 * slot, phase ^ 1, p.error_flag, 1);
             mbar_arrive_expect_tx(bars + BAR_W_FULL + 8 * slot, HALF_BYTES);
-            bulk_g2s(w_base + slot * HALF_BYTES, src, HALF_BYTES, bars + BAR_W_FULL + 8 * slot);
+            bulk_g2s(w_base + slot * HALF_BYTES, from, HALF_BYTES, bars + BAR_W_FULL + 8 * slot);
             if (leader) { UQ_TRACE(0, 2, tr_it++); }
-            src += STAGE_BYTES;
             if (++slot == NS) { slot = 0; phase ^= 1; }
+          };
+          if (BIAS) {   // per (layer, accumulator half): its weight stages, then its bias stage
+            const uint8_t* bsrc =
+                p.bias_image +
+                (p.shared_weights ? 0 : (size_t)(p.member_begin + k) * p.L_mma * NH * STAGE_BYTES) +
+                rank * HALF_BYTES;
+            for (int l = 0; l < p.L_mma; ++l)
+              for (int nh = 0; nh < NH; ++nh) {
+                for (int s = 0; s < (l == 0 ? 1 : KC); ++s, src += STAGE_BYTES) load(src);
+                load(bsrc);
+                bsrc += STAGE_BYTES;
+              }
+          } else {
+            for (int s = 0; s < p.stages_per_member; ++s, src += STAGE_BYTES) load(src);
           }
         }
       }
@@ -325,7 +354,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
         const int split = unit % p.splits;
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
-        const int n_stages = (me - mb) * p.stages_per_member;
+        const int n_stages = (me - mb) * (p.stages_per_member + (BIAS ? p.L_mma * NH : 0));
         for (int s = 0; s < n_stages; ++s) {
           mbar_wait(bars + BAR_W_FULL + 8 * slot, phase, p.error_flag, 6);
           mbar_arrive_cluster(full0 + 8 * slot);
@@ -342,6 +371,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
     constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, NT);
     const uint64_t a_desc0 = make_sw128_desc(a_base);
     const uint64_t b_desc0 = make_sw128_desc(w_base);
+    const uint64_t ones_desc = make_sw128_const_desc(smem_u32(ones_smem));
     const int k0_steps = p.K0 / 16;
     uint32_t slot = 0, phase = 0;
     uint32_t g = 0;      // layer-step counter (d_full / chunk phases)
@@ -362,6 +392,14 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
       slot = nslot;
       phase = nphase;
       w_ready = w_ready_next;
+    };
+    // accumulator half nh += ones . bias^T: one K = 16 step on the half's bias stage
+    auto bias_mma = [&](int nh) {
+      acquire();
+      if (elect_one())
+        umma_bf16_pair(tmem_base + nh * NT, ones_desc,
+                       b_desc0 + (uint64_t)((slot * HALF_BYTES) >> 4), idesc, 1u);
+      release();
     };
     for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
       const int split = unit % p.splits;
@@ -394,6 +432,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
                                ks > 0 ? 1u : 0u);
             }
             release();
+            if (BIAS) bias_mma(nh);
           }
           if (elect_one()) umma_commit_pair(bars + BAR_D_FULL, 3);
           UQ_TRACE(1, 4, g);
@@ -441,6 +480,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
               release();
               UQ_TRACE(1, 3, tr_it++);
             }
+            if (BIAS) bias_mma(nh);
           }
           if (elect_one()) umma_commit_pair(bars + BAR_D_FULL, 3);  // whole layer accumulated
           UQ_TRACE(1, 4, g);
@@ -506,8 +546,8 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
       for (int j = 0; j < AUX_PER_THREAD; ++j) {
         const int i = et + j * EPI_THREADS;
         float v = 0.f;
-        if (i < H) v = __ldg(bias + i);
-        else if (DOUT == 1 && last && i < 2 * H) v = __ldg(wl + (i - H));
+        if (!BIAS && i < H) v = __ldg(bias + i);
+        else if (DOUT == 1 && last && i >= G::WL_OFF && i < G::WL_OFF + H) v = __ldg(wl + (i - G::WL_OFF));
         aux_pf[j] = v;
       }
     };
@@ -579,7 +619,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           cx.lane = lane;
           cx.chunk_bar0 = chunk_bar0;
           cx.bias_s = aux;
-          cx.wl_s = aux + H;
+          cx.wl_s = aux + G::WL_OFF;
           cx.wl_g = p.w_last + (size_t)wslot * DOUT * H;
           cx.drop = drop;
           cx.kg = kg;
@@ -618,14 +658,14 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           if (last && have_next) publish_x(ntile, p.member_begin + nk);
 
           const int c_begin = grp;
-          UQ_STEP_DISPATCH((drain_step<H, DOUT, NG, true, MC, true>(p, cx, c_begin, kw, dot)),
-                           (drain_step<H, DOUT, NG, true, false, true>(p, cx, c_begin, kw, dot)),
-                           (drain_step<H, DOUT, NG, false, MC, true>(p, cx, c_begin, kw, dot)),
-                           (drain_step<H, DOUT, NG, false, false, true>(p, cx, c_begin, kw, dot)),
-                           (drain_step<H, DOUT, NG, true, MC, false>(p, cx, c_begin, kw, dot)),
-                           (drain_step<H, DOUT, NG, true, false, false>(p, cx, c_begin, kw, dot)),
-                           (drain_step<H, DOUT, NG, false, MC, false>(p, cx, c_begin, kw, dot)),
-                           (drain_step<H, DOUT, NG, false, false, false>(p, cx, c_begin, kw, dot)))
+          UQ_STEP_DISPATCH((drain_step<H, DOUT, NG, true, MC, true, BIAS>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, true, false, true, BIAS>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, false, MC, true, BIAS>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, false, false, true, BIAS>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, true, MC, false, BIAS>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, true, false, false, BIAS>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, false, MC, false, BIAS>(p, cx, c_begin, kw, dot)),
+                           (drain_step<H, DOUT, NG, false, false, false, BIAS>(p, cx, c_begin, kw, dot)))
           if (lane == 0 && (warp == 2 || (warp == 6 && leader))) { UQ_TRACE(leader ? (warp == 2 ? 2 : 3) : 4, 2, g); }
           if (has_drop) {
             if (p.masks) mask_layer += (size_t)p.total_members * (size_t)p.n * (size_t)H;
@@ -690,10 +730,19 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-template <int H, int DOUT, int NG, bool MC>
+// The bias-in-the-MMA variant is the default where it applies (ensembles and dropout-off passes,
+// d_out 1): ensemble16x512_1M 14.33 -> 13.58 ms, 0.757 -> 0.798 of the burst peak, same error
+// against the oracle (profiles/r02_j_bias_mma_*).  UQ_TC_BIAS_MMA=0 selects the epilogue-bias
+// variant for A/B runs.
+static bool bias_in_mma_enabled() {
+  const char* e = getenv("UQ_TC_BIAS_MMA");
+  return e ? e[0] == '1' : true;
+}
+
+template <int H, int DOUT, int NG, bool MC, bool BIAS = false>
 int launch_tc2_mc(const TcParams& p, cudaStream_t st) {
-  using G = Geo2<H, DOUT, NG>;
-  auto kern = uq_mlp_tc2_kernel<H, DOUT, NG, MC>;
+  using G = Geo2<H, DOUT, NG, BIAS>;
+  auto kern = uq_mlp_tc2_kernel<H, DOUT, NG, MC, BIAS>;
   // per-device launch geometry of this instantiation, queried once (the occupancy query and the
   // attribute call cost tens of microseconds, which shows on millisecond-sized forwards)
   static std::atomic<int> cached_clusters[64];   // zero-initialised; races only repeat the query
@@ -736,6 +785,8 @@ int launch_tc2_mc(const TcParams& p, cudaStream_t st) {
 template <int H, int DOUT, int NG>
 int launch_tc2(const TcParams& p, cudaStream_t st) {
   const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
+  if (DOUT == 1 && NG == 2 && !mc && p.bias_image != nullptr && bias_in_mma_enabled())
+    return launch_tc2_mc<H, 1, 2, false, true>(p, st);
   return mc ? launch_tc2_mc<H, DOUT, NG, true>(p, st) : launch_tc2_mc<H, DOUT, NG, false>(p, st);
 }
 

@@ -82,14 +82,20 @@ __device__ __forceinline__ uint32_t keep_bits32(const TcParams& p, int drop, int
 
 // One NC-column block of one accumulator row: + bias, dropout, then either ReLU + bf16 rounding
 // into NC/2 packed words (cvt.rn[.relu].bf16x2) or the last-Linear dot product.
-template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST>
+// BIAS_IN_ACC: the accumulator already holds acc + bias (mlp_tc2.cu's bias-in-the-MMA variant, which
+// only runs where in_scale == 1); bv is not read.
+template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST, bool BIAS_IN_ACC = false>
 __device__ __forceinline__ void epi_math(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
                                          uint32_t keep, float in_scale, uint32_t* packed,
                                          const float* __restrict__ wl_s,
                                          const float* __restrict__ wl_g, float (&dot)[DOUT]) {
   float v[NC];
+  if (BIAS_IN_ACC) {
 #pragma unroll
-  for (int j4 = 0; j4 < NC / 4; ++j4) {
+    for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+#pragma unroll
+  for (int j4 = 0; j4 < (BIAS_IN_ACC ? 0 : NC / 4); ++j4) {
     // in_scale = 1 / (1 - p) when the previous layer's output went through a dropout (which only
     // zeroes; the rescale rides on this FMA for free), else 1.0 -- fma(acc, 1, b) == acc + b exactly
     v[j4 * 4 + 0] = fmaf(__uint_as_float(acc[j4 * 4 + 0]), in_scale, bv[j4].x);
@@ -151,13 +157,14 @@ __device__ __forceinline__ void epi_store(const uint32_t* packed, uint32_t a_dst
   }
 }
 
-template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST>
+template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST, bool BIAS_IN_ACC = false>
 __device__ __forceinline__ void epi_block2(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
                                            uint32_t keep, float in_scale, uint32_t a_dst,
                                            int piece0, int rx, const float* __restrict__ wl_s,
                                            const float* __restrict__ wl_g, float (&dot)[DOUT]) {
   uint32_t packed[NC / 2];
-  epi_math<H, DOUT, NC, RELU, DROP, LAST>(acc, bv, keep, in_scale, packed, wl_s, wl_g, dot);
+  epi_math<H, DOUT, NC, RELU, DROP, LAST, BIAS_IN_ACC>(acc, bv, keep, in_scale, packed, wl_s, wl_g,
+                                                       dot);
   if (!LAST) epi_store<NC / 2>(packed, a_dst, piece0, rx);
 }
 

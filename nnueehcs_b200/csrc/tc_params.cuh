@@ -29,6 +29,10 @@ struct TcParams {
   int shared_weights;
   int bias0_per_member;  // layer-0 bias is indexed by the global member id (Delta-UQ anchors)
   const uint8_t* image;
+  // mlp_tc2.cu, bias-in-the-MMA variant: per weight slot, one stage [N x 64] bf16 per (layer,
+  // accumulator half) whose K columns 0..2 hold the folded bias as bf16 hi + mid + lo; null = the
+  // epilogue adds the bias
+  const uint8_t* bias_image;
   const float* bias[MAX_MMA_LAYERS];  // [K or 1][H] folded bias per MMA layer
   uint32_t relu_mask, dropout_mask;   // bit l: MMA layer l has ReLU / dropout on its output
   const float* w_last;                // [K or 1][DOUT][H]  (zero rows beyond d_out)

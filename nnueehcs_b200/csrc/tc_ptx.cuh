@@ -155,6 +155,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same descriptor with an 8-row-group stride of 256 B over a region filled with one constant:
+// a [128 x 16] "all ones" A operand in 15 * 256 + 1024 = 4864 bytes (the row groups overlap; the
+// swizzle only permutes 16-byte pieces inside a 128-byte line, so every read stays in the region).
+constexpr int CONST_TILE_BYTES = 15 * 256 + 1024;
+__device__ __forceinline__ uint64_t make_sw128_const_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=F32, A=B=BF16, K-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
