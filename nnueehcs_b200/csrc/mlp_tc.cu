@@ -80,29 +80,36 @@ __global__ void fold_bias_kernel(const float* __restrict__ bias, const float* __
   out[i] = b;
 }
 
-// Bias stages of mlp_tc2.cu's bias-in-the-MMA variant: stage (k, l, nh) is a zeroed [n_tile x 64]
-// SW128 stage whose row r carries the folded bias of output feature nh * n_tile + r as three bf16
-// pieces (hi + mid + lo == the fp32 bias to 24 bits) in K columns 0..2; the kernel multiplies it by
-// an all-ones A tile as one K = 16 step, which leaves acc + bias in the accumulator.
+// Bias stages of the bias-in-the-MMA variants (mlp_tc2.cu, mlp_tc4.cu): stage (k, l, nh) is a
+// [n_tile x 64] SW128 stage, zero except that row r carries the folded bias of output feature
+// nh * n_tile + r as three bf16 pieces (hi + mid + lo == the fp32 bias to 24 bits) in K columns
+// 0..2; the kernel multiplies it by an all-ones A tile as one K = 16 step, which leaves acc + bias
+// in the accumulator.  Rows k_begin .. k_begin + K - 1 of bias [..][H] -> stages of the same k; one
+// thread per (k, feature, 16-byte piece) writes the whole stage (no memset needed).
 __global__ void pack_bias_image_kernel(__nv_bfloat16* __restrict__ image,
-                                       const float* __restrict__ bias_folded, int K, int l,
+                                       const float* __restrict__ bias, int k_begin, int K, int l,
                                        int L_mma, int H, int n_tile, size_t stage_elems) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K * H) return;
-  const int k = i / H, n = i % H;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)K * H * 8) return;
+  const int piece = (int)(i & 7);
+  const int n = (int)((i >> 3) % H);
+  const int k = k_begin + (int)((i >> 3) / H);
   const int nh = n / n_tile, r = n % n_tile;
   const int NH = H / n_tile;
-  const float b = bias_folded[(size_t)k * H + n];
-  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
-  const float r1 = b - __bfloat162float(hi);
-  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-  uint8_t* dst = reinterpret_cast<uint8_t*>(image + ((size_t)(k * L_mma + l) * NH + nh) * stage_elems) +
-                 sw128_offset(r, 0);
-  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
-  d[0] = hi;
-  d[1] = mid;
-  d[2] = lo;
+  __nv_bfloat16 vals[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) vals[e] = __float2bfloat16_rn(0.f);
+  if (piece == 0) {
+    const float b = bias[(size_t)k * H + n];
+    vals[0] = __float2bfloat16_rn(b);
+    const float r1 = b - __bfloat162float(vals[0]);
+    vals[1] = __float2bfloat16_rn(r1);
+    vals[2] = __float2bfloat16_rn(r1 - __bfloat162float(vals[1]));
+  }
+  uint8_t* dst =
+      reinterpret_cast<uint8_t*>(image + (((size_t)k * L_mma + l) * NH + nh) * stage_elems) +
+      sw128_offset(r, piece);
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
 }
 
 // padded outputs of the last Linear: zero rows / zero bias beyond d_out
@@ -283,10 +290,9 @@ int tc_pack(uq_model* m, cudaStream_t st) {
     UQ_CUDA(cudaMalloc(&pb, bias_elems * sizeof(__nv_bfloat16)));
     m->allocations.push_back(pb);
     t.bias_image = static_cast<__nv_bfloat16*>(pb);
-    UQ_CUDA(cudaMemsetAsync(pb, 0, bias_elems * sizeof(__nv_bfloat16), st));
     for (int l = 0; l < t.n_mma_layers; ++l) {
-      pack_bias_image_kernel<<<(K * H + 255) / 256, 256, 0, st>>>(
-          t.bias_image, m->layers[l].bias_folded, K, l, t.n_mma_layers, H, t.n_tile, stage_elems);
+      pack_bias_image_kernel<<<(unsigned)(((int64_t)K * H * 8 + 255) / 256), 256, 0, st>>>(
+          t.bias_image, m->layers[l].bias_folded, 0, K, l, t.n_mma_layers, H, t.n_tile, stage_elems);
       UQ_LAUNCH_CHECK();
     }
   }
@@ -357,6 +363,8 @@ size_t tc_workspace_bytes(const uq_model* m, int64_t n, const uq_forward_args* a
   if (a->mode == UQ_MODE_DELTA_UQ || a->mode == UQ_MODE_PAGER) {  // per-anchor layer-0 bias [K][H]
     b += (((size_t)a->total_members * m->tc.hidden * sizeof(float)) + 255) & ~(size_t)255;
     if (split) b += (((size_t)a->total_members * sizeof(float)) + 255) & ~(size_t)255;  // max |bias0[k]|
+    // per-anchor layer-0 bias stages of the bias-in-the-MMA variants
+    else if (m->tc.bias_image) b += (size_t)a->total_members * (m->tc.hidden / m->tc.n_tile) * m->tc.stage_bytes;
   }
   return b;
 }
@@ -412,10 +420,9 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.stages_per_member = t.stages_per_member;
   p.shared_weights = (a->mode != UQ_MODE_ENSEMBLE) ? 1 : 0;
   p.image = reinterpret_cast<const uint8_t*>(t.image);
-  // the bias rides in the MMA only where the epilogue's accumulator scale is 1 (no live dropout)
-  // and the layer-0 bias is the packed one (no anchors); mlp_tc2.cu checks the rest
-  p.bias_image = (!split && a->mode != UQ_MODE_DELTA_UQ && a->mode != UQ_MODE_PAGER)
-                     ? reinterpret_cast<const uint8_t*>(t.bias_image) : nullptr;
+  // the bias rides in the MMA only where the epilogue's accumulator scale is 1 (no live dropout);
+  // the kernels' launchers check that
+  p.bias_image = !split ? reinterpret_cast<const uint8_t*>(t.bias_image) : nullptr;
   if (split) {  // fp32-parity split mode: its own image, three input segments always
     p.K0 = ((3 * t.d_in + 15) / 16) * 16 + 16;   // + the all-zero step (see mlp_tcx.cu)
     p.split_s = 3;
@@ -484,6 +491,16 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
       p.lstats = pager ? t.x_stats_pager : t.x_stats_delta;
       p.K0 = ((3 * dx + 15) / 16) * 16 + 16;
       p.split_s = 3;
+    } else if (p.bias_image != nullptr) {
+      // the per-anchor biases as layer-0 bias stages (indexed by the global member id)
+      __nv_bfloat16* b0img = reinterpret_cast<__nv_bfloat16*>(
+          wsb + off + ((((size_t)a->total_members * t.hidden * sizeof(float)) + 255) & ~(size_t)255));
+      const int64_t threads = (int64_t)a->member_count * t.hidden * 8;
+      pack_bias_image_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+          b0img, bias0, a->member_begin, a->member_count, 0, 1, t.hidden, t.n_tile,
+          t.stage_bytes / sizeof(__nv_bfloat16));
+      UQ_LAUNCH_CHECK();
+      p.bias0_image = reinterpret_cast<const uint8_t*>(b0img);
     }
     p.mode = UQ_MODE_MC_DROPOUT;   // shared weights, members differ only in bias0
     p.anchors = nullptr;

@@ -335,7 +335,11 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
             for (int l = 0; l < p.L_mma; ++l)
               for (int nh = 0; nh < NH; ++nh) {
                 for (int s = 0; s < (l == 0 ? 1 : KC); ++s, src += STAGE_BYTES) load(src);
-                load(bsrc);
+                if (l == 0 && p.bias0_image != nullptr)   // per-anchor layer-0 bias
+                  load(p.bias0_image + ((size_t)(p.member_begin + k) * NH + nh) * STAGE_BYTES +
+                       rank * HALF_BYTES);
+                else
+                  load(bsrc);
                 bsrc += STAGE_BYTES;
               }
           } else {
@@ -730,14 +734,9 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-// The bias-in-the-MMA variant is the default where it applies (ensembles and dropout-off passes,
-// d_out 1): ensemble16x512_1M 14.33 -> 13.58 ms, 0.757 -> 0.798 of the burst peak, same error
-// against the oracle (profiles/r02_j_bias_mma_*).  UQ_TC_BIAS_MMA=0 selects the epilogue-bias
-// variant for A/B runs.
-static bool bias_in_mma_enabled() {
-  const char* e = getenv("UQ_TC_BIAS_MMA");
-  return e ? e[0] == '1' : true;
-}
+// The bias-in-the-MMA variant is the default where it applies (no live dropout, d_out 1):
+// ensemble16x512_1M 14.33 -> 13.58 ms, 0.757 -> 0.798 of the burst peak, same error against the
+// oracle (profiles/r02_j_bias_mma_*); see bias_in_mma_enabled() in tc_params.cuh.
 
 template <int H, int DOUT, int NG, bool MC, bool BIAS = false>
 int launch_tc2_mc(const TcParams& p, cudaStream_t st) {

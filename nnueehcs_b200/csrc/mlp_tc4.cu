@@ -42,7 +42,10 @@ constexpr int NG4 = 2;                         // epilogue warp groups
 constexpr int EPI4_THREADS = NG4 * 128;
 constexpr int NUM4_THREADS = 64 + EPI4_THREADS;
 
-template <int H>
+// BIAS: the folded bias is accumulated by the tensor core (per layer one bias stage in the ring,
+// per slot one extra K = 16 MMA of an all-ones A tile against it), not added by the epilogue; only
+// launched where the epilogue's accumulator scale is 1 (no live dropout).
+template <int H, bool BIAS = false>
 struct Geo4 {
   static_assert(H == 64 || H == 128, "narrow-net kernel: hidden width 64 or 128");
   static constexpr int KC = H / CHUNK_K;                 // 1 or 2
@@ -52,16 +55,20 @@ struct Geo4 {
   static constexpr int HALF_BYTES = STAGE_BYTES / 2;
   static constexpr int A_SLOT_BYTES = KC * CHUNK_BYTES;
   static constexpr int A_BYTES = TS * A_SLOT_BYTES;
-  static constexpr int AUX_FLOATS = 2 * H;               // bias + w_last of one step
+  static constexpr int WL_OFF = BIAS ? 0 : H;            // w_last inside a step's aux block
+  static constexpr int AUX_FLOATS = WL_OFF + H;          // [bias +] w_last of one step
   static constexpr int AUX_BYTES = 2 * AUX_FLOATS * 4;
+  static constexpr int ONES_BYTES = BIAS ? CONST_TILE_BYTES : 0;
+  static constexpr int LSTAGES = KC + (BIAS ? 1 : 0);    // ring stages of one hidden layer
   static constexpr int XS_SLOT_BYTES = TILE_M * 64;      // x stash (K0 <= 32)
   static constexpr int BAR_BYTES = 384;
   static constexpr int MISC_BYTES = 1024 + BAR_BYTES + TS * XS_SLOT_BYTES;
-  static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES;
+  static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES - ONES_BYTES;
   static constexpr int NS_RAW = BUDGET / HALF_BYTES;
   static constexpr int NSTAGES = NS_RAW > 8 ? 8 : NS_RAW;
-  static_assert(NSTAGES >= 2 * KC, "the ring must hold two layers of weight stages");
-  static constexpr int SMEM_BYTES = A_BYTES + NSTAGES * HALF_BYTES + AUX_BYTES + MISC_BYTES;
+  static_assert(NSTAGES >= 2 * LSTAGES, "the ring must hold two layers of weight stages");
+  static constexpr int SMEM_BYTES =
+      A_BYTES + NSTAGES * HALF_BYTES + ONES_BYTES + AUX_BYTES + MISC_BYTES;
 };
 
 constexpr uint32_t B4_W_FULL = 0;       // 8 x 8 B
@@ -75,7 +82,7 @@ constexpr uint32_t B4_TMEM_PTR = 224;
 // keepw: the keep-mask words of the slot's 2 KC blocks, computed by the caller BEFORE it waits for
 // the slot's MMAs (they do not depend on the activations; several independent Philox chains in
 // flight hide each other's latency -- with two warps per scheduler a single chain does not)
-template <int H, bool RELU, bool DROP, bool LAST>
+template <int H, bool RELU, bool DROP, bool LAST, bool BIAS>
 __device__ __forceinline__ void drain4(uint32_t lane_addr, uint32_t a_row, int rx,
                                        const float* bias_s, const float* wl_s,
                                        const uint32_t (&keepw)[2 * (H / CHUNK_K)], float in_scale,
@@ -88,26 +95,32 @@ __device__ __forceinline__ void drain4(uint32_t lane_addr, uint32_t a_row, int r
     const int col0 = c * CHUNK_K;
     const uint32_t a_dst = a_row + (uint32_t)c * CHUNK_BYTES;
     float4 bv[8];
+    if (!BIAS) {
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0)[j4];
+      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0)[j4];
+    }
     tmem_ld_wait();
     tmem_ld32(lane_addr + (uint32_t)(col0 + 32), acc1);
-    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc0, bv, DROP ? keepw[2 * c] : 0xffffffffu, in_scale,
-                                           a_dst, 0, rx, wl_s + col0, wl_s + col0, dot);
+    epi_block2<H, 1, 32, RELU, DROP, LAST, BIAS>(acc0, bv, DROP ? keepw[2 * c] : 0xffffffffu,
+                                                 in_scale, a_dst, 0, rx, wl_s + col0, wl_s + col0,
+                                                 dot);
+    if (!BIAS) {
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
+      for (int j4 = 0; j4 < 8; ++j4)
+        bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
+    }
     tmem_ld_wait();
     if (c + 1 < KC) tmem_ld32(lane_addr + (uint32_t)(col0 + CHUNK_K), acc0);
-    epi_block2<H, 1, 32, RELU, DROP, LAST>(acc1, bv, DROP ? keepw[2 * c + 1] : 0xffffffffu,
-                                           in_scale, a_dst, 4, rx, wl_s + col0 + 32,
-                                           wl_s + col0 + 32, dot);
+    epi_block2<H, 1, 32, RELU, DROP, LAST, BIAS>(acc1, bv, DROP ? keepw[2 * c + 1] : 0xffffffffu,
+                                                 in_scale, a_dst, 4, rx, wl_s + col0 + 32,
+                                                 wl_s + col0 + 32, dot);
   }
 }
 
-template <int H>
+template <int H, bool BIAS>
 __global__ void __launch_bounds__(NUM4_THREADS, 1)
 uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
-  using G = Geo4<H>;
+  using G = Geo4<H, BIAS>;
   constexpr int KC = G::KC, NT = G::NT, NS = G::NSTAGES;
   constexpr uint32_t STAGE_BYTES = G::STAGE_BYTES, HALF_BYTES = G::HALF_BYTES;
 
@@ -116,7 +129,8 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                  // TS slots x KC chunks of 16 KB
   uint8_t* w_smem = smem + G::A_BYTES;                     // NS half-stages
-  float* aux_smem = reinterpret_cast<float*>(w_smem + NS * HALF_BYTES);
+  uint8_t* ones_smem = w_smem + NS * HALF_BYTES;           // BIAS: constant-1 A tile (bf16)
+  float* aux_smem = reinterpret_cast<float*>(ones_smem + G::ONES_BYTES);
   uint8_t* bar_smem = reinterpret_cast<uint8_t*>(aux_smem) + G::AUX_BYTES;
   const uint32_t xstash = smem_u32(bar_smem + G::BAR_BYTES);         // [TS][K0/8][128] x 16 B
   const uint32_t a_base = smem_u32(a_smem);
@@ -144,6 +158,11 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(bars + B4_TMEM_PTR, (uint32_t)G::TMEM_COLS);
+  if (BIAS) {   // the all-ones A tile of the bias MMAs (read by the tensor core: async proxy)
+    for (int i = threadIdx.x; i < G::ONES_BYTES / 4; i += NUM4_THREADS)
+      reinterpret_cast<uint32_t*>(ones_smem)[i] = 0x3F803F80u;   // bf16 (1.0, 1.0)
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -162,12 +181,26 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           const uint8_t* src =
               p.image + (p.shared_weights ? 0 : (size_t)(p.member_begin + k) * member_bytes) +
               rank * HALF_BYTES;
-          for (int s = 0; s < p.stages_per_member; ++s) {
+          auto load = [&](const uint8_t* from) {
             mbar_wait(bars + B4_W_EMPTY + 8 * slot, phase ^ 1, p.error_flag, 1);
             mbar_arrive_expect_tx(bars + B4_W_FULL + 8 * slot, HALF_BYTES);
-            bulk_g2s(w_base + slot * HALF_BYTES, src, HALF_BYTES, bars + B4_W_FULL + 8 * slot);
-            src += STAGE_BYTES;
+            bulk_g2s(w_base + slot * HALF_BYTES, from, HALF_BYTES, bars + B4_W_FULL + 8 * slot);
             if (++slot == NS) { slot = 0; phase ^= 1; }
+          };
+          if (BIAS) {   // per layer: its weight stages, then its bias stage
+            const uint8_t* bsrc =
+                p.bias_image +
+                (p.shared_weights ? 0 : (size_t)(p.member_begin + k) * p.L_mma * STAGE_BYTES) +
+                rank * HALF_BYTES;
+            for (int l = 0; l < p.L_mma; ++l, bsrc += STAGE_BYTES) {
+              for (int s = 0; s < (l == 0 ? 1 : KC); ++s, src += STAGE_BYTES) load(src);
+              if (l == 0 && p.bias0_image != nullptr)   // per-anchor layer-0 bias
+                load(p.bias0_image + (size_t)(p.member_begin + k) * STAGE_BYTES + rank * HALF_BYTES);
+              else
+                load(bsrc);
+            }
+          } else {
+            for (int s = 0; s < p.stages_per_member; ++s, src += STAGE_BYTES) load(src);
           }
         }
       }
@@ -181,7 +214,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
         const int split = unit % p.splits;
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
-        const int n_stages = (me - mb) * p.stages_per_member;
+        const int n_stages = (me - mb) * (p.stages_per_member + (BIAS ? p.L_mma : 0));
         for (int s = 0; s < n_stages; ++s) {
           mbar_wait(bars + B4_W_FULL + 8 * slot, phase, p.error_flag, 6);
           mbar_arrive_cluster(full0 + 8 * slot);
@@ -195,6 +228,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
     constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, NT);
     const uint64_t a_desc0 = make_sw128_desc(a_base);
     const uint64_t b_desc0 = make_sw128_desc(w_base);
+    const uint64_t ones_desc = make_sw128_const_desc(smem_u32(ones_smem));
     const int k0_steps = p.K0 / 16;
     uint32_t slot = 0, phase = 0;
     uint32_t g = 0, xm = 0;
@@ -219,6 +253,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
         {
           const uint32_t prev_par = (g - 1) & 1;
           const uint32_t r0 = wait_stage(0);
+          const uint32_t rb = BIAS ? wait_stage(1) : 0;
 #pragma unroll 1
           for (int t = 0; t < TS; ++t) {
             mbar_wait_cluster_inline(bars + B4_X_READY + 8 * t, xm & 1, p.error_flag, 2);
@@ -229,11 +264,14 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
               const uint64_t bd = b_desc0 + (uint64_t)((r0 * HALF_BYTES) >> 4);
               for (int ks = 0; ks < k0_steps; ++ks)
                 umma_bf16_pair(tmem_base + t * H, ad + 2 * ks, bd + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+              if (BIAS)   // accumulator += ones . bias^T
+                umma_bf16_pair(tmem_base + t * H, ones_desc,
+                               b_desc0 + (uint64_t)((rb * HALF_BYTES) >> 4), idesc, 1u);
               umma_commit_pair(bars + B4_D_FULL + 8 * t, 3);
             }
             __syncwarp();
           }
-          release_stages(1);
+          release_stages(1 + (BIAS ? 1 : 0));
           ++g;
         }
         // ---- hidden layers ----------------------------------------------------------------------
@@ -242,6 +280,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           uint32_t rr[KC];
 #pragma unroll
           for (int kc = 0; kc < KC; ++kc) rr[kc] = wait_stage(kc);
+          const uint32_t rb = BIAS ? wait_stage(KC) : 0;
 #pragma unroll 1
           for (int t = 0; t < TS; ++t) {
             mbar_wait_cluster_inline(bars + B4_DRAINED + 8 * t, prev_par, p.error_flag, 3);
@@ -257,11 +296,14 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
                   umma_bf16_pair(tmem_base + t * H, ad + 2 * ks, bd + 2 * ks, idesc,
                                  (kc > 0 || ks > 0) ? 1u : 0u);
               }
+              if (BIAS)
+                umma_bf16_pair(tmem_base + t * H, ones_desc,
+                               b_desc0 + (uint64_t)((rb * HALF_BYTES) >> 4), idesc, 1u);
               umma_commit_pair(bars + B4_D_FULL + 8 * t, 3);
             }
             __syncwarp();
           }
-          release_stages(KC);
+          release_stages(G::LSTAGES);
           ++g;
         }
       }
@@ -319,8 +361,8 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
       for (int j = 0; j < AUX_PER_THREAD; ++j) {
         const int i = et + j * EPI4_THREADS;
         float v = 0.f;
-        if (i < H) v = __ldg(bias + i);
-        else if (last && i < 2 * H) v = __ldg(wl + (i - H));
+        if (!BIAS && i < H) v = __ldg(bias + i);
+        else if (last && i >= G::WL_OFF && i < G::WL_OFF + H) v = __ldg(wl + (i - G::WL_OFF));
         aux_pf[j] = v;
       }
     };
@@ -370,7 +412,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           const bool last = (l == p.L_mma - 1);
           const bool relu = (p.relu_mask >> l) & 1u;
           const bool has_drop = (p.dropout_mask >> l) & 1u;
-          const int drop = has_drop ? p.drop_mode : 0;
+          const int drop = (!BIAS && has_drop) ? p.drop_mode : 0;
           const float in_scale =
               (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
 
@@ -406,7 +448,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
             const uint32_t lane_addr = lane_addr0 + (uint32_t)(t * H);
             const uint32_t a_row = a_row0 + (uint32_t)(t * G::A_SLOT_BYTES);
 #define UQ_DRAIN4(R, D, L) \
-  drain4<H, R, D, L>(lane_addr, a_row, rx, aux, aux + H, keepw, in_scale, dslot)
+  drain4<H, R, (D) && !BIAS, L, BIAS>(lane_addr, a_row, rx, aux, aux + G::WL_OFF, keepw, in_scale, dslot)
             if (last) {
               if (relu) { if (drop) UQ_DRAIN4(true, true, true); else UQ_DRAIN4(true, false, true); }
               else { if (drop) UQ_DRAIN4(false, true, true); else UQ_DRAIN4(false, false, true); }
@@ -471,10 +513,10 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-template <int H>
+template <int H, bool BIAS>
 int launch_tc4(const TcParams& p, cudaStream_t st) {
-  using G = Geo4<H>;
-  auto kern = uq_mlp_tc4_kernel<H>;
+  using G = Geo4<H, BIAS>;
+  auto kern = uq_mlp_tc4_kernel<H, BIAS>;
   // per-device launch geometry of this instantiation, queried once (the occupancy query and the
   // attribute call cost tens of microseconds, which shows on millisecond-sized forwards)
   static std::atomic<int> cached_clusters[64];   // zero-initialised; races only repeat the query
@@ -521,8 +563,11 @@ bool tc4_supported(int hidden, int dout_pad) { return (hidden == 64 || hidden ==
 int tc4_rows_per_unit() { return 2 * TS * tc::TILE_M; }
 
 int tc4_launch(const tc::TcParams& p, int hidden, cudaStream_t st) {
-  if (hidden == 64) return launch_tc4<64>(p, st);
-  if (hidden == 128) return launch_tc4<128>(p, st);
+  // bias in the MMA where the epilogue's accumulator scale is 1 (no live dropout)
+  const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
+  const bool bias = !mc && p.bias_image != nullptr && bias_in_mma_enabled();
+  if (hidden == 64) return bias ? launch_tc4<64, true>(p, st) : launch_tc4<64, false>(p, st);
+  if (hidden == 128) return bias ? launch_tc4<128, true>(p, st) : launch_tc4<128, false>(p, st);
   set_error("bf16 narrow-net kernel: unsupported hidden width %d", hidden);
   return UQ_ERR_UNSUPPORTED;
 }

@@ -1,6 +1,7 @@
 // Launch parameters shared by the fused tcgen05 kernels (mlp_tc.cu, mlp_tc2.cu).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -33,6 +34,9 @@ struct TcParams {
   // accumulator half) whose K columns 0..2 hold the folded bias as bf16 hi + mid + lo; null = the
   // epilogue adds the bias
   const uint8_t* bias_image;
+  // anchored modes: the layer-0 bias stages, one set per global member id (built per call from the
+  // per-anchor bias); null = layer 0 uses bias_image like every other layer
+  const uint8_t* bias0_image;
   const float* bias[MAX_MMA_LAYERS];  // [K or 1][H] folded bias per MMA layer
   uint32_t relu_mask, dropout_mask;   // bit l: MMA layer l has ReLU / dropout on its output
   const float* w_last;                // [K or 1][DOUT][H]  (zero rows beyond d_out)
@@ -59,6 +63,13 @@ struct TcParams {
 };
 
 }  // namespace tc
+
+// The bias-in-the-MMA variants (mlp_tc2.cu, mlp_tc4.cu) are the default where they apply (no live
+// dropout, d_out 1); UQ_TC_BIAS_MMA=0 selects the epilogue-bias variants for A/B runs.
+inline bool bias_in_mma_enabled() {
+  const char* e = getenv("UQ_TC_BIAS_MMA");
+  return e ? e[0] == '1' : true;
+}
 
 // mlp_tc2.cu: CTA-pair (cta_group::2) variant of the fused kernel; same weight image
 int tc2_launch(const tc::TcParams& p, int hidden, int dout_pad, cudaStream_t st);
