@@ -420,8 +420,7 @@ int tc_forward(const uq_model* m, const float* x, int64_t n, const uq_forward_ar
   p.stages_per_member = t.stages_per_member;
   p.shared_weights = (a->mode != UQ_MODE_ENSEMBLE) ? 1 : 0;
   p.image = reinterpret_cast<const uint8_t*>(t.image);
-  // the bias rides in the MMA only where the epilogue's accumulator scale is 1 (no live dropout);
-  // the kernels' launchers check that
+  // bias stages of the bias-in-the-MMA variants (mlp_tc2.cu, mlp_tc4.cu; d_out 1)
   p.bias_image = !split ? reinterpret_cast<const uint8_t*>(t.bias_image) : nullptr;
   if (split) {  // fp32-parity split mode: its own image, three input segments always
     p.K0 = ((3 * t.d_in + 15) / 16) * 16 + 16;   // + the all-zero step (see mlp_tcx.cu)

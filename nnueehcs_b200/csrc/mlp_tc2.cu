@@ -240,7 +240,7 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
 template <int H, int DOUT, int NG, bool MC, bool BIAS = false>
 __global__ void __launch_bounds__(Geo2<H, DOUT, NG, BIAS>::NUM_THREADS, 1)
 uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
-  static_assert(!BIAS || (!MC && NG == 2 && DOUT == 1), "bias-in-the-MMA variant: NG 2, d_out 1, no dropout");
+  static_assert(!BIAS || (NG == 2 && DOUT == 1), "bias-in-the-MMA variant: NG 2, d_out 1");
   using G = Geo2<H, DOUT, NG, BIAS>;
   constexpr int EPI_THREADS = G::EPI_THREADS;
   constexpr int KC = G::KC, NH = G::NH, NT = G::NT, NS = G::NSTAGES;
@@ -630,7 +630,10 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
           cx.drop_ord = drop_ord;
           cx.grow = grow;
           cx.mask_layer = mask_layer;
-          cx.in_scale = (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
+          // epilogue-bias: 1/(1-p) owed by the previous layer's dropout; bias in the MMA: this layer's
+          cx.in_scale = BIAS ? (drop ? p.drop_scale : 1.f)
+                             : (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode)
+                                   ? p.drop_scale : 1.f;
 #ifdef UQ_TC_TRACE
           {
             const int role = (lane == 0 && (warp == 2 || (warp == 6 && leader)))
@@ -698,7 +701,7 @@ uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int j = 0; j < NPART; ++j)
               y += ld_shared_f32(xb + (uint32_t)(((j * TILE_M + row) * DOUT + o) * 4));
-            y = fmaf(y, final_dropout_scale(p), __ldg(bl + o));
+            y = fmaf(y, BIAS ? 1.f : final_dropout_scale(p), __ldg(bl + o));
             if (p.last_relu) y = fmaxf(y, 0.f);
             member_fold(p, kg, o, y, inv_n, wf_mean[o], wf_m2[o]);
           }
@@ -784,8 +787,8 @@ int launch_tc2_mc(const TcParams& p, cudaStream_t st) {
 template <int H, int DOUT, int NG>
 int launch_tc2(const TcParams& p, cudaStream_t st) {
   const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
-  if (DOUT == 1 && NG == 2 && !mc && p.bias_image != nullptr && bias_in_mma_enabled())
-    return launch_tc2_mc<H, 1, 2, false, true>(p, st);
+  if (DOUT == 1 && NG == 2 && p.bias_image != nullptr && bias_in_mma_enabled())
+    return mc ? launch_tc2_mc<H, 1, 2, true, true>(p, st) : launch_tc2_mc<H, 1, 2, false, true>(p, st);
   return mc ? launch_tc2_mc<H, DOUT, NG, true>(p, st) : launch_tc2_mc<H, DOUT, NG, false>(p, st);
 }
 

@@ -43,8 +43,8 @@ constexpr int EPI4_THREADS = NG4 * 128;
 constexpr int NUM4_THREADS = 64 + EPI4_THREADS;
 
 // BIAS: the folded bias is accumulated by the tensor core (per layer one bias stage in the ring,
-// per slot one extra K = 16 MMA of an all-ones A tile against it), not added by the epilogue; only
-// launched where the epilogue's accumulator scale is 1 (no live dropout).
+// per slot one extra K = 16 MMA of an all-ones A tile against it), not added by the epilogue;
+// with live dropout the activations are then stored with their 1/(1-p) (see epi_math).
 template <int H, bool BIAS = false>
 struct Geo4 {
   static_assert(H == 64 || H == 128, "narrow-net kernel: hidden width 64 or 128");
@@ -412,9 +412,11 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           const bool last = (l == p.L_mma - 1);
           const bool relu = (p.relu_mask >> l) & 1u;
           const bool has_drop = (p.dropout_mask >> l) & 1u;
-          const int drop = (!BIAS && has_drop) ? p.drop_mode : 0;
+          const int drop = has_drop ? p.drop_mode : 0;
+          // epilogue-bias: 1/(1-p) owed by the previous layer's dropout; bias in the MMA: this layer's
           const float in_scale =
-              (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
+              BIAS ? (drop ? p.drop_scale : 1.f)
+                   : (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
 
           float* aux = aux_smem + (g & 1) * G::AUX_FLOATS;
 #pragma unroll
@@ -448,7 +450,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
             const uint32_t lane_addr = lane_addr0 + (uint32_t)(t * H);
             const uint32_t a_row = a_row0 + (uint32_t)(t * G::A_SLOT_BYTES);
 #define UQ_DRAIN4(R, D, L) \
-  drain4<H, R, (D) && !BIAS, L, BIAS>(lane_addr, a_row, rx, aux, aux + G::WL_OFF, keepw, in_scale, dslot)
+  drain4<H, R, D, L, BIAS>(lane_addr, a_row, rx, aux, aux + G::WL_OFF, keepw, in_scale, dslot)
             if (last) {
               if (relu) { if (drop) UQ_DRAIN4(true, true, true); else UQ_DRAIN4(true, false, true); }
               else { if (drop) UQ_DRAIN4(false, true, true); else UQ_DRAIN4(false, false, true); }
@@ -481,7 +483,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           const float bl = __ldg(p.b_last + wslot);
 #pragma unroll
           for (int j = 0; j < OWN; ++j) {
-            float y = fmaf(dot[j], final_dropout_scale(p), bl);
+            float y = fmaf(dot[j], BIAS ? 1.f : final_dropout_scale(p), bl);
             if (p.last_relu) y = fmaxf(y, 0.f);
             member_fold(p, kg, 0, y, inv_n, wf_mean[j], wf_m2[j]);
           }
@@ -563,9 +565,7 @@ bool tc4_supported(int hidden, int dout_pad) { return (hidden == 64 || hidden ==
 int tc4_rows_per_unit() { return 2 * TS * tc::TILE_M; }
 
 int tc4_launch(const tc::TcParams& p, int hidden, cudaStream_t st) {
-  // bias in the MMA where the epilogue's accumulator scale is 1 (no live dropout)
-  const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
-  const bool bias = !mc && p.bias_image != nullptr && bias_in_mma_enabled();
+  const bool bias = p.bias_image != nullptr && bias_in_mma_enabled();
   if (hidden == 64) return bias ? launch_tc4<64, true>(p, st) : launch_tc4<64, false>(p, st);
   if (hidden == 128) return bias ? launch_tc4<128, true>(p, st) : launch_tc4<128, false>(p, st);
   set_error("bf16 narrow-net kernel: unsupported hidden width %d", hidden);

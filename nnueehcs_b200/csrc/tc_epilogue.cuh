@@ -82,8 +82,10 @@ __device__ __forceinline__ uint32_t keep_bits32(const TcParams& p, int drop, int
 
 // One NC-column block of one accumulator row: + bias, dropout, then either ReLU + bf16 rounding
 // into NC/2 packed words (cvt.rn[.relu].bf16x2) or the last-Linear dot product.
-// BIAS_IN_ACC: the accumulator already holds acc + bias (mlp_tc2.cu's bias-in-the-MMA variant, which
-// only runs where in_scale == 1); bv is not read.
+// BIAS_IN_ACC (the bias-in-the-MMA variants): the accumulator already holds acc + bias, bv is not
+// read, and the activations are stored WITH their dropout's 1/(1-p) -- in_scale is then the scale of
+// THIS layer's dropout, applied to the kept elements (v * (keep ? s : 0): FSEL + FMUL, where the
+// epilogue-bias variant spends FFMA + FSEL), not the scale owed by the previous layer.
 template <int H, int DOUT, int NC, bool RELU, bool DROP, bool LAST, bool BIAS_IN_ACC = false>
 __device__ __forceinline__ void epi_math(const uint32_t (&acc)[NC], const float4 (&bv)[NC / 4],
                                          uint32_t keep, float in_scale, uint32_t* packed,
@@ -105,7 +107,9 @@ __device__ __forceinline__ void epi_math(const uint32_t (&acc)[NC], const float4
   }
   if (DROP) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) v[j] = ((keep >> j) & 1u) ? v[j] : 0.f;
+    for (int j = 0; j < NC; ++j)
+      v[j] = BIAS_IN_ACC ? v[j] * (((keep >> j) & 1u) ? in_scale : 0.f)
+                         : (((keep >> j) & 1u) ? v[j] : 0.f);
   }
   if (!LAST) {
 #pragma unroll

@@ -1,7 +1,7 @@
 #!/bin/bash
 # bias-in-the-MMA variants of mlp_tc2.cu / mlp_tc4.cu: parity A/B, the forward tests, bench A/B
 mkdir -p gpurun_out
-timeout 300 python tools/bias_mma_check.py > gpurun_out/bias_mma_check.log 2>&1; echo "bias_mma_check exit $?"; grep -c "^OK" gpurun_out/bias_mma_check.log; grep "FAIL\|ALL OK\|SOME\|Error\|error" gpurun_out/bias_mma_check.log | head -20; grep "narrow\|delta" gpurun_out/bias_mma_check.log | head -20
+timeout 300 python tools/bias_mma_check.py > gpurun_out/bias_mma_check.log 2>&1; echo "bias_mma_check exit $?"; grep -c "^OK" gpurun_out/bias_mma_check.log; grep "FAIL\|ALL OK\|SOME\|Error\|error" gpurun_out/bias_mma_check.log | head -20; grep "mc-dropout\|Traceback" -A3 gpurun_out/bias_mma_check.log | head -30
 timeout 600 python -m pytest tests/test_gpu_forward.py -q --timeout 300 -x > gpurun_out/pytest_forward_biasmma.log 2>&1; echo "pytest forward exit $?"; tail -3 gpurun_out/pytest_forward_biasmma.log
 bench() {  # name, workload, env...
   local name=$1; shift
@@ -16,8 +16,7 @@ except Exception as e:
     print('bench parse failed', e); print(open('gpurun_out/bench_$name.err').read()[-2000:])
 PY
 }
-for wl in deltauq32_binomial_4M ensemble32x128_4M; do
+for wl in ${WORKLOADS:-mcdropout100_binomial_10k mcdropout_1000x512_64k}; do
   bench ${wl}_bias0 $wl UQ_TC_BIAS_MMA=0
   bench ${wl}_bias1 $wl UQ_TC_BIAS_MMA=1
 done
-bench mcdropout100_binomial_10k mcdropout100_binomial_10k UQ_TC_BIAS_MMA=1
