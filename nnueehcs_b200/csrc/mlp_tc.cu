@@ -284,7 +284,7 @@ int tc_pack(uq_model* m, cudaStream_t st) {
                                                      ly.bias_folded, n);
     UQ_LAUNCH_CHECK();
   }
-  if (tc2_supported(H)) {   // bias stages (mlp_tc2.cu, bias-in-the-MMA variant)
+  {   // bias stages of the bias-in-the-MMA variants
     void* pb = nullptr;
     const size_t bias_elems = (size_t)K * t.n_mma_layers * NH * stage_elems;
     UQ_CUDA(cudaMalloc(&pb, bias_elems * sizeof(__nv_bfloat16)));

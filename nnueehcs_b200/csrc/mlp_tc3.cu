@@ -43,7 +43,10 @@ constexpr int NG = 2;                          // epilogue warp groups
 constexpr int EPI_THREADS = NG * 128;
 constexpr int NUM_THREADS = 64 + EPI_THREADS;
 
-template <int H, int DOUT>
+// BIAS (d_out 1): the folded bias is accumulated by the tensor core -- per layer and N tile one bias
+// stage in the ring and one extra K = 16 MMA of an all-ones A tile against it -- not added by the
+// epilogue; with live dropout the activations are then stored with their 1/(1-p) (see epi_math).
+template <int H, int DOUT, bool BIAS = false>
 struct Geo3 {
   static_assert(H % 256 == 0 && H >= 256 && H <= 1024, "hidden width must be a multiple of 256");
   static constexpr int KC = H / CHUNK_K;                 // activation chunks (<= 16)
@@ -55,17 +58,21 @@ struct Geo3 {
   static constexpr int STAGE_BYTES = NT * 128;           // whole stage [NT x 64] bf16 in the image
   static constexpr int HALF_BYTES = STAGE_BYTES / 2;
   static constexpr int A_BYTES = KC * CHUNK3_BYTES;
-  static constexpr int AUX_FLOATS = (DOUT == 1 ? 2 : 1) * H;
+  static constexpr int WL_OFF = BIAS ? 0 : H;            // w_last inside a step's aux block
+  static constexpr int AUX_FLOATS = WL_OFF + (DOUT == 1 ? H : 0);
   static constexpr int AUX_BYTES = 2 * AUX_FLOATS * 4;
+  // all-ones A tile of 64 rows: 8 row groups 256 B apart (see make_sw128_const_desc)
+  static constexpr int ONES_BYTES = BIAS ? 7 * 256 + 1024 : 0;
   static constexpr int XCHG_BYTES = 2 * 3 * ROWS * DOUT * 4;   // [2][3 partial owners][64][DOUT]
   static constexpr int XS_BYTES = ROWS * 64;                   // x stash (K0 <= 32)
   static constexpr int BAR_BYTES = 384;
   static constexpr int MISC_BYTES = 1024 + BAR_BYTES + XCHG_BYTES + XS_BYTES;
-  static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES;
+  static constexpr int BUDGET = SMEM_LIMIT - A_BYTES - AUX_BYTES - MISC_BYTES - ONES_BYTES;
   static constexpr int NS_RAW = BUDGET / HALF_BYTES;
   static constexpr int NSTAGES = NS_RAW > 8 ? 8 : NS_RAW;
   static_assert(NSTAGES >= 2, "not enough shared memory for a weight ring");
-  static constexpr int SMEM_BYTES = A_BYTES + NSTAGES * HALF_BYTES + AUX_BYTES + MISC_BYTES;
+  static constexpr int SMEM_BYTES =
+      A_BYTES + NSTAGES * HALF_BYTES + ONES_BYTES + AUX_BYTES + MISC_BYTES;
 };
 
 // barrier block (byte offsets inside the 384-byte barrier area)
@@ -105,7 +112,7 @@ __device__ __forceinline__ void compute_keep_words3(const TcParams& p, int grp, 
   }
 }
 
-template <int H, int DOUT, bool RELU, bool DROP, bool LAST>
+template <int H, int DOUT, bool RELU, bool DROP, bool LAST, bool BIAS>
 __device__ __forceinline__ void drain3(const TcParams& p, uint32_t lane_addr, uint32_t a_row, int rx,
                                        int grp, int ch, int lane, uint32_t chunk_bar0,
                                        const float* bias_s, const float* wl_s, const float* wl_g,
@@ -121,21 +128,25 @@ __device__ __forceinline__ void drain3(const TcParams& p, uint32_t lane_addr, ui
     const uint32_t tcol = (uint32_t)(j * G::TCOLS + e * CHUNK_K);  // TMEM column of this chunk
     const uint32_t a_dst = a_row + (uint32_t)c * CHUNK3_BYTES;
     float4 bv[8];
+    if (!BIAS) {
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0)[j4];
+      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(bias_s + col0)[j4];
+    }
     tmem_ld_wait();
     tmem_ld32(lane_addr + tcol + 32, acc1);
-    epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc0, bv, keep0, in_scale, a_dst, 0, rx,
-                                              wl_s + col0, wl_g + col0, dot);
+    epi_block2<H, DOUT, 32, RELU, DROP, LAST, BIAS>(acc0, bv, keep0, in_scale, a_dst, 0, rx,
+                                                    wl_s + col0, wl_g + col0, dot);
+    if (!BIAS) {
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4)
-      bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
+      for (int j4 = 0; j4 < 8; ++j4)
+        bv[j4] = reinterpret_cast<const float4*>(bias_s + col0 + 32)[j4];
+    }
     tmem_ld_wait();
     // next chunk of this warp: e == 0 -> same tile, next 64 TMEM columns; else tile j + NG
     if (e == 0) tmem_ld32(lane_addr + tcol + CHUNK_K, acc0);
     else if (j + NG < G::NTILES) tmem_ld32(lane_addr + (uint32_t)((j + NG) * G::TCOLS), acc0);
-    epi_block2<H, DOUT, 32, RELU, DROP, LAST>(acc1, bv, keep1, in_scale, a_dst, 4, rx,
-                                              wl_s + col0 + 32, wl_g + col0 + 32, dot);
+    epi_block2<H, DOUT, 32, RELU, DROP, LAST, BIAS>(acc1, bv, keep1, in_scale, a_dst, 4, rx,
+                                                    wl_s + col0 + 32, wl_g + col0 + 32, dot);
     tc_fence_before();
     if (!LAST) fence_proxy_async_smem();
     __syncwarp();
@@ -159,10 +170,11 @@ __device__ __forceinline__ void drain3(const TcParams& p, uint32_t lane_addr, ui
   }
 }
 
-template <int H, int DOUT>
+template <int H, int DOUT, bool BIAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
-  using G = Geo3<H, DOUT>;
+  static_assert(!BIAS || DOUT == 1, "bias-in-the-MMA variant: d_out 1");
+  using G = Geo3<H, DOUT, BIAS>;
   constexpr int KC = G::KC, NT = G::NT, NS = G::NSTAGES, NTILES = G::NTILES, CPT = G::CPT;
   constexpr uint32_t STAGE_BYTES = G::STAGE_BYTES, HALF_BYTES = G::HALF_BYTES;
 
@@ -171,7 +183,8 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                  // KC chunks of 8 KB
   uint8_t* w_smem = smem + G::A_BYTES;                     // NS half-stages
-  float* aux_smem = reinterpret_cast<float*>(w_smem + NS * HALF_BYTES);
+  uint8_t* ones_smem = w_smem + NS * HALF_BYTES;           // BIAS: constant-1 A tile (bf16)
+  float* aux_smem = reinterpret_cast<float*>(ones_smem + G::ONES_BYTES);
   uint8_t* bar_smem = reinterpret_cast<uint8_t*>(aux_smem) + G::AUX_BYTES;
   const uint32_t xchg = smem_u32(bar_smem + G::BAR_BYTES);
   const uint32_t xstash = xchg + G::XCHG_BYTES;
@@ -206,6 +219,11 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(bars + B3_TMEM_PTR, (uint32_t)G::TMEM_COLS);
+  if (BIAS) {   // the all-ones A tile of the bias MMAs (read by the tensor core: async proxy)
+    for (int i = threadIdx.x; i < G::ONES_BYTES / 4; i += NUM_THREADS)
+      reinterpret_cast<uint32_t*>(ones_smem)[i] = 0x3F803F80u;   // bf16 (1.0, 1.0)
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -224,12 +242,28 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
           const uint8_t* src =
               p.image + (p.shared_weights ? 0 : (size_t)(p.member_begin + k) * member_bytes) +
               rank * HALF_BYTES;
-          for (int s = 0; s < p.stages_per_member; ++s) {
+          auto load = [&](const uint8_t* from) {
             mbar_wait(bars + B3_W_EMPTY + 8 * slot, phase ^ 1, p.error_flag, 1);
             mbar_arrive_expect_tx(bars + B3_W_FULL + 8 * slot, HALF_BYTES);
-            bulk_g2s(w_base + slot * HALF_BYTES, src, HALF_BYTES, bars + B3_W_FULL + 8 * slot);
-            src += STAGE_BYTES;
+            bulk_g2s(w_base + slot * HALF_BYTES, from, HALF_BYTES, bars + B3_W_FULL + 8 * slot);
             if (++slot == NS) { slot = 0; phase ^= 1; }
+          };
+          if (BIAS) {   // per (layer, N tile): its weight stages, then its bias stage
+            const uint8_t* bsrc =
+                p.bias_image +
+                (p.shared_weights ? 0 : (size_t)(p.member_begin + k) * p.L_mma * NTILES * STAGE_BYTES) +
+                rank * HALF_BYTES;
+            for (int l = 0; l < p.L_mma; ++l)
+              for (int nt = 0; nt < NTILES; ++nt, bsrc += STAGE_BYTES) {
+                for (int s = 0; s < (l == 0 ? 1 : KC); ++s, src += STAGE_BYTES) load(src);
+                if (l == 0 && p.bias0_image != nullptr)   // per-anchor layer-0 bias
+                  load(p.bias0_image + ((size_t)(p.member_begin + k) * NTILES + nt) * STAGE_BYTES +
+                       rank * HALF_BYTES);
+                else
+                  load(bsrc);
+              }
+          } else {
+            for (int s = 0; s < p.stages_per_member; ++s, src += STAGE_BYTES) load(src);
           }
         }
       }
@@ -243,7 +277,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
         const int split = unit_split(unit);
         const int mb = (int)(((int64_t)p.member_count * split) / p.splits);
         const int me = (int)(((int64_t)p.member_count * (split + 1)) / p.splits);
-        const int n_stages = (me - mb) * p.stages_per_member;
+        const int n_stages = (me - mb) * (p.stages_per_member + (BIAS ? p.L_mma * NTILES : 0));
         for (int s = 0; s < n_stages; ++s) {
           mbar_wait(bars + B3_W_FULL + 8 * slot, phase, p.error_flag, 6);
           mbar_arrive_cluster(full0 + 8 * slot);
@@ -275,6 +309,15 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
       slot = nslot;
       phase = nphase;
       w_ready = w_ready_next;
+    };
+    const uint64_t ones_desc = make_sw128_const_desc(smem_u32(ones_smem));
+    // N tile nt += ones . bias^T: one K = 16 step on the tile's bias stage
+    auto bias_mma = [&](int nt) {
+      acquire();
+      if (elect_one())
+        umma_bf16_pair(tmem_base + nt * G::TCOLS, ones_desc,
+                       b_desc0 + (uint64_t)((slot * HALF_BYTES) >> 4), idesc, 1u);
+      release();
     };
     // all chunks of N tile nt drained by the previous step's epilogue (its TMEM columns are free)
     auto wait_tile_drained = [&](int nt, uint32_t prev_par) {
@@ -308,6 +351,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
                                ks > 0 ? 1u : 0u);
             }
             release();
+            if (BIAS) bias_mma(nt);
           }
           if (elect_one()) umma_commit_pair(bars + B3_D_FULL, 3);
           ++g;
@@ -339,6 +383,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
               }
               release();
             }
+            if (BIAS) bias_mma(nt);
           }
           if (elect_one()) umma_commit_pair(bars + B3_D_FULL, 3);
           ++g;
@@ -399,8 +444,8 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
       for (int j = 0; j < AUX_PER_THREAD; ++j) {
         const int i = et + j * EPI_THREADS;
         float v = 0.f;
-        if (i < H) v = __ldg(bias + i);
-        else if (DOUT == 1 && last && i < 2 * H) v = __ldg(wl + (i - H));
+        if (!BIAS && i < H) v = __ldg(bias + i);
+        else if (DOUT == 1 && last && i >= G::WL_OFF && i < G::WL_OFF + H) v = __ldg(wl + (i - G::WL_OFF));
         aux_pf[j] = v;
       }
     };
@@ -468,11 +513,13 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
           if (last && have_next) publish_x(ntile, p.member_begin + nk);
 
           const float* wl_g = p.w_last + (size_t)wslot * DOUT * H;
+          // epilogue-bias: 1/(1-p) owed by the previous layer's dropout; bias in the MMA: this layer's
           const float in_scale =
-              (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
+              BIAS ? (drop ? p.drop_scale : 1.f)
+                   : (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
 #define UQ_DRAIN3(R, D, L)                                                                       \
-  drain3<H, DOUT, R, D, L>(p, lane_addr, a_row, rx, grp, ch, lane, chunk_bar0, aux, aux + H, wl_g, \
-                           kw, in_scale, dot)
+  drain3<H, DOUT, R, D, L, BIAS>(p, lane_addr, a_row, rx, grp, ch, lane, chunk_bar0, aux,        \
+                                 aux + G::WL_OFF, wl_g, kw, in_scale, dot)
           if (last) {
             if (relu) { if (drop) UQ_DRAIN3(true, true, true); else UQ_DRAIN3(true, false, true); }
             else { if (drop) UQ_DRAIN3(false, true, true); else UQ_DRAIN3(false, false, true); }
@@ -505,7 +552,7 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int j = 0; j < 3; ++j)
               y += ld_shared_f32(xb + (uint32_t)(((j * ROWS + row) * DOUT + o) * 4));
-            y = fmaf(y, final_dropout_scale(p), __ldg(bl + o));
+            y = fmaf(y, BIAS ? 1.f : final_dropout_scale(p), __ldg(bl + o));
             if (p.last_relu) y = fmaxf(y, 0.f);
             member_fold(p, kg, o, y, inv_n, wf_mean[o], wf_m2[o]);
           }
@@ -539,10 +586,10 @@ uq_mlp_tc3_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-template <int H, int DOUT>
+template <int H, int DOUT, bool BIAS>
 int launch_tc3(const TcParams& p, cudaStream_t st) {
-  using G = Geo3<H, DOUT>;
-  auto kern = uq_mlp_tc3_kernel<H, DOUT>;
+  using G = Geo3<H, DOUT, BIAS>;
+  auto kern = uq_mlp_tc3_kernel<H, DOUT, BIAS>;
   // per-device launch geometry of this instantiation, queried once (the occupancy query and the
   // attribute call cost tens of microseconds, which shows on millisecond-sized forwards)
   static std::atomic<int> cached_clusters[64];   // zero-initialised; races only repeat the query
@@ -585,9 +632,10 @@ int launch_tc3(const TcParams& p, cudaStream_t st) {
 
 template <int DOUT>
 int dispatch_h3(int H, const TcParams& p, cudaStream_t st) {
+  const bool bias = DOUT == 1 && p.bias_image != nullptr && bias_in_mma_enabled();
   switch (H) {
-    case 768: return launch_tc3<768, DOUT>(p, st);
-    case 1024: return launch_tc3<1024, DOUT>(p, st);
+    case 768: return bias ? launch_tc3<768, 1, true>(p, st) : launch_tc3<768, DOUT, false>(p, st);
+    case 1024: return bias ? launch_tc3<1024, 1, true>(p, st) : launch_tc3<1024, DOUT, false>(p, st);
   }
   set_error("bf16 wide-net kernel: unsupported hidden width %d", H);
   return UQ_ERR_UNSUPPORTED;

@@ -40,7 +40,8 @@ def run(packed, x, k, flag):
 
 ok = True
 for width, n_hidden, k, n in [(192, 2, 3, 257), (256, 3, 4, 1030), (320, 2, 2, 383), (384, 4, 3, 999),
-                              (448, 2, 2, 129), (512, 3, 4, 5000), (512, 1, 2, 300), (256, 6, 5, 70000)]:
+                              (448, 2, 2, 129), (512, 3, 4, 5000), (512, 1, 2, 300), (256, 6, 5, 70000),
+                              (1024, 2, 3, 300), (768, 3, 2, 193), (1024, 7, 2, 20000)]:
     for bias_scale in (1.0, 20.0):
         nets = nets_of(width, n_hidden, k, 5, bias_scale)
         x = torch.rand(n, 5, generator=torch.Generator().manual_seed(n))
@@ -78,7 +79,8 @@ for width, n_hidden, k, n in [(64, 2, 3, 1), (64, 3, 2, 1025), (128, 2, 4, 2049)
               f"err vs oracle epilogue-bias {e0:.3e}, bias-in-MMA {e1:.3e}, A/B diff {ab:.3e} (of scale)")
 
 # anchored modes: per-anchor layer-0 bias stages built per call (narrow and pair kernels)
-for width, n_hidden, k, n in [(128, 6, 32, 20011), (64, 2, 5, 700), (256, 3, 7, 1500), (512, 2, 4, 900)]:
+for width, n_hidden, k, n in [(128, 6, 32, 20011), (64, 2, 5, 700), (256, 3, 7, 1500), (512, 2, 4, 900),
+                              (1024, 3, 5, 333)]:
     for bias_scale in (1.0, 20.0):
         net = nets_of(width, n_hidden, 1, 10, bias_scale)[0]
         x = torch.rand(n, 5, generator=torch.Generator().manual_seed(n))
@@ -138,7 +140,8 @@ def masks_from_flat(flat, n, widths, passes):
 
 for width, n_hidden, passes, n, final_drop in [(128, 6, 9, 700, False), (64, 3, 5, 300, True),
                                                (256, 4, 6, 500, False), (512, 3, 5, 400, True),
-                                               (320, 3, 4, 260, False)]:
+                                               (320, 3, 4, 260, False), (1024, 4, 5, 300, False),
+                                               (768, 3, 4, 200, True)]:
     pdrop, seed = 0.2, 1234 + width
     net = mc_net(width, n_hidden, pdrop, 5.0, final_drop)
     x = torch.rand(n, 5, generator=torch.Generator().manual_seed(n))
