@@ -54,11 +54,12 @@ N_ROTATE = 8  # input buffers rotated per step so the working set exceeds the 12
 def kernel_name(widths, d_out):
     """Which fused kernel the library dispatches to (csrc/mlp_tc.cu:tc_forward)."""
     h = max(widths)
+    bias = ", bias in the MMA" if d_out == 1 and os.environ.get("UQ_TC_BIAS_MMA", "1") == "1" else ""
     if h > 512:
-        return "uq_mlp_tc3_kernel (CTA pairs, 64 rows per CTA)"
+        return "uq_mlp_tc3_kernel (CTA pairs, 64 rows per CTA%s)" % bias
     if h <= 128 and d_out == 1:
-        return "uq_mlp_tc4_kernel (CTA pairs, 4 tile slots per CTA)"
-    return "uq_mlp_tc2_kernel (CTA pairs)"
+        return "uq_mlp_tc4_kernel (CTA pairs, 4 tile slots per CTA%s)" % bias
+    return "uq_mlp_tc2_kernel (CTA pairs%s)" % bias
 
 
 def flops_per_unit(d_in, widths, d_out):

@@ -117,7 +117,10 @@ __device__ __forceinline__ void drain4(uint32_t lane_addr, uint32_t a_row, int r
   }
 }
 
-template <int H, bool BIAS>
+// MC: the launch has live dropout.  The dropout-free instantiation carries no mask code (with it the
+// bias-in-the-MMA kernel needs 168 registers and spills; without, 154 and none: 19.9 -> 18.7 ms on
+// deltauq32_binomial_4M).
+template <int H, bool BIAS, bool MC>
 __global__ void __launch_bounds__(NUM4_THREADS, 1)
 uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
   using G = Geo4<H, BIAS>;
@@ -412,7 +415,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
           const bool last = (l == p.L_mma - 1);
           const bool relu = (p.relu_mask >> l) & 1u;
           const bool has_drop = (p.dropout_mask >> l) & 1u;
-          const int drop = has_drop ? p.drop_mode : 0;
+          const int drop = (MC && has_drop) ? p.drop_mode : 0;
           // epilogue-bias: 1/(1-p) owed by the previous layer's dropout; bias in the MMA: this layer's
           const float in_scale =
               BIAS ? (drop ? p.drop_scale : 1.f)
@@ -450,7 +453,7 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
             const uint32_t lane_addr = lane_addr0 + (uint32_t)(t * H);
             const uint32_t a_row = a_row0 + (uint32_t)(t * G::A_SLOT_BYTES);
 #define UQ_DRAIN4(R, D, L) \
-  drain4<H, R, D, L, BIAS>(lane_addr, a_row, rx, aux, aux + G::WL_OFF, keepw, in_scale, dslot)
+  drain4<H, R, (D) && MC, L, BIAS>(lane_addr, a_row, rx, aux, aux + G::WL_OFF, keepw, in_scale, dslot)
             if (last) {
               if (relu) { if (drop) UQ_DRAIN4(true, true, true); else UQ_DRAIN4(true, false, true); }
               else { if (drop) UQ_DRAIN4(false, true, true); else UQ_DRAIN4(false, false, true); }
@@ -515,10 +518,10 @@ uq_mlp_tc4_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-template <int H, bool BIAS>
+template <int H, bool BIAS, bool MC>
 int launch_tc4(const TcParams& p, cudaStream_t st) {
   using G = Geo4<H, BIAS>;
-  auto kern = uq_mlp_tc4_kernel<H, BIAS>;
+  auto kern = uq_mlp_tc4_kernel<H, BIAS, MC>;
   // per-device launch geometry of this instantiation, queried once (the occupancy query and the
   // attribute call cost tens of microseconds, which shows on millisecond-sized forwards)
   static std::atomic<int> cached_clusters[64];   // zero-initialised; races only repeat the query
@@ -566,8 +569,14 @@ int tc4_rows_per_unit() { return 2 * TS * tc::TILE_M; }
 
 int tc4_launch(const tc::TcParams& p, int hidden, cudaStream_t st) {
   const bool bias = p.bias_image != nullptr && bias_in_mma_enabled();
-  if (hidden == 64) return bias ? launch_tc4<64, true>(p, st) : launch_tc4<64, false>(p, st);
-  if (hidden == 128) return bias ? launch_tc4<128, true>(p, st) : launch_tc4<128, false>(p, st);
+  const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
+#define UQ_TC4_DISPATCH(HH)                                                                  \
+  if (hidden == HH)                                                                          \
+    return bias ? (mc ? launch_tc4<HH, true, true>(p, st) : launch_tc4<HH, true, false>(p, st))  \
+                : (mc ? launch_tc4<HH, false, true>(p, st) : launch_tc4<HH, false, false>(p, st));
+  UQ_TC4_DISPATCH(64)
+  UQ_TC4_DISPATCH(128)
+#undef UQ_TC4_DISPATCH
   set_error("bf16 narrow-net kernel: unsupported hidden width %d", hidden);
   return UQ_ERR_UNSUPPORTED;
 }

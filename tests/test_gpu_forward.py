@@ -932,3 +932,115 @@ def test_wide_ensemble_split_major_member_groups():
     mm, ss = ops.moments_merge(torch.stack([a[0], b[0]]), torch.stack([a[1], b[1]]), [10, 14])
     assert float((mm - mean).abs().max()) <= 1e-5 * float(mean.abs().max())
     assert float((ss - std).abs().max()) <= 1e-4 * float(std.abs().max())
+
+
+# ---- bias in the MMA (default) against the epilogue-bias variant ---------------------------------
+
+def _both_bias_variants(call):
+    """Run ``call()`` with UQ_TC_BIAS_MMA=0 (the epilogue adds the bias) and =1 (the tensor core
+    accumulates it from a bias stage: csrc/mlp_tc2.cu, mlp_tc3.cu, mlp_tc4.cu); the launchers read
+    the variable on every call."""
+    old = os.environ.get("UQ_TC_BIAS_MMA")
+    out = {}
+    try:
+        for flag in ("0", "1"):
+            os.environ["UQ_TC_BIAS_MMA"] = flag
+            mean, std = call()
+            torch.cuda.synchronize()
+            out[flag] = (mean.clone(), std.clone())
+    finally:
+        if old is None:
+            os.environ.pop("UQ_TC_BIAS_MMA", None)
+        else:
+            os.environ["UQ_TC_BIAS_MMA"] = old
+    return out
+
+
+def _large_bias_nets(width, n_hidden, k, d_in, bias_scale=20.0):
+    nets = []
+    for i in range(k):
+        torch.manual_seed(7 + i)
+        net = build_network(_wide_arch(d_in, width, n_hidden, 1, bn=False)).eval()
+        with torch.no_grad():
+            for m in net:
+                if isinstance(m, torch.nn.Linear):   # a dropped bias piece is an O(1) error
+                    m.bias.mul_(bias_scale).add_(0.37 * bias_scale * torch.randn_like(m.bias))
+        nets.append(net)
+    return nets
+
+
+@pytest.mark.parametrize("width,n_hidden,k,n", [
+    (64, 3, 2, 1025), (128, 6, 5, 3000),        # narrow-net kernel
+    (192, 2, 3, 257), (320, 2, 2, 383), (512, 3, 4, 5000),   # pair kernel (one / two unequal / two halves)
+    (768, 3, 2, 193), (1024, 2, 3, 300),        # wide-net kernel
+])
+def test_bias_in_mma_matches_epilogue_bias_ensemble(width, n_hidden, k, n):
+    nets = _large_bias_nets(width, n_hidden, k, 5)
+    x = torch.rand(n, 5, generator=torch.Generator().manual_seed(n))
+    packed = ops.PackedModel(nets, DEV)
+    ref_mean, ref_std = uq_oracle.ensemble_forward(nets, x)
+    out = _both_bias_variants(lambda: packed.forward(x.to(DEV), "ensemble", total_members=k,
+                                                     precision="bf16"))
+    for flag, (mean, std) in out.items():
+        _bf16_check(mean, std, ref_mean, ref_std, f"bias variant {flag}, {width}x{n_hidden}")
+    # the two variants differ by accumulation order only
+    scale = float(torch.as_tensor(ref_mean).abs().max() + torch.as_tensor(ref_std).abs().max())
+    assert float((out["1"][0] - out["0"][0]).abs().max()) <= 2e-3 * scale
+
+
+@pytest.mark.parametrize("width,n_hidden,k,n", [(128, 6, 32, 2011), (256, 3, 7, 1500), (1024, 3, 5, 333)])
+def test_bias_in_mma_per_anchor_layer0_stages(width, n_hidden, k, n):
+    """Delta-UQ: the per-anchor layer-0 bias reaches the kernel as bias stages built per call."""
+    net = _large_bias_nets(width, n_hidden, 1, 10)[0]
+    x = torch.rand(n, 5, generator=torch.Generator().manual_seed(n))
+    anchors = torch.rand(k, 5, generator=torch.Generator().manual_seed(2)) * 3.0
+    packed = ops.PackedModel([net], DEV)
+    ref_mean, ref_std = uq_oracle.delta_uq_forward(net, x, anchors, k)
+    out = _both_bias_variants(lambda: packed.forward(x.to(DEV), "delta_uq", total_members=k,
+                                                     precision="bf16", anchors=anchors.to(DEV)))
+    # the large biases put the outputs at ~10 with a spread over anchors of ~0.03: bf16 rounding of
+    # the last hidden activations alone is ~10 % of that spread (either variant), so the std is held
+    # to the output scale (1e-2, measured 3e-4) and to half of its own scale only
+    for flag, (mean, std) in out.items():
+        _bf16_check(mean, std, ref_mean, ref_std, f"bias variant {flag}, delta-uq {width}x{n_hidden}",
+                    tol_std=0.5)
+    scale = float(torch.as_tensor(ref_mean).abs().max() + torch.as_tensor(ref_std).abs().max())
+    assert float((out["1"][0] - out["0"][0]).abs().max()) <= 2e-3 * scale
+    assert float((out["1"][1] - out["0"][1]).abs().max()) <= 2e-3 * scale
+    # and a member shard [2, k) of the same call reads the same per-anchor stages
+    os.environ.pop("UQ_TC_BIAS_MMA", None)
+    m_a, q_a = packed.forward(x.to(DEV), "delta_uq", total_members=k, precision="bf16",
+                              anchors=anchors.to(DEV), member_begin=2, member_count=k - 2,
+                              output="moments")
+    ref_a = uq_oracle.delta_uq_forward(net, x, anchors[2:], k - 2)
+    _bf16_check(m_a, torch.sqrt(q_a / (k - 3)), ref_a[0], ref_a[1], "anchor shard", tol_std=0.5)
+
+
+@pytest.mark.parametrize("width,n_hidden,passes,n,final_drop", [
+    (128, 6, 9, 700, False), (64, 3, 5, 300, True), (512, 3, 5, 400, True), (1024, 4, 5, 300, False)])
+def test_bias_in_mma_with_live_dropout_philox_replay(width, n_hidden, passes, n, final_drop):
+    """With the bias in the MMA the activations are stored with their dropout's 1/(1-p); native
+    masks replayed through the oracle, including a Dropout right before the final Linear."""
+    pdrop, seed = 0.2, 1234 + width
+    torch.manual_seed(3)
+    layers, fan = [], 5
+    for i in range(n_hidden):
+        layers += [torch.nn.Linear(fan, width), torch.nn.ReLU()]
+        if 0 < i < n_hidden - 1 or (final_drop and i == n_hidden - 1):
+            layers.append(torch.nn.Dropout(pdrop))
+        fan = width
+    layers.append(torch.nn.Linear(fan, 1))
+    net = torch.nn.Sequential(*layers).eval()
+    with torch.no_grad():
+        for m in net:
+            if isinstance(m, torch.nn.Linear):
+                m.bias.mul_(5.0).add_(1.8 * torch.randn_like(m.bias))
+    x = torch.rand(n, 5, generator=torch.Generator().manual_seed(n))
+    packed = ops.PackedModel([net], DEV)
+    flat = ops.philox_keep_masks(n, packed.dropout_widths, passes, pdrop, seed, 0, DEV)
+    masks = injected_to_masks(flat.cpu(), n, packed.dropout_widths, passes)
+    ref_mean, ref_std = uq_oracle.mc_dropout_forward(net, x, passes, pdrop, masks=masks)
+    out = _both_bias_variants(lambda: packed.forward(x.to(DEV), "mc_dropout", total_members=passes,
+                                                     precision="bf16", dropout_p=pdrop, seed=seed))
+    for flag, (mean, std) in out.items():
+        _bf16_check(mean, std, ref_mean, ref_std, f"bias variant {flag}, mc-dropout {width}x{n_hidden}")
