@@ -160,7 +160,8 @@ __device__ __forceinline__ void drain_x(const TcParams& p, uint32_t lane_addr, u
   }
 }
 
-template <int H, int DOUT>
+// MC: the launch has live dropout; the dropout-free instantiation carries no mask code (registers)
+template <int H, int DOUT, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
   using G = GeoX<H, DOUT>;
@@ -476,7 +477,7 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
           const bool last = (l == p.L_mma - 1);
           const bool relu = (p.relu_mask >> l) & 1u;
           const bool has_drop = (p.dropout_mask >> l) & 1u;
-          const int drop = has_drop ? p.drop_mode : 0;
+          const int drop = (MC && has_drop) ? p.drop_mode : 0;
 
           float* aux = aux_smem + (g & 1) * G::AUX_FLOATS;
 #pragma unroll
@@ -532,7 +533,7 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
           const float* wl_g = p.w_last + (size_t)wslot * DOUT * H;
           float ss = 0.f;
 #define UQ_DRAINX(R, D, L)                                                                        \
-  drain_x<H, DOUT, R, D, L>(p, lane_addr, a_row, rx, grp, ch, lane, chunk_bar0, aux, aux + H, wl_g, \
+  drain_x<H, DOUT, R, (D) && MC, L>(p, lane_addr, a_row, rx, grp, ch, lane, chunk_bar0, aux, aux + H, wl_g, \
                             keepw, rs, s_out, dot, ss)
           if (last) {
             if (relu) { if (drop) UQ_DRAINX(true, true, true); else UQ_DRAINX(true, false, true); }
@@ -605,10 +606,10 @@ uq_mlp_tcx_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-template <int H, int DOUT>
+template <int H, int DOUT, bool MC>
 int launch_tcx(const TcParams& p, cudaStream_t st) {
   using G = GeoX<H, DOUT>;
-  auto kern = uq_mlp_tcx_kernel<H, DOUT>;
+  auto kern = uq_mlp_tcx_kernel<H, DOUT, MC>;
   // per-device launch geometry of this instantiation, queried once
   static std::atomic<int> cached_clusters[64];
   int dev = 0;
@@ -650,15 +651,16 @@ int launch_tcx(const TcParams& p, cudaStream_t st) {
 
 template <int DOUT>
 int dispatch_hx(int H, const TcParams& p, cudaStream_t st) {
+  const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
   switch (H) {
-    case 64: return launch_tcx<64, DOUT>(p, st);
-    case 128: return launch_tcx<128, DOUT>(p, st);
-    case 192: return launch_tcx<192, DOUT>(p, st);
-    case 256: return launch_tcx<256, DOUT>(p, st);
-    case 320: return launch_tcx<320, DOUT>(p, st);
-    case 384: return launch_tcx<384, DOUT>(p, st);
-    case 448: return launch_tcx<448, DOUT>(p, st);
-    case 512: return launch_tcx<512, DOUT>(p, st);
+    case 64: return mc ? launch_tcx<64, DOUT, true>(p, st) : launch_tcx<64, DOUT, false>(p, st);
+    case 128: return mc ? launch_tcx<128, DOUT, true>(p, st) : launch_tcx<128, DOUT, false>(p, st);
+    case 192: return mc ? launch_tcx<192, DOUT, true>(p, st) : launch_tcx<192, DOUT, false>(p, st);
+    case 256: return mc ? launch_tcx<256, DOUT, true>(p, st) : launch_tcx<256, DOUT, false>(p, st);
+    case 320: return mc ? launch_tcx<320, DOUT, true>(p, st) : launch_tcx<320, DOUT, false>(p, st);
+    case 384: return mc ? launch_tcx<384, DOUT, true>(p, st) : launch_tcx<384, DOUT, false>(p, st);
+    case 448: return mc ? launch_tcx<448, DOUT, true>(p, st) : launch_tcx<448, DOUT, false>(p, st);
+    case 512: return mc ? launch_tcx<512, DOUT, true>(p, st) : launch_tcx<512, DOUT, false>(p, st);
   }
   set_error("fp32 split kernel: unsupported hidden width %d", H);
   return UQ_ERR_UNSUPPORTED;

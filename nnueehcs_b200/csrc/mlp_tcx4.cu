@@ -119,7 +119,8 @@ __device__ __forceinline__ void drain_x4(uint32_t lane_addr, uint32_t a_row, int
   }
 }
 
-template <int H>
+// MC: the launch has live dropout; the dropout-free instantiation carries no mask code (registers)
+template <int H, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 uq_mlp_tcx4_kernel(const __grid_constant__ TcParams p) {
   using G = GeoX4<H>;
@@ -420,7 +421,7 @@ uq_mlp_tcx4_kernel(const __grid_constant__ TcParams p) {
           const bool last = (l == p.L_mma - 1);
           const bool relu = (p.relu_mask >> l) & 1u;
           const bool has_drop = (p.dropout_mask >> l) & 1u;
-          const int drop = has_drop ? p.drop_mode : 0;
+          const int drop = (MC && has_drop) ? p.drop_mode : 0;
           const float in_scale =
               (l > 0 && ((p.dropout_mask >> (l - 1)) & 1u) && p.drop_mode) ? p.drop_scale : 1.f;
 
@@ -476,7 +477,7 @@ uq_mlp_tcx4_kernel(const __grid_constant__ TcParams p) {
             float dslot[1] = {0.f};
             float ss = 0.f;
 #define UQ_DRAINX4(R, D, L) \
-  drain_x4<H, R, D, L>(lane_addr, a_row, rx, ch, aux, aux + H, keepw, rs, s_out, dslot, ss)
+  drain_x4<H, R, (D) && MC, L>(lane_addr, a_row, rx, ch, aux, aux + H, keepw, rs, s_out, dslot, ss)
             if (last) {
               if (relu) { if (drop) UQ_DRAINX4(true, true, true); else UQ_DRAINX4(true, false, true); }
               else { if (drop) UQ_DRAINX4(false, true, true); else UQ_DRAINX4(false, false, true); }
@@ -552,10 +553,10 @@ uq_mlp_tcx4_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-template <int H>
+template <int H, bool MC>
 int launch_tcx4(const TcParams& p, cudaStream_t st) {
   using G = GeoX4<H>;
-  auto kern = uq_mlp_tcx4_kernel<H>;
+  auto kern = uq_mlp_tcx4_kernel<H, MC>;
   static std::atomic<int> cached_clusters[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -603,8 +604,9 @@ bool tcx4_supported(int hidden, int dout_pad) {
 int tcx4_rows_per_unit() { return 2 * TS * ROWS; }
 
 int tcx4_launch(const tc::TcParams& p, int hidden, cudaStream_t st) {
-  if (hidden == 64) return launch_tcx4<64>(p, st);
-  if (hidden == 128) return launch_tcx4<128>(p, st);
+  const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
+  if (hidden == 64) return mc ? launch_tcx4<64, true>(p, st) : launch_tcx4<64, false>(p, st);
+  if (hidden == 128) return mc ? launch_tcx4<128, true>(p, st) : launch_tcx4<128, false>(p, st);
   set_error("narrow split kernel: unsupported hidden width %d", hidden);
   return UQ_ERR_UNSUPPORTED;
 }
