@@ -213,15 +213,17 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
         uint32_t acc[16];
         tmem_ld16(cx.lane_addr + (uint32_t)col0, acc);
         float4 bv[4];
+        if (!BIAS) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
+          for (int j4 = 0; j4 < 4; ++j4)
+            bv[j4] = reinterpret_cast<const float4*>(cx.bias_s + col0)[j4];
+        }
         if (DROP && (b & 1) == 0)
           keep32 = keep_bits32(p, cx.drop, cx.kg, cx.drop_ord, cx.grow, col0, cx.mask_layer, H);
         tmem_ld_wait();
-        epi_block2<H, DOUT, 16, RELU, DROP, LAST>(acc, bv, keep32 >> (16 * (b & 1)), cx.in_scale,
-                                                  a_dst, 2 * b, cx.rx, cx.wl_s + col0,
-                                                  cx.wl_g + col0, dot);
+        epi_block2<H, DOUT, 16, RELU, DROP, LAST, BIAS>(acc, bv, keep32 >> (16 * (b & 1)),
+                                                        cx.in_scale, a_dst, 2 * b, cx.rx,
+                                                        cx.wl_s + col0, cx.wl_g + col0, dot);
       }
       tc_fence_before();
       if (!LAST) fence_proxy_async_smem();
@@ -240,7 +242,7 @@ __device__ __forceinline__ void drain_step(const TcParams& p, const DrainCtx& cx
 template <int H, int DOUT, int NG, bool MC, bool BIAS = false>
 __global__ void __launch_bounds__(Geo2<H, DOUT, NG, BIAS>::NUM_THREADS, 1)
 uq_mlp_tc2_kernel(const __grid_constant__ TcParams p) {
-  static_assert(!BIAS || (NG == 2 && DOUT == 1), "bias-in-the-MMA variant: NG 2, d_out 1");
+  static_assert(!BIAS || DOUT == 1, "bias-in-the-MMA variant: d_out 1");
   using G = Geo2<H, DOUT, NG, BIAS>;
   constexpr int EPI_THREADS = G::EPI_THREADS;
   constexpr int KC = G::KC, NH = G::NH, NT = G::NT, NS = G::NSTAGES;
@@ -787,6 +789,9 @@ int launch_tc2_mc(const TcParams& p, cudaStream_t st) {
 template <int H, int DOUT, int NG>
 int launch_tc2(const TcParams& p, cudaStream_t st) {
   const bool mc = p.drop_mode != 0 && p.dropout_mask != 0;
+  // (16 epilogue warps with the bias in the MMA -- NG == 4 here -- were measured too: 15.0 ms against
+  // 13.7 on ensemble16x512_1M, 240 against 203 ms on mcdropout_1000x512_64k,
+  // profiles/r02_j_bench_epi16_*; the 16-warp A/B variant therefore stays epilogue-bias only)
   if (DOUT == 1 && NG == 2 && p.bias_image != nullptr && bias_in_mma_enabled())
     return mc ? launch_tc2_mc<H, 1, 2, true, true>(p, st) : launch_tc2_mc<H, 1, 2, false, true>(p, st);
   return mc ? launch_tc2_mc<H, DOUT, NG, true>(p, st) : launch_tc2_mc<H, DOUT, NG, false>(p, st);
