@@ -19,9 +19,12 @@
 //     leader's chunk barriers through mapa'd cluster addresses; tcgen05.commit multicasts
 //     "stage free" and "layer accumulated" to both CTAs.
 //
-// Epilogue (warps 2..9 of each CTA): the folded bias of the layer is staged once per layer-step in
-// shared memory (prefetched one step ahead), the accumulator is drained with double-buffered
-// tcgen05.ld, bias + ReLU + bf16 rounding are two instructions per pair (FADD, FADD,
+// Bias: BIAS = true (the default for d_out 1) lets the tensor core accumulate it -- one bias stage
+// per layer and accumulator half in the weight ring, one extra K = 16 MMA of an all-ones A tile
+// against it; BIAS = false stages the folded bias once per layer-step in shared memory (prefetched
+// one step ahead) and adds it in the epilogue.
+// Epilogue (warps 2..9 of each CTA): the accumulator is drained with double-buffered tcgen05.ld,
+// [bias +] ReLU + bf16 rounding are one to two instructions per pair ([FFMA, FFMA,]
 // cvt.rn.relu.bf16x2), and the result is stored straight into the next layer's swizzled A chunk.
 // The last Linear is a CUDA-core dot product feeding the per-row Welford, as in mlp_tc.cu.
 //

@@ -10,8 +10,9 @@
 // N = 256 tiles = 512 TMEM columns, and the A operand is sixteen [64 x 64] bf16 chunks = 128 KB.
 //
 // Everything else follows mlp_tc2.cu: split weight stages (each CTA streams N/2 rows), the peer
-// relay for "stage landed", chunk barriers on the leader, bias staged in shared memory one step
-// ahead, in-place bf16 write-back of the next layer's A operand, last Linear as a CUDA-core dot
+// relay for "stage landed", chunk barriers on the leader, the bias accumulated by the tensor core
+// from a bias stage (BIAS; d_out > 1: staged in shared memory one step ahead and added by the
+// epilogue), in-place bf16 write-back of the next layer's A operand, last Linear as a CUDA-core dot
 // product feeding the per-row Welford.  Per flop this shape streams twice the weight bytes of
 // the M = 256 kernel (a stage serves 128 rows instead of 256), which makes it L2 / shared-memory
 // bound rather than MMA bound; it exists so that BASELINE.json's 8-layer width-1024 MC-dropout

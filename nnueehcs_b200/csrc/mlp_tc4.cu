@@ -16,8 +16,8 @@
 // of the pair are done with its accumulator and have rewritten its A chunks), X_READY[t].  Epilogue
 // warp group g owns the slots t with t % 2 == g (whole rows: no cross-warp exchange for the last
 // Linear's dot product), so two slots are drained concurrently.
-// Everything else (split weight stages, peer relay, bias staging, in-place bf16 write-back,
-// CUDA-core last Linear + per-row Welford) follows mlp_tc2.cu.
+// Everything else (split weight stages, peer relay, bias in the MMA or staged for the epilogue,
+// in-place bf16 write-back, CUDA-core last Linear + per-row Welford) follows mlp_tc2_impl.cuh.
 //
 // Replaces: MCDropoutModel.forward (models.py:147-163), EnsembleModel.forward (:99-108) and the
 // anchored forward behind DeltaUQMLP.forward (:313-341) for hidden widths 64 and 128, d_out = 1
